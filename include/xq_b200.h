@@ -1,0 +1,103 @@
+/*
+ * xq_b200.h -- C ABI of libxq_b200.so, the B200 (sm_100a) self-play engine.
+ *
+ * This is the drop-in boundary for the reference's self-play hot path
+ * (wenjunyang/xiangqi-alphazero, training/): plain C, raw pointers and sizes, no torch or
+ * Python types.  Each entry point names the reference interface it replaces
+ * (paths relative to the reference's training/ directory).  INTEGRATION.md shows the
+ * ctypes binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - return value: 0 = ok, negative = error (xq_last_error() gives the text). No C++
+ *     exceptions cross the ABI.
+ *   - `d_` pointers are device pointers on the context's GPU, `h_` pointers are host
+ *     pointers (pinned memory recommended).  Device-pointer calls are asynchronous on the
+ *     `stream` argument (a cudaStream_t, 0 = default stream); host-pointer calls return when
+ *     the outputs are complete.
+ *   - the caller owns every buffer; the library borrows them for the duration of the
+ *     enqueued work and never retains them.
+ *   - one context per GPU and process; a context is not thread-safe (the reference's callers
+ *     are single-threaded, game.py / mcts.py hold the GIL throughout).
+ *
+ * Board encoding (game.py:50-65): int8[90], index row*9+col, row 0 = red back rank; red > 0,
+ * black < 0; 1 K, 2 A, 3 B, 4 N, 5 R, 6 C, 7 P.  side: +1 red, -1 black.
+ * Action id (game.py:112-114): from_square*90 + to_square, 0 <= id < 8100.
+ */
+#ifndef XQ_B200_H
+#define XQ_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XQ_SQUARES 90
+#define XQ_MAX_MOVES 128      /* action slots per position (reference MAX_MOVES=200, game_core.pyx:50;
+                                 max observed in legal play is 74; overflow is detected, never silent) */
+#define XQ_ACTION_SPACE 8100
+#define XQ_PLANES 15
+#define XQ_MAX_PLIES 201      /* positions a game can show: move_count 0..200 (game.py:595) */
+
+#define XQ_OK 0
+#define XQ_ERR_ARG (-1)
+#define XQ_ERR_CUDA (-2)
+#define XQ_ERR_OVERFLOW (-3)  /* a position produced more than XQ_MAX_MOVES legal moves */
+#define XQ_ERR_STATE (-4)
+
+typedef struct xq_ctx xq_ctx;
+
+/* ---- context ---------------------------------------------------------------------------- */
+int xq_create(int device, xq_ctx** out);
+void xq_destroy(xq_ctx* ctx);
+const char* xq_last_error(const xq_ctx* ctx);   /* ctx may be NULL: last global error */
+int xq_version(void);
+/* number of kernels this library launched since the last call with reset != 0 */
+long long xq_launch_count(xq_ctx* ctx, int reset);
+/* CUDA-event timing of the most recent xq_* device call's main kernel, in milliseconds
+ * (valid after the stream has been synchronised; <0 if timing is disabled) */
+int xq_set_timing(xq_ctx* ctx, int enabled);
+float xq_last_kernel_ms(xq_ctx* ctx);
+
+/* ---- K1: batched rules engine -------------------------------------------------------------
+ * Replaces cy_generate_legal_moves / cy_is_in_check (cython_engine/game_core.pyx:521-555) and
+ * XiangqiGame.get_legal_actions / get_state_for_nn (game.py:523-526, 618-640), one warp per board.
+ *
+ *   d_boards   [B][90]  int8
+ *   d_sides    [B]      int8  (+1 / -1)
+ *   d_actions  [B][128] int16  ordered legal action ids (reference generation order), unused = -1
+ *   d_n_moves  [B]      uint8  legal-move count (saturates at 128 and raises the overflow flag)
+ *   d_in_check [B]      uint8  cy_is_in_check(board, side): own king attacked or missing
+ *   d_planes   [B][15][10][9] float32, or NULL: get_state_for_nn planes (0.0 / 1.0)
+ */
+int xq_movegen_batch(xq_ctx* ctx, const int8_t* d_boards, const int8_t* d_sides, int B,
+                     int16_t* d_actions, uint8_t* d_n_moves, uint8_t* d_in_check, float* d_planes,
+                     void* stream);
+
+/* Same, host buffers: chunked H2D -> kernel -> D2H pipeline on internal streams.  Returns
+ * XQ_ERR_OVERFLOW if any position overflowed (outputs are still written, truncated). */
+int xq_movegen_batch_host(xq_ctx* ctx, const int8_t* h_boards, const int8_t* h_sides, int B,
+                          int16_t* h_actions, uint8_t* h_n_moves, uint8_t* h_in_check, float* h_planes);
+
+/* Replaces cy_is_attacked (game_core.pyx:508-518) / XiangqiGame._is_attacked (game.py:176-265):
+ *   out[i] = is square d_sq[i] (row*9+col) of board i attacked by side d_by[i]. */
+int xq_is_attacked_batch(xq_ctx* ctx, const int8_t* d_boards, const uint8_t* d_sq, const int8_t* d_by,
+                         int B, uint8_t* d_out, void* stream);
+int xq_is_attacked_batch_host(xq_ctx* ctx, const int8_t* h_boards, const uint8_t* h_sq, const int8_t* h_by,
+                              int B, uint8_t* h_out);
+
+/* overflow positions seen by movegen calls since the last reset (device counter, synchronises) */
+int xq_overflow_count(xq_ctx* ctx, int reset);
+
+/* Device-side uniform-random legal playouts from the start position (the recipe of the
+ * reference's own differential test, test_cython.py:87-123, and of BASELINE config 1):
+ * game g writes its positions to slots [g*201 .. g*201+n_positions[g]) of d_boards/d_sides;
+ * unused slots get side 0.  d_winner[g] in {1,-1,0} (is_game_over, game.py:565-616).
+ *   d_boards [G*201][90] int8, d_sides [G*201] int8, d_n_positions [G] int32, d_winner [G] int8 */
+int xq_random_playouts(xq_ctx* ctx, uint64_t seed, int n_games, int8_t* d_boards, int8_t* d_sides,
+                       int32_t* d_n_positions, int8_t* d_winner, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XQ_B200_H */

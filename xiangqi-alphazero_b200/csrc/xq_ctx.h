@@ -1,0 +1,102 @@
+// xq_ctx.h -- internal context shared by the translation units of libxq_b200.so
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdint>
+#include <string>
+
+#include "../../include/xq_b200.h"
+
+struct xq_ctx {
+    int device = 0;
+    int sm_count = 148;
+    char err[512] = {0};
+    long long launches = 0;
+    bool timing = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool ev_valid = false;
+    int* d_overflow = nullptr;            // movegen overflow counter
+    // host-pipeline resources (lazy)
+    cudaStream_t pipe[2] = {nullptr, nullptr};
+    void* d_stage[2] = {nullptr, nullptr};
+    size_t stage_bytes = 0;
+    // subsystem state owned by other translation units
+    void* mcts = nullptr;
+    void* net = nullptr;
+};
+
+extern char g_xq_last_error[512];
+
+inline int xq_fail(xq_ctx* ctx, int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_xq_last_error, sizeof(g_xq_last_error), fmt, ap);
+    va_end(ap);
+    if (ctx) snprintf(ctx->err, sizeof(ctx->err), "%s", g_xq_last_error);
+    return code;
+}
+
+#define XQ_CUDA(ctx, expr)                                                                         \
+    do {                                                                                           \
+        cudaError_t e_ = (expr);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return xq_fail(ctx, XQ_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr,         \
+                           cudaGetErrorString(e_));                                                \
+    } while (0)
+
+// brackets the main kernel of a call with events when timing is on
+struct XqTimer {
+    xq_ctx* c;
+    cudaStream_t s;
+    XqTimer(xq_ctx* ctx, cudaStream_t st) : c(ctx), s(st)
+    {
+        if (c->timing) cudaEventRecord(c->ev0, s);
+    }
+    ~XqTimer()
+    {
+        if (c->timing) {
+            cudaEventRecord(c->ev1, s);
+            c->ev_valid = true;
+        }
+    }
+};
+
+// ---- PTX helpers: mbarrier + 1-D bulk async copy (TMA engine, SASS UBLKCP) -----------------
+namespace xq {
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    while (!mbar_try_wait(bar, parity)) {}
+}
+// global -> shared bulk copy; bytes % 16 == 0, both addresses 16 B aligned
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+}  // namespace xq

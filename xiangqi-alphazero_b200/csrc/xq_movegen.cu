@@ -1,0 +1,477 @@
+// xq_movegen.cu -- K1: batched rules engine (legal moves, in-check, feature planes),
+// is_attacked queries and device-side random playouts, plus the context entry points.
+//
+// Replaces training/cython_engine/game_core.pyx (cy_generate_legal_moves :521-540,
+// cy_is_in_check :543-555, cy_is_attacked :508-518) and game.py get_state_for_nn :618-640.
+//
+// Kernel shape (HBM/instruction-bound integer work, no tensor cores):
+//   - persistent CTAs (grid = SMs x resident CTAs), 8 warps, one warp per board;
+//   - boards arrive in shared memory as 64-board tiles (5760 B + 64 B of sides) through the
+//     TMA engine (cp.async.bulk + mbarrier, double buffered) so the next tile streams in
+//     while the current one is being searched;
+//   - move lists leave as one 8-byte store per lane (256 B per board, coalesced), planes as
+//     coalesced float2 streaming stores, counts / in-check flags as one 64 B row per tile.
+#include "xq_ctx.h"
+#include "xq_rules.cuh"
+
+char g_xq_last_error[512] = {0};
+
+namespace xq {
+
+constexpr int kWarps = 8;
+constexpr int kThreads = kWarps * 32;
+constexpr int kTile = 64;                       // boards per CTA tile
+constexpr int kTileBytes = kTile * kSquares;    // 5760, multiple of 16
+
+struct __align__(16) MovegenSmem {
+    int8_t boards[2][kTileBytes];
+    int8_t sides[2][kTile];
+    uint8_t n_out[2][kTile];
+    uint8_t chk_out[2][kTile];
+    uint64_t bar[2];
+    WarpScratch ws[kWarps];
+    uint8_t code[kWarps][96];                   // per-square plane index (255 = empty)
+};
+
+template <bool PLANES>
+__global__ void __launch_bounds__(kThreads)
+movegen_kernel(const int8_t* __restrict__ boards, const int8_t* __restrict__ sides, int B,
+               int16_t* __restrict__ actions, uint8_t* __restrict__ n_moves,
+               uint8_t* __restrict__ in_check, float* __restrict__ planes, int* __restrict__ overflow,
+               int bulk_ok)
+{
+    __shared__ MovegenSmem sm;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_tiles = (B + kTile - 1) / kTile;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&sm.bar[0], 1);
+        mbar_init(&sm.bar[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    auto tile_is_bulk = [&](int t) { return bulk_ok && (t + 1) * kTile <= B; };
+    auto issue = [&](int t, int buf) {   // thread 0 only
+        mbar_expect_tx(&sm.bar[buf], kTileBytes + kTile);
+        bulk_g2s(sm.boards[buf], boards + (size_t)t * kTileBytes, kTileBytes, &sm.bar[buf]);
+        bulk_g2s(sm.sides[buf], sides + (size_t)t * kTile, kTile, &sm.bar[buf]);
+    };
+
+    uint32_t phase[2] = {0, 0};
+    int t = blockIdx.x;
+    if (t < num_tiles && tile_is_bulk(t) && threadIdx.x == 0) issue(t, 0);
+
+    for (int it = 0; t < num_tiles; ++it, t += gridDim.x) {
+        const int buf = it & 1;
+        const int tn = t + gridDim.x;
+        // the other buffer was released by the __syncthreads that ended the previous iteration
+        if (tn < num_tiles && tile_is_bulk(tn) && threadIdx.x == 0) issue(tn, buf ^ 1);
+
+        const int nb = min(kTile, B - t * kTile);
+        if (tile_is_bulk(t)) {
+            mbar_wait(&sm.bar[buf], phase[buf]);
+            phase[buf] ^= 1;
+        } else {
+            // ragged last tile / unaligned caller buffer: plain cooperative copy
+            for (int i = threadIdx.x; i < nb * kSquares; i += kThreads)
+                sm.boards[buf][i] = boards[(size_t)t * kTileBytes + i];
+            for (int i = threadIdx.x; i < nb; i += kThreads) sm.sides[buf][i] = sides[(size_t)t * kTile + i];
+            __syncthreads();
+        }
+
+        for (int j = warp; j < nb; j += kWarps) {
+            const int8_t* b = &sm.boards[buf][j * kSquares];
+            const int side = sm.sides[buf][j];
+            const size_t gi = (size_t)t * kTile + j;
+            WarpScratch& S = sm.ws[warp];
+
+            MovegenResult r = warp_movegen(b, side, S);
+            if (lane == 0) {
+                sm.n_out[buf][j] = (uint8_t)min(r.n_legal, kMaxMoves);
+                sm.chk_out[buf][j] = r.in_check ? 1 : 0;
+                if (r.overflow) atomicAdd(overflow, 1);
+            }
+            // 128 int16 = 256 B: one 8-byte store per lane
+            {
+                const uint2 v = reinterpret_cast<const uint2*>(S.actions)[lane];
+                __stcs(reinterpret_cast<uint2*>(actions + gi * kMaxMoves) + lane, v);
+            }
+            if (PLANES) {
+                // game.py:618-640: plane = kind-1 for the side to move, 7+kind-1 for the other side
+                uint8_t* code = sm.code[warp];
+                for (int sq = lane; sq < kSquares; sq += 32) {
+                    int v = b[sq] * side;
+                    code[sq] = v > 0 ? (uint8_t)(v - 1) : (v < 0 ? (uint8_t)(6 - v) : (uint8_t)255);
+                }
+                __syncwarp();
+                const float turn = side == 1 ? 1.0f : 0.0f;
+                float2* out = reinterpret_cast<float2*>(planes + gi * (15 * kSquares));
+#pragma unroll 3
+                for (int e2 = lane; e2 < 15 * kSquares / 2; e2 += 32) {
+                    const int e = 2 * e2;
+                    const int p = e / kSquares;
+                    const int sq = e - p * kSquares;
+                    float2 v;
+                    if (p == 14) {
+                        v.x = v.y = turn;
+                    } else {
+                        v.x = code[sq] == p ? 1.0f : 0.0f;
+                        v.y = code[sq + 1] == p ? 1.0f : 0.0f;
+                    }
+                    __stcs(out + e2, v);
+                }
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+        // per-tile rows of counts and flags
+        if (nb == kTile && (((uintptr_t)n_moves | (uintptr_t)in_check) & 3) == 0) {
+            if (threadIdx.x < 16)
+                reinterpret_cast<uint32_t*>(n_moves + (size_t)t * kTile)[threadIdx.x] =
+                    reinterpret_cast<const uint32_t*>(sm.n_out[buf])[threadIdx.x];
+            else if (threadIdx.x < 32)
+                reinterpret_cast<uint32_t*>(in_check + (size_t)t * kTile)[threadIdx.x - 16] =
+                    reinterpret_cast<const uint32_t*>(sm.chk_out[buf])[threadIdx.x - 16];
+        } else {
+            for (int i = threadIdx.x; i < nb; i += kThreads) {
+                n_moves[(size_t)t * kTile + i] = sm.n_out[buf][i];
+                in_check[(size_t)t * kTile + i] = sm.chk_out[buf][i];
+            }
+        }
+    }
+}
+
+// ---- is_attacked queries: one thread per query, boards staged per CTA ---------------------
+constexpr int kAtkThreads = 128;
+
+__global__ void __launch_bounds__(kAtkThreads)
+is_attacked_kernel(const int8_t* __restrict__ boards, const uint8_t* __restrict__ sq,
+                   const int8_t* __restrict__ by, int B, uint8_t* __restrict__ out)
+{
+    __shared__ int8_t sb[kAtkThreads * kSquares];
+    const int base = blockIdx.x * kAtkThreads;
+    const int nb = min(kAtkThreads, B - base);
+    for (int i = threadIdx.x; i < nb * kSquares; i += kAtkThreads) sb[i] = boards[(size_t)base * kSquares + i];
+    __syncthreads();
+    if (threadIdx.x < nb) {
+        const int s = sq[base + threadIdx.x];
+        bool a = false;
+        if (s < kSquares)
+            a = attacked_sq(&sb[threadIdx.x * kSquares], s / 9, s % 9, by[base + threadIdx.x], -1, -1, 0);
+        out[base + threadIdx.x] = a ? 1 : 0;
+    }
+}
+
+// ---- random playouts: one warp per game ----------------------------------------------------
+constexpr int kPlayWarps = 4;
+
+struct __align__(16) PlayoutSmem {
+    int8_t board[kPlayWarps][kBoardPad];
+    int8_t ring[kPlayWarps][kRing * kBoardPad];
+    WarpScratch ws[kPlayWarps];
+};
+
+__device__ __forceinline__ void warp_init_board(int8_t* b)
+{
+    // game.py:139-159
+    const int lane = lane_id();
+    for (int sq = lane; sq < kBoardPad; sq += 32) {
+        int r = sq / 9, c = sq % 9, v = 0;
+        if (sq < kSquares) {
+            const int back[9] = {5, 4, 3, 2, 1, 2, 3, 4, 5};
+            if (r == 0) v = back[c];
+            else if (r == 9) v = -back[c];
+            else if (r == 2 && (c == 1 || c == 7)) v = 6;
+            else if (r == 7 && (c == 1 || c == 7)) v = -6;
+            else if (r == 3 && (c & 1) == 0) v = 7;
+            else if (r == 6 && (c & 1) == 0) v = -7;
+        }
+        b[sq] = (int8_t)v;
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(kPlayWarps * 32)
+playout_kernel(uint64_t seed, int n_games, int8_t* __restrict__ boards, int8_t* __restrict__ sides,
+               int32_t* __restrict__ n_positions, int8_t* __restrict__ winner, int* __restrict__ overflow)
+{
+    __shared__ PlayoutSmem sm;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.x * kPlayWarps + warp;
+    if (g >= n_games) return;
+    int8_t* b = sm.board[warp];
+    int8_t* ring = sm.ring[warp];
+    WarpScratch& S = sm.ws[warp];
+    warp_init_board(b);
+    GameMeta gm{1, 0, 0};
+    int ply = 0, w = 2;
+    for (;; ++ply) {
+        MovegenResult r = warp_movegen(b, gm.side, S);
+        if (r.overflow && lane == 0) atomicAdd(overflow, 1);
+        w = warp_game_over(b, ring, gm, r);
+        const size_t slot = (size_t)g * XQ_MAX_PLIES + ply;
+        for (int i = lane; i < kSquares; i += 32) boards[slot * kSquares + i] = b[i];
+        if (lane == 0) sides[slot] = (int8_t)gm.side;
+        if (w != 2 || ply + 1 >= XQ_MAX_PLIES) break;
+        const uint64_t u = rng_u64(seed, (uint64_t)g, (uint64_t)ply, 0);
+        const int pick = (int)(u % (uint64_t)min(r.n_legal, kMaxMoves));
+        const int action = S.actions[pick];
+        __syncwarp();
+        warp_make_move(b, ring, gm, action);
+    }
+    for (int p = ply + 1 + lane; p < XQ_MAX_PLIES; p += 32) sides[(size_t)g * XQ_MAX_PLIES + p] = 0;
+    if (lane == 0) {
+        n_positions[g] = ply + 1;
+        winner[g] = (int8_t)w;
+    }
+}
+
+}  // namespace xq
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+using namespace xq;
+
+extern "C" int xq_version(void) { return 100; }
+
+extern "C" const char* xq_last_error(const xq_ctx* ctx) { return ctx ? ctx->err : g_xq_last_error; }
+
+extern "C" int xq_create(int device, xq_ctx** out)
+{
+    if (!out) return xq_fail(nullptr, XQ_ERR_ARG, "xq_create: out is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return xq_fail(nullptr, XQ_ERR_CUDA, "xq_create: no CUDA device (%s); this library has no CPU path",
+                       cudaGetErrorString(e));
+    if (device < 0 || device >= n) return xq_fail(nullptr, XQ_ERR_ARG, "xq_create: device %d out of range", device);
+    xq_ctx* c = new xq_ctx();
+    c->device = device;
+    XQ_CUDA(c, cudaSetDevice(device));
+    cudaDeviceProp prop;
+    XQ_CUDA(c, cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    if (prop.major != 10)
+        fprintf(stderr, "[xq_b200] warning: built for sm_100a, device is sm_%d%d\n", prop.major, prop.minor);
+    XQ_CUDA(c, cudaMalloc(&c->d_overflow, sizeof(int)));
+    XQ_CUDA(c, cudaMemset(c->d_overflow, 0, sizeof(int)));
+    XQ_CUDA(c, cudaEventCreate(&c->ev0));
+    XQ_CUDA(c, cudaEventCreate(&c->ev1));
+    *out = c;
+    return XQ_OK;
+}
+
+extern "C" void xq_mcts_free_(xq_ctx*);
+extern "C" void xq_net_free_(xq_ctx*);
+
+extern "C" void xq_destroy(xq_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    xq_mcts_free_(c);
+    xq_net_free_(c);
+    for (int i = 0; i < 2; ++i) {
+        if (c->pipe[i]) cudaStreamDestroy(c->pipe[i]);
+        if (c->d_stage[i]) cudaFree(c->d_stage[i]);
+    }
+    if (c->d_overflow) cudaFree(c->d_overflow);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    delete c;
+}
+
+extern "C" long long xq_launch_count(xq_ctx* c, int reset)
+{
+    long long v = c->launches;
+    if (reset) c->launches = 0;
+    return v;
+}
+
+extern "C" int xq_set_timing(xq_ctx* c, int enabled)
+{
+    c->timing = enabled != 0;
+    c->ev_valid = false;
+    return XQ_OK;
+}
+
+extern "C" float xq_last_kernel_ms(xq_ctx* c)
+{
+    if (!c->timing || !c->ev_valid) return -1.0f;
+    float ms = -1.0f;
+    if (cudaEventSynchronize(c->ev1) != cudaSuccess) return -1.0f;
+    if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) != cudaSuccess) return -1.0f;
+    return ms;
+}
+
+static int movegen_grid(xq_ctx* c, bool with_planes, int B)
+{
+    int per_sm = 0;
+    if (with_planes)
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, movegen_kernel<true>, kThreads, 0);
+    else
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, movegen_kernel<false>, kThreads, 0);
+    if (per_sm < 1) per_sm = 1;
+    const int tiles = (B + kTile - 1) / kTile;
+    int grid = c->sm_count * per_sm;       // persistent: a whole number of resident waves
+    return grid < tiles ? grid : tiles;
+}
+
+extern "C" int xq_movegen_batch(xq_ctx* c, const int8_t* d_boards, const int8_t* d_sides, int B,
+                                int16_t* d_actions, uint8_t* d_n_moves, uint8_t* d_in_check,
+                                float* d_planes, void* stream)
+{
+    if (!c) return xq_fail(nullptr, XQ_ERR_ARG, "xq_movegen_batch: ctx is NULL");
+    if (B < 0 || (B > 0 && (!d_boards || !d_sides || !d_actions || !d_n_moves || !d_in_check)))
+        return xq_fail(c, XQ_ERR_ARG, "xq_movegen_batch: bad arguments (B=%d)", B);
+    if (B == 0) return XQ_OK;
+    if (((uintptr_t)d_actions & 7) || (d_planes && ((uintptr_t)d_planes & 7)))
+        return xq_fail(c, XQ_ERR_ARG, "xq_movegen_batch: actions/planes must be 8-byte aligned");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int bulk_ok = (((uintptr_t)d_boards | (uintptr_t)d_sides) & 15) == 0;
+    const int grid = movegen_grid(c, d_planes != nullptr, B);
+    {
+        XqTimer tm(c, s);
+        if (d_planes)
+            movegen_kernel<true><<<grid, kThreads, 0, s>>>(d_boards, d_sides, B, d_actions, d_n_moves,
+                                                           d_in_check, d_planes, c->d_overflow, bulk_ok);
+        else
+            movegen_kernel<false><<<grid, kThreads, 0, s>>>(d_boards, d_sides, B, d_actions, d_n_moves,
+                                                            d_in_check, nullptr, c->d_overflow, bulk_ok);
+    }
+    c->launches += 1;
+    XQ_CUDA(c, cudaGetLastError());
+    return XQ_OK;
+}
+
+extern "C" int xq_overflow_count(xq_ctx* c, int reset)
+{
+    int v = 0;
+    if (cudaMemcpy(&v, c->d_overflow, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    if (reset) cudaMemset(c->d_overflow, 0, sizeof(int));
+    return v;
+}
+
+// ---- host-buffer pipeline -------------------------------------------------------------------
+static int ensure_pipe(xq_ctx* c, size_t bytes)
+{
+    for (int i = 0; i < 2; ++i)
+        if (!c->pipe[i]) XQ_CUDA(c, cudaStreamCreateWithFlags(&c->pipe[i], cudaStreamNonBlocking));
+    if (c->stage_bytes < bytes) {
+        for (int i = 0; i < 2; ++i) {
+            if (c->d_stage[i]) XQ_CUDA(c, cudaFree(c->d_stage[i]));
+            c->d_stage[i] = nullptr;
+            XQ_CUDA(c, cudaMalloc(&c->d_stage[i], bytes));
+        }
+        c->stage_bytes = bytes;
+    }
+    return XQ_OK;
+}
+
+extern "C" int xq_movegen_batch_host(xq_ctx* c, const int8_t* h_boards, const int8_t* h_sides, int B,
+                                     int16_t* h_actions, uint8_t* h_n_moves, uint8_t* h_in_check,
+                                     float* h_planes)
+{
+    if (!c) return xq_fail(nullptr, XQ_ERR_ARG, "xq_movegen_batch_host: ctx is NULL");
+    if (B < 0 || (B > 0 && (!h_boards || !h_sides || !h_actions || !h_n_moves || !h_in_check)))
+        return xq_fail(c, XQ_ERR_ARG, "xq_movegen_batch_host: bad arguments (B=%d)", B);
+    if (B == 0) return XQ_OK;
+    XQ_CUDA(c, cudaSetDevice(c->device));
+    // chunked so that H2D of chunk i+1, the kernel of chunk i and D2H of chunk i-1 overlap
+    const int chunk = 65536;
+    const size_t per_pos = 90 + 1 + 256 + 1 + 1 + (h_planes ? 5400 : 0);
+    // staging layout per chunk (each region 256 B aligned)
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t o_boards = 0, o_sides = al(o_boards + (size_t)chunk * 90), o_act = al(o_sides + chunk),
+                 o_n = al(o_act + (size_t)chunk * 256), o_chk = al(o_n + chunk), o_pl = al(o_chk + chunk),
+                 total = o_pl + (h_planes ? (size_t)chunk * 5400 : 0);
+    (void)per_pos;
+    int rc = ensure_pipe(c, total);
+    if (rc) return rc;
+    const int before = xq_overflow_count(c, 0);
+    int k = 0;
+    for (int off = 0; off < B; off += chunk, ++k) {
+        const int n = (B - off < chunk) ? (B - off) : chunk;
+        cudaStream_t s = c->pipe[k & 1];
+        char* d = (char*)c->d_stage[k & 1];
+        XQ_CUDA(c, cudaMemcpyAsync(d + o_boards, h_boards + (size_t)off * 90, (size_t)n * 90, cudaMemcpyHostToDevice, s));
+        XQ_CUDA(c, cudaMemcpyAsync(d + o_sides, h_sides + off, (size_t)n, cudaMemcpyHostToDevice, s));
+        rc = xq_movegen_batch(c, (const int8_t*)(d + o_boards), (const int8_t*)(d + o_sides), n,
+                              (int16_t*)(d + o_act), (uint8_t*)(d + o_n), (uint8_t*)(d + o_chk),
+                              h_planes ? (float*)(d + o_pl) : nullptr, s);
+        if (rc) return rc;
+        XQ_CUDA(c, cudaMemcpyAsync(h_actions + (size_t)off * 128, d + o_act, (size_t)n * 256, cudaMemcpyDeviceToHost, s));
+        XQ_CUDA(c, cudaMemcpyAsync(h_n_moves + off, d + o_n, (size_t)n, cudaMemcpyDeviceToHost, s));
+        XQ_CUDA(c, cudaMemcpyAsync(h_in_check + off, d + o_chk, (size_t)n, cudaMemcpyDeviceToHost, s));
+        if (h_planes)
+            XQ_CUDA(c, cudaMemcpyAsync(h_planes + (size_t)off * 1350, d + o_pl, (size_t)n * 5400, cudaMemcpyDeviceToHost, s));
+    }
+    XQ_CUDA(c, cudaStreamSynchronize(c->pipe[0]));
+    XQ_CUDA(c, cudaStreamSynchronize(c->pipe[1]));
+    const int after = xq_overflow_count(c, 0);
+    if (after > before)
+        return xq_fail(c, XQ_ERR_OVERFLOW, "xq_movegen_batch_host: %d position(s) exceeded %d legal moves",
+                       after - before, XQ_MAX_MOVES);
+    return XQ_OK;
+}
+
+extern "C" int xq_is_attacked_batch(xq_ctx* c, const int8_t* d_boards, const uint8_t* d_sq, const int8_t* d_by,
+                                    int B, uint8_t* d_out, void* stream)
+{
+    if (!c) return xq_fail(nullptr, XQ_ERR_ARG, "xq_is_attacked_batch: ctx is NULL");
+    if (B < 0 || (B > 0 && (!d_boards || !d_sq || !d_by || !d_out)))
+        return xq_fail(c, XQ_ERR_ARG, "xq_is_attacked_batch: bad arguments (B=%d)", B);
+    if (B == 0) return XQ_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    {
+        XqTimer tm(c, s);
+        is_attacked_kernel<<<(B + kAtkThreads - 1) / kAtkThreads, kAtkThreads, 0, s>>>(d_boards, d_sq, d_by, B, d_out);
+    }
+    c->launches += 1;
+    XQ_CUDA(c, cudaGetLastError());
+    return XQ_OK;
+}
+
+extern "C" int xq_is_attacked_batch_host(xq_ctx* c, const int8_t* h_boards, const uint8_t* h_sq,
+                                         const int8_t* h_by, int B, uint8_t* h_out)
+{
+    if (!c) return xq_fail(nullptr, XQ_ERR_ARG, "xq_is_attacked_batch_host: ctx is NULL");
+    if (B < 0 || (B > 0 && (!h_boards || !h_sq || !h_by || !h_out)))
+        return xq_fail(c, XQ_ERR_ARG, "xq_is_attacked_batch_host: bad arguments (B=%d)", B);
+    if (B == 0) return XQ_OK;
+    XQ_CUDA(c, cudaSetDevice(c->device));
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t o_b = 0, o_sq = al((size_t)B * 90), o_by = al(o_sq + B), o_out = al(o_by + B), total = o_out + B;
+    int rc = ensure_pipe(c, total);
+    if (rc) return rc;
+    cudaStream_t s = c->pipe[0];
+    char* d = (char*)c->d_stage[0];
+    XQ_CUDA(c, cudaMemcpyAsync(d + o_b, h_boards, (size_t)B * 90, cudaMemcpyHostToDevice, s));
+    XQ_CUDA(c, cudaMemcpyAsync(d + o_sq, h_sq, (size_t)B, cudaMemcpyHostToDevice, s));
+    XQ_CUDA(c, cudaMemcpyAsync(d + o_by, h_by, (size_t)B, cudaMemcpyHostToDevice, s));
+    rc = xq_is_attacked_batch(c, (const int8_t*)(d + o_b), (const uint8_t*)(d + o_sq), (const int8_t*)(d + o_by), B,
+                              (uint8_t*)(d + o_out), s);
+    if (rc) return rc;
+    XQ_CUDA(c, cudaMemcpyAsync(h_out, d + o_out, (size_t)B, cudaMemcpyDeviceToHost, s));
+    XQ_CUDA(c, cudaStreamSynchronize(s));
+    return XQ_OK;
+}
+
+extern "C" int xq_random_playouts(xq_ctx* c, uint64_t seed, int n_games, int8_t* d_boards, int8_t* d_sides,
+                                  int32_t* d_n_positions, int8_t* d_winner, void* stream)
+{
+    if (!c) return xq_fail(nullptr, XQ_ERR_ARG, "xq_random_playouts: ctx is NULL");
+    if (n_games < 0 || (n_games > 0 && (!d_boards || !d_sides || !d_n_positions || !d_winner)))
+        return xq_fail(c, XQ_ERR_ARG, "xq_random_playouts: bad arguments");
+    if (n_games == 0) return XQ_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    {
+        XqTimer tm(c, s);
+        playout_kernel<<<(n_games + kPlayWarps - 1) / kPlayWarps, kPlayWarps * 32, 0, s>>>(
+            seed, n_games, d_boards, d_sides, d_n_positions, d_winner, c->d_overflow);
+    }
+    c->launches += 1;
+    XQ_CUDA(c, cudaGetLastError());
+    return XQ_OK;
+}

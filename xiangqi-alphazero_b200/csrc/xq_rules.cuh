@@ -1,0 +1,482 @@
+// xq_rules.cuh -- warp-cooperative xiangqi rules for sm_100a.
+//
+// One warp owns one board (90 int8 cells staged in shared memory).  The functions here are
+// the device-side replacement of the reference's only native component,
+// training/cython_engine/game_core.pyx, plus the termination rules of training/game.py:
+//
+//   warp_movegen      <- _generate_moves  game_core.pyx:262-486 (ordered legal list)
+//   legal_after_move  <- _is_move_legal   game_core.pyx:209-252
+//   attacked_sq       <- _is_attacked     game_core.pyx:104-189
+//   warp_find_kings   <- _find_king       game_core.pyx:78-101 (palace-only scan)
+//   warp_game_over    <- is_game_over     game.py:565-616
+//
+// Ordering contract: moves come out in (from-square row-major, per-piece
+// direction order, ray step) order, because the MCTS child order and every first-max
+// tie-break downstream depend on it.  The generator is split in two warp-parallel phases:
+//   A. pseudo-legal targets: one lane per (own piece, direction slot) task, two-pass
+//      count/scan/write so the compact list keeps the reference order;
+//   B. legality: one lane per pseudo-legal move (make-move overlay on the shared board, no
+//      per-lane board copy), ballot-compaction keeps the order.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace xq {
+
+constexpr int kSquares = 90;
+constexpr int kMaxMoves = 128;    // output slots per position (max seen in play: 74)
+constexpr int kMaxPseudo = 192;   // pseudo-legal scratch (orthodox upper bound: 119)
+constexpr unsigned kFull = 0xffffffffu;
+
+struct alignas(16) WarpScratch {
+    uint8_t pfrom[kMaxPseudo];
+    uint8_t pto[kMaxPseudo];
+    int16_t actions[kMaxMoves];   // compacted legal actions, unused slots = -1
+    uint8_t own_sq[96];           // own-piece squares in row-major order (phase A task table)
+};
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+__device__ __forceinline__ bool is_own(int p, int side) { return side == 1 ? p > 0 : p < 0; }
+__device__ __forceinline__ bool is_foe(int p, int side) { return side == 1 ? p < 0 : p > 0; }
+__device__ __forceinline__ bool can_land(int p, int side) { return p == 0 || is_foe(p, side); }
+
+// board cell as seen after the overlay move from->to (from < 0: no move)
+__device__ __forceinline__ int cell_after(const int8_t* b, int sq, int from, int to, int mover)
+{
+    int v = b[sq];
+    v = (sq == from) ? 0 : v;
+    v = (sq == to) ? mover : v;
+    return v;
+}
+
+// game_core.pyx:104-189 evaluated on the overlaid board.  The rook/king ray test and the
+// cannon ray test of the reference walk the same four rays; one walk sees the first piece
+// (rook or king attacks) and the second piece (cannon attacks).
+__device__ __forceinline__ bool attacked_sq(const int8_t* b, int kr, int kc, int by, int from, int to,
+                                            int mover)
+{
+    const int rook = 5 * by, cannon = 6 * by, horse = 4 * by, pawn = 7 * by, king = by;
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+        const int dr = (d == 0) ? -1 : (d == 1 ? 1 : 0);
+        const int dc = (d == 2) ? -1 : (d == 3 ? 1 : 0);
+        int r = kr + dr, c = kc + dc;
+        bool screen = false;
+        while (r >= 0 && r < 10 && c >= 0 && c < 9) {
+            int p = cell_after(b, r * 9 + c, from, to, mover);
+            if (p != 0) {
+                if (!screen) {
+                    if (p == rook || p == king) return true;
+                    screen = true;
+                } else {
+                    if (p == cannon) return true;
+                    break;
+                }
+            }
+            r += dr;
+            c += dc;
+        }
+    }
+    // knights: leg is adjacent to the knight, on the knight's long axis (pyx:156-169)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int jr = (i < 4) ? ((i < 2) ? -2 : 2) : ((i < 6) ? -1 : 1);
+        const int jc = (i < 4) ? ((i & 1) ? 1 : -1) : ((i & 1) ? 2 : -2);
+        int nr = kr + jr, nc = kc + jc;
+        if (nr < 0 || nr >= 10 || nc < 0 || nc >= 9) continue;
+        if (cell_after(b, nr * 9 + nc, from, to, mover) != horse) continue;
+        // move from knight to target = (-jr, -jc); leg = knight + half of the long component
+        int lr = nr, lc = nc;
+        if (jr == 2 || jr == -2) lr = nr - jr / 2; else lc = nc - jc / 2;
+        if (cell_after(b, lr * 9 + lc, from, to, mover) == 0) return true;
+    }
+    // pawns (pyx:172-187)
+    if (by == 1) {
+        if (kr - 1 >= 0 && cell_after(b, (kr - 1) * 9 + kc, from, to, mover) == pawn) return true;
+        if (kr >= 5) {
+            if (kc - 1 >= 0 && cell_after(b, kr * 9 + kc - 1, from, to, mover) == pawn) return true;
+            if (kc + 1 < 9 && cell_after(b, kr * 9 + kc + 1, from, to, mover) == pawn) return true;
+        }
+    } else {
+        if (kr + 1 < 10 && cell_after(b, (kr + 1) * 9 + kc, from, to, mover) == pawn) return true;
+        if (kr <= 4) {
+            if (kc - 1 >= 0 && cell_after(b, kr * 9 + kc - 1, from, to, mover) == pawn) return true;
+            if (kc + 1 < 9 && cell_after(b, kr * 9 + kc + 1, from, to, mover) == pawn) return true;
+        }
+    }
+    return false;
+}
+
+// palace square index 0..8 -> board square (rows r0..r0+2, cols 3..5, row-major like pyx:93-98)
+__device__ __forceinline__ int palace_sq(int side, int i) { return ((side == 1 ? 0 : 7) + i / 3) * 9 + 3 + i % 3; }
+
+// first king of `side` in its own palace on the overlaid board, or -1
+__device__ __forceinline__ int find_king_after(const int8_t* b, int side, int from, int to, int mover)
+{
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        int sq = palace_sq(side, i);
+        if (cell_after(b, sq, from, to, mover) == side) return sq;
+    }
+    return -1;
+}
+
+struct KingInfo {
+    int own_sq, foe_sq;       // first king in each palace on the un-moved board (-1: none)
+    int own_cnt, foe_cnt;     // kings standing in each palace (1/1 on any orthodox board)
+};
+
+// Warp-parallel palace scan: lanes 0-8 own palace, 9-17 enemy palace.
+__device__ __forceinline__ KingInfo warp_find_kings(const int8_t* b, int side)
+{
+    const int lane = lane_id();
+    bool hit = false;
+    if (lane < 9) hit = b[palace_sq(side, lane)] == side;
+    else if (lane < 18) hit = b[palace_sq(-side, lane - 9)] == -side;
+    unsigned m = __ballot_sync(kFull, hit);
+    unsigned own = m & 0x1ffu, foe = (m >> 9) & 0x1ffu;
+    KingInfo k;
+    k.own_sq = own ? palace_sq(side, __ffs(own) - 1) : -1;
+    k.foe_sq = foe ? palace_sq(-side, __ffs(foe) - 1) : -1;
+    k.own_cnt = __popc(own);
+    k.foe_cnt = __popc(foe);
+    return k;
+}
+
+// game_core.pyx:209-252.  from < 0 probes the current board ("null move") without the
+// flying-general clause, i.e. plain is_attacked(own king) -- used for the in-check flag.
+__device__ __forceinline__ bool legal_after_move(const int8_t* b, int side, const KingInfo& ki, int from,
+                                                 int to)
+{
+    const int mover = b[from];
+    int k, e;
+    if (ki.own_cnt == 1 && ki.foe_cnt <= 1 && (mover != side || from == ki.own_sq)) {
+        // orthodox fast path: only a king move relocates the own king, only a capture on the
+        // enemy king square removes the enemy king
+        k = (from == ki.own_sq) ? to : ki.own_sq;
+        e = (to == ki.foe_sq) ? -1 : ki.foe_sq;
+        if (from == ki.own_sq) {      // the king must still stand in its palace to be "found"
+            int r = to / 9, c = to % 9;
+            bool in_palace = c >= 3 && c <= 5 && (side == 1 ? r <= 2 : r >= 7);
+            if (!in_palace) k = -1;
+        }
+    } else {
+        k = find_king_after(b, side, from, to, mover);
+        e = find_king_after(b, -side, from, to, mover);
+    }
+    if (k < 0) return false;
+    const int kr = k / 9, kc = k % 9;
+    if (e >= 0 && e % 9 == kc) {
+        const int er = e / 9;
+        const int lo = min(kr, er), hi = max(kr, er);
+        bool open = true;
+        for (int r = lo + 1; r < hi; ++r)
+            if (cell_after(b, r * 9 + kc, from, to, mover) != 0) { open = false; break; }
+        if (open) return false;       // flying general
+    }
+    return !attacked_sq(b, kr, kc, -side, from, to, mover);
+}
+
+// Pseudo-legal targets of one (piece, direction-slot) task in reference order.
+// WRITE=false counts, WRITE=true stores target squares at dst[0..].
+template <bool WRITE>
+__device__ __forceinline__ int gen_task(const int8_t* b, int side, int sq, int kind, int d, uint8_t* dst)
+{
+    const int r = sq / 9, c = sq % 9;
+    int n = 0;
+    auto emit = [&](int t) {
+        if (WRITE) dst[n] = (uint8_t)t;
+        ++n;
+    };
+    const int dr4 = (d == 0) ? -1 : (d == 1 ? 1 : 0);   // DIRECTIONS pyx:42-46
+    const int dc4 = (d == 2) ? -1 : (d == 3 ? 1 : 0);
+    switch (kind) {
+    case 1: {  // king pyx:287-304
+        int nr = r + dr4, nc = c + dc4;
+        int lo = side == 1 ? 0 : 7;
+        if (nr >= lo && nr <= lo + 2 && nc >= 3 && nc <= 5 && can_land(b[nr * 9 + nc], side)) emit(nr * 9 + nc);
+        break;
+    }
+    case 2: {  // advisor pyx:307-326: (dr,dc) = (-1,-1),(-1,1),(1,-1),(1,1); palace box only
+        int nr = r + (d < 2 ? -1 : 1), nc = c + ((d & 1) ? 1 : -1);
+        bool ok = nr >= 0 && nr < 10 && nc >= 3 && nc <= 5 && (side == 1 ? nr <= 2 : nr >= 7);
+        if (ok && can_land(b[nr * 9 + nc], side)) emit(nr * 9 + nc);
+        break;
+    }
+    case 3: {  // elephant pyx:329-349
+        int sr = (d < 2 ? -1 : 1), sc = ((d & 1) ? 1 : -1);
+        int nr = r + 2 * sr, nc = c + 2 * sc;
+        bool ok = nr >= 0 && nr < 10 && nc >= 0 && nc < 9 && (side == 1 ? nr <= 4 : nr >= 5);
+        if (ok && b[(r + sr) * 9 + c + sc] == 0 && can_land(b[nr * 9 + nc], side)) emit(nr * 9 + nc);
+        break;
+    }
+    case 4: {  // knight pyx:352-367: slot d covers KNIGHT_MOVES[2d], [2d+1]
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            int i = 2 * d + h;
+            int jr = (i < 4) ? ((i < 2) ? -2 : 2) : ((i < 6) ? -1 : 1);
+            int jc = (i < 4) ? ((i & 1) ? 1 : -1) : ((i & 1) ? 2 : -2);
+            int lr = (i < 4) ? ((i < 2) ? -1 : 1) : 0;
+            int lc = (i < 4) ? 0 : ((i & 1) ? 1 : -1);
+            int nr = r + jr, nc = c + jc;
+            if (nr < 0 || nr >= 10 || nc < 0 || nc >= 9) continue;
+            if (b[(r + lr) * 9 + c + lc] != 0) continue;
+            if (can_land(b[nr * 9 + nc], side)) emit(nr * 9 + nc);
+        }
+        break;
+    }
+    case 5: {  // rook pyx:370-396
+        int nr = r + dr4, nc = c + dc4;
+        while (nr >= 0 && nr < 10 && nc >= 0 && nc < 9) {
+            int p = b[nr * 9 + nc];
+            if (p == 0) emit(nr * 9 + nc);
+            else {
+                if (is_foe(p, side)) emit(nr * 9 + nc);
+                break;
+            }
+            nr += dr4;
+            nc += dc4;
+        }
+        break;
+    }
+    case 6: {  // cannon pyx:399-431
+        int nr = r + dr4, nc = c + dc4;
+        while (nr >= 0 && nr < 10 && nc >= 0 && nc < 9 && b[nr * 9 + nc] == 0) {
+            emit(nr * 9 + nc);
+            nr += dr4;
+            nc += dc4;
+        }
+        nr += dr4;   // hop over the screen (if we ran off the board the loop below is empty)
+        nc += dc4;
+        while (nr >= 0 && nr < 10 && nc >= 0 && nc < 9) {
+            int p = b[nr * 9 + nc];
+            if (p != 0) {
+                if (is_foe(p, side)) emit(nr * 9 + nc);
+                break;
+            }
+            nr += dr4;
+            nc += dc4;
+        }
+        break;
+    }
+    case 7: {  // pawn pyx:434-484: slot 0 forward, 1 left, 2 right (sideways once across the river)
+        int fwd = side == 1 ? 1 : -1;
+        bool crossed = side == 1 ? r >= 5 : r <= 4;
+        if (d == 0) {
+            int nr = r + fwd;
+            if (nr >= 0 && nr < 10 && can_land(b[nr * 9 + c], side)) emit(nr * 9 + c);
+        } else if (d == 1) {
+            if (crossed && c - 1 >= 0 && can_land(b[r * 9 + c - 1], side)) emit(r * 9 + c - 1);
+        } else if (d == 2) {
+            if (crossed && c + 1 < 9 && can_land(b[r * 9 + c + 1], side)) emit(r * 9 + c + 1);
+        }
+        break;
+    }
+    default:
+        break;
+    }
+    return n;
+}
+
+__device__ __forceinline__ int warp_incl_scan(int v)
+{
+    const int lane = lane_id();
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(kFull, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+struct MovegenResult {
+    int n_legal;      // may exceed kMaxMoves only on unorthodox boards (then truncated + flagged)
+    bool in_check;    // cy_is_in_check: own king attacked, or missing
+    bool overflow;
+    KingInfo kings;
+};
+
+// Full ordered legal-move generation for one board by one warp.
+// b: 90 cells in shared memory; S.actions receives the compacted list (unused slots = -1).
+__device__ __forceinline__ MovegenResult warp_movegen(const int8_t* b, int side, WarpScratch& S)
+{
+    const int lane = lane_id();
+    MovegenResult res;
+    res.overflow = false;
+    res.kings = warp_find_kings(b, side);
+
+    // ---- phase A: ordered pseudo-legal list --------------------------------------------
+    // own pieces in square order: rank among own pieces = task group
+    int n_pseudo = 0;
+    int n_pieces = 0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        int sq = k * 32 + lane;
+        bool o = sq < kSquares && is_own(b[sq], side);
+        unsigned m = __ballot_sync(kFull, o);
+        if (o) S.own_sq[n_pieces + __popc(m & ((1u << lane) - 1u))] = (uint8_t)sq;
+        n_pieces += __popc(m);
+    }
+    __syncwarp();
+    for (int t0 = 0; t0 < 4 * n_pieces; t0 += 32) {
+        const int t = t0 + lane;
+        int sq = -1, kind = 0, d = t & 3;
+        if (t < 4 * n_pieces) {
+            sq = S.own_sq[t >> 2];
+            int p = b[sq];
+            kind = p < 0 ? -p : p;
+        }
+        int cnt = (sq >= 0) ? gen_task<false>(b, side, sq, kind, d, nullptr) : 0;
+        int incl = warp_incl_scan(cnt);
+        int total = __shfl_sync(kFull, incl, 31);
+        int off = n_pseudo + incl - cnt;
+        if (cnt > 0) {
+            if (off + cnt <= kMaxPseudo) {
+                gen_task<true>(b, side, sq, kind, d, &S.pto[off]);
+                for (int i = 0; i < cnt; ++i) S.pfrom[off + i] = (uint8_t)sq;
+            } else {
+                res.overflow = true;
+            }
+        }
+        n_pseudo += total;
+    }
+    res.overflow = __any_sync(kFull, res.overflow);
+    if (n_pseudo > kMaxPseudo) n_pseudo = kMaxPseudo;
+    // unused output slots read back as -1
+    for (int i = lane; i < kMaxMoves; i += 32) S.actions[i] = -1;
+    __syncwarp();
+
+    // ---- phase B: legality + ordered compaction; item n_pseudo is the in-check probe -----
+    int n_legal = 0;
+    bool chk = false;
+    for (int i0 = 0; i0 <= n_pseudo; i0 += 32) {
+        const int i = i0 + lane;
+        bool ok = false;
+        int from = 0, to = 0;
+        if (i < n_pseudo) {
+            from = S.pfrom[i];
+            to = S.pto[i];
+            ok = legal_after_move(b, side, res.kings, from, to);
+        } else if (i == n_pseudo) {
+            // cy_is_in_check (pyx:543-555): missing king => True
+            int k = res.kings.own_sq;
+            chk = (k < 0) ? true : attacked_sq(b, k / 9, k % 9, -side, -1, -1, 0);
+        }
+        unsigned m = __ballot_sync(kFull, ok);
+        if (ok) {
+            int pos = n_legal + __popc(m & ((1u << lane) - 1u));
+            if (pos < kMaxMoves) S.actions[pos] = (int16_t)(from * 90 + to);
+        }
+        n_legal += __popc(m);
+    }
+    res.in_check = __any_sync(kFull, chk);
+    if (n_legal > kMaxMoves) res.overflow = true;
+    res.n_legal = n_legal;
+    __syncwarp();
+    return res;
+}
+
+// ------------------------------------------------------------------------------------------
+// Game state and termination (game.py:528-616).  len(history) == move_count and only
+// history[-12:] is ever compared, so a 12-slot ring of pre-move boards is the whole history.
+// ------------------------------------------------------------------------------------------
+constexpr int kRing = 12;
+constexpr int kBoardPad = 96;     // 90 cells padded to 96 B so every board is 16 B aligned
+
+struct GameMeta {
+    int side;          // current_player: +1 red, -1 black
+    int move_count;
+    int no_capture;
+};
+
+__device__ __forceinline__ int piece_value(int kind)
+{
+    // PIECE_VALUES game.py:74: K0 A20 B20 N40 R90 C45 P10
+    return kind == 2 || kind == 3 ? 20 : kind == 4 ? 40 : kind == 5 ? 90 : kind == 6 ? 45 : kind == 7 ? 10 : 0;
+}
+
+// red material minus black material, warp-reduced (game.py:552-563, 595-604)
+__device__ __forceinline__ int warp_material_diff(const int8_t* b)
+{
+    const int lane = lane_id();
+    int s = 0;
+    for (int sq = lane; sq < kSquares; sq += 32) {
+        int p = b[sq];
+        s += p > 0 ? piece_value(p) : -piece_value(-p);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(kFull, s, o);
+    return s;
+}
+
+// make_move (game.py:528-545) on a warp-owned state: ring[move_count % 12] <- board before the move.
+__device__ __forceinline__ void warp_make_move(int8_t* b, int8_t* ring, GameMeta& g, int action)
+{
+    const int lane = lane_id();
+    const int from = action / 90, to = action % 90;
+    int8_t* slot = ring + (g.move_count % kRing) * kBoardPad;
+    for (int i = lane; i < kSquares; i += 32) slot[i] = b[i];
+    __syncwarp();
+    int taken = b[to];
+    __syncwarp();
+    if (lane == 0) {
+        b[to] = b[from];
+        b[from] = 0;
+    }
+    g.no_capture = taken != 0 ? 0 : g.no_capture + 1;
+    g.side = -g.side;
+    g.move_count += 1;
+    __syncwarp();
+}
+
+// is_game_over (game.py:565-616).  Returns winner in {1,-1,0} or 2 when the game goes on.
+// mg must be the movegen result for (b, g.side).
+__device__ __forceinline__ int warp_game_over(const int8_t* b, const int8_t* ring, const GameMeta& g,
+                                              const MovegenResult& mg)
+{
+    const int lane = lane_id();
+    // king presence: _find_king scans the own palace only
+    int red_king = g.side == 1 ? mg.kings.own_sq : mg.kings.foe_sq;
+    int black_king = g.side == 1 ? mg.kings.foe_sq : mg.kings.own_sq;
+    if (red_king < 0) return -1;
+    if (black_king < 0) return 1;
+    if (mg.n_legal == 0) return -g.side;
+    if (g.no_capture >= 120) return 0;
+    if (g.move_count >= 200) {
+        int diff = warp_material_diff(b);
+        return diff > 30 ? 1 : (diff < -30 ? -1 : 0);
+    }
+    if (g.move_count >= 6) {
+        const int depth = min(g.move_count, kRing);
+        // lane k compares history slot k (one of the last `depth` pre-move boards)
+        bool same = false;
+        if (lane < depth) {
+            const int8_t* h = ring + ((g.move_count - 1 - lane) % kRing) * kBoardPad;
+            same = true;
+            // 90 bytes; boards are 16 B aligned in shared memory
+            const uint32_t* a = reinterpret_cast<const uint32_t*>(b);
+            const uint32_t* c = reinterpret_cast<const uint32_t*>(h);
+#pragma unroll
+            for (int w = 0; w < 22; ++w) same = same && (a[w] == c[w]);
+            same = same && (b[88] == h[88]) && (b[89] == h[89]);
+        }
+        if (__popc(__ballot_sync(kFull, same)) >= 3) return 0;
+    }
+    return 2;
+}
+
+// counter-based RNG (stateless, reproducible per (seed, game, ply, stream))
+__device__ __forceinline__ uint64_t mix64(uint64_t z)
+{
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ uint64_t rng_u64(uint64_t seed, uint64_t a, uint64_t b, uint64_t c)
+{
+    return mix64(mix64(mix64(seed + 0x9E3779B97F4A7C15ull * (a + 1)) ^ (b * 0xD1B54A32D192ED03ull)) ^
+                 (c * 0x8CB92BA72F3D8DD7ull));
+}
+
+}  // namespace xq

@@ -1,0 +1,205 @@
+"""ctypes binding of libxq_b200.so (include/xq_b200.h) -- the only way the Python host
+code reaches the GPU kernels.  torch is used for device memory and streams only.
+
+There is no CPU path: importing is harmless, but `Engine()` raises if the shared library
+has not been built (python __graft_entry__.py / make -C csrc) or no CUDA device is visible.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libxq_b200.so")
+
+MAX_MOVES = 128
+MAX_PLIES = 201
+ACTION_SPACE = 8100
+
+_lib = None
+
+
+class XqError(RuntimeError):
+    pass
+
+
+def build(verbose: bool = False) -> str:
+    """Compile csrc/*.cu for sm_100a into libxq_b200.so (nvcc cross-compiles without a GPU)."""
+    out = subprocess.run(["make", "-C", os.path.join(_HERE, "csrc")], capture_output=True, text=True)
+    if verbose or out.returncode != 0:
+        print(out.stdout[-4000:], out.stderr[-4000:])
+    if out.returncode != 0:
+        raise XqError("building libxq_b200.so failed")
+    return LIB_PATH
+
+
+def _sig(L, name, restype, *argtypes):
+    fn = getattr(L, name)
+    fn.restype = restype
+    fn.argtypes = list(argtypes)
+    return fn
+
+
+def lib():
+    """Load libxq_b200.so and declare every symbol of include/xq_b200.h."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise XqError(f"{LIB_PATH} is missing: build it with `python __graft_entry__.py` "
+                      "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, u64 = C.c_void_p, C.c_int, C.c_uint64
+    _sig(L, "xq_create", i32, i32, C.POINTER(vp))
+    _sig(L, "xq_destroy", None, vp)
+    _sig(L, "xq_last_error", C.c_char_p, vp)
+    _sig(L, "xq_version", i32)
+    _sig(L, "xq_launch_count", C.c_longlong, vp, i32)
+    _sig(L, "xq_set_timing", i32, vp, i32)
+    _sig(L, "xq_last_kernel_ms", C.c_float, vp)
+    _sig(L, "xq_movegen_batch", i32, vp, vp, vp, i32, vp, vp, vp, vp, vp)
+    _sig(L, "xq_movegen_batch_host", i32, vp, vp, vp, i32, vp, vp, vp, vp)
+    _sig(L, "xq_is_attacked_batch", i32, vp, vp, vp, vp, i32, vp, vp)
+    _sig(L, "xq_is_attacked_batch_host", i32, vp, vp, vp, vp, i32, vp)
+    _sig(L, "xq_overflow_count", i32, vp, i32)
+    _sig(L, "xq_random_playouts", i32, vp, u64, i32, vp, vp, vp, vp, vp)
+    _lib = L
+    return L
+
+
+EXPORTS = ["xq_create", "xq_destroy", "xq_last_error", "xq_version", "xq_launch_count", "xq_set_timing",
+           "xq_last_kernel_ms", "xq_movegen_batch", "xq_movegen_batch_host", "xq_is_attacked_batch",
+           "xq_is_attacked_batch_host", "xq_overflow_count", "xq_random_playouts"]
+
+
+def _np_ptr(a: np.ndarray):
+    return C.c_void_p(a.ctypes.data)
+
+
+class Engine:
+    """One context per GPU/process (xq_create).  Methods mirror the C entry points."""
+
+    def __init__(self, device: int = 0):
+        import torch
+        if not torch.cuda.is_available():
+            raise XqError("no CUDA device: the xq_b200 engine has no CPU path")
+        self.torch = torch
+        self.L = lib()
+        self.device = int(device)
+        self.dev = torch.device("cuda", self.device)
+        h = C.c_void_p()
+        rc = self.L.xq_create(self.device, C.byref(h))
+        if rc != 0:
+            raise XqError(self.L.xq_last_error(None).decode())
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.xq_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise XqError(f"xq error {rc}: {self.L.xq_last_error(self.h).decode()}")
+
+    def _stream(self):
+        return C.c_void_p(self.torch.cuda.current_stream(self.dev).cuda_stream)
+
+    # ---- diagnostics ----------------------------------------------------------------------
+    def launch_count(self, reset=False) -> int:
+        return int(self.L.xq_launch_count(self.h, int(reset)))
+
+    def set_timing(self, on: bool):
+        self._check(self.L.xq_set_timing(self.h, int(on)))
+
+    def last_kernel_ms(self) -> float:
+        return float(self.L.xq_last_kernel_ms(self.h))
+
+    def overflow_count(self, reset=False) -> int:
+        return int(self.L.xq_overflow_count(self.h, int(reset)))
+
+    # ---- K1 ---------------------------------------------------------------------------------
+    def movegen(self, boards, sides, planes: bool = False, out=None):
+        """Device tensors in, device tensors out (async on the current torch stream).
+
+        boards int8 [B,90] (or [B,10,9]), sides int8 [B] ->
+        actions int16 [B,128], n_moves uint8 [B], in_check uint8 [B], planes float32 [B,15,10,9] | None
+        """
+        t = self.torch
+        boards = boards.reshape(-1, 90)
+        assert boards.dtype == t.int8 and sides.dtype == t.int8 and boards.is_cuda and sides.is_cuda
+        boards = boards.contiguous()
+        sides = sides.contiguous()
+        B = boards.shape[0]
+        if out is None:
+            actions = t.empty((B, MAX_MOVES), dtype=t.int16, device=self.dev)
+            n = t.empty((B,), dtype=t.uint8, device=self.dev)
+            chk = t.empty((B,), dtype=t.uint8, device=self.dev)
+            pl = t.empty((B, 15, 10, 9), dtype=t.float32, device=self.dev) if planes else None
+        else:
+            actions, n, chk, pl = out
+        self._check(self.L.xq_movegen_batch(self.h, boards.data_ptr(), sides.data_ptr(), B, actions.data_ptr(),
+                                            n.data_ptr(), chk.data_ptr(), pl.data_ptr() if pl is not None else None,
+                                            self._stream()))
+        return actions, n, chk, pl
+
+    def movegen_host(self, boards: np.ndarray, sides: np.ndarray, planes: bool = False, out=None):
+        """Host arrays in, host arrays out (the reference-facing form: numpy boards, like
+        cy_generate_legal_moves).  Copies run inside the call; pass pinned arrays for full speed."""
+        boards = np.ascontiguousarray(boards, np.int8).reshape(-1, 90)
+        sides = np.ascontiguousarray(sides, np.int8)
+        B = boards.shape[0]
+        if out is None:
+            actions = np.empty((B, MAX_MOVES), np.int16)
+            n = np.empty(B, np.uint8)
+            chk = np.empty(B, np.uint8)
+            pl = np.empty((B, 15, 10, 9), np.float32) if planes else None
+        else:
+            actions, n, chk, pl = out
+        rc = self.L.xq_movegen_batch_host(self.h, _np_ptr(boards), _np_ptr(sides), B, _np_ptr(actions), _np_ptr(n),
+                                          _np_ptr(chk), _np_ptr(pl) if pl is not None else None)
+        self._check(rc)
+        return actions, n, chk, pl
+
+    def is_attacked(self, boards, sq, by):
+        t = self.torch
+        boards = boards.reshape(-1, 90).contiguous()
+        B = boards.shape[0]
+        out = t.empty((B,), dtype=t.uint8, device=self.dev)
+        self._check(self.L.xq_is_attacked_batch(self.h, boards.data_ptr(), sq.contiguous().data_ptr(),
+                                                by.contiguous().data_ptr(), B, out.data_ptr(), self._stream()))
+        return out
+
+    def is_attacked_host(self, boards: np.ndarray, sq: np.ndarray, by: np.ndarray) -> np.ndarray:
+        boards = np.ascontiguousarray(boards, np.int8).reshape(-1, 90)
+        sq = np.ascontiguousarray(sq, np.uint8)
+        by = np.ascontiguousarray(by, np.int8)
+        out = np.empty(boards.shape[0], np.uint8)
+        self._check(self.L.xq_is_attacked_batch_host(self.h, _np_ptr(boards), _np_ptr(sq), _np_ptr(by),
+                                                     boards.shape[0], _np_ptr(out)))
+        return out
+
+    def random_playouts(self, seed: int, n_games: int, compact: bool = True):
+        """Uniform-random legal playouts on the device.  Returns (boards int8 [N,90], sides int8 [N],
+        n_positions int32 [G], winner int8 [G]) as device tensors; with compact=False boards/sides keep
+        the [G*201] slot layout (side 0 marks unused slots)."""
+        t = self.torch
+        boards = t.empty((n_games * MAX_PLIES, 90), dtype=t.int8, device=self.dev)
+        sides = t.empty((n_games * MAX_PLIES,), dtype=t.int8, device=self.dev)
+        npos = t.empty((n_games,), dtype=t.int32, device=self.dev)
+        win = t.empty((n_games,), dtype=t.int8, device=self.dev)
+        self._check(self.L.xq_random_playouts(self.h, C.c_uint64(seed), n_games, boards.data_ptr(), sides.data_ptr(),
+                                              npos.data_ptr(), win.data_ptr(), self._stream()))
+        if compact:
+            keep = sides != 0
+            boards, sides = boards[keep].contiguous(), sides[keep].contiguous()
+        return boards, sides, npos, win
