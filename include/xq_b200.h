@@ -97,6 +97,57 @@ int xq_overflow_count(xq_ctx* ctx, int reset);
 int xq_random_playouts(xq_ctx* ctx, uint64_t seed, int n_games, int8_t* d_boards, int8_t* d_sides,
                        int32_t* d_n_positions, int8_t* d_winner, void* stream);
 
+/* ---- K2: batched GPU-resident MCTS -----------------------------------------------------------
+ * Replaces training/mcts.py (MCTSNode :21-73, MCTS.search :94-155) for n_games independent games
+ * searched in lockstep: one warp per game, one simulation per game per step, so the leaves of a
+ * step form ONE evaluator batch (what inference_server.py:145-279 assembled over sockets).
+ * Arithmetic follows the reference bit for bit (float32 UCB, float64 noisy root, float64 W,
+ * first-max tie-breaks); see csrc/xq_mcts.cu.
+ *
+ * One search =  set_games -> root_begin -> [evaluate roots] -> root_expand ->
+ *               S x ( select -> [evaluate leaves] -> expand_backup ) -> root_visits.
+ * The evaluator sits between the calls and may be anything that fills `policy`/`value`.
+ *
+ * policy_kind: 0 = float32 probabilities, the predict() contract (model.py:109-124);
+ *              1 = bf16 logits, 2 = float32 logits (softmax over the legal entries is taken here).
+ * row_stride: elements between consecutive games' policy rows (>= 8100).
+ */
+int xq_mcts_create(xq_ctx* ctx, int max_games, long long node_capacity /* 0 = max_games*801*64 */);
+
+/* Copies game states in: d_boards [G][90], d_sides [G]; optional d_move_count / d_no_capture [G]
+ * int32 (NULL = 0), d_ring [G][12][90] = board before move i at slot i%12, the last 12 entries of
+ * XiangqiGame.history (NULL = zeros), d_active [G] uint8 (NULL = all active). */
+int xq_mcts_set_games(xq_ctx* ctx, int n_games, const int8_t* d_boards, const int8_t* d_sides,
+                      const int32_t* d_move_count, const int32_t* d_no_capture, const int8_t* d_ring,
+                      const uint8_t* d_active, void* stream);
+
+/* Evaluator inputs of the roots / of the current leaves; every output pointer is optional:
+ *   d_planes [G][15][10][9] float32 (get_state_for_nn), d_x_nhwc = conv input tile of xq_net_*
+ *   (bf16 [G*110+..][16]), d_boards_out [G][90] + d_sides_out [G]. */
+int xq_mcts_root_begin(xq_ctx* ctx, float* d_planes, void* d_x_nhwc, int8_t* d_boards_out, int8_t* d_sides_out,
+                       void* stream);
+/* mcts.py:110-123: mask + normalise the root policy, optional Dirichlet mixing 0.75 P + 0.25 eta.
+ * d_noise [G][128] float64 injects eta (tests); NULL draws Dirichlet(alpha) on the device. */
+int xq_mcts_root_expand(xq_ctx* ctx, const void* d_policy, int policy_kind, long long row_stride,
+                        const double* d_noise, int add_noise, uint64_t noise_seed, double alpha, void* stream);
+/* mcts.py:126-140: descend by PUCT, replay the moves, is_game_over at the leaf; terminal leaves are
+ * backed up here, the others wait for expand_backup. */
+int xq_mcts_select(xq_ctx* ctx, double c_puct, float* d_planes, void* d_x_nhwc, int8_t* d_boards_out,
+                   int8_t* d_sides_out, void* stream);
+/* mcts.py:142-153: expand the leaf with masked priors, back up -value. d_value [G] float32. */
+int xq_mcts_expand_backup(xq_ctx* ctx, const void* d_policy, int policy_kind, long long row_stride,
+                          const float* d_value, void* stream);
+/* leaf bookkeeping of the last root_begin/select: state (0 wants evaluation, 1 terminal, 2 idle),
+ * legal count and ordered actions; any pointer may be NULL. */
+int xq_mcts_leaf_info(xq_ctx* ctx, int32_t* d_state, int32_t* d_n, int16_t* d_actions, void* stream);
+/* visit counts of the root children in child (= move generation) order: d_actions/d_visits [G][128],
+ * d_n [G], optional d_w [G][128] float64 total values. */
+int xq_mcts_root_visits(xq_ctx* ctx, int16_t* d_actions, int32_t* d_visits, int32_t* d_n, double* d_w,
+                        void* stream);
+/* h_stats6: simulations, terminal-leaf simulations, max depth, evaluations consumed, nodes in the
+ * current search, error bits (1 node pool overflow, 2 >128 legal moves). Synchronises. */
+int xq_mcts_stats(xq_ctx* ctx, long long* h_stats6, int reset);
+
 #ifdef __cplusplus
 }
 #endif

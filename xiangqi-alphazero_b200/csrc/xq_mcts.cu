@@ -1,3 +1,637 @@
-// placeholder -- filled in by the K2 milestone
+// xq_mcts.cu -- K2: GPU-resident batched MCTS (one flat tree per game, one warp per game).
+//
+// Replaces training/mcts.py: MCTSNode (:21-73: select_child :43-58, expand :60-64, backup
+// :66-73) and the body of MCTS.search (:94-155) for B independent games advanced in lockstep,
+// one simulation per game per step, so that the B leaves of a step form one evaluator batch
+// (the in-device replacement of inference_server.py's socket batching).
+//
+// Bit-level contract (pinned by tests/golden/mcts_golden.json):
+//   - children are created in legal-move generation order; argmax uses strict '>' so the
+//     first maximum wins;
+//   - priors are np.float32 (p[a] / sequential-float32-sum), UCB is evaluated in float32 with
+//     the reference's operation order;  a root with Dirichlet noise has float64 priors
+//     (0.75*P32 + 0.25*noise) and float64 UCB;  the all-zero-mass fallback is the python float 1/n;
+//   - W accumulates in float64, q = W/N in float64 then (float32 path) rounded to float32;
+//   - a decisive terminal leaf backs up +1.0 whoever won (mcts.py:140), a drawn one 0.0, and
+//     stays a leaf; a non-terminal leaf is expanded and backs up -value.
+//
+// Memory: two 16-byte records per node -- Hot {W f64, N i32, P f32} read by the select
+// argmax with one coalesced 16 B load per lane, and Link {first child, parent, action, child
+// count, flags} read once per descent level.  Nodes of one expansion are contiguous.
 #include "xq_ctx.h"
-extern "C" void xq_mcts_free_(xq_ctx*) {}
+#include "xq_rules.cuh"
+
+#include <cuda_bf16.h>
+
+namespace xq {
+
+struct __align__(16) NodeHot {
+    double W;
+    int32_t N;
+    float P;
+};
+struct __align__(16) NodeLink {
+    int32_t child0;   // -1 while leaf
+    int32_t parent;   // -1 for a root
+    int16_t action;
+    uint8_t nchild;
+    uint8_t flags;    // priors of this node's CHILDREN: 0 float32, 1 float64 uniform 1/n, 2 float64 in rootP64
+    int32_t pad;
+};
+
+enum { kLeafEval = 0, kLeafTerminal = 1, kLeafIdle = 2 };
+
+struct MctsState {
+    int max_games = 0;
+    long long cap_nodes = 0;
+    int n_games = 0;
+    // game state
+    int8_t* board = nullptr;      // [G][96]
+    int8_t* ring = nullptr;       // [G][12][96]
+    int32_t* meta = nullptr;      // [G][4] side, move_count, no_capture, active
+    // tree
+    NodeHot* hot = nullptr;
+    NodeLink* link = nullptr;
+    double* rootP64 = nullptr;    // [G][128]
+    int* alloc = nullptr;         // bump pointer into the node pool
+    int* error = nullptr;         // bit0 pool overflow, bit1 move overflow
+    // per-step leaf records
+    int32_t* leaf_node = nullptr;   // [G]
+    int32_t* leaf_state = nullptr;  // [G]
+    int16_t* leaf_actions = nullptr;  // [G][128]
+    int32_t* leaf_n = nullptr;        // [G]
+    int64_t* stats = nullptr;         // [4] sims, terminal sims, max depth, evals
+};
+
+constexpr int kSelWarps = 4;
+
+struct __align__(16) SelectSmem {
+    int8_t board[kSelWarps][kBoardPad];
+    int8_t ring[kSelWarps][kRing * kBoardPad];
+    WarpScratch ws[kSelWarps];
+};
+
+__device__ __forceinline__ void warp_load_game(const MctsState& M, int g, int8_t* b, int8_t* ring, GameMeta& gm)
+{
+    const int lane = lane_id();
+    // 96 B board = 6 x uint4, 1152 B ring = 72 x uint4
+    const uint4* gb = reinterpret_cast<const uint4*>(M.board + (size_t)g * kBoardPad);
+    const uint4* gr = reinterpret_cast<const uint4*>(M.ring + (size_t)g * kRing * kBoardPad);
+    if (lane < 6) reinterpret_cast<uint4*>(b)[lane] = gb[lane];
+    for (int i = lane; i < 72; i += 32) reinterpret_cast<uint4*>(ring)[i] = gr[i];
+    gm.side = M.meta[g * 4 + 0];
+    gm.move_count = M.meta[g * 4 + 1];
+    gm.no_capture = M.meta[g * 4 + 2];
+    warp_sync();
+}
+
+// get_state_for_nn planes (game.py:618-640) and/or the conv input tile of the network kernels
+// (bf16, 16 channels per cell, rows padded as [board][11][10] with zero halo cells never written).
+__device__ __forceinline__ void warp_emit_eval_inputs(const int8_t* b, int side, int g, float* planes_f32,
+                                                      __nv_bfloat16* x_nhwc, int8_t* boards_out, int8_t* sides_out)
+{
+    const int lane = lane_id();
+    if (boards_out) {
+        for (int i = lane; i < kSquares; i += 32) boards_out[(size_t)g * kSquares + i] = b[i];
+        if (lane == 0) sides_out[g] = (int8_t)side;
+    }
+    if (planes_f32) {
+        float2* out = reinterpret_cast<float2*>(planes_f32 + (size_t)g * 15 * kSquares);
+        const float turn = side == 1 ? 1.0f : 0.0f;
+        for (int e2 = lane; e2 < 15 * kSquares / 2; e2 += 32) {
+            const int e = 2 * e2, p = e / kSquares, sq = e - p * kSquares;
+            float2 v;
+            if (p == 14) v.x = v.y = turn;
+            else {
+                int v0 = b[sq] * side, v1 = b[sq + 1] * side;
+                int c0 = v0 > 0 ? v0 - 1 : (v0 < 0 ? 6 - v0 : -1);
+                int c1 = v1 > 0 ? v1 - 1 : (v1 < 0 ? 6 - v1 : -1);
+                v.x = c0 == p ? 1.0f : 0.0f;
+                v.y = c1 == p ? 1.0f : 0.0f;
+            }
+            out[e2] = v;
+        }
+    }
+    if (x_nhwc) {
+        // cell (r,c) of board g lives at row g*110 + (r+1)*10 + c, 16 bf16 channels = 32 B
+        const uint32_t one = 0x3f80u;   // bf16 1.0
+        for (int sq = lane; sq < kSquares; sq += 32) {
+            int v = b[sq] * side;
+            int ch = v > 0 ? v - 1 : (v < 0 ? 6 - v : -1);
+            uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            if (ch >= 0) w[ch >> 1] = one << ((ch & 1) * 16);
+            if (side == 1) w[7] |= one;   // channel 14 (low half of word 7); channel 15 is padding
+            const int r = sq / 9, c = sq - r * 9;
+            uint4* dst = reinterpret_cast<uint4*>(x_nhwc + ((size_t)g * 110 + (r + 1) * 10 + c) * 16);
+            dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+            dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+        }
+    }
+}
+
+// lane 0 walks the parent chain (mcts.py:66-73)
+__device__ __forceinline__ int backup_path(const MctsState& M, int node, double value)
+{
+    int depth = 0;
+    while (node >= 0) {
+        NodeHot h = M.hot[node];
+        h.N += 1;
+        h.W = __dadd_rn(h.W, value);
+        M.hot[node] = h;
+        value = -value;
+        node = M.link[node].parent;
+        ++depth;
+    }
+    return depth;
+}
+
+// ---- root preparation: movegen on every root, emit evaluator inputs -------------------------
+__global__ void __launch_bounds__(kSelWarps * 32)
+mcts_root_begin_kernel(MctsState M, float* planes_f32, __nv_bfloat16* x_nhwc, int8_t* boards_out, int8_t* sides_out)
+{
+    __shared__ SelectSmem sm;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.x * kSelWarps + warp;
+    if (g >= M.n_games) return;
+    int8_t* b = sm.board[warp];
+    GameMeta gm;
+    warp_load_game(M, g, b, sm.ring[warp], gm);
+    WarpScratch& S = sm.ws[warp];
+    const bool active = M.meta[g * 4 + 3] != 0;
+    MovegenResult r = warp_movegen(b, gm.side, S);
+    if (r.overflow && lane == 0) atomicOr(M.error, 2);
+    const int n = active ? min(r.n_legal, kMaxMoves) : 0;
+    reinterpret_cast<uint2*>(M.leaf_actions + (size_t)g * kMaxMoves)[lane] = reinterpret_cast<const uint2*>(S.actions)[lane];
+    if (lane == 0) {
+        M.leaf_n[g] = n;
+        M.leaf_node[g] = g;
+        M.leaf_state[g] = n > 0 ? kLeafEval : kLeafIdle;
+        // fresh root (mcts.py:104)
+        M.hot[g] = NodeHot{0.0, 0, 0.0f};
+        M.link[g] = NodeLink{-1, -1, (int16_t)-1, 0, 0, 0};
+    }
+    warp_emit_eval_inputs(b, gm.side, g, planes_f32, x_nhwc, boards_out, sides_out);
+}
+
+// Marsaglia-Tsang gamma(alpha<1) via gamma(alpha+1) * U^(1/alpha); counter-based uniforms
+__device__ __forceinline__ double u01(uint64_t x) { return ((x >> 11) + 0.5) * (1.0 / 9007199254740992.0); }
+__device__ double gamma_sample(double alpha, uint64_t seed, uint64_t a, uint64_t b)
+{
+    const double d = alpha + 1.0 - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+    uint64_t ctr = 0;
+    for (int it = 0; it < 64; ++it) {
+        double u1 = u01(rng_u64(seed, a, b, ctr++)), u2 = u01(rng_u64(seed, a, b, ctr++));
+        double z = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+        double v = 1.0 + c * z;
+        if (v <= 0.0) continue;
+        v = v * v * v;
+        double u = u01(rng_u64(seed, a, b, ctr++));
+        if (log(u) < 0.5 * z * z + d - d * v + d * log(v)) {
+            double uu = u01(rng_u64(seed, a, b, ctr++));
+            return d * v * pow(uu, 1.0 / alpha);
+        }
+    }
+    return alpha;
+}
+
+// priors of one expansion (mcts.py:176-188).  KIND 0: float32 probabilities [8100] per game
+// (the predict() contract); KIND 1: bf16 logits, KIND 2: float32 logits -> softmax over the legal
+// entries (== softmax over all 8100 then renormalised over the legal ones).
+// Returns true when the legal mass is <= 0 (uniform python-float fallback).
+template <int KIND>
+__device__ __forceinline__ bool warp_priors(const void* policy, size_t row_stride, int g, const int16_t* acts, int n,
+                                            float* pri /* smem [128] */)
+{
+    const int lane = lane_id();
+    if (KIND == 0) {
+        const float* p = reinterpret_cast<const float*>(policy) + (size_t)g * row_stride;
+        for (int i = lane; i < n; i += 32) pri[i] = p[acts[i]];
+        warp_sync();
+        float sum = 0.0f;
+        if (lane == 0)
+            for (int i = 0; i < n; ++i) sum = __fadd_rn(sum, pri[i]);   // python sum(): sequential float32
+        sum = warp_bcast_f(sum, 0);
+        if (!(sum > 0.0f)) return true;
+        for (int i = lane; i < n; i += 32) pri[i] = __fdiv_rn(pri[i], sum);
+        warp_sync();
+        return false;
+    } else {
+        float m = -INFINITY;
+        for (int i = lane; i < n; i += 32) {
+            float l = KIND == 1 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(policy)[(size_t)g * row_stride + acts[i]])
+                                : reinterpret_cast<const float*>(policy)[(size_t)g * row_stride + acts[i]];
+            pri[i] = l;
+            m = fmaxf(m, l);
+        }
+        m = warp_max_f(m);
+        float s = 0.0f;
+        for (int i = lane; i < n; i += 32) {
+            float e = __expf(pri[i] - m);
+            pri[i] = e;
+            s += e;
+        }
+        s = warp_sum_f(s);
+        const float inv = 1.0f / s;
+        for (int i = lane; i < n; i += 32) pri[i] *= inv;
+        warp_sync();
+        return false;
+    }
+}
+
+// create the children of `node` (mcts.py:60-64); returns false on pool overflow
+__device__ __forceinline__ bool warp_expand(const MctsState& M, int node, const int16_t* acts, int n, const float* pri,
+                                            bool uniform, int root_game, const double* noise, bool have_noise)
+{
+    const int lane = lane_id();
+    int base = 0;
+    if (lane == 0) base = atomicAdd(M.alloc, n);
+    base = warp_bcast(base, 0);
+    if ((long long)base + n > M.cap_nodes) {
+        if (lane == 0) atomicOr(M.error, 1);
+        return false;
+    }
+    for (int i = lane; i < n; i += 32) {
+        float p32 = uniform ? 0.0f : pri[i];
+        if (have_noise) {
+            // 0.75 * P + 0.25 * noise[i] -> np.float64 (mcts.py:117-121)
+            double mixed;
+            if (uniform) mixed = __dadd_rn(__dmul_rn(0.75, __ddiv_rn(1.0, (double)n)), __dmul_rn(0.25, noise[i]));
+            else mixed = __dadd_rn((double)__fmul_rn(0.75f, p32), __dmul_rn(0.25, noise[i]));
+            M.rootP64[(size_t)root_game * kMaxMoves + i] = mixed;
+        }
+        M.hot[base + i] = NodeHot{0.0, 0, p32};
+        M.link[base + i] = NodeLink{-1, node, acts[i], 0, 0, 0};
+    }
+    if (lane == 0) {
+        NodeLink l = M.link[node];
+        l.child0 = base;
+        l.nchild = (uint8_t)n;
+        l.flags = have_noise ? 2 : (uniform ? 1 : 0);
+        M.link[node] = l;
+    }
+    return true;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(kSelWarps * 32)
+mcts_root_expand_kernel(MctsState M, const void* policy, size_t row_stride, const double* noise_in, int add_noise,
+                        uint64_t seed, double alpha)
+{
+    __shared__ float pri[kSelWarps][kMaxMoves];
+    __shared__ double nz[kSelWarps][kMaxMoves];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.x * kSelWarps + warp;
+    if (g >= M.n_games) return;
+    if (M.leaf_state[g] != kLeafEval) return;
+    const int n = M.leaf_n[g];
+    const int16_t* acts = M.leaf_actions + (size_t)g * kMaxMoves;
+    bool uniform = warp_priors<KIND>(policy, row_stride, g, acts, n, pri[warp]);
+    if (add_noise) {
+        if (noise_in) {
+            for (int i = lane; i < n; i += 32) nz[warp][i] = noise_in[(size_t)g * kMaxMoves + i];
+        } else {
+            // np.random.dirichlet([alpha]*n): normalised gamma(alpha) draws (statistical parity only)
+            double s = 0.0;
+            for (int i = lane; i < n; i += 32) {
+                double x = gamma_sample(alpha, seed, (uint64_t)g, (uint64_t)i);
+                nz[warp][i] = x;
+                s += x;
+            }
+            s = warp_sum_d(s);
+            for (int i = lane; i < n; i += 32) nz[warp][i] = nz[warp][i] / s;
+        }
+        warp_sync();
+    }
+    warp_expand(M, g, acts, n, pri[warp], uniform, g, nz[warp], add_noise != 0);
+    if (lane == 0) atomicAdd((unsigned long long*)&M.stats[3], 1ull);
+}
+
+// ---- select: descend to a leaf, replay the moves, test termination, emit evaluator inputs ----
+__global__ void __launch_bounds__(kSelWarps * 32)
+mcts_select_kernel(MctsState M, double c_puct, float* planes_f32, __nv_bfloat16* x_nhwc, int8_t* boards_out,
+                   int8_t* sides_out)
+{
+    __shared__ SelectSmem sm;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.x * kSelWarps + warp;
+    if (g >= M.n_games) return;
+    // a game without a tree (finished, or no legal move at the root) idles
+    if (M.link[g].child0 < 0) {
+        if (lane == 0) M.leaf_state[g] = kLeafIdle;
+        return;
+    }
+    int8_t* b = sm.board[warp];
+    int8_t* ring = sm.ring[warp];
+    GameMeta gm;
+    warp_load_game(M, g, b, ring, gm);
+
+    int node = g, depth = 0;
+    NodeLink ln = M.link[node];
+    const float c32 = (float)c_puct;
+    while (ln.child0 >= 0) {
+        const int nch = ln.nchild, c0 = ln.child0, mode = ln.flags;
+        const double sqrt_parent = sqrt((double)M.hot[node].N);   // math.sqrt(self.visit_count)
+        const float sp32 = (float)sqrt_parent;
+        double best = -INFINITY;
+        int best_i = 0x7fffffff;
+        for (int i = lane; i < nch; i += 32) {
+            const NodeHot h = M.hot[c0 + i];
+            const double q = h.N == 0 ? 0.0 : __ddiv_rn(h.W, (double)h.N);
+            double score;
+            if (mode == 0) {
+                float u = __fmul_rn(c32, h.P);
+                u = __fmul_rn(u, sp32);
+                u = __fdiv_rn(u, (float)(1 + h.N));
+                score = (double)__fadd_rn((float)q, u);
+            } else {
+                const double p = mode == 2 ? M.rootP64[(size_t)g * kMaxMoves + i] : __ddiv_rn(1.0, (double)nch);
+                double u = __dmul_rn(c_puct, p);
+                u = __dmul_rn(u, sqrt_parent);
+                u = __ddiv_rn(u, (double)(1 + h.N));
+                score = __dadd_rn(q, u);
+            }
+            if (score > best) {   // strict '>' : first maximum wins (i ascends within a lane)
+                best = score;
+                best_i = i;
+            }
+        }
+        best_i = warp_argmax_first(best, best_i);
+        if (best_i == 0x7fffffff) best_i = 0;   // all-NaN guard; cannot happen with finite inputs
+        node = c0 + best_i;
+        ln = M.link[node];
+        warp_make_move(b, ring, gm, ln.action);
+        ++depth;
+    }
+
+    WarpScratch& S = sm.ws[warp];
+    MovegenResult r = warp_movegen(b, gm.side, S);
+    if (r.overflow && lane == 0) atomicOr(M.error, 2);
+    const int w = warp_game_over(b, ring, gm, r);
+    if (lane == 0) {
+        atomicAdd((unsigned long long*)&M.stats[0], 1ull);
+        atomicMax((unsigned long long*)&M.stats[2], (unsigned long long)depth);
+    }
+    if (w != 2) {
+        // terminal leaf: value needs no evaluator; back up now (mcts.py:137-140,153)
+        if (lane == 0) {
+            M.leaf_state[g] = kLeafTerminal;
+            M.leaf_node[g] = node;
+            backup_path(M, node, w == 0 ? 0.0 : 1.0);
+            atomicAdd((unsigned long long*)&M.stats[1], 1ull);
+        }
+        return;
+    }
+    reinterpret_cast<uint2*>(M.leaf_actions + (size_t)g * kMaxMoves)[lane] = reinterpret_cast<const uint2*>(S.actions)[lane];
+    if (lane == 0) {
+        M.leaf_state[g] = kLeafEval;
+        M.leaf_node[g] = node;
+        M.leaf_n[g] = min(r.n_legal, kMaxMoves);
+    }
+    warp_emit_eval_inputs(b, gm.side, g, planes_f32, x_nhwc, boards_out, sides_out);
+}
+
+// ---- expand + backup ---------------------------------------------------------------------
+template <int KIND>
+__global__ void __launch_bounds__(kSelWarps * 32)
+mcts_expand_backup_kernel(MctsState M, const void* policy, size_t row_stride, const float* value)
+{
+    __shared__ float pri[kSelWarps][kMaxMoves];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.x * kSelWarps + warp;
+    if (g >= M.n_games) return;
+    if (M.leaf_state[g] != kLeafEval) return;
+    const int node = M.leaf_node[g];
+    const int n = M.leaf_n[g];
+    const int16_t* acts = M.leaf_actions + (size_t)g * kMaxMoves;
+    bool uniform = warp_priors<KIND>(policy, row_stride, g, acts, n, pri[warp]);
+    warp_expand(M, node, acts, n, pri[warp], uniform, g, nullptr, false);
+    warp_sync();
+    if (lane == 0) {
+        __threadfence();
+        backup_path(M, node, -(double)value[g]);   // value = -value (mcts.py:150)
+        atomicAdd((unsigned long long*)&M.stats[3], 1ull);
+    }
+}
+
+// ---- results ---------------------------------------------------------------------------------
+__global__ void mcts_root_visits_kernel(MctsState M, int16_t* actions, int32_t* visits, int32_t* n_out, double* w_out)
+{
+    const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (g >= M.n_games) return;
+    const NodeLink l = M.link[g];
+    const int n = l.child0 >= 0 ? l.nchild : 0;
+    for (int i = lane; i < kMaxMoves; i += 32) {
+        const bool ok = i < n;
+        actions[(size_t)g * kMaxMoves + i] = ok ? M.link[l.child0 + i].action : (int16_t)-1;
+        visits[(size_t)g * kMaxMoves + i] = ok ? M.hot[l.child0 + i].N : 0;
+        if (w_out) w_out[(size_t)g * kMaxMoves + i] = ok ? M.hot[l.child0 + i].W : 0.0;
+    }
+    if (lane == 0) n_out[g] = n;
+}
+
+__global__ void mcts_set_games_kernel(MctsState M, const int8_t* boards, const int8_t* sides, const int32_t* move_count,
+                                      const int32_t* no_capture, const int8_t* ring, const uint8_t* active)
+{
+    const int g = blockIdx.x;
+    if (g >= M.n_games) return;
+    for (int i = threadIdx.x; i < kBoardPad; i += blockDim.x)
+        M.board[(size_t)g * kBoardPad + i] = i < kSquares ? boards[(size_t)g * kSquares + i] : (int8_t)0;
+    for (int i = threadIdx.x; i < kRing * kBoardPad; i += blockDim.x) {
+        const int s = i / kBoardPad, c = i % kBoardPad;
+        M.ring[(size_t)g * kRing * kBoardPad + i] = (ring && c < kSquares) ? ring[((size_t)g * kRing + s) * kSquares + c] : (int8_t)0;
+    }
+    if (threadIdx.x == 0) {
+        M.meta[g * 4 + 0] = sides[g];
+        M.meta[g * 4 + 1] = move_count ? move_count[g] : 0;
+        M.meta[g * 4 + 2] = no_capture ? no_capture[g] : 0;
+        M.meta[g * 4 + 3] = active ? active[g] : 1;
+    }
+}
+
+}  // namespace xq
+
+using namespace xq;
+
+static MctsState* S_(xq_ctx* c) { return reinterpret_cast<MctsState*>(c->mcts); }
+
+extern "C" void xq_mcts_free_(xq_ctx* c)
+{
+    MctsState* M = S_(c);
+    if (!M) return;
+    void* ptrs[] = {M->board, M->ring, M->meta, M->hot, M->link, M->rootP64, M->alloc, M->error,
+                    M->leaf_node, M->leaf_state, M->leaf_actions, M->leaf_n, M->stats};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    delete M;
+    c->mcts = nullptr;
+}
+
+extern "C" int xq_mcts_create(xq_ctx* c, int max_games, long long node_capacity)
+{
+    if (!c || max_games <= 0) return xq_fail(c, XQ_ERR_ARG, "xq_mcts_create: bad arguments");
+    XQ_CUDA(c, cudaSetDevice(c->device));
+    xq_mcts_free_(c);
+    MctsState* M = new MctsState();
+    c->mcts = M;
+    M->max_games = max_games;
+    if (node_capacity <= 0) node_capacity = (long long)max_games * 801 * 64;
+    if (node_capacity > 0x7fffff00ll) node_capacity = 0x7fffff00ll;
+    M->cap_nodes = node_capacity;
+    const size_t G = (size_t)max_games;
+    XQ_CUDA(c, cudaMalloc(&M->board, G * kBoardPad));
+    XQ_CUDA(c, cudaMalloc(&M->ring, G * kRing * kBoardPad));
+    XQ_CUDA(c, cudaMalloc(&M->meta, G * 4 * sizeof(int32_t)));
+    XQ_CUDA(c, cudaMalloc(&M->hot, (size_t)node_capacity * sizeof(NodeHot)));
+    XQ_CUDA(c, cudaMalloc(&M->link, (size_t)node_capacity * sizeof(NodeLink)));
+    XQ_CUDA(c, cudaMalloc(&M->rootP64, G * kMaxMoves * sizeof(double)));
+    XQ_CUDA(c, cudaMalloc(&M->alloc, sizeof(int)));
+    XQ_CUDA(c, cudaMalloc(&M->error, sizeof(int)));
+    XQ_CUDA(c, cudaMalloc(&M->leaf_node, G * sizeof(int32_t)));
+    XQ_CUDA(c, cudaMalloc(&M->leaf_state, G * sizeof(int32_t)));
+    XQ_CUDA(c, cudaMalloc(&M->leaf_actions, G * kMaxMoves * sizeof(int16_t)));
+    XQ_CUDA(c, cudaMalloc(&M->leaf_n, G * sizeof(int32_t)));
+    XQ_CUDA(c, cudaMalloc(&M->stats, 4 * sizeof(int64_t)));
+    XQ_CUDA(c, cudaMemset(M->error, 0, sizeof(int)));
+    XQ_CUDA(c, cudaMemset(M->stats, 0, 4 * sizeof(int64_t)));
+    XQ_CUDA(c, cudaMemset(M->meta, 0, G * 4 * sizeof(int32_t)));
+    return XQ_OK;
+}
+
+#define NEED_MCTS(c)                                                                    \
+    MctsState* Mp = (c) ? S_(c) : nullptr;                                              \
+    if (!Mp) return xq_fail(c, XQ_ERR_STATE, "%s: call xq_mcts_create first", __func__); \
+    MctsState& M = *Mp;                                                                 \
+    cudaStream_t s = (cudaStream_t)stream;
+
+static inline int blocks_for(int n) { return (n + kSelWarps - 1) / kSelWarps; }
+
+extern "C" int xq_mcts_set_games(xq_ctx* c, int n_games, const int8_t* d_boards, const int8_t* d_sides,
+                                 const int32_t* d_move_count, const int32_t* d_no_capture, const int8_t* d_ring,
+                                 const uint8_t* d_active, void* stream)
+{
+    NEED_MCTS(c);
+    if (n_games < 0 || n_games > M.max_games || (n_games && (!d_boards || !d_sides)))
+        return xq_fail(c, XQ_ERR_ARG, "xq_mcts_set_games: bad arguments (n_games=%d, max %d)", n_games, M.max_games);
+    M.n_games = n_games;
+    if (n_games == 0) return XQ_OK;
+    mcts_set_games_kernel<<<n_games, 128, 0, s>>>(M, d_boards, d_sides, d_move_count, d_no_capture, d_ring, d_active);
+    c->launches += 1;
+    XQ_CUDA(c, cudaGetLastError());
+    return XQ_OK;
+}
+
+extern "C" int xq_mcts_root_begin(xq_ctx* c, float* d_planes, void* d_x_nhwc, int8_t* d_boards_out, int8_t* d_sides_out,
+                                  void* stream)
+{
+    NEED_MCTS(c);
+    if (M.n_games == 0) return XQ_OK;
+    if (d_boards_out && !d_sides_out) return xq_fail(c, XQ_ERR_ARG, "xq_mcts_root_begin: sides_out missing");
+    // a new search: the pool restarts after the reserved root slots (one tree per search, mcts.py:104)
+    int first = M.max_games;
+    XQ_CUDA(c, cudaMemcpyAsync(M.alloc, &first, sizeof(int), cudaMemcpyHostToDevice, s));
+    mcts_root_begin_kernel<<<blocks_for(M.n_games), kSelWarps * 32, 0, s>>>(M, d_planes, (__nv_bfloat16*)d_x_nhwc,
+                                                                            d_boards_out, d_sides_out);
+    c->launches += 1;
+    XQ_CUDA(c, cudaGetLastError());
+    return XQ_OK;
+}
+
+extern "C" int xq_mcts_root_expand(xq_ctx* c, const void* d_policy, int policy_kind, long long row_stride,
+                                   const double* d_noise, int add_noise, uint64_t noise_seed, double alpha, void* stream)
+{
+    NEED_MCTS(c);
+    if (M.n_games == 0) return XQ_OK;
+    if (!d_policy || policy_kind < 0 || policy_kind > 2) return xq_fail(c, XQ_ERR_ARG, "xq_mcts_root_expand: bad policy");
+    const int nb = blocks_for(M.n_games), nt = kSelWarps * 32;
+    if (policy_kind == 0)
+        mcts_root_expand_kernel<0><<<nb, nt, 0, s>>>(M, d_policy, (size_t)row_stride, d_noise, add_noise, noise_seed, alpha);
+    else if (policy_kind == 1)
+        mcts_root_expand_kernel<1><<<nb, nt, 0, s>>>(M, d_policy, (size_t)row_stride, d_noise, add_noise, noise_seed, alpha);
+    else
+        mcts_root_expand_kernel<2><<<nb, nt, 0, s>>>(M, d_policy, (size_t)row_stride, d_noise, add_noise, noise_seed, alpha);
+    c->launches += 1;
+    XQ_CUDA(c, cudaGetLastError());
+    return XQ_OK;
+}
+
+extern "C" int xq_mcts_select(xq_ctx* c, double c_puct, float* d_planes, void* d_x_nhwc, int8_t* d_boards_out,
+                              int8_t* d_sides_out, void* stream)
+{
+    NEED_MCTS(c);
+    if (M.n_games == 0) return XQ_OK;
+    if (d_boards_out && !d_sides_out) return xq_fail(c, XQ_ERR_ARG, "xq_mcts_select: sides_out missing");
+    {
+        XqTimer tm(c, s);
+        mcts_select_kernel<<<blocks_for(M.n_games), kSelWarps * 32, 0, s>>>(M, c_puct, d_planes, (__nv_bfloat16*)d_x_nhwc,
+                                                                            d_boards_out, d_sides_out);
+    }
+    c->launches += 1;
+    XQ_CUDA(c, cudaGetLastError());
+    return XQ_OK;
+}
+
+extern "C" int xq_mcts_expand_backup(xq_ctx* c, const void* d_policy, int policy_kind, long long row_stride,
+                                     const float* d_value, void* stream)
+{
+    NEED_MCTS(c);
+    if (M.n_games == 0) return XQ_OK;
+    if (!d_policy || !d_value || policy_kind < 0 || policy_kind > 2)
+        return xq_fail(c, XQ_ERR_ARG, "xq_mcts_expand_backup: bad arguments");
+    const int nb = blocks_for(M.n_games), nt = kSelWarps * 32;
+    if (policy_kind == 0)
+        mcts_expand_backup_kernel<0><<<nb, nt, 0, s>>>(M, d_policy, (size_t)row_stride, d_value);
+    else if (policy_kind == 1)
+        mcts_expand_backup_kernel<1><<<nb, nt, 0, s>>>(M, d_policy, (size_t)row_stride, d_value);
+    else
+        mcts_expand_backup_kernel<2><<<nb, nt, 0, s>>>(M, d_policy, (size_t)row_stride, d_value);
+    c->launches += 1;
+    XQ_CUDA(c, cudaGetLastError());
+    return XQ_OK;
+}
+
+extern "C" int xq_mcts_leaf_info(xq_ctx* c, int32_t* d_state, int32_t* d_n, int16_t* d_actions, void* stream)
+{
+    NEED_MCTS(c);
+    const size_t G = (size_t)M.n_games;
+    if (G == 0) return XQ_OK;
+    if (d_state) XQ_CUDA(c, cudaMemcpyAsync(d_state, M.leaf_state, G * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+    if (d_n) XQ_CUDA(c, cudaMemcpyAsync(d_n, M.leaf_n, G * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+    if (d_actions)
+        XQ_CUDA(c, cudaMemcpyAsync(d_actions, M.leaf_actions, G * kMaxMoves * sizeof(int16_t), cudaMemcpyDeviceToDevice, s));
+    return XQ_OK;
+}
+
+extern "C" int xq_mcts_root_visits(xq_ctx* c, int16_t* d_actions, int32_t* d_visits, int32_t* d_n, double* d_w,
+                                   void* stream)
+{
+    NEED_MCTS(c);
+    if (M.n_games == 0) return XQ_OK;
+    if (!d_actions || !d_visits || !d_n) return xq_fail(c, XQ_ERR_ARG, "xq_mcts_root_visits: bad arguments");
+    mcts_root_visits_kernel<<<blocks_for(M.n_games), kSelWarps * 32, 0, s>>>(M, d_actions, d_visits, d_n, d_w);
+    c->launches += 1;
+    XQ_CUDA(c, cudaGetLastError());
+    return XQ_OK;
+}
+
+// stats[0..3] = simulations, terminal-leaf simulations, max depth, evaluator calls consumed;
+// stats[4] = nodes allocated in the current search; stats[5] = error bits (1 pool overflow, 2 move overflow)
+extern "C" int xq_mcts_stats(xq_ctx* c, long long* h_stats6, int reset)
+{
+    MctsState* Mp = c ? S_(c) : nullptr;
+    if (!Mp) return xq_fail(c, XQ_ERR_STATE, "xq_mcts_stats: call xq_mcts_create first");
+    int64_t st[4];
+    int alloc = 0, err = 0;
+    XQ_CUDA(c, cudaMemcpy(st, Mp->stats, sizeof(st), cudaMemcpyDeviceToHost));
+    XQ_CUDA(c, cudaMemcpy(&alloc, Mp->alloc, sizeof(int), cudaMemcpyDeviceToHost));
+    XQ_CUDA(c, cudaMemcpy(&err, Mp->error, sizeof(int), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 4; ++i) h_stats6[i] = st[i];
+    h_stats6[4] = alloc - Mp->max_games;
+    h_stats6[5] = err;
+    if (reset) {
+        XQ_CUDA(c, cudaMemset(Mp->stats, 0, sizeof(st)));
+        XQ_CUDA(c, cudaMemset(Mp->error, 0, sizeof(int)));
+    }
+    return XQ_OK;
+}
+

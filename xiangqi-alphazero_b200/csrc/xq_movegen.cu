@@ -104,7 +104,7 @@ movegen_kernel(const int8_t* __restrict__ boards, const int8_t* __restrict__ sid
                     int v = b[sq] * side;
                     code[sq] = v > 0 ? (uint8_t)(v - 1) : (v < 0 ? (uint8_t)(6 - v) : (uint8_t)255);
                 }
-                __syncwarp();
+                warp_sync();
                 const float turn = side == 1 ? 1.0f : 0.0f;
                 float2* out = reinterpret_cast<float2*>(planes + gi * (15 * kSquares));
 #pragma unroll 3
@@ -122,7 +122,7 @@ movegen_kernel(const int8_t* __restrict__ boards, const int8_t* __restrict__ sid
                     __stcs(out + e2, v);
                 }
             }
-            __syncwarp();
+            warp_sync();
         }
         __syncthreads();
         // per-tile rows of counts and flags
@@ -189,7 +189,7 @@ __device__ __forceinline__ void warp_init_board(int8_t* b)
         }
         b[sq] = (int8_t)v;
     }
-    __syncwarp();
+    warp_sync();
 }
 
 __global__ void __launch_bounds__(kPlayWarps * 32)
@@ -217,7 +217,7 @@ playout_kernel(uint64_t seed, int n_games, int8_t* __restrict__ boards, int8_t* 
         const uint64_t u = rng_u64(seed, (uint64_t)g, (uint64_t)ply, 0);
         const int pick = (int)(u % (uint64_t)min(r.n_legal, kMaxMoves));
         const int action = S.actions[pick];
-        __syncwarp();
+        warp_sync();
         warp_make_move(b, ring, gm, action);
     }
     for (int p = ply + 1 + lane; p < XQ_MAX_PLIES; p += 32) sides[(size_t)g * XQ_MAX_PLIES + p] = 0;

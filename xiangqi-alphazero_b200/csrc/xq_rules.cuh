@@ -26,7 +26,93 @@ namespace xq {
 constexpr int kSquares = 90;
 constexpr int kMaxMoves = 128;    // output slots per position (max seen in play: 74)
 constexpr int kMaxPseudo = 192;   // pseudo-legal scratch (orthodox upper bound: 119)
-constexpr unsigned kFull = 0xffffffffu;
+// ---- warp collectives ------------------------------------------------------------------------
+// Every collective of this library goes through these NON-INLINED helpers.  Reason (measured on
+// B200 with CUDA 12.9): when the collectives were inlined after the divergent move-generation
+// switch, ptxas trusted the closing BSYNC.RECONVERGENT and emitted SHFL/VOTE with no WARPSYNC in
+// front; some lanes (the late arrivals: cannon walks, far switch arms) were still running apart
+// there -- __activemask() showed groups like {22},{28,30},{29},{31} -- and the prefix scan of
+// warp_movegen combined stale values (moves written at wrong offsets; caught by the MCTS golden
+// test).  A call boundary makes ptxas assume nothing about convergence, so each helper starts
+// with a real WARPSYNC.ALL.
+constexpr unsigned kFullMask = 0xffffffffu;
+static __device__ __noinline__ void warp_sync() { __syncwarp(); }
+static __device__ __noinline__ unsigned warp_ballot(bool p)
+{
+    __syncwarp();
+    return __ballot_sync(kFullMask, p);
+}
+static __device__ __noinline__ bool warp_any(bool p)
+{
+    __syncwarp();
+    return __any_sync(kFullMask, p) != 0;
+}
+static __device__ __noinline__ int warp_bcast(int v, int src)
+{
+    __syncwarp();
+    return __shfl_sync(kFullMask, v, src);
+}
+static __device__ __noinline__ float warp_bcast_f(float v, int src)
+{
+    __syncwarp();
+    return __shfl_sync(kFullMask, v, src);
+}
+static __device__ __noinline__ int warp_sum(int v)
+{
+    __syncwarp();
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
+    return v;
+}
+static __device__ __noinline__ float warp_sum_f(float v)
+{
+    __syncwarp();
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
+    return v;
+}
+static __device__ __noinline__ double warp_sum_d(double v)
+{
+    __syncwarp();
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
+    return v;
+}
+static __device__ __noinline__ float warp_max_f(float v)
+{
+    __syncwarp();
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(kFullMask, v, o));
+    return v;
+}
+// inclusive prefix sum over lanes; *total receives the warp total
+static __device__ __noinline__ int warp_incl_scan(int v, int* total)
+{
+    __syncwarp();
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(kFullMask, v, o);
+        if (lane >= o) v += t;
+    }
+    *total = __shfl_sync(kFullMask, v, 31);
+    return v;
+}
+// argmax with first-maximum tie-break (smaller index wins among equal scores)
+static __device__ __noinline__ int warp_argmax_first(double best, int best_i)
+{
+    __syncwarp();
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        const double ob = __shfl_xor_sync(kFullMask, best, o);
+        const int oi = __shfl_xor_sync(kFullMask, best_i, o);
+        if (ob > best || (ob == best && oi < best_i)) {
+            best = ob;
+            best_i = oi;
+        }
+    }
+    return best_i;
+}
 
 struct alignas(16) WarpScratch {
     uint8_t pfrom[kMaxPseudo];
@@ -134,7 +220,7 @@ __device__ __forceinline__ KingInfo warp_find_kings(const int8_t* b, int side)
     bool hit = false;
     if (lane < 9) hit = b[palace_sq(side, lane)] == side;
     else if (lane < 18) hit = b[palace_sq(-side, lane - 9)] == -side;
-    unsigned m = __ballot_sync(kFull, hit);
+    unsigned m = warp_ballot(hit);
     unsigned own = m & 0x1ffu, foe = (m >> 9) & 0x1ffu;
     KingInfo k;
     k.own_sq = own ? palace_sq(side, __ffs(own) - 1) : -1;
@@ -279,17 +365,6 @@ __device__ __forceinline__ int gen_task(const int8_t* b, int side, int sq, int k
     return n;
 }
 
-__device__ __forceinline__ int warp_incl_scan(int v)
-{
-    const int lane = lane_id();
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        int t = __shfl_up_sync(kFull, v, o);
-        if (lane >= o) v += t;
-    }
-    return v;
-}
-
 struct MovegenResult {
     int n_legal;      // may exceed kMaxMoves only on unorthodox boards (then truncated + flagged)
     bool in_check;    // cy_is_in_check: own king attacked, or missing
@@ -314,11 +389,11 @@ __device__ __forceinline__ MovegenResult warp_movegen(const int8_t* b, int side,
     for (int k = 0; k < 3; ++k) {
         int sq = k * 32 + lane;
         bool o = sq < kSquares && is_own(b[sq], side);
-        unsigned m = __ballot_sync(kFull, o);
+        unsigned m = warp_ballot(o);
         if (o) S.own_sq[n_pieces + __popc(m & ((1u << lane) - 1u))] = (uint8_t)sq;
         n_pieces += __popc(m);
     }
-    __syncwarp();
+    warp_sync();
     for (int t0 = 0; t0 < 4 * n_pieces; t0 += 32) {
         const int t = t0 + lane;
         int sq = -1, kind = 0, d = t & 3;
@@ -328,8 +403,8 @@ __device__ __forceinline__ MovegenResult warp_movegen(const int8_t* b, int side,
             kind = p < 0 ? -p : p;
         }
         int cnt = (sq >= 0) ? gen_task<false>(b, side, sq, kind, d, nullptr) : 0;
-        int incl = warp_incl_scan(cnt);
-        int total = __shfl_sync(kFull, incl, 31);
+        int total;
+        int incl = warp_incl_scan(cnt, &total);
         int off = n_pseudo + incl - cnt;
         if (cnt > 0) {
             if (off + cnt <= kMaxPseudo) {
@@ -341,11 +416,11 @@ __device__ __forceinline__ MovegenResult warp_movegen(const int8_t* b, int side,
         }
         n_pseudo += total;
     }
-    res.overflow = __any_sync(kFull, res.overflow);
+    res.overflow = warp_any(res.overflow);
     if (n_pseudo > kMaxPseudo) n_pseudo = kMaxPseudo;
     // unused output slots read back as -1
     for (int i = lane; i < kMaxMoves; i += 32) S.actions[i] = -1;
-    __syncwarp();
+    warp_sync();
 
     // ---- phase B: legality + ordered compaction; item n_pseudo is the in-check probe -----
     int n_legal = 0;
@@ -363,17 +438,17 @@ __device__ __forceinline__ MovegenResult warp_movegen(const int8_t* b, int side,
             int k = res.kings.own_sq;
             chk = (k < 0) ? true : attacked_sq(b, k / 9, k % 9, -side, -1, -1, 0);
         }
-        unsigned m = __ballot_sync(kFull, ok);
+        unsigned m = warp_ballot(ok);
         if (ok) {
             int pos = n_legal + __popc(m & ((1u << lane) - 1u));
             if (pos < kMaxMoves) S.actions[pos] = (int16_t)(from * 90 + to);
         }
         n_legal += __popc(m);
     }
-    res.in_check = __any_sync(kFull, chk);
+    res.in_check = warp_any(chk);
     if (n_legal > kMaxMoves) res.overflow = true;
     res.n_legal = n_legal;
-    __syncwarp();
+    warp_sync();
     return res;
 }
 
@@ -405,9 +480,7 @@ __device__ __forceinline__ int warp_material_diff(const int8_t* b)
         int p = b[sq];
         s += p > 0 ? piece_value(p) : -piece_value(-p);
     }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(kFull, s, o);
-    return s;
+    return warp_sum(s);
 }
 
 // make_move (game.py:528-545) on a warp-owned state: ring[move_count % 12] <- board before the move.
@@ -417,9 +490,9 @@ __device__ __forceinline__ void warp_make_move(int8_t* b, int8_t* ring, GameMeta
     const int from = action / 90, to = action % 90;
     int8_t* slot = ring + (g.move_count % kRing) * kBoardPad;
     for (int i = lane; i < kSquares; i += 32) slot[i] = b[i];
-    __syncwarp();
+    warp_sync();
     int taken = b[to];
-    __syncwarp();
+    warp_sync();
     if (lane == 0) {
         b[to] = b[from];
         b[from] = 0;
@@ -427,7 +500,7 @@ __device__ __forceinline__ void warp_make_move(int8_t* b, int8_t* ring, GameMeta
     g.no_capture = taken != 0 ? 0 : g.no_capture + 1;
     g.side = -g.side;
     g.move_count += 1;
-    __syncwarp();
+    warp_sync();
 }
 
 // is_game_over (game.py:565-616).  Returns winner in {1,-1,0} or 2 when the game goes on.
@@ -461,7 +534,7 @@ __device__ __forceinline__ int warp_game_over(const int8_t* b, const int8_t* rin
             for (int w = 0; w < 22; ++w) same = same && (a[w] == c[w]);
             same = same && (b[88] == h[88]) && (b[89] == h[89]);
         }
-        if (__popc(__ballot_sync(kFull, same)) >= 3) return 0;
+        if (__popc(warp_ballot(same)) >= 3) return 0;
     }
     return 2;
 }

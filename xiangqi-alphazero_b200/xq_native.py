@@ -66,13 +66,25 @@ def lib():
     _sig(L, "xq_is_attacked_batch_host", i32, vp, vp, vp, vp, i32, vp)
     _sig(L, "xq_overflow_count", i32, vp, i32)
     _sig(L, "xq_random_playouts", i32, vp, u64, i32, vp, vp, vp, vp, vp)
+    i64, dbl = C.c_longlong, C.c_double
+    _sig(L, "xq_mcts_create", i32, vp, i32, i64)
+    _sig(L, "xq_mcts_set_games", i32, vp, i32, vp, vp, vp, vp, vp, vp, vp)
+    _sig(L, "xq_mcts_root_begin", i32, vp, vp, vp, vp, vp, vp)
+    _sig(L, "xq_mcts_root_expand", i32, vp, vp, i32, i64, vp, i32, u64, dbl, vp)
+    _sig(L, "xq_mcts_select", i32, vp, dbl, vp, vp, vp, vp, vp)
+    _sig(L, "xq_mcts_expand_backup", i32, vp, vp, i32, i64, vp, vp)
+    _sig(L, "xq_mcts_leaf_info", i32, vp, vp, vp, vp, vp)
+    _sig(L, "xq_mcts_root_visits", i32, vp, vp, vp, vp, vp, vp)
+    _sig(L, "xq_mcts_stats", i32, vp, C.POINTER(i64), i32)
     _lib = L
     return L
 
 
 EXPORTS = ["xq_create", "xq_destroy", "xq_last_error", "xq_version", "xq_launch_count", "xq_set_timing",
            "xq_last_kernel_ms", "xq_movegen_batch", "xq_movegen_batch_host", "xq_is_attacked_batch",
-           "xq_is_attacked_batch_host", "xq_overflow_count", "xq_random_playouts"]
+           "xq_is_attacked_batch_host", "xq_overflow_count", "xq_random_playouts",
+           "xq_mcts_create", "xq_mcts_set_games", "xq_mcts_root_begin", "xq_mcts_root_expand", "xq_mcts_select",
+           "xq_mcts_expand_backup", "xq_mcts_leaf_info", "xq_mcts_root_visits", "xq_mcts_stats"]
 
 
 def _np_ptr(a: np.ndarray):
@@ -203,3 +215,95 @@ class Engine:
             keep = sides != 0
             boards, sides = boards[keep].contiguous(), sides[keep].contiguous()
         return boards, sides, npos, win
+
+
+POLICY_PROBS, POLICY_LOGITS_BF16, POLICY_LOGITS_F32 = 0, 1, 2
+
+
+class MctsBatch:
+    """Lockstep search of G games on the device (xq_mcts_*).  The evaluator is a callable
+    between `select` and `expand_backup`; `search()` runs the whole loop of mcts.py:94-155."""
+
+    def __init__(self, eng: Engine, max_games: int, node_capacity: int = 0):
+        self.e = eng
+        self.t = eng.torch
+        self.G = int(max_games)
+        eng._check(eng.L.xq_mcts_create(eng.h, self.G, int(node_capacity)))
+        t, dev = self.t, eng.dev
+        self.planes = t.zeros((self.G, 15, 10, 9), dtype=t.float32, device=dev)
+        self.boards = t.zeros((self.G, 90), dtype=t.int8, device=dev)
+        self.sides = t.zeros((self.G,), dtype=t.int8, device=dev)
+        self.n = 0
+
+    def set_games(self, boards, sides, move_count=None, no_capture=None, ring=None, active=None):
+        t, dev = self.t, self.e.dev
+
+        def d(a, dt):
+            if a is None:
+                return None
+            if not t.is_tensor(a):
+                a = t.from_numpy(np.ascontiguousarray(a))
+            return a.to(device=dev, dtype=dt).contiguous()
+        b = d(boards, t.int8).reshape(-1, 90)
+        self.n = b.shape[0]
+        keep = [b, d(sides, t.int8), d(move_count, t.int32), d(no_capture, t.int32), d(ring, t.int8), d(active, t.uint8)]
+        ptr = [None if x is None else x.data_ptr() for x in keep]
+        self.e._check(self.e.L.xq_mcts_set_games(self.e.h, self.n, *ptr, self.e._stream()))
+        self._keep = keep
+
+    def root_begin(self, want_planes=True, x_nhwc=None):
+        self.e._check(self.e.L.xq_mcts_root_begin(self.e.h, self.planes.data_ptr() if want_planes else None,
+                                                  None if x_nhwc is None else x_nhwc.data_ptr(),
+                                                  self.boards.data_ptr(), self.sides.data_ptr(), self.e._stream()))
+
+    def root_expand(self, policy, kind=POLICY_PROBS, noise=None, add_noise=False, seed=0, alpha=0.3):
+        self.e._check(self.e.L.xq_mcts_root_expand(self.e.h, policy.data_ptr(), kind, policy.stride(0),
+                                                   None if noise is None else noise.data_ptr(), int(add_noise),
+                                                   C.c_uint64(seed), float(alpha), self.e._stream()))
+
+    def select(self, c_puct=1.5, want_planes=True, x_nhwc=None):
+        self.e._check(self.e.L.xq_mcts_select(self.e.h, float(c_puct), self.planes.data_ptr() if want_planes else None,
+                                              None if x_nhwc is None else x_nhwc.data_ptr(),
+                                              self.boards.data_ptr(), self.sides.data_ptr(), self.e._stream()))
+
+    def expand_backup(self, policy, value, kind=POLICY_PROBS):
+        self.e._check(self.e.L.xq_mcts_expand_backup(self.e.h, policy.data_ptr(), kind, policy.stride(0),
+                                                     value.data_ptr(), self.e._stream()))
+
+    def leaf_info(self):
+        t, dev = self.t, self.e.dev
+        st = t.empty((self.n,), dtype=t.int32, device=dev)
+        n = t.empty((self.n,), dtype=t.int32, device=dev)
+        acts = t.empty((self.n, MAX_MOVES), dtype=t.int16, device=dev)
+        self.e._check(self.e.L.xq_mcts_leaf_info(self.e.h, st.data_ptr(), n.data_ptr(), acts.data_ptr(), self.e._stream()))
+        return st, n, acts
+
+    def root_visits(self, want_w=False):
+        t, dev = self.t, self.e.dev
+        acts = t.empty((self.n, MAX_MOVES), dtype=t.int16, device=dev)
+        vis = t.empty((self.n, MAX_MOVES), dtype=t.int32, device=dev)
+        n = t.empty((self.n,), dtype=t.int32, device=dev)
+        w = t.empty((self.n, MAX_MOVES), dtype=t.float64, device=dev) if want_w else None
+        self.e._check(self.e.L.xq_mcts_root_visits(self.e.h, acts.data_ptr(), vis.data_ptr(), n.data_ptr(),
+                                                   None if w is None else w.data_ptr(), self.e._stream()))
+        return acts, vis, n, w
+
+    def stats(self, reset=False):
+        buf = (C.c_longlong * 6)()
+        self.e._check(self.e.L.xq_mcts_stats(self.e.h, buf, int(reset)))
+        return dict(sims=buf[0], terminal_sims=buf[1], max_depth=buf[2], evals=buf[3], nodes=buf[4], error=buf[5])
+
+    def search(self, evaluator, num_sims, c_puct=1.5, noise=None, add_noise=False, seed=0, kind=POLICY_PROBS):
+        """evaluator(self) -> (policy tensor [n, >=8100], value float32 tensor [n]) for the current
+        planes/boards/sides.  Returns (actions, visits, n) device tensors."""
+        self.root_begin()
+        policy, _ = evaluator(self)
+        self.root_expand(policy, kind, noise=noise, add_noise=add_noise, seed=seed)
+        for _ in range(num_sims):
+            self.select(c_puct)
+            policy, value = evaluator(self)
+            self.expand_backup(policy, value, kind)
+        st = self.stats()
+        if st["error"]:
+            raise XqError(f"MCTS device error bits {st['error']} (1 = node pool overflow, 2 = >128 legal moves)")
+        return self.root_visits()[:3]
