@@ -122,18 +122,19 @@ int xq_mcts_set_games(xq_ctx* ctx, int n_games, const int8_t* d_boards, const in
                       const uint8_t* d_active, void* stream);
 
 /* Evaluator inputs of the roots / of the current leaves; every output pointer is optional:
- *   d_planes [G][15][10][9] float32 (get_state_for_nn), d_x_nhwc = conv input tile of xq_net_*
- *   (bf16 [G*110+..][16]), d_boards_out [G][90] + d_sides_out [G]. */
-int xq_mcts_root_begin(xq_ctx* ctx, float* d_planes, void* d_x_nhwc, int8_t* d_boards_out, int8_t* d_sides_out,
-                       void* stream);
+ *   d_planes [G][15][10][9] float32 (get_state_for_nn); d_x_planes = input planes of xq_net_gemm
+ *   (bf16 [2][x_rows][8], cell (r,c) of game g at plane row x_row0 + g*110 + (r+1)*10 + c, halo rows
+ *   are never written and must be zero); d_boards_out [G][90] + d_sides_out [G]. */
+int xq_mcts_root_begin(xq_ctx* ctx, float* d_planes, void* d_x_planes, long long x_rows, long long x_row0,
+                       int8_t* d_boards_out, int8_t* d_sides_out, void* stream);
 /* mcts.py:110-123: mask + normalise the root policy, optional Dirichlet mixing 0.75 P + 0.25 eta.
  * d_noise [G][128] float64 injects eta (tests); NULL draws Dirichlet(alpha) on the device. */
 int xq_mcts_root_expand(xq_ctx* ctx, const void* d_policy, int policy_kind, long long row_stride,
                         const double* d_noise, int add_noise, uint64_t noise_seed, double alpha, void* stream);
 /* mcts.py:126-140: descend by PUCT, replay the moves, is_game_over at the leaf; terminal leaves are
  * backed up here, the others wait for expand_backup. */
-int xq_mcts_select(xq_ctx* ctx, double c_puct, float* d_planes, void* d_x_nhwc, int8_t* d_boards_out,
-                   int8_t* d_sides_out, void* stream);
+int xq_mcts_select(xq_ctx* ctx, double c_puct, float* d_planes, void* d_x_planes, long long x_rows, long long x_row0,
+                   int8_t* d_boards_out, int8_t* d_sides_out, void* stream);
 /* mcts.py:142-153: expand the leaf with masked priors, back up -value. d_value [G] float32. */
 int xq_mcts_expand_backup(xq_ctx* ctx, const void* d_policy, int policy_kind, long long row_stride,
                           const float* d_value, void* stream);
@@ -147,6 +148,49 @@ int xq_mcts_root_visits(xq_ctx* ctx, int16_t* d_actions, int32_t* d_visits, int3
 /* h_stats6: simulations, terminal-leaf simulations, max depth, evaluations consumed, nodes in the
  * current search, error bits (1 node pool overflow, 2 >128 legal moves). Synchronises. */
 int xq_mcts_stats(xq_ctx* ctx, long long* h_stats6, int reset);
+
+/* ---- K3: ResNet policy-value forward (bf16 tcgen05/TMA implicit GEMM) ---------------------------
+ * Replaces XiangqiNet.forward on the inference path (model.py:87-124): every conv / linear layer
+ * is one xq_net_gemm launch over "channel-chunk plane" tensors (layout: csrc/xq_net.cu), BatchNorm
+ * folded into weights + bias by the host (eval mode).  The host builds the descriptors once
+ * (xiangqi-alphazero_b200/model.py, class B200Net) and replays them with xq_net_run.
+ *
+ *   mode 0  3x3 conv: out = act(conv(a) + bias [+ residual]); a/out/residual are plane tensors
+ *           [chunk][rows][8] bf16 with logical row m at plane row row0+m (row0 >= 16)
+ *   mode 1  1x1 policy/value head conv (nt = 48: 32 policy + 4 value channels + padding):
+ *           out = FC input planes [360][out_rows][8] bf16, out2 = value features [B][90][4] fp32
+ *   mode 2  dense layer: a = planes [K/8][a_rows][8], out = row-major bf16 [B][out_stride] logits
+ * w = weight image [n_tile][tap][k_block][chunk][nt][8] bf16, bias fp32 [n_tiles*nt].
+ */
+typedef struct xq_gemm_desc {
+    int32_t mode;
+    int32_t m_tiles;      /* 128-row output tiles */
+    int32_t n_tiles;      /* tiles of nt output channels */
+    int32_t nt;           /* 128, or 48 for the head conv */
+    int32_t kchunks;      /* K / 8 */
+    int32_t kch_iter;     /* chunks per pipeline stage: 8, or 2 for the 15(+1)-plane input conv */
+    int32_t relu;
+    int32_t n_boards;
+    int64_t a_rows, a_row0;
+    int64_t out_rows, out_row0;
+    int64_t out_stride;
+    const void* a;
+    const void* w;
+    const float* bias;
+    const void* residual; /* mode 0 only, may be NULL */
+    void* out;
+    void* out2;           /* mode 1 only */
+} xq_gemm_desc;
+
+int xq_net_gemm(xq_ctx* ctx, const xq_gemm_desc* desc, void* stream);
+/* value head tail, model.py:79-83: tanh(w2 . relu(W1 f + b1) + b2); d_feats [B][90][4] fp32,
+ * d_w1t [360][128] fp32 with k = pos*4 + ch. */
+int xq_net_value_head(xq_ctx* ctx, const float* d_feats, const float* d_w1t, const float* d_b1,
+                      const float* d_w2, float b2, float* d_value, int B, void* stream);
+/* all layers of one forward + the value head, one call */
+int xq_net_run(xq_ctx* ctx, const xq_gemm_desc* layers, int n_layers, const float* d_vfeats,
+               const float* d_w1t, const float* d_b1, const float* d_w2, float b2, float* d_value, int B,
+               void* stream);
 
 #ifdef __cplusplus
 }

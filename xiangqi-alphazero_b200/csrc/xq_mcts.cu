@@ -88,7 +88,8 @@ __device__ __forceinline__ void warp_load_game(const MctsState& M, int g, int8_t
 // get_state_for_nn planes (game.py:618-640) and/or the conv input tile of the network kernels
 // (bf16, 16 channels per cell, rows padded as [board][11][10] with zero halo cells never written).
 __device__ __forceinline__ void warp_emit_eval_inputs(const int8_t* b, int side, int g, float* planes_f32,
-                                                      __nv_bfloat16* x_nhwc, int8_t* boards_out, int8_t* sides_out)
+                                                      __nv_bfloat16* x_planes, long long x_rows, long long x_row0,
+                                                      int8_t* boards_out, int8_t* sides_out)
 {
     const int lane = lane_id();
     if (boards_out) {
@@ -112,19 +113,21 @@ __device__ __forceinline__ void warp_emit_eval_inputs(const int8_t* b, int side,
             out[e2] = v;
         }
     }
-    if (x_nhwc) {
-        // cell (r,c) of board g lives at row g*110 + (r+1)*10 + c, 16 bf16 channels = 32 B
+    if (x_planes) {
+        // network input planes [2 chunks][x_rows][8 ch] bf16: channels 0-7 in chunk 0, 8-14 (+pad) in chunk 1
         const uint32_t one = 0x3f80u;   // bf16 1.0
         for (int sq = lane; sq < kSquares; sq += 32) {
             int v = b[sq] * side;
             int ch = v > 0 ? v - 1 : (v < 0 ? 6 - v : -1);
             uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             if (ch >= 0) w[ch >> 1] = one << ((ch & 1) * 16);
-            if (side == 1) w[7] |= one;   // channel 14 (low half of word 7); channel 15 is padding
+            if (side == 1) w[7] |= one;   // channel 14 = low half of word 7; channel 15 is padding
             const int r = sq / 9, c = sq - r * 9;
-            uint4* dst = reinterpret_cast<uint4*>(x_nhwc + ((size_t)g * 110 + (r + 1) * 10 + c) * 16);
-            dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
-            dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+            const size_t row = (size_t)(x_row0 + (long long)g * 110 + (r + 1) * 10 + c);
+            uint4* p0 = reinterpret_cast<uint4*>(x_planes + row * 8);
+            uint4* p1 = reinterpret_cast<uint4*>(x_planes + ((size_t)x_rows + row) * 8);
+            *p0 = make_uint4(w[0], w[1], w[2], w[3]);
+            *p1 = make_uint4(w[4], w[5], w[6], w[7]);
         }
     }
 }
@@ -147,7 +150,8 @@ __device__ __forceinline__ int backup_path(const MctsState& M, int node, double 
 
 // ---- root preparation: movegen on every root, emit evaluator inputs -------------------------
 __global__ void __launch_bounds__(kSelWarps * 32)
-mcts_root_begin_kernel(MctsState M, float* planes_f32, __nv_bfloat16* x_nhwc, int8_t* boards_out, int8_t* sides_out)
+mcts_root_begin_kernel(MctsState M, float* planes_f32, __nv_bfloat16* x_planes, long long x_rows, long long x_row0,
+                       int8_t* boards_out, int8_t* sides_out)
 {
     __shared__ SelectSmem sm;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -170,7 +174,7 @@ mcts_root_begin_kernel(MctsState M, float* planes_f32, __nv_bfloat16* x_nhwc, in
         M.hot[g] = NodeHot{0.0, 0, 0.0f};
         M.link[g] = NodeLink{-1, -1, (int16_t)-1, 0, 0, 0};
     }
-    warp_emit_eval_inputs(b, gm.side, g, planes_f32, x_nhwc, boards_out, sides_out);
+    warp_emit_eval_inputs(b, gm.side, g, planes_f32, x_planes, x_rows, x_row0, boards_out, sides_out);
 }
 
 // Marsaglia-Tsang gamma(alpha<1) via gamma(alpha+1) * U^(1/alpha); counter-based uniforms
@@ -308,8 +312,8 @@ mcts_root_expand_kernel(MctsState M, const void* policy, size_t row_stride, cons
 
 // ---- select: descend to a leaf, replay the moves, test termination, emit evaluator inputs ----
 __global__ void __launch_bounds__(kSelWarps * 32)
-mcts_select_kernel(MctsState M, double c_puct, float* planes_f32, __nv_bfloat16* x_nhwc, int8_t* boards_out,
-                   int8_t* sides_out)
+mcts_select_kernel(MctsState M, double c_puct, float* planes_f32, __nv_bfloat16* x_planes, long long x_rows,
+                   long long x_row0, int8_t* boards_out, int8_t* sides_out)
 {
     __shared__ SelectSmem sm;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -387,7 +391,7 @@ mcts_select_kernel(MctsState M, double c_puct, float* planes_f32, __nv_bfloat16*
         M.leaf_node[g] = node;
         M.leaf_n[g] = min(r.n_legal, kMaxMoves);
     }
-    warp_emit_eval_inputs(b, gm.side, g, planes_f32, x_nhwc, boards_out, sides_out);
+    warp_emit_eval_inputs(b, gm.side, g, planes_f32, x_planes, x_rows, x_row0, boards_out, sides_out);
 }
 
 // ---- expand + backup ---------------------------------------------------------------------
@@ -521,8 +525,8 @@ extern "C" int xq_mcts_set_games(xq_ctx* c, int n_games, const int8_t* d_boards,
     return XQ_OK;
 }
 
-extern "C" int xq_mcts_root_begin(xq_ctx* c, float* d_planes, void* d_x_nhwc, int8_t* d_boards_out, int8_t* d_sides_out,
-                                  void* stream)
+extern "C" int xq_mcts_root_begin(xq_ctx* c, float* d_planes, void* d_x_planes, long long x_rows, long long x_row0,
+                                  int8_t* d_boards_out, int8_t* d_sides_out, void* stream)
 {
     NEED_MCTS(c);
     if (M.n_games == 0) return XQ_OK;
@@ -530,7 +534,7 @@ extern "C" int xq_mcts_root_begin(xq_ctx* c, float* d_planes, void* d_x_nhwc, in
     // a new search: the pool restarts after the reserved root slots (one tree per search, mcts.py:104)
     int first = M.max_games;
     XQ_CUDA(c, cudaMemcpyAsync(M.alloc, &first, sizeof(int), cudaMemcpyHostToDevice, s));
-    mcts_root_begin_kernel<<<blocks_for(M.n_games), kSelWarps * 32, 0, s>>>(M, d_planes, (__nv_bfloat16*)d_x_nhwc,
+    mcts_root_begin_kernel<<<blocks_for(M.n_games), kSelWarps * 32, 0, s>>>(M, d_planes, (__nv_bfloat16*)d_x_planes, x_rows, x_row0,
                                                                             d_boards_out, d_sides_out);
     c->launches += 1;
     XQ_CUDA(c, cudaGetLastError());
@@ -555,16 +559,16 @@ extern "C" int xq_mcts_root_expand(xq_ctx* c, const void* d_policy, int policy_k
     return XQ_OK;
 }
 
-extern "C" int xq_mcts_select(xq_ctx* c, double c_puct, float* d_planes, void* d_x_nhwc, int8_t* d_boards_out,
-                              int8_t* d_sides_out, void* stream)
+extern "C" int xq_mcts_select(xq_ctx* c, double c_puct, float* d_planes, void* d_x_planes, long long x_rows,
+                              long long x_row0, int8_t* d_boards_out, int8_t* d_sides_out, void* stream)
 {
     NEED_MCTS(c);
     if (M.n_games == 0) return XQ_OK;
     if (d_boards_out && !d_sides_out) return xq_fail(c, XQ_ERR_ARG, "xq_mcts_select: sides_out missing");
     {
         XqTimer tm(c, s);
-        mcts_select_kernel<<<blocks_for(M.n_games), kSelWarps * 32, 0, s>>>(M, c_puct, d_planes, (__nv_bfloat16*)d_x_nhwc,
-                                                                            d_boards_out, d_sides_out);
+        mcts_select_kernel<<<blocks_for(M.n_games), kSelWarps * 32, 0, s>>>(M, c_puct, d_planes, (__nv_bfloat16*)d_x_planes, x_rows,
+                                                                            x_row0, d_boards_out, d_sides_out);
     }
     c->launches += 1;
     XQ_CUDA(c, cudaGetLastError());

@@ -1,3 +1,509 @@
-// placeholder -- filled in by the K3 milestone
+// xq_net.cu -- K3: bf16 tcgen05/TMA implicit-GEMM kernels for the policy-value ResNet forward.
+//
+// Replaces the library calls of XiangqiNet.forward (training/model.py:87-107; conv3x3+BN+ReLU
+// stack, residual blocks :30-36, 1x1 heads, 2880->8100 policy FC, value MLP + tanh) on the
+// inference path of self-play (model.py:109-124 predict, inference_server.py:251-263).
+// BatchNorm is folded into the conv weights/bias on the host (eval mode, model.py:118).
+//
+// Data layout ("channel-chunk planes").  An activation tensor is stored as
+//     X[chunk = C/8][row][8 channels]   (bf16, 16 bytes per (chunk,row))
+// where `row` walks the boards with a zero halo: board b, cell (r,c) lives at row
+// b*110 + (r+1)*10 + c; row slots with c == 9 and the 10 slots before each board are zero
+// and double as left/right/top/bottom padding for every neighbour, so a 3x3 tap (dy,dx) is
+// the SAME matrix shifted by dy*10+dx rows.  Consequences:
+//   * the A operand of a 128-row output tile for all 9 taps is one block of 150 rows per chunk,
+//     fetched ONCE per tile with 1-D TMA bulk copies (2400 contiguous bytes per chunk);
+//   * in shared memory the block is the canonical no-swizzle K-major UMMA layout with
+//     SBO = 128 B, i.e. address = base + row*16 + chunk*LBO -- linear in the row, so each tap
+//     only moves the descriptor start address by shift*16 bytes; no im2col, no re-load;
+//   * the epilogue stores 16 B per (chunk,row) with consecutive lanes on consecutive rows:
+//     fully coalesced, and the next layer's TMA reads exactly what was written.
+// Weights are pre-arranged on the host as per-iteration shared-memory images
+// [n_tile][tap][k_block][chunk][n][8] so a pipeline stage is one contiguous bulk copy.
+//
+// Kernel: persistent, warp-specialised -- warp 0 lane 0 = TMA producer, warp 1 = TMEM owner +
+// single-thread tcgen05.mma issuer, warps 2-5 = epilogue (tcgen05.ld -> bias/residual/ReLU ->
+// bf16 -> global).  mbarrier rings: w_full/w_empty per stage, a_full/a_empty for the resident A
+// block, tmem_full/tmem_empty for the accumulator.  Two CTAs per SM (128 TMEM columns each)
+// let one CTA's epilogue overlap the other's MMAs.
 #include "xq_ctx.h"
+
+#include <cuda_bf16.h>
+
+namespace xq {
+
+struct GemmArgs {
+    int mode, m_tiles, n_tiles, kchunks, relu, n_boards;
+    long long a_rows, a_row0, out_rows, out_row0, out_stride;
+    const uint8_t* a;
+    const uint8_t* w;
+    const float* bias;
+    const uint8_t* residual;
+    uint8_t* out;
+    float* out2;
+};
+
+// ---- PTX wrappers -----------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish()
+{
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], bf16 x bf16 -> fp32, issued by ONE thread
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// mbarrier arrives when every tcgen05 op issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v)
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v)
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor, no swizzle, K-major (cute/arch/mma_sm100_desc.hpp layout):
+// [0,14) start>>4, [16,30) LBO>>4 (stride between the two 8-element K chunks of one MMA),
+// [32,46) SBO>>4 (stride between 8-row groups), [46,48) version = 1, [61,64) layout = 0.
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+{
+    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+// instruction descriptor kind::f16: D=f32 (bit 4), A=B=bf16 (bits 7,10), K-major A/B, N>>3 at 17, M>>4 at 24
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n)
+{
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b)
+{
+    __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&t);
+}
+
+constexpr int kGemmThreads = 192;
+constexpr int kARows = 150;                 // 128 + 11 halo rows either side
+constexpr int kAPlane = kARows * 16;        // bytes per chunk of the resident A block
+constexpr int kHalo = 11;                   // largest |dy*10+dx|
+
+template <int MODE, int NT, int KCH>
+struct GemmCfg {
+    static constexpr int kStages = (MODE == 2) ? 3 : 4;
+    static constexpr int kWStage = KCH * NT * 16;
+    static constexpr int kAStage = (MODE == 2) ? KCH * 128 * 16 : 0;
+    static constexpr int kStageBytes = kWStage + kAStage;
+    static constexpr int kTmemCols = NT > 64 ? 128 : 64;
+    static constexpr int kTaps = (MODE == 0) ? 9 : 1;
+    static int smem_bytes(int kchunks)
+    {
+        int a = (MODE == 2) ? 0 : kchunks * kAPlane;
+        a = (a + 127) & ~127;
+        return a + kStages * kStageBytes + 256;
+    }
+};
+
+// MODE 0: 3x3 conv (9 shifted taps), epilogue = bias (+residual) (+ReLU), halo rows zeroed, plane output
+// MODE 1: 1x1 head conv (policy 32 ch + value 4 ch, NT = 48), epilogue scatters into the FC's A planes / value features
+// MODE 2: dense FC (A streamed per k-block), epilogue = bias, row-major bf16 logits
+template <int MODE, int NT, int KCH>
+__global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const GemmArgs p)
+{
+    using Cfg = GemmCfg<MODE, NT, KCH>;
+    constexpr int S = Cfg::kStages;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int a_res = (MODE == 2) ? 0 : ((p.kchunks * kAPlane + 127) & ~127);
+    uint8_t* sA = smem;
+    uint8_t* sStage = smem + a_res;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + S * Cfg::kStageBytes);
+    uint64_t* w_full = bars;
+    uint64_t* w_empty = bars + S;
+    uint64_t* a_full = bars + 2 * S;
+    uint64_t* a_empty = bars + 2 * S + 1;
+    uint64_t* t_full = bars + 2 * S + 2;
+    uint64_t* t_empty = bars + 2 * S + 3;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kblocks = p.kchunks / KCH;
+    const int iters = Cfg::kTaps * kblocks;
+    const int total_tiles = p.m_tiles * p.n_tiles;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < S; ++i) {
+            mbar_init(&w_full[i], 1);
+            mbar_init(&w_empty[i], 1);
+        }
+        mbar_init(a_full, 1);
+        mbar_init(a_empty, 1);
+        mbar_init(t_full, 1);
+        mbar_init(t_empty, 4);      // one arrival per epilogue warp
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, Cfg::kTmemCols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer (one thread) =====================
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0, tile_ph = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+                const long long m0 = (long long)m_tile * 128;
+                if (MODE != 2) {
+                    mbar_wait(a_empty, tile_ph ^ 1);
+                    mbar_expect_tx(a_full, (uint32_t)(p.kchunks * kAPlane));
+                    for (int c = 0; c < p.kchunks; ++c)
+                        bulk_g2s(sA + c * kAPlane, p.a + ((size_t)c * p.a_rows + (size_t)(p.a_row0 + m0 - kHalo)) * 16,
+                                 kAPlane, a_full);
+                }
+                const uint8_t* wt = p.w + (size_t)n_tile * iters * Cfg::kWStage;
+                for (int it = 0; it < iters; ++it) {
+                    mbar_wait(&w_empty[s], ph ^ 1);
+                    uint8_t* st = sStage + s * Cfg::kStageBytes;
+                    mbar_expect_tx(&w_full[s], Cfg::kStageBytes);
+                    bulk_g2s(st, wt + (size_t)it * Cfg::kWStage, Cfg::kWStage, &w_full[s]);
+                    if (MODE == 2) {
+#pragma unroll
+                        for (int c = 0; c < KCH; ++c)
+                            bulk_g2s(st + Cfg::kWStage + c * 2048,
+                                     p.a + ((size_t)(it * KCH + c) * p.a_rows + (size_t)(p.a_row0 + m0)) * 16, 2048,
+                                     &w_full[s]);
+                    }
+                    if (++s == S) { s = 0; ph ^= 1; }
+                }
+                tile_ph ^= 1;
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one thread) =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(128, NT);
+            int s = 0;
+            uint32_t ph = 0, tile_ph = 0;
+            const uint32_t sA_addr = smem_u32(sA);
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                mbar_wait(t_empty, tile_ph ^ 1);     // epilogue has drained the accumulator
+                tc_fence_after();
+                if (MODE != 2) mbar_wait(a_full, tile_ph);
+                for (int it = 0; it < iters; ++it) {
+                    const int tap = (MODE == 0) ? it / kblocks : 0;
+                    const int kb = it - tap * kblocks;
+                    const int shift = (MODE == 0) ? ((tap / 3) - 1) * 10 + (tap % 3) - 1 : 0;
+                    mbar_wait(&w_full[s], ph);
+                    tc_fence_after();
+                    const uint32_t st_addr = smem_u32(sStage + s * Cfg::kStageBytes);
+#pragma unroll
+                    for (int j = 0; j < KCH / 2; ++j) {
+                        uint64_t adesc, bdesc;
+                        if (MODE == 2)
+                            adesc = make_desc(st_addr + Cfg::kWStage + (2 * j) * 2048, 2048, 128);
+                        else
+                            adesc = make_desc(sA_addr + (uint32_t)((kb * KCH + 2 * j) * kAPlane + (kHalo + shift) * 16),
+                                              kAPlane, 128);
+                        bdesc = make_desc(st_addr + (2 * j) * (NT * 16), NT * 16, 128);
+                        umma_bf16(tmem_base, adesc, bdesc, idesc, (it | j) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&w_empty[s]);        // frees the stage when these MMAs have read it
+                    if (++s == S) { s = 0; ph ^= 1; }
+                }
+                umma_commit(t_full);
+                if (MODE != 2) umma_commit(a_empty);
+                tile_ph ^= 1;
+            }
+        }
+    } else {
+        // ===================== epilogue (4 warps, one TMEM lane = one output row each) =====================
+        const int q = warp & 3;                      // TMEM lane quarter this warp may read
+        const int row = q * 32 + lane;
+        uint32_t tile_ph = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+            const long long m = (long long)m_tile * 128 + row;
+            mbar_wait(t_full, tile_ph);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+
+            if (MODE == 0) {
+                const int rr = (int)(m % 110);
+                const bool real = m < (long long)p.n_boards * 110 && rr >= 10 && (rr % 10) != 9;
+#pragma unroll 1
+                for (int c0 = 0; c0 < NT; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + c0, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const int n = n_tile * NT + c0 + g * 8;
+                        const size_t off = ((size_t)(n >> 3) * p.out_rows + (size_t)(p.out_row0 + m)) * 16;
+                        uint4 o = make_uint4(0, 0, 0, 0);
+                        if (real) {
+                            float f[8];
+                            const float4 b0 = *reinterpret_cast<const float4*>(p.bias + n);
+                            const float4 b1 = *reinterpret_cast<const float4*>(p.bias + n + 4);
+                            f[0] = __uint_as_float(v[g * 8 + 0]) + b0.x;
+                            f[1] = __uint_as_float(v[g * 8 + 1]) + b0.y;
+                            f[2] = __uint_as_float(v[g * 8 + 2]) + b0.z;
+                            f[3] = __uint_as_float(v[g * 8 + 3]) + b0.w;
+                            f[4] = __uint_as_float(v[g * 8 + 4]) + b1.x;
+                            f[5] = __uint_as_float(v[g * 8 + 5]) + b1.y;
+                            f[6] = __uint_as_float(v[g * 8 + 6]) + b1.z;
+                            f[7] = __uint_as_float(v[g * 8 + 7]) + b1.w;
+                            if (p.residual) {
+                                const uint4 r = *reinterpret_cast<const uint4*>(p.residual + off);
+                                const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    f[2 * k] += __uint_as_float(rw[k] << 16);
+                                    f[2 * k + 1] += __uint_as_float(rw[k] & 0xffff0000u);
+                                }
+                            }
+                            if (p.relu) {
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.0f);
+                            }
+                            o = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]),
+                                           pack_bf16(f[6], f[7]));
+                        }
+                        *reinterpret_cast<uint4*>(p.out + off) = o;
+                    }
+                }
+            } else if (MODE == 1) {
+                const int rr = (int)(m % 110);
+                const bool real = m < (long long)p.n_boards * 110 && rr >= 10 && (rr % 10) != 9;
+                const long long b = m / 110;
+                const int pos = (rr / 10 - 1) * 9 + (rr % 10);
+                uint32_t v[32], v2[16];
+                tmem_ld32(taddr, v);
+                tmem_ld16(taddr + 32, v2);
+                tmem_ld_wait();
+                if (real) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        float f[8];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) f[k] = fmaxf(__uint_as_float(v[g * 8 + k]) + p.bias[g * 8 + k], 0.0f);
+                        const uint4 o = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]),
+                                                   pack_bf16(f[6], f[7]));
+                        // FC A plane (pos*4 + g), row b
+                        *reinterpret_cast<uint4*>(p.out + ((size_t)(pos * 4 + g) * p.out_rows + (size_t)(p.out_row0 + b)) * 16) = o;
+                    }
+                    float4 vf;
+                    vf.x = fmaxf(__uint_as_float(v2[0]) + p.bias[32], 0.0f);
+                    vf.y = fmaxf(__uint_as_float(v2[1]) + p.bias[33], 0.0f);
+                    vf.z = fmaxf(__uint_as_float(v2[2]) + p.bias[34], 0.0f);
+                    vf.w = fmaxf(__uint_as_float(v2[3]) + p.bias[35], 0.0f);
+                    *reinterpret_cast<float4*>(p.out2 + ((size_t)b * 90 + pos) * 4) = vf;
+                }
+            } else {
+                const bool real = m < (long long)p.n_boards;
+#pragma unroll 1
+                for (int c0 = 0; c0 < NT; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + c0, v);
+                    tmem_ld_wait();
+                    if (real) {
+                        const int n = n_tile * NT + c0;
+                        uint4* dst = reinterpret_cast<uint4*>(p.out + ((size_t)m * p.out_stride + n) * 2);
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            const float4 b0 = *reinterpret_cast<const float4*>(p.bias + n + g * 8);
+                            const float4 b1 = *reinterpret_cast<const float4*>(p.bias + n + g * 8 + 4);
+                            dst[g] = make_uint4(pack_bf16(__uint_as_float(v[g * 8 + 0]) + b0.x, __uint_as_float(v[g * 8 + 1]) + b0.y),
+                                                pack_bf16(__uint_as_float(v[g * 8 + 2]) + b0.z, __uint_as_float(v[g * 8 + 3]) + b0.w),
+                                                pack_bf16(__uint_as_float(v[g * 8 + 4]) + b1.x, __uint_as_float(v[g * 8 + 5]) + b1.y),
+                                                pack_bf16(__uint_as_float(v[g * 8 + 6]) + b1.z, __uint_as_float(v[g * 8 + 7]) + b1.w));
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(t_empty);
+            tile_ph ^= 1;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+// ---- value head: Linear(360,128)+ReLU -> Linear(128,1) -> tanh (model.py:74-83) ----------------
+// feats [B][90][4] fp32 (already conv1x1+BN+ReLU), w1t [360][128] fp32 with k = pos*4+ch, 16 boards per CTA.
+constexpr int kVhBoards = 16;
+__global__ void __launch_bounds__(128) value_head_kernel(const float* __restrict__ feats, const float* __restrict__ w1t,
+                                                          const float* __restrict__ b1, const float* __restrict__ w2,
+                                                          float b2, float* __restrict__ value, int B)
+{
+    __shared__ float f[kVhBoards][360];
+    __shared__ float red[kVhBoards][4];
+    const int b0 = blockIdx.x * kVhBoards;
+    const int nb = min(kVhBoards, B - b0);
+    for (int i = threadIdx.x; i < kVhBoards * 360; i += 128) {
+        const int bb = i / 360;
+        f[bb][i - bb * 360] = bb < nb ? feats[(size_t)(b0 + bb) * 360 + (i - bb * 360)] : 0.0f;
+    }
+    __syncthreads();
+    const int j = threadIdx.x;
+    float acc[kVhBoards];
+#pragma unroll
+    for (int bb = 0; bb < kVhBoards; ++bb) acc[bb] = b1[j];
+    for (int k = 0; k < 360; ++k) {
+        const float w = w1t[k * 128 + j];
+#pragma unroll
+        for (int bb = 0; bb < kVhBoards; ++bb) acc[bb] = fmaf(w, f[bb][k], acc[bb]);
+    }
+    const float wj = w2[j];
+#pragma unroll
+    for (int bb = 0; bb < kVhBoards; ++bb) {
+        float t = fmaxf(acc[bb], 0.0f) * wj;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if ((threadIdx.x & 31) == 0) red[bb][threadIdx.x >> 5] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x < nb) {
+        const float s = red[threadIdx.x][0] + red[threadIdx.x][1] + red[threadIdx.x][2] + red[threadIdx.x][3] + b2;
+        value[b0 + threadIdx.x] = tanhf(s);
+    }
+}
+
+template <int MODE, int NT, int KCH>
+static int launch_gemm(xq_ctx* c, const GemmArgs& a, cudaStream_t s)
+{
+    using Cfg = GemmCfg<MODE, NT, KCH>;
+    const int smem = Cfg::smem_bytes(a.kchunks);
+    static bool configured = false;
+    static int per_sm = 1;
+    if (!configured) {
+        XQ_CUDA(c, cudaFuncSetAttribute(gemm_kernel<MODE, NT, KCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = true;
+    }
+    XQ_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gemm_kernel<MODE, NT, KCH>, kGemmThreads, smem));
+    if (per_sm < 1) return xq_fail(c, XQ_ERR_ARG, "gemm kernel does not fit: %d bytes of shared memory", smem);
+    // TMEM: 512 columns per SM; each CTA takes kTmemCols
+    const int tmem_cap = 512 / Cfg::kTmemCols;
+    if (per_sm > tmem_cap) per_sm = tmem_cap;
+    if (per_sm > 2) per_sm = 2;
+    const int total = a.m_tiles * a.n_tiles;
+    int grid = c->sm_count * per_sm;
+    if (grid > total) grid = total;
+    gemm_kernel<MODE, NT, KCH><<<grid, kGemmThreads, smem, s>>>(a);
+    c->launches += 1;
+    XQ_CUDA(c, cudaGetLastError());
+    return XQ_OK;
+}
+
+}  // namespace xq
+
+using namespace xq;
+
 extern "C" void xq_net_free_(xq_ctx*) {}
+
+extern "C" int xq_net_gemm(xq_ctx* c, const xq_gemm_desc* d, void* stream)
+{
+    if (!c || !d) return xq_fail(c, XQ_ERR_ARG, "xq_net_gemm: NULL argument");
+    if (!d->a || !d->w || !d->bias || !d->out || d->m_tiles <= 0 || d->n_tiles <= 0 || d->kchunks <= 0)
+        return xq_fail(c, XQ_ERR_ARG, "xq_net_gemm: bad descriptor");
+    GemmArgs a;
+    a.mode = d->mode;
+    a.m_tiles = d->m_tiles;
+    a.n_tiles = d->n_tiles;
+    a.kchunks = d->kchunks;
+    a.relu = d->relu;
+    a.n_boards = d->n_boards;
+    a.a_rows = d->a_rows;
+    a.a_row0 = d->a_row0;
+    a.out_rows = d->out_rows;
+    a.out_row0 = d->out_row0;
+    a.out_stride = d->out_stride;
+    a.a = (const uint8_t*)d->a;
+    a.w = (const uint8_t*)d->w;
+    a.bias = d->bias;
+    a.residual = (const uint8_t*)d->residual;
+    a.out = (uint8_t*)d->out;
+    a.out2 = (float*)d->out2;
+    cudaStream_t s = (cudaStream_t)stream;
+    XqTimer tm(c, s);
+    if (d->mode == 0 && d->nt == 128 && d->kch_iter == 8 && d->kchunks % 8 == 0) return launch_gemm<0, 128, 8>(c, a, s);
+    if (d->mode == 0 && d->nt == 128 && d->kch_iter == 2 && d->kchunks == 2) return launch_gemm<0, 128, 2>(c, a, s);
+    if (d->mode == 1 && d->nt == 48 && d->kch_iter == 8 && d->kchunks % 8 == 0 && d->out2) return launch_gemm<1, 48, 8>(c, a, s);
+    if (d->mode == 2 && d->nt == 128 && d->kch_iter == 8 && d->kchunks % 8 == 0) return launch_gemm<2, 128, 8>(c, a, s);
+    return xq_fail(c, XQ_ERR_ARG, "xq_net_gemm: unsupported (mode=%d nt=%d kch_iter=%d kchunks=%d)", d->mode, d->nt,
+                   d->kch_iter, d->kchunks);
+}
+
+extern "C" int xq_net_value_head(xq_ctx* c, const float* d_feats, const float* d_w1t, const float* d_b1,
+                                 const float* d_w2, float b2, float* d_value, int B, void* stream)
+{
+    if (!c || !d_feats || !d_w1t || !d_b1 || !d_w2 || !d_value || B < 0)
+        return xq_fail(c, XQ_ERR_ARG, "xq_net_value_head: bad arguments");
+    if (B == 0) return XQ_OK;
+    value_head_kernel<<<(B + kVhBoards - 1) / kVhBoards, 128, 0, (cudaStream_t)stream>>>(d_feats, d_w1t, d_b1, d_w2, b2,
+                                                                                       d_value, B);
+    c->launches += 1;
+    XQ_CUDA(c, cudaGetLastError());
+    return XQ_OK;
+}
+
+// Run a whole forward (a list of layer descriptors followed by the value head) from one call.
+extern "C" int xq_net_run(xq_ctx* c, const xq_gemm_desc* layers, int n_layers, const float* d_vfeats,
+                          const float* d_w1t, const float* d_b1, const float* d_w2, float b2, float* d_value, int B,
+                          void* stream)
+{
+    for (int i = 0; i < n_layers; ++i) {
+        int rc = xq_net_gemm(c, &layers[i], stream);
+        if (rc) return rc;
+    }
+    return xq_net_value_head(c, d_vfeats, d_w1t, d_b1, d_w2, b2, d_value, B, stream);
+}

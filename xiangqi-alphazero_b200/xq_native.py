@@ -69,13 +69,16 @@ def lib():
     i64, dbl = C.c_longlong, C.c_double
     _sig(L, "xq_mcts_create", i32, vp, i32, i64)
     _sig(L, "xq_mcts_set_games", i32, vp, i32, vp, vp, vp, vp, vp, vp, vp)
-    _sig(L, "xq_mcts_root_begin", i32, vp, vp, vp, vp, vp, vp)
+    _sig(L, "xq_mcts_root_begin", i32, vp, vp, vp, i64, i64, vp, vp, vp)
     _sig(L, "xq_mcts_root_expand", i32, vp, vp, i32, i64, vp, i32, u64, dbl, vp)
-    _sig(L, "xq_mcts_select", i32, vp, dbl, vp, vp, vp, vp, vp)
+    _sig(L, "xq_mcts_select", i32, vp, dbl, vp, vp, i64, i64, vp, vp, vp)
     _sig(L, "xq_mcts_expand_backup", i32, vp, vp, i32, i64, vp, vp)
     _sig(L, "xq_mcts_leaf_info", i32, vp, vp, vp, vp, vp)
     _sig(L, "xq_mcts_root_visits", i32, vp, vp, vp, vp, vp, vp)
     _sig(L, "xq_mcts_stats", i32, vp, C.POINTER(i64), i32)
+    _sig(L, "xq_net_gemm", i32, vp, vp, vp)
+    _sig(L, "xq_net_value_head", i32, vp, vp, vp, vp, vp, C.c_float, vp, i32, vp)
+    _sig(L, "xq_net_run", i32, vp, vp, i32, vp, vp, vp, vp, C.c_float, vp, i32, vp)
     _lib = L
     return L
 
@@ -84,7 +87,8 @@ EXPORTS = ["xq_create", "xq_destroy", "xq_last_error", "xq_version", "xq_launch_
            "xq_last_kernel_ms", "xq_movegen_batch", "xq_movegen_batch_host", "xq_is_attacked_batch",
            "xq_is_attacked_batch_host", "xq_overflow_count", "xq_random_playouts",
            "xq_mcts_create", "xq_mcts_set_games", "xq_mcts_root_begin", "xq_mcts_root_expand", "xq_mcts_select",
-           "xq_mcts_expand_backup", "xq_mcts_leaf_info", "xq_mcts_root_visits", "xq_mcts_stats"]
+           "xq_mcts_expand_backup", "xq_mcts_leaf_info", "xq_mcts_root_visits", "xq_mcts_stats",
+           "xq_net_gemm", "xq_net_value_head", "xq_net_run"]
 
 
 def _np_ptr(a: np.ndarray):
@@ -251,9 +255,14 @@ class MctsBatch:
         self.e._check(self.e.L.xq_mcts_set_games(self.e.h, self.n, *ptr, self.e._stream()))
         self._keep = keep
 
-    def root_begin(self, want_planes=True, x_nhwc=None):
-        self.e._check(self.e.L.xq_mcts_root_begin(self.e.h, self.planes.data_ptr() if want_planes else None,
-                                                  None if x_nhwc is None else x_nhwc.data_ptr(),
+    def _xargs(self, x_planes, x_row0):
+        if x_planes is None:
+            return None, 0, 0
+        return x_planes.data_ptr(), x_planes.shape[1], x_row0
+
+    def root_begin(self, want_planes=True, x_planes=None, x_row0=16):
+        xp, xr, x0 = self._xargs(x_planes, x_row0)
+        self.e._check(self.e.L.xq_mcts_root_begin(self.e.h, self.planes.data_ptr() if want_planes else None, xp, xr, x0,
                                                   self.boards.data_ptr(), self.sides.data_ptr(), self.e._stream()))
 
     def root_expand(self, policy, kind=POLICY_PROBS, noise=None, add_noise=False, seed=0, alpha=0.3):
@@ -261,10 +270,10 @@ class MctsBatch:
                                                    None if noise is None else noise.data_ptr(), int(add_noise),
                                                    C.c_uint64(seed), float(alpha), self.e._stream()))
 
-    def select(self, c_puct=1.5, want_planes=True, x_nhwc=None):
+    def select(self, c_puct=1.5, want_planes=True, x_planes=None, x_row0=16):
+        xp, xr, x0 = self._xargs(x_planes, x_row0)
         self.e._check(self.e.L.xq_mcts_select(self.e.h, float(c_puct), self.planes.data_ptr() if want_planes else None,
-                                              None if x_nhwc is None else x_nhwc.data_ptr(),
-                                              self.boards.data_ptr(), self.sides.data_ptr(), self.e._stream()))
+                                              xp, xr, x0, self.boards.data_ptr(), self.sides.data_ptr(), self.e._stream()))
 
     def expand_backup(self, policy, value, kind=POLICY_PROBS):
         self.e._check(self.e.L.xq_mcts_expand_backup(self.e.h, policy.data_ptr(), kind, policy.stride(0),
