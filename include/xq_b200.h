@@ -192,6 +192,61 @@ int xq_net_run(xq_ctx* ctx, const xq_gemm_desc* layers, int n_layers, const floa
                const float* d_w1t, const float* d_b1, const float* d_w2, float b2, float* d_value, int B,
                void* stream);
 
+/* ---- device-resident self-play ------------------------------------------------------------------
+ * Replaces parallel_selfplay.py:_play_one_game (:42-134) + the worker fan-out (:337-474): n_slots
+ * games advance in lockstep on one GPU, each ply = root evaluation -> num_simulations x (select,
+ * network forward, expand+backup) -> temperature sampling; finished games are replaced in their
+ * slot until target_games have been started.  Config fields are the reference's 8 worker keys
+ * (parallel_selfplay.py:184-187).
+ */
+typedef struct xq_selfplay_config {
+    int32_t num_simulations;
+    float c_puct;
+    int32_t temperature_threshold;
+    int32_t max_game_length;
+    int32_t random_opening_moves;
+    int32_t enable_resign;
+    float resign_threshold;
+    int32_t resign_check_steps;
+    int32_t add_noise;          /* root Dirichlet noise (mcts.py:117-121); the reference always uses 1 */
+    float dirichlet_alpha;      /* 0.3 */
+    uint64_t seed;
+    int32_t target_games;       /* games to start in total (num_games_per_iter share of this GPU) */
+} xq_selfplay_config;
+
+/* what the loop needs to run the evaluator: the layer list of xq_net_run plus its I/O buffers */
+typedef struct xq_net_plan {
+    const xq_gemm_desc* layers;
+    int32_t n_layers;
+    int32_t batch;              /* boards the descriptors were built for (>= n_slots) */
+    const float* vfeats;
+    const float* w1t;
+    const float* b1;
+    const float* w2;
+    float b2;
+    float* value;               /* [batch] */
+    void* x_planes;             /* network input planes written by the search kernels */
+    int64_t x_rows, x_row0;
+    const void* logits;         /* [batch][logit_stride] */
+    int64_t logit_stride;
+    int32_t logits_kind;        /* 1 bf16, 2 float32 */
+} xq_net_plan;
+
+/* sample record (896 bytes): board int8[90] @0, side int8 @90, n_moves uint8 @91, game uid int32 @92,
+ * ply int32 @96, action played int16 @100, actions int16[128] @128, visit probabilities float32[128] @384 */
+#define XQ_SAMPLE_BYTES 896
+
+int xq_selfplay_create(xq_ctx* ctx, int n_slots, int max_games_total, long long sample_capacity,
+                       long long node_capacity);
+int xq_selfplay_reset(xq_ctx* ctx, void* stream);
+int xq_selfplay_play(xq_ctx* ctx, const xq_selfplay_config* cfg, const xq_net_plan* net, int n_plies, void* stream);
+/* h_out14: games started, finished, samples, red wins, black wins, draws, plies of finished games, dropped
+ * samples, then the 6 values of xq_mcts_stats */
+int xq_selfplay_counters(xq_ctx* ctx, long long* h_out14);
+int xq_selfplay_fetch(xq_ctx* ctx, long long first, long long count, void* h_samples, int8_t* h_winner,
+                      int16_t* h_plies, int n_results);
+int xq_selfplay_slots(xq_ctx* ctx, int8_t* h_boards, int32_t* h_meta, int32_t* h_status, int32_t* h_uid);
+
 #ifdef __cplusplus
 }
 #endif

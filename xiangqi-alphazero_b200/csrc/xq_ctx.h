@@ -24,6 +24,7 @@ struct xq_ctx {
     // subsystem state owned by other translation units
     void* mcts = nullptr;
     void* net = nullptr;
+    void* selfplay = nullptr;
 };
 
 extern char g_xq_last_error[512];

@@ -61,6 +61,7 @@ struct MctsState {
     int16_t* leaf_actions = nullptr;  // [G][128]
     int32_t* leaf_n = nullptr;        // [G]
     int64_t* stats = nullptr;         // [4] sims, terminal sims, max depth, evals
+    int32_t* root_winner = nullptr;   // [G] is_game_over at the root: 1/-1/0, or 2 = game goes on
 };
 
 constexpr int kSelWarps = 4;
@@ -164,6 +165,8 @@ mcts_root_begin_kernel(MctsState M, float* planes_f32, __nv_bfloat16* x_planes, 
     const bool active = M.meta[g * 4 + 3] != 0;
     MovegenResult r = warp_movegen(b, gm.side, S);
     if (r.overflow && lane == 0) atomicOr(M.error, 2);
+    const int rw = warp_game_over(b, sm.ring[warp], gm, r);
+    if (lane == 0) M.root_winner[g] = rw;
     const int n = active ? min(r.n_legal, kMaxMoves) : 0;
     reinterpret_cast<uint2*>(M.leaf_actions + (size_t)g * kMaxMoves)[lane] = reinterpret_cast<const uint2*>(S.actions)[lane];
     if (lane == 0) {
@@ -434,6 +437,8 @@ __global__ void mcts_root_visits_kernel(MctsState M, int16_t* actions, int32_t* 
     if (lane == 0) n_out[g] = n;
 }
 
+__global__ void set_int_kernel(int* p, int v) { *p = v; }
+
 __global__ void mcts_set_games_kernel(MctsState M, const int8_t* boards, const int8_t* sides, const int32_t* move_count,
                                       const int32_t* no_capture, const int8_t* ring, const uint8_t* active)
 {
@@ -464,7 +469,7 @@ extern "C" void xq_mcts_free_(xq_ctx* c)
     MctsState* M = S_(c);
     if (!M) return;
     void* ptrs[] = {M->board, M->ring, M->meta, M->hot, M->link, M->rootP64, M->alloc, M->error,
-                    M->leaf_node, M->leaf_state, M->leaf_actions, M->leaf_n, M->stats};
+                    M->leaf_node, M->leaf_state, M->leaf_actions, M->leaf_n, M->stats, M->root_winner};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     delete M;
@@ -496,6 +501,7 @@ extern "C" int xq_mcts_create(xq_ctx* c, int max_games, long long node_capacity)
     XQ_CUDA(c, cudaMalloc(&M->leaf_actions, G * kMaxMoves * sizeof(int16_t)));
     XQ_CUDA(c, cudaMalloc(&M->leaf_n, G * sizeof(int32_t)));
     XQ_CUDA(c, cudaMalloc(&M->stats, 4 * sizeof(int64_t)));
+    XQ_CUDA(c, cudaMalloc(&M->root_winner, G * sizeof(int32_t)));
     XQ_CUDA(c, cudaMemset(M->error, 0, sizeof(int)));
     XQ_CUDA(c, cudaMemset(M->stats, 0, 4 * sizeof(int64_t)));
     XQ_CUDA(c, cudaMemset(M->meta, 0, G * 4 * sizeof(int32_t)));
@@ -532,8 +538,7 @@ extern "C" int xq_mcts_root_begin(xq_ctx* c, float* d_planes, void* d_x_planes, 
     if (M.n_games == 0) return XQ_OK;
     if (d_boards_out && !d_sides_out) return xq_fail(c, XQ_ERR_ARG, "xq_mcts_root_begin: sides_out missing");
     // a new search: the pool restarts after the reserved root slots (one tree per search, mcts.py:104)
-    int first = M.max_games;
-    XQ_CUDA(c, cudaMemcpyAsync(M.alloc, &first, sizeof(int), cudaMemcpyHostToDevice, s));
+    set_int_kernel<<<1, 1, 0, s>>>(M.alloc, M.max_games);
     mcts_root_begin_kernel<<<blocks_for(M.n_games), kSelWarps * 32, 0, s>>>(M, d_planes, (__nv_bfloat16*)d_x_planes, x_rows, x_row0,
                                                                             d_boards_out, d_sides_out);
     c->launches += 1;
@@ -639,3 +644,445 @@ extern "C" int xq_mcts_stats(xq_ctx* c, long long* h_stats6, int reset)
     return XQ_OK;
 }
 
+
+// =============================================================================================
+// Device-resident self-play loop
+// =============================================================================================
+// Replaces parallel_selfplay.py:_play_one_game (:42-134) for n_slots games advanced in lockstep:
+// random opening, per-ply search with root Dirichlet noise, temperature schedule (1.0 below
+// temperature_threshold plies, 0.3 after), visit-count sampling, resign rule, z-labelling inputs
+// (winner per game), and the sample records _augment_data / train.py consume.  A finished game
+// is replaced by a fresh one in the same slot while games remain to be started, so the evaluator
+// batch stays full.  Nothing crosses PCIe inside the loop.
+namespace xq {
+
+struct SpConfig {
+    int num_simulations;
+    float c_puct;
+    int temperature_threshold;
+    int max_game_length;
+    int random_opening_moves;
+    int enable_resign;
+    float resign_threshold;
+    int resign_check_steps;
+    int add_noise;
+    float dirichlet_alpha;
+    unsigned long long seed;
+    int target_games;
+};
+
+constexpr int kSampleBytes = 896;   // board 90 | side 1 | n 1 | uid 4 | ply 4 | played action 2 | pad | actions @128 (256) | probs @384 (512)
+
+struct SpState {
+    int n_slots = 0;
+    int max_games_total = 0;
+    long long sample_cap = 0;
+    int32_t* status = nullptr;      // [slots] 0 = empty (wants a new game), 1 = playing
+    int32_t* n_samples = nullptr;   // [slots] samples recorded by the current game (len(training_data))
+    int32_t* resign_run = nullptr;  // [slots] consecutive resign-probe values below the threshold
+    int32_t* game_uid = nullptr;    // [slots]
+    int32_t* counters = nullptr;    // [8] started, finished, samples, red wins, black wins, draws, plies of finished games, dropped samples
+    int8_t* res_winner = nullptr;   // [max_games_total]
+    int16_t* res_plies = nullptr;   // [max_games_total]
+    uint8_t* samples = nullptr;     // [sample_cap][kSampleBytes]
+    unsigned long long ply_counter = 0;   // host side: plies played since reset (RNG stream index)
+};
+
+__device__ __forceinline__ void warp_store_game(const MctsState& M, int g, const int8_t* b, const int8_t* ring, const GameMeta& gm,
+                                                int active)
+{
+    const int lane = lane_id();
+    uint4* gb = reinterpret_cast<uint4*>(M.board + (size_t)g * kBoardPad);
+    uint4* gr = reinterpret_cast<uint4*>(M.ring + (size_t)g * kRing * kBoardPad);
+    if (lane < 6) gb[lane] = reinterpret_cast<const uint4*>(b)[lane];
+    for (int i = lane; i < 72; i += 32) gr[i] = reinterpret_cast<const uint4*>(ring)[i];
+    if (lane == 0) {
+        M.meta[g * 4 + 0] = gm.side;
+        M.meta[g * 4 + 1] = gm.move_count;
+        M.meta[g * 4 + 2] = gm.no_capture;
+        M.meta[g * 4 + 3] = active;
+    }
+}
+
+__device__ __forceinline__ void warp_start_position(int8_t* b)
+{
+    const int lane = lane_id();
+    for (int sq = lane; sq < kBoardPad; sq += 32) {
+        int r = sq / 9, c = sq % 9, v = 0;
+        if (sq < kSquares) {
+            const int back[9] = {5, 4, 3, 2, 1, 2, 3, 4, 5};
+            if (r == 0) v = back[c];
+            else if (r == 9) v = -back[c];
+            else if (r == 2 && (c == 1 || c == 7)) v = 6;
+            else if (r == 7 && (c == 1 || c == 7)) v = -6;
+            else if (r == 3 && (c & 1) == 0) v = 7;
+            else if (r == 6 && (c & 1) == 0) v = -7;
+        }
+        b[sq] = (int8_t)v;
+    }
+    warp_sync();
+}
+
+// fill empty slots with fresh games: start position + k ~ U{0..random_opening_moves} uniformly random
+// legal plies; a game that ends inside its opening restarts from the start position (parallel_selfplay.py:60-72)
+__global__ void __launch_bounds__(kSelWarps * 32) sp_new_games_kernel(MctsState M, SpState P, SpConfig cfg, unsigned long long ply_idx)
+{
+    __shared__ SelectSmem sm;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.x * kSelWarps + warp;
+    if (g >= M.n_games) return;
+    if (P.status[g] != 0) return;
+    int uid = -1;
+    if (lane == 0) {
+        uid = atomicAdd(&P.counters[0], 1);
+        if (uid >= cfg.target_games) {
+            atomicSub(&P.counters[0], 1);
+            uid = -1;
+        }
+    }
+    uid = warp_bcast(uid, 0);
+    int8_t* b = sm.board[warp];
+    int8_t* ring = sm.ring[warp];
+    WarpScratch& S = sm.ws[warp];
+    GameMeta gm{1, 0, 0};
+    warp_start_position(b);
+    for (int i = lane; i < kRing * kBoardPad; i += 32) ring[i] = 0;
+    warp_sync();
+    if (uid < 0) {   // nothing left to start: the slot idles
+        warp_store_game(M, g, b, ring, gm, 0);
+        return;
+    }
+    const int k = (int)(rng_u64(cfg.seed, 0x0A11CEull + (uint64_t)uid, ply_idx, 1) % (uint64_t)(cfg.random_opening_moves + 1));
+    for (int i = 0; i < k; ++i) {
+        MovegenResult r = warp_movegen(b, gm.side, S);
+        if (r.n_legal == 0) break;
+        const int pick = (int)(rng_u64(cfg.seed, 0x0A11CEull + (uint64_t)uid, ply_idx, 2 + i) % (uint64_t)min(r.n_legal, kMaxMoves));
+        const int action = S.actions[pick];
+        warp_sync();
+        warp_make_move(b, ring, gm, action);
+        MovegenResult r2 = warp_movegen(b, gm.side, S);
+        if (warp_game_over(b, ring, gm, r2) != 2) {
+            warp_start_position(b);
+            for (int j = lane; j < kRing * kBoardPad; j += 32) ring[j] = 0;
+            gm = GameMeta{1, 0, 0};
+            warp_sync();
+            break;
+        }
+    }
+    warp_store_game(M, g, b, ring, gm, 1);
+    if (lane == 0) {
+        P.status[g] = 1;
+        P.n_samples[g] = 0;
+        P.resign_run[g] = 0;
+        P.game_uid[g] = uid;
+    }
+}
+
+__device__ __forceinline__ void sp_finish_game(const MctsState& M, const SpState& P, int g, int winner, int plies)
+{
+    // lane 0 only
+    const int uid = P.game_uid[g];
+    if (uid >= 0 && uid < P.max_games_total) {
+        P.res_winner[uid] = (int8_t)winner;
+        P.res_plies[uid] = (int16_t)plies;
+    }
+    atomicAdd(&P.counters[1], 1);
+    atomicAdd(&P.counters[winner == 1 ? 3 : (winner == -1 ? 4 : 5)], 1);
+    atomicAdd(&P.counters[6], plies);
+    P.status[g] = 0;
+    M.meta[g * 4 + 3] = 0;
+}
+
+// After the root evaluation: resign rule, termination, length adjudication, else expand the root
+// (parallel_selfplay.py:74-95,110-121 in the reference's order: resign probe first).
+template <int KIND>
+__global__ void __launch_bounds__(kSelWarps * 32)
+sp_after_root_kernel(MctsState M, SpState P, SpConfig cfg, const void* policy, size_t row_stride, const float* value,
+                     unsigned long long ply_idx)
+{
+    __shared__ float pri[kSelWarps][kMaxMoves];
+    __shared__ double nz[kSelWarps][kMaxMoves];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.x * kSelWarps + warp;
+    if (g >= M.n_games) return;
+    if (P.status[g] != 1) return;
+    const int side = M.meta[g * 4 + 0], move_count = M.meta[g * 4 + 1];
+    // resign probe: the value of the position just reached, for the side to move
+    if (cfg.enable_resign && P.n_samples[g] > 10) {
+        int run = P.resign_run[g];
+        run = value[g] < cfg.resign_threshold ? run + 1 : 0;
+        if (lane == 0) P.resign_run[g] = run;
+        if (run >= cfg.resign_check_steps) {
+            if (lane == 0) sp_finish_game(M, P, g, -side, move_count);
+            return;
+        }
+    }
+    const int rw = M.root_winner[g];
+    if (rw != 2) {
+        if (lane == 0) sp_finish_game(M, P, g, rw, move_count);
+        return;
+    }
+    if (move_count >= cfg.max_game_length) {
+        // material adjudication (parallel_selfplay.py:79-89); unreachable while max_game_length >= 200
+        __shared__ int8_t tb[kSelWarps][kBoardPad];
+        for (int i = lane; i < kBoardPad; i += 32) tb[warp][i] = M.board[(size_t)g * kBoardPad + i];
+        warp_sync();
+        const int diff = warp_material_diff(tb[warp]);
+        if (lane == 0) sp_finish_game(M, P, g, diff > 30 ? 1 : (diff < -30 ? -1 : 0), move_count);
+        return;
+    }
+    const int n = M.leaf_n[g];
+    const int16_t* acts = M.leaf_actions + (size_t)g * kMaxMoves;
+    bool uniform = warp_priors<KIND>(policy, row_stride, g, acts, n, pri[warp]);
+    if (cfg.add_noise) {
+        double s = 0.0;
+        const uint64_t stream = ((uint64_t)P.game_uid[g] << 20) ^ ply_idx;
+        for (int i = lane; i < n; i += 32) {
+            double x = gamma_sample((double)cfg.dirichlet_alpha, cfg.seed ^ 0xD1B1C1E7ull, stream, (uint64_t)i);
+            nz[warp][i] = x;
+            s += x;
+        }
+        s = warp_sum_d(s);
+        for (int i = lane; i < n; i += 32) nz[warp][i] = nz[warp][i] / s;
+        warp_sync();
+    }
+    warp_expand(M, g, acts, n, pri[warp], uniform, g, nz[warp], cfg.add_noise != 0);
+    if (lane == 0) atomicAdd((unsigned long long*)&M.stats[3], 1ull);
+}
+
+// End of a search: visit distribution -> sample record, temperature sampling, make the move
+// (parallel_selfplay.py:91-107, mcts.py:190-206).
+__global__ void __launch_bounds__(kSelWarps * 32)
+sp_end_move_kernel(MctsState M, SpState P, SpConfig cfg, unsigned long long ply_idx)
+{
+    __shared__ SelectSmem sm;
+    __shared__ double wts[kSelWarps][kMaxMoves];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.x * kSelWarps + warp;
+    if (g >= M.n_games) return;
+    if (P.status[g] != 1) return;
+    const NodeLink root = M.link[g];
+    if (root.child0 < 0) return;
+    int8_t* b = sm.board[warp];
+    int8_t* ring = sm.ring[warp];
+    GameMeta gm;
+    warp_load_game(M, g, b, ring, gm);
+    const int n = root.nchild;
+    const double inv_t = gm.move_count < cfg.temperature_threshold ? 1.0 : 1.0 / 0.3;
+    double s = 0.0;
+    for (int i = lane; i < n; i += 32) {
+        const int cnt = M.hot[root.child0 + i].N;
+        const double w = cnt > 0 ? (inv_t == 1.0 ? (double)cnt : pow((double)cnt, inv_t)) : 0.0;
+        wts[warp][i] = w;
+        s += w;
+    }
+    s = warp_sum_d(s);
+    warp_sync();
+    // np.random.choice(8100, p=probs): inverse-CDF draw in child order (statistical parity only)
+    int chosen = 0;
+    if (lane == 0) {
+        const double u = u01(rng_u64(cfg.seed ^ 0x5A3D1Eull, (uint64_t)P.game_uid[g], ply_idx, 7)) * s;
+        double acc = 0.0;
+        chosen = n - 1;
+        for (int i = 0; i < n; ++i) {
+            acc += wts[warp][i];
+            if (u < acc) { chosen = i; break; }
+        }
+        while (chosen > 0 && wts[warp][chosen] == 0.0) --chosen;   // never pick an unvisited move by rounding
+    }
+    chosen = warp_bcast(chosen, 0);
+    const int action = M.link[root.child0 + chosen].action;
+    // sample record
+    int slot = -1;
+    if (lane == 0) {
+        slot = atomicAdd(&P.counters[2], 1);
+        if ((long long)slot >= P.sample_cap) {
+            atomicSub(&P.counters[2], 1);
+            atomicAdd(&P.counters[7], 1);
+            slot = -1;
+        }
+    }
+    slot = warp_bcast(slot, 0);
+    if (slot >= 0) {
+        uint8_t* rec = P.samples + (size_t)slot * kSampleBytes;
+        for (int i = lane; i < kSquares; i += 32) rec[i] = (uint8_t)b[i];
+        if (lane == 0) {
+            rec[90] = (uint8_t)(int8_t)gm.side;
+            rec[91] = (uint8_t)n;
+            *reinterpret_cast<int32_t*>(rec + 92) = P.game_uid[g];
+            *reinterpret_cast<int32_t*>(rec + 96) = gm.move_count;
+            *reinterpret_cast<int16_t*>(rec + 100) = (int16_t)action;
+        }
+        int16_t* ra = reinterpret_cast<int16_t*>(rec + 128);
+        float* rp = reinterpret_cast<float*>(rec + 384);
+        for (int i = lane; i < kMaxMoves; i += 32) {
+            ra[i] = i < n ? M.link[root.child0 + i].action : (int16_t)-1;
+            rp[i] = i < n ? (float)(wts[warp][i] / s) : 0.0f;
+        }
+    }
+    warp_sync();
+    warp_make_move(b, ring, gm, action);
+    warp_store_game(M, g, b, ring, gm, 1);
+    if (lane == 0) P.n_samples[g] += 1;
+}
+
+}  // namespace xq
+
+static SpState* SP_(xq_ctx* c) { return reinterpret_cast<SpState*>(c->selfplay); }
+
+extern "C" void xq_selfplay_free_(xq_ctx* c)
+{
+    SpState* P = SP_(c);
+    if (!P) return;
+    void* ptrs[] = {P->status, P->n_samples, P->resign_run, P->game_uid, P->counters, P->res_winner, P->res_plies, P->samples};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    delete P;
+    c->selfplay = nullptr;
+}
+
+extern "C" int xq_selfplay_create(xq_ctx* c, int n_slots, int max_games_total, long long sample_capacity,
+                                  long long node_capacity)
+{
+    if (!c || n_slots <= 0 || max_games_total <= 0 || sample_capacity <= 0)
+        return xq_fail(c, XQ_ERR_ARG, "xq_selfplay_create: bad arguments");
+    int rc = xq_mcts_create(c, n_slots, node_capacity);
+    if (rc) return rc;
+    xq_selfplay_free_(c);
+    SpState* P = new SpState();
+    c->selfplay = P;
+    P->n_slots = n_slots;
+    P->max_games_total = max_games_total;
+    P->sample_cap = sample_capacity;
+    const size_t G = (size_t)n_slots;
+    XQ_CUDA(c, cudaMalloc(&P->status, G * 4));
+    XQ_CUDA(c, cudaMalloc(&P->n_samples, G * 4));
+    XQ_CUDA(c, cudaMalloc(&P->resign_run, G * 4));
+    XQ_CUDA(c, cudaMalloc(&P->game_uid, G * 4));
+    XQ_CUDA(c, cudaMalloc(&P->counters, 8 * 4));
+    XQ_CUDA(c, cudaMalloc(&P->res_winner, (size_t)max_games_total));
+    XQ_CUDA(c, cudaMalloc(&P->res_plies, (size_t)max_games_total * 2));
+    XQ_CUDA(c, cudaMalloc(&P->samples, (size_t)sample_capacity * kSampleBytes));
+    XQ_CUDA(c, cudaMemset(P->status, 0, G * 4));
+    XQ_CUDA(c, cudaMemset(P->counters, 0, 8 * 4));
+    XQ_CUDA(c, cudaMemset(P->res_winner, 2, (size_t)max_games_total));
+    S_(c)->n_games = n_slots;
+    return XQ_OK;
+}
+
+extern "C" int xq_selfplay_reset(xq_ctx* c, void* stream)
+{
+    SpState* P = c ? SP_(c) : nullptr;
+    if (!P) return xq_fail(c, XQ_ERR_STATE, "xq_selfplay_reset: call xq_selfplay_create first");
+    cudaStream_t s = (cudaStream_t)stream;
+    XQ_CUDA(c, cudaMemsetAsync(P->status, 0, (size_t)P->n_slots * 4, s));
+    XQ_CUDA(c, cudaMemsetAsync(P->counters, 0, 8 * 4, s));
+    XQ_CUDA(c, cudaMemsetAsync(P->res_winner, 2, (size_t)P->max_games_total, s));
+    XQ_CUDA(c, cudaMemsetAsync(S_(c)->meta, 0, (size_t)P->n_slots * 16, s));
+    XQ_CUDA(c, cudaMemsetAsync(S_(c)->stats, 0, 4 * sizeof(int64_t), s));
+    XQ_CUDA(c, cudaMemsetAsync(S_(c)->error, 0, sizeof(int), s));
+    P->ply_counter = 0;
+    return XQ_OK;
+}
+
+extern "C" int xq_selfplay_play(xq_ctx* c, const xq_selfplay_config* cfg, const xq_net_plan* net, int n_plies, void* stream)
+{
+    SpState* Pp = c ? SP_(c) : nullptr;
+    MctsState* Mp = c ? S_(c) : nullptr;
+    if (!Pp || !Mp) return xq_fail(c, XQ_ERR_STATE, "xq_selfplay_play: call xq_selfplay_create first");
+    if (!cfg || !net || n_plies < 0) return xq_fail(c, XQ_ERR_ARG, "xq_selfplay_play: bad arguments");
+    if (net->batch < Pp->n_slots) return xq_fail(c, XQ_ERR_ARG, "xq_selfplay_play: network batch %d < slots %d", net->batch, Pp->n_slots);
+    if (net->logits_kind != 1 && net->logits_kind != 2) return xq_fail(c, XQ_ERR_ARG, "xq_selfplay_play: logits_kind must be 1 (bf16) or 2 (f32)");
+    MctsState& M = *Mp;
+    SpState& P = *Pp;
+    cudaStream_t s = (cudaStream_t)stream;
+    SpConfig k;
+    k.num_simulations = cfg->num_simulations;
+    k.c_puct = cfg->c_puct;
+    k.temperature_threshold = cfg->temperature_threshold;
+    k.max_game_length = cfg->max_game_length;
+    k.random_opening_moves = cfg->random_opening_moves;
+    k.enable_resign = cfg->enable_resign;
+    k.resign_threshold = cfg->resign_threshold;
+    k.resign_check_steps = cfg->resign_check_steps;
+    k.add_noise = cfg->add_noise;
+    k.dirichlet_alpha = cfg->dirichlet_alpha;
+    k.seed = cfg->seed;
+    k.target_games = cfg->target_games < P.max_games_total ? cfg->target_games : P.max_games_total;
+    const int nb = blocks_for(M.n_games), nt = kSelWarps * 32;
+    auto run_net = [&]() {
+        return xq_net_run(c, net->layers, net->n_layers, net->vfeats, net->w1t, net->b1, net->w2, net->b2, net->value, net->batch, stream);
+    };
+    for (int ply = 0; ply < n_plies; ++ply) {
+        const unsigned long long pi = P.ply_counter++;
+        sp_new_games_kernel<<<nb, nt, 0, s>>>(M, P, k, pi);
+        set_int_kernel<<<1, 1, 0, s>>>(M.alloc, M.max_games);
+        mcts_root_begin_kernel<<<nb, nt, 0, s>>>(M, nullptr, (__nv_bfloat16*)net->x_planes, net->x_rows, net->x_row0, nullptr, nullptr);
+        c->launches += 3;
+        int rc = run_net();
+        if (rc) return rc;
+        if (net->logits_kind == 1)
+            sp_after_root_kernel<1><<<nb, nt, 0, s>>>(M, P, k, net->logits, (size_t)net->logit_stride, net->value, pi);
+        else
+            sp_after_root_kernel<2><<<nb, nt, 0, s>>>(M, P, k, net->logits, (size_t)net->logit_stride, net->value, pi);
+        c->launches += 1;
+        for (int sim = 0; sim < k.num_simulations; ++sim) {
+            mcts_select_kernel<<<nb, nt, 0, s>>>(M, (double)k.c_puct, nullptr, (__nv_bfloat16*)net->x_planes, net->x_rows, net->x_row0,
+                                                 nullptr, nullptr);
+            rc = run_net();
+            if (rc) return rc;
+            if (net->logits_kind == 1)
+                mcts_expand_backup_kernel<1><<<nb, nt, 0, s>>>(M, net->logits, (size_t)net->logit_stride, net->value);
+            else
+                mcts_expand_backup_kernel<2><<<nb, nt, 0, s>>>(M, net->logits, (size_t)net->logit_stride, net->value);
+            c->launches += 2;
+        }
+        sp_end_move_kernel<<<nb, nt, 0, s>>>(M, P, k, pi);
+        c->launches += 1;
+        XQ_CUDA(c, cudaGetLastError());
+    }
+    return XQ_OK;
+}
+
+// counters: games started, games finished, samples, red wins, black wins, draws, plies of finished games,
+// dropped samples; then the 6 values of xq_mcts_stats.  Synchronises.
+extern "C" int xq_selfplay_counters(xq_ctx* c, long long* h_out14)
+{
+    SpState* P = c ? SP_(c) : nullptr;
+    if (!P) return xq_fail(c, XQ_ERR_STATE, "xq_selfplay_counters: call xq_selfplay_create first");
+    int32_t v[8];
+    XQ_CUDA(c, cudaMemcpy(v, P->counters, sizeof(v), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 8; ++i) h_out14[i] = v[i];
+    return xq_mcts_stats(c, h_out14 + 8, 0);
+}
+
+// Copies sample records [first, first+count) (896 B each, see kSampleBytes) and the per-game results to HOST buffers.
+extern "C" int xq_selfplay_fetch(xq_ctx* c, long long first, long long count, void* h_samples, int8_t* h_winner,
+                                 int16_t* h_plies, int n_results)
+{
+    SpState* P = c ? SP_(c) : nullptr;
+    if (!P) return xq_fail(c, XQ_ERR_STATE, "xq_selfplay_fetch: call xq_selfplay_create first");
+    if (first < 0 || count < 0 || first + count > P->sample_cap || n_results > P->max_games_total)
+        return xq_fail(c, XQ_ERR_ARG, "xq_selfplay_fetch: range out of bounds");
+    if (count && h_samples)
+        XQ_CUDA(c, cudaMemcpy(h_samples, P->samples + (size_t)first * kSampleBytes, (size_t)count * kSampleBytes, cudaMemcpyDeviceToHost));
+    if (n_results > 0 && h_winner) XQ_CUDA(c, cudaMemcpy(h_winner, P->res_winner, (size_t)n_results, cudaMemcpyDeviceToHost));
+    if (n_results > 0 && h_plies) XQ_CUDA(c, cudaMemcpy(h_plies, P->res_plies, (size_t)n_results * 2, cudaMemcpyDeviceToHost));
+    return XQ_OK;
+}
+
+// current game states of all slots (device -> host), for inspection and tests
+extern "C" int xq_selfplay_slots(xq_ctx* c, int8_t* h_boards /*[slots][90]*/, int32_t* h_meta /*[slots][4]*/, int32_t* h_status,
+                                 int32_t* h_uid)
+{
+    SpState* P = c ? SP_(c) : nullptr;
+    MctsState* M = c ? S_(c) : nullptr;
+    if (!P || !M) return xq_fail(c, XQ_ERR_STATE, "xq_selfplay_slots: call xq_selfplay_create first");
+    const int G = P->n_slots;
+    if (h_boards)
+        XQ_CUDA(c, cudaMemcpy2D(h_boards, 90, M->board, kBoardPad, 90, (size_t)G, cudaMemcpyDeviceToHost));
+    if (h_meta) XQ_CUDA(c, cudaMemcpy(h_meta, M->meta, (size_t)G * 16, cudaMemcpyDeviceToHost));
+    if (h_status) XQ_CUDA(c, cudaMemcpy(h_status, P->status, (size_t)G * 4, cudaMemcpyDeviceToHost));
+    if (h_uid) XQ_CUDA(c, cudaMemcpy(h_uid, P->game_uid, (size_t)G * 4, cudaMemcpyDeviceToHost));
+    return XQ_OK;
+}

@@ -265,11 +265,13 @@ extern "C" int xq_create(int device, xq_ctx** out)
 
 extern "C" void xq_mcts_free_(xq_ctx*);
 extern "C" void xq_net_free_(xq_ctx*);
+extern "C" void xq_selfplay_free_(xq_ctx*);
 
 extern "C" void xq_destroy(xq_ctx* c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
+    xq_selfplay_free_(c);
     xq_mcts_free_(c);
     xq_net_free_(c);
     for (int i = 0; i < 2; ++i) {

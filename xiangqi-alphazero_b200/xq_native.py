@@ -79,6 +79,12 @@ def lib():
     _sig(L, "xq_net_gemm", i32, vp, vp, vp)
     _sig(L, "xq_net_value_head", i32, vp, vp, vp, vp, vp, C.c_float, vp, i32, vp)
     _sig(L, "xq_net_run", i32, vp, vp, i32, vp, vp, vp, vp, C.c_float, vp, i32, vp)
+    _sig(L, "xq_selfplay_create", i32, vp, i32, i32, i64, i64)
+    _sig(L, "xq_selfplay_reset", i32, vp, vp)
+    _sig(L, "xq_selfplay_play", i32, vp, vp, vp, i32, vp)
+    _sig(L, "xq_selfplay_counters", i32, vp, C.POINTER(i64))
+    _sig(L, "xq_selfplay_fetch", i32, vp, i64, i64, vp, vp, vp, i32)
+    _sig(L, "xq_selfplay_slots", i32, vp, vp, vp, vp, vp)
     _lib = L
     return L
 
@@ -88,7 +94,8 @@ EXPORTS = ["xq_create", "xq_destroy", "xq_last_error", "xq_version", "xq_launch_
            "xq_is_attacked_batch_host", "xq_overflow_count", "xq_random_playouts",
            "xq_mcts_create", "xq_mcts_set_games", "xq_mcts_root_begin", "xq_mcts_root_expand", "xq_mcts_select",
            "xq_mcts_expand_backup", "xq_mcts_leaf_info", "xq_mcts_root_visits", "xq_mcts_stats",
-           "xq_net_gemm", "xq_net_value_head", "xq_net_run"]
+           "xq_net_gemm", "xq_net_value_head", "xq_net_run", "xq_selfplay_create", "xq_selfplay_reset",
+           "xq_selfplay_play", "xq_selfplay_counters", "xq_selfplay_fetch", "xq_selfplay_slots"]
 
 
 def _np_ptr(a: np.ndarray):
