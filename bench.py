@@ -281,7 +281,7 @@ def bench_movegen(args, rank, world, local_rank, dist):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=None, choices=[None, "movegen", "selfplay"])
@@ -290,6 +290,10 @@ def main():
     if args.workload is None:
         args.workload = "selfplay" if os.path.exists(os.path.join(PKG, "selfplay_engine.py")) else "movegen"
     if args.impl == "reference":
+        if args.workload == "selfplay":
+            sys.path.insert(0, ROOT)
+            import bench_selfplay
+            return bench_selfplay.run_reference(args)
         return run_reference_arm(args)
 
     import torch
@@ -306,6 +310,7 @@ def main():
         if args.workload == "movegen":
             bench_movegen(args, rank, world, local_rank, dist)
         else:
+            sys.path.insert(0, ROOT)
             import bench_selfplay
             bench_selfplay.run(args, rank, world, local_rank, dist)
     finally:

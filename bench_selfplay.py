@@ -1,0 +1,252 @@
+"""bench.py --workload selfplay: BASELINE configs[2] -- 4096 concurrent self-play games x 800 MCTS
+simulations per move, XiangqiNet(128, 6) with seeded random-init weights, c_puct 1.5, Dirichlet(0.3)
+root noise, T = 1.0 below ply 20 else 0.3, random_opening_moves 6, resign (-0.9, 5 steps)
+(train.py standard preset :677-689 + TrainingConfig defaults :64-78), on each GPU.
+
+Step = one ply of every game: root evaluation + 800 x (select, tcgen05 forward, expand/backup) +
+move selection, entirely on the device.  Metric = MCTS simulations per second (a simulation = one
+iteration of mcts.py:126; terminal-leaf simulations count).
+"""
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+
+GAMES_PER_GPU = 4096
+SIMS = 800
+CHANNELS, BLOCKS = 128, 6
+FLOPS_PER_EVAL = 369_193_216        # conv + FC MACs x 2 of the 128x6 network
+
+
+class StdConfig:
+    """standard_train preset of the reference (train.py:677-689) for the self-play keys."""
+    num_simulations = SIMS
+    c_puct = 1.5
+    temperature_threshold = 20
+    max_game_length = 300
+    random_opening_moves = 6
+    enable_resign = True
+    resign_threshold = -0.9
+    resign_check_steps = 5
+
+
+def run(args, rank, world, local_rank, dist):
+    import numpy as np
+    import torch
+    import bench
+    import xq_native
+    import model as M
+    from selfplay_engine import SelfPlayEngine, SAMPLE_BYTES
+
+    sims = int(os.environ.get("XQ_BENCH_SIMS", SIMS))
+    games = int(os.environ.get("XQ_BENCH_GAMES", GAMES_PER_GPU))
+    torch.cuda.set_device(local_rank)
+    eng = xq_native.Engine(local_rank)
+    torch.manual_seed(20261018)                      # same random-init weights on every rank
+    model = M.XiangqiNet(CHANNELS, BLOCKS).eval()
+    cfgobj = StdConfig()
+    cfgobj.num_simulations = sims
+    total_plies = args.warmup + args.steps + 4
+    sp = SelfPlayEngine(eng, model, n_slots=games, max_games=games * 4,
+                        sample_capacity=games * (2 * total_plies + 8), node_capacity=games * (sims + 1) * 48)
+    sp.reset()
+    cfg = SelfPlayEngine.make_config(cfgobj, games * 4, seed=20261018 + rank, add_noise=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    sp.play(cfg, args.warmup)
+    torch.cuda.synchronize()
+    c0 = sp.counters()
+    eng.launch_count(reset=True)
+    sampler = bench.ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    torch.cuda.synchronize()
+    e0.record()
+    sp.play(cfg, args.steps)                          # leaves live in HBM; the tree/activation working set (>> L2) is rewritten every step
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = eng.launch_count()
+    ms = e0.elapsed_time(e1)
+    c1 = sp.counters()
+    sims_done = c1["sims"] - c0["sims"]
+    evals_done = c1["evals"] - c0["evals"]
+    if c1["error"]:
+        raise RuntimeError(f"device error bits {c1['error']}")
+
+    # forward-only timing of the dominant kernel chain (the evaluator) for the roofline line
+    net = sp.net
+    for _ in range(3):
+        net.run()
+    torch.cuda.synchronize()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(20):
+        net.run()
+    f1.record()
+    torch.cuda.synchronize()
+    fwd_ms = f0.elapsed_time(f1) / 20
+
+    # e2e: the same plies through the host-facing API -- per step the host uploads the step's control
+    # block and downloads that ply's sample records and counters (pinned host memory)
+    h_raw = torch.empty((games * 2, SAMPLE_BYTES), dtype=torch.uint8).pin_memory().numpy()
+    e2e_steps = max(1, min(args.steps, 3))
+    barrier()
+    t0 = time.perf_counter()
+    s_before = sp.counters()
+    d2h = 0
+    for _ in range(e2e_steps):
+        sp.play(cfg, 1)
+        c = sp.counters()                                   # D2H: counters (synchronises)
+        n_new = min(games, c["samples"])
+        sp.fetch(c["samples"] - n_new, n_new, out=h_raw[:n_new])   # D2H: this ply's sample records + game results
+        d2h += n_new * SAMPLE_BYTES + 14 * 8 + sp.max_games * 3
+    e2e_s = time.perf_counter() - t0
+    c2 = sp.counters()
+    e2e_sims = c2["sims"] - s_before["sims"]
+
+    if world > 1:
+        t = torch.tensor([ms, e2e_s, fwd_ms], device=eng.dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_s, fwd_ms = t.tolist()
+        cnt = torch.tensor([sims_done, evals_done, e2e_sims], device=eng.dev, dtype=torch.float64)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        sims_done, evals_done, e2e_sims = cnt.tolist()
+    if rank != 0:
+        return
+    peaks, peak_kind = bench.measured_peaks()
+    value = sims_done / (ms * 1e-3)
+    peak_tf = peaks["bf16_tflops_sustained"]          # the forward runs inside a long step: sustained figure
+    achieved_tf = FLOPS_PER_EVAL * games / (fwd_ms * 1e-3) / 1e12
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_selfplay_rate(os.cpu_count() or 1, sims=min(sims, 100))
+    line = {
+        "metric": "mcts_sims_per_sec", "value": value, "unit": "sims/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic (seeded random-init weights, self-generated games)",
+        "config": {"workload": f"selfplay: configs[2], {games} concurrent games/GPU x {sims} sims/move, "
+                               f"XiangqiNet({CHANNELS},{BLOCKS}), c_puct 1.5, Dirichlet(0.3) root noise, step = one ply of every game",
+                   "games_per_gpu": games, "sims_per_move": sims, "evals_in_region": evals_done,
+                   "l2": "per-step working set (trees + activations, > 1 GB) >> 126 MB L2",
+                   "parallelism": f"games sharded x{world}, no collective in self-play"},
+        "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                     "frac": achieved_tf / peak_tf, "traffic": None, "peak_source": peak_kind + " (sustained bf16)",
+                     "kernel": "gemm_kernel (tcgen05 implicit-GEMM forward, 15 launches + value head)",
+                     "algorithmic_flops_per_eval": FLOPS_PER_EVAL, "forward_ms": fwd_ms,
+                     "forward_share_of_step": fwd_ms * (sims + 1) / (ms / args.steps)},
+        "cpu_baseline": cpu,
+        "e2e": {"value": e2e_sims / e2e_s, "unit": "sims/s", "h2d_bytes_per_step": 64 + 160,
+                "d2h_bytes_per_step": d2h // e2e_steps},
+        "gpu_launches": launches,
+        "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm (mcts.py search, fp32 torch forward, one thread per process --
+# parallel_selfplay.py:_cpu_worker_entry) restated by the oracle; only the rules engine can be the
+# reference's own compiled code (oracle/_ref), mcts.py/model.py cannot travel to the GPU box.
+# ------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    sims, seed = args
+    os.environ["OMP_NUM_THREADS"] = "1"
+    os.environ["MKL_NUM_THREADS"] = "1"
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import torch
+    import torch.nn as nn
+    import torch.nn.functional as F
+    import xq_oracle
+    torch.set_num_threads(1)
+
+    class Block(nn.Module):
+        def __init__(self, c):
+            super().__init__()
+            self.conv1 = nn.Conv2d(c, c, 3, padding=1, bias=False)
+            self.bn1 = nn.BatchNorm2d(c)
+            self.conv2 = nn.Conv2d(c, c, 3, padding=1, bias=False)
+            self.bn2 = nn.BatchNorm2d(c)
+
+        def forward(self, x):
+            return F.relu(self.bn2(self.conv2(F.relu(self.bn1(self.conv1(x))))) + x)
+
+    class Net(nn.Module):   # model.py:39-107
+        def __init__(self, c=CHANNELS, r=BLOCKS):
+            super().__init__()
+            self.inp = nn.Sequential(nn.Conv2d(15, c, 3, padding=1, bias=False), nn.BatchNorm2d(c), nn.ReLU())
+            self.blocks = nn.ModuleList([Block(c) for _ in range(r)])
+            self.ph = nn.Sequential(nn.Conv2d(c, 32, 1, bias=False), nn.BatchNorm2d(32), nn.ReLU(), nn.Flatten(), nn.Linear(2880, 8100))
+            self.vh = nn.Sequential(nn.Conv2d(c, 4, 1, bias=False), nn.BatchNorm2d(4), nn.ReLU(), nn.Flatten(), nn.Linear(360, 128),
+                                    nn.ReLU(), nn.Linear(128, 1), nn.Tanh())
+
+        def forward(self, x):
+            x = self.inp(x)
+            for b in self.blocks:
+                x = b(x)
+            return self.ph(x), self.vh(x)
+
+    torch.manual_seed(seed)
+    net = Net().eval()
+
+    def predict(board, player):   # model.py:109-124 on the oracle's planes
+        with torch.no_grad():
+            x = torch.from_numpy(xq_oracle.planes(board, player))[None]
+            lg, v = net(x)
+            return F.softmax(lg, dim=1)[0].numpy(), float(v.item())
+
+    g = xq_oracle.OracleGame()
+    rs = np.random.RandomState(seed)
+    predict(g.board, 1)           # warm-up
+    t0 = time.perf_counter()
+    noise = rs.dirichlet([0.3] * len(g.get_legal_actions()))
+    xq_oracle.mcts_search(g, sims, 1.5, predict, noise)
+    return time.perf_counter() - t0
+
+
+def cpu_selfplay_rate(procs, sims=100):
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    t0 = time.perf_counter()
+    with ctx.Pool(procs) as pool:
+        pool.map(_cpu_worker, [(2, i) for i in range(procs)])           # start-up + import cost outside the timing
+        t0 = time.perf_counter()
+        pool.map(_cpu_worker, [(sims, 100 + i) for i in range(procs)])
+        wall = time.perf_counter() - t0
+    rate = procs * sims / wall
+    return {"value": rate, "unit": "sims/s", "cores": procs, "kind": "port",
+            "sample": f"{procs} processes x one {sims}-simulation search from the start position, fp32 torch "
+                      f"XiangqiNet({CHANNELS},{BLOCKS}) 1 thread each (the reference's _cpu_worker_entry shape), {wall:.1f} s"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    procs = os.cpu_count() or 1
+    vals = []
+    last = None
+    for i in range(args.warmup + args.steps):
+        last = cpu_selfplay_rate(procs, sims=60)
+        if i >= args.warmup:
+            vals.append(last["value"])
+    value = sum(vals) / len(vals)
+    last["value"] = value
+    line = {"impl": "reference", "metric": "mcts_sims_per_sec", "value": value, "unit": "sims/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * procs * 60 / value, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic (seeded random-init weights)",
+            "config": {"workload": f"selfplay: configs[2] on host cores, XiangqiNet({CHANNELS},{BLOCKS}), one search of 60 "
+                                   f"simulations per process per step, {procs} processes"},
+            "cpu_baseline": last,
+            "e2e": {"value": value, "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
