@@ -25,6 +25,7 @@ struct xq_ctx {
     void* mcts = nullptr;
     void* net = nullptr;
     void* selfplay = nullptr;
+    bool net_v1 = false;                  // XQ_NET_V1=1: use the first-generation conv kernel (A/B comparisons)
 };
 
 extern char g_xq_last_error[512];

@@ -13,6 +13,7 @@
 //     coalesced float2 streaming stores, counts / in-check flags as one 64 B row per tile.
 #include "xq_ctx.h"
 #include "xq_rules.cuh"
+#include <cstdlib>
 
 char g_xq_last_error[512] = {0};
 
@@ -249,6 +250,7 @@ extern "C" int xq_create(int device, xq_ctx** out)
     if (device < 0 || device >= n) return xq_fail(nullptr, XQ_ERR_ARG, "xq_create: device %d out of range", device);
     xq_ctx* c = new xq_ctx();
     c->device = device;
+    c->net_v1 = getenv("XQ_NET_V1") != nullptr;
     XQ_CUDA(c, cudaSetDevice(device));
     cudaDeviceProp prop;
     XQ_CUDA(c, cudaGetDeviceProperties(&prop, device));

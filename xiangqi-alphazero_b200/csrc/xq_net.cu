@@ -29,6 +29,7 @@
 #include "xq_ctx.h"
 
 #include <cuda_bf16.h>
+#include <cstdlib>
 
 namespace xq {
 
@@ -378,6 +379,287 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const GemmArgs p)
     if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
 }
 
+// =============================================================================================
+// v2 conv kernel: TWO 128-row tiles per weight stage + double-buffered accumulators and A blocks
+// =============================================================================================
+// v1 (above) streams 288 KB of weights + 38 KB of A per 128-row tile and serialises A-load -> MMA ->
+// epilogue inside a CTA (ncu: tensor pipe 30-45 % active, L2 25 %).  v2 keeps one CTA per SM and
+//   * feeds each 16 KB weight stage to two row tiles (accumulators t=0,1): L2->SM bytes per row halve;
+//   * double-buffers the accumulator pair in TMEM (2 x 2 x 128 = all 512 columns) so the epilogue of
+//     pair i runs under the MMAs of pair i+1, and double-buffers the 278-row A block so its TMA load
+//     is issued a whole pair ahead;
+//   * prefetches the residual operand into registers before the accumulator is ready (v1 issued 16
+//     dependent global loads per row after the MMAs: +60 us per layer).
+constexpr int kPairRows = 256;
+constexpr int kARows2 = kPairRows + 2 * kHalo;   // 278
+constexpr int kAPlane2 = kARows2 * 16;           // 4448 B per chunk
+
+template <int NT, int KCH, bool HEADS, int ABUFS>
+struct Conv2Cfg {
+    static constexpr int kStages = 4;
+    static constexpr int kWStage = KCH * NT * 16;
+    static constexpr int kTileCols = NT > 64 ? 128 : 64;       // TMEM columns per row tile
+    static constexpr int kTmemCols = 4 * kTileCols;            // 2 accumulator stages x 2 tiles
+    static constexpr int kTaps = HEADS ? 1 : 9;
+    static int smem_bytes(int kchunks)
+    {
+        int a = ABUFS * ((kchunks * kAPlane2 + 127) & ~127);
+        int total = a + kStages * kWStage + 256;
+        return total < 120 * 1024 ? 120 * 1024 : total;        // > half an SM: exactly one CTA per SM (it owns all of TMEM)
+    }
+};
+
+template <int NT, int KCH, bool HEADS, int ABUFS>
+__global__ void __launch_bounds__(kGemmThreads, 1) conv2_kernel(const GemmArgs p)
+{
+    using Cfg = Conv2Cfg<NT, KCH, HEADS, ABUFS>;
+    constexpr int S = Cfg::kStages;
+    constexpr int TS = Cfg::kTileCols;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int a_buf_bytes = (p.kchunks * kAPlane2 + 127) & ~127;
+    uint8_t* sA = smem;
+    uint8_t* sStage = smem + ABUFS * a_buf_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + S * Cfg::kWStage);
+    uint64_t* w_full = bars;
+    uint64_t* w_empty = bars + S;
+    uint64_t* a_full = bars + 2 * S;          // [ABUFS]
+    uint64_t* a_empty = bars + 2 * S + 2;     // [ABUFS]
+    uint64_t* t_full = bars + 2 * S + 4;      // [2]
+    uint64_t* t_empty = bars + 2 * S + 6;     // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kblocks = p.kchunks / KCH;
+    const int iters = Cfg::kTaps * kblocks;
+    const int m_pairs = (p.m_tiles + 1) / 2;
+    const int total = m_pairs * p.n_tiles;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < S; ++i) {
+            mbar_init(&w_full[i], 1);
+            mbar_init(&w_empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&a_full[i], 1);
+            mbar_init(&a_empty[i], 1);
+            mbar_init(&t_full[i], 1);
+            mbar_init(&t_empty[i], 4);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, Cfg::kTmemCols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            int n = 0;
+            for (int work = blockIdx.x; work < total; work += gridDim.x, ++n) {
+                const int pair = work / p.n_tiles, n_tile = work - pair * p.n_tiles;
+                const long long m0 = (long long)pair * kPairRows;
+                const int ab = n % ABUFS;
+                const uint32_t aph = (uint32_t)(n / ABUFS) & 1u;
+                mbar_wait(&a_empty[ab], aph ^ 1);
+                mbar_expect_tx(&a_full[ab], (uint32_t)(p.kchunks * kAPlane2));
+                for (int c = 0; c < p.kchunks; ++c)
+                    bulk_g2s(sA + ab * a_buf_bytes + c * kAPlane2,
+                             p.a + ((size_t)c * p.a_rows + (size_t)(p.a_row0 + m0 - kHalo)) * 16, kAPlane2, &a_full[ab]);
+                const uint8_t* wt = p.w + (size_t)n_tile * iters * Cfg::kWStage;
+                for (int it = 0; it < iters; ++it) {
+                    mbar_wait(&w_empty[s], ph ^ 1);
+                    mbar_expect_tx(&w_full[s], Cfg::kWStage);
+                    bulk_g2s(sStage + s * Cfg::kWStage, wt + (size_t)it * Cfg::kWStage, Cfg::kWStage, &w_full[s]);
+                    if (++s == S) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(128, NT);
+            int s = 0;
+            uint32_t ph = 0;
+            int n = 0;
+            for (int work = blockIdx.x; work < total; work += gridDim.x, ++n) {
+                const int ab = n % ABUFS;
+                const uint32_t aph = (uint32_t)(n / ABUFS) & 1u;
+                const int acc = n & 1;
+                const uint32_t tph = (uint32_t)(n >> 1) & 1u;
+                mbar_wait(&t_empty[acc], tph ^ 1);
+                tc_fence_after();
+                mbar_wait(&a_full[ab], aph);
+                const uint32_t a_addr = smem_u32(sA + ab * a_buf_bytes);
+                const uint32_t d_addr = tmem_base + (uint32_t)(acc * 2 * TS);
+                for (int it = 0; it < iters; ++it) {
+                    const int tap = HEADS ? 0 : it / kblocks;
+                    const int kb = it - tap * kblocks;
+                    const int shift = HEADS ? 0 : ((tap / 3) - 1) * 10 + (tap % 3) - 1;
+                    mbar_wait(&w_full[s], ph);
+                    tc_fence_after();
+                    const uint32_t st_addr = smem_u32(sStage + s * Cfg::kWStage);
+#pragma unroll
+                    for (int t = 0; t < 2; ++t) {
+#pragma unroll
+                        for (int j = 0; j < KCH / 2; ++j) {
+                            const uint64_t adesc = make_desc(
+                                a_addr + (uint32_t)((kb * KCH + 2 * j) * kAPlane2 + (kHalo + shift + t * 128) * 16), kAPlane2, 128);
+                            const uint64_t bdesc = make_desc(st_addr + (2 * j) * (NT * 16), NT * 16, 128);
+                            umma_bf16(d_addr + (uint32_t)(t * TS), adesc, bdesc, idesc, (it | j) != 0 ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(&w_empty[s]);
+                    if (++s == S) { s = 0; ph ^= 1; }
+                }
+                umma_commit(&t_full[acc]);
+                umma_commit(&a_empty[ab]);
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        int n = 0;
+        for (int work = blockIdx.x; work < total; work += gridDim.x, ++n) {
+            const int pair = work / p.n_tiles, n_tile = work - pair * p.n_tiles;
+            const int acc = n & 1;
+            const uint32_t tph = (uint32_t)(n >> 1) & 1u;
+            const long long mrow[2] = {(long long)pair * kPairRows + row, (long long)pair * kPairRows + 128 + row};
+            bool real[2];
+            int rr[2];
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                rr[t] = (int)(mrow[t] % 110);
+                real[t] = mrow[t] < (long long)p.n_boards * 110 && rr[t] >= 10 && (rr[t] % 10) != 9;
+            }
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 * TS);
+
+            if (!HEADS) {
+                // residual operand of tile 0 goes to registers before the accumulator is waited for
+                uint4 res[NT / 8];
+                const bool has_res = p.residual != nullptr;
+#pragma unroll
+                for (int k = 0; k < NT / 8; ++k) {
+                    res[k] = make_uint4(0, 0, 0, 0);
+                    if (has_res && real[0])
+                        res[k] = __ldg(reinterpret_cast<const uint4*>(
+                            p.residual + ((size_t)(n_tile * (NT / 8) + k) * p.out_rows + (size_t)(p.out_row0 + mrow[0])) * 16));
+                }
+                mbar_wait(&t_full[acc], tph);
+                tc_fence_after();
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+#pragma unroll
+                    for (int c0 = 0; c0 < NT; c0 += 32) {
+                        uint32_t v[32];
+                        tmem_ld32(taddr + (uint32_t)(t * TS + c0), v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            const int k = c0 / 8 + g;
+                            const int nn = n_tile * NT + c0 + g * 8;
+                            const size_t off = ((size_t)(nn >> 3) * p.out_rows + (size_t)(p.out_row0 + mrow[t])) * 16;
+                            uint4 o = make_uint4(0, 0, 0, 0);
+                            if (real[t]) {
+                                float f[8];
+                                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + nn));
+                                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + nn + 4));
+                                f[0] = __uint_as_float(v[g * 8 + 0]) + b0.x;
+                                f[1] = __uint_as_float(v[g * 8 + 1]) + b0.y;
+                                f[2] = __uint_as_float(v[g * 8 + 2]) + b0.z;
+                                f[3] = __uint_as_float(v[g * 8 + 3]) + b0.w;
+                                f[4] = __uint_as_float(v[g * 8 + 4]) + b1.x;
+                                f[5] = __uint_as_float(v[g * 8 + 5]) + b1.y;
+                                f[6] = __uint_as_float(v[g * 8 + 6]) + b1.z;
+                                f[7] = __uint_as_float(v[g * 8 + 7]) + b1.w;
+                                const uint32_t rw[4] = {res[k].x, res[k].y, res[k].z, res[k].w};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    f[2 * e] += __uint_as_float(rw[e] << 16);
+                                    f[2 * e + 1] += __uint_as_float(rw[e] & 0xffff0000u);
+                                }
+                                if (p.relu) {
+#pragma unroll
+                                    for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.0f);
+                                }
+                                o = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]),
+                                               pack_bf16(f[6], f[7]));
+                            }
+                            *reinterpret_cast<uint4*>(p.out + off) = o;
+                            // this register is free again: refill it with tile 1's residual
+                            if (t == 0) {
+                                res[k] = make_uint4(0, 0, 0, 0);
+                                if (has_res && real[1])
+                                    res[k] = __ldg(reinterpret_cast<const uint4*>(
+                                        p.residual + ((size_t)(nn >> 3) * p.out_rows + (size_t)(p.out_row0 + mrow[1])) * 16));
+                            }
+                        }
+                    }
+                }
+            } else {
+                mbar_wait(&t_full[acc], tph);
+                tc_fence_after();
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    const long long b = mrow[t] / 110;
+                    const int pos = (rr[t] / 10 - 1) * 9 + (rr[t] % 10);
+                    uint32_t v[32], v2[16];
+                    tmem_ld32(taddr + (uint32_t)(t * TS), v);
+                    tmem_ld16(taddr + (uint32_t)(t * TS + 32), v2);
+                    tmem_ld_wait();
+                    if (real[t]) {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            float f[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) f[e] = fmaxf(__uint_as_float(v[g * 8 + e]) + __ldg(p.bias + g * 8 + e), 0.0f);
+                            const uint4 o = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]),
+                                                       pack_bf16(f[6], f[7]));
+                            *reinterpret_cast<uint4*>(p.out + ((size_t)(pos * 4 + g) * p.out_rows + (size_t)(p.out_row0 + b)) * 16) = o;
+                        }
+                        float4 vf;
+                        vf.x = fmaxf(__uint_as_float(v2[0]) + __ldg(p.bias + 32), 0.0f);
+                        vf.y = fmaxf(__uint_as_float(v2[1]) + __ldg(p.bias + 33), 0.0f);
+                        vf.z = fmaxf(__uint_as_float(v2[2]) + __ldg(p.bias + 34), 0.0f);
+                        vf.w = fmaxf(__uint_as_float(v2[3]) + __ldg(p.bias + 35), 0.0f);
+                        *reinterpret_cast<float4*>(p.out2 + ((size_t)b * 90 + pos) * 4) = vf;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&t_empty[acc]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+template <int NT, int KCH, bool HEADS, int ABUFS>
+static int launch_conv2(xq_ctx* c, const GemmArgs& a, cudaStream_t s)
+{
+    using Cfg = Conv2Cfg<NT, KCH, HEADS, ABUFS>;
+    const int smem = Cfg::smem_bytes(a.kchunks);
+    static bool configured = false;
+    if (!configured) {
+        XQ_CUDA(c, cudaFuncSetAttribute(conv2_kernel<NT, KCH, HEADS, ABUFS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        configured = true;
+    }
+    if (smem > 227 * 1024) return xq_fail(c, XQ_ERR_ARG, "conv2 kernel needs %d bytes of shared memory", smem);
+    const int total = ((a.m_tiles + 1) / 2) * a.n_tiles;
+    int grid = c->sm_count < total ? c->sm_count : total;     // persistent, one CTA per SM
+    conv2_kernel<NT, KCH, HEADS, ABUFS><<<grid, kGemmThreads, smem, s>>>(a);
+    c->launches += 1;
+    XQ_CUDA(c, cudaGetLastError());
+    return XQ_OK;
+}
+
 // ---- value head: Linear(360,128)+ReLU -> Linear(128,1) -> tanh (model.py:74-83) ----------------
 // feats [B][90][4] fp32 (already conv1x1+BN+ReLU), w1t [360][128] fp32 with k = pos*4+ch, 16 boards per CTA.
 constexpr int kVhBoards = 16;
@@ -427,17 +709,23 @@ static int launch_gemm(xq_ctx* c, const GemmArgs& a, cudaStream_t s)
     static int per_sm = 1;
     if (!configured) {
         XQ_CUDA(c, cudaFuncSetAttribute(gemm_kernel<MODE, NT, KCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        // without this the driver keeps a smaller shared-memory carve-out and only ONE CTA fits per SM
+        XQ_CUDA(c, cudaFuncSetAttribute(gemm_kernel<MODE, NT, KCH>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                        (int)cudaSharedmemCarveoutMaxShared));
         configured = true;
     }
-    XQ_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gemm_kernel<MODE, NT, KCH>, kGemmThreads, smem));
+    // two CTAs per SM when shared memory (227 KB, 1 KB reserved per CTA) and TMEM (512 columns) allow it.
+    // (cudaOccupancyMaxActiveBlocksPerMultiprocessor reported 1 here even with the max carve-out requested;
+    // the persistent tile loop is correct for any grid size, so the launch does not depend on it.)
+    per_sm = (227 * 1024) / (smem + 1024);
     if (per_sm < 1) return xq_fail(c, XQ_ERR_ARG, "gemm kernel does not fit: %d bytes of shared memory", smem);
-    // TMEM: 512 columns per SM; each CTA takes kTmemCols
     const int tmem_cap = 512 / Cfg::kTmemCols;
     if (per_sm > tmem_cap) per_sm = tmem_cap;
     if (per_sm > 2) per_sm = 2;
     const int total = a.m_tiles * a.n_tiles;
     int grid = c->sm_count * per_sm;
     if (grid > total) grid = total;
+    if (getenv("XQ_DEBUG")) fprintf(stderr, "[xq] gemm<%d,%d,%d> per_sm=%d grid=%d smem=%d\n", MODE, NT, KCH, per_sm, grid, smem);
     gemm_kernel<MODE, NT, KCH><<<grid, kGemmThreads, smem, s>>>(a);
     c->launches += 1;
     XQ_CUDA(c, cudaGetLastError());
@@ -475,6 +763,12 @@ extern "C" int xq_net_gemm(xq_ctx* c, const xq_gemm_desc* d, void* stream)
     a.out2 = (float*)d->out2;
     cudaStream_t s = (cudaStream_t)stream;
     XqTimer tm(c, s);
+    const bool v1 = c->net_v1;
+    if (!v1 && d->mode == 0 && d->nt == 128 && d->kch_iter == 8 && d->kchunks % 8 == 0 && d->kchunks <= 16) return launch_conv2<128, 8, false, 2>(c, a, s);
+    if (!v1 && d->mode == 0 && d->nt == 128 && d->kch_iter == 8 && d->kchunks % 8 == 0 && d->kchunks <= 32) return launch_conv2<128, 8, false, 1>(c, a, s);
+    if (!v1 && d->mode == 0 && d->nt == 128 && d->kch_iter == 2 && d->kchunks == 2) return launch_conv2<128, 2, false, 2>(c, a, s);
+    if (!v1 && d->mode == 1 && d->nt == 48 && d->kch_iter == 8 && d->kchunks % 8 == 0 && d->kchunks <= 16 && d->out2) return launch_conv2<48, 8, true, 2>(c, a, s);
+    if (!v1 && d->mode == 1 && d->nt == 48 && d->kch_iter == 8 && d->kchunks % 8 == 0 && d->kchunks <= 32 && d->out2) return launch_conv2<48, 8, true, 1>(c, a, s);
     if (d->mode == 0 && d->nt == 128 && d->kch_iter == 8 && d->kchunks % 8 == 0) return launch_gemm<0, 128, 8>(c, a, s);
     if (d->mode == 0 && d->nt == 128 && d->kch_iter == 2 && d->kchunks == 2) return launch_gemm<0, 128, 2>(c, a, s);
     if (d->mode == 1 && d->nt == 48 && d->kch_iter == 8 && d->kchunks % 8 == 0 && d->out2) return launch_gemm<1, 48, 8>(c, a, s);
