@@ -17,6 +17,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 GAMES_PER_GPU = 4096
 SIMS = 800
 CHANNELS, BLOCKS = 128, 6
+REF_SIMS = 200                      # simulations per process per step in the CPU reference arm (bounded sample)
 FLOPS_PER_EVAL = 369_193_216        # conv + FC MACs x 2 of the 128x6 network
 
 
@@ -236,15 +237,15 @@ def run_reference(args):
     vals = []
     last = None
     for i in range(args.warmup + args.steps):
-        last = cpu_selfplay_rate(procs, sims=60)
+        last = cpu_selfplay_rate(procs, sims=REF_SIMS)
         if i >= args.warmup:
             vals.append(last["value"])
     value = sum(vals) / len(vals)
     last["value"] = value
     line = {"impl": "reference", "metric": "mcts_sims_per_sec", "value": value, "unit": "sims/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * procs * 60 / value, "higher_is_better": True,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * procs * REF_SIMS / value, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic (seeded random-init weights)",
-            "config": {"workload": f"selfplay: configs[2] on host cores, XiangqiNet({CHANNELS},{BLOCKS}), one search of 60 "
+            "config": {"workload": f"selfplay: configs[2] on host cores, XiangqiNet({CHANNELS},{BLOCKS}), one search of {REF_SIMS} "
                                    f"simulations per process per step, {procs} processes"},
             "cpu_baseline": last,
             "e2e": {"value": value, "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

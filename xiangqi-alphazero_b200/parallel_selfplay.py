@@ -45,6 +45,36 @@ def shard_games(num_games: int, rank: int, world: int) -> int:
     return num_games // world + (1 if rank < num_games % world else 0)
 
 
+def _play_local(model, config, my_games: int, local_device: int):
+    """This rank's share of the games on its GPU -> (samples, wins, total_plies, valid_games)."""
+    data, wins, total_steps, valid = [], {1: 0, -1: 0, 0: 0}, 0, 0
+    if my_games <= 0:
+        return data, wins, total_steps, valid
+    eng = engine(local_device)
+    slots = min(my_games, int(os.environ.get("XQ_SELFPLAY_SLOTS", "4096")))
+    key = (id(eng), slots, model.num_channels, model.num_res_blocks)
+    sp = _ENGINES.get(key)
+    if sp is None or sp.max_games < my_games:
+        sp = SelfPlayEngine(eng, model, n_slots=slots, max_games=my_games)
+        _ENGINES.clear()
+        _ENGINES[key] = sp
+    else:
+        sp.set_model(model)                      # fresh weights every iteration
+    sp.reset()
+    seed = int.from_bytes(os.urandom(8), 'big')  # the reference seeds workers from os.urandom (:167-170)
+    cfg = SelfPlayEngine.make_config(config, my_games, seed=seed, add_noise=True)
+    c = sp.play_games(cfg)
+    raw, winner, plies = sp.fetch(0, c["samples"])
+    dec = decode_samples(raw)
+    data = samples_to_reference_tuples(dec, winner, augment=True)
+    for g in range(my_games):
+        if winner[g] != 2:
+            valid += 1
+            wins[int(winner[g])] += 1
+            total_steps += int(plies[g])
+    return data, wins, total_steps, valid
+
+
 def parallel_self_play(model, config, num_workers: Optional[int] = None, use_gpu_server: bool = False,
                        gpu_device: str = 'cuda') -> Tuple[List[Tuple[np.ndarray, np.ndarray, float]], Dict[str, Any]]:
     dist = _dist()
@@ -52,30 +82,8 @@ def parallel_self_play(model, config, num_workers: Optional[int] = None, use_gpu
     num_games = int(config.num_games_per_iter)
     my_games = shard_games(num_games, rank, world)
     start = time.time()
-    data, wins, total_steps, valid = [], {1: 0, -1: 0, 0: 0}, 0, 0
-    if my_games > 0:
-        eng = engine(int(os.environ.get("LOCAL_RANK", "0")) if dist else 0)
-        slots = min(my_games, int(os.environ.get("XQ_SELFPLAY_SLOTS", "4096")))
-        key = (id(eng), slots, model.num_channels, model.num_res_blocks)
-        sp = _ENGINES.get(key)
-        if sp is None or sp.max_games < my_games:
-            sp = SelfPlayEngine(eng, model, n_slots=slots, max_games=my_games)
-            _ENGINES.clear()
-            _ENGINES[key] = sp
-        else:
-            sp.set_model(model)                      # fresh weights every iteration
-        sp.reset()
-        seed = int.from_bytes(os.urandom(8), 'big')  # the reference seeds workers from os.urandom (:167-170)
-        cfg = SelfPlayEngine.make_config(config, my_games, seed=seed, add_noise=True)
-        c = sp.play_games(cfg)
-        raw, winner, plies = sp.fetch(0, c["samples"])
-        dec = decode_samples(raw)
-        data = samples_to_reference_tuples(dec, winner, augment=True)
-        for g in range(my_games):
-            if winner[g] != 2:
-                valid += 1
-                wins[int(winner[g])] += 1
-                total_steps += int(plies[g])
+    local_device = int(os.environ.get("LOCAL_RANK", "0")) if dist else 0
+    data, wins, total_steps, valid = _play_local(model, config, my_games, local_device)
     if dist and world > 1:
         parts = [None] * world
         dist.all_gather_object(parts, (data, wins, total_steps, valid))
