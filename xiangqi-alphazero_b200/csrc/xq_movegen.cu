@@ -251,6 +251,8 @@ extern "C" int xq_create(int device, xq_ctx** out)
     xq_ctx* c = new xq_ctx();
     c->device = device;
     c->net_v1 = getenv("XQ_NET_V1") != nullptr;
+    if (const char* e = getenv("XQ_NET_CLUSTER")) c->net_cluster = atoi(e);
+    if (const char* e = getenv("XQ_NET_GEN")) c->net_gen = atoi(e);
     XQ_CUDA(c, cudaSetDevice(device));
     cudaDeviceProp prop;
     XQ_CUDA(c, cudaGetDeviceProperties(&prop, device));

@@ -42,6 +42,7 @@ struct GemmArgs {
     const uint8_t* residual;
     uint8_t* out;
     float* out2;
+    int dbg;   // timing experiments only (XQ_NET_DBG): 1 = no weight copies, 2 = quarter of the MMAs, 4 = empty epilogue
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------
@@ -102,6 +103,34 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v)
           "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
         : "r"(taddr)
         : "memory");
+}
+// ---- thread-block cluster helpers (weight-stage multicast) ----
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// global -> shared of EVERY CTA in cta_mask (same offset), completing tx bytes on each CTA's own barrier
+__device__ __forceinline__ void bulk_g2s_mc(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar, uint16_t cta_mask)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
+        : "memory");
+}
+// arrive on the barrier at this offset in every CTA of cta_mask once the MMAs issued so far are done
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"(cta_mask)
+                 : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -171,6 +200,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const GemmArgs p)
     const int kblocks = p.kchunks / KCH;
     const int iters = Cfg::kTaps * kblocks;
     const int total_tiles = p.m_tiles * p.n_tiles;
+    __shared__ __align__(16) float sBiasT[2][128];
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < S; ++i) {
@@ -243,15 +273,17 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const GemmArgs p)
                     mbar_wait(&w_full[s], ph);
                     tc_fence_after();
                     const uint32_t st_addr = smem_u32(sStage + s * Cfg::kStageBytes);
+                    constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);        // SBO = 128 B, version 1
+                    // low descriptor words are additive in 16-byte units: build them once per stage
+                    const uint32_t a_lo = (MODE == 2)
+                        ? ((((st_addr + Cfg::kWStage) >> 4) & 0x3FFFu) | ((2048u >> 4) << 16))
+                        : ((((sA_addr + (uint32_t)(kb * KCH * kAPlane + (kHalo + shift) * 16)) >> 4) & 0x3FFFu) | ((uint32_t)(kAPlane >> 4) << 16));
+                    const uint32_t a_step = (MODE == 2) ? (2u * 2048u) >> 4 : (2u * kAPlane) >> 4;
+                    const uint32_t b_lo = ((st_addr >> 4) & 0x3FFFu) | ((uint32_t)((NT * 16) >> 4) << 16);
 #pragma unroll
                     for (int j = 0; j < KCH / 2; ++j) {
-                        uint64_t adesc, bdesc;
-                        if (MODE == 2)
-                            adesc = make_desc(st_addr + Cfg::kWStage + (2 * j) * 2048, 2048, 128);
-                        else
-                            adesc = make_desc(sA_addr + (uint32_t)((kb * KCH + 2 * j) * kAPlane + (kHalo + shift) * 16),
-                                              kAPlane, 128);
-                        bdesc = make_desc(st_addr + (2 * j) * (NT * 16), NT * 16, 128);
+                        const uint64_t adesc = ((uint64_t)kDescHi << 32) | (uint64_t)(a_lo + (uint32_t)j * a_step);
+                        const uint64_t bdesc = ((uint64_t)kDescHi << 32) | (uint64_t)(b_lo + (uint32_t)(2 * j * NT));
                         umma_bf16(tmem_base, adesc, bdesc, idesc, (it | j) != 0 ? 1u : 0u);
                     }
                     umma_commit(&w_empty[s]);        // frees the stage when these MMAs have read it
@@ -270,6 +302,11 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const GemmArgs p)
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
             const long long m = (long long)m_tile * 128 + row;
+            if (MODE == 2) {
+                // this tile's 128 bias values -> shared memory (double buffered by tile parity), one per epilogue thread
+                sBiasT[tile_ph][row] = p.bias[n_tile * NT + row];
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
             mbar_wait(t_full, tile_ph);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -357,8 +394,8 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const GemmArgs p)
                         uint4* dst = reinterpret_cast<uint4*>(p.out + ((size_t)m * p.out_stride + n) * 2);
 #pragma unroll
                         for (int g = 0; g < 4; ++g) {
-                            const float4 b0 = *reinterpret_cast<const float4*>(p.bias + n + g * 8);
-                            const float4 b1 = *reinterpret_cast<const float4*>(p.bias + n + g * 8 + 4);
+                            const float4 b0 = *reinterpret_cast<const float4*>(&sBiasT[tile_ph][c0 + g * 8]);
+                            const float4 b1 = *reinterpret_cast<const float4*>(&sBiasT[tile_ph][c0 + g * 8 + 4]);
                             dst[g] = make_uint4(pack_bf16(__uint_as_float(v[g * 8 + 0]) + b0.x, __uint_as_float(v[g * 8 + 1]) + b0.y),
                                                 pack_bf16(__uint_as_float(v[g * 8 + 2]) + b0.z, __uint_as_float(v[g * 8 + 3]) + b0.w),
                                                 pack_bf16(__uint_as_float(v[g * 8 + 4]) + b1.x, __uint_as_float(v[g * 8 + 5]) + b1.y),
@@ -409,10 +446,15 @@ struct Conv2Cfg {
     }
 };
 
-template <int NT, int KCH, bool HEADS, int ABUFS>
+template <int NT, int KCH, bool HEADS, int ABUFS, int CL>
 __global__ void __launch_bounds__(kGemmThreads, 1) conv2_kernel(const GemmArgs p)
 {
     using Cfg = Conv2Cfg<NT, KCH, HEADS, ABUFS>;
+    // CL > 1: the CTAs of a cluster work on CL consecutive row pairs with the SAME weights; each CTA fetches
+    // 1/CL of every weight stage and multicasts it to all of them, so L2 -> SM weight traffic drops CL-fold.
+    const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
+    constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
+    const int cluster_id = blockIdx.x / CL, n_clusters = gridDim.x / CL;
     constexpr int S = Cfg::kStages;
     constexpr int TS = Cfg::kTileCols;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -432,12 +474,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv2_kernel(const GemmArgs p
     const int kblocks = p.kchunks / KCH;
     const int iters = Cfg::kTaps * kblocks;
     const int m_pairs = (p.m_tiles + 1) / 2;
-    const int total = m_pairs * p.n_tiles;
+    const int groups = (m_pairs + CL - 1) / CL;        // CL row pairs per work item (one per CTA of the cluster)
+    const int total = groups * p.n_tiles;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < S; ++i) {
             mbar_init(&w_full[i], 1);
-            mbar_init(&w_empty[i], 1);
+            mbar_init(&w_empty[i], CL);                // every CTA of the cluster releases the stage
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&a_full[i], 1);
@@ -447,12 +490,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv2_kernel(const GemmArgs p
         }
         mbar_fence_init();
     }
+    // bias is uniform across rows and tiles: stage it once (the first version re-read it from global memory
+    // in every tile -- ncu showed the epilogue stalled on those dependent loads, and it paced the whole kernel)
+    __shared__ __align__(16) float sBias[256];
+    for (int i = threadIdx.x; i < p.n_tiles * NT && i < 256; i += kGemmThreads) sBias[i] = p.bias[i];
     if (warp == 1) {
         tmem_alloc(tmem_slot, Cfg::kTmemCols);
         tmem_relinquish();
     }
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();                    // peers' barriers are initialised before anything lands on them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -461,8 +509,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv2_kernel(const GemmArgs p
             int s = 0;
             uint32_t ph = 0;
             int n = 0;
-            for (int work = blockIdx.x; work < total; work += gridDim.x, ++n) {
-                const int pair = work / p.n_tiles, n_tile = work - pair * p.n_tiles;
+            for (int work = cluster_id; work < total; work += n_clusters, ++n) {
+                const int grp = work / p.n_tiles, n_tile = work - grp * p.n_tiles;
+                const int pair = grp * CL + (int)crank;
                 const long long m0 = (long long)pair * kPairRows;
                 const int ab = n % ABUFS;
                 const uint32_t aph = (uint32_t)(n / ABUFS) & 1u;
@@ -474,8 +523,19 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv2_kernel(const GemmArgs p
                 const uint8_t* wt = p.w + (size_t)n_tile * iters * Cfg::kWStage;
                 for (int it = 0; it < iters; ++it) {
                     mbar_wait(&w_empty[s], ph ^ 1);
+                    if (p.dbg & 1) {
+                        mbar_arrive(&w_full[s]);
+                        if (++s == S) { s = 0; ph ^= 1; }
+                        continue;
+                    }
                     mbar_expect_tx(&w_full[s], Cfg::kWStage);
-                    bulk_g2s(sStage + s * Cfg::kWStage, wt + (size_t)it * Cfg::kWStage, Cfg::kWStage, &w_full[s]);
+                    if (CL == 1) {
+                        bulk_g2s(sStage + s * Cfg::kWStage, wt + (size_t)it * Cfg::kWStage, Cfg::kWStage, &w_full[s]);
+                    } else {
+                        constexpr int kSlice = Cfg::kWStage / CL;
+                        bulk_g2s_mc(sStage + s * Cfg::kWStage + crank * kSlice, wt + (size_t)it * Cfg::kWStage + crank * kSlice,
+                                    kSlice, &w_full[s], kMask);
+                    }
                     if (++s == S) { s = 0; ph ^= 1; }
                 }
             }
@@ -486,7 +546,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv2_kernel(const GemmArgs p
             int s = 0;
             uint32_t ph = 0;
             int n = 0;
-            for (int work = blockIdx.x; work < total; work += gridDim.x, ++n) {
+            for (int work = cluster_id; work < total; work += n_clusters, ++n) {
                 const int ab = n % ABUFS;
                 const uint32_t aph = (uint32_t)(n / ABUFS) & 1u;
                 const int acc = n & 1;
@@ -494,26 +554,33 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv2_kernel(const GemmArgs p
                 mbar_wait(&t_empty[acc], tph ^ 1);
                 tc_fence_after();
                 mbar_wait(&a_full[ab], aph);
-                const uint32_t a_addr = smem_u32(sA + ab * a_buf_bytes);
+                // Descriptors are 16-byte-granular and additive in their low word, so the issue loop only adds
+                // small constants (the first version rebuilt both 64-bit descriptors per MMA: ~25 dependent
+                // instructions per MMA from ONE thread paced the tensor pipe at ~45 % -- see DESIGN.md).
+                const uint32_t a_lo0 = (((smem_u32(sA + ab * a_buf_bytes)) >> 4) & 0x3FFFu) | ((uint32_t)(kAPlane2 >> 4) << 16);
+                constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);            // SBO = 128 B, version 1
                 const uint32_t d_addr = tmem_base + (uint32_t)(acc * 2 * TS);
                 for (int it = 0; it < iters; ++it) {
                     const int tap = HEADS ? 0 : it / kblocks;
                     const int kb = it - tap * kblocks;
                     const int shift = HEADS ? 0 : ((tap / 3) - 1) * 10 + (tap % 3) - 1;
+                    const uint32_t a_lo = a_lo0 + (uint32_t)(kb * KCH * (kAPlane2 >> 4) + kHalo + shift);
                     mbar_wait(&w_full[s], ph);
                     tc_fence_after();
-                    const uint32_t st_addr = smem_u32(sStage + s * Cfg::kWStage);
+                    const uint32_t b_lo = ((smem_u32(sStage + s * Cfg::kWStage) >> 4) & 0x3FFFu) | ((uint32_t)((NT * 16) >> 4) << 16);
+                    const uint32_t first = it != 0 ? 1u : 0u;
 #pragma unroll
                     for (int t = 0; t < 2; ++t) {
 #pragma unroll
                         for (int j = 0; j < KCH / 2; ++j) {
-                            const uint64_t adesc = make_desc(
-                                a_addr + (uint32_t)((kb * KCH + 2 * j) * kAPlane2 + (kHalo + shift + t * 128) * 16), kAPlane2, 128);
-                            const uint64_t bdesc = make_desc(st_addr + (2 * j) * (NT * 16), NT * 16, 128);
-                            umma_bf16(d_addr + (uint32_t)(t * TS), adesc, bdesc, idesc, (it | j) != 0 ? 1u : 0u);
+                            if ((p.dbg & 2) && j > 0) continue;
+                            const uint64_t adesc = ((uint64_t)kDescHi << 32) | (uint64_t)(a_lo + (uint32_t)(2 * j * (kAPlane2 >> 4) + t * 128));
+                            const uint64_t bdesc = ((uint64_t)kDescHi << 32) | (uint64_t)(b_lo + (uint32_t)(2 * j * NT));
+                            umma_bf16(d_addr + (uint32_t)(t * TS), adesc, bdesc, idesc, j == 0 ? first : 1u);
                         }
                     }
-                    umma_commit(&w_empty[s]);
+                    if (CL == 1) umma_commit(&w_empty[s]);
+                    else umma_commit_mc(&w_empty[s], kMask);
                     if (++s == S) { s = 0; ph ^= 1; }
                 }
                 umma_commit(&t_full[acc]);
@@ -524,8 +591,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv2_kernel(const GemmArgs p
         const int q = warp & 3;
         const int row = q * 32 + lane;
         int n = 0;
-        for (int work = blockIdx.x; work < total; work += gridDim.x, ++n) {
-            const int pair = work / p.n_tiles, n_tile = work - pair * p.n_tiles;
+        uint4 res[NT / 8];
+        for (int work = cluster_id; work < total; work += n_clusters, ++n) {
+            const int grp = work / p.n_tiles, n_tile = work - grp * p.n_tiles;
+            const int pair = grp * CL + (int)crank;
             const int acc = n & 1;
             const uint32_t tph = (uint32_t)(n >> 1) & 1u;
             const long long mrow[2] = {(long long)pair * kPairRows + row, (long long)pair * kPairRows + 128 + row};
@@ -539,20 +608,30 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv2_kernel(const GemmArgs p
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 * TS);
 
             if (!HEADS) {
-                // residual operand of tile 0 goes to registers before the accumulator is waited for
-                uint4 res[NT / 8];
+                // Residual operand: registers res[k] always hold the NEXT tile's values -- tile 0 of the first
+                // pair is loaded before the loop, tile 1 is loaded while tile 0 is processed, and tile 0 of the
+                // next pair while tile 1 is processed, so the loads are in flight for half a pair (~3 us).
                 const bool has_res = p.residual != nullptr;
+                if (n == 0) {
 #pragma unroll
-                for (int k = 0; k < NT / 8; ++k) {
-                    res[k] = make_uint4(0, 0, 0, 0);
-                    if (has_res && real[0])
-                        res[k] = __ldg(reinterpret_cast<const uint4*>(
-                            p.residual + ((size_t)(n_tile * (NT / 8) + k) * p.out_rows + (size_t)(p.out_row0 + mrow[0])) * 16));
+                    for (int k = 0; k < NT / 8; ++k) {
+                        res[k] = make_uint4(0, 0, 0, 0);
+                        if (has_res && real[0])
+                            res[k] = __ldg(reinterpret_cast<const uint4*>(
+                                p.residual + ((size_t)(n_tile * (NT / 8) + k) * p.out_rows + (size_t)(p.out_row0 + mrow[0])) * 16));
+                    }
                 }
+                // row / validity of tile 0 of this CTA's next work item
+                const int nwork = work + n_clusters;
+                const int ngrp = nwork / p.n_tiles, nn_tile = nwork - ngrp * p.n_tiles;
+                const long long nrow = (long long)(ngrp * CL + (int)crank) * kPairRows + row;
+                const int nrr = (int)(nrow % 110);
+                const bool nreal = nwork < total && nrow < (long long)p.n_boards * 110 && nrr >= 10 && (nrr % 10) != 9;
                 mbar_wait(&t_full[acc], tph);
                 tc_fence_after();
 #pragma unroll
                 for (int t = 0; t < 2; ++t) {
+                    if (p.dbg & 4) continue;
 #pragma unroll
                     for (int c0 = 0; c0 < NT; c0 += 32) {
                         uint32_t v[32];
@@ -566,8 +645,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv2_kernel(const GemmArgs p
                             uint4 o = make_uint4(0, 0, 0, 0);
                             if (real[t]) {
                                 float f[8];
-                                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + nn));
-                                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + nn + 4));
+                                const float4 b0 = *reinterpret_cast<const float4*>(&sBias[nn]);
+                                const float4 b1 = *reinterpret_cast<const float4*>(&sBias[nn + 4]);
                                 f[0] = __uint_as_float(v[g * 8 + 0]) + b0.x;
                                 f[1] = __uint_as_float(v[g * 8 + 1]) + b0.y;
                                 f[2] = __uint_as_float(v[g * 8 + 2]) + b0.z;
@@ -590,12 +669,16 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv2_kernel(const GemmArgs p
                                                pack_bf16(f[6], f[7]));
                             }
                             *reinterpret_cast<uint4*>(p.out + off) = o;
-                            // this register is free again: refill it with tile 1's residual
+                            // this register is free again: refill it for the tile after this one
+                            res[k] = make_uint4(0, 0, 0, 0);
                             if (t == 0) {
-                                res[k] = make_uint4(0, 0, 0, 0);
                                 if (has_res && real[1])
                                     res[k] = __ldg(reinterpret_cast<const uint4*>(
                                         p.residual + ((size_t)(nn >> 3) * p.out_rows + (size_t)(p.out_row0 + mrow[1])) * 16));
+                            } else {
+                                if (has_res && nreal)
+                                    res[k] = __ldg(reinterpret_cast<const uint4*>(
+                                        p.residual + ((size_t)(nn_tile * (NT / 8) + k) * p.out_rows + (size_t)(p.out_row0 + nrow)) * 16));
                             }
                         }
                     }
@@ -616,16 +699,356 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv2_kernel(const GemmArgs p
                         for (int g = 0; g < 4; ++g) {
                             float f[8];
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) f[e] = fmaxf(__uint_as_float(v[g * 8 + e]) + __ldg(p.bias + g * 8 + e), 0.0f);
+                            for (int e = 0; e < 8; ++e) f[e] = fmaxf(__uint_as_float(v[g * 8 + e]) + sBias[g * 8 + e], 0.0f);
                             const uint4 o = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]),
                                                        pack_bf16(f[6], f[7]));
                             *reinterpret_cast<uint4*>(p.out + ((size_t)(pos * 4 + g) * p.out_rows + (size_t)(p.out_row0 + b)) * 16) = o;
                         }
                         float4 vf;
-                        vf.x = fmaxf(__uint_as_float(v2[0]) + __ldg(p.bias + 32), 0.0f);
-                        vf.y = fmaxf(__uint_as_float(v2[1]) + __ldg(p.bias + 33), 0.0f);
-                        vf.z = fmaxf(__uint_as_float(v2[2]) + __ldg(p.bias + 34), 0.0f);
-                        vf.w = fmaxf(__uint_as_float(v2[3]) + __ldg(p.bias + 35), 0.0f);
+                        vf.x = fmaxf(__uint_as_float(v2[0]) + sBias[32], 0.0f);
+                        vf.y = fmaxf(__uint_as_float(v2[1]) + sBias[33], 0.0f);
+                        vf.z = fmaxf(__uint_as_float(v2[2]) + sBias[34], 0.0f);
+                        vf.w = fmaxf(__uint_as_float(v2[3]) + sBias[35], 0.0f);
+                        *reinterpret_cast<float4*>(p.out2 + ((size_t)b * 90 + pos) * 4) = vf;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&t_empty[acc]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (CL > 1) cluster_sync_all();                    // nobody leaves while a peer can still write to it
+    if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+template <int NT, int KCH, bool HEADS, int ABUFS, int CL>
+static int launch_conv2(xq_ctx* c, const GemmArgs& a, cudaStream_t s)
+{
+    using Cfg = Conv2Cfg<NT, KCH, HEADS, ABUFS>;
+    const int smem = Cfg::smem_bytes(a.kchunks);
+    static bool configured = false;
+    auto kern = conv2_kernel<NT, KCH, HEADS, ABUFS, CL>;
+    if (!configured) {
+        XQ_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));   // + 1 KB static (bias)
+        configured = true;
+    }
+    if (smem > 225 * 1024) return xq_fail(c, XQ_ERR_ARG, "conv2 kernel needs %d bytes of shared memory", smem);
+    const int groups = (((a.m_tiles + 1) / 2) + CL - 1) / CL;
+    const int total = groups * a.n_tiles;
+    int clusters = c->sm_count / CL;                           // persistent: one CTA per SM, whole clusters only
+    if (clusters > total) clusters = total;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(clusters * CL);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = CL > 1 ? 1 : 0;
+    XQ_CUDA(c, cudaLaunchKernelEx(&cfg, kern, a));
+    c->launches += 1;
+    return XQ_OK;
+}
+
+// =============================================================================================
+// v4 conv kernel: deep weight ring + rolling A segments
+// =============================================================================================
+// Measured on v2/v3 (XQ_NET_DBG experiments, profiles/r1_net_notes.md): a weight stage cannot be refilled
+// before the MMAs that read it have completed, and that completion -> refill -> MMA-issue round trip is
+// ~1.5-2.5 us.  A 4-stage ring holds only ~1.2 us of MMA work, so the tensor pipe idled ~55 % of the time no
+// matter how cheap the copies or the epilogue were.  v4 keeps the tile-pair scheme and
+//   * splits the resident A block into per-k-block SEGMENTS with their own full/empty barriers and walks
+//     k-blocks in the OUTER loop, so a segment is released after its 9 taps and re-filled with the next
+//     pair's rows while the other k-block computes -- A needs one buffer instead of two;
+//   * spends the freed shared memory on a 9-deep weight ring (2.6 us of MMA work in flight);
+//   * lets one stage carry several taps (TPS) when a tap is tiny (15-plane input conv: all 9 taps, 36 KB).
+constexpr int kMaxStages4 = 9;
+constexpr int kMaxSeg4 = 4;
+
+template <int NT, int KCH, bool HEADS, int TPS>
+struct Conv4Cfg {
+    static constexpr int kWTap = KCH * NT * 16;                // bytes of one (tap, k-block) weight slice
+    static constexpr int kWStage = TPS * kWTap;
+    static constexpr int kSeg = KCH * kAPlane2;                // bytes of one A segment (one k-block, 278 rows)
+    static constexpr int kTileCols = NT > 64 ? 128 : 64;
+    static constexpr int kTmemCols = 4 * kTileCols;
+    static constexpr int kTaps = HEADS ? 1 : 9;
+    static constexpr int kBudget = 225 * 1024 - 1024 - 512;    // dynamic smem minus static bias minus barriers
+    static int stages(int kchunks)
+    {
+        int st = (kBudget - (kchunks / KCH) * kSeg) / kWStage;
+        return st > kMaxStages4 ? kMaxStages4 : st;
+    }
+    static int smem_bytes(int kchunks)
+    {
+        int total = (kchunks / KCH) * kSeg + stages(kchunks) * kWStage + 512;
+        return total < 120 * 1024 ? 120 * 1024 : total;        // one CTA per SM: it owns all of TMEM
+    }
+};
+
+template <int NT, int KCH, bool HEADS, int TPS>
+__global__ void __launch_bounds__(kGemmThreads, 1) conv4_kernel(const GemmArgs p, const int S)
+{
+    using Cfg = Conv4Cfg<NT, KCH, HEADS, TPS>;
+    constexpr int TS = Cfg::kTileCols;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int kblocks = p.kchunks / KCH;
+    uint8_t* sA = smem;                                         // [kblocks][KCH][278][16 B]
+    uint8_t* sStage = smem + kblocks * Cfg::kSeg;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + S * Cfg::kWStage);
+    uint64_t* w_full = bars;                                    // [kMaxStages4]
+    uint64_t* w_empty = bars + kMaxStages4;
+    uint64_t* a_full = bars + 2 * kMaxStages4;                  // [kMaxSeg4]
+    uint64_t* a_empty = a_full + kMaxSeg4;
+    uint64_t* t_full = a_empty + kMaxSeg4;                      // [2]
+    uint64_t* t_empty = t_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tap_groups = Cfg::kTaps / TPS;
+    const int m_pairs = (p.m_tiles + 1) / 2;
+    const int total = m_pairs * p.n_tiles;
+
+    __shared__ __align__(16) float sBias[256];
+    for (int i = threadIdx.x; i < p.n_tiles * NT && i < 256; i += kGemmThreads) sBias[i] = p.bias[i];
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < S; ++i) {
+            mbar_init(&w_full[i], 1);
+            mbar_init(&w_empty[i], 1);
+        }
+        for (int i = 0; i < kblocks; ++i) {
+            mbar_init(&a_full[i], 1);
+            mbar_init(&a_empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&t_full[i], 1);
+            mbar_init(&t_empty[i], 4);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, Cfg::kTmemCols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            int n = 0;
+            for (int work = blockIdx.x; work < total; work += gridDim.x, ++n) {
+                const int pair = work / p.n_tiles, n_tile = work - pair * p.n_tiles;
+                const long long m0 = (long long)pair * kPairRows;
+                const uint8_t* wt = p.w + (size_t)n_tile * Cfg::kTaps * kblocks * Cfg::kWTap;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&a_empty[kb], (uint32_t)(n & 1) ^ 1u);
+                    mbar_expect_tx(&a_full[kb], (uint32_t)Cfg::kSeg);
+#pragma unroll
+                    for (int c = 0; c < KCH; ++c)
+                        bulk_g2s(sA + kb * Cfg::kSeg + c * kAPlane2,
+                                 p.a + ((size_t)(kb * KCH + c) * p.a_rows + (size_t)(p.a_row0 + m0 - kHalo)) * 16, kAPlane2,
+                                 &a_full[kb]);
+                    for (int tg = 0; tg < tap_groups; ++tg) {
+                        mbar_wait(&w_empty[s], ph ^ 1);
+                        mbar_expect_tx(&w_full[s], Cfg::kWStage);
+                        // host image order is [tap][k_block]; with TPS > 1 there is a single k-block and taps are contiguous
+                        bulk_g2s(sStage + s * Cfg::kWStage, wt + (size_t)((tg * TPS) * kblocks + kb) * Cfg::kWTap, Cfg::kWStage,
+                                 &w_full[s]);
+                        if (++s == S) { s = 0; ph ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(128, NT);
+            constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);            // SBO = 128 B, version 1
+            constexpr uint32_t kLboA = (uint32_t)(kAPlane2 >> 4);
+            int s = 0;
+            uint32_t ph = 0;
+            int n = 0;
+            for (int work = blockIdx.x; work < total; work += gridDim.x, ++n) {
+                const int acc = n & 1;
+                const uint32_t tph = (uint32_t)(n >> 1) & 1u;
+                mbar_wait(&t_empty[acc], tph ^ 1);
+                tc_fence_after();
+                const uint32_t d_addr = tmem_base + (uint32_t)(acc * 2 * TS);
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&a_full[kb], (uint32_t)(n & 1));
+                    const uint32_t a_seg = (((smem_u32(sA + kb * Cfg::kSeg)) >> 4) & 0x3FFFu) | (kLboA << 16);
+                    for (int tg = 0; tg < tap_groups; ++tg) {
+                        mbar_wait(&w_full[s], ph);
+                        tc_fence_after();
+                        const uint32_t b_st = ((smem_u32(sStage + s * Cfg::kWStage) >> 4) & 0x3FFFu) | ((uint32_t)((NT * 16) >> 4) << 16);
+#pragma unroll
+                        for (int tp = 0; tp < TPS; ++tp) {
+                            const int tap = tg * TPS + tp;
+                            const int shift = HEADS ? 0 : ((tap / 3) - 1) * 10 + (tap % 3) - 1;
+                            const uint32_t a_lo = a_seg + (uint32_t)(kHalo + shift);
+                            const uint32_t b_lo = b_st + (uint32_t)(tp * (Cfg::kWTap >> 4));
+                            const uint32_t first = (kb | tap) != 0 ? 1u : 0u;
+#pragma unroll
+                            for (int t = 0; t < 2; ++t) {
+#pragma unroll
+                                for (int j = 0; j < KCH / 2; ++j) {
+                                    const uint64_t adesc = ((uint64_t)kDescHi << 32) | (uint64_t)(a_lo + (uint32_t)(2 * j) * kLboA + (uint32_t)(t * 128));
+                                    const uint64_t bdesc = ((uint64_t)kDescHi << 32) | (uint64_t)(b_lo + (uint32_t)(2 * j * NT));
+                                    umma_bf16(d_addr + (uint32_t)(t * TS), adesc, bdesc, idesc, j == 0 ? first : 1u);
+                                }
+                            }
+                        }
+                        umma_commit(&w_empty[s]);
+                        if (++s == S) { s = 0; ph ^= 1; }
+                    }
+                    umma_commit(&a_empty[kb]);                  // this k-block's rows may be replaced by the next pair's
+                }
+                umma_commit(&t_full[acc]);
+            }
+        }
+    } else {
+        // ===================== epilogue =====================
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        int n = 0;
+        uint4 res[NT / 8];
+        for (int work = blockIdx.x; work < total; work += gridDim.x, ++n) {
+            const int pair = work / p.n_tiles, n_tile = work - pair * p.n_tiles;
+            const int acc = n & 1;
+            const uint32_t tph = (uint32_t)(n >> 1) & 1u;
+            const long long mrow[2] = {(long long)pair * kPairRows + row, (long long)pair * kPairRows + 128 + row};
+            bool real[2];
+            int rr[2];
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                rr[t] = (int)(mrow[t] % 110);
+                real[t] = mrow[t] < (long long)p.n_boards * 110 && rr[t] >= 10 && (rr[t] % 10) != 9;
+            }
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 * TS);
+
+            if (!HEADS) {
+                const bool has_res = p.residual != nullptr;
+                if (n == 0) {
+#pragma unroll
+                    for (int k = 0; k < NT / 8; ++k) {
+                        res[k] = make_uint4(0, 0, 0, 0);
+                        if (has_res && real[0])
+                            res[k] = __ldg(reinterpret_cast<const uint4*>(
+                                p.residual + ((size_t)(n_tile * (NT / 8) + k) * p.out_rows + (size_t)(p.out_row0 + mrow[0])) * 16));
+                    }
+                }
+                const int nwork = work + gridDim.x;
+                const int npair = nwork / p.n_tiles, nn_tile = nwork - npair * p.n_tiles;
+                const long long nrow = (long long)npair * kPairRows + row;
+                const int nrr = (int)(nrow % 110);
+                const bool nreal = nwork < total && nrow < (long long)p.n_boards * 110 && nrr >= 10 && (nrr % 10) != 9;
+                mbar_wait(&t_full[acc], tph);
+                tc_fence_after();
+                // one 32-column slab: bias (+residual) (+ReLU), halo rows -> 0, bf16, 4 coalesced 16-byte stores
+                auto emit = [&](const uint32_t* v, const int t, const int c0) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const int k = c0 / 8 + g;
+                        const int nn = n_tile * NT + c0 + g * 8;
+                        const size_t off = ((size_t)(nn >> 3) * p.out_rows + (size_t)(p.out_row0 + mrow[t])) * 16;
+                        uint4 o = make_uint4(0, 0, 0, 0);
+                        if (real[t]) {
+                            float f[8];
+                            const float4 b0 = *reinterpret_cast<const float4*>(&sBias[nn]);
+                            const float4 b1 = *reinterpret_cast<const float4*>(&sBias[nn + 4]);
+                            f[0] = __uint_as_float(v[g * 8 + 0]) + b0.x;
+                            f[1] = __uint_as_float(v[g * 8 + 1]) + b0.y;
+                            f[2] = __uint_as_float(v[g * 8 + 2]) + b0.z;
+                            f[3] = __uint_as_float(v[g * 8 + 3]) + b0.w;
+                            f[4] = __uint_as_float(v[g * 8 + 4]) + b1.x;
+                            f[5] = __uint_as_float(v[g * 8 + 5]) + b1.y;
+                            f[6] = __uint_as_float(v[g * 8 + 6]) + b1.z;
+                            f[7] = __uint_as_float(v[g * 8 + 7]) + b1.w;
+                            const uint32_t rw[4] = {res[k].x, res[k].y, res[k].z, res[k].w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                f[2 * e] += __uint_as_float(rw[e] << 16);
+                                f[2 * e + 1] += __uint_as_float(rw[e] & 0xffff0000u);
+                            }
+                            if (p.relu) {
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.0f);
+                            }
+                            o = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+                        }
+                        *reinterpret_cast<uint4*>(p.out + off) = o;
+                        res[k] = make_uint4(0, 0, 0, 0);      // refill for the tile after this one
+                        if (t == 0) {
+                            if (has_res && real[1])
+                                res[k] = __ldg(reinterpret_cast<const uint4*>(
+                                    p.residual + ((size_t)(nn >> 3) * p.out_rows + (size_t)(p.out_row0 + mrow[1])) * 16));
+                        } else {
+                            if (has_res && nreal)
+                                res[k] = __ldg(reinterpret_cast<const uint4*>(
+                                    p.residual + ((size_t)(nn_tile * (NT / 8) + k) * p.out_rows + (size_t)(p.out_row0 + nrow)) * 16));
+                        }
+                    }
+                };
+                if (!(p.dbg & 4)) {
+                    // software pipeline over the 2 x NT/32 slabs: the TMEM load of slab i+1 is in flight while slab i
+                    // is converted and stored (tcgen05.wait::ld waits for ALL outstanding loads, so it sits after emit)
+                    constexpr int kSlabs = 2 * (NT / 32);
+                    uint32_t va[32], vb[32];
+                    tmem_ld32(taddr, va);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < kSlabs; ++i) {
+                        const int t = i / (NT / 32), c0 = (i % (NT / 32)) * 32;
+                        const int tn = (i + 1) / (NT / 32), cn = ((i + 1) % (NT / 32)) * 32;
+                        if (i & 1) {
+                            if (i + 1 < kSlabs) tmem_ld32(taddr + (uint32_t)(tn * TS + cn), va);
+                            emit(vb, t, c0);
+                        } else {
+                            if (i + 1 < kSlabs) tmem_ld32(taddr + (uint32_t)(tn * TS + cn), vb);
+                            emit(va, t, c0);
+                        }
+                        if (i + 1 < kSlabs) tmem_ld_wait();
+                    }
+                }
+            } else {
+                mbar_wait(&t_full[acc], tph);
+                tc_fence_after();
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    const long long b = mrow[t] / 110;
+                    const int pos = (rr[t] / 10 - 1) * 9 + (rr[t] % 10);
+                    uint32_t v[32], v2[16];
+                    tmem_ld32(taddr + (uint32_t)(t * TS), v);
+                    tmem_ld16(taddr + (uint32_t)(t * TS + 32), v2);
+                    tmem_ld_wait();
+                    if (real[t]) {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            float f[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) f[e] = fmaxf(__uint_as_float(v[g * 8 + e]) + sBias[g * 8 + e], 0.0f);
+                            const uint4 o = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]),
+                                                       pack_bf16(f[6], f[7]));
+                            *reinterpret_cast<uint4*>(p.out + ((size_t)(pos * 4 + g) * p.out_rows + (size_t)(p.out_row0 + b)) * 16) = o;
+                        }
+                        float4 vf;
+                        vf.x = fmaxf(__uint_as_float(v2[0]) + sBias[32], 0.0f);
+                        vf.y = fmaxf(__uint_as_float(v2[1]) + sBias[33], 0.0f);
+                        vf.z = fmaxf(__uint_as_float(v2[2]) + sBias[34], 0.0f);
+                        vf.w = fmaxf(__uint_as_float(v2[3]) + sBias[35], 0.0f);
                         *reinterpret_cast<float4*>(p.out2 + ((size_t)b * 90 + pos) * 4) = vf;
                     }
                 }
@@ -641,20 +1064,24 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv2_kernel(const GemmArgs p
     if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
 }
 
-template <int NT, int KCH, bool HEADS, int ABUFS>
-static int launch_conv2(xq_ctx* c, const GemmArgs& a, cudaStream_t s)
+template <int NT, int KCH, bool HEADS, int TPS>
+static int launch_conv4(xq_ctx* c, const GemmArgs& a, cudaStream_t s)
 {
-    using Cfg = Conv2Cfg<NT, KCH, HEADS, ABUFS>;
+    using Cfg = Conv4Cfg<NT, KCH, HEADS, TPS>;
+    const int kblocks = a.kchunks / KCH;
+    const int S = Cfg::stages(a.kchunks);
+    if (kblocks > kMaxSeg4 || S < 2) return xq_fail(c, XQ_ERR_ARG, "conv4 kernel: %d k-blocks, %d stages do not fit", kblocks, S);
     const int smem = Cfg::smem_bytes(a.kchunks);
     static bool configured = false;
+    auto kern = conv4_kernel<NT, KCH, HEADS, TPS>;
     if (!configured) {
-        XQ_CUDA(c, cudaFuncSetAttribute(conv2_kernel<NT, KCH, HEADS, ABUFS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        XQ_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
         configured = true;
     }
-    if (smem > 227 * 1024) return xq_fail(c, XQ_ERR_ARG, "conv2 kernel needs %d bytes of shared memory", smem);
     const int total = ((a.m_tiles + 1) / 2) * a.n_tiles;
-    int grid = c->sm_count < total ? c->sm_count : total;     // persistent, one CTA per SM
-    conv2_kernel<NT, KCH, HEADS, ABUFS><<<grid, kGemmThreads, smem, s>>>(a);
+    const int grid = c->sm_count < total ? c->sm_count : total;   // persistent, one CTA per SM
+    if (getenv("XQ_DEBUG")) fprintf(stderr, "[xq] conv4<%d,%d,%d,%d> stages=%d smem=%d grid=%d\n", NT, KCH, (int)HEADS, TPS, S, smem, grid);
+    kern<<<grid, kGemmThreads, smem, s>>>(a, S);
     c->launches += 1;
     XQ_CUDA(c, cudaGetLastError());
     return XQ_OK;
@@ -761,14 +1188,28 @@ extern "C" int xq_net_gemm(xq_ctx* c, const xq_gemm_desc* d, void* stream)
     a.residual = (const uint8_t*)d->residual;
     a.out = (uint8_t*)d->out;
     a.out2 = (float*)d->out2;
+    a.dbg = getenv("XQ_NET_DBG") ? atoi(getenv("XQ_NET_DBG")) : 0;
     cudaStream_t s = (cudaStream_t)stream;
     XqTimer tm(c, s);
     const bool v1 = c->net_v1;
-    if (!v1 && d->mode == 0 && d->nt == 128 && d->kch_iter == 8 && d->kchunks % 8 == 0 && d->kchunks <= 16) return launch_conv2<128, 8, false, 2>(c, a, s);
-    if (!v1 && d->mode == 0 && d->nt == 128 && d->kch_iter == 8 && d->kchunks % 8 == 0 && d->kchunks <= 32) return launch_conv2<128, 8, false, 1>(c, a, s);
-    if (!v1 && d->mode == 0 && d->nt == 128 && d->kch_iter == 2 && d->kchunks == 2) return launch_conv2<128, 2, false, 2>(c, a, s);
-    if (!v1 && d->mode == 1 && d->nt == 48 && d->kch_iter == 8 && d->kchunks % 8 == 0 && d->kchunks <= 16 && d->out2) return launch_conv2<48, 8, true, 2>(c, a, s);
-    if (!v1 && d->mode == 1 && d->nt == 48 && d->kch_iter == 8 && d->kchunks % 8 == 0 && d->kchunks <= 32 && d->out2) return launch_conv2<48, 8, true, 1>(c, a, s);
+    const int cl = c->net_cluster;
+    if (!v1 && c->net_gen >= 4) {
+        if (d->mode == 0 && d->nt == 128 && d->kch_iter == 8 && d->kchunks % 8 == 0 && d->kchunks <= 32) return launch_conv4<128, 8, false, 1>(c, a, s);
+        if (d->mode == 0 && d->nt == 128 && d->kch_iter == 2 && d->kchunks == 2) return launch_conv4<128, 2, false, 9>(c, a, s);
+        if (d->mode == 1 && d->nt == 48 && d->kch_iter == 8 && d->kchunks % 8 == 0 && d->kchunks <= 32 && d->out2) return launch_conv4<48, 8, true, 1>(c, a, s);
+    }
+    if (!v1 && d->mode == 0 && d->nt == 128 && d->kch_iter == 8 && d->kchunks % 8 == 0 && d->kchunks <= 16) {
+        if (cl == 4) return launch_conv2<128, 8, false, 2, 4>(c, a, s);
+        if (cl == 2) return launch_conv2<128, 8, false, 2, 2>(c, a, s);
+        return launch_conv2<128, 8, false, 2, 1>(c, a, s);
+    }
+    if (!v1 && d->mode == 0 && d->nt == 128 && d->kch_iter == 8 && d->kchunks % 8 == 0 && d->kchunks <= 32) {
+        if (cl >= 2) return launch_conv2<128, 8, false, 1, 2>(c, a, s);
+        return launch_conv2<128, 8, false, 1, 1>(c, a, s);
+    }
+    if (!v1 && d->mode == 0 && d->nt == 128 && d->kch_iter == 2 && d->kchunks == 2) return launch_conv2<128, 2, false, 2, 1>(c, a, s);
+    if (!v1 && d->mode == 1 && d->nt == 48 && d->kch_iter == 8 && d->kchunks % 8 == 0 && d->kchunks <= 16 && d->out2) return launch_conv2<48, 8, true, 2, 1>(c, a, s);
+    if (!v1 && d->mode == 1 && d->nt == 48 && d->kch_iter == 8 && d->kchunks % 8 == 0 && d->kchunks <= 32 && d->out2) return launch_conv2<48, 8, true, 1, 1>(c, a, s);
     if (d->mode == 0 && d->nt == 128 && d->kch_iter == 8 && d->kchunks % 8 == 0) return launch_gemm<0, 128, 8>(c, a, s);
     if (d->mode == 0 && d->nt == 128 && d->kch_iter == 2 && d->kchunks == 2) return launch_gemm<0, 128, 2>(c, a, s);
     if (d->mode == 1 && d->nt == 48 && d->kch_iter == 8 && d->kchunks % 8 == 0 && d->out2) return launch_gemm<1, 48, 8>(c, a, s);
@@ -800,4 +1241,60 @@ extern "C" int xq_net_run(xq_ctx* c, const xq_gemm_desc* layers, int n_layers, c
         if (rc) return rc;
     }
     return xq_net_value_head(c, d_vfeats, d_w1t, d_b1, d_w2, b2, d_value, B, stream);
+}
+
+// ---- micro-benchmark: issue rate of SS-mode tcgen05.mma from resident no-swizzle operands ----------
+namespace xq {
+template <int NT>
+__global__ void __launch_bounds__(128) umma_rate_kernel(long long* out, int n_mma, int a_stride_rows)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t slot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < 96 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    if (warp == 0) { tmem_alloc(&slot, 512); tmem_relinquish(); }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tb = slot;
+    if (warp == 1 && lane == 0) {
+        constexpr uint32_t idesc = make_idesc(128, NT);
+        const uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem + 48 * 1024);
+        long long t0 = clock64();
+        for (int i = 0; i < n_mma; ++i) {
+            const int j = i & 3, t = (i >> 2) & 1;
+            const uint64_t ad = make_desc(a0 + (uint32_t)(2 * j * 4448 + (t * 128 + (i % 9)) * 16), 4448, 128);
+            const uint64_t bd = make_desc(b0 + (uint32_t)(2 * j * NT * 16), NT * 16, 128);
+            umma_bf16(tb + (uint32_t)(t * NT), ad, bd, idesc, 1u);
+        }
+        umma_commit(&bar);
+        mbar_wait(&bar, 0);
+        long long t1 = clock64();
+        out[blockIdx.x] = t1 - t0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tb, 512);
+}
+}  // namespace xq
+
+extern "C" int xq_debug_umma_rate(xq_ctx* c, int nt, int n_mma, int grid, long long* h_cycles)
+{
+    long long* d = nullptr;
+    XQ_CUDA(c, cudaMalloc(&d, sizeof(long long) * grid));
+    XQ_CUDA(c, cudaMemset(d, 0, sizeof(long long) * grid));
+    if (nt == 128) {
+        XQ_CUDA(c, cudaFuncSetAttribute(xq::umma_rate_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        xq::umma_rate_kernel<128><<<grid, 128, 120 * 1024>>>(d, n_mma, 0);
+    } else {
+        XQ_CUDA(c, cudaFuncSetAttribute(xq::umma_rate_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        xq::umma_rate_kernel<256><<<grid, 128, 120 * 1024>>>(d, n_mma, 0);
+    }
+    XQ_CUDA(c, cudaDeviceSynchronize());
+    XQ_CUDA(c, cudaMemcpy(h_cycles, d, sizeof(long long) * grid, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    return XQ_OK;
 }

@@ -134,7 +134,8 @@ class B200Net:
         self.C, self.R = Cc, R
         B = self.max_batch
         self.m_tiles = (B * 110 + 127) // 128
-        self.rows = ROW0 + ((self.m_tiles + 1) // 2) * 256 + 16   # conv kernels work on pairs of 128-row tiles
+        pairs = (self.m_tiles + 1) // 2                            # conv kernels work on pairs of 128-row tiles,
+        self.rows = ROW0 + ((pairs + 3) // 4) * 4 * 256 + 16       # clusters of up to 4 CTAs on 4 consecutive pairs
         self.b_tiles = (B + 127) // 128
         self.fc_rows = self.b_tiles * 128
         bf = torch.bfloat16
