@@ -770,6 +770,7 @@ static int launch_conv2(xq_ctx* c, const GemmArgs& a, cudaStream_t s)
 //     pair's rows while the other k-block computes -- A needs one buffer instead of two;
 //   * spends the freed shared memory on a 9-deep weight ring (2.6 us of MMA work in flight);
 //   * lets one stage carry several taps (TPS) when a tap is tiny (15-plane input conv: all 9 taps, 36 KB).
+constexpr int kConv4Threads = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
 constexpr int kMaxStages4 = 9;
 constexpr int kMaxSeg4 = 4;
 
@@ -795,7 +796,7 @@ struct Conv4Cfg {
 };
 
 template <int NT, int KCH, bool HEADS, int TPS>
-__global__ void __launch_bounds__(kGemmThreads, 1) conv4_kernel(const GemmArgs p, const int S)
+__global__ void __launch_bounds__(kConv4Threads, 1) conv4_kernel(const GemmArgs p, const int S)
 {
     using Cfg = Conv4Cfg<NT, KCH, HEADS, TPS>;
     constexpr int TS = Cfg::kTileCols;
@@ -818,7 +819,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv4_kernel(const GemmArgs p
     const int total = m_pairs * p.n_tiles;
 
     __shared__ __align__(16) float sBias[256];
-    for (int i = threadIdx.x; i < p.n_tiles * NT && i < 256; i += kGemmThreads) sBias[i] = p.bias[i];
+    for (int i = threadIdx.x; i < p.n_tiles * NT && i < 256; i += kConv4Threads) sBias[i] = p.bias[i];
     if (threadIdx.x == 0) {
         for (int i = 0; i < S; ++i) {
             mbar_init(&w_full[i], 1);
@@ -830,7 +831,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv4_kernel(const GemmArgs p
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&t_full[i], 1);
-            mbar_init(&t_empty[i], 4);
+            mbar_init(&t_empty[i], 8);                 // 8 epilogue warps: 4 lane quarters x 2 row tiles
         }
         mbar_fence_init();
     }
@@ -920,8 +921,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv4_kernel(const GemmArgs p
             }
         }
     } else {
-        // ===================== epilogue =====================
-        const int q = warp & 3;
+        // ===================== epilogue: 8 warps, warp -> (row tile t, TMEM lane quarter q) =====================
+        const int q = warp & 3;                          // a warp may only read TMEM lanes 32*(warp%4) ..
+        const int t = (warp - 2) >> 2;                   // warps 2-5: tile 0, warps 6-9: tile 1
         const int row = q * 32 + lane;
         int n = 0;
         uint4 res[NT / 8];
@@ -929,43 +931,40 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv4_kernel(const GemmArgs p
             const int pair = work / p.n_tiles, n_tile = work - pair * p.n_tiles;
             const int acc = n & 1;
             const uint32_t tph = (uint32_t)(n >> 1) & 1u;
-            const long long mrow[2] = {(long long)pair * kPairRows + row, (long long)pair * kPairRows + 128 + row};
-            bool real[2];
-            int rr[2];
-#pragma unroll
-            for (int t = 0; t < 2; ++t) {
-                rr[t] = (int)(mrow[t] % 110);
-                real[t] = mrow[t] < (long long)p.n_boards * 110 && rr[t] >= 10 && (rr[t] % 10) != 9;
-            }
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 * TS);
+            const long long mrow = (long long)pair * kPairRows + t * 128 + row;
+            const int rr = (int)(mrow % 110);
+            const bool real = mrow < (long long)p.n_boards * 110 && rr >= 10 && (rr % 10) != 9;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 * TS + t * TS);
 
             if (!HEADS) {
+                // Residual operand: res[k] always holds the values of this warp's NEXT tile; loaded before the
+                // first wait, then refilled slab by slab for the next work item, i.e. a whole pair (~5 us) ahead.
                 const bool has_res = p.residual != nullptr;
                 if (n == 0) {
 #pragma unroll
                     for (int k = 0; k < NT / 8; ++k) {
                         res[k] = make_uint4(0, 0, 0, 0);
-                        if (has_res && real[0])
+                        if (has_res && real)
                             res[k] = __ldg(reinterpret_cast<const uint4*>(
-                                p.residual + ((size_t)(n_tile * (NT / 8) + k) * p.out_rows + (size_t)(p.out_row0 + mrow[0])) * 16));
+                                p.residual + ((size_t)(n_tile * (NT / 8) + k) * p.out_rows + (size_t)(p.out_row0 + mrow)) * 16));
                     }
                 }
                 const int nwork = work + gridDim.x;
                 const int npair = nwork / p.n_tiles, nn_tile = nwork - npair * p.n_tiles;
-                const long long nrow = (long long)npair * kPairRows + row;
+                const long long nrow = (long long)npair * kPairRows + t * 128 + row;
                 const int nrr = (int)(nrow % 110);
                 const bool nreal = nwork < total && nrow < (long long)p.n_boards * 110 && nrr >= 10 && (nrr % 10) != 9;
                 mbar_wait(&t_full[acc], tph);
                 tc_fence_after();
                 // one 32-column slab: bias (+residual) (+ReLU), halo rows -> 0, bf16, 4 coalesced 16-byte stores
-                auto emit = [&](const uint32_t* v, const int t, const int c0) {
+                auto emit = [&](const uint32_t* v, const int c0) {
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
                         const int k = c0 / 8 + g;
                         const int nn = n_tile * NT + c0 + g * 8;
-                        const size_t off = ((size_t)(nn >> 3) * p.out_rows + (size_t)(p.out_row0 + mrow[t])) * 16;
+                        const size_t off = ((size_t)(nn >> 3) * p.out_rows + (size_t)(p.out_row0 + mrow)) * 16;
                         uint4 o = make_uint4(0, 0, 0, 0);
-                        if (real[t]) {
+                        if (real) {
                             float f[8];
                             const float4 b0 = *reinterpret_cast<const float4*>(&sBias[nn]);
                             const float4 b1 = *reinterpret_cast<const float4*>(&sBias[nn + 4]);
@@ -990,35 +989,27 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv4_kernel(const GemmArgs p
                             o = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
                         }
                         *reinterpret_cast<uint4*>(p.out + off) = o;
-                        res[k] = make_uint4(0, 0, 0, 0);      // refill for the tile after this one
-                        if (t == 0) {
-                            if (has_res && real[1])
-                                res[k] = __ldg(reinterpret_cast<const uint4*>(
-                                    p.residual + ((size_t)(nn >> 3) * p.out_rows + (size_t)(p.out_row0 + mrow[1])) * 16));
-                        } else {
-                            if (has_res && nreal)
-                                res[k] = __ldg(reinterpret_cast<const uint4*>(
-                                    p.residual + ((size_t)(nn_tile * (NT / 8) + k) * p.out_rows + (size_t)(p.out_row0 + nrow)) * 16));
-                        }
+                        res[k] = make_uint4(0, 0, 0, 0);
+                        if (has_res && nreal)
+                            res[k] = __ldg(reinterpret_cast<const uint4*>(
+                                p.residual + ((size_t)(nn_tile * (NT / 8) + k) * p.out_rows + (size_t)(p.out_row0 + nrow)) * 16));
                     }
                 };
                 if (!(p.dbg & 4)) {
-                    // software pipeline over the 2 x NT/32 slabs: the TMEM load of slab i+1 is in flight while slab i
-                    // is converted and stored (tcgen05.wait::ld waits for ALL outstanding loads, so it sits after emit)
-                    constexpr int kSlabs = 2 * (NT / 32);
+                    // software pipeline over the NT/32 slabs: the TMEM load of slab i+1 is in flight while slab i is
+                    // converted and stored (tcgen05.wait::ld waits for ALL outstanding loads, so it follows emit)
+                    constexpr int kSlabs = NT / 32;
                     uint32_t va[32], vb[32];
                     tmem_ld32(taddr, va);
                     tmem_ld_wait();
 #pragma unroll
                     for (int i = 0; i < kSlabs; ++i) {
-                        const int t = i / (NT / 32), c0 = (i % (NT / 32)) * 32;
-                        const int tn = (i + 1) / (NT / 32), cn = ((i + 1) % (NT / 32)) * 32;
                         if (i & 1) {
-                            if (i + 1 < kSlabs) tmem_ld32(taddr + (uint32_t)(tn * TS + cn), va);
-                            emit(vb, t, c0);
+                            if (i + 1 < kSlabs) tmem_ld32(taddr + (uint32_t)((i + 1) * 32), va);
+                            emit(vb, i * 32);
                         } else {
-                            if (i + 1 < kSlabs) tmem_ld32(taddr + (uint32_t)(tn * TS + cn), vb);
-                            emit(va, t, c0);
+                            if (i + 1 < kSlabs) tmem_ld32(taddr + (uint32_t)((i + 1) * 32), vb);
+                            emit(va, i * 32);
                         }
                         if (i + 1 < kSlabs) tmem_ld_wait();
                     }
@@ -1026,31 +1017,28 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv4_kernel(const GemmArgs p
             } else {
                 mbar_wait(&t_full[acc], tph);
                 tc_fence_after();
+                const long long b = mrow / 110;
+                const int pos = (rr / 10 - 1) * 9 + (rr % 10);
+                uint32_t v[32], v2[16];
+                tmem_ld32(taddr, v);
+                tmem_ld16(taddr + 32u, v2);
+                tmem_ld_wait();
+                if (real) {
 #pragma unroll
-                for (int t = 0; t < 2; ++t) {
-                    const long long b = mrow[t] / 110;
-                    const int pos = (rr[t] / 10 - 1) * 9 + (rr[t] % 10);
-                    uint32_t v[32], v2[16];
-                    tmem_ld32(taddr + (uint32_t)(t * TS), v);
-                    tmem_ld16(taddr + (uint32_t)(t * TS + 32), v2);
-                    tmem_ld_wait();
-                    if (real[t]) {
+                    for (int g = 0; g < 4; ++g) {
+                        float f[8];
 #pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            float f[8];
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) f[e] = fmaxf(__uint_as_float(v[g * 8 + e]) + sBias[g * 8 + e], 0.0f);
-                            const uint4 o = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]),
-                                                       pack_bf16(f[6], f[7]));
-                            *reinterpret_cast<uint4*>(p.out + ((size_t)(pos * 4 + g) * p.out_rows + (size_t)(p.out_row0 + b)) * 16) = o;
-                        }
-                        float4 vf;
-                        vf.x = fmaxf(__uint_as_float(v2[0]) + sBias[32], 0.0f);
-                        vf.y = fmaxf(__uint_as_float(v2[1]) + sBias[33], 0.0f);
-                        vf.z = fmaxf(__uint_as_float(v2[2]) + sBias[34], 0.0f);
-                        vf.w = fmaxf(__uint_as_float(v2[3]) + sBias[35], 0.0f);
-                        *reinterpret_cast<float4*>(p.out2 + ((size_t)b * 90 + pos) * 4) = vf;
+                        for (int e = 0; e < 8; ++e) f[e] = fmaxf(__uint_as_float(v[g * 8 + e]) + sBias[g * 8 + e], 0.0f);
+                        const uint4 o = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]),
+                                                   pack_bf16(f[6], f[7]));
+                        *reinterpret_cast<uint4*>(p.out + ((size_t)(pos * 4 + g) * p.out_rows + (size_t)(p.out_row0 + b)) * 16) = o;
                     }
+                    float4 vf;
+                    vf.x = fmaxf(__uint_as_float(v2[0]) + sBias[32], 0.0f);
+                    vf.y = fmaxf(__uint_as_float(v2[1]) + sBias[33], 0.0f);
+                    vf.z = fmaxf(__uint_as_float(v2[2]) + sBias[34], 0.0f);
+                    vf.w = fmaxf(__uint_as_float(v2[3]) + sBias[35], 0.0f);
+                    *reinterpret_cast<float4*>(p.out2 + ((size_t)b * 90 + pos) * 4) = vf;
                 }
             }
             tc_fence_before();
@@ -1081,7 +1069,7 @@ static int launch_conv4(xq_ctx* c, const GemmArgs& a, cudaStream_t s)
     const int total = ((a.m_tiles + 1) / 2) * a.n_tiles;
     const int grid = c->sm_count < total ? c->sm_count : total;   // persistent, one CTA per SM
     if (getenv("XQ_DEBUG")) fprintf(stderr, "[xq] conv4<%d,%d,%d,%d> stages=%d smem=%d grid=%d\n", NT, KCH, (int)HEADS, TPS, S, smem, grid);
-    kern<<<grid, kGemmThreads, smem, s>>>(a, S);
+    kern<<<grid, kConv4Threads, smem, s>>>(a, S);
     c->launches += 1;
     XQ_CUDA(c, cudaGetLastError());
     return XQ_OK;
