@@ -35,7 +35,7 @@ struct __align__(16) MovegenSmem {
 };
 
 template <bool PLANES>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 3)
 movegen_kernel(const int8_t* __restrict__ boards, const int8_t* __restrict__ sides, int B,
                int16_t* __restrict__ actions, uint8_t* __restrict__ n_moves,
                uint8_t* __restrict__ in_check, float* __restrict__ planes, int* __restrict__ overflow,
@@ -108,11 +108,10 @@ movegen_kernel(const int8_t* __restrict__ boards, const int8_t* __restrict__ sid
                 warp_sync();
                 const float turn = side == 1 ? 1.0f : 0.0f;
                 float2* out = reinterpret_cast<float2*>(planes + gi * (15 * kSquares));
-#pragma unroll 3
+                // 675 float2 per position, lane stride 32 float2 = 64 elements: (plane, square) advance without division
+                int p = 0, sq = 2 * lane;
+                if (sq >= kSquares) { sq -= kSquares; p = 1; }
                 for (int e2 = lane; e2 < 15 * kSquares / 2; e2 += 32) {
-                    const int e = 2 * e2;
-                    const int p = e / kSquares;
-                    const int sq = e - p * kSquares;
                     float2 v;
                     if (p == 14) {
                         v.x = v.y = turn;
@@ -121,6 +120,8 @@ movegen_kernel(const int8_t* __restrict__ boards, const int8_t* __restrict__ sid
                         v.y = code[sq + 1] == p ? 1.0f : 0.0f;
                     }
                     __stcs(out + e2, v);
+                    sq += 64;
+                    if (sq >= kSquares) { sq -= kSquares; ++p; }
                 }
             }
             warp_sync();

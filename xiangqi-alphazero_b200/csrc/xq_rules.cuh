@@ -119,6 +119,9 @@ struct alignas(16) WarpScratch {
     uint8_t pto[kMaxPseudo];
     int16_t actions[kMaxMoves];   // compacted legal actions, unused slots = -1
     uint8_t own_sq[96];           // own-piece squares in row-major order (phase A task table)
+    uint16_t rowocc[10];          // occupancy of each row (bit c) and
+    uint16_t colocc[10];          // of each column (bit r) of the un-moved board: ray scans become bit scans
+    uint8_t pad_[8];
 };
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
@@ -194,6 +197,82 @@ __device__ __forceinline__ bool attacked_sq(const int8_t* b, int kr, int kc, int
     return false;
 }
 
+// Same predicate as attacked_sq, with the four ray walks replaced by bit scans of the king's row and
+// column occupancy (overlay applied to the two masks): first blocker = rook/king test, second = cannon test.
+__device__ __forceinline__ bool attacked_sq_occ(const int8_t* b, const uint16_t* rowocc, const uint16_t* colocc, int kr,
+                                                int kc, int by, int from, int to, int mover)
+{
+    const int rook = 5 * by, cannon = 6 * by, horse = 4 * by, pawn = 7 * by, king = by;
+    unsigned R = rowocc[kr], Cm = colocc[kc];
+    if (from >= 0) {
+        const int fr = from / 9, fc = from - fr * 9, tr = to / 9, tc = to - tr * 9;
+        if (fr == kr) R &= ~(1u << fc);
+        if (fc == kc) Cm &= ~(1u << fr);
+        if (tr == kr) R |= 1u << tc;
+        if (tc == kc) Cm |= 1u << tr;
+    }
+    // toward smaller index: highest set bit below the king; toward larger: lowest set bit above
+    {
+        unsigned m = R & ((1u << kc) - 1u);
+        if (m) {
+            int c1 = 31 - __clz(m);
+            int p1 = cell_after(b, kr * 9 + c1, from, to, mover);
+            if (p1 == rook || p1 == king) return true;
+            m ^= 1u << c1;
+            if (m && cell_after(b, kr * 9 + 31 - __clz(m), from, to, mover) == cannon) return true;
+        }
+        m = R >> (kc + 1);
+        if (m) {
+            int c1 = kc + __ffs(m);
+            int p1 = cell_after(b, kr * 9 + c1, from, to, mover);
+            if (p1 == rook || p1 == king) return true;
+            m &= m - 1u;
+            if (m && cell_after(b, kr * 9 + kc + __ffs(m), from, to, mover) == cannon) return true;
+        }
+        m = Cm & ((1u << kr) - 1u);
+        if (m) {
+            int r1 = 31 - __clz(m);
+            int p1 = cell_after(b, r1 * 9 + kc, from, to, mover);
+            if (p1 == rook || p1 == king) return true;
+            m ^= 1u << r1;
+            if (m && cell_after(b, (31 - __clz(m)) * 9 + kc, from, to, mover) == cannon) return true;
+        }
+        m = Cm >> (kr + 1);
+        if (m) {
+            int r1 = kr + __ffs(m);
+            int p1 = cell_after(b, r1 * 9 + kc, from, to, mover);
+            if (p1 == rook || p1 == king) return true;
+            m &= m - 1u;
+            if (m && cell_after(b, (kr + __ffs(m)) * 9 + kc, from, to, mover) == cannon) return true;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int jr = (i < 4) ? ((i < 2) ? -2 : 2) : ((i < 6) ? -1 : 1);
+        const int jc = (i < 4) ? ((i & 1) ? 1 : -1) : ((i & 1) ? 2 : -2);
+        int nr = kr + jr, nc = kc + jc;
+        if (nr < 0 || nr >= 10 || nc < 0 || nc >= 9) continue;
+        if (cell_after(b, nr * 9 + nc, from, to, mover) != horse) continue;
+        int lr = nr, lc = nc;
+        if (jr == 2 || jr == -2) lr = nr - jr / 2; else lc = nc - jc / 2;
+        if (cell_after(b, lr * 9 + lc, from, to, mover) == 0) return true;
+    }
+    if (by == 1) {
+        if (kr - 1 >= 0 && cell_after(b, (kr - 1) * 9 + kc, from, to, mover) == pawn) return true;
+        if (kr >= 5) {
+            if (kc - 1 >= 0 && cell_after(b, kr * 9 + kc - 1, from, to, mover) == pawn) return true;
+            if (kc + 1 < 9 && cell_after(b, kr * 9 + kc + 1, from, to, mover) == pawn) return true;
+        }
+    } else {
+        if (kr + 1 < 10 && cell_after(b, (kr + 1) * 9 + kc, from, to, mover) == pawn) return true;
+        if (kr <= 4) {
+            if (kc - 1 >= 0 && cell_after(b, kr * 9 + kc - 1, from, to, mover) == pawn) return true;
+            if (kc + 1 < 9 && cell_after(b, kr * 9 + kc + 1, from, to, mover) == pawn) return true;
+        }
+    }
+    return false;
+}
+
 // palace square index 0..8 -> board square (rows r0..r0+2, cols 3..5, row-major like pyx:93-98)
 __device__ __forceinline__ int palace_sq(int side, int i) { return ((side == 1 ? 0 : 7) + i / 3) * 9 + 3 + i % 3; }
 
@@ -232,8 +311,8 @@ __device__ __forceinline__ KingInfo warp_find_kings(const int8_t* b, int side)
 
 // game_core.pyx:209-252.  from < 0 probes the current board ("null move") without the
 // flying-general clause, i.e. plain is_attacked(own king) -- used for the in-check flag.
-__device__ __forceinline__ bool legal_after_move(const int8_t* b, int side, const KingInfo& ki, int from,
-                                                 int to)
+__device__ __forceinline__ bool legal_after_move(const int8_t* b, const uint16_t* rowocc, const uint16_t* colocc, int side,
+                                                 const KingInfo& ki, int from, int to)
 {
     const int mover = b[from];
     int k, e;
@@ -254,14 +333,17 @@ __device__ __forceinline__ bool legal_after_move(const int8_t* b, int side, cons
     if (k < 0) return false;
     const int kr = k / 9, kc = k % 9;
     if (e >= 0 && e % 9 == kc) {
+        // flying general: no piece strictly between the kings on their common file (overlaid column mask)
         const int er = e / 9;
         const int lo = min(kr, er), hi = max(kr, er);
-        bool open = true;
-        for (int r = lo + 1; r < hi; ++r)
-            if (cell_after(b, r * 9 + kc, from, to, mover) != 0) { open = false; break; }
-        if (open) return false;       // flying general
+        unsigned Cm = colocc[kc];
+        const int fr = from / 9, fc = from - fr * 9, tr = to / 9, tc = to - tr * 9;
+        if (fc == kc) Cm &= ~(1u << fr);
+        if (tc == kc) Cm |= 1u << tr;
+        const unsigned between = ((1u << hi) - 1u) & ~((1u << (lo + 1)) - 1u);
+        if ((Cm & between) == 0) return false;
     }
-    return !attacked_sq(b, kr, kc, -side, from, to, mover);
+    return !attacked_sq_occ(b, rowocc, colocc, kr, kc, -side, from, to, mover);
 }
 
 // Pseudo-legal targets of one (piece, direction-slot) task in reference order.
@@ -380,6 +462,18 @@ __device__ __forceinline__ MovegenResult warp_movegen(const int8_t* b, int side,
     MovegenResult res;
     res.overflow = false;
     res.kings = warp_find_kings(b, side);
+    // occupancy masks: lanes 0-9 one row each, lanes 10-18 one column each
+    if (lane < 10) {
+        unsigned m = 0;
+#pragma unroll
+        for (int c = 0; c < 9; ++c) m |= (b[lane * 9 + c] != 0 ? 1u : 0u) << c;
+        S.rowocc[lane] = (uint16_t)m;
+    } else if (lane < 19) {
+        unsigned m = 0;
+#pragma unroll
+        for (int r = 0; r < 10; ++r) m |= (b[r * 9 + lane - 10] != 0 ? 1u : 0u) << r;
+        S.colocc[lane - 10] = (uint16_t)m;
+    }
 
     // ---- phase A: ordered pseudo-legal list --------------------------------------------
     // own pieces in square order: rank among own pieces = task group
@@ -432,11 +526,11 @@ __device__ __forceinline__ MovegenResult warp_movegen(const int8_t* b, int side,
         if (i < n_pseudo) {
             from = S.pfrom[i];
             to = S.pto[i];
-            ok = legal_after_move(b, side, res.kings, from, to);
+            ok = legal_after_move(b, S.rowocc, S.colocc, side, res.kings, from, to);
         } else if (i == n_pseudo) {
             // cy_is_in_check (pyx:543-555): missing king => True
             int k = res.kings.own_sq;
-            chk = (k < 0) ? true : attacked_sq(b, k / 9, k % 9, -side, -1, -1, 0);
+            chk = (k < 0) ? true : attacked_sq_occ(b, S.rowocc, S.colocc, k / 9, k % 9, -side, -1, -1, 0);
         }
         unsigned m = warp_ballot(ok);
         if (ok) {
