@@ -180,6 +180,8 @@ typedef struct xq_gemm_desc {
     const void* residual; /* mode 0 only, may be NULL */
     void* out;
     void* out2;           /* mode 1 only */
+    const void* w_half;   /* mode 0, optional: the same weights tiled by 64 output channels
+                             [n_tile64][tap][k_block][chunk][64][8] for the cta_group::2 kernel (NULL: not used) */
 } xq_gemm_desc;
 
 int xq_net_gemm(xq_ctx* ctx, const xq_gemm_desc* desc, void* stream);

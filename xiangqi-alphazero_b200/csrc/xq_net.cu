@@ -42,6 +42,7 @@ struct GemmArgs {
     const uint8_t* residual;
     uint8_t* out;
     float* out2;
+    const uint8_t* w_half;   // weight image tiled by 64 output channels (cta_group::2 kernel: each CTA of a pair holds half of N)
     int dbg;   // timing experiments only (XQ_NET_DBG): 1 = no weight copies, 2 = quarter of the MMAs, 4 = empty epilogue
 };
 
@@ -1075,14 +1076,371 @@ static int launch_conv4(xq_ctx* c, const GemmArgs& a, cudaStream_t s)
     return XQ_OK;
 }
 
+// =============================================================================================
+// v5 conv kernel: v4 on a CTA pair with cta_group::2 MMAs (M = 256 across two SMs)
+// =============================================================================================
+// v4 is bound by shared-memory bandwidth: every 128x128x16 MMA reads 4 KB of A and 4 KB of B, and the TMA
+// writes share the same 128 B/clk.  With cta_group::2 the two SMs of a pair run ONE 256x128x16 MMA: each CTA
+// supplies its own 128 rows of A and only HALF of B (64 of the 128 output channels, its own 8 KB weight
+// stage); the tensor cores exchange the halves.  B reads and weight-stage writes per SM halve.
+//   * cluster (2,1,1); CTA r of pair works on row pair 2*item + r; rank 0 is the MMA leader
+//   * both CTAs run their own TMA producer (own A segments, own half of every weight stage); the follower's
+//     warp 1 relays "my stage / my segment has landed" to the leader with remote mbarrier arrives
+//   * the leader's commits are multicast to both CTAs (stage empty, segment empty, accumulator full);
+//     both epilogues arrive on the leader's accumulator-empty barrier
+constexpr int kMaxStages5 = 18;
+
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* local_bar, uint32_t target_cta)
+{
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(local_bar)),
+        "r"(target_cta)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* slot, uint32_t cols)
+{
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish2()
+{
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t addr, uint32_t cols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma2_commit_mc(uint64_t* bar, uint16_t cta_mask)
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"(cta_mask)
+                 : "memory");
+}
+
+template <int KCH>
+struct Conv5Cfg {
+    static constexpr int NT = 128;                             // output channels per MMA (64 per CTA)
+    static constexpr int kWTap = KCH * 64 * 16;                // this CTA's half of one (tap, k-block) weight slice
+    static constexpr int kWStage = kWTap;
+    static constexpr int kSeg = KCH * kAPlane2;
+    static constexpr int kTmemCols = 512;
+    static constexpr int kBudget = 225 * 1024 - 1024 - 1024;
+    static int stages(int kchunks)
+    {
+        int st = (kBudget - (kchunks / KCH) * kSeg) / kWStage;
+        return st > kMaxStages5 ? kMaxStages5 : st;
+    }
+    static int smem_bytes(int kchunks)
+    {
+        int total = (kchunks / KCH) * kSeg + stages(kchunks) * kWStage + 1024;
+        return total < 120 * 1024 ? 120 * 1024 : total;
+    }
+};
+
+template <int KCH>
+__global__ void __launch_bounds__(kConv4Threads, 1) conv5_kernel(const GemmArgs p, const int S)
+{
+    using Cfg = Conv5Cfg<KCH>;
+    constexpr int NT = 128, TS = 128;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int kblocks = p.kchunks / KCH;
+    uint8_t* sA = smem;
+    uint8_t* sStage = smem + kblocks * Cfg::kSeg;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + S * Cfg::kWStage);
+    uint64_t* w_full = bars;                                    // [18] own half of the stage has landed
+    uint64_t* w_empty = bars + kMaxStages5;                     // [18] MMAs reading the stage are done (leader multicast)
+    uint64_t* w_peer = bars + 2 * kMaxStages5;                  // [18] leader only: the follower's half has landed
+    uint64_t* a_full = bars + 3 * kMaxStages5;                  // [4]
+    uint64_t* a_empty = a_full + kMaxSeg4;
+    uint64_t* a_peer = a_empty + kMaxSeg4;
+    uint64_t* t_full = a_peer + kMaxSeg4;                       // [2]
+    uint64_t* t_empty = t_full + 2;                             // [2] leader only: 16 epilogue warps of the pair
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t crank = cluster_ctarank();
+    const bool leader = crank == 0;
+    const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+    const int m_pairs = (p.m_tiles + 1) / 2;
+    const int items = (m_pairs + 1) / 2;
+    const int total = items * p.n_tiles;
+
+    __shared__ __align__(16) float sBias[256];
+    for (int i = threadIdx.x; i < p.n_tiles * NT && i < 256; i += kConv4Threads) sBias[i] = p.bias[i];
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < S; ++i) {
+            mbar_init(&w_full[i], 1);
+            mbar_init(&w_empty[i], 1);
+            mbar_init(&w_peer[i], 1);
+        }
+        for (int i = 0; i < kblocks; ++i) {
+            mbar_init(&a_full[i], 1);
+            mbar_init(&a_empty[i], 1);
+            mbar_init(&a_peer[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&t_full[i], 1);
+            mbar_init(&t_empty[i], 16);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        tmem_alloc2(tmem_slot, Cfg::kTmemCols);
+        tmem_relinquish2();
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs): own rows, own half of the weights =====================
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            int n = 0;
+            for (int work = cluster_id; work < total; work += n_clusters, ++n) {
+                const int item = work / p.n_tiles, n_tile = work - item * p.n_tiles;
+                const int pair = item * 2 + (int)crank;
+                const long long m0 = (long long)pair * kPairRows;
+                // image tiled by 64 channels: [n_tile64][tap][k_block][chunk][64][8], n_tile64 = 2 * n_tile + rank
+                const uint8_t* wt = p.w_half + (size_t)(2 * n_tile + (int)crank) * 9 * kblocks * Cfg::kWTap;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&a_empty[kb], (uint32_t)(n & 1) ^ 1u);
+                    mbar_expect_tx(&a_full[kb], (uint32_t)Cfg::kSeg);
+#pragma unroll
+                    for (int c = 0; c < KCH; ++c)
+                        bulk_g2s(sA + kb * Cfg::kSeg + c * kAPlane2,
+                                 p.a + ((size_t)(kb * KCH + c) * p.a_rows + (size_t)(p.a_row0 + m0 - kHalo)) * 16, kAPlane2,
+                                 &a_full[kb]);
+                    for (int tap = 0; tap < 9; ++tap) {
+                        mbar_wait(&w_empty[s], ph ^ 1);
+                        mbar_expect_tx(&w_full[s], Cfg::kWStage);
+                        bulk_g2s(sStage + s * Cfg::kWStage, wt + (size_t)(tap * kblocks + kb) * Cfg::kWTap, Cfg::kWStage, &w_full[s]);
+                        if (++s == S) { s = 0; ph ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            int n = 0;
+            if (!leader) {
+                // ===================== follower: relay "landed" events to the leader =====================
+                for (int work = cluster_id; work < total; work += n_clusters, ++n) {
+                    for (int kb = 0; kb < kblocks; ++kb) {
+                        mbar_wait(&a_full[kb], (uint32_t)(n & 1));
+                        mbar_arrive_remote(&a_peer[kb], 0);
+                        for (int tap = 0; tap < 9; ++tap) {
+                            mbar_wait(&w_full[s], ph);
+                            mbar_arrive_remote(&w_peer[s], 0);
+                            if (++s == S) { s = 0; ph ^= 1; }
+                        }
+                    }
+                }
+            } else {
+                // ===================== leader: MMA issuer for both SMs =====================
+                constexpr uint32_t idesc = make_idesc(256, NT);
+                constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);
+                constexpr uint32_t kLboA = (uint32_t)(kAPlane2 >> 4);
+                for (int work = cluster_id; work < total; work += n_clusters, ++n) {
+                    const int acc = n & 1;
+                    const uint32_t tph = (uint32_t)(n >> 1) & 1u;
+                    mbar_wait(&t_empty[acc], tph ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_addr = tmem_base + (uint32_t)(acc * 2 * TS);
+                    for (int kb = 0; kb < kblocks; ++kb) {
+                        mbar_wait(&a_full[kb], (uint32_t)(n & 1));
+                        mbar_wait(&a_peer[kb], (uint32_t)(n & 1));
+                        const uint32_t a_seg = (((smem_u32(sA + kb * Cfg::kSeg)) >> 4) & 0x3FFFu) | (kLboA << 16);
+                        for (int tap = 0; tap < 9; ++tap) {
+                            mbar_wait(&w_full[s], ph);
+                            mbar_wait(&w_peer[s], ph);
+                            tc_fence_after();
+                            const uint32_t b_lo = ((smem_u32(sStage + s * Cfg::kWStage) >> 4) & 0x3FFFu) | ((uint32_t)((64 * 16) >> 4) << 16);
+                            const int shift = ((tap / 3) - 1) * 10 + (tap % 3) - 1;
+                            const uint32_t a_lo = a_seg + (uint32_t)(kHalo + shift);
+                            const uint32_t first = (kb | tap) != 0 ? 1u : 0u;
+#pragma unroll
+                            for (int t = 0; t < 2; ++t) {
+#pragma unroll
+                                for (int j = 0; j < KCH / 2; ++j) {
+                                    const uint64_t adesc = ((uint64_t)kDescHi << 32) | (uint64_t)(a_lo + (uint32_t)(2 * j) * kLboA + (uint32_t)(t * 128));
+                                    const uint64_t bdesc = ((uint64_t)kDescHi << 32) | (uint64_t)(b_lo + (uint32_t)(2 * j * 64));
+                                    umma2_bf16(d_addr + (uint32_t)(t * TS), adesc, bdesc, idesc, j == 0 ? first : 1u);
+                                }
+                            }
+                            umma2_commit_mc(&w_empty[s], 3);
+                            if (++s == S) { s = 0; ph ^= 1; }
+                        }
+                        umma2_commit_mc(&a_empty[kb], 3);
+                    }
+                    umma2_commit_mc(&t_full[acc], 3);
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue (both CTAs): as v4, accumulator release goes to the leader =====================
+        const int q = warp & 3;
+        const int t = (warp - 2) >> 2;
+        const int row = q * 32 + lane;
+        int n = 0;
+        uint4 res[NT / 8];
+        for (int work = cluster_id; work < total; work += n_clusters, ++n) {
+            const int item = work / p.n_tiles, n_tile = work - item * p.n_tiles;
+            const int pair = item * 2 + (int)crank;
+            const int acc = n & 1;
+            const uint32_t tph = (uint32_t)(n >> 1) & 1u;
+            const long long mrow = (long long)pair * kPairRows + t * 128 + row;
+            const int rr = (int)(mrow % 110);
+            const bool real = mrow < (long long)p.n_boards * 110 && rr >= 10 && (rr % 10) != 9;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 * TS + t * TS);
+            const bool has_res = p.residual != nullptr;
+            if (n == 0) {
+#pragma unroll
+                for (int k = 0; k < NT / 8; ++k) {
+                    res[k] = make_uint4(0, 0, 0, 0);
+                    if (has_res && real)
+                        res[k] = __ldg(reinterpret_cast<const uint4*>(
+                            p.residual + ((size_t)(n_tile * (NT / 8) + k) * p.out_rows + (size_t)(p.out_row0 + mrow)) * 16));
+                }
+            }
+            const int nwork = work + n_clusters;
+            const int nitem = nwork / p.n_tiles, nn_tile = nwork - nitem * p.n_tiles;
+            const long long nrow = (long long)(nitem * 2 + (int)crank) * kPairRows + t * 128 + row;
+            const int nrr = (int)(nrow % 110);
+            const bool nreal = nwork < total && nrow < (long long)p.n_boards * 110 && nrr >= 10 && (nrr % 10) != 9;
+            mbar_wait(&t_full[acc], tph);
+            tc_fence_after();
+            auto emit = [&](const uint32_t* v, const int c0) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const int k = c0 / 8 + g;
+                    const int nn = n_tile * NT + c0 + g * 8;
+                    const size_t off = ((size_t)(nn >> 3) * p.out_rows + (size_t)(p.out_row0 + mrow)) * 16;
+                    uint4 o = make_uint4(0, 0, 0, 0);
+                    if (real) {
+                        float f[8];
+                        const float4 b0 = *reinterpret_cast<const float4*>(&sBias[nn]);
+                        const float4 b1 = *reinterpret_cast<const float4*>(&sBias[nn + 4]);
+                        f[0] = __uint_as_float(v[g * 8 + 0]) + b0.x;
+                        f[1] = __uint_as_float(v[g * 8 + 1]) + b0.y;
+                        f[2] = __uint_as_float(v[g * 8 + 2]) + b0.z;
+                        f[3] = __uint_as_float(v[g * 8 + 3]) + b0.w;
+                        f[4] = __uint_as_float(v[g * 8 + 4]) + b1.x;
+                        f[5] = __uint_as_float(v[g * 8 + 5]) + b1.y;
+                        f[6] = __uint_as_float(v[g * 8 + 6]) + b1.z;
+                        f[7] = __uint_as_float(v[g * 8 + 7]) + b1.w;
+                        const uint32_t rw[4] = {res[k].x, res[k].y, res[k].z, res[k].w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            f[2 * e] += __uint_as_float(rw[e] << 16);
+                            f[2 * e + 1] += __uint_as_float(rw[e] & 0xffff0000u);
+                        }
+                        if (p.relu) {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.0f);
+                        }
+                        o = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+                    }
+                    *reinterpret_cast<uint4*>(p.out + off) = o;
+                    res[k] = make_uint4(0, 0, 0, 0);
+                    if (has_res && nreal)
+                        res[k] = __ldg(reinterpret_cast<const uint4*>(
+                            p.residual + ((size_t)(nn_tile * (NT / 8) + k) * p.out_rows + (size_t)(p.out_row0 + nrow)) * 16));
+                }
+            };
+            {
+                constexpr int kSlabs = NT / 32;
+                uint32_t va[32], vb[32];
+                tmem_ld32(taddr, va);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < kSlabs; ++i) {
+                    if (i & 1) {
+                        if (i + 1 < kSlabs) tmem_ld32(taddr + (uint32_t)((i + 1) * 32), va);
+                        emit(vb, i * 32);
+                    } else {
+                        if (i + 1 < kSlabs) tmem_ld32(taddr + (uint32_t)((i + 1) * 32), vb);
+                        emit(va, i * 32);
+                    }
+                    if (i + 1 < kSlabs) tmem_ld_wait();
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (leader) mbar_arrive(&t_empty[acc]);
+                else mbar_arrive_remote(&t_empty[acc], 0);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                // both CTAs are done with TMEM and with each other's barriers
+    if (warp == 1) tmem_dealloc2(tmem_base, Cfg::kTmemCols);
+}
+
+template <int KCH>
+static int launch_conv5(xq_ctx* c, const GemmArgs& a, cudaStream_t s)
+{
+    using Cfg = Conv5Cfg<KCH>;
+    const int kblocks = a.kchunks / KCH;
+    const int S = Cfg::stages(a.kchunks);
+    if (kblocks > kMaxSeg4 || S < 2 || !a.w_half) return xq_fail(c, XQ_ERR_ARG, "conv5 kernel: %d k-blocks, %d stages, w_half %p", kblocks, S, (const void*)a.w_half);
+    const int smem = Cfg::smem_bytes(a.kchunks);
+    static bool configured = false;
+    auto kern = conv5_kernel<KCH>;
+    if (!configured) {
+        XQ_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+        configured = true;
+    }
+    const int items = ((((a.m_tiles + 1) / 2) + 1) / 2) * a.n_tiles;
+    int clusters = c->sm_count / 2;
+    if (clusters > items) clusters = items;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(clusters * 2);
+    cfg.blockDim = dim3(kConv4Threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (getenv("XQ_DEBUG")) fprintf(stderr, "[xq] conv5<%d> stages=%d smem=%d grid=%d\n", KCH, S, smem, clusters * 2);
+    XQ_CUDA(c, cudaLaunchKernelEx(&cfg, kern, a, S));
+    c->launches += 1;
+    return XQ_OK;
+}
+
 // ---- value head: Linear(360,128)+ReLU -> Linear(128,1) -> tanh (model.py:74-83) ----------------
 // feats [B][90][4] fp32 (already conv1x1+BN+ReLU), w1t [360][128] fp32 with k = pos*4+ch, 16 boards per CTA.
 constexpr int kVhBoards = 16;
+constexpr int kVhChunk = 40;   // rows of W1^T staged per step (40 x 128 floats = 20 KB)
 __global__ void __launch_bounds__(128) value_head_kernel(const float* __restrict__ feats, const float* __restrict__ w1t,
                                                           const float* __restrict__ b1, const float* __restrict__ w2,
                                                           float b2, float* __restrict__ value, int B)
 {
-    __shared__ float f[kVhBoards][360];
+    __shared__ __align__(16) float f[kVhBoards][360];
+    __shared__ __align__(16) float wsm[kVhChunk][128];
     __shared__ float red[kVhBoards][4];
     const int b0 = blockIdx.x * kVhBoards;
     const int nb = min(kVhBoards, B - b0);
@@ -1090,15 +1448,22 @@ __global__ void __launch_bounds__(128) value_head_kernel(const float* __restrict
         const int bb = i / 360;
         f[bb][i - bb * 360] = bb < nb ? feats[(size_t)(b0 + bb) * 360 + (i - bb * 360)] : 0.0f;
     }
-    __syncthreads();
     const int j = threadIdx.x;
     float acc[kVhBoards];
 #pragma unroll
     for (int bb = 0; bb < kVhBoards; ++bb) acc[bb] = b1[j];
-    for (int k = 0; k < 360; ++k) {
-        const float w = w1t[k * 128 + j];
+    for (int k0 = 0; k0 < 360; k0 += kVhChunk) {
+        __syncthreads();
+        // coalesced float4 copy of 40 rows of W1^T (the first version read one dependent global word per k)
+        for (int i = threadIdx.x; i < kVhChunk * 32; i += 128)
+            reinterpret_cast<float4*>(&wsm[0][0])[i] = reinterpret_cast<const float4*>(w1t + (size_t)k0 * 128)[i];
+        __syncthreads();
+#pragma unroll 8
+        for (int k = 0; k < kVhChunk; ++k) {
+            const float w = wsm[k][j];
 #pragma unroll
-        for (int bb = 0; bb < kVhBoards; ++bb) acc[bb] = fmaf(w, f[bb][k], acc[bb]);
+            for (int bb = 0; bb < kVhBoards; ++bb) acc[bb] = fmaf(w, f[bb][k0 + k], acc[bb]);
+        }
     }
     const float wj = w2[j];
 #pragma unroll
@@ -1176,11 +1541,14 @@ extern "C" int xq_net_gemm(xq_ctx* c, const xq_gemm_desc* d, void* stream)
     a.residual = (const uint8_t*)d->residual;
     a.out = (uint8_t*)d->out;
     a.out2 = (float*)d->out2;
+    a.w_half = (const uint8_t*)d->w_half;
     a.dbg = getenv("XQ_NET_DBG") ? atoi(getenv("XQ_NET_DBG")) : 0;
     cudaStream_t s = (cudaStream_t)stream;
     XqTimer tm(c, s);
     const bool v1 = c->net_v1;
     const int cl = c->net_cluster;
+    if (!v1 && c->net_gen >= 5 && d->w_half && d->mode == 0 && d->nt == 128 && d->kch_iter == 8 && d->kchunks % 8 == 0 && d->kchunks <= 32)
+        return launch_conv5<8>(c, a, s);
     if (!v1 && c->net_gen >= 4) {
         if (d->mode == 0 && d->nt == 128 && d->kch_iter == 8 && d->kchunks % 8 == 0 && d->kchunks <= 32) return launch_conv4<128, 8, false, 1>(c, a, s);
         if (d->mode == 0 && d->nt == 128 && d->kch_iter == 2 && d->kchunks == 2) return launch_conv4<128, 2, false, 9>(c, a, s);
