@@ -1,0 +1,144 @@
+"""The drop-in Python modules (game / mcts / model / parallel_selfplay / inference_server) keep the
+reference's contracts: these are the acceptance tests a reference user would run (test_v3.py,
+test_cython.py, test_gpu_train.py shapes), with the oracle as the checker."""
+import random
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_xiangqigame_random_games_follow_the_rules(oracle):
+    """test_cython.py:87-123 / test_v3.py:16-103 recipe on the drop-in XiangqiGame."""
+    import game as G
+    rnd = random.Random(11)
+    for _ in range(6):
+        g, og = G.XiangqiGame(), oracle.OracleGame()
+        for _ply in range(300):
+            done, winner = g.is_game_over()
+            odone, owinner = og.is_game_over()
+            assert (done, winner) == (odone, owinner)
+            if done:
+                break
+            moves = g.get_legal_moves()
+            acts = g.get_legal_actions()
+            assert acts == og.get_legal_actions().tolist()               # ordered, like the Cython engine
+            assert len(acts) == len(moves) and g.get_legal_moves() is moves   # cache coherence (test_v3.py:40-47)
+            assert all(G.encode_action(*G.decode_action(a)) == a for a in acts[:5])
+            assert g._is_in_check(g.current_player) == oracle.in_check(g.board, g.current_player)
+            assert np.array_equal(g.get_state_for_nn(), og.get_state_for_nn())
+            assert g.get_material_score(1) == og.material(1) and g.get_material_score(-1) == og.material(-1)
+            m = rnd.choice(moves)
+            assert g.board[m[0], m[1]] != 0
+            g.make_move(*m)
+            og.make_action(G.encode_action(*m))
+            assert g._legal_moves_cache is None
+        c = g.clone()
+        assert np.array_equal(c.board, g.board) and c.history == g.history and c.move_count == g.move_count
+
+
+def test_known_positions_of_the_reference_tests():
+    import game as G
+    g = G.XiangqiGame()
+    assert len(g.get_legal_moves()) == 44                            # test_v3.py:115-120
+    g3 = G.XiangqiGame(); g3.board[:] = 0
+    g3.board[0, 4], g3.board[9, 4], g3.board[5, 4] = 1, -1, -5
+    g3._legal_moves_cache = None
+    assert g3._is_in_check(1) is True                                # test_v3.py:139-151
+    g4 = G.XiangqiGame(); g4.board[:] = 0
+    g4.board[0, 4], g4.board[2, 3] = 1, -4
+    assert G.XiangqiGame._is_attacked(g4.board, 0, 4, -1) is True    # test_v3.py:154-166
+    g4.board[1, 3] = 7
+    assert G.XiangqiGame._is_attacked(g4.board, 0, 4, -1) is False   # horse leg, test_v3.py:169-181
+    g6 = G.XiangqiGame(); g6.board[:] = 0
+    g6.board[0, 4], g6.board[9, 4], g6.board[5, 4], g6.board[8, 4] = 1, -1, 7, -6
+    assert G.XiangqiGame._is_attacked(g6.board, 0, 4, -1) is True    # cannon + screen, test_v3.py:184-197
+
+
+def test_mcts_dropin_equals_oracle_search_with_the_same_network(oracle):
+    """MCTS(model).search on the GPU tree == the reference algorithm (oracle) driven by the very same
+    predict(): visit counts must be identical because both consume identical float32 probabilities."""
+    import torch
+    import game as G
+    import mcts as MC
+    import model as M
+    torch.manual_seed(4)
+    net = M.XiangqiNet(128, 1).eval()
+    g, og = G.XiangqiGame(), oracle.OracleGame()
+    for a in (1792, 6337):
+        g.make_action(a)
+        og.make_action(a)
+
+    def predict(board, player):
+        return net.predict(oracle.planes(board, player))
+    search = MC.MCTS(net, num_simulations=48, c_puct=1.5)
+    probs = search.search(g, temperature=1.0, add_noise=False)
+    acts, vis, _, _ = oracle.mcts_search(og, 48, 1.5, predict)
+    want = np.zeros(8100)
+    want[acts.astype(np.int64)] = vis / 48.0
+    assert np.array_equal(probs, want)
+    assert search.get_action(g, temperature=0.0) == int(acts[int(np.argmax(vis))])   # first max wins
+    # with noise: a distribution over legal moves only
+    p2 = search.search(g, temperature=0.3, add_noise=True)
+    assert abs(p2.sum() - 1.0) < 1e-9 and set(np.nonzero(p2)[0]) <= set(acts.tolist())
+
+
+def test_one_training_iteration_dropin():
+    """test_gpu_train.py shape: self-play -> samples -> one optimiser step on the torch module ->
+    self-play again with the UPDATED weights (the kernel-side copy must follow the parameters)."""
+    import torch
+    import torch.nn.functional as F
+    import model as M
+    import parallel_selfplay as ps
+
+    class Cfg:
+        num_simulations, c_puct, temperature_threshold, max_game_length = 8, 1.5, 20, 60
+        random_opening_moves, enable_resign, resign_threshold, resign_check_steps = 4, True, -0.9, 5
+        num_games_per_iter = 4
+    torch.manual_seed(0)
+    net = M.XiangqiNet(128, 1)
+    data, stats = ps.parallel_self_play(net, Cfg(), num_workers=2, use_gpu_server=True, gpu_device='cpu')
+    assert stats['games'] == 4 and len(data) > 0
+    dev = torch.device('cuda')
+    net.to(dev).train()
+    opt = torch.optim.Adam(net.parameters(), lr=2e-3, weight_decay=1e-4)
+    s = torch.from_numpy(np.stack([d[0] for d in data[:64]])).to(dev)
+    p = torch.from_numpy(np.stack([d[1] for d in data[:64]])).float().to(dev)
+    z = torch.tensor([d[2] for d in data[:64]], dtype=torch.float32, device=dev)
+    logits, v = net(s)
+    loss = -(p * F.log_softmax(logits, dim=1)).sum(1).mean() + F.mse_loss(v.squeeze(1), z)   # train.py:410-414
+    loss.backward()
+    torch.nn.utils.clip_grad_norm_(net.parameters(), 1.0)
+    opt.step()
+    net.eval()
+    state = data[0][0]
+    before = net._b200_version
+    probs, value = net.predict(state)                                 # refolds: parameters changed
+    assert net._b200_version != before
+    with torch.no_grad():
+        lr, vr = net(torch.from_numpy(state)[None].to(dev))
+    pr = torch.softmax(lr, 1)[0].cpu().numpy()
+    assert np.abs(probs - pr).max() / pr.max() < 1e-2 and abs(value - float(vr)) < 1e-2
+    data2, stats2 = ps.parallel_self_play(net, Cfg())
+    assert stats2['games'] == 4 and stats2['mode'] == 'gpu'
+
+
+def test_inference_server_shim():
+    import torch
+    import model as M
+    import inference_server as IS
+    torch.manual_seed(1)
+    net = M.XiangqiNet(128, 1)
+    srv = IS.InferenceServer(M.XiangqiNet, {'num_channels': 128, 'num_res_blocks': 1},
+                             {k: v.clone() for k, v in net.state_dict().items()}, device='cuda', num_workers=2)
+    path = srv.start()
+    cl = IS.InferenceClient(0, path)
+    state = np.zeros((15, 10, 9), np.float32); state[14] = 1; state[0, 0, 4] = 1; state[7, 9, 4] = 1
+    probs, value = cl.predict(state)
+    p2, v2 = net.eval().predict(state)
+    assert probs.shape == (8100,) and np.array_equal(probs, p2) and value == v2
+    srv.stop()
+    with pytest.raises(RuntimeError):
+        cl.predict(state)
+    cl.close()

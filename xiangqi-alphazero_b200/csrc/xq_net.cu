@@ -105,6 +105,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v)
         : "r"(taddr)
         : "memory");
 }
+// ---- programmatic dependent launch: a kernel launched with the PDL attribute may start while its
+// predecessor is still draining; pdl_wait() blocks until the predecessor has completed and flushed, so
+// everything before it (barrier init, TMEM allocation) overlaps the predecessor's tail.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- thread-block cluster helpers (weight-stage multicast) ----
 __device__ __forceinline__ uint32_t cluster_ctarank()
 {
@@ -222,6 +228,8 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const GemmArgs p)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();
+    pdl_wait();
 
     if (warp == 0) {
         // ===================== TMA producer (one thread) =====================
@@ -844,6 +852,8 @@ __global__ void __launch_bounds__(kConv4Threads, 1) conv4_kernel(const GemmArgs 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();                           // the next layer may start its prologue now
+    pdl_wait();                                        // activations written by the previous kernel are visible after this
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -1070,7 +1080,19 @@ static int launch_conv4(xq_ctx* c, const GemmArgs& a, cudaStream_t s)
     const int total = ((a.m_tiles + 1) / 2) * a.n_tiles;
     const int grid = c->sm_count < total ? c->sm_count : total;   // persistent, one CTA per SM
     if (getenv("XQ_DEBUG")) fprintf(stderr, "[xq] conv4<%d,%d,%d,%d> stages=%d smem=%d grid=%d\n", NT, KCH, (int)HEADS, TPS, S, smem, grid);
-    kern<<<grid, kConv4Threads, smem, s>>>(a, S);
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(kConv4Threads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = c->net_pdl ? 1 : 0;
+        XQ_CUDA(c, cudaLaunchKernelEx(&cfg, kern, a, S));
+    }
     c->launches += 1;
     XQ_CUDA(c, cudaGetLastError());
     return XQ_OK;
@@ -1444,6 +1466,8 @@ __global__ void __launch_bounds__(128) value_head_kernel(const float* __restrict
     __shared__ float red[kVhBoards][4];
     const int b0 = blockIdx.x * kVhBoards;
     const int nb = min(kVhBoards, B - b0);
+    pdl_launch_dependents();
+    pdl_wait();
     for (int i = threadIdx.x; i < kVhBoards * 360; i += 128) {
         const int bb = i / 360;
         f[bb][i - bb * 360] = bb < nb ? feats[(size_t)(b0 + bb) * 360 + (i - bb * 360)] : 0.0f;
@@ -1506,7 +1530,19 @@ static int launch_gemm(xq_ctx* c, const GemmArgs& a, cudaStream_t s)
     int grid = c->sm_count * per_sm;
     if (grid > total) grid = total;
     if (getenv("XQ_DEBUG")) fprintf(stderr, "[xq] gemm<%d,%d,%d> per_sm=%d grid=%d smem=%d\n", MODE, NT, KCH, per_sm, grid, smem);
-    gemm_kernel<MODE, NT, KCH><<<grid, kGemmThreads, smem, s>>>(a);
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(kGemmThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = c->net_pdl ? 1 : 0;
+        XQ_CUDA(c, cudaLaunchKernelEx(&cfg, gemm_kernel<MODE, NT, KCH>, a));
+    }
     c->launches += 1;
     XQ_CUDA(c, cudaGetLastError());
     return XQ_OK;
@@ -1580,8 +1616,19 @@ extern "C" int xq_net_value_head(xq_ctx* c, const float* d_feats, const float* d
     if (!c || !d_feats || !d_w1t || !d_b1 || !d_w2 || !d_value || B < 0)
         return xq_fail(c, XQ_ERR_ARG, "xq_net_value_head: bad arguments");
     if (B == 0) return XQ_OK;
-    value_head_kernel<<<(B + kVhBoards - 1) / kVhBoards, 128, 0, (cudaStream_t)stream>>>(d_feats, d_w1t, d_b1, d_w2, b2,
-                                                                                       d_value, B);
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((B + kVhBoards - 1) / kVhBoards);
+        cfg.blockDim = dim3(128);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = c->net_pdl ? 1 : 0;
+        XQ_CUDA(c, cudaLaunchKernelEx(&cfg, value_head_kernel, d_feats, d_w1t, d_b1, d_w2, b2, d_value, B));
+    }
     c->launches += 1;
     XQ_CUDA(c, cudaGetLastError());
     return XQ_OK;
