@@ -114,6 +114,30 @@ def run(args, rank, world, local_rank, dist):
     c2 = sp.counters()
     e2e_sims = c2["sims"] - s_before["sims"]
 
+    # secondary headline of BASELINE.json ("legal-move positions/sec"): K1 over 1M device-generated positions
+    mv = None
+    try:
+        pb, ps_, _, _ = eng.random_playouts(20261018 + rank, 5600)
+        pb, ps_ = pb[:1_000_000].contiguous(), ps_[:1_000_000].contiguous()
+        outb = (torch.empty((pb.shape[0], 128), dtype=torch.int16, device=eng.dev), torch.empty((pb.shape[0],), dtype=torch.uint8, device=eng.dev),
+                torch.empty((pb.shape[0],), dtype=torch.uint8, device=eng.dev), torch.empty((pb.shape[0], 15, 10, 9), dtype=torch.float32, device=eng.dev))
+        for _ in range(3):
+            eng.movegen(pb, ps_, planes=True, out=outb)
+        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        m0.record()
+        for _ in range(5):
+            eng.movegen(pb, ps_, planes=True, out=outb)
+        m1.record()
+        torch.cuda.synchronize()
+        mv_ms = m0.elapsed_time(m1) / 5
+        mv = {"metric": "legal_move_positions_per_sec", "value": pb.shape[0] / (mv_ms * 1e-3), "unit": "positions/s (per GPU)",
+              "kernel": "movegen_kernel<true> (moves + in-check + fp32 planes)", "kernel_ms": mv_ms,
+              "achieved_gbs": 5563.4 * pb.shape[0] / (mv_ms * 1e-3) / 1e9,
+              "frac_of_hbm_peak": 5563.4 * pb.shape[0] / (mv_ms * 1e-3) / 1e9 / bench.measured_peaks()[0]["hbm_gbs"]}
+        del outb, pb, ps_
+    except Exception as ex:   # never let the secondary line break the headline
+        mv = {"error": str(ex)[:200]}
+
     if world > 1:
         t = torch.tensor([ms, e2e_s, fwd_ms], device=eng.dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -143,13 +167,17 @@ def run(args, rank, world, local_rank, dist):
                    "l2": "per-step working set (trees + activations, > 1 GB) >> 126 MB L2",
                    "parallelism": f"games sharded x{world}, no collective in self-play"},
         "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": achieved_tf / peak_tf, "traffic": None, "peak_source": peak_kind + " (sustained bf16)",
+                     "frac": achieved_tf / peak_tf,
+                     "traffic": {"unit": "MB per launch", "conv4_kernel<128,8,0,1>": 184.3, "conv4_kernel<128,8,0,1> (+residual)": 307.6,
+                                 "gemm_kernel<2,128,8>": 134.9, "source": "profiles/r1_net_ncu.md (ncu --set full, dram read+write)"},
+                     "peak_source": peak_kind + " (sustained bf16)",
                      "kernel": "conv4_kernel x14 + gemm_kernel<2> (tcgen05 implicit-GEMM forward) + value_head_kernel",
                      "algorithmic_flops_per_eval": FLOPS_PER_EVAL, "forward_ms_isolated": fwd_ms,
                      "forward_isolated_tflops": isolated_tf, "forward_isolated_frac_of_burst_peak": isolated_tf / peaks["bf16_tflops"],
                      "note": "achieved = FLOPs of all evaluations in the timed region / region time (search kernels and "
                              "power-capped clocks included); the isolated forward is timed back to back for 20 launches"},
         "cpu_baseline": cpu,
+        "secondary": mv,
         "e2e": {"value": e2e_sims / e2e_s, "unit": "sims/s", "h2d_bytes_per_step": 64 + 160,
                 "d2h_bytes_per_step": d2h // e2e_steps},
         "gpu_launches": launches,
