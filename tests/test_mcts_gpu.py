@@ -131,3 +131,35 @@ def test_device_dirichlet_noise_and_idle_games(eng, oracle):
     assert not np.array_equal(v[0], v[1])              # per-game noise streams differ
     a2, v2, _ = mb.search(host_evaluator("uniform"), 64, 1.5, add_noise=True, seed=11)
     assert np.array_equal(v2.cpu().numpy(), v)         # same seed -> same search
+
+
+def test_large_lockstep_batch_equals_oracle(eng, oracle):
+    """512 games in one lockstep batch (128 CTAs of the tree kernels, one shared node pool with atomic
+    bump allocation): every game's search equals its own independent oracle search."""
+    import xq_native
+    G = 512
+    boards, sides = oracle.random_playout_positions(77, 40000)
+    rs = np.random.RandomState(1)
+    games = []
+    while len(games) < G:
+        g = oracle.OracleGame()
+        for _ in range(int(rs.randint(0, 120))):
+            if g.is_game_over()[0]:
+                break
+            a = g.get_legal_actions()
+            g.make_action(int(a[rs.randint(len(a))]))
+        if not g.is_game_over()[0]:
+            games.append(g)
+    mb = xq_native.MctsBatch(eng, G)
+    mb.set_games(*game_arrays(games))
+    sims = 24
+    acts, vis, n = mb.search(host_evaluator("hash"), sims, 1.5)
+    _, _, _, w = mb.root_visits(want_w=True)
+    st = mb.stats(reset=True)
+    assert st["error"] == 0 and st["sims"] == G * sims
+    acts, vis, n, w = acts.cpu().numpy(), vis.cpu().numpy(), n.cpu().numpy(), w.cpu().numpy()
+    for i, g in enumerate(games):
+        ea, ev, ew, _ = oracle.mcts_search(g, sims, 1.5, "hash")
+        k = int(n[i])
+        assert acts[i, :k].tolist() == ea.tolist() and vis[i, :k].tolist() == ev.tolist(), i
+        assert np.array_equal(w[i, :k], ew), i
