@@ -16,9 +16,19 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 
 GAMES_PER_GPU = 4096
 SIMS = 800
-CHANNELS, BLOCKS = 128, 6
+CHANNELS = int(os.environ.get("XQ_BENCH_CHANNELS", 128))   # XQ_BENCH_CHANNELS=256 XQ_BENCH_BLOCKS=20: BASELINE configs[3] network
+BLOCKS = int(os.environ.get("XQ_BENCH_BLOCKS", 6))
 REF_SIMS = 200                      # simulations per process per step in the CPU reference arm (bounded sample)
-FLOPS_PER_EVAL = 369_193_216        # conv + FC MACs x 2 of the 128x6 network
+
+
+def flops_per_eval(c, r):
+    """conv + linear MACs x 2 of XiangqiNet(c, r) (369 193 216 for 128x6, 4 301 360 896 for 256x20)."""
+    return (2 * 90 * 9 * 15 * c + 2 * r * 2 * 90 * 9 * c * c + 2 * 90 * c * 32 + 2 * 2880 * 8100 + 2 * 90 * c * 4
+            + 2 * (360 * 128 + 128))
+
+
+FLOPS_PER_EVAL = flops_per_eval(CHANNELS, BLOCKS)
+assert flops_per_eval(128, 6) == 369_193_216 and flops_per_eval(256, 20) == 4_301_360_896
 
 
 class StdConfig:

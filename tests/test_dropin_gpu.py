@@ -142,3 +142,37 @@ def test_inference_server_shim():
     with pytest.raises(RuntimeError):
         cl.predict(state)
     cl.close()
+
+
+def test_hand_rolled_search_loop_like_benchmark_py(oracle):
+    """benchmark.py:18-153 unrolls MCTS.search around MCTSNode (root.expand / select_child / backup) with
+    game.clone / make_action / is_game_over and model.predict.  The same loop on the drop-ins must walk
+    the same tree as the device search (and the oracle)."""
+    import torch
+    import game as G
+    import mcts as MC
+    import model as M
+    torch.manual_seed(7)
+    net = M.XiangqiNet(128, 1).eval()
+    g = G.XiangqiGame()
+    root = MC.MCTSNode()
+    probs, _ = net.predict(g.get_state_for_nn(), 'cpu')
+    priors = MC.MCTS._mask_and_normalize(probs, g.get_legal_actions())
+    root.expand(priors)
+    sims = 24
+    for _ in range(sims):
+        node, sim = root, g.clone()
+        while not node.is_leaf():
+            action, node = node.select_child(1.5)
+            sim.make_action(action)
+        done, winner = sim.is_game_over()
+        if done:
+            value = 0.0 if winner == 0 else 1.0                       # mcts.py:140
+        else:
+            p, value = net.predict(sim.get_state_for_nn(), 'cpu')
+            node.expand(MC.MCTS._mask_and_normalize(p, sim.get_legal_actions()))
+            value = -value
+        node.backup(value)
+    host_counts = [c.visit_count for c in root.children.values()]
+    dev = MC.MCTS(net, num_simulations=sims, c_puct=1.5).search(g, temperature=1.0, add_noise=False)
+    assert [int(round(dev[a] * sims)) for a in root.children] == host_counts

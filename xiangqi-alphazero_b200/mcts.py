@@ -8,6 +8,7 @@ per-game interface runs a batch of one and calls `predict` once per simulation, 
 the reference; the high-throughput path is the lockstep batched search
 (xq_native.MctsBatch / selfplay_engine) where thousands of games share each evaluator batch.
 """
+import math
 from typing import Optional
 
 import numpy as np
@@ -17,8 +18,12 @@ from game import ACTION_SPACE, XiangqiGame, engine
 
 
 class MCTSNode:
-    """Host-side view of a root child (benchmark.py:23 imports the name).  The live tree is a
-    flat device array; see csrc/xq_mcts.cu."""
+    """Host-side node with the reference's fields and methods (mcts.py:21-73).
+
+    `MCTS.search` below does NOT use it -- the live tree is a flat device array (csrc/xq_mcts.cu).
+    The class exists for callers that hand-roll the search loop around it, as the reference's own
+    benchmark.py:18-153 does (root.expand / node.select_child / node.backup), so that script keeps
+    running with the rules engine and the network on the GPU."""
 
     __slots__ = ['parent', 'children', 'visit_count', 'total_value', 'prior']
 
@@ -34,7 +39,28 @@ class MCTSNode:
         return 0.0 if self.visit_count == 0 else self.total_value / self.visit_count
 
     def is_leaf(self) -> bool:
-        return len(self.children) == 0
+        return not self.children
+
+    def select_child(self, c_puct: float = 1.5):
+        """PUCT argmax, strict '>' so the first maximum in insertion order wins (mcts.py:43-58)."""
+        root_n = math.sqrt(self.visit_count)
+        pick, pick_score = (-1, None), -math.inf
+        for action, child in self.children.items():
+            score = child.q_value + c_puct * child.prior * root_n / (1 + child.visit_count)
+            if score > pick_score:
+                pick_score, pick = score, (action, child)
+        return pick
+
+    def expand(self, action_priors):
+        for action, prior in action_priors.items():
+            self.children.setdefault(action, MCTSNode(parent=self, prior=prior))
+
+    def backup(self, value: float):
+        node = self
+        while node is not None:                      # leaf -> root, sign flips per ply (mcts.py:66-73)
+            node.visit_count += 1
+            node.total_value += value
+            value, node = -value, node.parent
 
 
 def game_to_arrays(game: XiangqiGame):
@@ -97,6 +123,29 @@ class MCTS:
             return probs
         probs[acts] = counts
         if probs.sum() > 0:                                      # mcts.py:201-203
+            probs = probs ** (1.0 / temperature)
+            probs /= probs.sum()
+        return probs
+
+    @staticmethod
+    def _mask_and_normalize(policy_probs, legal_actions):
+        """mcts.py:176-188 (float32 sequential sum, like the device kernel's policy_kind 0)."""
+        total = sum(policy_probs[a] for a in legal_actions)
+        if total > 0:
+            return {a: policy_probs[a] / total for a in legal_actions}
+        return {a: 1.0 / len(legal_actions) for a in legal_actions}
+
+    @staticmethod
+    def _get_action_probs(root: MCTSNode, temperature: float) -> np.ndarray:
+        """mcts.py:190-206 for a host-side MCTSNode root."""
+        probs = np.zeros(ACTION_SPACE)
+        for a, child in root.children.items():
+            probs[a] = child.visit_count
+        if temperature == 0:
+            best = max(root.children, key=lambda a: root.children[a].visit_count)
+            probs = np.zeros(ACTION_SPACE)
+            probs[best] = 1.0
+        elif probs.sum() > 0:
             probs = probs ** (1.0 / temperature)
             probs /= probs.sum()
         return probs
