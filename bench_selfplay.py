@@ -257,19 +257,27 @@ def _cpu_worker(args):
     return time.perf_counter() - t0
 
 
-def cpu_selfplay_rate(procs, sims=100):
+def _cpu_sample_text(procs, sims, wall):
+    return (f"{procs} processes x one {sims}-simulation search from the start position, fp32 torch "
+            f"XiangqiNet({CHANNELS},{BLOCKS}) 1 thread each (the reference's _cpu_worker_entry shape), {wall:.1f} s")
+
+
+def cpu_selfplay_rate(procs, sims=100, pool=None):
     import multiprocessing as mp
-    ctx = mp.get_context("spawn")
-    t0 = time.perf_counter()
-    with ctx.Pool(procs) as pool:
+    own = pool is None
+    if own:
+        pool = mp.get_context("spawn").Pool(procs)
         pool.map(_cpu_worker, [(2, i) for i in range(procs)])           # start-up + import cost outside the timing
+    try:
         t0 = time.perf_counter()
         pool.map(_cpu_worker, [(sims, 100 + i) for i in range(procs)])
         wall = time.perf_counter() - t0
+    finally:
+        if own:
+            pool.close()
+            pool.join()
     rate = procs * sims / wall
-    return {"value": rate, "unit": "sims/s", "cores": procs, "kind": "port",
-            "sample": f"{procs} processes x one {sims}-simulation search from the start position, fp32 torch "
-                      f"XiangqiNet({CHANNELS},{BLOCKS}) 1 thread each (the reference's _cpu_worker_entry shape), {wall:.1f} s"}
+    return {"value": rate, "unit": "sims/s", "cores": procs, "kind": "port", "sample": _cpu_sample_text(procs, sims, wall)}
 
 
 def run_reference(args):
@@ -277,12 +285,15 @@ def run_reference(args):
     if rank != 0:
         return
     procs = os.cpu_count() or 1
+    import multiprocessing as mp
     vals = []
     last = None
-    for i in range(args.warmup + args.steps):
-        last = cpu_selfplay_rate(procs, sims=REF_SIMS)
-        if i >= args.warmup:
-            vals.append(last["value"])
+    with mp.get_context("spawn").Pool(procs) as pool:
+        pool.map(_cpu_worker, [(2, i) for i in range(procs)])               # worker start-up outside every timed step
+        for i in range(args.warmup + args.steps):
+            last = cpu_selfplay_rate(procs, sims=REF_SIMS, pool=pool)
+            if i >= args.warmup:
+                vals.append(last["value"])
     value = sum(vals) / len(vals)
     last["value"] = value
     line = {"impl": "reference", "metric": "mcts_sims_per_sec", "value": value, "unit": "sims/s", "n_gpus": args.gpus,
