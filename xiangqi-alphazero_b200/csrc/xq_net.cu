@@ -779,7 +779,7 @@ static int launch_conv2(xq_ctx* c, const GemmArgs& a, cudaStream_t s)
 //     pair's rows while the other k-block computes -- A needs one buffer instead of two;
 //   * spends the freed shared memory on a 9-deep weight ring (2.6 us of MMA work in flight);
 //   * lets one stage carry several taps (TPS) when a tap is tiny (15-plane input conv: all 9 taps, 36 KB).
-constexpr int kConv4Threads = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
+constexpr int kConv4Threads = 352;   // warp 0 TMA, warps 1 and 10 MMA issuers (row tile 0 / 1), warps 2-9 epilogue
 constexpr int kMaxStages4 = 9;
 constexpr int kMaxSeg4 = 4;
 
@@ -818,9 +818,9 @@ __global__ void __launch_bounds__(kConv4Threads, 1) conv4_kernel(const GemmArgs 
     uint64_t* w_empty = bars + kMaxStages4;
     uint64_t* a_full = bars + 2 * kMaxStages4;                  // [kMaxSeg4]
     uint64_t* a_empty = a_full + kMaxSeg4;
-    uint64_t* t_full = a_empty + kMaxSeg4;                      // [2]
-    uint64_t* t_empty = t_full + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+    uint64_t* t_full = a_empty + kMaxSeg4;                      // [2 accumulator stages][2 row tiles]
+    uint64_t* t_empty = t_full + 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tap_groups = Cfg::kTaps / TPS;
@@ -832,15 +832,15 @@ __global__ void __launch_bounds__(kConv4Threads, 1) conv4_kernel(const GemmArgs 
     if (threadIdx.x == 0) {
         for (int i = 0; i < S; ++i) {
             mbar_init(&w_full[i], 1);
-            mbar_init(&w_empty[i], 1);
+            mbar_init(&w_empty[i], 2);                 // both MMA issuers release a stage
         }
         for (int i = 0; i < kblocks; ++i) {
             mbar_init(&a_full[i], 1);
-            mbar_init(&a_empty[i], 1);
+            mbar_init(&a_empty[i], 2);
         }
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&t_full[i], 1);
-            mbar_init(&t_empty[i], 8);                 // 8 epilogue warps: 4 lane quarters x 2 row tiles
+        for (int i = 0; i < 4; ++i) {
+            mbar_init(&t_full[i], 1);                  // per (accumulator stage, row tile)
+            mbar_init(&t_empty[i], 4);                 // the 4 epilogue warps (lane quarters) of that row tile
         }
         mbar_fence_init();
     }
@@ -867,25 +867,40 @@ __global__ void __launch_bounds__(kConv4Threads, 1) conv4_kernel(const GemmArgs 
                 const uint8_t* wt = p.w + (size_t)n_tile * Cfg::kTaps * kblocks * Cfg::kWTap;
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(&a_empty[kb], (uint32_t)(n & 1) ^ 1u);
-                    mbar_expect_tx(&a_full[kb], (uint32_t)Cfg::kSeg);
+                    if (p.dbg & 8) {                          // timing experiment: no activation traffic
+                        mbar_arrive(&a_full[kb]);
+                    } else {
+                        mbar_expect_tx(&a_full[kb], (uint32_t)Cfg::kSeg);
 #pragma unroll
-                    for (int c = 0; c < KCH; ++c)
-                        bulk_g2s(sA + kb * Cfg::kSeg + c * kAPlane2,
-                                 p.a + ((size_t)(kb * KCH + c) * p.a_rows + (size_t)(p.a_row0 + m0 - kHalo)) * 16, kAPlane2,
-                                 &a_full[kb]);
+                        for (int c = 0; c < KCH; ++c)
+                            bulk_g2s(sA + kb * Cfg::kSeg + c * kAPlane2,
+                                     p.a + ((size_t)(kb * KCH + c) * p.a_rows + (size_t)(p.a_row0 + m0 - kHalo)) * 16, kAPlane2,
+                                     &a_full[kb]);
+                    }
                     for (int tg = 0; tg < tap_groups; ++tg) {
                         mbar_wait(&w_empty[s], ph ^ 1);
+                        if (p.dbg & 1) {                      // timing experiment: no weight traffic
+                            mbar_arrive(&w_full[s]);
+                            if (++s == S) { s = 0; ph ^= 1; }
+                            continue;
+                        }
                         mbar_expect_tx(&w_full[s], Cfg::kWStage);
-                        // host image order is [tap][k_block]; with TPS > 1 there is a single k-block and taps are contiguous
-                        bulk_g2s(sStage + s * Cfg::kWStage, wt + (size_t)((tg * TPS) * kblocks + kb) * Cfg::kWTap, Cfg::kWStage,
-                                 &w_full[s]);
+                        // host image order is [tap][k_block]: one copy per tap of the stage
+#pragma unroll
+                        for (int tp = 0; tp < TPS; ++tp)
+                            bulk_g2s(sStage + s * Cfg::kWStage + tp * Cfg::kWTap,
+                                     wt + (size_t)((tg * TPS + tp) * kblocks + kb) * Cfg::kWTap, Cfg::kWTap, &w_full[s]);
                         if (++s == S) { s = 0; ph ^= 1; }
                     }
                 }
             }
         }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
+    } else if (warp == 1 || warp == 10) {
+        // ===================== MMA issuers: one thread per row tile =====================
+        // A single issuing thread spends ~0.2 us per stage hand-off (wait, fence, commit) on top of ~66 cycles per
+        // tcgen05.mma, which kept the tensor pipe at ~90 cycles per MMA; two issuers interleave their MMAs and
+        // hide each other's hand-offs.
+        const int t = warp == 1 ? 0 : 1;
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc(128, NT);
             constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);            // SBO = 128 B, version 1
@@ -896,9 +911,9 @@ __global__ void __launch_bounds__(kConv4Threads, 1) conv4_kernel(const GemmArgs 
             for (int work = blockIdx.x; work < total; work += gridDim.x, ++n) {
                 const int acc = n & 1;
                 const uint32_t tph = (uint32_t)(n >> 1) & 1u;
-                mbar_wait(&t_empty[acc], tph ^ 1);
+                mbar_wait(&t_empty[acc * 2 + t], tph ^ 1);
                 tc_fence_after();
-                const uint32_t d_addr = tmem_base + (uint32_t)(acc * 2 * TS);
+                const uint32_t d_addr = tmem_base + (uint32_t)(acc * 2 * TS + t * TS);
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(&a_full[kb], (uint32_t)(n & 1));
                     const uint32_t a_seg = (((smem_u32(sA + kb * Cfg::kSeg)) >> 4) & 0x3FFFu) | (kLboA << 16);
@@ -914,13 +929,11 @@ __global__ void __launch_bounds__(kConv4Threads, 1) conv4_kernel(const GemmArgs 
                             const uint32_t b_lo = b_st + (uint32_t)(tp * (Cfg::kWTap >> 4));
                             const uint32_t first = (kb | tap) != 0 ? 1u : 0u;
 #pragma unroll
-                            for (int t = 0; t < 2; ++t) {
-#pragma unroll
-                                for (int j = 0; j < KCH / 2; ++j) {
-                                    const uint64_t adesc = ((uint64_t)kDescHi << 32) | (uint64_t)(a_lo + (uint32_t)(2 * j) * kLboA + (uint32_t)(t * 128));
-                                    const uint64_t bdesc = ((uint64_t)kDescHi << 32) | (uint64_t)(b_lo + (uint32_t)(2 * j * NT));
-                                    umma_bf16(d_addr + (uint32_t)(t * TS), adesc, bdesc, idesc, j == 0 ? first : 1u);
-                                }
+                            for (int j = 0; j < KCH / 2; ++j) {
+                                if ((p.dbg & 2) && j > 0) continue;   // timing experiment: a quarter of the MMAs
+                                const uint64_t adesc = ((uint64_t)kDescHi << 32) | (uint64_t)(a_lo + (uint32_t)(2 * j) * kLboA + (uint32_t)(t * 128));
+                                const uint64_t bdesc = ((uint64_t)kDescHi << 32) | (uint64_t)(b_lo + (uint32_t)(2 * j * NT));
+                                umma_bf16(d_addr, adesc, bdesc, idesc, j == 0 ? first : 1u);
                             }
                         }
                         umma_commit(&w_empty[s]);
@@ -928,7 +941,7 @@ __global__ void __launch_bounds__(kConv4Threads, 1) conv4_kernel(const GemmArgs 
                     }
                     umma_commit(&a_empty[kb]);                  // this k-block's rows may be replaced by the next pair's
                 }
-                umma_commit(&t_full[acc]);
+                umma_commit(&t_full[acc * 2 + t]);
             }
         }
     } else {
@@ -965,7 +978,7 @@ __global__ void __launch_bounds__(kConv4Threads, 1) conv4_kernel(const GemmArgs 
                 const long long nrow = (long long)npair * kPairRows + t * 128 + row;
                 const int nrr = (int)(nrow % 110);
                 const bool nreal = nwork < total && nrow < (long long)p.n_boards * 110 && nrr >= 10 && (nrr % 10) != 9;
-                mbar_wait(&t_full[acc], tph);
+                mbar_wait(&t_full[acc * 2 + t], tph);
                 tc_fence_after();
                 // one 32-column slab: bias (+residual) (+ReLU), halo rows -> 0, bf16, 4 coalesced 16-byte stores
                 auto emit = [&](const uint32_t* v, const int c0) {
@@ -1026,7 +1039,7 @@ __global__ void __launch_bounds__(kConv4Threads, 1) conv4_kernel(const GemmArgs 
                     }
                 }
             } else {
-                mbar_wait(&t_full[acc], tph);
+                mbar_wait(&t_full[acc * 2 + t], tph);
                 tc_fence_after();
                 const long long b = mrow / 110;
                 const int pos = (rr / 10 - 1) * 9 + (rr % 10);
@@ -1054,7 +1067,7 @@ __global__ void __launch_bounds__(kConv4Threads, 1) conv4_kernel(const GemmArgs 
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&t_empty[acc]);
+            if (lane == 0) mbar_arrive(&t_empty[acc * 2 + t]);
         }
     }
 
@@ -1315,7 +1328,7 @@ __global__ void __launch_bounds__(kConv4Threads, 1) conv5_kernel(const GemmArgs 
                 }
             }
         }
-    } else {
+    } else if (warp < 10) {
         // ===================== epilogue (both CTAs): as v4, accumulator release goes to the leader =====================
         const int q = warp & 3;
         const int t = (warp - 2) >> 2;
@@ -1586,6 +1599,9 @@ extern "C" int xq_net_gemm(xq_ctx* c, const xq_gemm_desc* d, void* stream)
     if (!v1 && c->net_gen >= 5 && d->w_half && d->mode == 0 && d->nt == 128 && d->kch_iter == 8 && d->kchunks % 8 == 0 && d->kchunks <= 32)
         return launch_conv5<8>(c, a, s);
     if (!v1 && c->net_gen >= 4) {
+        // 128-channel layers: 3 taps per weight stage (48 KB x 3 stages): a stage hand-off costs the single MMA-issuing
+        // thread ~0.2 us (measured with XQ_NET_DBG=15), so fewer, larger stages beat a finer ring
+        if (d->mode == 0 && d->nt == 128 && d->kch_iter == 8 && d->kchunks == 16 && c->net_tps == 3) return launch_conv4<128, 8, false, 3>(c, a, s);
         if (d->mode == 0 && d->nt == 128 && d->kch_iter == 8 && d->kchunks % 8 == 0 && d->kchunks <= 32) return launch_conv4<128, 8, false, 1>(c, a, s);
         if (d->mode == 0 && d->nt == 128 && d->kch_iter == 2 && d->kchunks == 2) return launch_conv4<128, 2, false, 9>(c, a, s);
         if (d->mode == 1 && d->nt == 48 && d->kch_iter == 8 && d->kchunks % 8 == 0 && d->kchunks <= 32 && d->out2) return launch_conv4<48, 8, true, 1>(c, a, s);
