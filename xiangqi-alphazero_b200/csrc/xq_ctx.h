@@ -26,6 +26,7 @@ struct xq_ctx {
     void* net = nullptr;
     void* selfplay = nullptr;
     bool net_pdl = false;                 // XQ_NET_PDL=1: programmatic dependent launch between layers (measured: no gain, off by default)
+    bool net_fc4 = true;                  // XQ_NET_FC4=0: first-generation FC kernel
     int net_tps = 3;                      // XQ_NET_TPS=1: one tap per weight stage in the 128-channel conv
     int net_gen = 4;                      // XQ_NET_GEN=2: previous conv kernel generation (A/B comparisons)
     int net_cluster = 1;                  // XQ_NET_CLUSTER=1|2|4: CTAs per cluster sharing each weight stage by TMA multicast

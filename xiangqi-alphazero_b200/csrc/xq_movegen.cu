@@ -255,6 +255,7 @@ extern "C" int xq_create(int device, xq_ctx** out)
     if (const char* e = getenv("XQ_NET_CLUSTER")) c->net_cluster = atoi(e);
     if (const char* e = getenv("XQ_NET_GEN")) c->net_gen = atoi(e);
     if (const char* e = getenv("XQ_NET_TPS")) c->net_tps = atoi(e);
+    if (const char* e = getenv("XQ_NET_FC4")) c->net_fc4 = atoi(e) != 0;
     if (const char* e = getenv("XQ_NET_PDL")) c->net_pdl = atoi(e) != 0;
     XQ_CUDA(c, cudaSetDevice(device));
     cudaDeviceProp prop;

@@ -1466,6 +1466,188 @@ static int launch_conv5(xq_ctx* c, const GemmArgs& a, cudaStream_t s)
     return XQ_OK;
 }
 
+// =============================================================================================
+// fc4: dense layer (policy FC 2880 -> 8100) in the conv4 style
+// =============================================================================================
+// The first FC kernel (gemm_kernel<2>: 128x128 tiles, 3-stage ring, 2 CTAs/SM) spent more time handing
+// stages over than multiplying (4 MMAs per hand-off).  fc4: one CTA per SM, a 256-board x 128-output work item
+// (two M tiles share each weight stage, one MMA-issuing thread per tile), 48 KB stages (W 16 KB + A 2 x 16 KB,
+// the two M tiles are adjacent rows of the A planes so a chunk is ONE 4 KB bulk copy), 4-deep ring,
+// accumulators double buffered in TMEM (2 x 2 x 128 columns), epilogue on 8 warps.
+template <int KCH_, int STAGES_>
+struct Fc4CfgT {
+    static constexpr int kKch = KCH_;                          // 8 input features per chunk
+    static constexpr int kWBytes = kKch * 128 * 16;
+    static constexpr int kABytes = kKch * 256 * 16;
+    static constexpr int kStage = kWBytes + kABytes;
+    static constexpr int kStages = STAGES_;
+    static constexpr int kSmem = kStages * kStage + 512;
+};
+
+template <class Fc4Cfg>
+__global__ void __launch_bounds__(kConv4Threads, 1) fc4_kernel(const GemmArgs p)
+{
+    constexpr int S = Fc4Cfg::kStages, TS = 128, NT = 128;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Fc4Cfg::kStage);
+    uint64_t* w_full = bars;
+    uint64_t* w_empty = bars + S;
+    uint64_t* t_full = bars + 2 * S;          // [2 accumulator stages][2 tiles]
+    uint64_t* t_empty = t_full + 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 4);
+    __shared__ __align__(16) float sBias[2][128];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int iters = p.kchunks / Fc4Cfg::kKch;
+    const int m_pairs = (p.m_tiles + 1) / 2;
+    const int total = m_pairs * p.n_tiles;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < S; ++i) {
+            mbar_init(&w_full[i], 1);
+            mbar_init(&w_empty[i], 2);
+        }
+        for (int i = 0; i < 4; ++i) {
+            mbar_init(&t_full[i], 1);
+            mbar_init(&t_empty[i], 4);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int work = blockIdx.x; work < total; work += gridDim.x) {
+                const int pair = work / p.n_tiles, n_tile = work - pair * p.n_tiles;
+                const long long m0 = (long long)pair * 256;
+                const uint8_t* wt = p.w + (size_t)n_tile * iters * Fc4Cfg::kWBytes;
+                for (int it = 0; it < iters; ++it) {
+                    mbar_wait(&w_empty[s], ph ^ 1);
+                    uint8_t* st = smem + s * Fc4Cfg::kStage;
+                    mbar_expect_tx(&w_full[s], Fc4Cfg::kStage);
+                    bulk_g2s(st, wt + (size_t)it * Fc4Cfg::kWBytes, Fc4Cfg::kWBytes, &w_full[s]);
+#pragma unroll
+                    for (int c = 0; c < Fc4Cfg::kKch; ++c)
+                        bulk_g2s(st + Fc4Cfg::kWBytes + c * 4096,
+                                 p.a + ((size_t)(it * Fc4Cfg::kKch + c) * p.a_rows + (size_t)(p.a_row0 + m0)) * 16, 4096, &w_full[s]);
+                    if (++s == S) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1 || warp == 10) {
+        const int t = warp == 1 ? 0 : 1;
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(128, NT);
+            constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);
+            int s = 0;
+            uint32_t ph = 0;
+            int n = 0;
+            for (int work = blockIdx.x; work < total; work += gridDim.x, ++n) {
+                const int acc = n & 1;
+                const uint32_t tph = (uint32_t)(n >> 1) & 1u;
+                mbar_wait(&t_empty[acc * 2 + t], tph ^ 1);
+                tc_fence_after();
+                const uint32_t d_addr = tmem_base + (uint32_t)(acc * 2 * TS + t * TS);
+                for (int it = 0; it < iters; ++it) {
+                    mbar_wait(&w_full[s], ph);
+                    tc_fence_after();
+                    const uint32_t st = smem_u32(smem + s * Fc4Cfg::kStage);
+                    const uint32_t b_lo = ((st >> 4) & 0x3FFFu) | ((2048u >> 4) << 16);
+                    const uint32_t a_lo = (((st + Fc4Cfg::kWBytes + (uint32_t)t * 2048u) >> 4) & 0x3FFFu) | ((4096u >> 4) << 16);
+#pragma unroll
+                    for (int j = 0; j < Fc4Cfg::kKch / 2; ++j) {
+                        const uint64_t adesc = ((uint64_t)kDescHi << 32) | (uint64_t)(a_lo + (uint32_t)(2 * j) * (4096u >> 4));
+                        const uint64_t bdesc = ((uint64_t)kDescHi << 32) | (uint64_t)(b_lo + (uint32_t)(2 * j * NT));
+                        umma_bf16(d_addr, adesc, bdesc, idesc, (it | j) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&w_empty[s]);
+                    if (++s == S) { s = 0; ph ^= 1; }
+                }
+                umma_commit(&t_full[acc * 2 + t]);
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int t = (warp - 2) >> 2;
+        const int row = q * 32 + lane;
+        const int et = threadIdx.x - 64;          // 0..255 among the epilogue threads
+        int n = 0;
+        for (int work = blockIdx.x; work < total; work += gridDim.x, ++n) {
+            const int pair = work / p.n_tiles, n_tile = work - pair * p.n_tiles;
+            const int acc = n & 1;
+            const uint32_t tph = (uint32_t)(n >> 1) & 1u;
+            const long long m = (long long)pair * 256 + t * 128 + row;
+            const bool real = m < (long long)p.n_boards;
+            // this work item's 128 bias values -> shared memory (double buffered by item parity)
+            if (et < 128) sBias[acc][et] = p.bias[n_tile * NT + et];
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 * TS + t * TS);
+            mbar_wait(&t_full[acc * 2 + t], tph);
+            tc_fence_after();
+            auto emit = [&](const uint32_t* v, const int c0) {
+                if (!real) return;
+                uint4* dst = reinterpret_cast<uint4*>(p.out + ((size_t)m * p.out_stride + (size_t)(n_tile * NT + c0)) * 2);
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const float4 b0 = *reinterpret_cast<const float4*>(&sBias[acc][c0 + g * 8]);
+                    const float4 b1 = *reinterpret_cast<const float4*>(&sBias[acc][c0 + g * 8 + 4]);
+                    dst[g] = make_uint4(pack_bf16(__uint_as_float(v[g * 8 + 0]) + b0.x, __uint_as_float(v[g * 8 + 1]) + b0.y),
+                                        pack_bf16(__uint_as_float(v[g * 8 + 2]) + b0.z, __uint_as_float(v[g * 8 + 3]) + b0.w),
+                                        pack_bf16(__uint_as_float(v[g * 8 + 4]) + b1.x, __uint_as_float(v[g * 8 + 5]) + b1.y),
+                                        pack_bf16(__uint_as_float(v[g * 8 + 6]) + b1.z, __uint_as_float(v[g * 8 + 7]) + b1.w));
+                }
+            };
+            uint32_t va[32], vb[32];
+            tmem_ld32(taddr, va);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (i & 1) {
+                    if (i + 1 < 4) tmem_ld32(taddr + (uint32_t)((i + 1) * 32), va);
+                    emit(vb, i * 32);
+                } else {
+                    if (i + 1 < 4) tmem_ld32(taddr + (uint32_t)((i + 1) * 32), vb);
+                    emit(va, i * 32);
+                }
+                if (i + 1 < 4) tmem_ld_wait();
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&t_empty[acc * 2 + t]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+template <class Fc4Cfg>
+static int launch_fc4(xq_ctx* c, const GemmArgs& a, cudaStream_t s)
+{
+    static bool configured = false;
+    if (!configured) {
+        XQ_CUDA(c, cudaFuncSetAttribute(fc4_kernel<Fc4Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+        configured = true;
+    }
+    if (a.kchunks % Fc4Cfg::kKch) return xq_fail(c, XQ_ERR_ARG, "fc4: K/8 = %d is not a multiple of %d", a.kchunks, Fc4Cfg::kKch);
+    const int total = ((a.m_tiles + 1) / 2) * a.n_tiles;
+    const int grid = c->sm_count < total ? c->sm_count : total;
+    fc4_kernel<Fc4Cfg><<<grid, kConv4Threads, Fc4Cfg::kSmem, s>>>(a);
+    c->launches += 1;
+    XQ_CUDA(c, cudaGetLastError());
+    return XQ_OK;
+}
+
 // ---- value head: Linear(360,128)+ReLU -> Linear(128,1) -> tanh (model.py:74-83) ----------------
 // feats [B][90][4] fp32 (already conv1x1+BN+ReLU), w1t [360][128] fp32 with k = pos*4+ch, 16 boards per CTA.
 constexpr int kVhBoards = 16;
@@ -1598,6 +1780,12 @@ extern "C" int xq_net_gemm(xq_ctx* c, const xq_gemm_desc* d, void* stream)
     const int cl = c->net_cluster;
     if (!v1 && c->net_gen >= 5 && d->w_half && d->mode == 0 && d->nt == 128 && d->kch_iter == 8 && d->kchunks % 8 == 0 && d->kchunks <= 32)
         return launch_conv5<8>(c, a, s);
+    if (!v1 && c->net_gen >= 4 && c->net_fc4 && d->mode == 2 && d->nt == 128 && d->kch_iter == 8 && d->kchunks % 8 == 0) {
+        const int v = getenv("XQ_NET_FCK") ? atoi(getenv("XQ_NET_FCK")) : 12;
+        if (v == 16 && d->kchunks % 16 == 0) return launch_fc4<Fc4CfgT<16, 2>>(c, a, s);
+        if (v == 12 && d->kchunks % 12 == 0) return launch_fc4<Fc4CfgT<12, 3>>(c, a, s);
+        return launch_fc4<Fc4CfgT<8, 4>>(c, a, s);
+    }
     if (!v1 && c->net_gen >= 4) {
         // 128-channel layers: 3 taps per weight stage (48 KB x 3 stages): a stage hand-off costs the single MMA-issuing
         // thread ~0.2 us (measured with XQ_NET_DBG=15), so fewer, larger stages beat a finer ring

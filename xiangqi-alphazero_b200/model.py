@@ -137,7 +137,7 @@ class B200Net:
         pairs = (self.m_tiles + 1) // 2                            # conv kernels work on pairs of 128-row tiles,
         self.rows = ROW0 + ((pairs + 3) // 4) * 4 * 256 + 16       # clusters of up to 4 CTAs on 4 consecutive pairs
         self.b_tiles = (B + 127) // 128
-        self.fc_rows = self.b_tiles * 128
+        self.fc_rows = ((self.b_tiles + 1) // 2) * 256               # the FC kernel works on pairs of 128-board tiles
         bf = torch.bfloat16
         z = lambda *shape, dt=bf: torch.zeros(shape, dtype=dt, device=dev)
         self.x0 = z(2, self.rows, 8)                     # input planes (15 + 1 pad channels)
