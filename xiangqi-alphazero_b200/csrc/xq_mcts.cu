@@ -480,12 +480,22 @@ extern "C" int xq_mcts_create(xq_ctx* c, int max_games, long long node_capacity)
 {
     if (!c || max_games <= 0) return xq_fail(c, XQ_ERR_ARG, "xq_mcts_create: bad arguments");
     XQ_CUDA(c, cudaSetDevice(c->device));
+    if (node_capacity <= 0) node_capacity = (long long)max_games * 801 * 64;
+    if (node_capacity > 0x7fffff00ll) node_capacity = 0x7fffff00ll;
+    // One search state per context, shared by xq_mcts_* and xq_selfplay_*: it only ever grows, so a small
+    // request (a single-game MCTS object) never shrinks the arrays a self-play engine was built on.
+    if (MctsState* old = S_(c)) {
+        if (old->max_games >= max_games && old->cap_nodes >= node_capacity) {
+            old->n_games = 0;
+            return XQ_OK;
+        }
+        if (old->max_games > max_games) max_games = old->max_games;
+        if (old->cap_nodes > node_capacity) node_capacity = old->cap_nodes;
+    }
     xq_mcts_free_(c);
     MctsState* M = new MctsState();
     c->mcts = M;
     M->max_games = max_games;
-    if (node_capacity <= 0) node_capacity = (long long)max_games * 801 * 64;
-    if (node_capacity > 0x7fffff00ll) node_capacity = 0x7fffff00ll;
     M->cap_nodes = node_capacity;
     const size_t G = (size_t)max_games;
     XQ_CUDA(c, cudaMalloc(&M->board, G * kBoardPad));
@@ -995,6 +1005,8 @@ extern "C" int xq_selfplay_play(xq_ctx* c, const xq_selfplay_config* cfg, const 
     if (net->logits_kind != 1 && net->logits_kind != 2) return xq_fail(c, XQ_ERR_ARG, "xq_selfplay_play: logits_kind must be 1 (bf16) or 2 (f32)");
     MctsState& M = *Mp;
     SpState& P = *Pp;
+    if (M.max_games < P.n_slots) return xq_fail(c, XQ_ERR_STATE, "xq_selfplay_play: search state smaller than the slot count");
+    M.n_games = P.n_slots;     // a standalone xq_mcts_set_games call may have changed it since the last ply
     cudaStream_t s = (cudaStream_t)stream;
     SpConfig k;
     k.num_simulations = cfg->num_simulations;

@@ -52,10 +52,14 @@ def _play_local(model, config, my_games: int, local_device: int):
         return data, wins, total_steps, valid
     eng = engine(local_device)
     slots = min(my_games, int(os.environ.get("XQ_SELFPLAY_SLOTS", "4096")))
+    sims = int(getattr(config, "num_simulations", 200))
     key = (id(eng), slots, model.num_channels, model.num_res_blocks)
     sp = _ENGINES.get(key)
-    if sp is None or sp.max_games < my_games:
-        sp = SelfPlayEngine(eng, model, n_slots=slots, max_games=my_games)
+    if sp is None or sp.max_games < my_games or sp.max_simulations < sims:
+        if sp is not None:
+            _ENGINES.clear()
+            del sp
+        sp = SelfPlayEngine(eng, model, n_slots=slots, max_games=my_games, max_simulations=sims)
         _ENGINES.clear()
         _ENGINES[key] = sp
     else:

@@ -73,14 +73,20 @@ def decode_samples(raw: np.ndarray):
 
 class SelfPlayEngine:
     def __init__(self, eng: "xq_native.Engine", model, n_slots: int, max_games: int, sample_capacity=None,
-                 node_capacity: int = 0):
+                 node_capacity: int = 0, max_simulations: int = 800):
         self.e = eng
         self.n_slots = int(n_slots)
         self.max_games = int(max_games)
+        self.max_simulations = int(max_simulations)
         if sample_capacity is None:
             sample_capacity = self.max_games * 201 + self.n_slots
         self.sample_capacity = int(sample_capacity)
-        eng._check(eng.L.xq_selfplay_create(eng.h, self.n_slots, self.max_games, self.sample_capacity, int(node_capacity)))
+        if not node_capacity:
+            # one expansion per simulation (+ the root), at most 128 children each, 35 on average: 64 per
+            # expansion is a safe pool size and the kernels flag an overflow instead of writing past it
+            node_capacity = self.n_slots * (self.max_simulations + 2) * 64 + self.n_slots
+        self.node_capacity = int(node_capacity)
+        eng._check(eng.L.xq_selfplay_create(eng.h, self.n_slots, self.max_games, self.sample_capacity, self.node_capacity))
         self.net = None
         self.set_model(model)
         self.fetched = 0
@@ -112,6 +118,9 @@ class SelfPlayEngine:
         self.fetched = 0
 
     def play(self, cfg: _SpConfig, n_plies: int):
+        if cfg.num_simulations > self.max_simulations:
+            raise xq_native.XqError(f"num_simulations {cfg.num_simulations} exceeds the node pool sized for "
+                                    f"{self.max_simulations}: build the SelfPlayEngine with max_simulations >= it")
         self.e._check(self.e.L.xq_selfplay_play(self.e.h, C.byref(cfg), C.byref(self.plan), int(n_plies), self.e._stream()))
 
     def counters(self):
