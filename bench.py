@@ -168,7 +168,7 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": "positions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -275,10 +275,44 @@ def bench_movegen(args, rank, world, local_rank, dist):
         "gpu_launches": launches,
         "clocks": clocks,
     }
+    emit(line)
+
+
+class _QuietStdout:
+    """Route fd 1 to stderr while the benchmark runs (NCCL and other native libraries print banners to
+    stdout) and restore it for the single JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def restore(self):
+        if self.saved is not None:
+            sys.stdout.flush()
+            os.dup2(self.saved, 1)
+            os.close(self.saved)
+            self.saved = None
+
+    def __exit__(self, *exc):
+        self.restore()
+        return False
+
+
+QUIET = None
+
+
+def emit(line: dict):
+    """Print the one JSON line on the real stdout."""
+    q = QUIET or getattr(sys.modules.get("__main__"), "QUIET", None)   # bench_selfplay imports this file as a module
+    if q is not None:
+        q.restore()
     print(json.dumps(line), flush=True)
 
 
 def main():
+    global QUIET
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=6)
@@ -289,6 +323,7 @@ def main():
     args = ap.parse_args()
     if args.workload is None:
         args.workload = "selfplay" if os.path.exists(os.path.join(PKG, "selfplay_engine.py")) else "movegen"
+    QUIET = _QuietStdout().__enter__()
     if args.impl == "reference":
         if args.workload == "selfplay":
             sys.path.insert(0, ROOT)
@@ -317,6 +352,8 @@ def main():
     finally:
         if dist is not None:
             dist.destroy_process_group()
+        if QUIET is not None:
+            QUIET.restore()
 
 
 if __name__ == "__main__":

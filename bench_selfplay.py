@@ -193,7 +193,7 @@ def run(args, rank, world, local_rank, dist):
         "gpu_launches": launches,
         "clocks": clocks,
     }
-    print(json.dumps(line), flush=True)
+    bench.emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -281,6 +281,7 @@ def cpu_selfplay_rate(procs, sims=100, pool=None):
 
 
 def run_reference(args):
+    import bench
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -304,4 +305,4 @@ def run_reference(args):
             "cpu_baseline": last,
             "e2e": {"value": value, "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    bench.emit(line)
