@@ -139,3 +139,23 @@ def test_parallel_self_play_dropin(eng, net_model):
         fr, fc, tr, tc = decode_action(int(a))
         assert pm[encode_action(fr, 8 - fc, tr, 8 - tc)] == p[a]
     assert ps._augment_data([(s, p, z)])[1][1].tolist() == pm.tolist()
+
+
+def test_same_seed_same_games(eng, net_model):
+    """Counter-based RNG + deterministic kernels: two runs with one seed produce the same records
+    (the append order of records and the node numbering may differ, the content may not)."""
+    cfg = Cfg()
+    cfg.random_opening_moves = 4
+    cfg.num_simulations = 16
+    runs = []
+    for _ in range(2):
+        sp, c, dec, winner, plies = play(eng, net_model, cfg, slots=8, games=12, seed=77)
+        order = np.lexsort((dec["ply"], dec["uid"]))
+        runs.append((c["samples"], winner[:12].copy(), plies[:12].copy(),
+                     {k: dec[k][order] for k in ("board", "side", "n", "actions", "probs", "played", "uid", "ply")}))
+    a, b = runs
+    assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    for k in a[3]:
+        assert np.array_equal(a[3][k], b[3][k]), k
+    sp2, c2, dec2, w2, p2 = play(eng, net_model, cfg, slots=8, games=12, seed=78)
+    assert not np.array_equal(np.sort(dec2["played"]), np.sort(a[3]["played"])) or c2["samples"] != a[0]
