@@ -107,21 +107,30 @@ movegen_kernel(const int8_t* __restrict__ boards, const int8_t* __restrict__ sid
                 }
                 warp_sync();
                 const float turn = side == 1 ? 1.0f : 0.0f;
-                float2* out = reinterpret_cast<float2*>(planes + gi * (15 * kSquares));
-                // 675 float2 per position, lane stride 32 float2 = 64 elements: (plane, square) advance without division
-                int p = 0, sq = 2 * lane;
-                if (sq >= kSquares) { sq -= kSquares; p = 1; }
-                for (int e2 = lane; e2 < 15 * kSquares / 2; e2 += 32) {
+                float* outp = planes + gi * (15 * kSquares);
+                auto plane_val = [&](int p, int sq) { return p == 14 ? turn : (code[sq] == p ? 1.0f : 0.0f); };
+                // 1350 floats per position; positions alternate between 16-byte aligned and 8-byte offset bases:
+                // one float2 at the head (odd positions) or tail (even), 337 coalesced float4 in between
+                const int head = (int)(gi & 1) * 2;
+                if (lane == 0) {
                     float2 v;
-                    if (p == 14) {
-                        v.x = v.y = turn;
-                    } else {
-                        v.x = code[sq] == p ? 1.0f : 0.0f;
-                        v.y = code[sq + 1] == p ? 1.0f : 0.0f;
+                    if (head) { v.x = plane_val(0, 0); v.y = plane_val(0, 1); __stcs(reinterpret_cast<float2*>(outp), v); }
+                    else { v.x = plane_val(14, 88); v.y = plane_val(14, 89); __stcs(reinterpret_cast<float2*>(outp + 1348), v); }
+                }
+                float4* out4 = reinterpret_cast<float4*>(outp + head);
+                int e = head + 4 * lane;
+                int p = e / kSquares, sq = e - p * kSquares;
+                for (int k = lane; k < 337; k += 32) {
+                    float f[4];
+                    int pp = p, ss = sq;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        f[j] = plane_val(pp, ss);
+                        if (++ss == kSquares) { ss = 0; ++pp; }
                     }
-                    __stcs(out + e2, v);
-                    sq += 64;
-                    if (sq >= kSquares) { sq -= kSquares; ++p; }
+                    __stcs(out4 + k, make_float4(f[0], f[1], f[2], f[3]));
+                    sq += 128;                      // 32 lanes x 4 floats
+                    while (sq >= kSquares) { sq -= kSquares; ++p; }
                 }
             }
             warp_sync();

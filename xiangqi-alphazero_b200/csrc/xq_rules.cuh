@@ -346,18 +346,20 @@ __device__ __forceinline__ bool legal_after_move(const int8_t* b, const uint16_t
     return !attacked_sq_occ(b, rowocc, colocc, kr, kc, -side, from, to, mover);
 }
 
-// Pseudo-legal targets of one (piece, direction-slot) task in reference order.
-// WRITE=false counts, WRITE=true stores target squares at dst[0..].
-template <bool WRITE>
-__device__ __forceinline__ int gen_task(const int8_t* b, int side, int sq, int kind, int d, uint8_t* dst)
+// Pseudo-legal targets of one (piece, direction-slot) task in reference order, ONE pass: the (at most 9)
+// target squares are packed 7 bits each into a 64-bit word.  Rook and cannon rays are bit scans of the
+// row / column occupancy masks instead of cell walks; only the blocker's colour is read from the board.
+__device__ __forceinline__ int gen_task_packed(const int8_t* b, const uint16_t* rowocc, const uint16_t* colocc, int side,
+                                               int sq, int kind, int d, unsigned long long& packed)
 {
-    const int r = sq / 9, c = sq % 9;
+    const int r = sq / 9, c = sq - r * 9;
     int n = 0;
+    packed = 0ull;
     auto emit = [&](int t) {
-        if (WRITE) dst[n] = (uint8_t)t;
+        packed |= (unsigned long long)t << (7 * n);
         ++n;
     };
-    const int dr4 = (d == 0) ? -1 : (d == 1 ? 1 : 0);   // DIRECTIONS pyx:42-46
+    const int dr4 = (d == 0) ? -1 : (d == 1 ? 1 : 0);   // DIRECTIONS pyx:42-46: up, down, left, right
     const int dc4 = (d == 2) ? -1 : (d == 3 ? 1 : 0);
     switch (kind) {
     case 1: {  // king pyx:287-304
@@ -366,7 +368,7 @@ __device__ __forceinline__ int gen_task(const int8_t* b, int side, int sq, int k
         if (nr >= lo && nr <= lo + 2 && nc >= 3 && nc <= 5 && can_land(b[nr * 9 + nc], side)) emit(nr * 9 + nc);
         break;
     }
-    case 2: {  // advisor pyx:307-326: (dr,dc) = (-1,-1),(-1,1),(1,-1),(1,1); palace box only
+    case 2: {  // advisor pyx:307-326
         int nr = r + (d < 2 ? -1 : 1), nc = c + ((d & 1) ? 1 : -1);
         bool ok = nr >= 0 && nr < 10 && nc >= 3 && nc <= 5 && (side == 1 ? nr <= 2 : nr >= 7);
         if (ok && can_land(b[nr * 9 + nc], side)) emit(nr * 9 + nc);
@@ -394,41 +396,43 @@ __device__ __forceinline__ int gen_task(const int8_t* b, int side, int sq, int k
         }
         break;
     }
-    case 5: {  // rook pyx:370-396
-        int nr = r + dr4, nc = c + dc4;
-        while (nr >= 0 && nr < 10 && nc >= 0 && nc < 9) {
-            int p = b[nr * 9 + nc];
-            if (p == 0) emit(nr * 9 + nc);
-            else {
-                if (is_foe(p, side)) emit(nr * 9 + nc);
-                break;
+    case 5:
+    case 6: {  // rook pyx:370-396, cannon pyx:399-431 along one ray
+        // line = occupancy of the ray's row (d >= 2) or column (d < 2); pos = own index on it; step = square stride
+        const bool along_row = d >= 2;
+        const unsigned line = along_row ? rowocc[r] : colocc[c];
+        const int pos = along_row ? c : r;
+        const int len = along_row ? 9 : 10;
+        const int stride = along_row ? 1 : 9;
+        const bool neg = (d == 0 || d == 2);             // toward smaller index
+        int first = -1, second = -1;                      // indices of the first and second piece on the ray
+        if (neg) {
+            unsigned m = line & ((1u << pos) - 1u);
+            if (m) {
+                first = 31 - __clz(m);
+                m ^= 1u << first;
+                if (m) second = 31 - __clz(m);
             }
-            nr += dr4;
-            nc += dc4;
+        } else {
+            unsigned m = line >> (pos + 1);
+            if (m) {
+                first = pos + __ffs(m);
+                m &= m - 1u;
+                if (m) second = pos + __ffs(m);
+            }
+        }
+        const int base = along_row ? r * 9 : c;           // square = base + index * stride
+        const int end = first >= 0 ? first : (neg ? -1 : len);   // empties run up to (not including) `end`
+        if (neg) { for (int i = pos - 1; i > end; --i) emit(base + i * stride); }
+        else     { for (int i = pos + 1; i < end; ++i) emit(base + i * stride); }
+        if (kind == 5) {
+            if (first >= 0 && is_foe(b[base + first * stride], side)) emit(base + first * stride);
+        } else {
+            if (second >= 0 && is_foe(b[base + second * stride], side)) emit(base + second * stride);
         }
         break;
     }
-    case 6: {  // cannon pyx:399-431
-        int nr = r + dr4, nc = c + dc4;
-        while (nr >= 0 && nr < 10 && nc >= 0 && nc < 9 && b[nr * 9 + nc] == 0) {
-            emit(nr * 9 + nc);
-            nr += dr4;
-            nc += dc4;
-        }
-        nr += dr4;   // hop over the screen (if we ran off the board the loop below is empty)
-        nc += dc4;
-        while (nr >= 0 && nr < 10 && nc >= 0 && nc < 9) {
-            int p = b[nr * 9 + nc];
-            if (p != 0) {
-                if (is_foe(p, side)) emit(nr * 9 + nc);
-                break;
-            }
-            nr += dr4;
-            nc += dc4;
-        }
-        break;
-    }
-    case 7: {  // pawn pyx:434-484: slot 0 forward, 1 left, 2 right (sideways once across the river)
+    case 7: {  // pawn pyx:434-484
         int fwd = side == 1 ? 1 : -1;
         bool crossed = side == 1 ? r >= 5 : r <= 4;
         if (d == 0) {
@@ -496,14 +500,17 @@ __device__ __forceinline__ MovegenResult warp_movegen(const int8_t* b, int side,
             int p = b[sq];
             kind = p < 0 ? -p : p;
         }
-        int cnt = (sq >= 0) ? gen_task<false>(b, side, sq, kind, d, nullptr) : 0;
+        unsigned long long packed = 0ull;
+        int cnt = (sq >= 0) ? gen_task_packed(b, S.rowocc, S.colocc, side, sq, kind, d, packed) : 0;
         int total;
         int incl = warp_incl_scan(cnt, &total);
         int off = n_pseudo + incl - cnt;
         if (cnt > 0) {
             if (off + cnt <= kMaxPseudo) {
-                gen_task<true>(b, side, sq, kind, d, &S.pto[off]);
-                for (int i = 0; i < cnt; ++i) S.pfrom[off + i] = (uint8_t)sq;
+                for (int i = 0; i < cnt; ++i) {
+                    S.pto[off + i] = (uint8_t)((packed >> (7 * i)) & 127ull);
+                    S.pfrom[off + i] = (uint8_t)sq;
+                }
             } else {
                 res.overflow = true;
             }
