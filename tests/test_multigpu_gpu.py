@@ -1,0 +1,21 @@
+"""Two-process NCCL run of the drop-in parallel_self_play (skipped on a single-GPU box; the gloo
+version of the same fan-in runs on CPU in tests/test_multirank_cpu.py)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_two_gpu_self_play_shards_and_gathers():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29577", os.path.join(ROOT, "tests", "mgpu_selfplay_script.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+    assert "MGPU_OK ranks=2 games=7" in out.stdout

@@ -87,6 +87,9 @@ def parallel_self_play(model, config, num_workers: Optional[int] = None, use_gpu
     my_games = shard_games(num_games, rank, world)
     start = time.time()
     local_device = int(os.environ.get("LOCAL_RANK", "0")) if dist else 0
+    if dist and dist.get_backend() == "nccl":
+        import torch
+        torch.cuda.set_device(local_device)          # object collectives stage through the current CUDA device
     data, wins, total_steps, valid = _play_local(model, config, my_games, local_device)
     if dist and world > 1:
         parts = [None] * world
