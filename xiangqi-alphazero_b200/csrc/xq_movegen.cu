@@ -23,6 +23,7 @@ constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
 constexpr int kTile = 64;                       // boards per CTA tile
 constexpr int kTileBytes = kTile * kSquares;    // 5760, multiple of 16
+constexpr int kPlaneWords = 44;                 // 1350 bits = 43 words, + 1 so that the funnel shift may read word 43
 
 struct __align__(16) MovegenSmem {
     int8_t boards[2][kTileBytes];
@@ -31,7 +32,8 @@ struct __align__(16) MovegenSmem {
     uint8_t chk_out[2][kTile];
     uint64_t bar[2];
     WarpScratch ws[kWarps];
-    uint8_t code[kWarps][96];                   // per-square plane index (255 = empty)
+    uint32_t pbits[kWarps][kPlaneWords];        // the 1350 plane values of a position as bits
+    float4 nib_lut[16];                         // 4 bits -> 4 floats
 };
 
 template <bool PLANES>
@@ -50,6 +52,9 @@ movegen_kernel(const int8_t* __restrict__ boards, const int8_t* __restrict__ sid
         mbar_init(&sm.bar[1], 1);
         mbar_fence_init();
     }
+    if (PLANES && threadIdx.x < 16)
+        sm.nib_lut[threadIdx.x] = make_float4((threadIdx.x & 1) ? 1.0f : 0.0f, (threadIdx.x & 2) ? 1.0f : 0.0f,
+                                              (threadIdx.x & 4) ? 1.0f : 0.0f, (threadIdx.x & 8) ? 1.0f : 0.0f);
     __syncthreads();
 
     auto tile_is_bulk = [&](int t) { return bulk_ok && (t + 1) * kTile <= B; };
@@ -99,38 +104,47 @@ movegen_kernel(const int8_t* __restrict__ boards, const int8_t* __restrict__ sid
                 __stcs(reinterpret_cast<uint2*>(actions + gi * kMaxMoves) + lane, v);
             }
             if (PLANES) {
-                // game.py:618-640: plane = kind-1 for the side to move, 7+kind-1 for the other side
-                uint8_t* code = sm.code[warp];
-                for (int sq = lane; sq < kSquares; sq += 32) {
-                    int v = b[sq] * side;
-                    code[sq] = v > 0 ? (uint8_t)(v - 1) : (v < 0 ? (uint8_t)(6 - v) : (uint8_t)255);
-                }
+                // game.py:618-640: plane = kind-1 for the side to move, 7+kind-1 for the other side, plane 14 = 1
+                // iff red moves.  The 1350 values are first set as BITS (one shared-memory atomic per piece), then
+                // every lane expands 4 bits at a time into one float4 through a 16-entry table: ~10 instructions
+                // per 16-byte store instead of 4 compares + selects.
+                uint32_t* bits = sm.pbits[warp];
+                bits[lane] = 0u;
+                if (lane < kPlaneWords - 32) bits[32 + lane] = 0u;
                 warp_sync();
-                const float turn = side == 1 ? 1.0f : 0.0f;
+                for (int sq = lane; sq < kSquares; sq += 32) {
+                    const int v = b[sq] * side;
+                    if (v != 0) {
+                        const int e = (v > 0 ? v - 1 : 6 - v) * kSquares + sq;
+                        atomicOr(&bits[e >> 5], 1u << (e & 31));
+                    }
+                }
+                // plane 14 = elements 1260..1349 = bits 12..31 of word 39, words 40-41, bits 0..5 of word 42
+                if (side == 1 && lane < 4)
+                    atomicOr(&bits[39 + lane], lane == 0 ? 0xfffff000u : (lane == 3 ? 0x3fu : 0xffffffffu));
+                warp_sync();
                 float* outp = planes + gi * (15 * kSquares);
-                auto plane_val = [&](int p, int sq) { return p == 14 ? turn : (code[sq] == p ? 1.0f : 0.0f); };
                 // 1350 floats per position; positions alternate between 16-byte aligned and 8-byte offset bases:
                 // one float2 at the head (odd positions) or tail (even), 337 coalesced float4 in between
                 const int head = (int)(gi & 1) * 2;
                 if (lane == 0) {
+                    const uint32_t two = head ? bits[0] : bits[42] >> 4;
                     float2 v;
-                    if (head) { v.x = plane_val(0, 0); v.y = plane_val(0, 1); __stcs(reinterpret_cast<float2*>(outp), v); }
-                    else { v.x = plane_val(14, 88); v.y = plane_val(14, 89); __stcs(reinterpret_cast<float2*>(outp + 1348), v); }
+                    v.x = (two & 1u) ? 1.0f : 0.0f;
+                    v.y = (two & 2u) ? 1.0f : 0.0f;
+                    __stcs(reinterpret_cast<float2*>(head ? outp : outp + 1348), v);
                 }
                 float4* out4 = reinterpret_cast<float4*>(outp + head);
-                int e = head + 4 * lane;
-                int p = e / kSquares, sq = e - p * kSquares;
-                for (int k = lane; k < 337; k += 32) {
-                    float f[4];
-                    int pp = p, ss = sq;
+                const int e0 = head + 4 * lane;              // first element of this lane's float4 in iteration 0
+                const int sh = e0 & 31;
+                const uint32_t* wp = bits + (e0 >> 5);       // advances 4 words (128 elements) per iteration
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        f[j] = plane_val(pp, ss);
-                        if (++ss == kSquares) { ss = 0; ++pp; }
+                for (int it = 0; it < 11; ++it) {
+                    const int k = it * 32 + lane;
+                    if (it < 10 || k < 337) {
+                        const uint32_t nib = __funnelshift_r(wp[4 * it], wp[4 * it + 1], sh) & 15u;
+                        __stcs(out4 + k, sm.nib_lut[nib]);
                     }
-                    __stcs(out4 + k, make_float4(f[0], f[1], f[2], f[3]));
-                    sq += 128;                      // 32 lanes x 4 floats
-                    while (sq >= kSquares) { sq -= kSquares; ++p; }
                 }
             }
             warp_sync();

@@ -115,8 +115,7 @@ static __device__ __noinline__ int warp_argmax_first(double best, int best_i)
 }
 
 struct alignas(16) WarpScratch {
-    uint8_t pfrom[kMaxPseudo];
-    uint8_t pto[kMaxPseudo];
+    uint16_t pm[kMaxPseudo];      // pseudo-legal moves in reference order: from << 7 | to
     int16_t actions[kMaxMoves];   // compacted legal actions, unused slots = -1
     uint8_t own_sq[96];           // own-piece squares in row-major order (phase A task table)
     uint16_t rowocc[10];          // occupancy of each row (bit c) and
@@ -346,66 +345,73 @@ __device__ __forceinline__ bool legal_after_move(const int8_t* b, const uint16_t
     return !attacked_sq_occ(b, rowocc, colocc, kr, kc, -side, from, to, mover);
 }
 
-// Pseudo-legal targets of one (piece, direction-slot) task in reference order, ONE pass: the (at most 9)
-// target squares are packed 7 bits each into a 64-bit word.  Rook and cannon rays are bit scans of the
-// row / column occupancy masks instead of cell walks; only the blocker's colour is read from the board.
-__device__ __forceinline__ int gen_task_packed(const int8_t* b, const uint16_t* rowocc, const uint16_t* colocc, int side,
-                                               int sq, int kind, int d, unsigned long long& packed)
+// ---- phase A tables ------------------------------------------------------------------------------
+// Leaper moves (king, advisor, elephant, knight, pawn) of one (kind, direction slot d) task, two entries
+// per task (only the knight uses the second: slot d covers KNIGHT_MOVES[2d], [2d+1], pyx:31-39).
+// Entry: byte0 flags, byte1 dr, byte2 dc, byte3 leg offset in squares (0 = no leg).
+//   flags: 1 valid, 2 target must be in the mover's palace (king pyx:287-304, advisor pyx:307-326: the Cython
+//   advisor only checks the palace box), 4 target must be on the mover's half (elephant pyx:329-349),
+//   8 dr is multiplied by side (pawn forward, pyx:434-484), 16 only after crossing the river (pawn sideways).
+// One table-driven path replaces a 5-way divergent switch: a warp iteration holds tasks of every kind.
+#define XQ_LEAP(fl, dr, dc, leg) \
+    ((uint32_t)(fl) | ((uint32_t)(uint8_t)(int8_t)(dr) << 8) | ((uint32_t)(uint8_t)(int8_t)(dc) << 16) | \
+     ((uint32_t)(uint8_t)(int8_t)(leg) << 24))
+__device__ const uint2 kLeapTable[32] = {
+    // kind 0 (empty)
+    {0, 0}, {0, 0}, {0, 0}, {0, 0},
+    // kind 1 king: DIRECTIONS pyx:42-46 up, down, left, right
+    {XQ_LEAP(3, -1, 0, 0), 0}, {XQ_LEAP(3, 1, 0, 0), 0}, {XQ_LEAP(3, 0, -1, 0), 0}, {XQ_LEAP(3, 0, 1, 0), 0},
+    // kind 2 advisor: (dr, dc) in (-1,-1), (-1,1), (1,-1), (1,1)
+    {XQ_LEAP(3, -1, -1, 0), 0}, {XQ_LEAP(3, -1, 1, 0), 0}, {XQ_LEAP(3, 1, -1, 0), 0}, {XQ_LEAP(3, 1, 1, 0), 0},
+    // kind 3 elephant: two steps diagonally, eye = one step
+    {XQ_LEAP(5, -2, -2, -10), 0}, {XQ_LEAP(5, -2, 2, -8), 0}, {XQ_LEAP(5, 2, -2, 8), 0}, {XQ_LEAP(5, 2, 2, 10), 0},
+    // kind 4 knight: KNIGHT_MOVES[2d], [2d+1] with the leg next to the knight on its long axis
+    {XQ_LEAP(1, -2, -1, -9), XQ_LEAP(1, -2, 1, -9)}, {XQ_LEAP(1, 2, -1, 9), XQ_LEAP(1, 2, 1, 9)},
+    {XQ_LEAP(1, -1, -2, -1), XQ_LEAP(1, -1, 2, 1)}, {XQ_LEAP(1, 1, -2, -1), XQ_LEAP(1, 1, 2, 1)},
+    // kinds 5, 6 rook / cannon: slider path
+    {0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0},
+    // kind 7 pawn: forward, left, right
+    {XQ_LEAP(9, 1, 0, 0), 0}, {XQ_LEAP(17, 0, -1, 0), 0}, {XQ_LEAP(17, 0, 1, 0), 0}, {0, 0},
+};
+
+// one leaper entry -> target square or -1
+__device__ __forceinline__ int leap_target(const int8_t* b, int side, int sq, int r, int c, uint32_t e)
+{
+    if (!(e & 1u)) return -1;
+    int dr = (int)(int8_t)(e >> 8), dc = (int)(int8_t)(e >> 16), leg = (int)(int8_t)(e >> 24);
+    if (e & 8u) dr *= side;
+    const int nr = r + dr, nc = c + dc;
+    bool ok = (unsigned)nr < 10u && (unsigned)nc < 9u;
+    if (e & 2u) ok = ok && nc >= 3 && nc <= 5 && (side == 1 ? nr <= 2 : nr >= 7);
+    if (e & 4u) ok = ok && (side == 1 ? nr <= 4 : nr >= 5);
+    if (e & 16u) ok = ok && (side == 1 ? r >= 5 : r <= 4);
+    if (!ok) return -1;
+    if (leg != 0 && b[sq + leg] != 0) return -1;
+    const int t = nr * 9 + nc;
+    return (b[t] * side <= 0) ? t : -1;       // _can_move_to: empty or enemy
+}
+
+// Pseudo-legal targets of one (piece, direction slot) task in reference order, as a run plus one extra target:
+// squares t0, t0+step, ... (n_run of them) followed by x (if >= 0).  Leapers: run = first table entry (0/1
+// squares), x = second entry.  Rook pyx:370-396 / cannon pyx:399-431: run = the empty squares up to the first
+// blocker (a bit scan of the row / column occupancy), x = the capture (first blocker for the rook, second for
+// the cannon) when it is an enemy piece.
+__device__ __forceinline__ int gen_task_run(const int8_t* b, const uint16_t* rowocc, const uint16_t* colocc, int side,
+                                            int sq, int kind, int d, int& t0, int& step, int& x)
 {
     const int r = sq / 9, c = sq - r * 9;
-    int n = 0;
-    packed = 0ull;
-    auto emit = [&](int t) {
-        packed |= (unsigned long long)t << (7 * n);
-        ++n;
-    };
-    const int dr4 = (d == 0) ? -1 : (d == 1 ? 1 : 0);   // DIRECTIONS pyx:42-46: up, down, left, right
-    const int dc4 = (d == 2) ? -1 : (d == 3 ? 1 : 0);
-    switch (kind) {
-    case 1: {  // king pyx:287-304
-        int nr = r + dr4, nc = c + dc4;
-        int lo = side == 1 ? 0 : 7;
-        if (nr >= lo && nr <= lo + 2 && nc >= 3 && nc <= 5 && can_land(b[nr * 9 + nc], side)) emit(nr * 9 + nc);
-        break;
-    }
-    case 2: {  // advisor pyx:307-326
-        int nr = r + (d < 2 ? -1 : 1), nc = c + ((d & 1) ? 1 : -1);
-        bool ok = nr >= 0 && nr < 10 && nc >= 3 && nc <= 5 && (side == 1 ? nr <= 2 : nr >= 7);
-        if (ok && can_land(b[nr * 9 + nc], side)) emit(nr * 9 + nc);
-        break;
-    }
-    case 3: {  // elephant pyx:329-349
-        int sr = (d < 2 ? -1 : 1), sc = ((d & 1) ? 1 : -1);
-        int nr = r + 2 * sr, nc = c + 2 * sc;
-        bool ok = nr >= 0 && nr < 10 && nc >= 0 && nc < 9 && (side == 1 ? nr <= 4 : nr >= 5);
-        if (ok && b[(r + sr) * 9 + c + sc] == 0 && can_land(b[nr * 9 + nc], side)) emit(nr * 9 + nc);
-        break;
-    }
-    case 4: {  // knight pyx:352-367: slot d covers KNIGHT_MOVES[2d], [2d+1]
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            int i = 2 * d + h;
-            int jr = (i < 4) ? ((i < 2) ? -2 : 2) : ((i < 6) ? -1 : 1);
-            int jc = (i < 4) ? ((i & 1) ? 1 : -1) : ((i & 1) ? 2 : -2);
-            int lr = (i < 4) ? ((i < 2) ? -1 : 1) : 0;
-            int lc = (i < 4) ? 0 : ((i & 1) ? 1 : -1);
-            int nr = r + jr, nc = c + jc;
-            if (nr < 0 || nr >= 10 || nc < 0 || nc >= 9) continue;
-            if (b[(r + lr) * 9 + c + lc] != 0) continue;
-            if (can_land(b[nr * 9 + nc], side)) emit(nr * 9 + nc);
-        }
-        break;
-    }
-    case 5:
-    case 6: {  // rook pyx:370-396, cannon pyx:399-431 along one ray
-        // line = occupancy of the ray's row (d >= 2) or column (d < 2); pos = own index on it; step = square stride
+    int n_run = 0;
+    t0 = 0;
+    step = 0;
+    x = -1;
+    if (kind == 5 || kind == 6) {
         const bool along_row = d >= 2;
         const unsigned line = along_row ? rowocc[r] : colocc[c];
         const int pos = along_row ? c : r;
         const int len = along_row ? 9 : 10;
         const int stride = along_row ? 1 : 9;
-        const bool neg = (d == 0 || d == 2);             // toward smaller index
-        int first = -1, second = -1;                      // indices of the first and second piece on the ray
+        const bool neg = (d & 1) == 0;                    // d = 0 up, 2 left: toward smaller index
+        int first = -1, second = -1;
         if (neg) {
             unsigned m = line & ((1u << pos) - 1u);
             if (m) {
@@ -421,34 +427,127 @@ __device__ __forceinline__ int gen_task_packed(const int8_t* b, const uint16_t* 
                 if (m) second = pos + __ffs(m);
             }
         }
-        const int base = along_row ? r * 9 : c;           // square = base + index * stride
-        const int end = first >= 0 ? first : (neg ? -1 : len);   // empties run up to (not including) `end`
-        if (neg) { for (int i = pos - 1; i > end; --i) emit(base + i * stride); }
-        else     { for (int i = pos + 1; i < end; ++i) emit(base + i * stride); }
-        if (kind == 5) {
-            if (first >= 0 && is_foe(b[base + first * stride], side)) emit(base + first * stride);
-        } else {
-            if (second >= 0 && is_foe(b[base + second * stride], side)) emit(base + second * stride);
+        const int end = first >= 0 ? first : (neg ? -1 : len);
+        n_run = neg ? pos - 1 - end : end - pos - 1;
+        step = neg ? -stride : stride;
+        t0 = sq + step;
+        const int cap = kind == 5 ? first : second;
+        if (cap >= 0) {
+            const int csq = sq + (cap - pos) * stride;
+            if (is_foe(b[csq], side)) x = csq;
         }
-        break;
-    }
-    case 7: {  // pawn pyx:434-484
-        int fwd = side == 1 ? 1 : -1;
-        bool crossed = side == 1 ? r >= 5 : r <= 4;
-        if (d == 0) {
-            int nr = r + fwd;
-            if (nr >= 0 && nr < 10 && can_land(b[nr * 9 + c], side)) emit(nr * 9 + c);
-        } else if (d == 1) {
-            if (crossed && c - 1 >= 0 && can_land(b[r * 9 + c - 1], side)) emit(r * 9 + c - 1);
-        } else if (d == 2) {
-            if (crossed && c + 1 < 9 && can_land(b[r * 9 + c + 1], side)) emit(r * 9 + c + 1);
+    } else {
+        const uint2 e = kLeapTable[(kind <= 7 ? kind : 0) * 4 + d];
+        const int a = leap_target(b, side, sq, r, c, e.x);
+        if (a >= 0) {
+            t0 = a;
+            n_run = 1;
         }
-        break;
+        if (e.y) x = leap_target(b, side, sq, r, c, e.y);
     }
-    default:
-        break;
+    return n_run;
+}
+
+// ---- attack tests used by the legality phase ---------------------------------------------------------
+// Both directions of one line (the king's row or column) on the overlaid board: first piece = rook/king test,
+// second piece = cannon test (pyx:104-153).  line = occupancy with the overlay applied, pos = the king's index
+// on it, sq0 = square of index 0, stride = squares per index.
+__device__ __forceinline__ bool line_attacked(const int8_t* b, unsigned line, int pos, int sq0, int stride, int by,
+                                              int from, int to, int mover)
+{
+    const int rook = 5 * by, cannon = 6 * by, king = by;
+    unsigned m = line & ((1u << pos) - 1u);
+    if (m) {
+        const int i1 = 31 - __clz(m);
+        const int p1 = cell_after(b, sq0 + i1 * stride, from, to, mover);
+        if (p1 == rook || p1 == king) return true;
+        m ^= 1u << i1;
+        if (m && cell_after(b, sq0 + (31 - __clz(m)) * stride, from, to, mover) == cannon) return true;
     }
-    return n;
+    m = line >> (pos + 1);
+    if (m) {
+        const int i1 = pos + __ffs(m);
+        const int p1 = cell_after(b, sq0 + i1 * stride, from, to, mover);
+        if (p1 == rook || p1 == king) return true;
+        m &= m - 1u;
+        if (m && cell_after(b, sq0 + (pos + __ffs(m)) * stride, from, to, mover) == cannon) return true;
+    }
+    return false;
+}
+
+// _is_attacked (pyx:104-189) spread over the 16 lanes of a half warp: sub-lanes 0-3 one ray each, 4-11 one knight
+// origin each, 12-14 the three pawn origins.  Each half warp answers its own query (kr, kc, overlay from/to/mover;
+// from < 0: no overlay); the returned ballot has the low / high 16 bits set where a half found an attacker.
+__device__ __forceinline__ unsigned warp_attacked_pair(const int8_t* b, const uint16_t* rowocc, const uint16_t* colocc,
+                                                       bool active, int kr, int kc, int by, int from, int to, int mover)
+{
+    const int l = lane_id() & 15;
+    bool hit = false;
+    if (active) {
+        if (l < 4) {
+            const bool col = l < 2;
+            unsigned line = col ? colocc[kc] : rowocc[kr];
+            const int pos = col ? kr : kc;
+            const int sq0 = col ? kc : kr * 9;
+            const int stride = col ? 9 : 1;
+            if (from >= 0) {
+                const int fr = from / 9, fc = from - fr * 9, tr = to / 9, tc = to - tr * 9;
+                if (col) {
+                    if (fc == kc) line &= ~(1u << fr);
+                    if (tc == kc) line |= 1u << tr;
+                } else {
+                    if (fr == kr) line &= ~(1u << fc);
+                    if (tr == kr) line |= 1u << tc;
+                }
+            }
+            const int rook = 5 * by, cannon = 6 * by, king = by;
+            unsigned m;
+            int i1 = -1, i2 = -1;
+            if ((l & 1) == 0) {
+                m = line & ((1u << pos) - 1u);
+                if (m) {
+                    i1 = 31 - __clz(m);
+                    m ^= 1u << i1;
+                    if (m) i2 = 31 - __clz(m);
+                }
+            } else {
+                m = line >> (pos + 1);
+                if (m) {
+                    i1 = pos + __ffs(m);
+                    m &= m - 1u;
+                    if (m) i2 = pos + __ffs(m);
+                }
+            }
+            if (i1 >= 0) {
+                const int p1 = cell_after(b, sq0 + i1 * stride, from, to, mover);
+                hit = (p1 == rook || p1 == king);
+                if (!hit && i2 >= 0) hit = cell_after(b, sq0 + i2 * stride, from, to, mover) == cannon;
+            }
+        } else if (l < 12) {
+            const int i = l - 4;
+            const int jr = (i < 4) ? ((i < 2) ? -2 : 2) : ((i < 6) ? -1 : 1);
+            const int jc = (i < 4) ? ((i & 1) ? 1 : -1) : ((i & 1) ? 2 : -2);
+            const int nr = kr + jr, nc = kc + jc;
+            if ((unsigned)nr < 10u && (unsigned)nc < 9u && cell_after(b, nr * 9 + nc, from, to, mover) == 4 * by) {
+                int lr = nr, lc = nc;
+                if (i < 4) lr = nr - jr / 2; else lc = nc - jc / 2;
+                hit = cell_after(b, lr * 9 + lc, from, to, mover) == 0;
+            }
+        } else if (l < 15) {
+            const int j = l - 12;
+            int pr = kr, pc = kc;
+            bool ok;
+            if (j == 0) {
+                pr = kr - by;                               // the pawn stands one step behind its forward move
+                ok = (unsigned)pr < 10u;
+            } else {
+                pc = kc + (j == 1 ? -1 : 1);
+                ok = (by == 1 ? kr >= 5 : kr <= 4) && (unsigned)pc < 9u;
+            }
+            if (ok) hit = cell_after(b, pr * 9 + pc, from, to, mover) == 7 * by;
+        }
+    }
+    return warp_ballot(hit);
 }
 
 struct MovegenResult {
@@ -492,25 +591,26 @@ __device__ __forceinline__ MovegenResult warp_movegen(const int8_t* b, int side,
         n_pieces += __popc(m);
     }
     warp_sync();
+    bool odd_king = false;        // a king-valued own piece that is not THE palace king (unreachable boards)
     for (int t0 = 0; t0 < 4 * n_pieces; t0 += 32) {
         const int t = t0 + lane;
-        int sq = -1, kind = 0, d = t & 3;
+        int cnt = 0, first_t = 0, step = 0, x = -1, n_run = 0, sq = 0;
         if (t < 4 * n_pieces) {
             sq = S.own_sq[t >> 2];
-            int p = b[sq];
-            kind = p < 0 ? -p : p;
+            const int p = b[sq];
+            const int kind = p < 0 ? -p : p;
+            if (kind == 1 && sq != res.kings.own_sq) odd_king = true;
+            n_run = gen_task_run(b, S.rowocc, S.colocc, side, sq, kind, t & 3, first_t, step, x);
+            cnt = n_run + (x >= 0 ? 1 : 0);
         }
-        unsigned long long packed = 0ull;
-        int cnt = (sq >= 0) ? gen_task_packed(b, S.rowocc, S.colocc, side, sq, kind, d, packed) : 0;
         int total;
-        int incl = warp_incl_scan(cnt, &total);
-        int off = n_pseudo + incl - cnt;
+        const int incl = warp_incl_scan(cnt, &total);
+        const int off = n_pseudo + incl - cnt;
         if (cnt > 0) {
             if (off + cnt <= kMaxPseudo) {
-                for (int i = 0; i < cnt; ++i) {
-                    S.pto[off + i] = (uint8_t)((packed >> (7 * i)) & 127ull);
-                    S.pfrom[off + i] = (uint8_t)sq;
-                }
+                const int hi = sq << 7;
+                for (int i = 0; i < n_run; ++i) S.pm[off + i] = (uint16_t)(hi | (first_t + i * step));
+                if (x >= 0) S.pm[off + n_run] = (uint16_t)(hi | x);
             } else {
                 res.overflow = true;
             }
@@ -521,32 +621,106 @@ __device__ __forceinline__ MovegenResult warp_movegen(const int8_t* b, int side,
     if (n_pseudo > kMaxPseudo) n_pseudo = kMaxPseudo;
     // unused output slots read back as -1
     for (int i = lane; i < kMaxMoves; i += 32) S.actions[i] = -1;
-    warp_sync();
 
-    // ---- phase B: legality + ordered compaction; item n_pseudo is the in-check probe -----
-    int n_legal = 0;
-    bool chk = false;
-    for (int i0 = 0; i0 <= n_pseudo; i0 += 32) {
-        const int i = i0 + lane;
-        bool ok = false;
-        int from = 0, to = 0;
-        if (i < n_pseudo) {
-            from = S.pfrom[i];
-            to = S.pto[i];
-            ok = legal_after_move(b, S.rowocc, S.colocc, side, res.kings, from, to);
-        } else if (i == n_pseudo) {
-            // cy_is_in_check (pyx:543-555): missing king => True
-            int k = res.kings.own_sq;
-            chk = (k < 0) ? true : attacked_sq_occ(b, S.rowocc, S.colocc, k / 9, k % 9, -side, -1, -1, 0);
-        }
-        unsigned m = warp_ballot(ok);
-        if (ok) {
-            int pos = n_legal + __popc(m & ((1u << lane) - 1u));
-            if (pos < kMaxMoves) S.actions[pos] = (int16_t)(from * 90 + to);
-        }
-        n_legal += __popc(m);
+    // ---- in-check flag (cy_is_in_check pyx:543-555: missing king => True), 16 lanes ----------------
+    const int K = res.kings.own_sq;
+    const int kr = K < 0 ? 0 : K / 9, kc = K < 0 ? 0 : K - kr * 9;
+    {
+        const unsigned hits = warp_attacked_pair(b, S.rowocc, S.colocc, K >= 0 && lane < 16, kr, kc, -side, -1, -1, 0);
+        res.in_check = K < 0 || hits != 0u;
     }
-    res.in_check = warp_any(chk);
+    const bool odd = warp_any(odd_king);
+    // warp_any's leading __syncwarp also orders the pm / actions writes above before the reads below
+
+    // ---- phase B: legality + ordered compaction ---------------------------------------------------
+    int n_legal = 0;
+    const bool fast = !res.in_check && !odd && res.kings.own_cnt == 1 && res.kings.foe_cnt <= 1;
+    if (fast) {
+        // The king is not attacked now, so a move of another piece can only expose it by changing the king's own
+        // row or column (a blocker leaves, a cannon screen arrives) or by vacating a knight leg next to the king;
+        // only those lines / those two knight origins are re-examined on the overlaid board.  Enemy pawns and
+        // every other knight see the same squares as before.  Facing kings (pyx:231-245) are covered by the
+        // column test: the enemy king counts as a rook on open rays (pyx:117).  King moves get the full test at
+        // the new square, two moves per pass (one per half warp).
+        const int by = -side;
+        for (int i0 = 0; i0 < n_pseudo; i0 += 32) {
+            const int i = i0 + lane;
+            bool ok = false, kingmove = false;
+            int from = 0, to = 0;
+            if (i < n_pseudo) {
+                const int e = S.pm[i];
+                from = e >> 7;
+                to = e & 127;
+                const int mover = b[from];
+                if (mover == side) {
+                    kingmove = true;
+                } else {
+                    const int fr = from / 9, fc = from - fr * 9, tr = to / 9, tc = to - tr * 9;
+                    bool bad = false;
+                    if (fr == kr || tr == kr) {
+                        unsigned R = S.rowocc[kr];
+                        if (fr == kr) R &= ~(1u << fc);
+                        if (tr == kr) R |= 1u << tc;
+                        bad = line_attacked(b, R, kc, kr * 9, 1, by, from, to, mover);
+                    }
+                    if (!bad && (fc == kc || tc == kc)) {
+                        unsigned Cm = S.colocc[kc];
+                        if (fc == kc) Cm &= ~(1u << fr);
+                        if (tc == kc) Cm |= 1u << tr;
+                        bad = line_attacked(b, Cm, kr, kc, 9, by, from, to, mover);
+                    }
+                    const int ddr = fr - kr, ddc = fc - kc;
+                    if (!bad && (ddr == 1 || ddr == -1) && (ddc == 1 || ddc == -1)) {
+                        const int r1 = kr + 2 * ddr, c2 = kc + 2 * ddc;
+                        if ((unsigned)r1 < 10u && cell_after(b, r1 * 9 + fc, from, to, mover) == 4 * by) bad = true;
+                        if ((unsigned)c2 < 9u && cell_after(b, fr * 9 + c2, from, to, mover) == 4 * by) bad = true;
+                    }
+                    ok = !bad;
+                }
+            }
+            unsigned mk = warp_ballot(kingmove);
+            while (mk) {
+                const int l0 = __ffs(mk) - 1;
+                mk &= mk - 1u;
+                int l1 = -1;
+                if (mk) {
+                    l1 = __ffs(mk) - 1;
+                    mk &= mk - 1u;
+                }
+                const int src = lane < 16 ? l0 : l1;
+                const int qto = warp_bcast(to, src < 0 ? 0 : src);
+                const int qr = qto / 9, qc = qto - qr * 9;
+                const unsigned hits = warp_attacked_pair(b, S.rowocc, S.colocc, src >= 0, qr, qc, by, K, qto, side);
+                if (lane == l0) ok = (hits & 0xffffu) == 0u;
+                if (lane == l1) ok = (hits >> 16) == 0u;
+            }
+            const unsigned m = warp_ballot(ok);
+            if (ok) {
+                const int pos = n_legal + __popc(m & ((1u << lane) - 1u));
+                if (pos < kMaxMoves) S.actions[pos] = (int16_t)(from * 90 + to);
+            }
+            n_legal += __popc(m);
+        }
+    } else {
+        // in check, or a board no game can reach: every move through the general test (pyx:209-252)
+        for (int i0 = 0; i0 < n_pseudo; i0 += 32) {
+            const int i = i0 + lane;
+            bool ok = false;
+            int from = 0, to = 0;
+            if (i < n_pseudo) {
+                const int e = S.pm[i];
+                from = e >> 7;
+                to = e & 127;
+                ok = legal_after_move(b, S.rowocc, S.colocc, side, res.kings, from, to);
+            }
+            const unsigned m = warp_ballot(ok);
+            if (ok) {
+                const int pos = n_legal + __popc(m & ((1u << lane) - 1u));
+                if (pos < kMaxMoves) S.actions[pos] = (int16_t)(from * 90 + to);
+            }
+            n_legal += __popc(m);
+        }
+    }
     if (n_legal > kMaxMoves) res.overflow = true;
     res.n_legal = n_legal;
     warp_sync();
