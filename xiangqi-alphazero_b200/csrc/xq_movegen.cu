@@ -37,7 +37,7 @@ struct __align__(16) MovegenSmem {
 };
 
 template <bool PLANES>
-__global__ void __launch_bounds__(kThreads, 3)
+__global__ void __launch_bounds__(kThreads, 4)
 movegen_kernel(const int8_t* __restrict__ boards, const int8_t* __restrict__ sides, int B,
                int16_t* __restrict__ actions, uint8_t* __restrict__ n_moves,
                uint8_t* __restrict__ in_check, float* __restrict__ planes, int* __restrict__ overflow,

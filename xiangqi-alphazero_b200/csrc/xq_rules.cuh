@@ -120,7 +120,8 @@ struct alignas(16) WarpScratch {
     uint8_t own_sq[96];           // own-piece squares in row-major order (phase A task table)
     uint16_t rowocc[10];          // occupancy of each row (bit c) and
     uint16_t colocc[10];          // of each column (bit r) of the un-moved board: ray scans become bit scans
-    uint8_t pad_[8];
+    uint8_t kingto[4];            // target square of the palace king's move in direction d (0xff: none), 4-byte aligned
+    uint8_t pad_[4];
 };
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
@@ -557,41 +558,87 @@ struct MovegenResult {
     KingInfo kings;
 };
 
+// Everything the generator needs to know about the whole board, from ONE warp-synchronous pass: every lane reads
+// its three squares (row-major index k*32+lane) and its three squares in column-major order, 18 votes follow.
+struct BoardScan {
+    uint32_t own[3];      // own pieces, bit = square
+    uint32_t occ[3];      // occupied squares, bit = square
+    uint32_t occT[3];     // occupied squares, bit = col*10 + row
+    uint32_t kown[3];     // squares holding a king of `side`
+    uint32_t kfoe[3];     // squares holding a king of `-side`
+};
+static __device__ __noinline__ BoardScan warp_board_scan(const int8_t* b, int side)
+{
+    __syncwarp();
+    const int lane = threadIdx.x & 31;
+    BoardScan s;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int i = k * 32 + lane;
+        const int p = i < kSquares ? b[i] : 0;
+        const int c = i / 10, r = i - c * 10;
+        const int pT = i < kSquares ? b[r * 9 + c] : 0;
+        s.own[k] = __ballot_sync(kFullMask, p * side > 0);
+        s.occ[k] = __ballot_sync(kFullMask, p != 0);
+        s.occT[k] = __ballot_sync(kFullMask, pT != 0);
+        s.kown[k] = __ballot_sync(kFullMask, p == side);
+        s.kfoe[k] = __ballot_sync(kFullMask, p == -side);
+    }
+    return s;
+}
+
+// `n` bits starting at bit `start` of the 96-bit value w2:w1:w0 (start + n <= 96)
+__device__ __forceinline__ unsigned bits96(uint32_t w0, uint32_t w1, uint32_t w2, int start, int n)
+{
+    const int w = start >> 5;
+    const uint32_t lo = w == 0 ? w0 : (w == 1 ? w1 : w2);
+    const uint32_t hi = w == 0 ? w1 : (w == 1 ? w2 : 0u);
+    return __funnelshift_r(lo, hi, start & 31) & ((1u << n) - 1u);
+}
+
+constexpr uint32_t kPalaceRedW0 = (7u << 3) | (7u << 12) | (7u << 21);     // squares 3-5, 12-14, 21-23
+constexpr uint32_t kPalaceBlackW2 = (7u << 2) | (7u << 11) | (7u << 20);   // squares 66-68, 75-77, 84-86 (bit = sq-64)
+
 // Full ordered legal-move generation for one board by one warp.
 // b: 90 cells in shared memory; S.actions receives the compacted list (unused slots = -1).
 __device__ __forceinline__ MovegenResult warp_movegen(const int8_t* b, int side, WarpScratch& S)
 {
     const int lane = lane_id();
     MovegenResult res;
-    res.overflow = false;
-    res.kings = warp_find_kings(b, side);
-    // occupancy masks: lanes 0-9 one row each, lanes 10-18 one column each
-    if (lane < 10) {
-        unsigned m = 0;
-#pragma unroll
-        for (int c = 0; c < 9; ++c) m |= (b[lane * 9 + c] != 0 ? 1u : 0u) << c;
-        S.rowocc[lane] = (uint16_t)m;
-    } else if (lane < 19) {
-        unsigned m = 0;
-#pragma unroll
-        for (int r = 0; r < 10; ++r) m |= (b[r * 9 + lane - 10] != 0 ? 1u : 0u) << r;
-        S.colocc[lane - 10] = (uint16_t)m;
+    if (lane == 0) *reinterpret_cast<uint32_t*>(S.kingto) = 0xffffffffu;
+    const BoardScan bs = warp_board_scan(b, side);
+    // kings: _find_king scans the own palace only, row-major (pyx:78-101) = lowest set bit
+    bool odd;                     // a king-valued own piece outside its palace (unreachable boards)
+    {
+        const uint32_t ownp = side == 1 ? (bs.kown[0] & kPalaceRedW0) : (bs.kown[2] & kPalaceBlackW2);
+        const uint32_t foep = side == 1 ? (bs.kfoe[2] & kPalaceBlackW2) : (bs.kfoe[0] & kPalaceRedW0);
+        const int own_base = side == 1 ? 0 : 64, foe_base = side == 1 ? 64 : 0;
+        res.kings.own_sq = ownp ? own_base + __ffs(ownp) - 1 : -1;
+        res.kings.foe_sq = foep ? foe_base + __ffs(foep) - 1 : -1;
+        res.kings.own_cnt = __popc(ownp);
+        res.kings.foe_cnt = __popc(foep);
+        odd = (side == 1 ? ((bs.kown[0] & ~kPalaceRedW0) | bs.kown[1] | bs.kown[2])
+                         : (bs.kown[0] | bs.kown[1] | (bs.kown[2] & ~kPalaceBlackW2))) != 0u;
     }
+    // occupancy masks: lanes 0-9 one row each, lanes 10-18 one column each
+    if (lane < 10) S.rowocc[lane] = (uint16_t)bits96(bs.occ[0], bs.occ[1], bs.occ[2], lane * 9, 9);
+    else if (lane < 19) S.colocc[lane - 10] = (uint16_t)bits96(bs.occT[0], bs.occT[1], bs.occT[2], (lane - 10) * 10, 10);
+    // own pieces in square order: rank among own pieces = task group
+    const int n0 = __popc(bs.own[0]), n1 = __popc(bs.own[1]);
+    const int n_pieces = n0 + n1 + __popc(bs.own[2]);
+    {
+        const uint32_t lt = (1u << lane) - 1u;
+        if (bs.own[0] >> lane & 1u) S.own_sq[__popc(bs.own[0] & lt)] = (uint8_t)lane;
+        if (bs.own[1] >> lane & 1u) S.own_sq[n0 + __popc(bs.own[1] & lt)] = (uint8_t)(32 + lane);
+        if (bs.own[2] >> lane & 1u) S.own_sq[n0 + n1 + __popc(bs.own[2] & lt)] = (uint8_t)(64 + lane);
+    }
+    // unused output slots read back as -1
+    for (int i = lane; i < kMaxMoves; i += 32) S.actions[i] = -1;
+    warp_sync();
 
     // ---- phase A: ordered pseudo-legal list --------------------------------------------
-    // own pieces in square order: rank among own pieces = task group
+    const int K = res.kings.own_sq;
     int n_pseudo = 0;
-    int n_pieces = 0;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        int sq = k * 32 + lane;
-        bool o = sq < kSquares && is_own(b[sq], side);
-        unsigned m = warp_ballot(o);
-        if (o) S.own_sq[n_pieces + __popc(m & ((1u << lane) - 1u))] = (uint8_t)sq;
-        n_pieces += __popc(m);
-    }
-    warp_sync();
-    bool odd_king = false;        // a king-valued own piece that is not THE palace king (unreachable boards)
     for (int t0 = 0; t0 < 4 * n_pieces; t0 += 32) {
         const int t = t0 + lane;
         int cnt = 0, first_t = 0, step = 0, x = -1, n_run = 0, sq = 0;
@@ -599,38 +646,52 @@ __device__ __forceinline__ MovegenResult warp_movegen(const int8_t* b, int side,
             sq = S.own_sq[t >> 2];
             const int p = b[sq];
             const int kind = p < 0 ? -p : p;
-            if (kind == 1 && sq != res.kings.own_sq) odd_king = true;
             n_run = gen_task_run(b, S.rowocc, S.colocc, side, sq, kind, t & 3, first_t, step, x);
             cnt = n_run + (x >= 0 ? 1 : 0);
+            if (sq == K && n_run) S.kingto[t & 3] = (uint8_t)first_t;    // the palace king's target in direction t&3
         }
         int total;
         const int incl = warp_incl_scan(cnt, &total);
         const int off = n_pseudo + incl - cnt;
-        if (cnt > 0) {
-            if (off + cnt <= kMaxPseudo) {
-                const int hi = sq << 7;
-                for (int i = 0; i < n_run; ++i) S.pm[off + i] = (uint16_t)(hi | (first_t + i * step));
-                if (x >= 0) S.pm[off + n_run] = (uint16_t)(hi | x);
-            } else {
-                res.overflow = true;
-            }
+        if (cnt > 0 && off + cnt <= kMaxPseudo) {
+            const int hi = sq << 7;
+            for (int i = 0; i < n_run; ++i) S.pm[off + i] = (uint16_t)(hi | (first_t + i * step));
+            if (x >= 0) S.pm[off + n_run] = (uint16_t)(hi | x);
         }
         n_pseudo += total;
     }
-    res.overflow = warp_any(res.overflow);
+    res.overflow = n_pseudo > kMaxPseudo;
     if (n_pseudo > kMaxPseudo) n_pseudo = kMaxPseudo;
-    // unused output slots read back as -1
-    for (int i = lane; i < kMaxMoves; i += 32) S.actions[i] = -1;
+    warp_sync();                  // pm / kingto / actions writes above are visible to every lane below
 
-    // ---- in-check flag (cy_is_in_check pyx:543-555: missing king => True), 16 lanes ----------------
-    const int K = res.kings.own_sq;
+    // ---- attack queries on half warps: the in-check flag (cy_is_in_check pyx:543-555: missing king => True) and
+    // the palace king's own moves (full _is_attacked at the new square, old square vacated) ----------------
     const int kr = K < 0 ? 0 : K / 9, kc = K < 0 ? 0 : K - kr * 9;
-    {
-        const unsigned hits = warp_attacked_pair(b, S.rowocc, S.colocc, K >= 0 && lane < 16, kr, kc, -side, -1, -1, 0);
-        res.in_check = K < 0 || hits != 0u;
+    unsigned king_ok = 0u;        // bit d: the king's move in direction d is legal
+    res.in_check = true;
+    if (K >= 0) {
+        const uint32_t kt = *reinterpret_cast<const uint32_t*>(S.kingto);
+        unsigned vm = 0u;
+#pragma unroll
+        for (int d = 0; d < 4; ++d) vm |= ((kt >> (8 * d)) & 0xffu) != 0xffu ? 1u << d : 0u;
+        bool first = true;
+        do {
+            // low half: the probe (first pass) or a king move; high half: the next king move
+            int d0 = -1, d1 = -1;
+            if (!first && vm) { d0 = __ffs(vm) - 1; vm &= vm - 1u; }
+            if (vm) { d1 = __ffs(vm) - 1; vm &= vm - 1u; }
+            const int d = lane < 16 ? d0 : d1;
+            const bool probe = first && lane < 16;
+            const int qto = d >= 0 ? (int)((kt >> (8 * d)) & 0xffu) : K;
+            const int qr = qto / 9, qc = qto - qr * 9;
+            const unsigned hits = warp_attacked_pair(b, S.rowocc, S.colocc, probe || d >= 0, qr, qc, -side,
+                                                     probe ? -1 : K, qto, side);
+            if (first) res.in_check = (hits & 0xffffu) != 0u;
+            else if (d0 >= 0 && (hits & 0xffffu) == 0u) king_ok |= 1u << d0;
+            if (d1 >= 0 && (hits >> 16) == 0u) king_ok |= 1u << d1;
+            first = false;
+        } while (vm);
     }
-    const bool odd = warp_any(odd_king);
-    // warp_any's leading __syncwarp also orders the pm / actions writes above before the reads below
 
     // ---- phase B: legality + ordered compaction ---------------------------------------------------
     int n_legal = 0;
@@ -640,12 +701,11 @@ __device__ __forceinline__ MovegenResult warp_movegen(const int8_t* b, int side,
         // row or column (a blocker leaves, a cannon screen arrives) or by vacating a knight leg next to the king;
         // only those lines / those two knight origins are re-examined on the overlaid board.  Enemy pawns and
         // every other knight see the same squares as before.  Facing kings (pyx:231-245) are covered by the
-        // column test: the enemy king counts as a rook on open rays (pyx:117).  King moves get the full test at
-        // the new square, two moves per pass (one per half warp).
+        // column test: the enemy king counts as a rook on open rays (pyx:117).  King moves were answered above.
         const int by = -side;
         for (int i0 = 0; i0 < n_pseudo; i0 += 32) {
             const int i = i0 + lane;
-            bool ok = false, kingmove = false;
+            bool ok = false;
             int from = 0, to = 0;
             if (i < n_pseudo) {
                 const int e = S.pm[i];
@@ -653,7 +713,9 @@ __device__ __forceinline__ MovegenResult warp_movegen(const int8_t* b, int side,
                 to = e & 127;
                 const int mover = b[from];
                 if (mover == side) {
-                    kingmove = true;
+                    const int dl = to - from;             // -9 up, 9 down, -1 left, 1 right = directions 0..3
+                    const int d = dl == -9 ? 0 : (dl == 9 ? 1 : (dl == -1 ? 2 : 3));
+                    ok = (king_ok >> d) & 1u;
                 } else {
                     const int fr = from / 9, fc = from - fr * 9, tr = to / 9, tc = to - tr * 9;
                     bool bad = false;
@@ -677,22 +739,6 @@ __device__ __forceinline__ MovegenResult warp_movegen(const int8_t* b, int side,
                     }
                     ok = !bad;
                 }
-            }
-            unsigned mk = warp_ballot(kingmove);
-            while (mk) {
-                const int l0 = __ffs(mk) - 1;
-                mk &= mk - 1u;
-                int l1 = -1;
-                if (mk) {
-                    l1 = __ffs(mk) - 1;
-                    mk &= mk - 1u;
-                }
-                const int src = lane < 16 ? l0 : l1;
-                const int qto = warp_bcast(to, src < 0 ? 0 : src);
-                const int qr = qto / 9, qc = qto - qr * 9;
-                const unsigned hits = warp_attacked_pair(b, S.rowocc, S.colocc, src >= 0, qr, qc, by, K, qto, side);
-                if (lane == l0) ok = (hits & 0xffffu) == 0u;
-                if (lane == l1) ok = (hits >> 16) == 0u;
             }
             const unsigned m = warp_ballot(ok);
             if (ok) {
