@@ -32,12 +32,13 @@ struct __align__(16) MovegenSmem {
     uint8_t chk_out[2][kTile];
     uint64_t bar[2];
     WarpScratch ws[kWarps];
-    uint32_t pbits[kWarps][kPlaneWords];        // the 1350 plane values of a position as bits
+    uint32_t pbits[kWarps][2][kPlaneWords];     // the 1350 plane values of a position as bits (two buffers: the next
+                                                // position's bits are cleared while slow lanes still read these)
     float4 nib_lut[16];                         // 4 bits -> 4 floats
 };
 
 template <bool PLANES>
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(kThreads, 4)   // 4 CTAs/SM (61 registers); 5 or 6 resident CTAs measured no faster
 movegen_kernel(const int8_t* __restrict__ boards, const int8_t* __restrict__ sides, int B,
                int16_t* __restrict__ actions, uint8_t* __restrict__ n_moves,
                uint8_t* __restrict__ in_check, float* __restrict__ planes, int* __restrict__ overflow,
@@ -86,12 +87,17 @@ movegen_kernel(const int8_t* __restrict__ boards, const int8_t* __restrict__ sid
             __syncthreads();
         }
 
-        for (int j = warp; j < nb; j += kWarps) {
+        for (int j = warp, flip = 0; j < nb; j += kWarps, flip ^= 1) {
             const int8_t* b = &sm.boards[buf][j * kSquares];
             const int side = sm.sides[buf][j];
             const size_t gi = (size_t)t * kTile + j;
             WarpScratch& S = sm.ws[warp];
 
+            uint32_t* bits = sm.pbits[warp][flip];
+            if (PLANES) {         // cleared here: warp_movegen's warp-wide syncs order it before the atomics below
+                bits[lane] = 0u;
+                if (lane < kPlaneWords - 32) bits[32 + lane] = 0u;
+            }
             MovegenResult r = warp_movegen(b, side, S);
             if (lane == 0) {
                 sm.n_out[buf][j] = (uint8_t)min(r.n_legal, kMaxMoves);
@@ -108,10 +114,6 @@ movegen_kernel(const int8_t* __restrict__ boards, const int8_t* __restrict__ sid
                 // iff red moves.  The 1350 values are first set as BITS (one shared-memory atomic per piece), then
                 // every lane expands 4 bits at a time into one float4 through a 16-entry table: ~10 instructions
                 // per 16-byte store instead of 4 compares + selects.
-                uint32_t* bits = sm.pbits[warp];
-                bits[lane] = 0u;
-                if (lane < kPlaneWords - 32) bits[32 + lane] = 0u;
-                warp_sync();
                 for (int sq = lane; sq < kSquares; sq += 32) {
                     const int v = b[sq] * side;
                     if (v != 0) {
@@ -147,7 +149,8 @@ movegen_kernel(const int8_t* __restrict__ boards, const int8_t* __restrict__ sid
                     }
                 }
             }
-            warp_sync();
+            // no warp-wide sync here: the next position starts with warp_board_scan (a __syncwarp), which orders this
+            // position's reads of S.actions before their re-initialisation; the plane bits are double buffered
         }
         __syncthreads();
         // per-tile rows of counts and flags

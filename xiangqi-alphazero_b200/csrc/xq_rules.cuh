@@ -633,7 +633,7 @@ __device__ __forceinline__ MovegenResult warp_movegen(const int8_t* b, int side,
         if (bs.own[2] >> lane & 1u) S.own_sq[n0 + n1 + __popc(bs.own[2] & lt)] = (uint8_t)(64 + lane);
     }
     // unused output slots read back as -1
-    for (int i = lane; i < kMaxMoves; i += 32) S.actions[i] = -1;
+    reinterpret_cast<uint2*>(S.actions)[lane] = make_uint2(0xffffffffu, 0xffffffffu);   // 128 x int16
     warp_sync();
 
     // ---- phase A: ordered pseudo-legal list --------------------------------------------
@@ -671,9 +671,8 @@ __device__ __forceinline__ MovegenResult warp_movegen(const int8_t* b, int side,
     res.in_check = true;
     if (K >= 0) {
         const uint32_t kt = *reinterpret_cast<const uint32_t*>(S.kingto);
-        unsigned vm = 0u;
-#pragma unroll
-        for (int d = 0; d < 4; ++d) vm |= ((kt >> (8 * d)) & 0xffu) != 0xffu ? 1u << d : 0u;
+        // bit d set where byte d of kt is a square (< 0x80) and not 0xff
+        unsigned vm = (~kt & 0x80808080u) * 0x00204081u >> 28;
         bool first = true;
         do {
             // low half: the probe (first pass) or a king move; high half: the next king move
