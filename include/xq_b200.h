@@ -249,6 +249,54 @@ int xq_selfplay_fetch(xq_ctx* ctx, long long first, long long count, void* h_sam
                       int16_t* h_plies, int n_results);
 int xq_selfplay_slots(xq_ctx* ctx, int8_t* h_boards, int32_t* h_meta, int32_t* h_status, int32_t* h_uid);
 
+/* Device pointers of the sample records [sample_capacity][896] and of the per-game results (winner in {1,-1,0}, 2 = not
+ * finished; plies), for consumers that stay on the GPU (xq_replay_append). */
+int xq_selfplay_device_buffers(xq_ctx* ctx, void** d_samples, int8_t** d_winner, int16_t** d_plies);
+
+/* ---- evaluation arena -----------------------------------------------------------------------------
+ * Replaces AlphaZeroTrainer._serial_evaluate (train.py:453-535): cfg->target_games evaluation games played in the
+ * slots of xq_selfplay_create, game uid with the NEW model as red when uid is even (:474), every move =
+ * get_action(game, temperature=0, add_noise=False) of the model to move (:481-483) with cfg->num_simulations
+ * simulations, from the initial position, no resignation; a game still undecided after cfg->max_game_length plies is a
+ * draw (:496-498).  Both networks evaluate every leaf batch; results land in the per-game result arrays
+ * (xq_selfplay_fetch / xq_selfplay_counters).  d_move_log [max_games_total][XQ_MAX_PLIES] int16 receives the actions played
+ * (optional).  Call xq_selfplay_reset before a new match. */
+int xq_arena_play(xq_ctx* ctx, const xq_selfplay_config* cfg, const xq_net_plan* net_new, const xq_net_plan* net_old,
+                  int n_plies, int16_t* d_move_log, void* stream);
+
+/* ---- training step around the torch forward/backward (train.py:376-447) ---------------------------------
+ * Device-resident replay ring of the 896-byte sparse self-play records, replacing the deque of dense tuples
+ * (train.py:203) and SelfPlayDataset (:114-129).
+ *
+ * xq_replay_append: records d_src_records[d_src_index[j]], j < n, go to ring slots (head + j) % capacity with their value
+ * label z (parallel_selfplay.py:124-132: 0 draw, +1 if the side to move at the sample won, -1 otherwise) computed from
+ * d_winner[game uid]. */
+int xq_replay_append(xq_ctx* ctx, const void* d_src_records, const int64_t* d_src_index, int n, const int8_t* d_winner,
+                     int n_results, void* d_ring, float* d_ring_z, long long capacity, long long head, void* stream);
+/* xq_train_batch: minibatch from LOGICAL indices L: ring record (start + (L >> 1)) % capacity, its column-mirrored twin
+ * when L is odd (_augment_data, parallel_selfplay.py:137-151, as an index permutation).  Outputs: planes float32
+ * [B][15][10][9] (get_state_for_nn, game.py:618-640), sparse policy target (action ids int16 [B][128], visit
+ * probabilities float32 [B][128], counts int32 [B]) and z float32 [B]. */
+int xq_train_batch(xq_ctx* ctx, const void* d_ring, const float* d_ring_z, long long capacity, long long start,
+                   const int64_t* d_logical_index, int B, float* d_planes, int16_t* d_actions, float* d_probs,
+                   int32_t* d_n_moves, float* d_z, void* stream);
+/* xq_policy_value_loss: train.py:408-414 and its gradient in one pass over the logits.  Per row i:
+ *   policy_loss_rows[i] = -sum_a pi_a log_softmax(logits_i)_a,  value_loss_rows[i] = (value_i - z_i)^2,
+ *   grad_logits_i = (softmax(logits_i) sum(pi) - pi) * inv_batch,  grad_value_i = 2 (value_i - z_i) * inv_batch
+ * (inv_batch = 1 / GLOBAL batch size, so that the data-parallel sum of gradients is the full-batch gradient). */
+int xq_policy_value_loss(xq_ctx* ctx, const float* d_logits, long long logit_stride, const float* d_value,
+                         const int16_t* d_actions, const float* d_probs, const int32_t* d_n_moves, const float* d_z, int B,
+                         float inv_batch, float* d_grad_logits, long long grad_stride, float* d_grad_value,
+                         float* d_policy_loss_rows, float* d_value_loss_rows, void* stream);
+/* sum of squares of a flat float32 buffer in a fixed order (d_partial: scratch of n_partial >= 1 floats) */
+int xq_grad_sumsq(xq_ctx* ctx, const float* d_grad, long long n, float* d_partial, int n_partial, float* d_out, void* stream);
+/* clip_grad_norm_(max_norm) + torch.optim.Adam.step (L2 weight decay, no amsgrad) over flat buffers (train.py:190-194,
+ * 418-419).  d_grad_sumsq: device scalar from xq_grad_sumsq (NULL or max_norm <= 0: no clipping); grad_scale multiplies
+ * the gradient first (1 / world size when the all-reduce summed per-rank means).  step = 1, 2, ... */
+int xq_adam_step(xq_ctx* ctx, float* d_param, const float* d_grad, float* d_exp_avg, float* d_exp_avg_sq, long long n,
+                 float lr, float beta1, float beta2, float eps, float weight_decay, long long step,
+                 const float* d_grad_sumsq, float max_norm, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

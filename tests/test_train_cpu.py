@@ -1,0 +1,82 @@
+"""Host logic of the training path that needs no GPU: shuffles identical to the reference's DataLoader, minibatch
+sharding, evaluation-pair sharding, and the 2-rank gloo fan-in of new sample records."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_epoch_permutation_is_the_dataloaders():
+    from torch.utils.data import DataLoader, TensorDataset
+    import train as T
+    for n, bs in ((1000, 256), (300, 64), (7, 3)):
+        torch.manual_seed(123 + n)
+        dl = DataLoader(TensorDataset(torch.arange(n)), batch_size=bs, shuffle=True, num_workers=0, drop_last=False)   # train.py:384-391
+        want = [torch.cat([b[0] for b in dl]) for _ in range(3)]
+        torch.manual_seed(123 + n)
+        got = [T.epoch_permutation(n) for _ in range(3)]
+        assert all(torch.equal(a, b) for a, b in zip(want, got))
+
+
+def test_shard_batch_partitions_every_global_batch():
+    import train as T
+    for n in (256, 255, 44, 9, 8):
+        idx = torch.randperm(1000)[:n]
+        for world in (1, 2, 4, 8):
+            parts = [T.shard_batch(idx, r, world) for r in range(world)]
+            assert torch.equal(torch.cat(parts), idx) and min(p.numel() for p in parts) >= 1
+    idx = torch.arange(5)
+    assert all(torch.equal(T.shard_batch(idx, r, 8), idx) for r in range(8))      # fewer samples than ranks: replicated
+
+
+def test_shard_pairs_keeps_colour_parity():
+    import arena
+    for games in range(0, 40):
+        for world in (1, 2, 4, 8):
+            mine = [arena.shard_pairs(games, r, world) for r in range(world)]
+            assert sum(mine) == games
+            # a rank's local game i has the new model as red iff i is even: every rank must hold whole pairs, except that
+            # the rank with the last (unpaired, red) game holds it last
+            assert sum(m % 2 for m in mine) == games % 2
+            reds = sum((m + 1) // 2 for m in mine)
+            assert reds == (games + 1) // 2                                       # train.py:474 new_is_red = (game_idx % 2 == 0)
+
+
+def test_dense_tuples_round_trip_through_records():
+    import xq_oracle
+    from replay import dense_to_records
+    from selfplay_engine import decode_samples, samples_to_reference_tuples
+    boards, sides = xq_oracle.random_playout_positions(4, 60)
+    acts, cnt, _, _ = xq_oracle.movegen_batch(boards, sides)
+    rs = np.random.RandomState(0)
+    data = []
+    for i in range(len(sides)):
+        if cnt[i] == 0:
+            continue
+        pol = np.zeros(8100)
+        p = rs.dirichlet([1.0] * int(cnt[i])).astype(np.float32)
+        pol[acts[i, :cnt[i]].astype(np.int64)] = p
+        data.append((xq_oracle.planes(boards[i], int(sides[i])), pol, float(rs.choice([-1, 0, 1]))))
+    rec, z = dense_to_records(data)
+    dec = decode_samples(rec)
+    for i, (st, pol, val) in enumerate(data):
+        assert np.array_equal(xq_oracle.planes(dec["board"][i], int(dec["side"][i])), st)
+        got = np.zeros(8100)
+        got[dec["actions"][i, :dec["n"][i]].astype(np.int64)] = dec["probs"][i, :dec["n"][i]]
+        assert np.array_equal(got.astype(np.float32), pol.astype(np.float32)) and z[i] == val
+
+
+def test_two_rank_gloo_record_fan_in(tmp_path):
+    script = os.path.join(ROOT, "tests", "mrank_gather_script.py")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29653", script, str(tmp_path)],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    a = torch.load(os.path.join(str(tmp_path), "rank0.pt"))
+    b = torch.load(os.path.join(str(tmp_path), "rank1.pt"))
+    assert torch.equal(a["rec"], b["rec"]) and torch.equal(a["z"], b["z"]) and torch.equal(a["perm"], b["perm"])
+    assert a["rec"].shape[0] == 5 + 9 and a["rec"][:5, 0].eq(0).all() and a["rec"][5:, 0].eq(1).all()

@@ -1,0 +1,278 @@
+"""Training-step kernels and the drop-in trainer against numpy / torch restatements and
+against the REFERENCE's own train_network (tests/golden/train_golden.npz, made by make_train_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from game import engine
+    return engine(0)
+
+
+def make_records(oracle, n, seed):
+    """n sparse sample records from random-playout positions (oracle) with random visit distributions."""
+    boards, sides = oracle.random_playout_positions(seed, n)
+    acts, cnt, _, _ = oracle.movegen_batch(boards, sides)
+    keep = cnt > 0
+    boards, sides, acts, cnt = boards[keep], sides[keep], acts[keep], cnt[keep]
+    rs = np.random.RandomState(seed)
+    rec = np.zeros((len(cnt), 896), np.uint8)
+    probs = np.zeros((len(cnt), 128), np.float32)
+    for i in range(len(cnt)):
+        p = rs.dirichlet([0.5] * int(cnt[i])).astype(np.float32)
+        p[rs.rand(int(cnt[i])) < 0.3] = 0
+        if p.sum() <= 0:
+            p[0] = 1
+        probs[i, :cnt[i]] = p / p.sum()
+    rec[:, :90] = boards.view(np.uint8)
+    rec[:, 90] = sides.view(np.uint8)
+    rec[:, 91] = cnt
+    uid = np.arange(len(cnt), dtype=np.int32) % 7
+    rec[:, 92:96] = uid.view(np.uint8).reshape(-1, 4)
+    rec[:, 128:384] = acts.astype(np.int16).view(np.uint8).reshape(len(cnt), 256)
+    rec[:, 384:896] = probs.view(np.uint8).reshape(len(cnt), 512)
+    return rec, boards, sides, acts, cnt, probs, uid
+
+
+def dense_reference(oracle, board, side, acts, n, probs, mirror):
+    """The reference tuple of one sample: get_state_for_nn planes + dense policy, mirrored as _augment_data does."""
+    from selfplay_engine import MIRROR
+    pl = oracle.planes(board, int(side))
+    pol = np.zeros(8100, np.float32)
+    a = acts[:n].astype(np.int64)
+    if mirror:
+        pl = np.flip(pl, axis=2).copy()
+        a = MIRROR[a]
+    pol[a] = probs[:n]
+    return pl, pol
+
+
+def test_replay_append_labels_and_ring_wraparound(eng):
+    import torch
+    from replay import DeviceReplayBuffer
+    import xq_oracle as oracle
+    rec, boards, sides, acts, cnt, probs, uid = make_records(oracle, 300, 3)
+    winner = np.array([1, -1, 0, 2, 1, -1, 0], np.int8)           # uid 3 = unfinished game
+    buf = DeviceReplayBuffer(eng, 2 * 100)                        # capacity 100 records
+    d_rec = torch.from_numpy(rec).to(eng.dev)
+    d_win = torch.from_numpy(winner).to(eng.dev)
+    order = []
+    for lo in range(0, len(rec), 70):                             # several appends, wraps around twice
+        idx = np.arange(lo, min(lo + 70, len(rec)))
+        idx = idx[winner[uid[idx]] != 2]
+        buf.append_records(d_rec, torch.from_numpy(idx).to(eng.dev), d_win)
+        order.extend(idx.tolist())
+    order = order[-100:]
+    assert len(buf) == 200
+    got_r, got_z = buf.records_in_order()
+    assert np.array_equal(got_r.cpu().numpy(), rec[order])
+    w = winner[uid[order]].astype(np.int32)
+    want_z = np.where(w == 0, 0.0, np.where(w == sides[order], 1.0, -1.0)).astype(np.float32)
+    assert np.array_equal(got_z.cpu().numpy(), want_z)
+
+
+def test_train_batch_equals_reference_tuples(eng, oracle):
+    import torch
+    from replay import DeviceReplayBuffer
+    rec, boards, sides, acts, cnt, probs, uid = make_records(oracle, 400, 5)
+    n = len(rec)
+    z = np.random.RandomState(1).choice([-1.0, 0.0, 1.0], n).astype(np.float32)
+    buf = DeviceReplayBuffer(eng, 2 * n)
+    buf.append_raw(torch.from_numpy(rec), torch.from_numpy(z))
+    rs = np.random.RandomState(2)
+    for B in (1, 2, 7, 64, 255):
+        L = rs.randint(0, 2 * n, B)
+        planes, (a, p, k), zz = buf.batch(torch.from_numpy(L))
+        planes, a, p, k, zz = planes.cpu().numpy(), a.cpu().numpy(), p.cpu().numpy(), k.cpu().numpy(), zz.cpu().numpy()
+        for j, l in enumerate(L):
+            i, m = l >> 1, bool(l & 1)
+            pl, pol = dense_reference(oracle, boards[i], sides[i], acts[i], int(cnt[i]), probs[i], m)
+            assert np.array_equal(planes[j], pl)
+            got = np.zeros(8100, np.float32)
+            got[a[j, :k[j]].astype(np.int64)] = p[j, :k[j]]
+            assert k[j] == cnt[i] and np.array_equal(got, pol) and zz[j] == z[i]
+            assert (a[j, k[j]:] == -1).all() and (p[j, k[j]:] == 0).all()
+
+
+def test_policy_value_loss_matches_torch(eng, oracle):
+    import torch
+    import torch.nn.functional as F
+    from replay import DeviceReplayBuffer, policy_value_loss
+    rec, boards, sides, acts, cnt, probs, uid = make_records(oracle, 200, 9)
+    n = len(rec)
+    buf = DeviceReplayBuffer(eng, 2 * n)
+    buf.append_raw(torch.from_numpy(rec), torch.from_numpy(np.random.RandomState(0).choice([-1.0, 0.0, 1.0], n).astype(np.float32)))
+    g = torch.Generator(device="cpu").manual_seed(4)
+    for B, gb in ((1, None), (37, None), (128, 256)):
+        L = torch.randint(0, 2 * n, (B,), generator=g)
+        _, target, z = buf.batch(L)
+        a, p, k = target
+        logits = (torch.randn(B, 8100, generator=g) * 3).to(eng.dev).requires_grad_(True)
+        value = torch.tanh(torch.randn(B, 1, generator=g)).to(eng.dev).requires_grad_(True)
+        pl, vl = policy_value_loss(eng, logits, value, target, z, global_batch=gb)
+        (pl + 0.5 * vl).backward()
+        # train.py:408-413 on dense targets
+        dense = torch.zeros(B, 8100, device=eng.dev)
+        for j in range(B):
+            dense[j, a[j, :k[j]].long()] = p[j, :k[j]]
+        l2 = logits.detach().clone().requires_grad_(True)
+        v2 = value.detach().clone().requires_grad_(True)
+        scale = B / float(gb or B)
+        rp = -torch.mean(torch.sum(dense * F.log_softmax(l2, dim=1), dim=1)) * scale
+        rv = F.mse_loss(v2, z.reshape(B, 1)) * scale
+        (rp + 0.5 * rv).backward()
+        assert torch.allclose(pl, rp, rtol=1e-5, atol=1e-6) and torch.allclose(vl, rv, rtol=1e-5, atol=1e-6)
+        assert torch.allclose(logits.grad, l2.grad, rtol=1e-4, atol=1e-8)
+        assert torch.allclose(value.grad, v2.grad, rtol=1e-5, atol=1e-8)
+
+
+def test_flat_adam_matches_torch_adam_with_clipping(eng):
+    import torch
+    from train import FlatAdam
+    torch.manual_seed(0)
+    mk = lambda: torch.nn.Sequential(torch.nn.Linear(37, 53), torch.nn.Tanh(), torch.nn.Linear(53, 11)).to(eng.dev)
+    a, b = mk(), mk()
+    b.load_state_dict(a.state_dict())
+    oa = FlatAdam(eng, a, lr=2e-3, weight_decay=1e-4, max_grad_norm=1.0)
+    ob = torch.optim.Adam(b.parameters(), lr=2e-3, weight_decay=1e-4)
+    for step in range(25):
+        x = torch.randn(64, 37, device=eng.dev) * (10.0 if step % 3 == 0 else 0.1)     # clipped and unclipped steps
+        oa.zero_grad()
+        a(x).pow(2).mean().backward()
+        oa.step()
+        ob.zero_grad()
+        b(x).pow(2).mean().backward()
+        torch.nn.utils.clip_grad_norm_(b.parameters(), 1.0)
+        ob.step()
+    for pa, pb in zip(a.parameters(), b.parameters()):
+        assert torch.allclose(pa, pb, rtol=1e-4, atol=1e-6)
+    sa, sb = oa.state_dict(), ob.state_dict()
+    assert sa["param_groups"][0]["lr"] == sb["param_groups"][0]["lr"] and set(sa["state"]) == set(sb["state"])
+    for k in sb["state"]:
+        assert float(sa["state"][k]["step"]) == float(sb["state"][k]["step"]) == 25
+        assert torch.allclose(sa["state"][k]["exp_avg"], sb["state"][k]["exp_avg"], rtol=1e-4, atol=1e-8)
+    # a torch Adam checkpoint loads into the flat optimiser (train.py:573-575) and training continues identically
+    oa.load_state_dict(ob.state_dict())
+    x = torch.randn(64, 37, device=eng.dev)
+    oa.zero_grad(); a(x).pow(2).mean().backward(); oa.step()
+    ob.zero_grad(); b(x).pow(2).mean().backward(); torch.nn.utils.clip_grad_norm_(b.parameters(), 1.0); ob.step()
+    for pa, pb in zip(a.parameters(), b.parameters()):
+        assert torch.allclose(pa, pb, rtol=1e-4, atol=1e-6)
+
+
+def _checksums(model):
+    return np.array([[float(p.detach().double().sum()), float(p.detach().double().abs().sum())] for p in model.parameters()])
+
+
+def test_train_network_matches_the_reference_run(eng, tmp_path):
+    """Same samples, same seeds as tests/golden/make_train_golden.py (the reference's AlphaZeroTrainer.train_network on
+    the CPU, fp32): same shuffles, losses within 2e-3 relative, parameter checksums within 2e-3 of the reference's change."""
+    import torch
+    import train as T
+    g = dict(np.load(os.path.join(GOLDEN, "train_golden.npz")))
+    ch, blocks, records, batch, epochs, seed = (int(x) for x in g["meta"])
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    cfg = T.TrainingConfig()
+    cfg.num_channels, cfg.num_res_blocks, cfg.batch_size, cfg.num_epochs, cfg.min_buffer_size = ch, blocks, batch, epochs, 10
+    cfg.checkpoint_dir = str(tmp_path)
+    torch.manual_seed(seed)
+    tr = T.AlphaZeroTrainer(cfg)
+    assert np.allclose(_checksums(tr.current_model), g["init"], rtol=1e-6, atol=1e-6), "initial weights differ from the reference's"
+    rec = np.zeros((records, 896), np.uint8)
+    rec[:, :90] = g["board"].view(np.uint8)
+    rec[:, 90] = g["side"].view(np.uint8)
+    rec[:, 91] = g["n"]
+    rec[:, 128:384] = g["actions"].view(np.uint8).reshape(records, 256)
+    rec[:, 384:896] = g["probs"].view(np.uint8).reshape(records, 512)
+    tr.replay_buffer.append_raw(torch.from_numpy(rec), torch.from_numpy(g["z"]))
+    assert len(tr.replay_buffer) == 2 * records
+    torch.manual_seed(seed + 1)
+    s1 = tr.train_network()
+    c1 = _checksums(tr.current_model)
+    s2 = tr.train_network()
+    c2 = _checksums(tr.current_model)
+    for s, want in ((s1, g["stats1"]), (s2, g["stats2"])):
+        got = np.array([s["policy_loss"], s["value_loss"], s["total_loss"], s["learning_rate"]])
+        assert np.allclose(got, want, rtol=2e-3), (got, want)
+    # parameters: per-tensor float64 checksums (sum, abs-sum) land where the reference's landed, measured against how far the
+    # reference moved them (CPU vs cuDNN summation order is amplified by Adam's m / sqrt(v) on small gradients)
+    for c, want in ((c1, g["after1"]), (c2, g["after2"])):
+        moved = np.abs(want - g["init"]).max(axis=1)
+        ratio = np.abs(c - want).max(axis=1) / (moved + 1e-2 * np.abs(want).max(axis=1) + 1e-6)
+        assert ratio.max() < 0.1, ratio
+    # checkpoint dictionary: the reference's keys (train.py:539-551), loadable again
+    tr.save_checkpoint(3, is_best=True)
+    ck = torch.load(os.path.join(str(tmp_path), "checkpoint_iter3.pt"), map_location="cpu")
+    assert set(ck) == {"iteration", "model_state_dict", "best_model_state_dict", "optimizer_state_dict", "scheduler_state_dict",
+                       "config", "total_games"}
+    best = torch.load(os.path.join(str(tmp_path), "best_model.pt"), map_location="cpu")
+    assert set(best) == {"model_state_dict", "config", "iteration", "total_games"}
+    tr.load_checkpoint(os.path.join(str(tmp_path), "checkpoint_iter3.pt"))
+    assert tr.iteration == 3 and tr.optimizer.steps == 2 * epochs * ((2 * records + batch - 1) // batch)
+
+
+def test_arena_equals_serial_evaluation_on_the_dropin_modules(eng):
+    """xq_arena_play against the reference's evaluation loop (train.py:470-498) run move by move on the drop-in
+    MCTS / XiangqiGame with the same two networks: identical move sequences and results."""
+    import torch
+    from model import XiangqiNet
+    from mcts import MCTS
+    from game import XiangqiGame, decode_action
+    import arena
+    torch.manual_seed(11)
+    new, old = XiangqiNet(128, 1).eval(), XiangqiNet(128, 1).eval()
+    games, sims, max_len = 4, 12, 14
+    r = arena.Arena(eng, new, old, games, sims).play(sims, 1.5, max_len)
+    new_m, old_m = MCTS(new, num_simulations=sims, c_puct=1.5), MCTS(old, num_simulations=sims, c_puct=1.5)
+    for gi in range(games):
+        game = XiangqiGame()
+        new_is_red = gi % 2 == 0
+        moves = []
+        step = 0
+        while step < max_len:
+            red = game.current_player == 1
+            m = new_m if new_is_red == red else old_m
+            a = m.get_action(game, temperature=0, add_noise=False)
+            moves.append(a)
+            game.make_move(*decode_action(a))
+            step += 1
+            if game.is_game_over()[0]:
+                break
+        done, winner = game.is_game_over()
+        if not done:
+            winner = 0
+        assert list(r["moves"][gi][:len(moves)]) == moves, f"game {gi}"
+        assert r["winners"][gi] == winner and r["plies"][gi] == len(moves)
+    assert r["new_wins"] + r["old_wins"] + r["draws"] == games
+
+
+def test_one_iteration_self_play_train_evaluate(eng, tmp_path):
+    """self_play -> train_network -> evaluate on the device-resident path; stats dictionaries keep the reference's keys."""
+    import torch
+    import train as T
+    cfg = T.TrainingConfig()
+    cfg.num_channels, cfg.num_res_blocks, cfg.num_simulations, cfg.num_games_per_iter = 128, 1, 8, 24
+    cfg.max_game_length, cfg.batch_size, cfg.num_epochs, cfg.min_buffer_size = 30, 64, 1, 50
+    cfg.eval_games, cfg.eval_simulations, cfg.random_opening_moves = 5, 6, 4
+    cfg.checkpoint_dir = str(tmp_path)
+    torch.manual_seed(0)
+    tr = T.AlphaZeroTrainer(cfg)
+    sp = tr.self_play()
+    assert set(sp) >= {"games", "red_wins", "black_wins", "draws", "avg_steps", "new_samples", "buffer_size"}
+    assert sp["games"] == 24 and sp["buffer_size"] == len(tr.replay_buffer) == sp["new_samples"] > 0
+    before = [p.detach().clone() for p in tr.current_model.parameters()]
+    st = tr.train_network()
+    assert set(st) == {"policy_loss", "value_loss", "total_loss", "learning_rate"} and np.isfinite(st["total_loss"])
+    assert any(not torch.equal(a, b) for a, b in zip(before, tr.current_model.parameters()))
+    ev = tr.evaluate()
+    assert set(ev) == {"new_wins", "old_wins", "draws", "win_rate", "model_updated"}
+    assert ev["new_wins"] + ev["old_wins"] + ev["draws"] == 5
+    same = all(torch.equal(a, b) for a, b in zip(tr.current_model.state_dict().values(), tr.best_model.state_dict().values()))
+    assert same                                        # promoted or reverted: both models agree afterwards (train.py:528-533)

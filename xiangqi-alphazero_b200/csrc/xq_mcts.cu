@@ -679,6 +679,10 @@ struct SpConfig {
     float dirichlet_alpha;
     unsigned long long seed;
     int target_games;
+    // evaluation arena (train.py:453-535): greedy move choice (temperature 0: first maximum of the visit counts in child
+    // order, mcts.py:197-200), no sample records, a game that reaches max_game_length undecided is a draw (:496-498)
+    int arena;
+    int16_t* move_log;              // [max_games_total][XQ_MAX_PLIES] actions played, or nullptr
 };
 
 constexpr int kSampleBytes = 896;   // board 90 | side 1 | n 1 | uid 4 | ply 4 | played action 2 | pad | actions @128 (256) | probs @384 (512)
@@ -832,6 +836,10 @@ sp_after_root_kernel(MctsState M, SpState P, SpConfig cfg, const void* policy, s
         if (lane == 0) sp_finish_game(M, P, g, rw, move_count);
         return;
     }
+    if (move_count >= cfg.max_game_length && cfg.arena) {
+        if (lane == 0) sp_finish_game(M, P, g, 0, move_count);
+        return;
+    }
     if (move_count >= cfg.max_game_length) {
         // material adjudication (parallel_selfplay.py:79-89); unreachable while max_game_length >= 200
         __shared__ int8_t tb[kSelWarps][kBoardPad];
@@ -900,11 +908,25 @@ sp_end_move_kernel(MctsState M, SpState P, SpConfig cfg, unsigned long long ply_
         }
         while (chosen > 0 && wts[warp][chosen] == 0.0) --chosen;   // never pick an unvisited move by rounding
     }
+    if (cfg.arena && lane == 0) {
+        // temperature 0: max(children, key=visit_count) keeps the first maximum in child order (mcts.py:197-200)
+        int best = -1;
+        chosen = 0;
+        for (int i = 0; i < n; ++i) {
+            const int cnt = M.hot[root.child0 + i].N;
+            if (cnt > best) { best = cnt; chosen = i; }
+        }
+    }
     chosen = warp_bcast(chosen, 0);
     const int action = M.link[root.child0 + chosen].action;
+    if (cfg.move_log && lane == 0) {
+        const int uid = P.game_uid[g];
+        if (uid >= 0 && uid < P.max_games_total && gm.move_count < XQ_MAX_PLIES)
+            cfg.move_log[(size_t)uid * XQ_MAX_PLIES + gm.move_count] = (int16_t)action;
+    }
     // sample record
     int slot = -1;
-    if (lane == 0) {
+    if (lane == 0 && !cfg.arena) {
         slot = atomicAdd(&P.counters[2], 1);
         if ((long long)slot >= P.sample_cap) {
             atomicSub(&P.counters[2], 1);
@@ -1021,6 +1043,8 @@ extern "C" int xq_selfplay_play(xq_ctx* c, const xq_selfplay_config* cfg, const 
     k.dirichlet_alpha = cfg->dirichlet_alpha;
     k.seed = cfg->seed;
     k.target_games = cfg->target_games < P.max_games_total ? cfg->target_games : P.max_games_total;
+    k.arena = 0;
+    k.move_log = nullptr;
     const int nb = blocks_for(M.n_games), nt = kSelWarps * 32;
     auto run_net = [&]() {
         return xq_net_run(c, net->layers, net->n_layers, net->vfeats, net->w1t, net->b1, net->w2, net->b2, net->value, net->batch, stream);
@@ -1053,6 +1077,118 @@ extern "C" int xq_selfplay_play(xq_ctx* c, const xq_selfplay_config* cfg, const 
         c->launches += 1;
         XQ_CUDA(c, cudaGetLastError());
     }
+    return XQ_OK;
+}
+
+// ---- evaluation arena: new model vs best model (train.py:453-535) -------------------------------------------
+// Game uid plays with the NEW model as red when uid is even (train.py:474).  Every search belongs to the player to
+// move at the ROOT; both networks evaluate every batch and this kernel overwrites the new model's outputs with the
+// old model's for the games whose root player is the old model.
+namespace xq {
+__global__ void __launch_bounds__(256)
+arena_blend_kernel(MctsState M, SpState P, void* logits_new, const void* logits_old, size_t row_bytes, float* value_new,
+                   const float* value_old)
+{
+    const int g = blockIdx.x;
+    if (g >= M.n_games || P.status[g] != 1) return;
+    const int uid = P.game_uid[g];
+    const int root_side = M.meta[g * 4 + 0];
+    const bool uses_new = ((uid & 1) == 0) == (root_side == 1);
+    if (uses_new) return;
+    uint4* d = reinterpret_cast<uint4*>((char*)logits_new + (size_t)g * row_bytes);
+    const uint4* s = reinterpret_cast<const uint4*>((const char*)logits_old + (size_t)g * row_bytes);
+    for (size_t i = threadIdx.x; i < row_bytes / 16; i += blockDim.x) d[i] = s[i];
+    if (threadIdx.x == 0) value_new[g] = value_old[g];
+}
+}  // namespace xq
+
+extern "C" int xq_arena_play(xq_ctx* c, const xq_selfplay_config* cfg, const xq_net_plan* net_new, const xq_net_plan* net_old,
+                             int n_plies, int16_t* d_move_log, void* stream)
+{
+    SpState* Pp = c ? SP_(c) : nullptr;
+    MctsState* Mp = c ? S_(c) : nullptr;
+    if (!Pp || !Mp) return xq_fail(c, XQ_ERR_STATE, "xq_arena_play: call xq_selfplay_create first");
+    if (!cfg || !net_new || !net_old || n_plies < 0) return xq_fail(c, XQ_ERR_ARG, "xq_arena_play: bad arguments");
+    if (net_new->batch < Pp->n_slots || net_old->batch < Pp->n_slots || net_new->x_rows != net_old->x_rows ||
+        net_new->x_row0 != net_old->x_row0 || net_new->logit_stride != net_old->logit_stride ||
+        net_new->logits_kind != net_old->logits_kind || (net_new->logits_kind != 1 && net_new->logits_kind != 2))
+        return xq_fail(c, XQ_ERR_ARG, "xq_arena_play: the two network plans must have the same batch geometry");
+    MctsState& M = *Mp;
+    SpState& P = *Pp;
+    if (M.max_games < P.n_slots) return xq_fail(c, XQ_ERR_STATE, "xq_arena_play: search state smaller than the slot count");
+    M.n_games = P.n_slots;
+    cudaStream_t s = (cudaStream_t)stream;
+    SpConfig k;
+    k.num_simulations = cfg->num_simulations;
+    k.c_puct = cfg->c_puct;
+    k.temperature_threshold = 0;
+    k.max_game_length = cfg->max_game_length;
+    k.random_opening_moves = 0;          // evaluation games start from the initial position (train.py:473)
+    k.enable_resign = 0;
+    k.resign_threshold = -2.0f;
+    k.resign_check_steps = 1 << 30;
+    k.add_noise = 0;                     // get_action(game, temperature=0, add_noise=False) (train.py:481-483)
+    k.dirichlet_alpha = cfg->dirichlet_alpha;
+    k.seed = cfg->seed;
+    k.target_games = cfg->target_games < P.max_games_total ? cfg->target_games : P.max_games_total;
+    k.arena = 1;
+    k.move_log = d_move_log;
+    const int nb = blocks_for(M.n_games), nt = kSelWarps * 32;
+    const size_t x_bytes = (size_t)2 * (size_t)net_new->x_rows * 8 * 2;        // bf16 [2][x_rows][8]
+    const size_t row_bytes = (size_t)net_new->logit_stride * (net_new->logits_kind == 1 ? 2 : 4);
+    auto run_both = [&]() -> int {
+        XQ_CUDA(c, cudaMemcpyAsync(net_old->x_planes, net_new->x_planes, x_bytes, cudaMemcpyDeviceToDevice, s));
+        int rc = xq_net_run(c, net_new->layers, net_new->n_layers, net_new->vfeats, net_new->w1t, net_new->b1, net_new->w2,
+                            net_new->b2, net_new->value, net_new->batch, stream);
+        if (rc) return rc;
+        rc = xq_net_run(c, net_old->layers, net_old->n_layers, net_old->vfeats, net_old->w1t, net_old->b1, net_old->w2,
+                        net_old->b2, net_old->value, net_old->batch, stream);
+        if (rc) return rc;
+        arena_blend_kernel<<<M.n_games, 256, 0, s>>>(M, P, (void*)net_new->logits, net_old->logits, row_bytes, net_new->value,
+                                                     net_old->value);
+        c->launches += 1;
+        return XQ_OK;
+    };
+    for (int ply = 0; ply < n_plies; ++ply) {
+        const unsigned long long pi = P.ply_counter++;
+        sp_new_games_kernel<<<nb, nt, 0, s>>>(M, P, k, pi);
+        set_int_kernel<<<1, 1, 0, s>>>(M.alloc, M.max_games);
+        mcts_root_begin_kernel<<<nb, nt, 0, s>>>(M, nullptr, (__nv_bfloat16*)net_new->x_planes, net_new->x_rows, net_new->x_row0, nullptr,
+                                                 nullptr);
+        c->launches += 3;
+        int rc = run_both();
+        if (rc) return rc;
+        if (net_new->logits_kind == 1)
+            sp_after_root_kernel<1><<<nb, nt, 0, s>>>(M, P, k, net_new->logits, (size_t)net_new->logit_stride, net_new->value, pi);
+        else
+            sp_after_root_kernel<2><<<nb, nt, 0, s>>>(M, P, k, net_new->logits, (size_t)net_new->logit_stride, net_new->value, pi);
+        c->launches += 1;
+        for (int sim = 0; sim < k.num_simulations; ++sim) {
+            mcts_select_kernel<<<nb, nt, 0, s>>>(M, (double)k.c_puct, nullptr, (__nv_bfloat16*)net_new->x_planes, net_new->x_rows,
+                                                 net_new->x_row0, nullptr, nullptr);
+            rc = run_both();
+            if (rc) return rc;
+            if (net_new->logits_kind == 1)
+                mcts_expand_backup_kernel<1><<<nb, nt, 0, s>>>(M, net_new->logits, (size_t)net_new->logit_stride, net_new->value);
+            else
+                mcts_expand_backup_kernel<2><<<nb, nt, 0, s>>>(M, net_new->logits, (size_t)net_new->logit_stride, net_new->value);
+            c->launches += 2;
+        }
+        sp_end_move_kernel<<<nb, nt, 0, s>>>(M, P, k, pi);
+        c->launches += 1;
+        XQ_CUDA(c, cudaGetLastError());
+    }
+    return XQ_OK;
+}
+
+// device pointers of the sample records and per-game results, for consumers that stay on the GPU (the replay ring)
+extern "C" int xq_selfplay_device_buffers(xq_ctx* c, void** d_samples, int8_t** d_winner, int16_t** d_plies)
+{
+    SpState* P = c ? SP_(c) : nullptr;
+    if (!P) return xq_fail(c, XQ_ERR_STATE, "xq_selfplay_device_buffers: call xq_selfplay_create first");
+    if (d_samples) *d_samples = P->samples;
+    if (d_winner) *d_winner = P->res_winner;
+    if (d_plies) *d_plies = P->res_plies;
     return XQ_OK;
 }
 

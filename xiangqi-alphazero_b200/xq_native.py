@@ -85,6 +85,14 @@ def lib():
     _sig(L, "xq_selfplay_counters", i32, vp, C.POINTER(i64))
     _sig(L, "xq_selfplay_fetch", i32, vp, i64, i64, vp, vp, vp, i32)
     _sig(L, "xq_selfplay_slots", i32, vp, vp, vp, vp, vp)
+    _sig(L, "xq_selfplay_device_buffers", i32, vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp))
+    _sig(L, "xq_arena_play", i32, vp, vp, vp, vp, i32, vp, vp)
+    f32 = C.c_float
+    _sig(L, "xq_replay_append", i32, vp, vp, vp, i32, vp, i32, vp, vp, i64, i64, vp)
+    _sig(L, "xq_train_batch", i32, vp, vp, vp, i64, i64, vp, i32, vp, vp, vp, vp, vp, vp)
+    _sig(L, "xq_policy_value_loss", i32, vp, vp, i64, vp, vp, vp, vp, vp, i32, f32, vp, i64, vp, vp, vp, vp)
+    _sig(L, "xq_grad_sumsq", i32, vp, vp, i64, vp, i32, vp, vp)
+    _sig(L, "xq_adam_step", i32, vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i64, vp, f32, f32, vp)
     _lib = L
     return L
 
@@ -95,7 +103,9 @@ EXPORTS = ["xq_create", "xq_destroy", "xq_last_error", "xq_version", "xq_launch_
            "xq_mcts_create", "xq_mcts_set_games", "xq_mcts_root_begin", "xq_mcts_root_expand", "xq_mcts_select",
            "xq_mcts_expand_backup", "xq_mcts_leaf_info", "xq_mcts_root_visits", "xq_mcts_stats",
            "xq_net_gemm", "xq_net_value_head", "xq_net_run", "xq_selfplay_create", "xq_selfplay_reset",
-           "xq_selfplay_play", "xq_selfplay_counters", "xq_selfplay_fetch", "xq_selfplay_slots"]
+           "xq_selfplay_play", "xq_selfplay_counters", "xq_selfplay_fetch", "xq_selfplay_slots",
+           "xq_selfplay_device_buffers", "xq_arena_play", "xq_replay_append", "xq_train_batch", "xq_policy_value_loss",
+           "xq_grad_sumsq", "xq_adam_step"]
 
 
 def _np_ptr(a: np.ndarray):
