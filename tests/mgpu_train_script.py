@@ -1,0 +1,85 @@
+"""Launched by tests/test_multigpu_gpu.py under torchrun (one process per GPU, NCCL): the data-parallel training step of
+the drop-in train.py (minibatches split across ranks, SyncBatchNorm, one flat gradient all-reduce, fused clip + Adam)
+must reproduce the REFERENCE's single-process train_network run of tests/golden/train_golden.npz; then one sharded
+self-play + evaluation round checks the record fan-in and the weight broadcast."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "xiangqi-alphazero_b200"))
+
+import torch
+import torch.distributed as dist
+
+
+def checksums(model):
+    return np.array([[float(p.detach().double().sum()), float(p.detach().double().abs().sum())] for p in model.parameters()])
+
+
+def main():
+    local = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import train as T
+    g = dict(np.load(os.path.join(ROOT, "tests", "golden", "train_golden.npz")))
+    ch, blocks, records, batch, epochs, seed = (int(x) for x in g["meta"])
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    cfg = T.TrainingConfig()
+    cfg.num_channels, cfg.num_res_blocks, cfg.batch_size, cfg.num_epochs, cfg.min_buffer_size = ch, blocks, batch, epochs, 10
+    cfg.checkpoint_dir = "/tmp/xq_mgpu_train"
+    torch.manual_seed(seed if dist.get_rank() == 0 else 999)      # other ranks start elsewhere: the broadcast must fix it
+    tr = T.AlphaZeroTrainer(cfg)
+    assert np.allclose(checksums(tr.current_model), g["init"], rtol=1e-6, atol=1e-6)
+    rec = np.zeros((records, 896), np.uint8)
+    rec[:, :90] = g["board"].view(np.uint8)
+    rec[:, 90] = g["side"].view(np.uint8)
+    rec[:, 91] = g["n"]
+    rec[:, 128:384] = g["actions"].view(np.uint8).reshape(records, 256)
+    rec[:, 384:896] = g["probs"].view(np.uint8).reshape(records, 512)
+    tr.replay_buffer.append_raw(torch.from_numpy(rec), torch.from_numpy(g["z"]))
+    torch.manual_seed(seed + 1 if dist.get_rank() == 0 else 5)
+    s1 = tr.train_network()
+    c1 = checksums(tr.current_model)
+    got = np.array([s1["policy_loss"], s1["value_loss"], s1["total_loss"], s1["learning_rate"]])
+    assert np.allclose(got, g["stats1"], rtol=2e-3), (got, g["stats1"])
+    moved = np.abs(g["after1"] - g["init"]).max(axis=1)
+    ratio = np.abs(c1 - g["after1"]).max(axis=1) / (moved + 1e-2 * np.abs(g["after1"]).max(axis=1) + 1e-6)
+    assert ratio.max() < 0.1, ratio
+    # every rank holds the same weights after data-parallel steps
+    flat = tr.optimizer.flat_p.clone()
+    ref = flat.clone()
+    dist.broadcast(ref, 0)
+    assert torch.equal(flat, ref)
+
+    # sharded self-play -> all ranks append the same records; evaluation pairs sharded; weights broadcast
+    cfg2 = T.TrainingConfig()
+    cfg2.num_channels, cfg2.num_res_blocks, cfg2.num_simulations, cfg2.num_games_per_iter = 128, 1, 6, 9
+    cfg2.max_game_length, cfg2.batch_size, cfg2.num_epochs, cfg2.min_buffer_size = 24, 64, 1, 20
+    cfg2.eval_games, cfg2.eval_simulations = 5, 4
+    cfg2.checkpoint_dir = "/tmp/xq_mgpu_train"
+    tr2 = T.AlphaZeroTrainer(cfg2)
+    sp = tr2.self_play()
+    assert sp["games"] == 9 and sp["buffer_size"] == len(tr2.replay_buffer)
+    r, z = tr2.replay_buffer.records_in_order()
+    r0 = r.clone()
+    dist.broadcast(r0, 0)
+    assert torch.equal(r, r0)
+    st = tr2.train_network()
+    assert np.isfinite(st["total_loss"])
+    ev = tr2.evaluate()
+    assert ev["new_wins"] + ev["old_wins"] + ev["draws"] == 5
+    f = tr2.optimizer.flat_p.clone()
+    f0 = f.clone()
+    dist.broadcast(f0, 0)
+    assert torch.equal(f, f0)
+    dist.barrier()
+    if dist.get_rank() == 0:
+        print(f"MGPU_TRAIN_OK ranks={dist.get_world_size()} loss={s1['total_loss']:.4f}")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

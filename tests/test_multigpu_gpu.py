@@ -19,3 +19,14 @@ def test_two_gpu_self_play_shards_and_gathers():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
     assert "MGPU_OK ranks=2 games=7" in out.stdout
+
+
+def test_two_gpu_data_parallel_training_matches_the_reference_run():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29579", os.path.join(ROOT, "tests", "mgpu_train_script.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+    assert "MGPU_TRAIN_OK ranks=2" in out.stdout
