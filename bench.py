@@ -7,8 +7,9 @@ Workloads (BASELINE.json `configs`):
   movegen   configs[1]: batched legal-move generation + in-check + feature planes over 1M
             random-playout positions per GPU; metric = legal-move positions/s.
   selfplay  configs[2]: 4096 concurrent self-play games x 800 MCTS simulations/move with the
-            128ch x 6 ResNet evaluator; metric = MCTS simulations/s.  (Default once the
-            device-resident search is built; until then the default is `movegen`.)
+            128ch x 6 ResNet evaluator; metric = MCTS simulations/s.  (The default.)
+  train     configs[4], training step: global batch 256, Adam, clip, XiangqiNet(128,6) on the
+            device-resident replay ring; metric = training samples/s (bench_train.py).
 
 A "step" is one pass of the hot path over one batch of synthetic input already resident in
 HBM.  `value` is device-timed (CUDA events, barrier + synchronize on both sides, max over
@@ -318,13 +319,17 @@ def main():
     ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default=None, choices=[None, "movegen", "selfplay"])
+    ap.add_argument("--workload", default=None, choices=[None, "movegen", "selfplay", "train"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.workload is None:
         args.workload = "selfplay" if os.path.exists(os.path.join(PKG, "selfplay_engine.py")) else "movegen"
     QUIET = _QuietStdout().__enter__()
     if args.impl == "reference":
+        if args.workload == "train":
+            sys.path.insert(0, ROOT)
+            import bench_train
+            return bench_train.run_reference(args)
         if args.workload == "selfplay":
             sys.path.insert(0, ROOT)
             import bench_selfplay
@@ -345,6 +350,10 @@ def main():
     try:
         if args.workload == "movegen":
             bench_movegen(args, rank, world, local_rank, dist)
+        elif args.workload == "train":
+            sys.path.insert(0, ROOT)
+            import bench_train
+            bench_train.run(args, rank, world, local_rank, dist)
         else:
             sys.path.insert(0, ROOT)
             import bench_selfplay

@@ -128,10 +128,12 @@ class B200Net:
         self.e = eng
         self.max_batch = int(max_batch)
         dev = eng.dev
-        Cc, R = model.num_channels, model.num_res_blocks
-        assert Cc % 128 == 0 or Cc == 64 or Cc % 64 == 0, "channels must be a multiple of 64"
-        assert Cc % 128 == 0, "this build tiles output channels by 128"
-        self.C, self.R = Cc, R
+        Cm, R = model.num_channels, model.num_res_blocks
+        # The conv kernels tile output channels by 128.  Narrower towers (the reference's quick preset uses 64,
+        # train.py:661) run zero-padded to the next multiple of 128: padded channels have zero weights and zero bias,
+        # stay exactly 0 through ReLU / residual adds and contribute nothing downstream.
+        Cc = (Cm + 127) // 128 * 128
+        self.C, self.R, self.C_model = Cc, R, Cm
         B = self.max_batch
         self.m_tiles = (B * 110 + 127) // 128
         pairs = (self.m_tiles + 1) // 2                            # conv kernels work on pairs of 128-row tiles,
@@ -149,7 +151,7 @@ class B200Net:
         self.keep = []                                   # weight images / biases (owned here)
         self.layers = []
         # fold on a private CPU copy so the caller's module (device, mode) is left untouched
-        m = XiangqiNet(Cc, R)
+        m = XiangqiNet(Cm, R)
         m.load_state_dict({k: v.detach().cpu().clone() for k, v in model.state_dict().items()})
         m.eval()
 
@@ -159,7 +161,15 @@ class B200Net:
             self.keep.append(t)
             return t
 
+        def pad_channels(w, b, co, ci):
+            wp = torch.zeros((co, ci) + tuple(w.shape[2:]), dtype=torch.float32)
+            wp[:w.shape[0], :w.shape[1]] = w
+            bp = torch.zeros(co, dtype=torch.float32)
+            bp[:b.shape[0]] = b
+            return wp, bp
+
         def conv_layer(w, b, a_buf, out_buf, residual, relu, kch_iter):
+            w, b = pad_channels(w, b, Cc, w.shape[1] if w.shape[1] == 15 else Cc)
             img = dev_t(conv_image(w, 128, kch_iter))
             img64 = dev_t(conv_image(w, 64, kch_iter)) if kch_iter == 8 else None   # halves of N for the CTA-pair kernel
             bias = dev_t(b, torch.float32)
@@ -187,7 +197,7 @@ class B200Net:
             wv, bv = fold_bn(m.value_head[0].weight, m.value_head[1])
             wh = torch.zeros((48, Cc, 1, 1))
             bh = torch.zeros(48)
-            wh[:32], wh[32:36] = wp, wv
+            wh[:32, :Cm], wh[32:36, :Cm] = wp, wv
             bh[:32], bh[32:36] = bp, bv
             img = dev_t(conv_image(wh, 48, 8))
             bias = dev_t(bh, torch.float32)
@@ -255,6 +265,6 @@ class B200Net:
         return x[:, 1:, :9].permute(0, 3, 1, 2).float()
 
     def flops_per_board(self):
-        Cc, R = self.C, self.R
+        Cc, R = self.C_model, self.R                      # algorithmic FLOPs of the model, not of the padded tiles
         conv = 2 * 90 * 9
         return conv * 15 * Cc + 2 * R * conv * Cc * Cc + 2 * 90 * Cc * 36 + 2 * 2880 * ACTION_SPACE + 2 * (360 * 128 + 128)
