@@ -86,12 +86,35 @@ def main():
     stats2 = tr.train_network()                               # second call: Adam moments and the LR schedule carry over
     after2 = checksums(tr.current_model)
     bn = np.array([[float(b.detach().double().sum())] for b in tr.current_model.buffers()])
+
+    # (b) the reference's loss on ONE batch holding the whole buffer, initial weights, learning rate 0 (no update):
+    # pins the CPU oracle's planes + mirroring + loss against train_network itself
+    cfg0 = reftrain.TrainingConfig()
+    cfg0.num_channels, cfg0.num_res_blocks = CHANNELS, BLOCKS
+    cfg0.batch_size, cfg0.num_epochs, cfg0.min_buffer_size, cfg0.learning_rate = 2 * RECORDS, 1, 10, 0.0
+    cfg0.device = 'cpu'
+    cfg0.checkpoint_dir = '/tmp/xq_train_golden'
+    torch.manual_seed(SEED)
+    tr0 = reftrain.AlphaZeroTrainer(cfg0)
+    tr0.replay_buffer.extend(pairs)
+    stats0 = tr0.train_network()
+    # (c) `_augment_data` outputs of the first 24 samples (mirrored twin: packed planes, policy as sorted (index, value))
+    K = 24
+    mir_planes = np.array([np.packbits(pairs[2 * i + 1][0].reshape(-1) > 0.5) for i in range(K)])
+    mir_idx = np.full((K, 128), -1, np.int32)
+    mir_val = np.zeros((K, 128), np.float32)
+    for i in range(K):
+        nz = np.nonzero(pairs[2 * i + 1][1] > 0)[0]
+        mir_idx[i, :len(nz)] = nz
+        mir_val[i, :len(nz)] = pairs[2 * i + 1][1][nz]
     np.savez_compressed(
         os.path.join(HERE, "train_golden.npz"),
         board=np.array(boards, np.int8), side=np.array(sides, np.int8), n=np.array(ns, np.uint8), actions=np.array(acts),
         probs=np.array(probs), z=np.array(zs, np.float32), init=init, after1=after1, after2=after2, buffers=bn,
         stats1=np.array([stats1['policy_loss'], stats1['value_loss'], stats1['total_loss'], stats1['learning_rate']]),
         stats2=np.array([stats2['policy_loss'], stats2['value_loss'], stats2['total_loss'], stats2['learning_rate']]),
+        full_batch=np.array([stats0['policy_loss'], stats0['value_loss']]), mirror_planes=mir_planes, mirror_index=mir_idx,
+        mirror_value=mir_val,
         meta=np.array([CHANNELS, BLOCKS, RECORDS, BATCH, EPOCHS, SEED]))
     print("stats1", stats1)
     print("stats2", stats2)

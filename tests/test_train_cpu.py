@@ -80,3 +80,58 @@ def test_two_rank_gloo_record_fan_in(tmp_path):
     b = torch.load(os.path.join(str(tmp_path), "rank1.pt"))
     assert torch.equal(a["rec"], b["rec"]) and torch.equal(a["z"], b["z"]) and torch.equal(a["perm"], b["perm"])
     assert a["rec"].shape[0] == 5 + 9 and a["rec"][:5, 0].eq(0).all() and a["rec"][5:, 0].eq(1).all()
+
+
+# ---- the training oracle (oracle/xq_train_oracle.py) pinned against outputs of the reference itself ------------------
+GOLDEN = os.path.join(ROOT, "tests", "golden", "train_golden.npz")
+
+
+def test_oracle_augment_equals_the_references_augment_data():
+    import xq_train_oracle as O
+    g = dict(np.load(GOLDEN))
+    for i in range(len(g["mirror_planes"])):
+        n = int(g["n"][i])
+        st, pol, z = O.sample_tuple(g["board"][i], g["side"][i], g["actions"][i], g["probs"][i], n, g["z"][i], mirrored=True)
+        assert np.array_equal(np.packbits(st.reshape(-1) > 0.5), g["mirror_planes"][i])          # parallel_selfplay.py:142
+        nz = np.nonzero(pol > 0)[0]
+        k = int((g["mirror_index"][i] >= 0).sum())
+        assert np.array_equal(nz, g["mirror_index"][i, :k]) and np.array_equal(pol[nz], g["mirror_value"][i, :k])
+        # and the dense-tuple form of the same function
+        s0, p0, _ = O.sample_tuple(g["board"][i], g["side"][i], g["actions"][i], g["probs"][i], n, g["z"][i])
+        pair = O.augment([(s0, p0, z)])
+        assert np.array_equal(pair[1][0], st) and np.array_equal(pair[1][1], pol)
+
+
+def test_oracle_loss_equals_the_references_full_batch_loss():
+    """The reference's train_network on one batch holding the whole buffer with lr = 0 reports the loss of the initial
+    weights; the oracle's tuples + loss on the same network must give the same numbers (train.py:408-413)."""
+    import xq_train_oracle as O
+    from model import XiangqiNet
+    g = dict(np.load(GOLDEN))
+    ch, blocks, records, batch, epochs, seed = (int(x) for x in g["meta"])
+    torch.manual_seed(seed)
+    net = XiangqiNet(ch, blocks).train()
+    tuples = []
+    for i in range(records):
+        for m in (False, True):
+            tuples.append(O.sample_tuple(g["board"][i], g["side"][i], g["actions"][i], g["probs"][i], int(g["n"][i]), g["z"][i], m))
+    x = torch.from_numpy(np.stack([t[0] for t in tuples]))
+    with torch.no_grad():
+        logits, value = net(x)
+    pl, vl, _, _ = O.policy_value_loss(logits.numpy(), value.numpy(), np.stack([t[1] for t in tuples]), np.array([t[2] for t in tuples]))
+    assert abs(pl - g["full_batch"][0]) < 2e-4 * abs(g["full_batch"][0]) and abs(vl - g["full_batch"][1]) < 2e-4
+
+
+def test_oracle_clip_and_adam_equals_torch():
+    import xq_train_oracle as O
+    torch.manual_seed(3)
+    p = torch.nn.Parameter(torch.randn(1000, dtype=torch.float64))
+    opt = torch.optim.Adam([p], lr=0.002, weight_decay=1e-4)
+    pn, m, v = p.detach().numpy().copy(), np.zeros(1000), np.zeros(1000)
+    for step in range(1, 8):
+        grad = torch.randn(1000, dtype=torch.float64) * (5.0 if step % 2 else 0.01)
+        p.grad = grad.clone()
+        torch.nn.utils.clip_grad_norm_([p], 1.0)
+        opt.step()
+        pn, m, v = O.clip_and_adam(pn, grad.numpy(), m, v, step)
+        assert np.allclose(pn, p.detach().numpy(), rtol=1e-10, atol=1e-12)

@@ -41,15 +41,10 @@ def make_records(oracle, n, seed):
 
 
 def dense_reference(oracle, board, side, acts, n, probs, mirror):
-    """The reference tuple of one sample: get_state_for_nn planes + dense policy, mirrored as _augment_data does."""
-    from selfplay_engine import MIRROR
-    pl = oracle.planes(board, int(side))
-    pol = np.zeros(8100, np.float32)
-    a = acts[:n].astype(np.int64)
-    if mirror:
-        pl = np.flip(pl, axis=2).copy()
-        a = MIRROR[a]
-    pol[a] = probs[:n]
+    """The reference tuple of one sample from the training oracle (pinned against the reference's _augment_data)."""
+    import xq_train_oracle as O
+    pl, pol, _ = O.sample_tuple(board, side, acts, probs, n, 0.0, mirrored=mirror)
+    assert np.array_equal(pl if not mirror else np.flip(pl, axis=2), oracle.planes(board, int(side)))
     return pl, pol
 
 
@@ -128,6 +123,11 @@ def test_policy_value_loss_matches_torch(eng, oracle):
         rv = F.mse_loss(v2, z.reshape(B, 1)) * scale
         (rp + 0.5 * rv).backward()
         assert torch.allclose(pl, rp, rtol=1e-5, atol=1e-6) and torch.allclose(vl, rv, rtol=1e-5, atol=1e-6)
+        import xq_train_oracle as O                       # float64 restatement of train.py:408-413
+        opl, ovl, og, ogv = O.policy_value_loss(logits.detach().cpu().numpy(), value.detach().cpu().numpy(), dense.cpu().numpy(),
+                                                z.cpu().numpy())
+        assert abs(pl.item() - opl * scale) < 1e-5 * abs(opl) + 1e-6 and abs(vl.item() - ovl * scale) < 1e-5
+        assert np.allclose(logits.grad.cpu().numpy(), og * scale, rtol=1e-4, atol=1e-8)
         assert torch.allclose(logits.grad, l2.grad, rtol=1e-4, atol=1e-8)
         assert torch.allclose(value.grad, v2.grad, rtol=1e-5, atol=1e-8)
 
