@@ -8,6 +8,8 @@ Workloads (BASELINE.json `configs`):
             random-playout positions per GPU; metric = legal-move positions/s.
   selfplay  configs[2]: 4096 concurrent self-play games x 800 MCTS simulations/move with the
             128ch x 6 ResNet evaluator; metric = MCTS simulations/s.  (The default.)
+  iteration configs[4]: one full iteration (self-play, training, evaluation) of the standard preset
+            with 1024 games per GPU; metric = seconds per iteration (bench_iteration.py).
   train     configs[4], training step: global batch 256, Adam, clip, XiangqiNet(128,6) on the
             device-resident replay ring; metric = training samples/s (bench_train.py).
 
@@ -319,7 +321,7 @@ def main():
     ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default=None, choices=[None, "movegen", "selfplay", "train"])
+    ap.add_argument("--workload", default=None, choices=[None, "movegen", "selfplay", "train", "iteration"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.workload is None:
@@ -354,6 +356,10 @@ def main():
             sys.path.insert(0, ROOT)
             import bench_train
             bench_train.run(args, rank, world, local_rank, dist)
+        elif args.workload == "iteration":
+            sys.path.insert(0, ROOT)
+            import bench_iteration
+            bench_iteration.run(args, rank, world, local_rank, dist)
         else:
             sys.path.insert(0, ROOT)
             import bench_selfplay

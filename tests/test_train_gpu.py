@@ -276,3 +276,21 @@ def test_one_iteration_self_play_train_evaluate(eng, tmp_path):
     assert ev["new_wins"] + ev["old_wins"] + ev["draws"] == 5
     same = all(torch.equal(a, b) for a, b in zip(tr.current_model.state_dict().values(), tr.best_model.state_dict().values()))
     assert same                                        # promoted or reverted: both models agree afterwards (train.py:528-533)
+    # second iteration: the arena ran on its own context, the self-play slots are still this trainer's
+    sp2 = tr.self_play()
+    assert sp2["games"] == 24 and sp2["buffer_size"] == len(tr.replay_buffer) == sp["new_samples"] + sp2["new_samples"]
+
+
+def test_superseded_selfplay_engine_fails_loudly(eng):
+    import torch
+    import xq_native
+    from model import XiangqiNet
+    from selfplay_engine import SelfPlayEngine
+    e2 = xq_native.Engine(0)
+    m = XiangqiNet(128, 1).eval()
+    a = SelfPlayEngine(e2, m, n_slots=4, max_games=4, max_simulations=4)
+    b = SelfPlayEngine(e2, m, n_slots=2, max_games=2, max_simulations=4)     # same context: takes the state over
+    with pytest.raises(xq_native.XqError):
+        a.reset()
+    b.reset()
+    e2.close()

@@ -34,6 +34,8 @@ def shard_pairs(num_games: int, rank: int, world: int) -> int:
 
 class Arena:
     def __init__(self, eng: "xq_native.Engine", model_new, model_old, num_games: int, max_simulations: int):
+        # NOTE: a context holds one self-play state; give the arena its own xq_native.Engine when a SelfPlayEngine on
+        # `eng` must stay usable (AlphaZeroTrainer does)
         self.e = eng
         self.num_games = int(num_games)
         self.sp = SelfPlayEngine(eng, model_new, n_slots=self.num_games, max_games=self.num_games, sample_capacity=1,
@@ -75,7 +77,8 @@ class Arena:
 
 def evaluate_models(eng, model_new, model_old, eval_games: int, eval_simulations: int, c_puct: float,
                     max_game_length: int, dist=None):
-    """The numbers of train.py:512-520: new_wins, old_wins, draws, win_rate (all ranks return the same dict)."""
+    """The numbers of train.py:512-520: new_wins, old_wins, draws, win_rate (all ranks return the same dict).
+    `eng`: the context the arena may take over (its previous SelfPlayEngine, if any, is superseded)."""
     rank, world = (dist.get_rank(), dist.get_world_size()) if dist is not None else (0, 1)
     mine = shard_pairs(eval_games, rank, world)
     counts = torch.zeros(3, dtype=torch.int64, device=eng.dev)

@@ -87,6 +87,7 @@ class SelfPlayEngine:
             node_capacity = self.n_slots * (self.max_simulations + 2) * 64 + self.n_slots
         self.node_capacity = int(node_capacity)
         eng._check(eng.L.xq_selfplay_create(eng.h, self.n_slots, self.max_games, self.sample_capacity, self.node_capacity))
+        eng._selfplay_owner = self      # a context holds ONE self-play state: a later SelfPlayEngine on it supersedes this one
         self.net = None
         self.set_model(model)
         self.fetched = 0
@@ -113,17 +114,25 @@ class SelfPlayEngine:
                          resign_check_steps=int(g("resign_check_steps", 5)), add_noise=int(bool(add_noise)),
                          dirichlet_alpha=0.3, seed=int(seed) & 0xFFFFFFFFFFFFFFFF, target_games=int(target_games))
 
+    def _own(self):
+        if getattr(self.e, "_selfplay_owner", None) is not self:
+            raise xq_native.XqError("this SelfPlayEngine was superseded by a newer one on the same engine context "
+                                    "(one context holds one self-play state); create it on its own xq_native.Engine")
+
     def reset(self):
+        self._own()
         self.e._check(self.e.L.xq_selfplay_reset(self.e.h, self.e._stream()))
         self.fetched = 0
 
     def play(self, cfg: _SpConfig, n_plies: int):
+        self._own()
         if cfg.num_simulations > self.max_simulations:
             raise xq_native.XqError(f"num_simulations {cfg.num_simulations} exceeds the node pool sized for "
                                     f"{self.max_simulations}: build the SelfPlayEngine with max_simulations >= it")
         self.e._check(self.e.L.xq_selfplay_play(self.e.h, C.byref(cfg), C.byref(self.plan), int(n_plies), self.e._stream()))
 
     def counters(self):
+        self._own()
         buf = (C.c_longlong * 14)()
         self.e._check(self.e.L.xq_selfplay_counters(self.e.h, buf))
         k = ["started", "finished", "samples", "red_wins", "black_wins", "draws", "plies_finished", "dropped",
@@ -152,6 +161,7 @@ class SelfPlayEngine:
     def play_games(self, cfg: _SpConfig, max_plies: int = 100000, chunk: int = 8):
         """Play until cfg.target_games games have finished (or max_plies plies)."""
         played = 0
+        last_finished, last_progress = -1, 0
         while played < max_plies:
             step = min(chunk, max_plies - played)
             self.play(cfg, step)
@@ -159,8 +169,12 @@ class SelfPlayEngine:
             c = self.counters()
             if c["error"]:
                 raise xq_native.XqError(f"self-play device error bits {c['error']}")
-            if c["finished"] >= cfg.target_games:
+            if c["finished"] >= min(cfg.target_games, self.max_games):
                 break
+            if c["finished"] != last_finished:
+                last_finished, last_progress = c["finished"], played
+            elif played - last_progress > 2 * 201 + 64:      # no game can last this long (game.py:595: 200 plies)
+                raise xq_native.XqError(f"self-play made no progress for {played - last_progress} plies: {c}")
         return self.counters()
 
 

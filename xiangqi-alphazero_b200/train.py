@@ -245,6 +245,7 @@ class AlphaZeroTrainer:
         self.total_games = 0
         self.training_stats = []
         self._sp = None
+        self._arena_eng = None          # second context on the same GPU: the arena's slots do not disturb the self-play state
         if self.rank == 0:
             os.makedirs(config.checkpoint_dir, exist_ok=True)
         self.num_workers = self.world
@@ -272,7 +273,8 @@ class AlphaZeroTrainer:
             slots = min(my_games, int(getattr(cfg, "selfplay_slots", 4096)))
             sims = int(cfg.num_simulations)
             sp = self._sp
-            if sp is None or sp.n_slots != slots or sp.max_games < my_games or sp.max_simulations < sims:
+            if (sp is None or getattr(self.eng, "_selfplay_owner", None) is not sp or sp.n_slots != slots
+                    or sp.max_games < my_games or sp.max_simulations < sims):
                 self._sp = None
                 sp = SelfPlayEngine(self.eng, self.best_model, n_slots=slots, max_games=my_games, max_simulations=sims)
                 self._sp = sp
@@ -347,7 +349,10 @@ class AlphaZeroTrainer:
     # ---- evaluation ------------------------------------------------------------------------------------
     def evaluate(self) -> dict:
         cfg = self.config
-        r = _arena.evaluate_models(self.eng, self.current_model, self.best_model, int(cfg.eval_games), int(cfg.eval_simulations),
+        if self._arena_eng is None:
+            import xq_native
+            self._arena_eng = xq_native.Engine(self.local_device)
+        r = _arena.evaluate_models(self._arena_eng, self.current_model, self.best_model, int(cfg.eval_games), int(cfg.eval_simulations),
                                    float(cfg.c_puct), int(cfg.max_game_length), dist=self.dist if self.world > 1 else None)
         stats = {'new_wins': r['new_wins'], 'old_wins': r['old_wins'], 'draws': r['draws'], 'win_rate': r['win_rate'],
                  'model_updated': r['win_rate'] >= cfg.eval_win_rate}
