@@ -267,6 +267,14 @@ def test_one_iteration_self_play_train_evaluate(eng, tmp_path):
     sp = tr.self_play()
     assert set(sp) >= {"games", "red_wins", "black_wins", "draws", "avg_steps", "new_samples", "buffer_size"}
     assert sp["games"] == 24 and sp["buffer_size"] == len(tr.replay_buffer) == sp["new_samples"] > 0
+    # the ring holds whole games in game-major order (the reference extends its deque game by game), z in {-1, 0, 1}
+    from selfplay_engine import decode_samples
+    r, z = tr.replay_buffer.records_in_order()
+    dec = decode_samples(r.cpu().numpy())
+    key = dec["uid"].astype(np.int64) * 1024 + dec["ply"]
+    assert (np.diff(key) > 0).all() and set(np.unique(z.cpu().numpy())) <= {-1.0, 0.0, 1.0}
+    first = np.r_[True, np.diff(dec["uid"]) != 0]
+    assert (np.diff(dec["ply"])[~first[1:]] == 1).all()           # consecutive plies of one game
     before = [p.detach().clone() for p in tr.current_model.parameters()]
     st = tr.train_network()
     assert set(st) == {"policy_loss", "value_loss", "total_loss", "learning_rate"} and np.isfinite(st["total_loss"])

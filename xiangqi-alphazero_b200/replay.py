@@ -115,16 +115,21 @@ class DeviceReplayBuffer:
         return n
 
     def append_from_selfplay(self, sp, n_samples: int) -> int:
-        """All samples of FINISHED games among the first n_samples records of a SelfPlayEngine, in device order."""
+        """All samples of FINISHED games among the first n_samples records of a SelfPlayEngine, GAME-MAJOR (game uid, then
+        ply): the reference extends its deque game by game (parallel_selfplay.py:373-386), so when an iteration yields
+        more samples than the buffer holds, whole recent games survive -- not the last plies of every game, which is
+        what the device's ply-interleaved append order would keep."""
         if n_samples <= 0:
             return 0
         rec, winner, _ = selfplay_buffers(sp)
         uid = rec[:n_samples, 92:96].contiguous().view(torch.int32).reshape(-1).long()
+        ply = rec[:n_samples, 96:100].contiguous().view(torch.int32).reshape(-1).long()
         ok = (uid >= 0) & (uid < winner.numel())
         done = torch.zeros_like(ok)
         done[ok] = winner[uid[ok]] != 2
         index = torch.nonzero(done).reshape(-1)
-        return self.append_records(rec, index, winner)
+        order = torch.argsort(uid[index] * 1024 + ply[index], stable=True)
+        return self.append_records(rec, index[order], winner)
 
     def append_raw(self, records: torch.Tensor, z: torch.Tensor) -> int:
         """Already-labelled records (device or host tensors): uid is ignored, z is taken as given."""
