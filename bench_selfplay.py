@@ -171,7 +171,7 @@ def run(args, rank, world, local_rank, dist):
         "metric": "mcts_sims_per_sec", "value": value, "unit": "sims/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic (seeded random-init weights, self-generated games)",
-        "config": {"workload": f"selfplay: configs[2], {games} concurrent games/GPU x {sims} sims/move, "
+        "config": {"workload": f"selfplay: {'configs[3] (32768 games over 8 GPUs = 4096 per GPU)' if (CHANNELS, BLOCKS) == (256, 20) else 'configs[2]'}, {games} concurrent games/GPU x {sims} sims/move, "
                                f"XiangqiNet({CHANNELS},{BLOCKS}), c_puct 1.5, Dirichlet(0.3) root noise, step = one ply of every game",
                    "games_per_gpu": games, "sims_per_move": sims, "evals_in_region": evals_done,
                    "l2": "per-step working set (trees + activations, > 1 GB) >> 126 MB L2",
