@@ -105,6 +105,16 @@ def run(args, rank, world, local_rank, dist):
     f1.record()
     torch.cuda.synchronize()
     fwd_ms = f0.elapsed_time(f1) / 20
+    # the dominant kernel alone: one residual-tower conv (layer 1 = first conv of block 0), 20 back-to-back launches
+    for _ in range(3):
+        net.run_layer(1)
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    for _ in range(20):
+        net.run_layer(1)
+    k1.record()
+    torch.cuda.synchronize()
+    conv_ms = k0.elapsed_time(k1) / 20
 
     # e2e: the same plies through the host-facing API -- per step the host uploads the step's control
     # block and downloads that ply's sample records and counters (pinned host memory)
@@ -149,9 +159,9 @@ def run(args, rank, world, local_rank, dist):
         mv = {"error": str(ex)[:200]}
 
     if world > 1:
-        t = torch.tensor([ms, e2e_s, fwd_ms], device=eng.dev, dtype=torch.float64)
+        t = torch.tensor([ms, e2e_s, fwd_ms, conv_ms], device=eng.dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_s, fwd_ms = t.tolist()
+        ms, e2e_s, fwd_ms, conv_ms = t.tolist()
         cnt = torch.tensor([sims_done, evals_done, e2e_sims], device=eng.dev, dtype=torch.float64)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
         sims_done, evals_done, e2e_sims = cnt.tolist()
@@ -164,6 +174,10 @@ def run(args, rank, world, local_rank, dist):
     # i.e. the whole step (search kernels, launch gaps, power-capped clocks) is charged to the tensor kernels
     achieved_tf = FLOPS_PER_EVAL * evals_done / world / (ms * 1e-3) / 1e12
     isolated_tf = FLOPS_PER_EVAL * games / (fwd_ms * 1e-3) / 1e12
+    conv_flops = 2 * 90 * 9 * CHANNELS * CHANNELS * games          # algorithmic: 90 cells x 9 taps x C x C MACs per board
+    conv_tf = conv_flops / (conv_ms * 1e-3) / 1e12
+    # ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one tower conv at batch 4096 (profiles/r1_net_ncu.md)
+    conv_traffic = {(128, 4096): 182.6e6, (256, 4096): None}.get((CHANNELS, games))
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cpu = cpu_selfplay_rate(os.cpu_count() or 1, sims=min(sims, 100))
@@ -178,10 +192,16 @@ def run(args, rank, world, local_rank, dist):
                    "parallelism": f"games sharded x{world}, no collective in self-play"},
         "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": achieved_tf / peak_tf,
-                     "traffic": {"unit": "MB per launch", "conv4_kernel<128,8,0,1>": 184.3, "conv4_kernel<128,8,0,1> (+residual)": 307.6,
-                                 "gemm_kernel<2,128,8>": 134.9, "source": "profiles/r1_net_ncu.md (ncu --set full, dram read+write)"},
+                     "traffic": conv_traffic,
+                     "traffic_detail": {"unit": "MB per launch (ncu --set full, dram read + write, batch 4096, 128 channels)",
+                                        "conv4_kernel<128,8,0,3>": 182.6, "conv4_kernel<128,8,0,3> (+residual)": 306.3,
+                                        "fc4_kernel": 142.5, "algorithmic conv": 230.7, "source": "profiles/r1_net_ncu.md"},
                      "peak_source": peak_kind + " (sustained bf16)",
-                     "kernel": "conv4_kernel x14 + gemm_kernel<2> (tcgen05 implicit-GEMM forward) + value_head_kernel",
+                     "kernel": f"conv4_kernel x{2 * BLOCKS + 2} + fc4_kernel (tcgen05 implicit-GEMM forward) + value_head_kernel",
+                     "dominant_kernel": {"name": f"conv4_kernel<{CHANNELS}->{CHANNELS}, 3x3> (residual tower, {2 * BLOCKS} launches per forward)",
+                                         "ms_per_launch": conv_ms, "algorithmic_flops_per_launch": conv_flops,
+                                         "achieved_tflops": conv_tf, "frac_of_burst_peak": conv_tf / peaks["bf16_tflops"],
+                                         "timing": "20 back-to-back launches alone, CUDA events"},
                      "algorithmic_flops_per_eval": FLOPS_PER_EVAL, "forward_ms_isolated": fwd_ms,
                      "forward_isolated_tflops": isolated_tf, "forward_isolated_frac_of_burst_peak": isolated_tf / peaks["bf16_tflops"],
                      "note": "achieved = FLOPs of all evaluations in the timed region / region time (search kernels and "

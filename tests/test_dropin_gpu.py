@@ -176,3 +176,71 @@ def test_hand_rolled_search_loop_like_benchmark_py(oracle):
     host_counts = [c.visit_count for c in root.children.values()]
     dev = MC.MCTS(net, num_simulations=sims, c_puct=1.5).search(g, temperature=1.0, add_noise=False)
     assert [int(round(dev[a] * sims)) for a in root.children] == host_counts
+
+
+def test_is_move_legal_agrees_with_the_move_list():
+    """game.py:441-490: every listed move passes, moves that leave the king attacked or facing fail."""
+    import game as G
+    g = G.XiangqiGame()
+    g._init_board()
+    assert len(g.get_legal_moves()) == 44
+    rnd = random.Random(5)
+    for _ in range(40):
+        moves = g.get_legal_moves()
+        if not moves:
+            break
+        legal = set(moves)
+        side = g.current_player
+        for m in rnd.sample(moves, min(4, len(moves))):
+            assert g._is_move_legal(*m, side) is True
+        before = g.board.copy()
+        own = [(r, c) for r in range(10) for c in range(9) if g.board[r, c] * side > 0]
+        for (r, c) in own[:6]:
+            for (tr, tc) in ((r + 1, c), (r, c + 1)):
+                if 0 <= tr < 10 and 0 <= tc < 9 and g.board[tr, tc] * side <= 0 and (r, c, tr, tc) in legal:
+                    assert g._is_move_legal(r, c, tr, tc, side)
+        assert np.array_equal(before, g.board)                        # the board is left untouched
+        g.make_move(*rnd.choice(moves))
+    # facing kings: the red king may not step onto the open file of the black king
+    f = G.XiangqiGame(); f.board[:] = 0
+    f.board[0, 3], f.board[9, 4] = 1, -1
+    assert f._is_move_legal(0, 3, 0, 4, 1) is False and f._is_move_legal(0, 3, 1, 3, 1) is True
+    assert (0, 3, 0, 4) not in f.get_legal_moves() and (0, 3, 1, 3) in f.get_legal_moves()
+
+
+def test_single_game_entry_points_of_the_reference(tmp_path):
+    """parallel_selfplay._play_one_game (:42-134) and AlphaZeroTrainer.self_play_game / _serial_self_play
+    (train.py:227-301, 329-374): return shapes, labels and buffer accounting."""
+    import torch
+    import model as M
+    import parallel_selfplay as ps
+    import train as T
+
+    class Cfg:
+        num_simulations, c_puct, temperature_threshold, max_game_length = 8, 1.5, 4, 12
+        random_opening_moves, enable_resign, resign_threshold, resign_check_steps = 2, True, -0.9, 5
+        num_games_per_iter = 1
+    torch.manual_seed(3)
+    net = M.XiangqiNet(128, 1).eval()
+    data, winner, plies = ps._play_one_game(net, Cfg(), 'cpu')
+    assert winner in (1, -1, 0) and 0 < len(data) <= plies <= 12 + 2
+    for st, pol, z in data:
+        assert st.shape == (15, 10, 9) and pol.shape == (8100,) and abs(pol.sum() - 1) < 1e-6
+        assert z == (0.0 if winner == 0 else (1.0 if (st[14, 0, 0] == 1) == (winner == 1) else -1.0))
+
+    cfg = T.TrainingConfig()
+    cfg.num_channels, cfg.num_res_blocks, cfg.num_simulations, cfg.num_games_per_iter = 128, 1, 6, 2
+    cfg.max_game_length, cfg.temperature_threshold, cfg.random_opening_moves = 5, 2, 2
+    cfg.checkpoint_dir = str(tmp_path)
+    tr = T.AlphaZeroTrainer(cfg)
+    random.seed(1); np.random.seed(1)
+    data, winner, steps = tr.self_play_game()
+    assert steps == len(data) == 5 and winner in (1, -1, 0)
+    assert all(abs(p.sum() - 1) < 1e-9 and z in (-1.0, 0.0, 1.0) for _, p, z in data)
+    st = tr._serial_self_play()
+    assert st['games'] == 2 and st['new_samples'] == 20 == st['buffer_size'] == len(tr.replay_buffer)
+    assert st['red_wins'] + st['black_wins'] + st['draws'] == 2
+    pair = T.augment_data(*data[0])
+    assert np.array_equal(pair[1][0], np.flip(data[0][0], axis=2)) and abs(pair[1][1].sum() - 1) < 1e-9
+    g = T.make_random_opening(T.XiangqiGame(), 3)
+    assert g.move_count == 3 and len(g.history) == 3

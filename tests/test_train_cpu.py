@@ -135,3 +135,31 @@ def test_oracle_clip_and_adam_equals_torch():
         opt.step()
         pn, m, v = O.clip_and_adam(pn, grad.numpy(), m, v, step)
         assert np.allclose(pn, p.detach().numpy(), rtol=1e-10, atol=1e-12)
+
+
+def test_train_module_augment_data_and_dataset_follow_the_reference():
+    """train.augment_data (train.py:132-151) and SelfPlayDataset (train.py:114-129) against the committed outputs of the
+    reference's own augmentation (tests/golden/make_train_golden.py)."""
+    import ast
+    src = open(os.path.join(ROOT, "xiangqi-alphazero_b200", "train.py")).read()
+    # the module imports the CUDA library's bindings; the two helpers are pure numpy/torch and are checked on their own
+    tree = ast.parse(src)
+    keep = [n for n in tree.body if isinstance(n, (ast.FunctionDef, ast.ClassDef)) and n.name in ("augment_data", "SelfPlayDataset")]
+    ns = {"np": np, "torch": torch, "List": list, "Tuple": tuple}
+    sys.path.insert(0, os.path.join(ROOT, "xiangqi-alphazero_b200"))
+    exec(compile(ast.Module(body=keep, type_ignores=[]), "train.py", "exec"), ns)
+    import xq_train_oracle as O
+    g = dict(np.load(GOLDEN))
+    for i in range(len(g["mirror_planes"])):
+        n = int(g["n"][i])
+        s0, p0, z = O.sample_tuple(g["board"][i], g["side"][i], g["actions"][i], g["probs"][i], n, g["z"][i])
+        pair = ns["augment_data"](s0, p0, z)
+        assert pair[0][0] is s0 and pair[0][1] is p0 and len(pair) == 2
+        assert np.array_equal(np.packbits(pair[1][0].reshape(-1) > 0.5), g["mirror_planes"][i])
+        nz = np.nonzero(pair[1][1] > 0)[0]
+        k = int((g["mirror_index"][i] >= 0).sum())
+        assert np.array_equal(nz, g["mirror_index"][i, :k]) and np.array_equal(pair[1][1][nz], g["mirror_value"][i, :k])
+        ds = ns["SelfPlayDataset"](pair)
+        st, pol, val = ds[1]
+        assert len(ds) == 2 and st.dtype == torch.float32 and st.shape == (15, 10, 9) and pol.shape == (8100,) and val.shape == (1,)
+        assert float(val) == float(z)

@@ -67,13 +67,18 @@ class XiangqiGame:
                  '_legal_moves_cache', '_check_cache']
 
     def __init__(self):
-        self.board = _START.copy()
+        self.board = np.zeros((ROWS, COLS), dtype=np.int8)
+        self._init_board()
         self.current_player = 1
         self.move_count = 0
         self.history = []
         self.no_capture_count = 0
         self._legal_moves_cache = None
         self._check_cache = None
+
+    def _init_board(self):
+        """Start position (game.py:139-159): red on rows 0-4, black on rows 5-9."""
+        self.board[:] = _START
 
     def clone(self) -> 'XiangqiGame':
         g = XiangqiGame.__new__(XiangqiGame)
@@ -126,6 +131,18 @@ class XiangqiGame:
         if k is None:
             return True                                            # game_core.pyx:552-554
         return self._is_attacked(board, k[0], k[1], -player)
+
+    def _is_move_legal(self, fr: int, fc: int, tr: int, tc: int, player: int) -> bool:
+        """game.py:441-490: after the move `player`'s king must stand in its palace, must not face the other
+        king on an open file and must not be attacked.  One GPU query on the moved board: the attack test
+        counts the enemy king as a rook (game.py:176-200), which is the facing-kings test."""
+        b = self.board.copy()
+        b[tr, tc] = b[fr, fc]
+        b[fr, fc] = EMPTY
+        k = self._find_king_pos(player, b)
+        if k is None:
+            return False
+        return not self._is_attacked(b, k[0], k[1], -player)
 
     @staticmethod
     def _kings_facing_fast(board: np.ndarray) -> bool:

@@ -45,8 +45,9 @@ def shard_games(num_games: int, rank: int, world: int) -> int:
     return num_games // world + (1 if rank < num_games % world else 0)
 
 
-def _play_local(model, config, my_games: int, local_device: int):
-    """This rank's share of the games on its GPU -> (samples, wins, total_plies, valid_games)."""
+def _play_local(model, config, my_games: int, local_device: int, augment: bool = True, detail: bool = False):
+    """This rank's share of the games on its GPU -> (samples, wins, total_plies, valid_games)
+    (+ per-game winner and ply arrays when `detail`)."""
     data, wins, total_steps, valid = [], {1: 0, -1: 0, 0: 0}, 0, 0
     if my_games <= 0:
         return data, wins, total_steps, valid
@@ -70,13 +71,33 @@ def _play_local(model, config, my_games: int, local_device: int):
     c = sp.play_games(cfg)
     raw, winner, plies = sp.fetch(0, c["samples"])
     dec = decode_samples(raw)
-    data = samples_to_reference_tuples(dec, winner, augment=True)
+    data = samples_to_reference_tuples(dec, winner, augment=augment)
     for g in range(my_games):
         if winner[g] != 2:
             valid += 1
             wins[int(winner[g])] += 1
             total_steps += int(plies[g])
+    if detail:
+        return data, wins, total_steps, valid, winner[:my_games].copy(), plies[:my_games].copy()
     return data, wins, total_steps, valid
+
+
+def _play_one_game(model_or_client, config, device='cpu') -> Tuple[List, int, int]:
+    """parallel_selfplay.py:42-134 for callers that play single games: one game on the device loop (one slot),
+    returning (training_data without the mirrored twins, winner, plies).  `model_or_client` is a XiangqiNet or an
+    inference_server.InferenceClient (its server's model is used); `device` is accepted and ignored -- the game
+    runs on the engine's GPU."""
+    model = model_or_client
+    if not hasattr(model, "num_res_blocks"):
+        import inference_server
+        model = inference_server._MODELS.get(getattr(model_or_client, "socket_path", None))
+        if model is None:
+            raise RuntimeError("inference server is not running")
+    local_device = int(os.environ.get("LOCAL_RANK", "0")) if _dist() else 0
+    data, _, _, valid, winner, plies = _play_local(model, config, 1, local_device, augment=False, detail=True)
+    if not valid:
+        raise RuntimeError("self-play game did not finish")
+    return data, int(winner[0]), int(plies[0])
 
 
 def parallel_self_play(model, config, num_workers: Optional[int] = None, use_gpu_server: bool = False,

@@ -88,6 +88,46 @@ class TrainingConfig:
         self.sync_batchnorm = True      # data parallel: BatchNorm statistics over the GLOBAL minibatch (reference semantics)
 
 
+class SelfPlayDataset(torch.utils.data.Dataset):
+    """train.py:114-129: dense (planes, policy[8100], z) tuples as float tensors.  The trainer below does not use it
+    (minibatches are built on the device from the sparse replay ring); it stays for scripts that feed their own
+    DataLoader."""
+
+    def __init__(self, data: List[Tuple[np.ndarray, np.ndarray, float]]):
+        self.data = data
+
+    def __len__(self):
+        return len(self.data)
+
+    def __getitem__(self, idx):
+        state, policy, value = self.data[idx]
+        return (torch.as_tensor(np.ascontiguousarray(state), dtype=torch.float32),
+                torch.as_tensor(np.ascontiguousarray(policy), dtype=torch.float32),
+                torch.tensor([float(value)], dtype=torch.float32))
+
+
+def augment_data(state: np.ndarray, policy: np.ndarray, value: float) -> List[Tuple]:
+    """train.py:132-151: the sample and its column mirror; the policy is moved by the action permutation
+    (fr,fc,tr,tc) -> (fr,8-fc,tr,8-tc) in one scatter instead of a loop over the 8100 actions."""
+    from selfplay_engine import MIRROR
+    flipped_policy = np.zeros_like(policy)
+    nz = np.nonzero(policy > 0)[0]
+    flipped_policy[MIRROR[nz]] = policy[nz]
+    return [(state, policy, value), (np.flip(state, axis=2).copy(), flipped_policy, value)]
+
+
+def make_random_opening(game: XiangqiGame, num_moves: int) -> XiangqiGame:
+    """train.py:154-165: up to `num_moves` uniformly random legal moves, stopping at a finished game."""
+    for _ in range(num_moves):
+        moves = game.get_legal_moves()
+        if not moves:
+            break
+        game.make_move(*random.choice(moves))
+        if game.is_game_over()[0]:
+            break
+    return game
+
+
 def _dist():
     try:
         import torch.distributed as dist
@@ -261,6 +301,67 @@ class AlphaZeroTrainer:
 
     def _gather_new_records(self, rec, z):
         return gather_records(rec, z, self.dist if self.world > 1 else None)
+
+    # ---- single-game path of the reference (train.py:227-301, 329-374): kept for debugging ------------------
+    def self_play_game(self) -> Tuple[List, int, int]:
+        """One game of the reference's SERIAL loop (its own temperature ramp 1.0 -> 0.1 over 10 plies after the
+        threshold and its resign test from ply 41 on, train.py:245-283) on the drop-in MCTS / XiangqiGame, i.e. every
+        search, rule query and evaluation runs on the GPU kernels, one position at a time."""
+        cfg = self.config
+        game = XiangqiGame()
+        if cfg.random_opening_moves > 0:
+            game = make_random_opening(game, random.randint(0, cfg.random_opening_moves))
+        mcts = MCTS(self.best_model, num_simulations=cfg.num_simulations, c_puct=cfg.c_puct, device=self.device)
+        records, step, low_values, done, winner = [], 0, 0, False, None
+        while step < cfg.max_game_length:
+            over = step - cfg.temperature_threshold
+            temperature = 1.0 if over < 0 else (1.0 - 0.9 * over / 10 if over < 10 else 0.1)
+            probs = mcts.search(game, temperature=temperature, add_noise=True)
+            records.append((game.get_state_for_nn(), probs, game.current_player))
+            action = int(np.random.choice(len(probs), p=probs)) if temperature > 0.05 else int(np.argmax(probs))
+            game.make_move(*decode_action(action))
+            step += 1
+            done, winner = game.is_game_over()
+            if done:
+                break
+            if cfg.enable_resign and step > 40:
+                _, value = self.best_model.predict(game.get_state_for_nn(), self.device)
+                low_values = low_values + 1 if value < cfg.resign_threshold else 0
+                if low_values >= cfg.resign_check_steps:
+                    done, winner = True, -game.current_player
+                    break
+        if not done:
+            done, winner = game.is_game_over()
+        winner = 0 if winner is None else winner
+        data = [(st, pr, 0.0 if winner == 0 else (1.0 if winner == side else -1.0)) for st, pr, side in records]
+        return data, winner, step
+
+    def _serial_self_play(self) -> dict:
+        """train.py:329-374: `num_games_per_iter` single games, each sample stored with its mirror."""
+        cfg = self.config
+        results, total_steps, new = {1: 0, -1: 0, 0: 0}, 0, 0
+        for _ in range(cfg.num_games_per_iter):
+            data, winner, steps = self.self_play_game()
+            pairs = []
+            for st, pr, z in data:
+                pairs.extend(augment_data(st, pr, z))
+            self.replay_buffer.extend(pairs)
+            new += len(pairs)
+            results[winner] = results.get(winner, 0) + 1
+            total_steps += steps
+            self.total_games += 1
+        return {'games': cfg.num_games_per_iter, 'red_wins': results[1], 'black_wins': results[-1], 'draws': results[0],
+                'avg_steps': total_steps / max(cfg.num_games_per_iter, 1), 'buffer_size': len(self.replay_buffer),
+                'new_samples': new}
+
+    def _parallel_self_play(self) -> dict:
+        """train.py:313-327.  The parallel path IS the device-resident loop of self_play()."""
+        return self.self_play()
+
+    def _serial_evaluate(self) -> dict:
+        """train.py:453-535.  evaluate() plays the same games (same colours, greedy moves, same promotion rule)
+        as one batched arena; tests/test_train_gpu.py checks it move for move against the serial loop."""
+        return self.evaluate()
 
     # ---- self-play -----------------------------------------------------------------------------------
     def self_play(self) -> dict:
