@@ -107,7 +107,7 @@ def planes(board, player) -> np.ndarray:
     return out
 
 
-def movegen_batch(boards, sides, want_planes=False):
+def movegen_batch(boards, sides, want_planes=False, allow_overflow=False):
     boards = np.ascontiguousarray(boards, np.int8).reshape(-1, 90)
     sides = np.ascontiguousarray(sides, np.int8)
     B = boards.shape[0]
@@ -118,7 +118,7 @@ def movegen_batch(boards, sides, want_planes=False):
     ovf = lib().xqo_movegen_batch(_p(boards, C.c_int8), _p(sides, C.c_int8), B, _p(acts, C.c_int16),
                                   _p(n, C.c_uint8), _p(chk, C.c_uint8),
                                   _p(pl, C.c_float) if want_planes else None)
-    assert ovf == 0, "a position had more than 128 legal moves"
+    assert ovf == 0 or allow_overflow, "a position had more than 128 legal moves"
     return acts, n, chk, pl
 
 

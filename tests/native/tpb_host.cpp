@@ -1,0 +1,25 @@
+// Test-only host build of csrc/xq_rules_tpb.h (the scalar rules the thread-per-board kernel runs):
+// g++ compiles the very same header, tests/test_tpb_cpu.py compares it with the oracle.  Not part of
+// libxq_b200.so -- the product has no CPU path.
+#include <cstdint>
+#include <cstring>
+#include "../../xiangqi-alphazero_b200/csrc/xq_rules_tpb.h"
+
+extern "C" int xqt_host_movegen_batch(const int8_t* boards, const int8_t* sides, int B, int16_t* actions,
+                                      uint8_t* n_moves, uint8_t* in_check)
+{
+    int overflow = 0;
+    for (int i = 0; i < B; ++i) {
+        int8_t b[90];
+        std::memcpy(b, boards + (size_t)i * 90, 90);
+        uint16_t list[xqt::kListCap];
+        int chk = 0;
+        int n = xqt::movegen(b, sides[i], list, &chk);
+        if (std::memcmp(b, boards + (size_t)i * 90, 90) != 0) return -1 - i;   // the board must come back untouched
+        if (n > 128) { ++overflow; n = 128; }
+        for (int k = 0; k < 128; ++k) actions[(size_t)i * 128 + k] = k < n ? (int16_t)list[k] : (int16_t)-1;
+        n_moves[i] = (uint8_t)n;
+        in_check[i] = (uint8_t)chk;
+    }
+    return overflow;
+}
