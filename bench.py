@@ -270,7 +270,9 @@ def bench_movegen(args, rank, world, local_rank, dist):
                    "l2": "outputs 5.66 GB/step >> 126 MB L2, no flush needed", "parallelism": f"games sharded x{world}, no collective"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_kind,
-                     "kernel": "movegen_kernel<true>", "algorithmic_bytes_per_position": ALGO_BYTES_MOVEGEN_PLANES,
+                     "kernel": {"warp": "movegen_kernel<true> (one warp per board)",
+                                "thread": "movegen_tpb_kernel<true> (one thread per board)"}[eng.movegen_impl],
+                     "algorithmic_bytes_per_position": ALGO_BYTES_MOVEGEN_PLANES,
                      "kernel_ms": kern_ms},
         "cpu_baseline": cpu,
         "e2e": {"value": world * NE / e2e_s, "unit": "positions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -151,7 +151,8 @@ def run(args, rank, world, local_rank, dist):
         torch.cuda.synchronize()
         mv_ms = m0.elapsed_time(m1) / 5
         mv = {"metric": "legal_move_positions_per_sec", "value": pb.shape[0] / (mv_ms * 1e-3), "unit": "positions/s (per GPU)",
-              "kernel": "movegen_kernel<true> (moves + in-check + fp32 planes)", "kernel_ms": mv_ms,
+              "kernel": {"warp": "movegen_kernel<true>", "thread": "movegen_tpb_kernel<true>"}[eng.movegen_impl]
+                        + " (moves + in-check + fp32 planes)", "kernel_ms": mv_ms,
               "achieved_gbs": 5563.4 * pb.shape[0] / (mv_ms * 1e-3) / 1e9,
               "frac_of_hbm_peak": 5563.4 * pb.shape[0] / (mv_ms * 1e-3) / 1e9 / bench.measured_peaks()[0]["hbm_gbs"]}
         del outb, pb, ps_

@@ -86,6 +86,11 @@ int xq_is_attacked_batch(xq_ctx* ctx, const int8_t* d_boards, const uint8_t* d_s
 int xq_is_attacked_batch_host(xq_ctx* ctx, const int8_t* h_boards, const uint8_t* h_sq, const int8_t* h_by,
                               int B, uint8_t* h_out);
 
+/* Which K1 kernel xq_movegen_batch[_host] launches: 0 = one warp per board (first generation), 1 = one thread per
+ * board (csrc/xq_rules_tpb.h).  Same outputs bit for bit; returns the previous value (or < 0 on a bad argument).
+ * The default can also be chosen with the environment variable XQ_MOVEGEN_IMPL=warp|thread. */
+int xq_set_movegen_impl(xq_ctx* ctx, int impl);
+
 /* overflow positions seen by movegen calls since the last reset (device counter, synchronises) */
 int xq_overflow_count(xq_ctx* ctx, int reset);
 

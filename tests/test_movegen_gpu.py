@@ -6,10 +6,13 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def eng():
+@pytest.fixture(scope="module", params=["warp", "thread"])
+def eng(request):
+    """Both K1 kernel generations (one warp per board / one thread per board) answer every test of this file."""
     import xq_native
     e = xq_native.Engine(0)
+    e.set_movegen_impl(request.param)
+    assert e.set_movegen_impl(request.param) == request.param
     yield e
     e.close()
 
@@ -69,6 +72,29 @@ def test_unorthodox_random_boards_follow_oracle(eng, oracle):
     a, n, c, p = run(eng, boards, sides, planes=True)
     assert np.array_equal(n, en) and np.array_equal(a, ea) and np.array_equal(c, ec)
     assert np.array_equal(p, ep)
+    eng.overflow_count(reset=True)
+
+
+def test_overflow_is_counted_and_lists_are_capped(eng, oracle):
+    """Rook / cannon crowds with more than 128 legal moves (no game reaches them): the first 128 moves, n = 128 and the
+    overflow counter -- never a silent truncation; the host call reports XQ_ERR_OVERFLOW."""
+    import xq_native
+    rs = np.random.RandomState(9)
+    boards = np.zeros((600, 90), np.int8)
+    sides = rs.choice(np.array([1, -1], np.int8), len(boards))
+    for i in range(len(boards)):
+        s = int(sides[i])
+        sq = rs.choice(90, rs.randint(8, 13), replace=False)
+        boards[i, sq] = rs.choice([5 * s, 6 * s], len(sq))
+        boards[i, rs.choice([3, 4, 5, 12, 13, 14, 21, 22, 23] if s == 1 else [66, 67, 68, 75, 76, 77, 84, 85, 86])] = s
+    ea, en, ec, _ = oracle.movegen_batch(boards, sides, allow_overflow=True)
+    n_over = int((en == 128).sum())            # capped rows (a count of exactly 128 is not an overflow, but none occurs here)
+    eng.overflow_count(reset=True)
+    a, n, c, _ = run(eng, boards, sides)
+    assert np.array_equal(n, en) and np.array_equal(a, ea) and np.array_equal(c, ec)
+    assert n_over > 0 and 0 < eng.overflow_count(reset=True) <= n_over
+    with pytest.raises(xq_native.XqError):
+        eng.movegen_host(boards, sides)
     eng.overflow_count(reset=True)
 
 

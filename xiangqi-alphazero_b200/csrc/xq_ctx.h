@@ -25,6 +25,7 @@ struct xq_ctx {
     void* mcts = nullptr;
     void* net = nullptr;
     void* selfplay = nullptr;
+    int movegen_impl = 0;                 // XQ_MOVEGEN_IMPL=thread|warp: K1 kernel generation (thread = one thread per board)
     bool net_pdl = false;                 // XQ_NET_PDL=1: programmatic dependent launch between layers (measured: no gain, off by default)
     bool net_fc4 = true;                  // XQ_NET_FC4=0: first-generation FC kernel
     int net_tps = 3;                      // XQ_NET_TPS=1: one tap per weight stage in the 128-channel conv

@@ -13,6 +13,7 @@
 //     coalesced float2 streaming stores, counts / in-check flags as one 64 B row per tile.
 #include "xq_ctx.h"
 #include "xq_rules.cuh"
+#include "xq_rules_tpb.h"
 #include <cstdlib>
 
 char g_xq_last_error[512] = {0};
@@ -170,6 +171,146 @@ movegen_kernel(const int8_t* __restrict__ boards, const int8_t* __restrict__ sid
     }
 }
 
+// ---- K1, second generation: one THREAD per board (rules: xq_rules_tpb.h) -----------------------------------
+// A warp takes 32 consecutive positions: their 2 880 board bytes arrive with coalesced 16-byte loads into the
+// warp's own shared-memory slice, every lane then runs the scalar generator on its board (move list built and
+// compacted in a per-lane shared-memory array), and the warp leaves the results cooperatively -- one 8-byte store
+// per lane per move list (256 B rows), the planes as bits -> float4 like the first-generation kernel, counts and
+// flags as one 32-byte row.  Warps never wait for each other: no __syncthreads after the table set-up.
+constexpr int kTpbWarps = 4;
+constexpr int kTpbThreads = kTpbWarps * 32;
+constexpr int kTpbListStride = 150;        // uint16 per lane: 300 B = 75 words (odd: equal indices fall on different banks)
+static_assert(kTpbListStride >= xqt::kListCap && (kTpbListStride & 1) == 0, "list stride");
+
+struct __align__(16) TpbWarpSmem {
+    int8_t boards[32 * kSquares];          // 2 880 B, lane l owns bytes [90 l, 90 l + 90)
+    uint16_t list[32 * kTpbListStride];    // per-lane scratch -> action ids
+    uint32_t pbits[3][kPlaneWords];        // plane bits, triple buffered: one warp sync per position
+    int8_t sides[32];
+};
+
+struct __align__(16) TpbSmem {
+    TpbWarpSmem w[kTpbWarps];
+    float4 nib_lut[16];
+};
+
+template <bool PLANES>
+__global__ void __launch_bounds__(kTpbThreads, 4)
+movegen_tpb_kernel(const int8_t* __restrict__ boards, const int8_t* __restrict__ sides, int B,
+                   int16_t* __restrict__ actions, uint8_t* __restrict__ n_moves,
+                   uint8_t* __restrict__ in_check, float* __restrict__ planes, int* __restrict__ overflow,
+                   int vec_ok)
+{
+    extern __shared__ __align__(16) unsigned char tpb_smem_raw[];
+    TpbSmem& sm = *reinterpret_cast<TpbSmem*>(tpb_smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    TpbWarpSmem& W = sm.w[warp];
+    if (PLANES && threadIdx.x < 16)
+        sm.nib_lut[threadIdx.x] = make_float4((threadIdx.x & 1) ? 1.0f : 0.0f, (threadIdx.x & 2) ? 1.0f : 0.0f,
+                                              (threadIdx.x & 4) ? 1.0f : 0.0f, (threadIdx.x & 8) ? 1.0f : 0.0f);
+    if (PLANES) {
+        for (int i = lane; i < 3 * kPlaneWords; i += 32) (&W.pbits[0][0])[i] = 0u;
+    }
+    __syncthreads();
+
+    const int n_tasks = (B + 31) >> 5;
+    for (int t = blockIdx.x * kTpbWarps + warp; t < n_tasks; t += gridDim.x * kTpbWarps) {
+        const int base = t << 5;
+        const int nb = min(32, B - base);
+        // the previous task's cooperative reads of W are complete for every lane before anything is overwritten
+        warp_sync();
+        if (vec_ok && nb == 32) {
+            const uint4* src = reinterpret_cast<const uint4*>(boards + (size_t)base * kSquares);
+            uint4* dst = reinterpret_cast<uint4*>(W.boards);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                const int k = i * 32 + lane;
+                if (k < 180) dst[k] = __ldcs(src + k);
+            }
+        } else {
+            for (int i = lane; i < nb * kSquares; i += 32) W.boards[i] = boards[(size_t)base * kSquares + i];
+        }
+        int side = 0;
+        if (lane < nb) side = sides[base + lane];
+        W.sides[lane] = (int8_t)side;
+        warp_sync();
+
+        uint16_t* list = W.list + lane * kTpbListStride;
+        if (lane < nb) {
+            int chk = 0;
+            int n = xqt::movegen(W.boards + lane * kSquares, side, list, &chk);
+            if (n > kMaxMoves) {
+                atomicAdd(overflow, 1);
+                n = kMaxMoves;
+            }
+            n_moves[base + lane] = (uint8_t)n;
+            in_check[base + lane] = (uint8_t)chk;
+            int k = n;                                   // unused slots = -1, written as 32-bit words
+            if (k & 1) list[k++] = 0xffffu;
+            uint32_t* lw = reinterpret_cast<uint32_t*>(list);
+            for (k >>= 1; k < kMaxMoves / 2; ++k) lw[k] = 0xffffffffu;
+        }
+        warp_sync();
+
+        // move lists: 128 int16 = 64 words per position, two words per lane, one coalesced 8-byte store
+        for (int j = 0; j < nb; ++j) {
+            const uint32_t* lw = reinterpret_cast<const uint32_t*>(W.list + j * kTpbListStride);
+            const uint2 v = make_uint2(lw[2 * lane], lw[2 * lane + 1]);
+            __stcs(reinterpret_cast<uint2*>(actions + (size_t)(base + j) * kMaxMoves) + lane, v);
+        }
+
+        if (PLANES) {
+            // game.py:618-640, see movegen_kernel: the 1 350 values of a position are set as bits (one shared-memory
+            // atomic per piece) and expanded 4 bits -> one float4.  Buffer j % 3 is filled here, buffer (j + 1) % 3 --
+            // last read two positions ago -- is cleared for the next position, so one warp sync per position suffices.
+            for (int j = 0; j < nb; ++j) {
+                uint32_t* bits = W.pbits[j % 3];
+                uint32_t* nxt = W.pbits[(j + 1) % 3];
+                nxt[lane] = 0u;
+                if (lane < kPlaneWords - 32) nxt[32 + lane] = 0u;
+                const int8_t* b = W.boards + j * kSquares;
+                const int sd = W.sides[j];
+                for (int sq = lane; sq < kSquares; sq += 32) {
+                    const int v = b[sq] * sd;
+                    if (v != 0) {
+                        const int e = (v > 0 ? v - 1 : 6 - v) * kSquares + sq;
+                        atomicOr(&bits[e >> 5], 1u << (e & 31));
+                    }
+                }
+                if (sd == 1 && lane < 4)
+                    atomicOr(&bits[39 + lane], lane == 0 ? 0xfffff000u : (lane == 3 ? 0x3fu : 0xffffffffu));
+                warp_sync();
+                const size_t gi = (size_t)base + j;
+                float* outp = planes + gi * (15 * kSquares);
+                const int head = (int)(gi & 1) * 2;
+                if (lane == 0) {
+                    const uint32_t two = head ? bits[0] : bits[42] >> 4;
+                    float2 v;
+                    v.x = (two & 1u) ? 1.0f : 0.0f;
+                    v.y = (two & 2u) ? 1.0f : 0.0f;
+                    __stcs(reinterpret_cast<float2*>(head ? outp : outp + 1348), v);
+                }
+                float4* out4 = reinterpret_cast<float4*>(outp + head);
+                const int e0 = head + 4 * lane;
+                const int sh = e0 & 31;
+                const uint32_t* wp = bits + (e0 >> 5);
+#pragma unroll
+                for (int it = 0; it < 11; ++it) {
+                    const int k = it * 32 + lane;
+                    if (it < 10 || k < 337) {
+                        const uint32_t nib = __funnelshift_r(wp[4 * it], wp[4 * it + 1], sh) & 15u;
+                        __stcs(out4 + k, sm.nib_lut[nib]);
+                    }
+                }
+            }
+            // leave all three buffers clear for the next task: buffer nb % 3 was cleared as "next" of the last position
+            // and never filled; the other two are cleared at the top of the positions that follow them
+            warp_sync();
+            for (int i = lane; i < 3 * kPlaneWords; i += 32) (&W.pbits[0][0])[i] = 0u;
+        }
+    }
+}
+
 // ---- is_attacked queries: one thread per query, boards staged per CTA ---------------------
 constexpr int kAtkThreads = 128;
 
@@ -283,6 +424,7 @@ extern "C" int xq_create(int device, xq_ctx** out)
     if (const char* e = getenv("XQ_NET_TPS")) c->net_tps = atoi(e);
     if (const char* e = getenv("XQ_NET_FC4")) c->net_fc4 = atoi(e) != 0;
     if (const char* e = getenv("XQ_NET_PDL")) c->net_pdl = atoi(e) != 0;
+    if (const char* e = getenv("XQ_MOVEGEN_IMPL")) c->movegen_impl = (e[0] == 't' || e[0] == '1') ? 1 : 0;
     XQ_CUDA(c, cudaSetDevice(device));
     cudaDeviceProp prop;
     XQ_CUDA(c, cudaGetDeviceProperties(&prop, device));
@@ -365,6 +507,39 @@ extern "C" int xq_movegen_batch(xq_ctx* c, const int8_t* d_boards, const int8_t*
     if (((uintptr_t)d_actions & 7) || (d_planes && ((uintptr_t)d_planes & 7)))
         return xq_fail(c, XQ_ERR_ARG, "xq_movegen_batch: actions/planes must be 8-byte aligned");
     cudaStream_t s = (cudaStream_t)stream;
+    if (c->movegen_impl == 1) {
+        // second generation: one thread per board (xq_rules_tpb.h)
+        static bool attr_set[2] = {false, false};
+        const int smem = (int)sizeof(TpbSmem);
+        if (!attr_set[0]) {
+            XQ_CUDA(c, cudaFuncSetAttribute(movegen_tpb_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            XQ_CUDA(c, cudaFuncSetAttribute(movegen_tpb_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            attr_set[0] = true;
+        }
+        int per_sm = 0;
+        if (d_planes)
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, movegen_tpb_kernel<true>, kTpbThreads, smem);
+        else
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, movegen_tpb_kernel<false>, kTpbThreads, smem);
+        if (per_sm < 1) per_sm = 1;
+        const int tasks = (B + 31) / 32;
+        const int ctas = (tasks + kTpbWarps - 1) / kTpbWarps;
+        int grid = c->sm_count * per_sm;
+        if (grid > ctas) grid = ctas;
+        const int vec_ok = ((uintptr_t)d_boards & 15) == 0;
+        {
+            XqTimer tm(c, s);
+            if (d_planes)
+                movegen_tpb_kernel<true><<<grid, kTpbThreads, smem, s>>>(d_boards, d_sides, B, d_actions, d_n_moves,
+                                                                         d_in_check, d_planes, c->d_overflow, vec_ok);
+            else
+                movegen_tpb_kernel<false><<<grid, kTpbThreads, smem, s>>>(d_boards, d_sides, B, d_actions, d_n_moves,
+                                                                          d_in_check, nullptr, c->d_overflow, vec_ok);
+        }
+        c->launches += 1;
+        XQ_CUDA(c, cudaGetLastError());
+        return XQ_OK;
+    }
     const int bulk_ok = (((uintptr_t)d_boards | (uintptr_t)d_sides) & 15) == 0;
     const int grid = movegen_grid(c, d_planes != nullptr, B);
     {
@@ -379,6 +554,14 @@ extern "C" int xq_movegen_batch(xq_ctx* c, const int8_t* d_boards, const int8_t*
     c->launches += 1;
     XQ_CUDA(c, cudaGetLastError());
     return XQ_OK;
+}
+
+extern "C" int xq_set_movegen_impl(xq_ctx* c, int impl)
+{
+    if (!c || impl < 0 || impl > 1) return xq_fail(c, XQ_ERR_ARG, "xq_set_movegen_impl: impl must be 0 (warp) or 1 (thread)");
+    const int prev = c->movegen_impl;
+    c->movegen_impl = impl;
+    return prev;
 }
 
 extern "C" int xq_overflow_count(xq_ctx* c, int reset)

@@ -65,6 +65,7 @@ def lib():
     _sig(L, "xq_is_attacked_batch", i32, vp, vp, vp, vp, i32, vp, vp)
     _sig(L, "xq_is_attacked_batch_host", i32, vp, vp, vp, vp, i32, vp)
     _sig(L, "xq_overflow_count", i32, vp, i32)
+    _sig(L, "xq_set_movegen_impl", i32, vp, i32)
     _sig(L, "xq_random_playouts", i32, vp, u64, i32, vp, vp, vp, vp, vp)
     i64, dbl = C.c_longlong, C.c_double
     _sig(L, "xq_mcts_create", i32, vp, i32, i64)
@@ -99,7 +100,7 @@ def lib():
 
 EXPORTS = ["xq_create", "xq_destroy", "xq_last_error", "xq_version", "xq_launch_count", "xq_set_timing",
            "xq_last_kernel_ms", "xq_movegen_batch", "xq_movegen_batch_host", "xq_is_attacked_batch",
-           "xq_is_attacked_batch_host", "xq_overflow_count", "xq_random_playouts",
+           "xq_is_attacked_batch_host", "xq_overflow_count", "xq_set_movegen_impl", "xq_random_playouts",
            "xq_mcts_create", "xq_mcts_set_games", "xq_mcts_root_begin", "xq_mcts_root_expand", "xq_mcts_select",
            "xq_mcts_expand_backup", "xq_mcts_leaf_info", "xq_mcts_root_visits", "xq_mcts_stats",
            "xq_net_gemm", "xq_net_value_head", "xq_net_run", "xq_selfplay_create", "xq_selfplay_reset",
@@ -156,6 +157,19 @@ class Engine:
 
     def last_kernel_ms(self) -> float:
         return float(self.L.xq_last_kernel_ms(self.h))
+
+    def set_movegen_impl(self, impl) -> str:
+        """'warp' (one warp per board) or 'thread' (one thread per board); returns the previous setting."""
+        prev = self.L.xq_set_movegen_impl(self.h, {"warp": 0, "thread": 1}[impl] if isinstance(impl, str) else int(impl))
+        if prev < 0:
+            raise XqError(self.L.xq_last_error(self.h).decode())
+        return ("warp", "thread")[prev]
+
+    @property
+    def movegen_impl(self) -> str:
+        cur = self.set_movegen_impl(0)
+        self.set_movegen_impl(cur)
+        return cur
 
     def overflow_count(self, reset=False) -> int:
         return int(self.L.xq_overflow_count(self.h, int(reset)))
