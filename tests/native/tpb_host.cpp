@@ -9,12 +9,14 @@ extern "C" int xqt_host_movegen_batch(const int8_t* boards, const int8_t* sides,
                                       uint8_t* n_moves, uint8_t* in_check)
 {
     int overflow = 0;
+    uint16_t tab[xqt::kSlotTableSize];
+    for (int i = 0; i < xqt::kSlotTableSize; ++i) tab[i] = xqt::slot_entry(i);
     for (int i = 0; i < B; ++i) {
         int8_t b[90];
         std::memcpy(b, boards + (size_t)i * 90, 90);
         uint16_t list[xqt::kListCap];
         int chk = 0;
-        int n = xqt::movegen(b, sides[i], list, &chk);
+        int n = xqt::movegen(b, sides[i], list, &chk, tab);
         if (std::memcmp(b, boards + (size_t)i * 90, 90) != 0) return -1 - i;   // the board must come back untouched
         if (n > 128) { ++overflow; n = 128; }
         for (int k = 0; k < 128; ++k) actions[(size_t)i * 128 + k] = k < n ? (int16_t)list[k] : (int16_t)-1;

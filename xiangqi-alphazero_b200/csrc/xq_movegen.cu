@@ -192,6 +192,7 @@ struct __align__(16) TpbWarpSmem {
 struct __align__(16) TpbSmem {
     TpbWarpSmem w[kTpbWarps];
     float4 nib_lut[16];
+    uint16_t slot_tab[xqt::kSlotTableSize];   // leaper table of xq_rules_tpb.h: 128 B, one word per bank
 };
 
 template <bool PLANES>
@@ -211,6 +212,7 @@ movegen_tpb_kernel(const int8_t* __restrict__ boards, const int8_t* __restrict__
     if (PLANES) {
         for (int i = lane; i < 3 * kPlaneWords; i += 32) (&W.pbits[0][0])[i] = 0u;
     }
+    if (threadIdx.x < xqt::kSlotTableSize) sm.slot_tab[threadIdx.x] = xqt::slot_entry(threadIdx.x);
     __syncthreads();
 
     const int n_tasks = (B + 31) >> 5;
@@ -228,17 +230,20 @@ movegen_tpb_kernel(const int8_t* __restrict__ boards, const int8_t* __restrict__
                 if (k < 180) dst[k] = __ldcs(src + k);
             }
         } else {
-            for (int i = lane; i < nb * kSquares; i += 32) W.boards[i] = boards[(size_t)base * kSquares + i];
+            // ragged last task / unaligned caller buffer: plain copy; lanes without a position get an empty board
+            for (int i = lane; i < 32 * kSquares; i += 32)
+                W.boards[i] = i < nb * kSquares ? boards[(size_t)base * kSquares + i] : (int8_t)0;
         }
-        int side = 0;
+        int side = 1;
         if (lane < nb) side = sides[base + lane];
         W.sides[lane] = (int8_t)side;
         warp_sync();
 
         uint16_t* list = W.list + lane * kTpbListStride;
+        int chk = 0;
+        int n = xqt::movegen(W.boards + lane * kSquares, side, list, &chk, sm.slot_tab);   // warp-synchronous: all 32 lanes
+        warp_sync();
         if (lane < nb) {
-            int chk = 0;
-            int n = xqt::movegen(W.boards + lane * kSquares, side, list, &chk);
             if (n > kMaxMoves) {
                 atomicAdd(overflow, 1);
                 n = kMaxMoves;

@@ -38,25 +38,56 @@
 #define XQT_HD inline
 #endif
 
+// Warp-uniform loops.  A loop whose trip count differs between the lanes of a warp lets the lanes drift apart for
+// good (the first version of this file ran with 9.5 of 32 lanes active: ncu, profiles/r1_movegen_ncu.md), so the two
+// long loops of movegen() run for the warp-wide MAXIMUM trip count with a predicated body and a reconvergence point
+// at the end of every iteration.  On the device all 32 lanes of a warp must therefore call movegen() together (lanes
+// without a position pass an empty board); on the host the three macros are the identity.
+#if defined(__CUDA_ARCH__)
+namespace xqt {
+static __device__ __noinline__ int warp_max_i(int v)
+{
+    __syncwarp();
+    return __reduce_max_sync(0xffffffffu, v);
+}
+}  // namespace xqt
+#define XQT_WARP_MAX(v) ::xqt::warp_max_i(v)
+#define XQT_RECONVERGE() __syncwarp()
+#else
+#define XQT_WARP_MAX(v) (v)
+#define XQT_RECONVERGE() ((void)0)
+#endif
+
 namespace xqt {
 
 constexpr int kListCap = 148;   // per-board scratch entries: 128 outputs + room for one more piece (a rook or cannon: 17 targets) + 3
 constexpr int kMaxOut = 128;
+
+XQT_HD int div9(int x) { return (x * 57) >> 9; }   // x / 9 for 0 <= x < 128
+
+XQT_HD int popc32(uint32_t v)
+{
+#if defined(__CUDA_ARCH__)
+    return __popc(v);
+#else
+    return __builtin_popcount(v);
+#endif
+}
 
 XQT_HD int ctz32(uint32_t v)
 {
 #if defined(__CUDA_ARCH__)
     return __ffs((int)v) - 1;
 #else
-    return __builtin_ctz(v);
+    return v ? __builtin_ctz(v) : -1;
 #endif
 }
-XQT_HD int top32(uint32_t v)   // index of the highest set bit (v != 0)
+XQT_HD int top32(uint32_t v)   // index of the highest set bit; -1 for 0 (like ctz32), callers select a safe index then
 {
 #if defined(__CUDA_ARCH__)
     return 31 - __clz((int)v);
 #else
-    return 31 - __builtin_clz(v);
+    return v ? 31 - __builtin_clz(v) : -1;
 #endif
 }
 
@@ -79,8 +110,11 @@ struct Scan {
     uint32_t occC[3];   // occupied squares, bit c*10+r
     uint32_t own[3];    // own pieces, bit r*9+c
     uint32_t kmask;     // own kings standing in the own palace, bit (r-r0)*3+(c-3)  (find_king order, pyx:93-98)
-    int n_ek;           // enemy knights on the board; the first two squares in ek0/ek1
-    int ek0, ek1;
+    int n_ek;           // enemy knights on the board; the first two squares in ek0/ek1 (-1: none) with their
+    int ek0, ek1;       // rows and columns (-100 when absent: no king square is a knight's move away)
+    int ek0r, ek0c, ek1r, ek1c;
+    uint32_t prow[3];   // occupancy of the three rows (bit c) and
+    uint32_t pcol[3];   // of the three columns (bit r) of the own palace: the only lines a king's attack test looks along
 };
 
 XQT_HD Scan scan_board(const int8_t* b, int side)
@@ -92,6 +126,7 @@ XQT_HD Scan scan_board(const int8_t* b, int side)
     s.kmask = 0u;
     s.n_ek = 0;
     s.ek0 = s.ek1 = -1;
+    s.ek0r = s.ek0c = s.ek1r = s.ek1c = -100;
     const int r0 = side == 1 ? 0 : 7;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -110,74 +145,91 @@ XQT_HD Scan scan_board(const int8_t* b, int side)
             if (pr >= 0 && pr <= 2 && p == side) s.kmask |= 1u << (pr * 3 + (c - 3));
         }
         if (p == -4 * side) {
-            if (s.n_ek == 0) s.ek0 = sq;
-            else if (s.n_ek == 1) s.ek1 = sq;
+            if (s.n_ek == 0) { s.ek0 = sq; s.ek0r = r; s.ek0c = c; }
+            else if (s.n_ek == 1) { s.ek1 = sq; s.ek1r = r; s.ek1c = c; }
             ++s.n_ek;
         }
+    }
+    // every start below is a compile-time constant: a shift and a mask each
+    for (int i = 0; i < 3; ++i) {
+        const uint32_t red = bits96(s.occR[0], s.occR[1], s.occR[2], i * 9, 9);
+        const uint32_t black = bits96(s.occR[0], s.occR[1], s.occR[2], (7 + i) * 9, 9);
+        s.prow[i] = side == 1 ? red : black;
+        s.pcol[i] = bits96(s.occC[0], s.occC[1], s.occC[2], (3 + i) * 10, 10);
     }
     return s;
 }
 
-// pyx:104-189 on the board as it stands in b[] (a move, if any, already made in place); the row / column occupancy
-// of the un-moved board is corrected for the move (fr, fc) -> (tr, tc) (fr < 0: no move).  `cap` is the square a
-// captured piece stood on (an enemy knight there no longer attacks), -1 for none.
-XQT_HD bool attacked(const int8_t* b, const Scan& s, int kr, int kc, int by, int fr, int fc, int tr, int tc, int cap)
+// pyx:104-189 for a KING square, given as palace coordinates (pr, pc) of the attacked side's palace (row r0 + pr,
+// column 3 + pc; a king is only ever "found" there, pyx:78-101) -- the cell holds a piece of the attacked side, which is what lets absent
+// blockers read that cell as a harmless stand-in -- on the board as it stands in b[] (a move, if any, already made in
+// place); the row / column occupancy of the un-moved board is corrected for the move (fr, fc) -> (tr, tc) (fr < 0: no
+// move).  `cap` is the square a captured piece stood on (an enemy knight there no longer attacks), -1 for none.
+// Straight-line code: a warp executes the union of its lanes' paths anyway, so early exits would only split it; the
+// 13 cell reads are independent and overlap.
+XQT_HD bool attacked(const int8_t* b, const Scan& s, int r0, int pr, int pc, int by, int fr, int fc, int tr, int tc, int cap)
 {
-    const int rook = 5 * by, cannon = 6 * by, horse = 4 * by, pawn = 7 * by, king = by;
-    uint32_t R = bits96(s.occR[0], s.occR[1], s.occR[2], kr * 9, 9);
-    uint32_t C = bits96(s.occC[0], s.occC[1], s.occC[2], kc * 10, 10);
+    const int rook = 5 * by, cannon = 6 * by, pawn = 7 * by, king = by;
+    const int kr = r0 + pr, kc = 3 + pc;
+    uint32_t R = pr == 0 ? s.prow[0] : (pr == 1 ? s.prow[1] : s.prow[2]);
+    uint32_t C = pc == 0 ? s.pcol[0] : (pc == 1 ? s.pcol[1] : s.pcol[2]);
     if (fr >= 0) {
-        if (fr == kr) R &= ~(1u << fc);
-        if (fc == kc) C &= ~(1u << fr);
-        if (tr == kr) R |= 1u << tc;
-        if (tc == kc) C |= 1u << tr;
+        R &= ~((fr == kr ? 1u : 0u) << fc);
+        C &= ~((fc == kc ? 1u : 0u) << fr);
+        R |= (tr == kr ? 1u : 0u) << tc;
+        C |= (tc == kc ? 1u : 0u) << tr;
     }
+    const int ksq = kr * 9 + kc;
     const int8_t* row = b + kr * 9;
-    uint32_t m = R & ((1u << kc) - 1u);                       // towards column 0: nearest = highest bit
-    if (m) {
-        const int c1 = top32(m);
-        const int p1 = row[c1];
-        if (p1 == rook || p1 == king) return true;
-        m ^= 1u << c1;
-        if (m && row[top32(m)] == cannon) return true;
+    const int8_t* col = b + kc;
+    bool hit = false;
+    {   // towards column 0: nearest piece = highest bit below kc, the one behind it = next highest
+        const uint32_t m = R & ((1u << kc) - 1u);
+        const int i1 = m ? top32(m) : kc;
+        const int p1 = row[i1];
+        const uint32_t m2 = m & ~(1u << i1);
+        const int i2 = m2 ? top32(m2) : kc;
+        hit |= (p1 == rook) | (p1 == king) | (row[i2] == cannon);
     }
-    m = R >> (kc + 1);                                        // towards column 8: nearest = lowest bit
-    if (m) {
-        const int p1 = row[kc + 1 + ctz32(m)];
-        if (p1 == rook || p1 == king) return true;
-        m &= m - 1u;
-        if (m && row[kc + 1 + ctz32(m)] == cannon) return true;
+    {   // towards column 8
+        const uint32_t m = R >> (kc + 1);
+        const int i1 = m ? kc + 1 + ctz32(m) : kc;
+        const int p1 = row[i1];
+        const uint32_t m2 = m & (m - 1u);
+        const int i2 = m2 ? kc + 1 + ctz32(m2) : kc;
+        hit |= (p1 == rook) | (p1 == king) | (row[i2] == cannon);
     }
-    m = C & ((1u << kr) - 1u);                                // towards row 0
-    if (m) {
-        const int r1 = top32(m);
-        const int p1 = b[r1 * 9 + kc];
-        if (p1 == rook || p1 == king) return true;
-        m ^= 1u << r1;
-        if (m && b[top32(m) * 9 + kc] == cannon) return true;
+    {   // towards row 0
+        const uint32_t m = C & ((1u << kr) - 1u);
+        const int i1 = m ? top32(m) : kr;
+        const int p1 = col[i1 * 9];
+        const uint32_t m2 = m & ~(1u << i1);
+        const int i2 = m2 ? top32(m2) : kr;
+        hit |= (p1 == rook) | (p1 == king) | (col[i2 * 9] == cannon);
     }
-    m = C >> (kr + 1);                                        // towards row 9
-    if (m) {
-        const int p1 = b[(kr + 1 + ctz32(m)) * 9 + kc];
-        if (p1 == rook || p1 == king) return true;
-        m &= m - 1u;
-        if (m && b[(kr + 1 + ctz32(m)) * 9 + kc] == cannon) return true;
+    {   // towards row 9
+        const uint32_t m = C >> (kr + 1);
+        const int i1 = m ? kr + 1 + ctz32(m) : kr;
+        const int p1 = col[i1 * 9];
+        const uint32_t m2 = m & (m - 1u);
+        const int i2 = m2 ? kr + 1 + ctz32(m2) : kr;
+        hit |= (p1 == rook) | (p1 == king) | (col[i2 * 9] == cannon);
     }
     // knights (pyx:156-169): the leg is the cell next to the knight on its long axis
     if (s.n_ek <= 2) {
-        for (int j = 0; j < s.n_ek; ++j) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int j = 0; j < 2; ++j) {
             const int nsq = j == 0 ? s.ek0 : s.ek1;
-            if (nsq == cap) continue;
-            const int nr = nsq / 9, nc = nsq - nr * 9;
-            const int dr = kr - nr, dc = kc - nc;
+            const int dr = kr - (j == 0 ? s.ek0r : s.ek1r), dc = kc - (j == 0 ? s.ek0c : s.ek1c);
             const int adr = dr < 0 ? -dr : dr, adc = dc < 0 ? -dc : dc;
-            int leg;
-            if (adr == 2 && adc == 1) leg = nsq + (dr / 2) * 9;
-            else if (adr == 1 && adc == 2) leg = nsq + dc / 2;
-            else continue;
-            if (b[leg] == 0) return true;
+            const bool geo = (adr * adc == 2) & (adr + adc == 3) & (nsq != cap);       // (1,2) or (2,1), still on the board
+            const int leg = nsq + (adr == 2 ? (dr > 0 ? 9 : -9) : (dc > 0 ? 1 : -1));
+            hit |= geo & (b[geo ? leg : ksq] == 0);
         }
     } else {
+        const int horse = 4 * by;
         for (int i = 0; i < 8; ++i) {                          // boards no game reaches: look at the 8 origins
             const int jr = (i < 4) ? ((i < 2) ? -2 : 2) : ((i < 6) ? -1 : 1);
             const int jc = (i < 4) ? ((i & 1) ? 1 : -1) : ((i & 1) ? 2 : -2);
@@ -186,72 +238,90 @@ XQT_HD bool attacked(const int8_t* b, const Scan& s, int kr, int kc, int by, int
             if (b[nr * 9 + nc] != horse) continue;
             int lr = nr, lc = nc;
             if (jr == 2 || jr == -2) lr = nr - jr / 2; else lc = nc - jc / 2;
-            if (b[lr * 9 + lc] == 0) return true;
+            if (b[lr * 9 + lc] == 0) hit = true;
         }
     }
     // pawns (pyx:172-187): from behind, and from the side once the target row is across the river for that colour
-    if (by == 1) {
-        if (kr >= 1 && row[kc - 9] == pawn) return true;
-        if (kr >= 5) {
-            if (kc >= 1 && row[kc - 1] == pawn) return true;
-            if (kc <= 7 && row[kc + 1] == pawn) return true;
-        }
-    } else {
-        if (kr <= 8 && row[kc + 9] == pawn) return true;
-        if (kr <= 4) {
-            if (kc >= 1 && row[kc - 1] == pawn) return true;
-            if (kc <= 7 && row[kc + 1] == pawn) return true;
-        }
+    {
+        const bool back_ok = by == 1 ? kr >= 1 : kr <= 8;
+        const bool side_ok = by == 1 ? kr >= 5 : kr <= 4;
+        const bool l_ok = side_ok & (kc >= 1), r_ok = side_ok & (kc <= 7);
+        hit |= (b[back_ok ? ksq - 9 * by : ksq] == pawn) | (b[l_ok ? ksq - 1 : ksq] == pawn) | (b[r_ok ? ksq + 1 : ksq] == pawn);
     }
-    return false;
+    return hit;
 }
 
-// leaper slot words: slot i in bits 8i..8i+7 = (dr+2) | (dc+2) << 3 | 0x40 (valid).  Orders: pyx:287-367, 434-484.
-#define XQT_SLOT(dr, dc) ((uint64_t)(((dr) + 2) | (((dc) + 2) << 3) | 0x40))
-#define XQT_SLOTS4(a, b, c, d) ((a) | ((b) << 8) | ((c) << 16) | ((d) << 24))
-constexpr uint64_t kSlotsKing = XQT_SLOTS4(XQT_SLOT(-1, 0), XQT_SLOT(1, 0), XQT_SLOT(0, -1), XQT_SLOT(0, 1));
-constexpr uint64_t kSlotsAdvisor = XQT_SLOTS4(XQT_SLOT(-1, -1), XQT_SLOT(-1, 1), XQT_SLOT(1, -1), XQT_SLOT(1, 1));
-constexpr uint64_t kSlotsElephant = XQT_SLOTS4(XQT_SLOT(-2, -2), XQT_SLOT(-2, 2), XQT_SLOT(2, -2), XQT_SLOT(2, 2));
-constexpr uint64_t kSlotsKnight = XQT_SLOTS4(XQT_SLOT(-2, -1), XQT_SLOT(-2, 1), XQT_SLOT(2, -1), XQT_SLOT(2, 1)) |
-                                  (XQT_SLOTS4(XQT_SLOT(-1, -2), XQT_SLOT(-1, 2), XQT_SLOT(1, -2), XQT_SLOT(1, 2)) << 32);
-constexpr uint64_t kSlotsPawnRed = XQT_SLOT(1, 0) | (XQT_SLOT(0, -1) << 8) | (XQT_SLOT(0, 1) << 16);
-constexpr uint64_t kSlotsPawnBlack = XQT_SLOT(-1, 0) | (XQT_SLOT(0, -1) << 8) | (XQT_SLOT(0, 1) << 16);
+// Leaper table (pyx:287-367, 434-484 orders): 8 rows x 8 slots of 16 bits, row = piece kind (1 king, 2 advisor,
+// 3 elephant, 4 knight, 7 red pawn; row 0 = black pawn), entry = dr+2 | (dc+2) << 3 | valid << 6 | has_leg << 7 |
+// (leg offset + 10) << 8.  128 bytes = one 32-bit word per shared-memory bank: lanes looking up different kinds never
+// conflict.  The kernel fills its copy with slot_entry(); the host build uses a static array.
+constexpr int kSlotTableSize = 64;
+XQT_HD uint16_t slot_entry(int idx)
+{
+    const int row = idx >> 3, sl = idx & 7;
+    int dr = 0, dc = 0, leg = 0;
+    bool valid = false, has_leg = false;
+    if (row == 1 && sl < 4) {                       // king: up, down, left, right
+        dr = sl == 0 ? -1 : (sl == 1 ? 1 : 0);
+        dc = sl == 2 ? -1 : (sl == 3 ? 1 : 0);
+        valid = true;
+    } else if ((row == 2 || row == 3) && sl < 4) {  // advisor / elephant: (-,-) (-,+) (+,-) (+,+)
+        const int k = row == 2 ? 1 : 2;
+        dr = sl < 2 ? -k : k;
+        dc = (sl & 1) ? k : -k;
+        valid = true;
+        if (row == 3) {
+            has_leg = true;
+            leg = (dr / 2) * 9 + dc / 2;
+        }
+    } else if (row == 4) {                          // knight (pyx:31-39)
+        dr = sl < 4 ? (sl < 2 ? -2 : 2) : (sl < 6 ? -1 : 1);
+        dc = sl < 4 ? ((sl & 1) ? 1 : -1) : ((sl & 1) ? 2 : -2);
+        valid = has_leg = true;
+        leg = sl < 4 ? (dr / 2) * 9 : dc / 2;
+    } else if ((row == 7 || row == 0) && sl < 3) {  // pawn: forward, left, right
+        dr = sl == 0 ? (row == 7 ? 1 : -1) : 0;
+        dc = sl == 1 ? -1 : (sl == 2 ? 1 : 0);
+        valid = true;
+    }
+    return (uint16_t)((dr + 2) | (dc + 2) << 3 | (valid ? 0x40 : 0) | (has_leg ? 0x80 : 0) | (leg + 10) << 8);
+}
 
 // Pseudo-legal targets of the piece on `from` appended to list[m...] as from << 7 | to; returns the new m.
-XQT_HD int gen_piece(const int8_t* b, const Scan& s, int side, int from, uint16_t* list, int m)
+// Two sections (sliders / leapers), each straight-line with predicated stores: the lanes of a warp that are in the same
+// section stay together.
+XQT_HD int gen_piece(const int8_t* b, const Scan& s, int side, int from, uint16_t* list, int m, const uint16_t* tab)
 {
     const int p = b[from];
     const int kind = p < 0 ? -p : p;
-    const int r = from / 9, c = from - r * 9;
+    const int r = div9(from), c = from - r * 9;
     if (kind == 5 || kind == 6) {
         const uint32_t Rm = bits96(s.occR[0], s.occR[1], s.occR[2], r * 9, 9);
         const uint32_t Cm = bits96(s.occC[0], s.occC[1], s.occC[2], c * 10, 10);
         // pyx:42-46 order: up (row - 1), down (row + 1), left (col - 1), right (col + 1)
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
         for (int d = 0; d < 4; ++d) {
             const bool vertical = d < 2, neg = (d & 1) == 0;
             const uint32_t line = vertical ? Cm : Rm;
             const int pos = vertical ? r : c;
             const int len = vertical ? 10 : 9;
             const int step = vertical ? 9 : 1;
-            int n_empty, first = -1, second = -1;
+            int n_empty, first, second;
             if (neg) {
-                uint32_t q = line & ((1u << pos) - 1u);
-                n_empty = pos;
-                if (q) {
-                    first = top32(q);
-                    n_empty = pos - 1 - first;
-                    q ^= 1u << first;
-                    if (q) second = top32(q);
-                }
+                const uint32_t q = line & ((1u << pos) - 1u);
+                first = top32(q);                               // -1: open to the edge
+                n_empty = pos - 1 - first;
+                const uint32_t q2 = q & ~(1u << (first & 31));
+                second = q ? top32(q2) : -1;
             } else {
-                uint32_t q = line >> (pos + 1);
-                n_empty = len - 1 - pos;
-                if (q) {
-                    first = pos + 1 + ctz32(q);
-                    n_empty = first - pos - 1;
-                    q &= q - 1u;
-                    if (q) second = pos + 1 + ctz32(q);
-                }
+                const uint32_t q = line >> (pos + 1);
+                const int z = ctz32(q);
+                first = q ? pos + 1 + z : -1;
+                n_empty = q ? z : len - 1 - pos;
+                const uint32_t q2 = q & (q - 1u);
+                second = q2 ? pos + 1 + ctz32(q2) : -1;
             }
             const int sgn = neg ? -step : step;
             int to = from;
@@ -260,44 +330,36 @@ XQT_HD int gen_piece(const int8_t* b, const Scan& s, int side, int from, uint16_
                 list[m++] = (uint16_t)(from << 7 | to);
             }
             const int hit = kind == 5 ? first : second;       // rook takes the first piece on the ray, cannon the second
-            if (hit >= 0) {
-                const int tsq = from + (hit - pos) * step;
-                if (b[tsq] * side < 0) list[m++] = (uint16_t)(from << 7 | tsq);
-            }
+            const int tsq = from + (hit - pos) * step;
+            if (hit >= 0 && b[tsq] * side < 0) list[m++] = (uint16_t)(from << 7 | tsq);
         }
-        return m;
-    }
-    uint64_t slots;
-    int rlo = 0, rhi = 9, clo = 0, chi = 8;
-    if (kind == 1 || kind == 2) {                              // palace box (the advisor test of pyx:307-326 is the box too)
-        slots = kind == 1 ? kSlotsKing : kSlotsAdvisor;
-        rlo = side == 1 ? 0 : 7;
-        rhi = rlo + 2;
-        clo = 3;
-        chi = 5;
-    } else if (kind == 3) {                                    // own half of the board
-        slots = kSlotsElephant;
-        rlo = side == 1 ? 0 : 5;
-        rhi = rlo + 4;
-    } else if (kind == 4) {
-        slots = kSlotsKnight;
-    } else if (kind == 7) {
-        slots = side == 1 ? kSlotsPawnRed : kSlotsPawnBlack;
+    } else if (kind == 1 || kind == 2 || kind == 3 || kind == 4 || kind == 7) {
+        // target box: palace for king and advisor (the advisor test of pyx:307-326 is the box too), own half for the
+        // elephant, the board for knight and pawn
+        const bool palace = kind <= 2;
+        const int rlo = palace ? (side == 1 ? 0 : 7) : (kind == 3 && side != 1 ? 5 : 0);
+        const int rhi = palace ? rlo + 2 : (kind == 3 && side == 1 ? 4 : 9);
+        const int clo = palace ? 3 : 0, chi = palace ? 5 : 8;
         const bool crossed = side == 1 ? r >= 5 : r <= 4;
-        if (!crossed) slots &= 0xffu;
-    } else {
-        return m;
-    }
-    for (; slots; slots >>= 8) {
-        const int e = (int)(slots & 0xffu);
-        const int dr = (e & 7) - 2, dc = ((e >> 3) & 7) - 2;
-        const int nr = r + dr, nc = c + dc;
-        if (nr < rlo || nr > rhi || nc < clo || nc > chi) continue;
-        if (dr == 2 || dr == -2 || dc == 2 || dc == -2)
-            if (b[from + (dr / 2) * 9 + dc / 2] != 0) continue;          // elephant eye / horse leg
-        const int to = nr * 9 + nc;
-        if (b[to] * side > 0) continue;
-        list[m++] = (uint16_t)(from << 7 | to);
+        const int nsl = (kind == 7 && !crossed) ? 1 : 8;
+        const uint16_t* row = tab + ((kind == 7 && side != 1) ? 0 : kind) * 8;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int sl = 0; sl < 8; ++sl) {
+            const int e = row[sl];
+            const int dr = (e & 7) - 2, dc = ((e >> 3) & 7) - 2;
+            const int nr = r + dr, nc = c + dc;
+            bool ok = ((e & 0x40) != 0) & (sl < nsl) & (nr >= rlo) & (nr <= rhi) & (nc >= clo) & (nc <= chi);
+            const int legoff = ((e >> 8) & 31) - 10;
+            const int to = from + dr * 9 + dc;
+            const int legv = b[ok ? from + legoff : from];     // elephant eye / horse leg (no leg: the own piece, ignored)
+            const int tgt = b[ok ? to : from];
+            ok &= ((e & 0x80) == 0) | (legv == 0);
+            ok &= !(tgt * side > 0);
+            if (ok) list[m] = (uint16_t)(from << 7 | to);
+            m += ok ? 1 : 0;
+        }
     }
     return m;
 }
@@ -305,54 +367,66 @@ XQT_HD int gen_piece(const int8_t* b, const Scan& s, int side, int from, uint16_
 // Ordered legal moves of `side` on b[] (mutated during the call, restored on return).  list must hold kListCap
 // entries; on return list[0 .. min(n, 128)) are action ids from*90+to.  Returns n, or 129 when the position has more
 // than 128 legal moves (no game reaches that; the caller counts it as an overflow).  *in_check = cy_is_in_check.
-XQT_HD int movegen(int8_t* b, int side, uint16_t* list, int* in_check)
+// Device: warp-synchronous -- every lane of the warp calls it (see XQT_WARP_MAX above).
+XQT_HD int movegen(int8_t* b, int side, uint16_t* list, int* in_check, const uint16_t* tab)
 {
     const Scan s = scan_board(b, side);
     const int r0 = side == 1 ? 0 : 7;
-    if (s.kmask) {
-        const int ki = ctz32(s.kmask);
+    {
+        const int ki = s.kmask ? ctz32(s.kmask) : 0;
         const int kdiv = (ki * 11) >> 5;           // ki / 3 for ki < 9
-        *in_check = attacked(b, s, r0 + kdiv, 3 + ki - kdiv * 3, -side, -1, 0, 0, 0, -1) ? 1 : 0;
-    } else {
-        *in_check = 1;                             // pyx:552-554: no king in the palace counts as check
+        const bool a = attacked(b, s, r0, kdiv, ki - kdiv * 3, -side, -1, 0, 0, 0, -1);
+        *in_check = (s.kmask == 0u || a) ? 1 : 0;  // pyx:552-554: no king in the palace counts as check
     }
     int n = 0;                                     // legal moves so far = list[0..n)
     uint32_t w0 = s.own[0], w1 = s.own[1], w2 = s.own[2];
-    while ((w0 | w1 | w2) != 0u) {
+    for (;;) {
+        const int left = popc32(w0) + popc32(w1) + popc32(w2);
+        const int ptrips = XQT_WARP_MAX(left);
+        if (ptrips == 0) break;
         int m = n;
-        while ((w0 | w1 | w2) != 0u && m + 17 <= kListCap) {
-            int from;
-            if (w0) { from = ctz32(w0); w0 &= w0 - 1u; }
-            else if (w1) { from = 32 + ctz32(w1); w1 &= w1 - 1u; }
-            else { from = 64 + ctz32(w2); w2 &= w2 - 1u; }
-            m = gen_piece(b, s, side, from, list, m);
+        for (int t = 0; t < ptrips; ++t) {
+            if ((w0 | w1 | w2) != 0u && m + 17 <= kListCap) {
+                int from;
+                if (w0) { from = ctz32(w0); w0 &= w0 - 1u; }
+                else if (w1) { from = 32 + ctz32(w1); w1 &= w1 - 1u; }
+                else { from = 64 + ctz32(w2); w2 &= w2 - 1u; }
+                m = gen_piece(b, s, side, from, list, m, tab);
+            }
+            XQT_RECONVERGE();
         }
-        for (int i = n; i < m; ++i) {
-            const int mv = list[i];
-            const int from = mv >> 7, to = mv & 127;
-            const int fr = from / 9, fc = from - fr * 9, tr = to / 9, tc = to - tr * 9;
-            const int8_t mover = b[from], taken = b[to];
-            b[to] = mover;
-            b[from] = 0;
-            uint32_t km = s.kmask;
-            if (mover == side) {                   // a king move (targets are always inside the palace box)
-                const int pr = fr - r0;
-                if (pr >= 0 && pr <= 2 && fc >= 3 && fc <= 5) km &= ~(1u << (pr * 3 + fc - 3));
-                km |= 1u << ((tr - r0) * 3 + tc - 3);
-            }
-            bool ok = false;
-            if (km) {
-                const int ki = ctz32(km);
+        const int ltrips = XQT_WARP_MAX(m - n);
+        int i = n;
+        for (int t = 0; t < ltrips; ++t) {
+            if (i < m) {
+                const int mv = list[i++];
+                const int from = mv >> 7, to = mv & 127;
+                const int fr = div9(from), fc = from - fr * 9, tr = div9(to), tc = to - tr * 9;
+                const int8_t mover = b[from], taken = b[to];
+                b[to] = mover;
+                b[from] = 0;
+                uint32_t km = s.kmask;
+                if (mover == side) {               // a king move (targets are always inside the palace box)
+                    const int pr = fr - r0;
+                    if (pr >= 0 && pr <= 2 && fc >= 3 && fc <= 5) km &= ~(1u << (pr * 3 + fc - 3));
+                    km |= 1u << ((tr - r0) * 3 + tc - 3);
+                }
+                const int ki = km ? ctz32(km) : 0;
                 const int kdiv = (ki * 11) >> 5;
-                ok = !attacked(b, s, r0 + kdiv, 3 + ki - kdiv * 3, -side, fr, fc, tr, tc, taken != 0 ? to : -1);
+                // km == 0 (no own king in the palace): the probe square may hold anything, its result is discarded
+                const bool ok = !attacked(b, s, r0, kdiv, ki - kdiv * 3, -side, fr, fc, tr, tc, taken != 0 ? to : -1)
+                                && km != 0u;
+                b[from] = mover;
+                b[to] = taken;
+                if (ok) {
+                    if (n < kMaxOut) list[n] = (uint16_t)(from * 90 + to);
+                    if (++n > kMaxOut) {           // overflow: stop this board (the warp-uniform loops run on, idle)
+                        i = m;
+                        w0 = w1 = w2 = 0u;
+                    }
+                }
             }
-            b[from] = mover;
-            b[to] = taken;
-            if (ok) {
-                if (n < kMaxOut) list[n] = (uint16_t)(from * 90 + to);
-                ++n;
-                if (n > kMaxOut) return kMaxOut + 1;
-            }
+            XQT_RECONVERGE();
         }
     }
     return n;
