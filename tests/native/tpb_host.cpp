@@ -15,11 +15,12 @@ extern "C" int xqt_host_movegen_batch(const int8_t* boards, const int8_t* sides,
         int8_t b[90];
         std::memcpy(b, boards + (size_t)i * 90, 90);
         uint16_t list[xqt::kListCap];
+        int16_t out[128];
         int chk = 0;
-        int n = xqt::movegen(b, sides[i], list, &chk, tab);
+        int n = xqt::movegen(b, sides[i], list, out, &chk, tab);
         if (std::memcmp(b, boards + (size_t)i * 90, 90) != 0) return -1 - i;   // the board must come back untouched
         if (n > 128) { ++overflow; n = 128; }
-        for (int k = 0; k < 128; ++k) actions[(size_t)i * 128 + k] = k < n ? (int16_t)list[k] : (int16_t)-1;
+        for (int k = 0; k < 128; ++k) actions[(size_t)i * 128 + k] = k < n ? out[k] : (int16_t)-1;
         n_moves[i] = (uint8_t)n;
         in_check[i] = (uint8_t)chk;
     }

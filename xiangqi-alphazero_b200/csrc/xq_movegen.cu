@@ -179,12 +179,12 @@ movegen_kernel(const int8_t* __restrict__ boards, const int8_t* __restrict__ sid
 // flags as one 32-byte row.  Warps never wait for each other: no __syncthreads after the table set-up.
 constexpr int kTpbWarps = 4;
 constexpr int kTpbThreads = kTpbWarps * 32;
-constexpr int kTpbListStride = 150;        // uint16 per lane: 300 B = 75 words (odd: equal indices fall on different banks)
-static_assert(kTpbListStride >= xqt::kListCap && (kTpbListStride & 1) == 0, "list stride");
+constexpr int kTpbListStride = 106;        // uint16 per lane: 212 B = 53 words (odd: equal indices fall on different banks)
+static_assert(kTpbListStride >= xqt::kListCap && (kTpbListStride & 1) == 0 && ((kTpbListStride / 2) & 1) == 1, "list stride");
 
 struct __align__(16) TpbWarpSmem {
     int8_t boards[32 * kSquares];          // 2 880 B, lane l owns bytes [90 l, 90 l + 90)
-    uint16_t list[32 * kTpbListStride];    // per-lane scratch -> action ids
+    uint16_t list[32 * kTpbListStride];    // per-lane pseudo-legal scratch
     uint32_t pbits[3][kPlaneWords];        // plane bits, triple buffered: one warp sync per position
     int8_t sides[32];
 };
@@ -196,7 +196,7 @@ struct __align__(16) TpbSmem {
 };
 
 template <bool PLANES>
-__global__ void __launch_bounds__(kTpbThreads, 4)
+__global__ void __launch_bounds__(kTpbThreads, 5)
 movegen_tpb_kernel(const int8_t* __restrict__ boards, const int8_t* __restrict__ sides, int B,
                    int16_t* __restrict__ actions, uint8_t* __restrict__ n_moves,
                    uint8_t* __restrict__ in_check, float* __restrict__ planes, int* __restrict__ overflow,
@@ -239,9 +239,16 @@ movegen_tpb_kernel(const int8_t* __restrict__ boards, const int8_t* __restrict__
         W.sides[lane] = (int8_t)side;
         warp_sync();
 
+        // move-list rows: filled with -1 by the whole warp (one 8-byte store per lane and row), then every lane writes
+        // its position's legal moves straight into its row as it finds them (2-byte stores that merge in L2 with the
+        // fill; the warp sync orders the two)
+        for (int j = 0; j < nb; ++j)
+            reinterpret_cast<uint2*>(actions + (size_t)(base + j) * kMaxMoves)[lane] = make_uint2(0xffffffffu, 0xffffffffu);
+        warp_sync();
         uint16_t* list = W.list + lane * kTpbListStride;
         int chk = 0;
-        int n = xqt::movegen(W.boards + lane * kSquares, side, list, &chk, sm.slot_tab);   // warp-synchronous: all 32 lanes
+        int16_t* out_row = actions + (size_t)(base + (lane < nb ? lane : 0)) * kMaxMoves;   // idle lanes find no move
+        int n = xqt::movegen(W.boards + lane * kSquares, side, list, out_row, &chk, sm.slot_tab);   // warp-synchronous: all 32 lanes
         warp_sync();
         if (lane < nb) {
             if (n > kMaxMoves) {
@@ -250,18 +257,6 @@ movegen_tpb_kernel(const int8_t* __restrict__ boards, const int8_t* __restrict__
             }
             n_moves[base + lane] = (uint8_t)n;
             in_check[base + lane] = (uint8_t)chk;
-            int k = n;                                   // unused slots = -1, written as 32-bit words
-            if (k & 1) list[k++] = 0xffffu;
-            uint32_t* lw = reinterpret_cast<uint32_t*>(list);
-            for (k >>= 1; k < kMaxMoves / 2; ++k) lw[k] = 0xffffffffu;
-        }
-        warp_sync();
-
-        // move lists: 128 int16 = 64 words per position, two words per lane, one coalesced 8-byte store
-        for (int j = 0; j < nb; ++j) {
-            const uint32_t* lw = reinterpret_cast<const uint32_t*>(W.list + j * kTpbListStride);
-            const uint2 v = make_uint2(lw[2 * lane], lw[2 * lane + 1]);
-            __stcs(reinterpret_cast<uint2*>(actions + (size_t)(base + j) * kMaxMoves) + lane, v);
         }
 
         if (PLANES) {

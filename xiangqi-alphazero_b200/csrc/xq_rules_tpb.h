@@ -60,7 +60,7 @@ static __device__ __noinline__ int warp_max_i(int v)
 
 namespace xqt {
 
-constexpr int kListCap = 148;   // per-board scratch entries: 128 outputs + room for one more piece (a rook or cannon: 17 targets) + 3
+constexpr int kListCap = 104;   // pseudo-legal scratch entries per board and round (a piece adds at most 17; orthodox maximum seen: 75)
 constexpr int kMaxOut = 128;
 
 XQT_HD int div9(int x) { return (x * 57) >> 9; }   // x / 9 for 0 <= x < 128
@@ -121,42 +121,57 @@ XQT_HD Scan scan_board(const int8_t* b, int side)
 {
     Scan s;
     s.occR[0] = s.occR[1] = s.occR[2] = 0u;
-    s.occC[0] = s.occC[1] = s.occC[2] = 0u;
     s.own[0] = s.own[1] = s.own[2] = 0u;
+    s.prow[0] = s.prow[1] = s.prow[2] = 0u;
     s.kmask = 0u;
     s.n_ek = 0;
     s.ek0 = s.ek1 = -1;
     s.ek0r = s.ek0c = s.ek1r = s.ek1c = -100;
     const int r0 = side == 1 ? 0 : 7;
+    uint32_t colm[9] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};   // column occupancy, bit r (compile-time column index)
+    // one row per iteration, NOT unrolled across rows: the fully unrolled 90-cell scan was 1 400 instructions and the
+    // kernel stalled on instruction fetch (ncu: 69 % of this section's samples)
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int r = 0; r < 10; ++r) {
+        const int8_t* rowp = b + r * 9;
+        uint32_t rm = 0u, om = 0u, kings = 0u;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (int sq = 0; sq < 90; ++sq) {
-        const int r = sq / 9, c = sq % 9;          // compile-time after unrolling
-        const int p = b[sq];
-        const uint32_t nz = p != 0 ? 1u : 0u;
-        const uint32_t mine = (p * side > 0) ? 1u : 0u;
-        s.occR[sq >> 5] |= nz << (sq & 31);
-        const int cq = c * 10 + r;
-        s.occC[cq >> 5] |= nz << (cq & 31);
-        s.own[sq >> 5] |= mine << (sq & 31);
-        if (c >= 3 && c <= 5) {                    // palace columns; the row test depends on the side
-            const int pr = r - r0;
-            if (pr >= 0 && pr <= 2 && p == side) s.kmask |= 1u << (pr * 3 + (c - 3));
+        for (int c = 0; c < 9; ++c) {
+            const int p = rowp[c];
+            const uint32_t nz = p != 0 ? 1u : 0u;
+            rm |= nz << c;
+            om |= ((p * side > 0) ? 1u : 0u) << c;
+            colm[c] |= nz << r;
+            if (c >= 3 && c <= 5) kings |= (p == side ? 1u : 0u) << (c - 3);
+            if (p == -4 * side) {
+                if (s.n_ek == 0) { s.ek0 = r * 9 + c; s.ek0r = r; s.ek0c = c; }
+                else if (s.n_ek == 1) { s.ek1 = r * 9 + c; s.ek1r = r; s.ek1c = c; }
+                ++s.n_ek;
+            }
         }
-        if (p == -4 * side) {
-            if (s.n_ek == 0) { s.ek0 = sq; s.ek0r = r; s.ek0c = c; }
-            else if (s.n_ek == 1) { s.ek1 = sq; s.ek1r = r; s.ek1c = c; }
-            ++s.n_ek;
+        // insert the 9 row bits at bit r*9 of the 96-bit sets
+        const int at = r * 9, w = at >> 5, sh = at & 31;
+        const uint32_t rlo = rm << sh, rhi = sh > 23 ? rm >> (32 - sh) : 0u;
+        const uint32_t olo = om << sh, ohi = sh > 23 ? om >> (32 - sh) : 0u;
+        if (w == 0) { s.occR[0] |= rlo; s.occR[1] |= rhi; s.own[0] |= olo; s.own[1] |= ohi; }
+        else if (w == 1) { s.occR[1] |= rlo; s.occR[2] |= rhi; s.own[1] |= olo; s.own[2] |= ohi; }
+        else { s.occR[2] |= rlo; s.own[2] |= olo; }
+        const int pr = r - r0;
+        if (pr >= 0 && pr <= 2) {
+            s.kmask |= kings << (pr * 3);
+            if (pr == 0) s.prow[0] = rm; else if (pr == 1) s.prow[1] = rm; else s.prow[2] = rm;
         }
     }
-    // every start below is a compile-time constant: a shift and a mask each
-    for (int i = 0; i < 3; ++i) {
-        const uint32_t red = bits96(s.occR[0], s.occR[1], s.occR[2], i * 9, 9);
-        const uint32_t black = bits96(s.occR[0], s.occR[1], s.occR[2], (7 + i) * 9, 9);
-        s.prow[i] = side == 1 ? red : black;
-        s.pcol[i] = bits96(s.occC[0], s.occC[1], s.occC[2], (3 + i) * 10, 10);
-    }
+    s.occC[0] = colm[0] | colm[1] << 10 | colm[2] << 20 | colm[3] << 30;
+    s.occC[1] = colm[3] >> 2 | colm[4] << 8 | colm[5] << 18 | colm[6] << 28;
+    s.occC[2] = colm[6] >> 4 | colm[7] << 6 | colm[8] << 16;
+    s.pcol[0] = colm[3];
+    s.pcol[1] = colm[4];
+    s.pcol[2] = colm[5];
     return s;
 }
 
@@ -344,7 +359,7 @@ XQT_HD int gen_piece(const int8_t* b, const Scan& s, int side, int from, uint16_
         const int nsl = (kind == 7 && !crossed) ? 1 : 8;
         const uint16_t* row = tab + ((kind == 7 && side != 1) ? 0 : kind) * 8;
 #if defined(__CUDA_ARCH__)
-#pragma unroll
+#pragma unroll 2
 #endif
         for (int sl = 0; sl < 8; ++sl) {
             const int e = row[sl];
@@ -364,11 +379,13 @@ XQT_HD int gen_piece(const int8_t* b, const Scan& s, int side, int from, uint16_
     return m;
 }
 
-// Ordered legal moves of `side` on b[] (mutated during the call, restored on return).  list must hold kListCap
-// entries; on return list[0 .. min(n, 128)) are action ids from*90+to.  Returns n, or 129 when the position has more
-// than 128 legal moves (no game reaches that; the caller counts it as an overflow).  *in_check = cy_is_in_check.
+// Ordered legal moves of `side` on b[] (mutated during the call, restored on return).  list = kListCap entries of
+// scratch for the pseudo-legal moves of a round; the action ids from*90+to of the first min(n, 128) legal moves are
+// stored to out[] as they are found (the kernel passes the position's row of the output array: the rows were filled
+// with -1 beforehand).  Returns n, or 129 when the position has more than 128 legal moves (no game reaches that; the
+// caller counts it as an overflow).  *in_check = cy_is_in_check.
 // Device: warp-synchronous -- every lane of the warp calls it (see XQT_WARP_MAX above).
-XQT_HD int movegen(int8_t* b, int side, uint16_t* list, int* in_check, const uint16_t* tab)
+XQT_HD int movegen(int8_t* b, int side, uint16_t* list, int16_t* out, int* in_check, const uint16_t* tab)
 {
     const Scan s = scan_board(b, side);
     const int r0 = side == 1 ? 0 : 7;
@@ -378,13 +395,13 @@ XQT_HD int movegen(int8_t* b, int side, uint16_t* list, int* in_check, const uin
         const bool a = attacked(b, s, r0, kdiv, ki - kdiv * 3, -side, -1, 0, 0, 0, -1);
         *in_check = (s.kmask == 0u || a) ? 1 : 0;  // pyx:552-554: no king in the palace counts as check
     }
-    int n = 0;                                     // legal moves so far = list[0..n)
+    int n = 0;                                     // legal moves so far
     uint32_t w0 = s.own[0], w1 = s.own[1], w2 = s.own[2];
-    for (;;) {
+    for (;;) {                                     // one round unless a board has more than kListCap - 17 pseudo-legal moves
         const int left = popc32(w0) + popc32(w1) + popc32(w2);
         const int ptrips = XQT_WARP_MAX(left);
         if (ptrips == 0) break;
-        int m = n;
+        int m = 0;
         for (int t = 0; t < ptrips; ++t) {
             if ((w0 | w1 | w2) != 0u && m + 17 <= kListCap) {
                 int from;
@@ -395,8 +412,8 @@ XQT_HD int movegen(int8_t* b, int side, uint16_t* list, int* in_check, const uin
             }
             XQT_RECONVERGE();
         }
-        const int ltrips = XQT_WARP_MAX(m - n);
-        int i = n;
+        const int ltrips = XQT_WARP_MAX(m);
+        int i = 0;
         for (int t = 0; t < ltrips; ++t) {
             if (i < m) {
                 const int mv = list[i++];
@@ -419,7 +436,7 @@ XQT_HD int movegen(int8_t* b, int side, uint16_t* list, int* in_check, const uin
                 b[from] = mover;
                 b[to] = taken;
                 if (ok) {
-                    if (n < kMaxOut) list[n] = (uint16_t)(from * 90 + to);
+                    if (n < kMaxOut) out[n] = (int16_t)(from * 90 + to);
                     if (++n > kMaxOut) {           // overflow: stop this board (the warp-uniform loops run on, idle)
                         i = m;
                         w0 = w1 = w2 = 0u;
