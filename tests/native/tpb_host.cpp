@@ -9,10 +9,11 @@ extern "C" int xqt_host_movegen_batch(const int8_t* boards, const int8_t* sides,
                                       uint8_t* n_moves, uint8_t* in_check)
 {
     int overflow = 0;
-    uint16_t tab[xqt::kSlotTableSize];
+    uint32_t tab[xqt::kSlotTableSize];
     for (int i = 0; i < xqt::kSlotTableSize; ++i) tab[i] = xqt::slot_entry(i);
     for (int i = 0; i < B; ++i) {
-        int8_t b[90];
+        int8_t padded[32 + 90 + 32] = {0};
+        int8_t* b = padded + 32;                  // the generator may read (never write) up to 20 bytes outside the board
         std::memcpy(b, boards + (size_t)i * 90, 90);
         uint16_t list[xqt::kListCap];
         int16_t out[128];

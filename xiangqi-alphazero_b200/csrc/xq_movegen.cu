@@ -179,20 +179,24 @@ movegen_kernel(const int8_t* __restrict__ boards, const int8_t* __restrict__ sid
 // flags as one 32-byte row.  Warps never wait for each other: no __syncthreads after the table set-up.
 constexpr int kTpbWarps = 4;
 constexpr int kTpbThreads = kTpbWarps * 32;
+constexpr int kPairWords = 86;             // 2 x 1350 plane bits = 2700 bits = 84.4 words (+1: the last float4 group reads word 84)
 constexpr int kTpbListStride = 106;        // uint16 per lane: 212 B = 53 words (odd: equal indices fall on different banks)
 static_assert(kTpbListStride >= xqt::kListCap && (kTpbListStride & 1) == 0 && ((kTpbListStride / 2) & 1) == 1, "list stride");
 
 struct __align__(16) TpbWarpSmem {
+    uint16_t list[32 * kTpbListStride];    // per-lane pseudo-legal scratch (first: the generator may READ up to 20 bytes
+                                           // before / after a board for off-board targets it then discards)
     int8_t boards[32 * kSquares];          // 2 880 B, lane l owns bytes [90 l, 90 l + 90)
-    uint16_t list[32 * kTpbListStride];    // per-lane pseudo-legal scratch
-    uint32_t pbits[3][kPlaneWords];        // plane bits, triple buffered: one warp sync per position
+    uint32_t pbits[3][kPairWords];         // plane bits of a PAIR of positions, triple buffered: one warp sync per pair
     int8_t sides[32];
+    int8_t pad_[8];
 };
+static_assert(sizeof(TpbWarpSmem) % 16 == 0 && (sizeof(uint16_t) * 32 * kTpbListStride) % 16 == 0, "16-byte aligned boards");
 
 struct __align__(16) TpbSmem {
     TpbWarpSmem w[kTpbWarps];
     float4 nib_lut[16];
-    uint16_t slot_tab[xqt::kSlotTableSize];   // leaper table of xq_rules_tpb.h: 128 B, one word per bank
+    uint32_t slot_tab[xqt::kSlotTableSize];   // leaper table of xq_rules_tpb.h (256 B)
 };
 
 template <bool PLANES>
@@ -210,7 +214,7 @@ movegen_tpb_kernel(const int8_t* __restrict__ boards, const int8_t* __restrict__
         sm.nib_lut[threadIdx.x] = make_float4((threadIdx.x & 1) ? 1.0f : 0.0f, (threadIdx.x & 2) ? 1.0f : 0.0f,
                                               (threadIdx.x & 4) ? 1.0f : 0.0f, (threadIdx.x & 8) ? 1.0f : 0.0f);
     if (PLANES) {
-        for (int i = lane; i < 3 * kPlaneWords; i += 32) (&W.pbits[0][0])[i] = 0u;
+        for (int i = lane; i < 3 * kPairWords; i += 32) (&W.pbits[0][0])[i] = 0u;
     }
     if (threadIdx.x < xqt::kSlotTableSize) sm.slot_tab[threadIdx.x] = xqt::slot_entry(threadIdx.x);
     __syncthreads();
@@ -260,53 +264,71 @@ movegen_tpb_kernel(const int8_t* __restrict__ boards, const int8_t* __restrict__
         }
 
         if (PLANES) {
-            // game.py:618-640, see movegen_kernel: the 1 350 values of a position are set as bits (one shared-memory
-            // atomic per piece) and expanded 4 bits -> one float4.  Buffer j % 3 is filled here, buffer (j + 1) % 3 --
-            // last read two positions ago -- is cleared for the next position, so one warp sync per position suffices.
-            for (int j = 0; j < nb; ++j) {
-                uint32_t* bits = W.pbits[j % 3];
-                uint32_t* nxt = W.pbits[(j + 1) % 3];
+            // game.py:618-640.  Two consecutive positions (even, odd) are 2 700 floats = 675 float4 starting on a 16-byte
+            // boundary, so a PAIR is expanded at a time: its 2 700 values are set as bits (the 180 cells of the two boards
+            // are 45 aligned words of shared memory, one atomic per piece), then float4 k is nibble k of the bit array --
+            // one shared load, a shift, a 16-entry table and one coalesced streaming store.  Buffer jp % 3 is filled,
+            // buffer (jp + 1) % 3 -- last read two pairs ago -- is cleared for the next pair: one warp sync per pair.
+            const int npair = nb >> 1;
+            const int sh = 4 * (lane & 7);
+            for (int jp = 0; jp < npair; ++jp) {
+                uint32_t* bits = W.pbits[jp % 3];
+                uint32_t* nxt = W.pbits[(jp + 1) % 3];
                 nxt[lane] = 0u;
-                if (lane < kPlaneWords - 32) nxt[32 + lane] = 0u;
-                const int8_t* b = W.boards + j * kSquares;
-                const int sd = W.sides[j];
-                for (int sq = lane; sq < kSquares; sq += 32) {
-                    const int v = b[sq] * sd;
-                    if (v != 0) {
-                        const int e = (v > 0 ? v - 1 : 6 - v) * kSquares + sq;
-                        atomicOr(&bits[e >> 5], 1u << (e & 31));
+                nxt[32 + lane] = 0u;
+                if (lane < kPairWords - 64) nxt[64 + lane] = 0u;
+                const uint32_t* cells = reinterpret_cast<const uint32_t*>(W.boards + jp * 2 * kSquares);
+                const int sd0 = W.sides[2 * jp], sd1 = W.sides[2 * jp + 1];
+                for (int w = lane; w < 45; w += 32) {
+                    const uint32_t word = cells[w];
+                    if (word != 0u) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int p = (int)(int8_t)(word >> (8 * k));
+                            if (p != 0) {
+                                const int ci = 4 * w + k;                   // cell 0..179 of the pair
+                                const bool second = ci >= kSquares;
+                                const int v = p * (second ? sd1 : sd0);
+                                const int e = (v > 0 ? v - 1 : 6 - v) * kSquares + ci + (second ? 14 * kSquares : 0);
+                                atomicOr(&bits[e >> 5], 1u << (e & 31));
+                            }
+                        }
                     }
                 }
-                if (sd == 1 && lane < 4)
-                    atomicOr(&bits[39 + lane], lane == 0 ? 0xfffff000u : (lane == 3 ? 0x3fu : 0xffffffffu));
-                warp_sync();
-                const size_t gi = (size_t)base + j;
-                float* outp = planes + gi * (15 * kSquares);
-                const int head = (int)(gi & 1) * 2;
-                if (lane == 0) {
-                    const uint32_t two = head ? bits[0] : bits[42] >> 4;
-                    float2 v;
-                    v.x = (two & 1u) ? 1.0f : 0.0f;
-                    v.y = (two & 2u) ? 1.0f : 0.0f;
-                    __stcs(reinterpret_cast<float2*>(head ? outp : outp + 1348), v);
+                // plane 14 = ones iff red moves: bits 1260..1349 (words 39..42) and 2610..2699 (words 81..84)
+                if (lane < 4) {
+                    if (sd0 == 1) atomicOr(&bits[39 + lane], lane == 0 ? 0xfffff000u : (lane == 3 ? 0x3fu : 0xffffffffu));
+                } else if (lane < 8) {
+                    if (sd1 == 1) atomicOr(&bits[77 + lane], lane == 4 ? 0xfffc0000u : (lane == 7 ? 0xfffu : 0xffffffffu));
                 }
-                float4* out4 = reinterpret_cast<float4*>(outp + head);
-                const int e0 = head + 4 * lane;
-                const int sh = e0 & 31;
-                const uint32_t* wp = bits + (e0 >> 5);
+                warp_sync();
+                float4* out4 = reinterpret_cast<float4*>(planes + (size_t)(base + 2 * jp) * (15 * kSquares));
+                const uint32_t* wp = bits + (lane >> 3);
 #pragma unroll
-                for (int it = 0; it < 11; ++it) {
+                for (int it = 0; it < 22; ++it) {
                     const int k = it * 32 + lane;
-                    if (it < 10 || k < 337) {
-                        const uint32_t nib = __funnelshift_r(wp[4 * it], wp[4 * it + 1], sh) & 15u;
+                    if (it < 21 || k < 675) {
+                        const uint32_t nib = (wp[4 * it] >> sh) & 15u;
                         __stcs(out4 + k, sm.nib_lut[nib]);
                     }
                 }
             }
-            // leave all three buffers clear for the next task: buffer nb % 3 was cleared as "next" of the last position
-            // and never filled; the other two are cleared at the top of the positions that follow them
+            if (nb & 1) {
+                // the last position of the whole batch stands alone (once per launch): element by element
+                const int j = nb - 1;
+                const int8_t* b = W.boards + j * kSquares;
+                const int sd = W.sides[j];
+                float* outp = planes + (size_t)(base + j) * (15 * kSquares);
+                for (int e = lane; e < 15 * kSquares; e += 32) {
+                    const int pl = e / kSquares, sq = e - pl * kSquares;
+                    const int v = b[sq] * sd;
+                    const bool one = pl == 14 ? sd == 1 : (v != 0 && (v > 0 ? v - 1 : 6 - v) == pl);
+                    outp[e] = one ? 1.0f : 0.0f;
+                }
+            }
+            // leave all three buffers clear for the next task
             warp_sync();
-            for (int i = lane; i < 3 * kPlaneWords; i += 32) (&W.pbits[0][0])[i] = 0u;
+            for (int i = lane; i < 3 * kPairWords; i += 32) (&W.pbits[0][0])[i] = 0u;
         }
     }
 }
@@ -507,8 +529,9 @@ extern "C" int xq_movegen_batch(xq_ctx* c, const int8_t* d_boards, const int8_t*
     if (((uintptr_t)d_actions & 7) || (d_planes && ((uintptr_t)d_planes & 7)))
         return xq_fail(c, XQ_ERR_ARG, "xq_movegen_batch: actions/planes must be 8-byte aligned");
     cudaStream_t s = (cudaStream_t)stream;
-    if (c->movegen_impl == 1) {
-        // second generation: one thread per board (xq_rules_tpb.h)
+    if (c->movegen_impl == 1 && (d_planes == nullptr || ((uintptr_t)d_planes & 15) == 0)) {
+        // second generation: one thread per board (xq_rules_tpb.h); a planes pointer that is not 16-byte aligned takes
+        // the first-generation kernel (same outputs)
         static bool attr_set[2] = {false, false};
         const int smem = (int)sizeof(TpbSmem);
         if (!attr_set[0]) {

@@ -266,46 +266,38 @@ XQT_HD bool attacked(const int8_t* b, const Scan& s, int r0, int pr, int pc, int
     return hit;
 }
 
-// Leaper table (pyx:287-367, 434-484 orders): 8 rows x 8 slots of 16 bits, row = piece kind (1 king, 2 advisor,
-// 3 elephant, 4 knight, 7 red pawn; row 0 = black pawn), entry = dr+2 | (dc+2) << 3 | valid << 6 | has_leg << 7 |
-// (leg offset + 10) << 8.  128 bytes = one 32-bit word per shared-memory bank: lanes looking up different kinds never
-// conflict.  The kernel fills its copy with slot_entry(); the host build uses a static array.
+// Leaper table (pyx:287-367, 434-484 orders): 8 rows x 8 slots, row = piece kind (1 king, 2 advisor, 3 elephant,
+// 4 knight, 7 red pawn; row 0 = black pawn), entry = four signed bytes {dr, dc, leg offset, square delta dr*9+dc};
+// delta == 0 marks an unused slot, leg offset == 0 a move without a leg / eye.  256 bytes of shared memory in the
+// kernel (filled with slot_entry()); the host build uses a plain array.
 constexpr int kSlotTableSize = 64;
-XQT_HD uint16_t slot_entry(int idx)
+XQT_HD uint32_t slot_entry(int idx)
 {
     const int row = idx >> 3, sl = idx & 7;
     int dr = 0, dc = 0, leg = 0;
-    bool valid = false, has_leg = false;
     if (row == 1 && sl < 4) {                       // king: up, down, left, right
         dr = sl == 0 ? -1 : (sl == 1 ? 1 : 0);
         dc = sl == 2 ? -1 : (sl == 3 ? 1 : 0);
-        valid = true;
     } else if ((row == 2 || row == 3) && sl < 4) {  // advisor / elephant: (-,-) (-,+) (+,-) (+,+)
         const int k = row == 2 ? 1 : 2;
         dr = sl < 2 ? -k : k;
         dc = (sl & 1) ? k : -k;
-        valid = true;
-        if (row == 3) {
-            has_leg = true;
-            leg = (dr / 2) * 9 + dc / 2;
-        }
+        if (row == 3) leg = (dr / 2) * 9 + dc / 2;
     } else if (row == 4) {                          // knight (pyx:31-39)
         dr = sl < 4 ? (sl < 2 ? -2 : 2) : (sl < 6 ? -1 : 1);
         dc = sl < 4 ? ((sl & 1) ? 1 : -1) : ((sl & 1) ? 2 : -2);
-        valid = has_leg = true;
         leg = sl < 4 ? (dr / 2) * 9 : dc / 2;
     } else if ((row == 7 || row == 0) && sl < 3) {  // pawn: forward, left, right
         dr = sl == 0 ? (row == 7 ? 1 : -1) : 0;
         dc = sl == 1 ? -1 : (sl == 2 ? 1 : 0);
-        valid = true;
     }
-    return (uint16_t)((dr + 2) | (dc + 2) << 3 | (valid ? 0x40 : 0) | (has_leg ? 0x80 : 0) | (leg + 10) << 8);
+    return (uint32_t)(dr & 0xff) | (uint32_t)(dc & 0xff) << 8 | (uint32_t)(leg & 0xff) << 16 | (uint32_t)((dr * 9 + dc) & 0xff) << 24;
 }
 
 // Pseudo-legal targets of the piece on `from` appended to list[m...] as from << 7 | to; returns the new m.
 // Two sections (sliders / leapers), each straight-line with predicated stores: the lanes of a warp that are in the same
 // section stay together.
-XQT_HD int gen_piece(const int8_t* b, const Scan& s, int side, int from, uint16_t* list, int m, const uint16_t* tab)
+XQT_HD int gen_piece(const int8_t* b, const Scan& s, int side, int from, uint16_t* list, int m, const uint32_t* tab)
 {
     const int p = b[from];
     const int kind = p < 0 ? -p : p;
@@ -353,26 +345,23 @@ XQT_HD int gen_piece(const int8_t* b, const Scan& s, int side, int from, uint16_
         // elephant, the board for knight and pawn
         const bool palace = kind <= 2;
         const int rlo = palace ? (side == 1 ? 0 : 7) : (kind == 3 && side != 1 ? 5 : 0);
-        const int rhi = palace ? rlo + 2 : (kind == 3 && side == 1 ? 4 : 9);
-        const int clo = palace ? 3 : 0, chi = palace ? 5 : 8;
+        const int rspan = palace ? 2 : (kind == 3 ? 4 : 9);          // target rows rlo .. rlo + rspan
+        const int clo = palace ? 3 : 0, cspan = palace ? 2 : 8;
         const bool crossed = side == 1 ? r >= 5 : r <= 4;
-        const int nsl = (kind == 7 && !crossed) ? 1 : 8;
-        const uint16_t* row = tab + ((kind == 7 && side != 1) ? 0 : kind) * 8;
-#if defined(__CUDA_ARCH__)
-#pragma unroll 2
-#endif
-        for (int sl = 0; sl < 8; ++sl) {
-            const int e = row[sl];
-            const int dr = (e & 7) - 2, dc = ((e >> 3) & 7) - 2;
-            const int nr = r + dr, nc = c + dc;
-            bool ok = ((e & 0x40) != 0) & (sl < nsl) & (nr >= rlo) & (nr <= rhi) & (nc >= clo) & (nc <= chi);
-            const int legoff = ((e >> 8) & 31) - 10;
-            const int to = from + dr * 9 + dc;
-            const int legv = b[ok ? from + legoff : from];     // elephant eye / horse leg (no leg: the own piece, ignored)
-            const int tgt = b[ok ? to : from];
-            ok &= ((e & 0x80) == 0) | (legv == 0);
-            ok &= !(tgt * side > 0);
-            if (ok) list[m] = (uint16_t)(from << 7 | to);
+        const int nsl = kind == 4 ? 8 : (kind == 7 ? (crossed ? 3 : 1) : 4);
+        const uint32_t* row = tab + ((kind == 7 && side != 1) ? 0 : kind) * 8;
+        const int from7 = from << 7;
+        // b[] may be read up to 20 bytes outside the board for targets that are then discarded (the caller keeps that
+        // much readable memory on both sides)
+        for (int sl = 0; sl < nsl; ++sl) {
+            const uint32_t e = row[sl];
+            const int dr = (int)(int8_t)e, dc = (int)(int8_t)(e >> 8), legoff = (int)(int8_t)(e >> 16), delta = (int)e >> 24;
+            const int to = from + delta;
+            const int legv = b[from + legoff];                        // elephant eye / horse leg
+            const int tgt = b[to];
+            const bool ok = ((unsigned)(r + dr - rlo) <= (unsigned)rspan) & ((unsigned)(c + dc - clo) <= (unsigned)cspan) &
+                            ((legoff == 0) | (legv == 0)) & !(tgt * side > 0);
+            if (ok) list[m] = (uint16_t)(from7 | to);
             m += ok ? 1 : 0;
         }
     }
@@ -385,7 +374,7 @@ XQT_HD int gen_piece(const int8_t* b, const Scan& s, int side, int from, uint16_
 // with -1 beforehand).  Returns n, or 129 when the position has more than 128 legal moves (no game reaches that; the
 // caller counts it as an overflow).  *in_check = cy_is_in_check.
 // Device: warp-synchronous -- every lane of the warp calls it (see XQT_WARP_MAX above).
-XQT_HD int movegen(int8_t* b, int side, uint16_t* list, int16_t* out, int* in_check, const uint16_t* tab)
+XQT_HD int movegen(int8_t* b, int side, uint16_t* list, int16_t* out, int* in_check, const uint32_t* tab)
 {
     const Scan s = scan_board(b, side);
     const int r0 = side == 1 ? 0 : 7;
@@ -396,6 +385,8 @@ XQT_HD int movegen(int8_t* b, int side, uint16_t* list, int16_t* out, int* in_ch
         *in_check = (s.kmask == 0u || a) ? 1 : 0;  // pyx:552-554: no king in the palace counts as check
     }
     int n = 0;                                     // legal moves so far
+    const int ki0 = s.kmask ? ctz32(s.kmask) : 0;
+    const int pr0 = (ki0 * 11) >> 5, pc0 = ki0 - pr0 * 3;          // the king every non-king move leaves where it is
     uint32_t w0 = s.own[0], w1 = s.own[1], w2 = s.own[2];
     for (;;) {                                     // one round unless a board has more than kListCap - 17 pseudo-legal moves
         const int left = popc32(w0) + popc32(w1) + popc32(w2);
@@ -422,17 +413,20 @@ XQT_HD int movegen(int8_t* b, int side, uint16_t* list, int16_t* out, int* in_ch
                 const int8_t mover = b[from], taken = b[to];
                 b[to] = mover;
                 b[from] = 0;
-                uint32_t km = s.kmask;
-                if (mover == side) {               // a king move (targets are always inside the palace box)
-                    const int pr = fr - r0;
-                    if (pr >= 0 && pr <= 2 && fc >= 3 && fc <= 5) km &= ~(1u << (pr * 3 + fc - 3));
+                int pr = pr0, pc = pc0;
+                bool have_king = s.kmask != 0u;
+                if (mover == side) {               // a king move (targets are always inside the palace box): the king that
+                    uint32_t km = s.kmask;         // is "found" afterwards is the first one in palace order (pyx:93-98)
+                    const int fpr = fr - r0;
+                    if (fpr >= 0 && fpr <= 2 && fc >= 3 && fc <= 5) km &= ~(1u << (fpr * 3 + fc - 3));
                     km |= 1u << ((tr - r0) * 3 + tc - 3);
+                    const int ki = ctz32(km);
+                    pr = (ki * 11) >> 5;
+                    pc = ki - pr * 3;
+                    have_king = true;
                 }
-                const int ki = km ? ctz32(km) : 0;
-                const int kdiv = (ki * 11) >> 5;
-                // km == 0 (no own king in the palace): the probe square may hold anything, its result is discarded
-                const bool ok = !attacked(b, s, r0, kdiv, ki - kdiv * 3, -side, fr, fc, tr, tc, taken != 0 ? to : -1)
-                                && km != 0u;
+                // no own king in the palace: the probe square may hold anything, its result is discarded
+                const bool ok = !attacked(b, s, r0, pr, pc, -side, fr, fc, tr, tc, taken != 0 ? to : -1) && have_king;
                 b[from] = mover;
                 b[to] = taken;
                 if (ok) {
