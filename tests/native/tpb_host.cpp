@@ -18,7 +18,10 @@ extern "C" int xqt_host_movegen_batch(const int8_t* boards, const int8_t* sides,
         uint16_t list[xqt::kListCap];
         int16_t out[128];
         int chk = 0;
-        int n = xqt::movegen(b, sides[i], list, out, &chk, tab);
+        uint32_t occ[3];
+        int n = xqt::movegen(b, sides[i], list, out, &chk, tab, occ);
+        for (int q = 0; q < 90; ++q)
+            if (((occ[q >> 5] >> (q & 31)) & 1u) != (b[q] != 0 ? 1u : 0u)) return -1 - i;
         if (std::memcmp(b, boards + (size_t)i * 90, 90) != 0) return -1 - i;   // the board must come back untouched
         if (n > 128) { ++overflow; n = 128; }
         for (int k = 0; k < 128; ++k) actions[(size_t)i * 128 + k] = k < n ? out[k] : (int16_t)-1;

@@ -187,10 +187,9 @@ struct __align__(16) TpbWarpSmem {
     uint16_t list[32 * kTpbListStride];    // per-lane pseudo-legal scratch (first: the generator may READ up to 20 bytes
                                            // before / after a board for off-board targets it then discards)
     int8_t boards[32 * kSquares];          // 2 880 B, lane l owns bytes [90 l, 90 l + 90)
-    uint32_t pbits[3][kPairWords];         // plane bits of a PAIR of positions, triple buffered: one warp sync per pair
     int8_t sides[32];
-    int8_t pad_[8];
 };
+static_assert(16 * kPairWords * 4 <= 32 * kTpbListStride * 2, "the 16 plane-bit buffers of a task reuse the list storage");
 static_assert(sizeof(TpbWarpSmem) % 16 == 0 && (sizeof(uint16_t) * 32 * kTpbListStride) % 16 == 0, "16-byte aligned boards");
 
 struct __align__(16) TpbSmem {
@@ -213,9 +212,6 @@ movegen_tpb_kernel(const int8_t* __restrict__ boards, const int8_t* __restrict__
     if (PLANES && threadIdx.x < 16)
         sm.nib_lut[threadIdx.x] = make_float4((threadIdx.x & 1) ? 1.0f : 0.0f, (threadIdx.x & 2) ? 1.0f : 0.0f,
                                               (threadIdx.x & 4) ? 1.0f : 0.0f, (threadIdx.x & 8) ? 1.0f : 0.0f);
-    if (PLANES) {
-        for (int i = lane; i < 3 * kPairWords; i += 32) (&W.pbits[0][0])[i] = 0u;
-    }
     if (threadIdx.x < xqt::kSlotTableSize) sm.slot_tab[threadIdx.x] = xqt::slot_entry(threadIdx.x);
     __syncthreads();
 
@@ -252,7 +248,8 @@ movegen_tpb_kernel(const int8_t* __restrict__ boards, const int8_t* __restrict__
         uint16_t* list = W.list + lane * kTpbListStride;
         int chk = 0;
         int16_t* out_row = actions + (size_t)(base + (lane < nb ? lane : 0)) * kMaxMoves;   // idle lanes find no move
-        int n = xqt::movegen(W.boards + lane * kSquares, side, list, out_row, &chk, sm.slot_tab);   // warp-synchronous: all 32 lanes
+        uint32_t occ[3];
+        int n = xqt::movegen(W.boards + lane * kSquares, side, list, out_row, &chk, sm.slot_tab, occ);   // warp-synchronous: all 32 lanes
         warp_sync();
         if (lane < nb) {
             if (n > kMaxMoves) {
@@ -265,45 +262,50 @@ movegen_tpb_kernel(const int8_t* __restrict__ boards, const int8_t* __restrict__
 
         if (PLANES) {
             // game.py:618-640.  Two consecutive positions (even, odd) are 2 700 floats = 675 float4 starting on a 16-byte
-            // boundary, so a PAIR is expanded at a time: its 2 700 values are set as bits (the 180 cells of the two boards
-            // are 45 aligned words of shared memory, one atomic per piece), then float4 k is nibble k of the bit array --
-            // one shared load, a shift, a 16-entry table and one coalesced streaming store.  Buffer jp % 3 is filled,
-            // buffer (jp + 1) % 3 -- last read two pairs ago -- is cleared for the next pair: one warp sync per pair.
+            // boundary, so a PAIR is expanded at a time.  The 16 pairs of the task get 16 bit arrays of 2 700 bits in the
+            // (now idle) list storage; every lane sets the bits of ITS position by walking the occupied squares it
+            // found in the scan (one shared-memory atomic per piece, ~26 per board instead of a 90-cell sweep), and then
+            // float4 k of a pair is nibble k of its bit array: one shared load, a shift, a 16-entry table and one
+            // coalesced streaming store.
+            uint32_t* pair_bits = reinterpret_cast<uint32_t*>(W.list);
+            for (int i = lane; i < 16 * kPairWords; i += 32) pair_bits[i] = 0u;
+            warp_sync();
+            {
+                uint32_t* bits = pair_bits + (lane >> 1) * kPairWords;
+                const int ebase = (lane & 1) * (15 * kSquares);
+                const int8_t* b = W.boards + lane * kSquares;
+                uint32_t o0 = occ[0], o1 = occ[1], o2 = occ[2];
+                // warp-uniform trip count and branch-free plane-14 words: a per-lane loop bound or a red/black branch here
+                // left the warp split in two for the rest of the task (ncu: the stores below ran with 17.7 lanes)
+                const int trips = XQT_WARP_MAX(__popc(o0) + __popc(o1) + __popc(o2));
+                for (int t = 0; t < trips; ++t) {
+                    if ((o0 | o1 | o2) != 0u) {
+                        int sq;
+                        if (o0) { sq = __ffs(o0) - 1; o0 &= o0 - 1u; }
+                        else if (o1) { sq = 31 + __ffs(o1); o1 &= o1 - 1u; }
+                        else { sq = 63 + __ffs(o2); o2 &= o2 - 1u; }
+                        const int v = b[sq] * side;
+                        const int e = ebase + (v > 0 ? v - 1 : 6 - v) * kSquares + sq;
+                        atomicOr(&bits[e >> 5], 1u << (e & 31));
+                    }
+                    __syncwarp();
+                }
+                // plane 14 = ones iff red moves: elements 1260..1349 of the position = bits 1260..1349 (words 39..42) of an
+                // even lane's half, bits 2610..2699 (words 81..84) of an odd lane's; the two middle words belong to it alone
+                const uint32_t ones = (side == 1 && lane < nb) ? 0xffffffffu : 0u;
+                const bool odd = (lane & 1) != 0;
+                uint32_t* w14 = bits + (odd ? 81 : 39);
+                atomicOr(w14, (odd ? 0xfffc0000u : 0xfffff000u) & ones);
+                w14[1] = ones;
+                w14[2] = ones;
+                atomicOr(w14 + 3, (odd ? 0xfffu : 0x3fu) & ones);
+            }
+            warp_sync();
             const int npair = nb >> 1;
             const int sh = 4 * (lane & 7);
             for (int jp = 0; jp < npair; ++jp) {
-                uint32_t* bits = W.pbits[jp % 3];
-                uint32_t* nxt = W.pbits[(jp + 1) % 3];
-                nxt[lane] = 0u;
-                nxt[32 + lane] = 0u;
-                if (lane < kPairWords - 64) nxt[64 + lane] = 0u;
-                const uint32_t* cells = reinterpret_cast<const uint32_t*>(W.boards + jp * 2 * kSquares);
-                const int sd0 = W.sides[2 * jp], sd1 = W.sides[2 * jp + 1];
-                for (int w = lane; w < 45; w += 32) {
-                    const uint32_t word = cells[w];
-                    if (word != 0u) {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const int p = (int)(int8_t)(word >> (8 * k));
-                            if (p != 0) {
-                                const int ci = 4 * w + k;                   // cell 0..179 of the pair
-                                const bool second = ci >= kSquares;
-                                const int v = p * (second ? sd1 : sd0);
-                                const int e = (v > 0 ? v - 1 : 6 - v) * kSquares + ci + (second ? 14 * kSquares : 0);
-                                atomicOr(&bits[e >> 5], 1u << (e & 31));
-                            }
-                        }
-                    }
-                }
-                // plane 14 = ones iff red moves: bits 1260..1349 (words 39..42) and 2610..2699 (words 81..84)
-                if (lane < 4) {
-                    if (sd0 == 1) atomicOr(&bits[39 + lane], lane == 0 ? 0xfffff000u : (lane == 3 ? 0x3fu : 0xffffffffu));
-                } else if (lane < 8) {
-                    if (sd1 == 1) atomicOr(&bits[77 + lane], lane == 4 ? 0xfffc0000u : (lane == 7 ? 0xfffu : 0xffffffffu));
-                }
-                warp_sync();
                 float4* out4 = reinterpret_cast<float4*>(planes + (size_t)(base + 2 * jp) * (15 * kSquares));
-                const uint32_t* wp = bits + (lane >> 3);
+                const uint32_t* wp = pair_bits + jp * kPairWords + (lane >> 3);
 #pragma unroll
                 for (int it = 0; it < 22; ++it) {
                     const int k = it * 32 + lane;
@@ -326,9 +328,6 @@ movegen_tpb_kernel(const int8_t* __restrict__ boards, const int8_t* __restrict__
                     outp[e] = one ? 1.0f : 0.0f;
                 }
             }
-            // leave all three buffers clear for the next task
-            warp_sync();
-            for (int i = lane; i < 3 * kPairWords; i += 32) (&W.pbits[0][0])[i] = 0u;
         }
     }
 }

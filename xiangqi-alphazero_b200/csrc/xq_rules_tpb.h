@@ -372,11 +372,14 @@ XQT_HD int gen_piece(const int8_t* b, const Scan& s, int side, int from, uint16_
 // scratch for the pseudo-legal moves of a round; the action ids from*90+to of the first min(n, 128) legal moves are
 // stored to out[] as they are found (the kernel passes the position's row of the output array: the rows were filled
 // with -1 beforehand).  Returns n, or 129 when the position has more than 128 legal moves (no game reaches that; the
-// caller counts it as an overflow).  *in_check = cy_is_in_check.
+// caller counts it as an overflow).  *in_check = cy_is_in_check, occ[0..2] = the occupied-square set.
 // Device: warp-synchronous -- every lane of the warp calls it (see XQT_WARP_MAX above).
-XQT_HD int movegen(int8_t* b, int side, uint16_t* list, int16_t* out, int* in_check, const uint32_t* tab)
+XQT_HD int movegen(int8_t* b, int side, uint16_t* list, int16_t* out, int* in_check, const uint32_t* tab, uint32_t* occ)
 {
     const Scan s = scan_board(b, side);
+    occ[0] = s.occR[0];                            // occupied squares (bit r*9+c): the kernel walks them for the planes
+    occ[1] = s.occR[1];
+    occ[2] = s.occR[2];
     const int r0 = side == 1 ? 0 : 7;
     {
         const int ki = s.kmask ? ctz32(s.kmask) : 0;
