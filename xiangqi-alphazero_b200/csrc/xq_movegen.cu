@@ -180,7 +180,7 @@ movegen_kernel(const int8_t* __restrict__ boards, const int8_t* __restrict__ sid
 constexpr int kTpbWarps = 4;
 constexpr int kTpbThreads = kTpbWarps * 32;
 constexpr int kPairWords = 86;             // 2 x 1350 plane bits = 2700 bits = 84.4 words (+1: the last float4 group reads word 84)
-constexpr int kTpbListStride = 106;        // uint16 per lane: 212 B = 53 words (odd: equal indices fall on different banks)
+constexpr int kTpbListStride = 98;         // uint16 per lane: 196 B = 49 words (odd: equal indices fall on different banks)
 static_assert(kTpbListStride >= xqt::kListCap && (kTpbListStride & 1) == 0 && ((kTpbListStride / 2) & 1) == 1, "list stride");
 
 struct __align__(16) TpbWarpSmem {
@@ -199,7 +199,7 @@ struct __align__(16) TpbSmem {
 };
 
 template <bool PLANES>
-__global__ void __launch_bounds__(kTpbThreads, 5)
+__global__ void __launch_bounds__(kTpbThreads, 6)
 movegen_tpb_kernel(const int8_t* __restrict__ boards, const int8_t* __restrict__ sides, int B,
                    int16_t* __restrict__ actions, uint8_t* __restrict__ n_moves,
                    uint8_t* __restrict__ in_check, float* __restrict__ planes, int* __restrict__ overflow,

@@ -60,7 +60,7 @@ static __device__ __noinline__ int warp_max_i(int v)
 
 namespace xqt {
 
-constexpr int kListCap = 104;   // pseudo-legal scratch entries per board and round (a piece adds at most 17; orthodox maximum seen: 75)
+constexpr int kListCap = 98;    // pseudo-legal scratch entries per board and round (a piece adds at most 17; orthodox maximum seen: 75)
 constexpr int kMaxOut = 128;
 
 XQT_HD int div9(int x) { return (x * 57) >> 9; }   // x / 9 for 0 <= x < 128
