@@ -19,7 +19,9 @@ extern "C" int xqt_host_movegen_batch(const int8_t* boards, const int8_t* sides,
         int16_t out[128];
         int chk = 0;
         uint32_t occ[3];
-        int n = xqt::movegen(b, sides[i], list, out, &chk, tab, occ);
+        int nf = 0;
+        int n = xqt::movegen(b, sides[i], list, out, &nf, &chk, tab, occ);
+        for (int k = nf; k < n && k < 128; ++k) out[k] = (int16_t)list[k - nf];
         for (int q = 0; q < 90; ++q)
             if (((occ[q >> 5] >> (q & 31)) & 1u) != (b[q] != 0 ? 1u : 0u)) return -1 - i;
         if (std::memcmp(b, boards + (size_t)i * 90, 90) != 0) return -1 - i;   // the board must come back untouched

@@ -188,6 +188,8 @@ struct __align__(16) TpbWarpSmem {
                                            // before / after a board for off-board targets it then discards)
     int8_t boards[32 * kSquares];          // 2 880 B, lane l owns bytes [90 l, 90 l + 90)
     int8_t sides[32];
+    uint8_t n_out[32];                     // legal-move count of each lane's position and how many ids it already
+    uint8_t n_flushed[32];                 // wrote to its output row itself
 };
 static_assert(16 * kPairWords * 4 <= 32 * kTpbListStride * 2, "the 16 plane-bit buffers of a task reuse the list storage");
 static_assert(sizeof(TpbWarpSmem) % 16 == 0 && (sizeof(uint16_t) * 32 * kTpbListStride) % 16 == 0, "16-byte aligned boards");
@@ -239,26 +241,45 @@ movegen_tpb_kernel(const int8_t* __restrict__ boards, const int8_t* __restrict__
         W.sides[lane] = (int8_t)side;
         warp_sync();
 
-        // move-list rows: filled with -1 by the whole warp (one 8-byte store per lane and row), then every lane writes
-        // its position's legal moves straight into its row as it finds them (2-byte stores that merge in L2 with the
-        // fill; the warp sync orders the two)
-        for (int j = 0; j < nb; ++j)
-            reinterpret_cast<uint2*>(actions + (size_t)(base + j) * kMaxMoves)[lane] = make_uint2(0xffffffffu, 0xffffffffu);
-        warp_sync();
         uint16_t* list = W.list + lane * kTpbListStride;
-        int chk = 0;
-        int16_t* out_row = actions + (size_t)(base + (lane < nb ? lane : 0)) * kMaxMoves;   // idle lanes find no move
+        int chk = 0, flushed = 0;
         uint32_t occ[3];
-        int n = xqt::movegen(W.boards + lane * kSquares, side, list, out_row, &chk, sm.slot_tab, occ);   // warp-synchronous: all 32 lanes
-        warp_sync();
+        int16_t* out_row = actions + (size_t)(base + (lane < nb ? lane : 0)) * kMaxMoves;   // idle lanes find no move
+        int n = xqt::movegen(W.boards + lane * kSquares, side, list, out_row, &flushed, &chk, sm.slot_tab, occ);   // warp-synchronous: all 32 lanes
+        if (n > kMaxMoves) {
+            atomicAdd(overflow, 1);
+            n = kMaxMoves;
+        }
+        W.n_out[lane] = (uint8_t)n;
+        W.n_flushed[lane] = (uint8_t)flushed;
         if (lane < nb) {
-            if (n > kMaxMoves) {
-                atomicAdd(overflow, 1);
-                n = kMaxMoves;
-            }
             n_moves[base + lane] = (uint8_t)n;
             in_check[base + lane] = (uint8_t)chk;
         }
+        warp_sync();
+
+        // move lists: 128 int16 per position leave as one coalesced 8-byte store per lane (entries 4 lane .. 4 lane + 3
+        // from the position's staged ids, -1 behind the last move).  A position that flushed ids during generation
+        // (piece crowds no game reaches) keeps them and gets the rest entry by entry.
+        for (int j = 0; j < nb; ++j) {
+            const int nj = W.n_out[j], fj = W.n_flushed[j];
+            const uint16_t* lj = W.list + j * kTpbListStride;
+            int16_t* row = actions + (size_t)(base + j) * kMaxMoves;
+            if (fj == 0) {
+                const uint32_t* lw = reinterpret_cast<const uint32_t*>(lj);
+                const int k0 = 4 * lane;
+                // words beyond the staged ids are never read as data: the selects below replace them
+                uint32_t a = k0 < nj ? lw[2 * lane] : 0xffffffffu;
+                uint32_t c = k0 + 2 < nj ? lw[2 * lane + 1] : 0xffffffffu;
+                if (k0 + 1 >= nj) a |= 0xffff0000u;
+                if (k0 + 3 >= nj) c |= 0xffff0000u;
+                __stcs(reinterpret_cast<uint2*>(row) + lane, make_uint2(a, c));
+            } else {
+                for (int k = lane; k < kMaxMoves; k += 32)
+                    if (k >= fj) row[k] = k < nj ? (int16_t)lj[k - fj] : (int16_t)-1;
+            }
+        }
+        warp_sync();
 
         if (PLANES) {
             // game.py:618-640.  Two consecutive positions (even, odd) are 2 700 floats = 675 float4 starting on a 16-byte

@@ -368,13 +368,16 @@ XQT_HD int gen_piece(const int8_t* b, const Scan& s, int side, int from, uint16_
     return m;
 }
 
-// Ordered legal moves of `side` on b[] (mutated during the call, restored on return).  list = kListCap entries of
-// scratch for the pseudo-legal moves of a round; the action ids from*90+to of the first min(n, 128) legal moves are
-// stored to out[] as they are found (the kernel passes the position's row of the output array: the rows were filled
-// with -1 beforehand).  Returns n, or 129 when the position has more than 128 legal moves (no game reaches that; the
-// caller counts it as an overflow).  *in_check = cy_is_in_check, occ[0..2] = the occupied-square set.
+// Ordered legal moves of `side` on b[] (mutated during the call, restored on return).  list = kListCap entries: the
+// pseudo-legal moves of a round, compacted in place into the action ids from*90+to of the legal ones (a legal move is
+// written at or before the entry it was read from).  A board with more than kListCap - 17 pseudo-legal moves (piece
+// crowds no game reaches) takes further rounds; before each of them the ids staged so far are flushed to out[] (the
+// position's row of the output array).  On return *flushed ids are in out[0 .. *flushed), the following
+// min(n, 128) - *flushed ones in list[]; the caller copies those out.  Returns n, or 129 when the position has more
+// than 128 legal moves (the caller counts it as an overflow).  *in_check = cy_is_in_check, occ[0..2] = the
+// occupied-square set.
 // Device: warp-synchronous -- every lane of the warp calls it (see XQT_WARP_MAX above).
-XQT_HD int movegen(int8_t* b, int side, uint16_t* list, int16_t* out, int* in_check, const uint32_t* tab, uint32_t* occ)
+XQT_HD int movegen(int8_t* b, int side, uint16_t* list, int16_t* out, int* flushed, int* in_check, const uint32_t* tab, uint32_t* occ)
 {
     const Scan s = scan_board(b, side);
     occ[0] = s.occR[0];                            // occupied squares (bit r*9+c): the kernel walks them for the planes
@@ -388,6 +391,7 @@ XQT_HD int movegen(int8_t* b, int side, uint16_t* list, int16_t* out, int* in_ch
         *in_check = (s.kmask == 0u || a) ? 1 : 0;  // pyx:552-554: no king in the palace counts as check
     }
     int n = 0;                                     // legal moves so far
+    int nf = 0;                                    // ... of which already flushed to out[]
     const int ki0 = s.kmask ? ctz32(s.kmask) : 0;
     const int pr0 = (ki0 * 11) >> 5, pc0 = ki0 - pr0 * 3;          // the king every non-king move leaves where it is
     uint32_t w0 = s.own[0], w1 = s.own[1], w2 = s.own[2];
@@ -395,7 +399,12 @@ XQT_HD int movegen(int8_t* b, int side, uint16_t* list, int16_t* out, int* in_ch
         const int left = popc32(w0) + popc32(w1) + popc32(w2);
         const int ptrips = XQT_WARP_MAX(left);
         if (ptrips == 0) break;
-        int m = 0;
+        if (left != 0 && n > nf) {                 // another round for this board: make room
+            for (int k = nf; k < n && k < kMaxOut; ++k) out[k] = (int16_t)list[k - nf];
+            nf = n < kMaxOut ? n : kMaxOut;
+        }
+        const int m0 = n - nf;                     // staged legal ids occupy list[0 .. m0)
+        int m = m0;
         for (int t = 0; t < ptrips; ++t) {
             if ((w0 | w1 | w2) != 0u && m + 17 <= kListCap) {
                 int from;
@@ -406,8 +415,8 @@ XQT_HD int movegen(int8_t* b, int side, uint16_t* list, int16_t* out, int* in_ch
             }
             XQT_RECONVERGE();
         }
-        const int ltrips = XQT_WARP_MAX(m);
-        int i = 0;
+        const int ltrips = XQT_WARP_MAX(m - m0);
+        int i = m0;
         for (int t = 0; t < ltrips; ++t) {
             if (i < m) {
                 const int mv = list[i++];
@@ -433,7 +442,7 @@ XQT_HD int movegen(int8_t* b, int side, uint16_t* list, int16_t* out, int* in_ch
                 b[from] = mover;
                 b[to] = taken;
                 if (ok) {
-                    if (n < kMaxOut) out[n] = (int16_t)(from * 90 + to);
+                    if (n < kMaxOut) list[n - nf] = (uint16_t)(from * 90 + to);
                     if (++n > kMaxOut) {           // overflow: stop this board (the warp-uniform loops run on, idle)
                         i = m;
                         w0 = w1 = w2 = 0u;
@@ -443,6 +452,7 @@ XQT_HD int movegen(int8_t* b, int side, uint16_t* list, int16_t* out, int* in_ch
             XQT_RECONVERGE();
         }
     }
+    *flushed = nf;
     return n;
 }
 
