@@ -61,7 +61,7 @@ float xq_last_kernel_ms(xq_ctx* ctx);
 
 /* ---- K1: batched rules engine -------------------------------------------------------------
  * Replaces cy_generate_legal_moves / cy_is_in_check (cython_engine/game_core.pyx:521-555) and
- * XiangqiGame.get_legal_actions / get_state_for_nn (game.py:523-526, 618-640), one warp per board.
+ * XiangqiGame.get_legal_actions / get_state_for_nn (game.py:523-526, 618-640).
  *
  *   d_boards   [B][90]  int8
  *   d_sides    [B]      int8  (+1 / -1)
@@ -86,9 +86,10 @@ int xq_is_attacked_batch(xq_ctx* ctx, const int8_t* d_boards, const uint8_t* d_s
 int xq_is_attacked_batch_host(xq_ctx* ctx, const int8_t* h_boards, const uint8_t* h_sq, const int8_t* h_by,
                               int B, uint8_t* h_out);
 
-/* Which K1 kernel xq_movegen_batch[_host] launches: 0 = one warp per board (first generation), 1 = one thread per
- * board (csrc/xq_rules_tpb.h).  Same outputs bit for bit; returns the previous value (or < 0 on a bad argument).
- * The default can also be chosen with the environment variable XQ_MOVEGEN_IMPL=warp|thread. */
+/* Which K1 kernel xq_movegen_batch[_host] launches: 1 = one thread per board (csrc/xq_rules_tpb.h, the default),
+ * 0 = one warp per board (first generation; also the generator inside the MCTS kernels, where a warp owns a game).
+ * Same outputs bit for bit; returns the previous value (or < 0 on a bad argument).  The default can also be chosen
+ * with the environment variable XQ_MOVEGEN_IMPL=warp|thread. */
 int xq_set_movegen_impl(xq_ctx* ctx, int impl);
 
 /* overflow positions seen by movegen calls since the last reset (device counter, synchronises) */

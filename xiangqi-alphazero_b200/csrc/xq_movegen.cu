@@ -196,7 +196,6 @@ static_assert(sizeof(TpbWarpSmem) % 16 == 0 && (sizeof(uint16_t) * 32 * kTpbList
 
 struct __align__(16) TpbSmem {
     TpbWarpSmem w[kTpbWarps];
-    float4 nib_lut[16];
     uint32_t slot_tab[xqt::kSlotTableSize];   // leaper table of xq_rules_tpb.h (256 B)
 };
 
@@ -205,20 +204,23 @@ __global__ void __launch_bounds__(kTpbThreads, 6)
 movegen_tpb_kernel(const int8_t* __restrict__ boards, const int8_t* __restrict__ sides, int B,
                    int16_t* __restrict__ actions, uint8_t* __restrict__ n_moves,
                    uint8_t* __restrict__ in_check, float* __restrict__ planes, int* __restrict__ overflow,
-                   int vec_ok)
+                   int* __restrict__ task_counter, int vec_ok)
 {
     extern __shared__ __align__(16) unsigned char tpb_smem_raw[];
     TpbSmem& sm = *reinterpret_cast<TpbSmem*>(tpb_smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     TpbWarpSmem& W = sm.w[warp];
-    if (PLANES && threadIdx.x < 16)
-        sm.nib_lut[threadIdx.x] = make_float4((threadIdx.x & 1) ? 1.0f : 0.0f, (threadIdx.x & 2) ? 1.0f : 0.0f,
-                                              (threadIdx.x & 4) ? 1.0f : 0.0f, (threadIdx.x & 8) ? 1.0f : 0.0f);
     if (threadIdx.x < xqt::kSlotTableSize) sm.slot_tab[threadIdx.x] = xqt::slot_entry(threadIdx.x);
     __syncthreads();
 
     const int n_tasks = (B + 31) >> 5;
-    for (int t = blockIdx.x * kTpbWarps + warp; t < n_tasks; t += gridDim.x * kTpbWarps) {
+    // tasks are handed out dynamically (one atomic per 32 positions): positions differ in cost and a static split
+    // leaves the last wave of warps unevenly loaded
+    for (;;) {
+        int t = 0;
+        if (lane == 0) t = atomicAdd(task_counter, 1);
+        t = warp_bcast(t, 0);
+        if (t >= n_tasks) break;
         const int base = t << 5;
         const int nb = min(32, B - base);
         // the previous task's cooperative reads of W are complete for every lane before anything is overwritten
@@ -331,8 +333,16 @@ movegen_tpb_kernel(const int8_t* __restrict__ boards, const int8_t* __restrict__
                 for (int it = 0; it < 22; ++it) {
                     const int k = it * 32 + lane;
                     if (it < 21 || k < 675) {
-                        const uint32_t nib = (wp[4 * it] >> sh) & 15u;
-                        __stcs(out4 + k, sm.nib_lut[nib]);
+                        // 4 bits -> 4 floats without a table: 1.0f is 0x3f800000, so bit i of the nibble times
+                        // (0x3f800000 >> i) is the float; a 16-entry float4 table in shared memory cost 4 wavefronts
+                        // per load and a quarter of the kernel's shared-memory traffic (ncu)
+                        const uint32_t nib = wp[4 * it] >> sh;
+                        float4 v;
+                        v.x = __uint_as_float((nib & 1u) * 0x3f800000u);
+                        v.y = __uint_as_float((nib & 2u) * 0x1fc00000u);
+                        v.z = __uint_as_float((nib & 4u) * 0x0fe00000u);
+                        v.w = __uint_as_float((nib & 8u) * 0x07f00000u);
+                        __stcs(out4 + k, v);
                     }
                 }
             }
@@ -466,15 +476,15 @@ extern "C" int xq_create(int device, xq_ctx** out)
     if (const char* e = getenv("XQ_NET_TPS")) c->net_tps = atoi(e);
     if (const char* e = getenv("XQ_NET_FC4")) c->net_fc4 = atoi(e) != 0;
     if (const char* e = getenv("XQ_NET_PDL")) c->net_pdl = atoi(e) != 0;
-    if (const char* e = getenv("XQ_MOVEGEN_IMPL")) c->movegen_impl = (e[0] == 't' || e[0] == '1') ? 1 : 0;
+    if (const char* e = getenv("XQ_MOVEGEN_IMPL")) c->movegen_impl = (e[0] == 'w' || e[0] == '0') ? 0 : 1;
     XQ_CUDA(c, cudaSetDevice(device));
     cudaDeviceProp prop;
     XQ_CUDA(c, cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
     if (prop.major != 10)
         fprintf(stderr, "[xq_b200] warning: built for sm_100a, device is sm_%d%d\n", prop.major, prop.minor);
-    XQ_CUDA(c, cudaMalloc(&c->d_overflow, sizeof(int)));
-    XQ_CUDA(c, cudaMemset(c->d_overflow, 0, sizeof(int)));
+    XQ_CUDA(c, cudaMalloc(&c->d_overflow, 32 * sizeof(int)));     // [0] overflow counter, [1..16] task counters of the tpb kernel
+    XQ_CUDA(c, cudaMemset(c->d_overflow, 0, 32 * sizeof(int)));
     XQ_CUDA(c, cudaEventCreate(&c->ev0));
     XQ_CUDA(c, cudaEventCreate(&c->ev1));
     *out = c;
@@ -570,14 +580,17 @@ extern "C" int xq_movegen_batch(xq_ctx* c, const int8_t* d_boards, const int8_t*
         int grid = c->sm_count * per_sm;
         if (grid > ctas) grid = ctas;
         const int vec_ok = ((uintptr_t)d_boards & 15) == 0;
+        // one task counter per launch in flight: a small ring, zeroed on the launch's own stream
+        int* counter = c->d_overflow + 1 + (c->launches & 15);
+        XQ_CUDA(c, cudaMemsetAsync(counter, 0, sizeof(int), s));
         {
             XqTimer tm(c, s);
             if (d_planes)
                 movegen_tpb_kernel<true><<<grid, kTpbThreads, smem, s>>>(d_boards, d_sides, B, d_actions, d_n_moves,
-                                                                         d_in_check, d_planes, c->d_overflow, vec_ok);
+                                                                         d_in_check, d_planes, c->d_overflow, counter, vec_ok);
             else
                 movegen_tpb_kernel<false><<<grid, kTpbThreads, smem, s>>>(d_boards, d_sides, B, d_actions, d_n_moves,
-                                                                          d_in_check, nullptr, c->d_overflow, vec_ok);
+                                                                          d_in_check, nullptr, c->d_overflow, counter, vec_ok);
         }
         c->launches += 1;
         XQ_CUDA(c, cudaGetLastError());
