@@ -113,6 +113,7 @@ struct Scan {
     int n_ek;           // enemy knights on the board; the first two squares in ek0/ek1 (-1: none) with their
     int ek0, ek1;       // rows and columns (-100 when absent: no king square is a knight's move away)
     int ek0r, ek0c, ek1r, ek1c;
+    int n_own_kings;    // own king pieces anywhere on the board (1 in play)
     uint32_t prow[3];   // occupancy of the three rows (bit c) and
     uint32_t pcol[3];   // of the three columns (bit r) of the own palace: the only lines a king's attack test looks along
 };
@@ -125,6 +126,7 @@ XQT_HD Scan scan_board(const int8_t* b, int side)
     s.prow[0] = s.prow[1] = s.prow[2] = 0u;
     s.kmask = 0u;
     s.n_ek = 0;
+    s.n_own_kings = 0;
     s.ek0 = s.ek1 = -1;
     s.ek0r = s.ek0c = s.ek1r = s.ek1c = -100;
     const int r0 = side == 1 ? 0 : 7;
@@ -146,6 +148,7 @@ XQT_HD Scan scan_board(const int8_t* b, int side)
             rm |= nz << c;
             om |= ((p * side > 0) ? 1u : 0u) << c;
             colm[c] |= nz << r;
+            s.n_own_kings += p == side ? 1 : 0;
             if (c >= 3 && c <= 5) kings |= (p == side ? 1u : 0u) << (c - 3);
             if (p == -4 * side) {
                 if (s.n_ek == 0) { s.ek0 = r * 9 + c; s.ek0r = r; s.ek0c = c; }
@@ -266,6 +269,102 @@ XQT_HD bool attacked(const int8_t* b, const Scan& s, int r0, int pr, int pc, int
     return hit;
 }
 
+// The attack test for the common case: the own king stays on its square K0 (every move of another piece).  Everything
+// that depends only on K0 is prepared once per board: the occupancy of its row and column, for each of the (at most two)
+// enemy knights the leg square through which it would attack K0 (-1: it is not a knight's move away), and the up to
+// three squares from which an enemy pawn attacks K0 right now (-1: none there; pawn attacks cannot be blocked, only
+// captured).  Per move that leaves the two ray scans on the overlaid masks (8 cell reads), two leg reads and five
+// compares -- about half of attacked().
+struct KingCtx {
+    int kr, kc, ksq;
+    uint32_t R, C;
+    int leg0, leg1;          // leg square of enemy knight 0 / 1 against K0, or -1
+    int pw0, pw1, pw2;       // squares holding an enemy pawn that attacks K0 (behind, left, right), or -1
+};
+
+XQT_HD KingCtx king_context(const int8_t* b, const Scan& s, int r0, int pr, int pc, int by)
+{
+    KingCtx k;
+    k.kr = r0 + pr;
+    k.kc = 3 + pc;
+    k.ksq = k.kr * 9 + k.kc;
+    k.R = pr == 0 ? s.prow[0] : (pr == 1 ? s.prow[1] : s.prow[2]);
+    k.C = pc == 0 ? s.pcol[0] : (pc == 1 ? s.pcol[1] : s.pcol[2]);
+    {
+        const int dr = k.kr - s.ek0r, dc = k.kc - s.ek0c;
+        const int adr = dr < 0 ? -dr : dr, adc = dc < 0 ? -dc : dc;
+        const bool geo = (adr * adc == 2) & (adr + adc == 3);
+        k.leg0 = geo ? s.ek0 + (adr == 2 ? (dr > 0 ? 9 : -9) : (dc > 0 ? 1 : -1)) : -1;
+    }
+    {
+        const int dr = k.kr - s.ek1r, dc = k.kc - s.ek1c;
+        const int adr = dr < 0 ? -dr : dr, adc = dc < 0 ? -dc : dc;
+        const bool geo = (adr * adc == 2) & (adr + adc == 3);
+        k.leg1 = geo ? s.ek1 + (adr == 2 ? (dr > 0 ? 9 : -9) : (dc > 0 ? 1 : -1)) : -1;
+    }
+    const int pawn = 7 * by;
+    const bool back_ok = by == 1 ? k.kr >= 1 : k.kr <= 8;
+    const bool side_ok = by == 1 ? k.kr >= 5 : k.kr <= 4;
+    const int bsq = back_ok ? k.ksq - 9 * by : k.ksq, lsq = (side_ok & (k.kc >= 1)) ? k.ksq - 1 : k.ksq,
+              rsq = (side_ok & (k.kc <= 7)) ? k.ksq + 1 : k.ksq;
+    k.pw0 = b[bsq] == pawn ? bsq : -1;          // the king's own cell never holds an enemy pawn
+    k.pw1 = b[lsq] == pawn ? lsq : -1;
+    k.pw2 = b[rsq] == pawn ? rsq : -1;
+    return k;
+}
+
+XQT_HD bool attacked_fixed(const int8_t* b, const Scan& s, const KingCtx& k, int by, int fr, int fc, int tr, int tc, int to)
+{
+    const int rook = 5 * by, cannon = 6 * by, king = by;
+    const int kr = k.kr, kc = k.kc;
+    uint32_t R = k.R, C = k.C;
+    R &= ~((fr == kr ? 1u : 0u) << fc);
+    C &= ~((fc == kc ? 1u : 0u) << fr);
+    R |= (tr == kr ? 1u : 0u) << tc;
+    C |= (tc == kc ? 1u : 0u) << tr;
+    const int8_t* row = b + kr * 9;
+    const int8_t* col = b + kc;
+    bool hit = false;
+    {
+        const uint32_t m = R & ((1u << kc) - 1u);
+        const int i1 = m ? top32(m) : kc;
+        const int p1 = row[i1];
+        const uint32_t m2 = m & ~(1u << i1);
+        const int i2 = m2 ? top32(m2) : kc;
+        hit |= (p1 == rook) | (p1 == king) | (row[i2] == cannon);
+    }
+    {
+        const uint32_t m = R >> (kc + 1);
+        const int i1 = m ? kc + 1 + ctz32(m) : kc;
+        const int p1 = row[i1];
+        const uint32_t m2 = m & (m - 1u);
+        const int i2 = m2 ? kc + 1 + ctz32(m2) : kc;
+        hit |= (p1 == rook) | (p1 == king) | (row[i2] == cannon);
+    }
+    {
+        const uint32_t m = C & ((1u << kr) - 1u);
+        const int i1 = m ? top32(m) : kr;
+        const int p1 = col[i1 * 9];
+        const uint32_t m2 = m & ~(1u << i1);
+        const int i2 = m2 ? top32(m2) : kr;
+        hit |= (p1 == rook) | (p1 == king) | (col[i2 * 9] == cannon);
+    }
+    {
+        const uint32_t m = C >> (kr + 1);
+        const int i1 = m ? kr + 1 + ctz32(m) : kr;
+        const int p1 = col[i1 * 9];
+        const uint32_t m2 = m & (m - 1u);
+        const int i2 = m2 ? kr + 1 + ctz32(m2) : kr;
+        hit |= (p1 == rook) | (p1 == king) | (col[i2 * 9] == cannon);
+    }
+    // knights: still there (not the captured piece) and the leg empty on the moved board
+    hit |= (k.leg0 >= 0) & (s.ek0 != to) & (b[k.leg0 >= 0 ? k.leg0 : k.ksq] == 0);
+    hit |= (k.leg1 >= 0) & (s.ek1 != to) & (b[k.leg1 >= 0 ? k.leg1 : k.ksq] == 0);
+    // pawns: still there
+    hit |= ((k.pw0 >= 0) & (k.pw0 != to)) | ((k.pw1 >= 0) & (k.pw1 != to)) | ((k.pw2 >= 0) & (k.pw2 != to));
+    return hit;
+}
+
 // Leaper table (pyx:287-367, 434-484 orders): 8 rows x 8 slots, row = piece kind (1 king, 2 advisor, 3 elephant,
 // 4 knight, 7 red pawn; row 0 = black pawn), entry = four signed bytes {dr, dc, leg offset, square delta dr*9+dc};
 // delta == 0 marks an unused slot, leg offset == 0 a move without a leg / eye.  256 bytes of shared memory in the
@@ -350,7 +449,7 @@ XQT_HD int gen_piece(const int8_t* b, const Scan& s, int side, int from, uint16_
         const bool crossed = side == 1 ? r >= 5 : r <= 4;
         const int nsl = kind == 4 ? 8 : (kind == 7 ? (crossed ? 3 : 1) : 4);
         const uint32_t* row = tab + ((kind == 7 && side != 1) ? 0 : kind) * 8;
-        const int from7 = from << 7;
+        const int from7 = from << 7 | (kind == 1 ? 0x4000 : 0);       // bit 14 marks a king move (tested apart, see movegen)
         // b[] may be read up to 20 bytes outside the board for targets that are then discarded (the caller keeps that
         // much readable memory on both sides)
         for (int sl = 0; sl < nsl; ++sl) {
@@ -384,51 +483,65 @@ XQT_HD int movegen(int8_t* b, int side, uint16_t* list, int16_t* out, int* flush
     occ[1] = s.occR[1];
     occ[2] = s.occR[2];
     const int r0 = side == 1 ? 0 : 7;
-    {
-        const int ki = s.kmask ? ctz32(s.kmask) : 0;
-        const int kdiv = (ki * 11) >> 5;           // ki / 3 for ki < 9
-        const bool a = attacked(b, s, r0, kdiv, ki - kdiv * 3, -side, -1, 0, 0, 0, -1);
-        *in_check = (s.kmask == 0u || a) ? 1 : 0;  // pyx:552-554: no king in the palace counts as check
-    }
     int n = 0;                                     // legal moves so far
     int nf = 0;                                    // ... of which already flushed to out[]
     const int ki0 = s.kmask ? ctz32(s.kmask) : 0;
     const int pr0 = (ki0 * 11) >> 5, pc0 = ki0 - pr0 * 3;          // the king every non-king move leaves where it is
+    const KingCtx kc0 = king_context(b, s, r0, pr0, pc0, -side);
+    const bool have_king0 = s.kmask != 0u;         // no own king in the palace: every move is illegal (pyx:219-224)
+    // boards no game reaches -- several own kings, or more than two enemy knights -- get the general test for every move
+    const bool general_all = s.n_own_kings > 1 || s.n_ek > 2;
+    bool first_round = true;
+    *in_check = 1;
     uint32_t w0 = s.own[0], w1 = s.own[1], w2 = s.own[2];
     for (;;) {                                     // one round unless a board has more than kListCap - 17 pseudo-legal moves
         const int left = popc32(w0) + popc32(w1) + popc32(w2);
         const int ptrips = XQT_WARP_MAX(left);
-        if (ptrips == 0) break;
+        if (ptrips == 0 && !first_round) break;
         if (left != 0 && n > nf) {                 // another round for this board: make room
             for (int k = nf; k < n && k < kMaxOut; ++k) out[k] = (int16_t)list[k - nf];
             nf = n < kMaxOut ? n : kMaxOut;
         }
         const int m0 = n - nf;                     // staged legal ids occupy list[0 .. m0)
         int m = m0;
+        int kstart = 0, kcount = 0;                // list entries of the king's moves in this round
         for (int t = 0; t < ptrips; ++t) {
             if ((w0 | w1 | w2) != 0u && m + 17 <= kListCap) {
                 int from;
                 if (w0) { from = ctz32(w0); w0 &= w0 - 1u; }
                 else if (w1) { from = 32 + ctz32(w1); w1 &= w1 - 1u; }
                 else { from = 64 + ctz32(w2); w2 &= w2 - 1u; }
+                const int before = m;
                 m = gen_piece(b, s, side, from, list, m, tab);
+                if (b[from] == side) {
+                    kstart = before;
+                    kcount = m - before;
+                }
             }
             XQT_RECONVERGE();
         }
-        const int ltrips = XQT_WARP_MAX(m - m0);
-        int i = m0;
-        for (int t = 0; t < ltrips; ++t) {
-            if (i < m) {
-                const int mv = list[i++];
+        // General pass, all lanes together: the in-check probe of the position (first round, q = -1) and the king's
+        // moves (every board has a king with at most 4 moves).  They need the full attack test -- the king's square,
+        // lines, knights and pawns all change -- and would otherwise drag that path into nine out of ten iterations of
+        // the main loop for one or two lanes.  The verdict replaces the list entry: 0x8000 | id (legal), 0xc000 (not).
+        const int gstart = general_all ? m0 : kstart;
+        const int gcount = general_all ? m - m0 : kcount;
+        const int gtrips = XQT_WARP_MAX(gcount);
+        for (int q = first_round ? -1 : 0; q < gtrips; ++q) {
+            if (q < gcount) {
+                const bool probe = q < 0;
+                const int mv = probe ? 0 : (list[gstart + q] & 0x3fff);
                 const int from = mv >> 7, to = mv & 127;
                 const int fr = div9(from), fc = from - fr * 9, tr = div9(to), tc = to - tr * 9;
                 const int8_t mover = b[from], taken = b[to];
-                b[to] = mover;
-                b[from] = 0;
+                if (!probe) {
+                    b[to] = mover;
+                    b[from] = 0;
+                }
                 int pr = pr0, pc = pc0;
-                bool have_king = s.kmask != 0u;
-                if (mover == side) {               // a king move (targets are always inside the palace box): the king that
-                    uint32_t km = s.kmask;         // is "found" afterwards is the first one in palace order (pyx:93-98)
+                bool have_king = have_king0;
+                if (!probe && mover == side) {     // the king "found" afterwards is the first one in palace order (pyx:93-98)
+                    uint32_t km = s.kmask;
                     const int fpr = fr - r0;
                     if (fpr >= 0 && fpr <= 2 && fc >= 3 && fc <= 5) km &= ~(1u << (fpr * 3 + fc - 3));
                     km |= 1u << ((tr - r0) * 3 + tc - 3);
@@ -437,12 +550,41 @@ XQT_HD int movegen(int8_t* b, int side, uint16_t* list, int16_t* out, int* flush
                     pc = ki - pr * 3;
                     have_king = true;
                 }
-                // no own king in the palace: the probe square may hold anything, its result is discarded
-                const bool ok = !attacked(b, s, r0, pr, pc, -side, fr, fc, tr, tc, taken != 0 ? to : -1) && have_king;
-                b[from] = mover;
-                b[to] = taken;
+                const bool att = attacked(b, s, r0, pr, pc, -side, probe ? -1 : fr, fc, tr, tc, (!probe && taken != 0) ? to : -1);
+                if (probe) {
+                    *in_check = (att || !have_king0) ? 1 : 0;      // pyx:552-554: no king in the palace counts as check
+                } else {
+                    b[from] = mover;
+                    b[to] = taken;
+                    list[gstart + q] = (!att && have_king) ? (uint16_t)(0x8000 | (from * 90 + to)) : (uint16_t)0xc000;
+                }
+            }
+            XQT_RECONVERGE();
+        }
+        first_round = false;
+        const int ltrips = XQT_WARP_MAX(m - m0);
+        int i = m0;
+        for (int t = 0; t < ltrips; ++t) {
+            if (i < m) {
+                const int e = list[i++];
+                bool ok;
+                int id;
+                if (e & 0x8000) {                  // judged in the general pass
+                    ok = (e & 0x4000) == 0;
+                    id = e & 0x1fff;
+                } else {
+                    const int from = e >> 7, to = e & 127;
+                    const int fr = div9(from), fc = from - fr * 9, tr = div9(to), tc = to - tr * 9;
+                    const int8_t mover = b[from], taken = b[to];
+                    b[to] = mover;
+                    b[from] = 0;
+                    ok = !attacked_fixed(b, s, kc0, -side, fr, fc, tr, tc, to) && have_king0;
+                    b[from] = mover;
+                    b[to] = taken;
+                    id = from * 90 + to;
+                }
                 if (ok) {
-                    if (n < kMaxOut) list[n - nf] = (uint16_t)(from * 90 + to);
+                    if (n < kMaxOut) list[n - nf] = (uint16_t)id;
                     if (++n > kMaxOut) {           // overflow: stop this board (the warp-uniform loops run on, idle)
                         i = m;
                         w0 = w1 = w2 = 0u;
