@@ -329,7 +329,7 @@ movegen_tpb_kernel(const int8_t* __restrict__ boards, const int8_t* __restrict__
             for (int jp = 0; jp < npair; ++jp) {
                 float4* out4 = reinterpret_cast<float4*>(planes + (size_t)(base + 2 * jp) * (15 * kSquares));
                 const uint32_t* wp = pair_bits + jp * kPairWords + (lane >> 3);
-#pragma unroll
+#pragma unroll 2                 // not fully: the kernel is sensitive to its instruction footprint (ncu: no_instruction stalls)
                 for (int it = 0; it < 22; ++it) {
                     const int k = it * 32 + lane;
                     if (it < 21 || k < 675) {

@@ -406,7 +406,7 @@ XQT_HD int gen_piece(const int8_t* b, const Scan& s, int side, int from, uint16_
         const uint32_t Cm = bits96(s.occC[0], s.occC[1], s.occC[2], c * 10, 10);
         // pyx:42-46 order: up (row - 1), down (row + 1), left (col - 1), right (col + 1)
 #if defined(__CUDA_ARCH__)
-#pragma unroll
+#pragma unroll 1
 #endif
         for (int d = 0; d < 4; ++d) {
             const bool vertical = d < 2, neg = (d & 1) == 0;
