@@ -4,7 +4,12 @@
 // Replaces training/cython_engine/game_core.pyx (cy_generate_legal_moves :521-540,
 // cy_is_in_check :543-555, cy_is_attacked :508-518) and game.py get_state_for_nn :618-640.
 //
-// Kernel shape (HBM/instruction-bound integer work, no tensor cores):
+// Two kernel generations answer xq_movegen_batch with the same bytes (xq_set_movegen_impl):
+//   movegen_tpb_kernel (default): one THREAD per board, a warp per 32 positions; rules in xq_rules_tpb.h.
+//       915 M positions/s with planes = 78 % of the measured HBM bandwidth (profiles/r1_movegen_ncu.md).
+//   movegen_kernel: one WARP per board (rules in xq_rules.cuh, the generator the MCTS kernels use for the one
+//       game a warp owns).  419 M positions/s, bound by instruction issue at 17.5 of 32 active lanes.
+// Shape of the first generation (HBM/instruction-bound integer work, no tensor cores):
 //   - persistent CTAs (grid = SMs x resident CTAs), 8 warps, one warp per board;
 //   - boards arrive in shared memory as 64-board tiles (5760 B + 64 B of sides) through the
 //     TMA engine (cp.async.bulk + mbarrier, double buffered) so the next tile streams in
@@ -172,11 +177,13 @@ movegen_kernel(const int8_t* __restrict__ boards, const int8_t* __restrict__ sid
 }
 
 // ---- K1, second generation: one THREAD per board (rules: xq_rules_tpb.h) -----------------------------------
-// A warp takes 32 consecutive positions: their 2 880 board bytes arrive with coalesced 16-byte loads into the
-// warp's own shared-memory slice, every lane then runs the scalar generator on its board (move list built and
-// compacted in a per-lane shared-memory array), and the warp leaves the results cooperatively -- one 8-byte store
-// per lane per move list (256 B rows), the planes as bits -> float4 like the first-generation kernel, counts and
-// flags as one 32-byte row.  Warps never wait for each other: no __syncthreads after the table set-up.
+// A warp takes 32 consecutive positions (tasks are handed out by an atomic counter): their 2 880 board bytes arrive
+// with coalesced 16-byte loads into the warp's own shared-memory slice, every lane then runs the scalar generator on
+// its board (pseudo-legal list built and compacted in a 98-entry per-lane shared-memory array), and the warp leaves
+// the results cooperatively -- one 8-byte store per lane per move list (256 B rows), the planes of a PAIR of
+// positions as 675 coalesced float4 expanded from a 2 700-bit array, counts and flags as one 32-byte row.  Warps never
+// wait for each other: no __syncthreads after the table set-up.  9.3 KB of shared memory per warp and 80 registers
+// give 6 CTAs x 4 warps per SM.
 constexpr int kTpbWarps = 4;
 constexpr int kTpbThreads = kTpbWarps * 32;
 constexpr int kPairWords = 86;             // 2 x 1350 plane bits = 2700 bits = 84.4 words (+1: the last float4 group reads word 84)

@@ -9,26 +9,32 @@
 // per position, 17.5 of 32 lanes active, profiles/r1_movegen_ncu.md) -- a 90-cell board does not have
 // 32-wide parallelism in its legality tests.  Here a lane owns a whole board, so a warp advances 32
 // positions per instruction stream and the only cost of divergence is the union of the code paths the
-// 32 boards take, which the structure below keeps small:
-//   1. one unrolled 90-cell scan builds, in registers, the occupancy bitboards (row-major and
-//      column-major 96-bit sets), the own-piece set, the own kings standing in their palace and the
-//      enemy knights;
-//   2. pseudo-legal generation walks the own-piece set in square order; the five leapers (king,
-//      advisor, elephant, knight, pawn) share one table-driven path (per-kind slot word: dr, dc; the
-//      leg is (dr/2, dc/2); a per-kind box bounds the target), rook and cannon share one path in which
-//      a ray is a bit scan of the row / column occupancy (first blocker = rook capture, second =
-//      cannon capture) and only the emission of the empty run is a loop;
-//   3. ONE uniform loop tests every pseudo-legal move: make the move in place, take the own king from
-//      the palace set, run the attack test on the moved board (rays = bit scans of the king's row and
-//      column with the move overlaid on the two masks; knights = the enemy-knight list; pawns = three
-//      cells), unmake.  Facing kings need no extra clause: _is_attacked counts the enemy king as a
-//      rook on an open ray (pyx:117), which is the flying-general test of pyx:226-240.
-// The move list is compacted in place (legal count <= tested count), so the per-thread scratch is one
-// array that ends up holding the action ids the kernel copies out with coalesced stores.
+// 32 boards take, which the structure below keeps small (916 warp-instructions per position, 22 lanes):
+//   1. scan_board: one pass over the 90 cells (a row per iteration) builds, in registers, the occupancy
+//      sets (row-major and column-major 96-bit), the own-piece set, the occupancy of the three rows and
+//      columns of the own palace, the own kings standing in the palace and the enemy knights;
+//   2. gen_piece: pseudo-legal generation walks the own-piece set in square order.  The five leapers
+//      (king, advisor, elephant, knight, pawn) share one table-driven loop (4 signed bytes per slot:
+//      dr, dc, leg offset, square delta; a per-kind box bounds the target), rook and cannon share one
+//      path in which a ray is a bit scan of the row / column occupancy (first blocker = rook capture,
+//      second = cannon capture) and only the emission of the empty run is a loop;
+//   3. a GENERAL pass, all lanes together: the in-check probe of the position and the king's own moves
+//      (at most 4), with the full attack test `attacked` -- king square, lines, knights, pawns all depend
+//      on the move; the verdict replaces the list entry;
+//   4. the main loop tests every other pseudo-legal move with `attacked_fixed`: the king stays where it
+//      is, so the row / column masks, the leg square of each enemy knight and the squares of attacking
+//      pawns are prepared once per board (KingCtx) and a move costs two ray scans on the overlaid masks
+//      (8 cell reads), two leg reads and five compares.  The move is made in place on the lane's board
+//      and unmade.  Facing kings need no extra clause: _is_attacked counts the enemy king as a rook on an
+//      open ray (pyx:117), which is the flying-general test of pyx:226-240.
+// Both long loops run for the warp-wide maximum trip count with predicated bodies (XQT_WARP_MAX): with
+// per-lane trip counts the lanes of a warp drifted apart for good (9.5 of 32 lanes active).  Legal moves
+// are compacted in place into action ids, which the kernel copies out with coalesced stores.
 //
-// The file is plain C++ (no warp intrinsics): tests/test_tpb_cpu.py compiles it with g++ and checks it
-// against the oracle over random-playout and piece-soup positions, so the rules logic the kernel runs
-// is verified on the CPU build box too; the kernel wrapper is xq_movegen.cu:movegen_tpb_kernel.
+// The file is plain C++ (the two warp collectives are macros that are the identity on the host):
+// tests/test_tpb_cpu.py compiles it with g++ and checks it against the oracle over random-playout and
+// piece-soup positions, so the rules logic the kernel runs is verified on the CPU build box too; the
+// kernel wrapper is xq_movegen.cu:movegen_tpb_kernel.
 #pragma once
 #include <cstdint>
 
