@@ -269,7 +269,10 @@ def bench_movegen(args, rank, world, local_rank, dist):
                    "positions_per_gpu": N, "mean_legal_moves": n_moves_mean,
                    "l2": "outputs 5.66 GB/step >> 126 MB L2, no flush needed", "parallelism": f"games sharded x{world}, no collective"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                     "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_kind,
+                     "frac": achieved / peaks["hbm_gbs"],
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch over 1M positions (ncu --set full,
+                     # profiles/r1_movegen_ncu.md): 0.091 + 5.600 GB (thread kernel), 0.09 + 5.60 GB (warp kernel)
+                     "traffic": 5.69e9 if N == 1_000_000 else None, "peak_source": peak_kind,
                      "kernel": {"warp": "movegen_kernel<true> (one warp per board)",
                                 "thread": "movegen_tpb_kernel<true> (one thread per board)"}[eng.movegen_impl],
                      "algorithmic_bytes_per_position": ALGO_BYTES_MOVEGEN_PLANES,
