@@ -279,11 +279,13 @@ XQT_HD bool attacked(const int8_t* b, const Scan& s, int r0, int pr, int pc, int
 // that depends only on K0 is prepared once per board: the occupancy of its row and column, for each of the (at most two)
 // enemy knights the leg square through which it would attack K0 (-1: it is not a knight's move away), and the up to
 // three squares from which an enemy pawn attacks K0 right now (-1: none there; pawn attacks cannot be blocked, only
-// captured).  Per move that leaves the two ray scans on the overlaid masks (8 cell reads), two leg reads and five
-// compares -- about half of attacked().
+// captured), and the sets of enemy rooks-or-kings and cannons standing in that row and column.  Per move that leaves
+// four rays of pure bit arithmetic on the overlaid masks, two leg reads and five compares -- a third of attacked().
 struct KingCtx {
     int kr, kc, ksq;
-    uint32_t R, C;
+    uint32_t R, C;           // occupancy of K0's row (bit c) and column (bit r)
+    uint32_t rk_r, cn_r;     // enemy rooks-or-kings / cannons standing in that row ...
+    uint32_t rk_c, cn_c;     // ... and in that column
     int leg0, leg1;          // leg square of enemy knight 0 / 1 against K0, or -1
     int pw0, pw1, pw2;       // squares holding an enemy pawn that attacks K0 (behind, left, right), or -1
 };
@@ -296,6 +298,18 @@ XQT_HD KingCtx king_context(const int8_t* b, const Scan& s, int r0, int pr, int 
     k.ksq = k.kr * 9 + k.kc;
     k.R = pr == 0 ? s.prow[0] : (pr == 1 ? s.prow[1] : s.prow[2]);
     k.C = pc == 0 ? s.pcol[0] : (pc == 1 ? s.pcol[1] : s.pcol[2]);
+    const int rook = 5 * by, cannon = 6 * by, king = by;
+    k.rk_r = k.cn_r = k.rk_c = k.cn_c = 0u;
+    for (int c = 0; c < 9; ++c) {
+        const int p = b[k.kr * 9 + c];
+        k.rk_r |= ((p == rook) | (p == king) ? 1u : 0u) << c;
+        k.cn_r |= (p == cannon ? 1u : 0u) << c;
+    }
+    for (int r = 0; r < 10; ++r) {
+        const int p = b[r * 9 + k.kc];
+        k.rk_c |= ((p == rook) | (p == king) ? 1u : 0u) << r;
+        k.cn_c |= (p == cannon ? 1u : 0u) << r;
+    }
     {
         const int dr = k.kr - s.ek0r, dc = k.kc - s.ek0c;
         const int adr = dr < 0 ? -dr : dr, adc = dc < 0 ? -dc : dc;
@@ -319,50 +333,38 @@ XQT_HD KingCtx king_context(const int8_t* b, const Scan& s, int r0, int pr, int 
     return k;
 }
 
-XQT_HD bool attacked_fixed(const int8_t* b, const Scan& s, const KingCtx& k, int by, int fr, int fc, int tr, int tc, int to)
+XQT_HD uint32_t hibit(uint32_t m) { return m ? 1u << top32(m) : 0u; }   // highest set bit as a mask
+
+// b[] holds the moved board (only the two knight legs are read from it).  A ray is pure bit arithmetic: the nearest
+// occupied cell of the overlaid line attacks if it is in the rook-or-king set, the one behind it if it is in the
+// cannon set; the piece captured on `to` leaves both sets, the moved piece is not in them.
+XQT_HD bool attacked_fixed(const int8_t* b, const Scan& s, const KingCtx& k, int fr, int fc, int tr, int tc, int to)
 {
-    const int rook = 5 * by, cannon = 6 * by, king = by;
     const int kr = k.kr, kc = k.kc;
-    uint32_t R = k.R, C = k.C;
-    R &= ~((fr == kr ? 1u : 0u) << fc);
-    C &= ~((fc == kc ? 1u : 0u) << fr);
-    R |= (tr == kr ? 1u : 0u) << tc;
-    C |= (tc == kc ? 1u : 0u) << tr;
-    const int8_t* row = b + kr * 9;
-    const int8_t* col = b + kc;
-    bool hit = false;
+    const uint32_t tb_r = (tr == kr ? 1u : 0u) << tc, tb_c = (tc == kc ? 1u : 0u) << tr;
+    const uint32_t R = (k.R & ~((fr == kr ? 1u : 0u) << fc)) | tb_r;
+    const uint32_t C = (k.C & ~((fc == kc ? 1u : 0u) << fr)) | tb_c;
+    const uint32_t rk_r = k.rk_r & ~tb_r, cn_r = k.cn_r & ~tb_r, rk_c = k.rk_c & ~tb_c, cn_c = k.cn_c & ~tb_c;
+    uint32_t att = 0u;
     {
-        const uint32_t m = R & ((1u << kc) - 1u);
-        const int i1 = m ? top32(m) : kc;
-        const int p1 = row[i1];
-        const uint32_t m2 = m & ~(1u << i1);
-        const int i2 = m2 ? top32(m2) : kc;
-        hit |= (p1 == rook) | (p1 == king) | (row[i2] == cannon);
+        const uint32_t lo = R & ((1u << kc) - 1u);            // towards column 0: nearest = highest bit
+        const uint32_t f = hibit(lo);
+        att |= (f & rk_r) | (hibit(lo ^ f) & cn_r);
+        const uint32_t hi = R & ~((2u << kc) - 1u);           // towards column 8: nearest = lowest bit
+        const uint32_t g = hi & (0u - hi);
+        const uint32_t hi2 = hi ^ g;
+        att |= (g & rk_r) | (hi2 & (0u - hi2) & cn_r);
     }
     {
-        const uint32_t m = R >> (kc + 1);
-        const int i1 = m ? kc + 1 + ctz32(m) : kc;
-        const int p1 = row[i1];
-        const uint32_t m2 = m & (m - 1u);
-        const int i2 = m2 ? kc + 1 + ctz32(m2) : kc;
-        hit |= (p1 == rook) | (p1 == king) | (row[i2] == cannon);
+        const uint32_t lo = C & ((1u << kr) - 1u);
+        const uint32_t f = hibit(lo);
+        att |= (f & rk_c) | (hibit(lo ^ f) & cn_c);
+        const uint32_t hi = C & ~((2u << kr) - 1u);
+        const uint32_t g = hi & (0u - hi);
+        const uint32_t hi2 = hi ^ g;
+        att |= (g & rk_c) | (hi2 & (0u - hi2) & cn_c);
     }
-    {
-        const uint32_t m = C & ((1u << kr) - 1u);
-        const int i1 = m ? top32(m) : kr;
-        const int p1 = col[i1 * 9];
-        const uint32_t m2 = m & ~(1u << i1);
-        const int i2 = m2 ? top32(m2) : kr;
-        hit |= (p1 == rook) | (p1 == king) | (col[i2 * 9] == cannon);
-    }
-    {
-        const uint32_t m = C >> (kr + 1);
-        const int i1 = m ? kr + 1 + ctz32(m) : kr;
-        const int p1 = col[i1 * 9];
-        const uint32_t m2 = m & (m - 1u);
-        const int i2 = m2 ? kr + 1 + ctz32(m2) : kr;
-        hit |= (p1 == rook) | (p1 == king) | (col[i2 * 9] == cannon);
-    }
+    bool hit = att != 0u;
     // knights: still there (not the captured piece) and the leg empty on the moved board
     hit |= (k.leg0 >= 0) & (s.ek0 != to) & (b[k.leg0 >= 0 ? k.leg0 : k.ksq] == 0);
     hit |= (k.leg1 >= 0) & (s.ek1 != to) & (b[k.leg1 >= 0 ? k.leg1 : k.ksq] == 0);
@@ -584,7 +586,7 @@ XQT_HD int movegen(int8_t* b, int side, uint16_t* list, int16_t* out, int* flush
                     const int8_t mover = b[from], taken = b[to];
                     b[to] = mover;
                     b[from] = 0;
-                    ok = !attacked_fixed(b, s, kc0, -side, fr, fc, tr, tc, to) && have_king0;
+                    ok = !attacked_fixed(b, s, kc0, fr, fc, tr, tc, to) && have_king0;
                     b[from] = mover;
                     b[to] = taken;
                     id = from * 90 + to;
