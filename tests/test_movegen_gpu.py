@@ -206,3 +206,28 @@ def test_full_size_million_positions(eng, oracle):
     # idempotence: a second launch over the same inputs gives identical bytes
     a2, n2, c2, _ = eng.movegen(boards_t, sides_t)
     assert t.equal(a2, a) and t.equal(n2, n) and t.equal(c2, c)
+
+
+def test_output_buffers_with_minimal_alignment_and_impl_switch(eng, oracle):
+    """The C ABI asks for 8-byte aligned move / plane buffers.  A planes pointer that is 8- but not 16-byte aligned (the
+    thread-per-board kernel stores float4) must still give the same bytes, and a bad implementation id is an error."""
+    import xq_native
+    t = eng.torch
+    B = 333
+    boards, sides = oracle.random_playout_positions(31, B)
+    ea, en, ec, ep = oracle.movegen_batch(boards, sides, want_planes=True)
+    raw_p = t.zeros(B * 1350 + 2, dtype=t.float32, device=eng.dev)
+    raw_a = t.zeros(B * 128 + 4, dtype=t.int16, device=eng.dev)
+    pl = raw_p[2:].reshape(B, 15, 10, 9)
+    ac = raw_a[4:].reshape(B, 128)
+    assert pl.data_ptr() % 16 == 8 and ac.data_ptr() % 16 == 8
+    out = (ac, t.empty(B, dtype=t.uint8, device=eng.dev), t.empty(B, dtype=t.uint8, device=eng.dev), pl)
+    a, n, c, p = eng.movegen(dev(eng, boards), dev(eng, sides), planes=True, out=out)
+    t.cuda.synchronize()
+    assert np.array_equal(a.cpu().numpy(), ea) and np.array_equal(n.cpu().numpy(), en) and np.array_equal(c.cpu().numpy(), ec)
+    assert np.array_equal(p.cpu().numpy(), ep)
+    assert float(raw_p[:2].abs().sum()) == 0 and int(raw_a[:4].abs().sum()) == 0      # nothing written in front of the buffers
+    cur = eng.movegen_impl
+    with pytest.raises(xq_native.XqError):
+        eng.set_movegen_impl(7)
+    assert eng.movegen_impl == cur

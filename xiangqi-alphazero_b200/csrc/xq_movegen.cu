@@ -134,7 +134,8 @@ movegen_kernel(const int8_t* __restrict__ boards, const int8_t* __restrict__ sid
                 float* outp = planes + gi * (15 * kSquares);
                 // 1350 floats per position; positions alternate between 16-byte aligned and 8-byte offset bases:
                 // one float2 at the head (odd positions) or tail (even), 337 coalesced float4 in between
-                const int head = (int)(gi & 1) * 2;
+                // ... for a 16-byte aligned planes buffer; an 8-byte aligned one (the ABI's minimum) swaps the two cases
+                const int head = (int)((gi + ((reinterpret_cast<uintptr_t>(planes) >> 3) & 1)) & 1) * 2;
                 if (lane == 0) {
                     const uint32_t two = head ? bits[0] : bits[42] >> 4;
                     float2 v;
