@@ -25,6 +25,8 @@ extern "C" int xqt_host_movegen_batch(const int8_t* boards, const int8_t* sides,
         for (int q = 0; q < 90; ++q)
             if (((occ[q >> 5] >> (q & 31)) & 1u) != (b[q] != 0 ? 1u : 0u)) return -1 - i;
         if (std::memcmp(b, boards + (size_t)i * 90, 90) != 0) return -1 - i;   // the board must come back untouched
+        for (int q = 0; q < 32; ++q)
+            if (padded[q] != 0 || padded[32 + 90 + q] != 0) return -1 - i;         // ... and nothing written around it
         if (n > 128) { ++overflow; n = 128; }
         for (int k = 0; k < 128; ++k) actions[(size_t)i * 128 + k] = k < n ? out[k] : (int16_t)-1;
         n_moves[i] = (uint8_t)n;
