@@ -570,12 +570,11 @@ extern "C" int xq_movegen_batch(xq_ctx* c, const int8_t* d_boards, const int8_t*
     if (c->movegen_impl == 1 && (d_planes == nullptr || ((uintptr_t)d_planes & 15) == 0)) {
         // second generation: one thread per board (xq_rules_tpb.h); a planes pointer that is not 16-byte aligned takes
         // the first-generation kernel (same outputs)
-        static bool attr_set[2] = {false, false};
         const int smem = (int)sizeof(TpbSmem);
-        if (!attr_set[0]) {
+        if (!c->tpb_attr_set) {                  // per context: the attribute belongs to the context's device
             XQ_CUDA(c, cudaFuncSetAttribute(movegen_tpb_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             XQ_CUDA(c, cudaFuncSetAttribute(movegen_tpb_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            attr_set[0] = true;
+            c->tpb_attr_set = true;
         }
         int per_sm = 0;
         if (d_planes)

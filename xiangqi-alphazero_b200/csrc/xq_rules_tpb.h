@@ -23,9 +23,10 @@
 //      on the move; the verdict replaces the list entry;
 //   4. the main loop tests every other pseudo-legal move with `attacked_fixed`: the king stays where it
 //      is, so the row / column masks, the leg square of each enemy knight and the squares of attacking
-//      pawns are prepared once per board (KingCtx) and a move costs two ray scans on the overlaid masks
-//      (8 cell reads), two leg reads and five compares.  The move is made in place on the lane's board
-//      and unmade.  Facing kings need no extra clause: _is_attacked counts the enemy king as a rook on an
+//      pawns and the rook / king / cannon sets of the two lines are prepared once per board (KingCtx) and a
+//      move costs four rays of bit arithmetic on the overlaid masks, two leg reads and five compares; the
+//      board is not touched (only the general pass makes and unmakes its moves in place).  Facing kings need
+//      no extra clause: _is_attacked counts the enemy king as a rook on an
 //      open ray (pyx:117), which is the flying-general test of pyx:226-240.
 // Both long loops run for the warp-wide maximum trip count with predicated bodies (XQT_WARP_MAX): with
 // per-lane trip counts the lanes of a warp drifted apart for good (9.5 of 32 lanes active).  Legal moves
@@ -120,6 +121,7 @@ struct Scan {
     int ek0, ek1;       // rows and columns (-100 when absent: no king square is a knight's move away)
     int ek0r, ek0c, ek1r, ek1c;
     int n_own_kings;    // own king pieces anywhere on the board (1 in play)
+    int n_own_knights;  // own knights (each takes two generation steps of four slots)
     uint32_t prow[3];   // occupancy of the three rows (bit c) and
     uint32_t pcol[3];   // of the three columns (bit r) of the own palace: the only lines a king's attack test looks along
 };
@@ -133,6 +135,7 @@ XQT_HD Scan scan_board(const int8_t* b, int side)
     s.kmask = 0u;
     s.n_ek = 0;
     s.n_own_kings = 0;
+    s.n_own_knights = 0;
     s.ek0 = s.ek1 = -1;
     s.ek0r = s.ek0c = s.ek1r = s.ek1c = -100;
     const int r0 = side == 1 ? 0 : 7;
@@ -155,6 +158,7 @@ XQT_HD Scan scan_board(const int8_t* b, int side)
             om |= ((p * side > 0) ? 1u : 0u) << c;
             colm[c] |= nz << r;
             s.n_own_kings += p == side ? 1 : 0;
+            s.n_own_knights += p == 4 * side ? 1 : 0;
             if (c >= 3 && c <= 5) kings |= (p == side ? 1u : 0u) << (c - 3);
             if (p == -4 * side) {
                 if (s.n_ek == 0) { s.ek0 = r * 9 + c; s.ek0r = r; s.ek0c = c; }
@@ -335,10 +339,11 @@ XQT_HD KingCtx king_context(const int8_t* b, const Scan& s, int r0, int pr, int 
 
 XQT_HD uint32_t hibit(uint32_t m) { return m ? 1u << top32(m) : 0u; }   // highest set bit as a mask
 
-// b[] holds the moved board (only the two knight legs are read from it).  A ray is pure bit arithmetic: the nearest
-// occupied cell of the overlaid line attacks if it is in the rook-or-king set, the one behind it if it is in the
-// cannon set; the piece captured on `to` leaves both sets, the moved piece is not in them.
-XQT_HD bool attacked_fixed(const int8_t* b, const Scan& s, const KingCtx& k, int fr, int fc, int tr, int tc, int to)
+// b[] is the UN-moved board: the move from -> to is overlaid, nothing is written (only the two knight legs are read).
+// A ray is pure bit arithmetic: the nearest occupied cell of the overlaid line attacks if it is in the rook-or-king
+// set, the one behind it if it is in the cannon set; the piece captured on `to` leaves both sets, the moved piece is
+// not in them.
+XQT_HD bool attacked_fixed(const int8_t* b, const Scan& s, const KingCtx& k, int from, int fr, int fc, int to, int tr, int tc)
 {
     const int kr = k.kr, kc = k.kc;
     const uint32_t tb_r = (tr == kr ? 1u : 0u) << tc, tb_c = (tc == kc ? 1u : 0u) << tr;
@@ -365,9 +370,11 @@ XQT_HD bool attacked_fixed(const int8_t* b, const Scan& s, const KingCtx& k, int
         att |= (g & rk_c) | (hi2 & (0u - hi2) & cn_c);
     }
     bool hit = att != 0u;
-    // knights: still there (not the captured piece) and the leg empty on the moved board
-    hit |= (k.leg0 >= 0) & (s.ek0 != to) & (b[k.leg0 >= 0 ? k.leg0 : k.ksq] == 0);
-    hit |= (k.leg1 >= 0) & (s.ek1 != to) & (b[k.leg1 >= 0 ? k.leg1 : k.ksq] == 0);
+    // knights: still there (not the captured piece) and the leg empty after the move (vacated by it, or empty before and
+    // not landed on)
+    const bool e0 = (k.leg0 == from) | ((k.leg0 != to) & (b[k.leg0 >= 0 ? k.leg0 : k.ksq] == 0));
+    const bool e1 = (k.leg1 == from) | ((k.leg1 != to) & (b[k.leg1 >= 0 ? k.leg1 : k.ksq] == 0));
+    hit |= ((k.leg0 >= 0) & (s.ek0 != to) & e0) | ((k.leg1 >= 0) & (s.ek1 != to) & e1);
     // pawns: still there
     hit |= ((k.pw0 >= 0) & (k.pw0 != to)) | ((k.pw1 >= 0) & (k.pw1 != to)) | ((k.pw2 >= 0) & (k.pw2 != to));
     return hit;
@@ -404,7 +411,7 @@ XQT_HD uint32_t slot_entry(int idx)
 // Pseudo-legal targets of the piece on `from` appended to list[m...] as from << 7 | to; returns the new m.
 // Two sections (sliders / leapers), each straight-line with predicated stores: the lanes of a warp that are in the same
 // section stay together.
-XQT_HD int gen_piece(const int8_t* b, const Scan& s, int side, int from, uint16_t* list, int m, const uint32_t* tab)
+XQT_HD int gen_piece(const int8_t* b, const Scan& s, int side, int from, int slot0, uint16_t* list, int m, const uint32_t* tab)
 {
     const int p = b[from];
     const int kind = p < 0 ? -p : p;
@@ -455,8 +462,10 @@ XQT_HD int gen_piece(const int8_t* b, const Scan& s, int side, int from, uint16_
         const int rspan = palace ? 2 : (kind == 3 ? 4 : 9);          // target rows rlo .. rlo + rspan
         const int clo = palace ? 3 : 0, cspan = palace ? 2 : 8;
         const bool crossed = side == 1 ? r >= 5 : r <= 4;
-        const int nsl = kind == 4 ? 8 : (kind == 7 ? (crossed ? 3 : 1) : 4);
-        const uint32_t* row = tab + ((kind == 7 && side != 1) ? 0 : kind) * 8;
+        // four slots per call: a knight's eight come in two calls (slot0 = 0, then 4), so that the slot loop of a warp
+        // never runs its second half for the knights alone
+        const int nsl = kind == 7 ? (crossed ? 3 : 1) : 4;
+        const uint32_t* row = tab + ((kind == 7 && side != 1) ? 0 : kind) * 8 + slot0;
         const int from7 = from << 7 | (kind == 1 ? 0x4000 : 0);       // bit 14 marks a king move (tested apart, see movegen)
         // b[] may be read up to 20 bytes outside the board for targets that are then discarded (the caller keeps that
         // much readable memory on both sides)
@@ -500,11 +509,12 @@ XQT_HD int movegen(int8_t* b, int side, uint16_t* list, int16_t* out, int* flush
     // boards no game reaches -- several own kings, or more than two enemy knights -- get the general test for every move
     const bool general_all = s.n_own_kings > 1 || s.n_ek > 2;
     bool first_round = true;
+    bool knight_half = false;                      // the knight on top of the set has had its first four slots
     *in_check = 1;
     uint32_t w0 = s.own[0], w1 = s.own[1], w2 = s.own[2];
     for (;;) {                                     // one round unless a board has more than kListCap - 17 pseudo-legal moves
         const int left = popc32(w0) + popc32(w1) + popc32(w2);
-        const int ptrips = XQT_WARP_MAX(left);
+        const int ptrips = XQT_WARP_MAX(left != 0 ? left + s.n_own_knights : 0);   // generation steps: one per piece, two per knight
         if (ptrips == 0 && !first_round) break;
         if (left != 0 && n > nf) {                 // another round for this board: make room
             for (int k = nf; k < n && k < kMaxOut; ++k) out[k] = (int16_t)list[k - nf];
@@ -515,12 +525,17 @@ XQT_HD int movegen(int8_t* b, int side, uint16_t* list, int16_t* out, int* flush
         int kstart = 0, kcount = 0;                // list entries of the king's moves in this round
         for (int t = 0; t < ptrips; ++t) {
             if ((w0 | w1 | w2) != 0u && m + 17 <= kListCap) {
-                int from;
-                if (w0) { from = ctz32(w0); w0 &= w0 - 1u; }
-                else if (w1) { from = 32 + ctz32(w1); w1 &= w1 - 1u; }
-                else { from = 64 + ctz32(w2); w2 &= w2 - 1u; }
+                const int from = w0 ? ctz32(w0) : (w1 ? 32 + ctz32(w1) : 64 + ctz32(w2));
+                const bool knight = b[from] == 4 * side;
+                const int slot0 = (knight && knight_half) ? 4 : 0;
+                knight_half = knight && !knight_half;          // a knight stays in the set for its second step
+                if (!knight_half) {
+                    if (w0) w0 &= w0 - 1u;
+                    else if (w1) w1 &= w1 - 1u;
+                    else w2 &= w2 - 1u;
+                }
                 const int before = m;
-                m = gen_piece(b, s, side, from, list, m, tab);
+                m = gen_piece(b, s, side, from, slot0, list, m, tab);
                 if (b[from] == side) {
                     kstart = before;
                     kcount = m - before;
@@ -583,12 +598,7 @@ XQT_HD int movegen(int8_t* b, int side, uint16_t* list, int16_t* out, int* flush
                 } else {
                     const int from = e >> 7, to = e & 127;
                     const int fr = div9(from), fc = from - fr * 9, tr = div9(to), tc = to - tr * 9;
-                    const int8_t mover = b[from], taken = b[to];
-                    b[to] = mover;
-                    b[from] = 0;
-                    ok = !attacked_fixed(b, s, kc0, fr, fc, tr, tc, to) && have_king0;
-                    b[from] = mover;
-                    b[to] = taken;
+                    ok = !attacked_fixed(b, s, kc0, from, fr, fc, to, tr, tc) && have_king0;    // overlay: the board is not touched
                     id = from * 90 + to;
                 }
                 if (ok) {
