@@ -17,8 +17,10 @@ A "step" is one pass of the hot path over one batch of synthetic input already r
 HBM.  `value` is device-timed (CUDA events, barrier + synchronize on both sides, max over
 ranks); `e2e` is the same work through the host-buffer C-ABI call (pinned host buffers, H2D and
 D2H inside the timed region).  `--impl reference` times the reference's CPU implementation
-(oracle/_ref = the reference's Cython engine compiled as-is, else the C oracle port) on the
-host cores; it is the only mode that executes anything under oracle/ besides `cpu_baseline`.
+on the host cores: for self-play the UNMODIFIED reference (baseline/_ref/training, a git-ignored mirror
+of the reference's training/ directory: parallel_self_play() in CPU mode, bench_reference.py), for movegen the
+reference's Cython engine compiled as-is (oracle/_ref); the C oracle port is the fallback and a cross-check key.
+It is the only mode that executes anything under oracle/ besides `cpu_baseline`.
 """
 import argparse
 import json
@@ -34,6 +36,14 @@ sys.path.insert(0, PKG)
 
 ALGO_BYTES_MOVEGEN_PLANES = 5563.4   # 90+1 read, 1+1+2*35.2 + 5400 written per position
 POSITIONS_PER_GPU = 1_000_000
+
+
+def movegen_config(world):
+    """`config` of the movegen line: identical in the GPU arm and in --impl reference."""
+    return {"workload": "movegen: configs[1], ordered legal moves + in-check + fp32 planes over 1M "
+                        "device-generated random-playout positions per GPU",
+            "positions_per_gpu": POSITIONS_PER_GPU,
+            "l2": "outputs 5.66 GB/step >> 126 MB L2, no flush needed", "parallelism": f"games sharded x{world}, no collective"}
 
 
 def log(*a):
@@ -165,8 +175,7 @@ def run_reference_arm(args):
         "impl": "reference", "metric": "legal_move_positions_per_sec", "value": value, "unit": "positions/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8", "data": "synthetic",
-        "config": {"workload": "movegen: configs[1], legal moves + in-check over random-playout positions",
-                   "positions_per_step": n},
+        "config": movegen_config(int(os.environ.get("WORLD_SIZE", str(args.gpus)))),
         "cpu_baseline": {"value": value, "unit": "positions/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "positions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -264,10 +273,7 @@ def bench_movegen(args, rank, world, local_rank, dist):
         "metric": "legal_move_positions_per_sec", "value": value, "unit": "positions/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int8", "data": "synthetic",
-        "config": {"workload": "movegen: configs[1], ordered legal moves + in-check + fp32 planes over 1M "
-                               "device-generated random-playout positions per GPU",
-                   "positions_per_gpu": N, "mean_legal_moves": n_moves_mean,
-                   "l2": "outputs 5.66 GB/step >> 126 MB L2, no flush needed", "parallelism": f"games sharded x{world}, no collective"},
+        "config": movegen_config(world), "mean_legal_moves": n_moves_mean,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved / peaks["hbm_gbs"],
                      # dram__bytes_read.sum + dram__bytes_write.sum of one launch over 1M positions (ncu --set full,

@@ -31,6 +31,19 @@ FLOPS_PER_EVAL = flops_per_eval(CHANNELS, BLOCKS)
 assert flops_per_eval(128, 6) == 369_193_216 and flops_per_eval(256, 20) == 4_301_360_896
 
 
+def workload_config(world, games=None, sims=None):
+    """`config` of the JSON line: a pure function of the workload and N, printed identically by the GPU arm and by
+    --impl reference (the driver compares the two)."""
+    games = GAMES_PER_GPU if games is None else games
+    sims = SIMS if sims is None else sims
+    name = "configs[3] (32768 games over 8 GPUs = 4096 per GPU)" if (CHANNELS, BLOCKS) == (256, 20) else "configs[2]"
+    return {"workload": f"selfplay: {name}, {games} concurrent games/GPU x {sims} sims/move, XiangqiNet({CHANNELS},{BLOCKS}), "
+                        f"c_puct 1.5, Dirichlet(0.3) root noise, step = one ply of every game",
+            "games_per_gpu": games, "sims_per_move": sims,
+            "l2": "per-step working set (trees + activations, > 1 GB) >> 126 MB L2",
+            "parallelism": f"games sharded x{world}, no collective in self-play"}
+
+
 class StdConfig:
     """standard_train preset of the reference (train.py:677-689) for the self-play keys."""
     num_simulations = SIMS
@@ -181,16 +194,15 @@ def run(args, rank, world, local_rank, dist):
     conv_traffic = {(128, 4096): 182.6e6, (256, 4096): None}.get((CHANNELS, games))
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_selfplay_rate(os.cpu_count() or 1, sims=min(sims, 100))
+        cpu, why = reference_selfplay_rate(steps=1, warmup=1, sims=sims, plies=1)
+        if cpu is None:
+            cpu = cpu_selfplay_rate(os.cpu_count() or 1, sims=min(sims, 100))
+            cpu["fallback_reason"] = str(why)[:300]
     line = {
         "metric": "mcts_sims_per_sec", "value": value, "unit": "sims/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic (seeded random-init weights, self-generated games)",
-        "config": {"workload": f"selfplay: {'configs[3] (32768 games over 8 GPUs = 4096 per GPU)' if (CHANNELS, BLOCKS) == (256, 20) else 'configs[2]'}, {games} concurrent games/GPU x {sims} sims/move, "
-                               f"XiangqiNet({CHANNELS},{BLOCKS}), c_puct 1.5, Dirichlet(0.3) root noise, step = one ply of every game",
-                   "games_per_gpu": games, "sims_per_move": sims, "evals_in_region": evals_done,
-                   "l2": "per-step working set (trees + activations, > 1 GB) >> 126 MB L2",
-                   "parallelism": f"games sharded x{world}, no collective in self-play"},
+        "config": workload_config(world, games, sims), "evals_in_region": evals_done,
         "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": achieved_tf / peak_tf,
                      "traffic": conv_traffic,
@@ -284,6 +296,8 @@ def _cpu_sample_text(procs, sims, wall):
 
 
 def cpu_selfplay_rate(procs, sims=100, pool=None):
+    """The oracle PORT of the CPU path (C search of oracle/xq_oracle.c + a re-declared fp32 torch net): cross-check
+    of the reference figure, and the fallback when baseline/_ref is absent."""
     import multiprocessing as mp
     own = pool is None
     if own:
@@ -301,29 +315,61 @@ def cpu_selfplay_rate(procs, sims=100, pool=None):
     return {"value": rate, "unit": "sims/s", "cores": procs, "kind": "port", "sample": _cpu_sample_text(procs, sims, wall)}
 
 
+def reference_selfplay_rate(steps=1, warmup=1, sims=SIMS, plies=1):
+    """The reference ITSELF: baseline/_ref/training/parallel_selfplay.parallel_self_play in CPU mode, run by
+    bench_reference.py in a clean process.  Returns the cpu_baseline object (kind "reference") and the raw record,
+    or (None, why) when baseline/_ref is not there."""
+    import subprocess
+    cmd = [sys.executable, os.path.join(ROOT, "bench_reference.py"), "selfplay", "--steps", str(steps), "--warmup", str(warmup),
+           "--sims", str(sims), "--plies", str(plies), "--channels", str(CHANNELS), "--blocks", str(BLOCKS)]
+    env = {k: v for k, v in os.environ.items() if k not in ("PYTHONPATH",)}
+    out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, cwd=ROOT)
+    rec = None
+    for ln in out.stdout.splitlines()[::-1]:
+        if ln.startswith("{"):
+            rec = json.loads(ln)
+            break
+    if out.returncode != 0 or rec is None or "unavailable" in rec or not rec.get("sims_total"):
+        return None, (rec or {}).get("unavailable") or ("bench_reference.py failed: " + out.stderr[-300:].replace("\n", " | "))
+    cpu = {"value": rec["sims_per_s"], "unit": "sims/s", "cores": rec["cores"], "kind": "reference",
+           "workers": rec["workers"], "value_including_pool_startup": rec["sims_per_s_raw"],
+           "pool_startup_s": rec["startup_median_s"],
+           "sample": (f"unmodified {rec['module']} parallel_self_play() CPU mode: {rec['workers']} spawned workers "
+                      f"(cpu_count-1 of {rec['cores']} cores, 1 torch thread each), one game per worker truncated to "
+                      f"max_game_length={plies} ply from the start position (random_opening_moves=0), {sims} sims/move, "
+                      f"Dirichlet noise on, XiangqiNet({CHANNELS},{BLOCKS}) fp32, Cython rules engine; {len(rec['steps'])} call(s), "
+                      f"{rec['wall_total_s']:.1f} s wall; value = plies x sims / (wall - {rec['startup_median_s']:.1f} s pool "
+                      f"start-up measured by the same call with a 0-ply budget)")}
+    return cpu, rec
+
+
 def run_reference(args):
     import bench
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    procs = os.cpu_count() or 1
-    import multiprocessing as mp
-    vals = []
-    last = None
-    with mp.get_context("spawn").Pool(procs) as pool:
-        pool.map(_cpu_worker, [(2, i) for i in range(procs)])               # worker start-up outside every timed step
-        for i in range(args.warmup + args.steps):
-            last = cpu_selfplay_rate(procs, sims=REF_SIMS, pool=pool)
-            if i >= args.warmup:
-                vals.append(last["value"])
-    value = sum(vals) / len(vals)
-    last["value"] = value
+    sims = int(os.environ.get("XQ_BENCH_SIMS", SIMS))
+    games = int(os.environ.get("XQ_BENCH_GAMES", GAMES_PER_GPU))
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    cpu, rec = reference_selfplay_rate(steps=args.steps, warmup=max(1, args.warmup), sims=sims, plies=1)
+    if cpu is None:                                   # baseline/_ref did not travel: fall back to the port, and say so
+        procs = os.cpu_count() or 1
+        cpu = cpu_selfplay_rate(procs, sims=REF_SIMS)
+        cpu["fallback_reason"] = str(rec)[:300]
+        ms = 1e3 * procs * REF_SIMS / cpu["value"]
+    else:
+        ms = 1e3 * rec["wall_total_s"] / max(1, len(rec["steps"]))
+        try:                                          # cross-check key: the oracle port on the same cores
+            port = cpu_selfplay_rate(os.cpu_count() or 1, sims=100)
+            cpu["port_cross_check"] = {"value": port["value"], "sample": port["sample"]}
+        except Exception as ex:
+            cpu["port_cross_check"] = {"error": str(ex)[:200]}
+    value = cpu["value"]
     line = {"impl": "reference", "metric": "mcts_sims_per_sec", "value": value, "unit": "sims/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * procs * REF_SIMS / value, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic (seeded random-init weights)",
-            "config": {"workload": f"selfplay: configs[2] on host cores, XiangqiNet({CHANNELS},{BLOCKS}), one search of {REF_SIMS} "
-                                   f"simulations per process per step, {procs} processes"},
-            "cpu_baseline": last,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic (seeded random-init weights, self-generated games)",
+            "config": workload_config(world, games, sims),
+            "cpu_baseline": cpu,
             "e2e": {"value": value, "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     bench.emit(line)
