@@ -129,8 +129,7 @@ int xq_mcts_set_games(xq_ctx* ctx, int n_games, const int8_t* d_boards, const in
 
 /* Evaluator inputs of the roots / of the current leaves; every output pointer is optional:
  *   d_planes [G][15][10][9] float32 (get_state_for_nn); d_x_planes = input planes of xq_net_gemm
- *   (bf16 [2][x_rows][8], cell (r,c) of game g at plane row x_row0 + g*110 + (r+1)*10 + c, halo rows
- *   are never written and must be zero); d_boards_out [G][90] + d_sides_out [G]. */
+ *   (bf16 [2][x_rows][8], cell (r,c) of game g at plane row x_row0 + g*90 + r*9 + c); d_boards_out [G][90] + d_sides_out [G]. */
 int xq_mcts_root_begin(xq_ctx* ctx, float* d_planes, void* d_x_planes, long long x_rows, long long x_row0,
                        int8_t* d_boards_out, int8_t* d_sides_out, void* stream);
 /* mcts.py:110-123: mask + normalise the root policy, optional Dirichlet mixing 0.75 P + 0.25 eta.
@@ -157,16 +156,19 @@ int xq_mcts_stats(xq_ctx* ctx, long long* h_stats6, int reset);
 
 /* ---- K3: ResNet policy-value forward (bf16 tcgen05/TMA implicit GEMM) ---------------------------
  * Replaces XiangqiNet.forward on the inference path (model.py:87-124): every conv / linear layer
- * is one xq_net_gemm launch over "channel-chunk plane" tensors (layout: csrc/xq_net.cu), BatchNorm
+ * is one xq_net_gemm launch over "channel-chunk plane" tensors (layout: csrc/xq_net.cu; cell (r,c) of
+ * board b at plane row row0 + b*90 + r*9 + c, no halo rows: off-board taps are masked inside the MMAs), BatchNorm
  * folded into weights + bias by the host (eval mode).  The host builds the descriptors once
  * (xiangqi-alphazero_b200/model.py, class B200Net) and replays them with xq_net_run.
  *
  *   mode 0  3x3 conv: out = act(conv(a) + bias [+ residual]); a/out/residual are plane tensors
- *           [chunk][rows][8] bf16 with logical row m at plane row row0+m (row0 >= 16)
+ *           [chunk][rows][8] bf16 with logical row m at plane row row0+m (row0 >= 10; the buffer must
+ *           extend 10 rows past the last 256-row tile pair)
  *   mode 1  1x1 policy/value head conv (nt = 48: 32 policy + 4 value channels + padding):
  *           out = FC input planes [360][out_rows][8] bf16, out2 = value features [B][90][4] fp32
  *   mode 2  dense layer: a = planes [K/8][a_rows][8], out = row-major bf16 [B][out_stride] logits
- * w = weight image [n_tile][tap][k_block][chunk][nt][8] bf16, bias fp32 [n_tiles*nt].
+ * w = weight image [n_tile][tap][k_block][chunk][nt][8] bf16 (3x3: tap 0 = centre, then the other 8 taps
+ * row-major), bias fp32 [n_tiles*nt].
  */
 typedef struct xq_gemm_desc {
     int32_t mode;
@@ -186,8 +188,6 @@ typedef struct xq_gemm_desc {
     const void* residual; /* mode 0 only, may be NULL */
     void* out;
     void* out2;           /* mode 1 only */
-    const void* w_half;   /* mode 0, optional: the same weights tiled by 64 output channels
-                             [n_tile64][tap][k_block][chunk][64][8] for the cta_group::2 kernel (NULL: not used) */
 } xq_gemm_desc;
 
 int xq_net_gemm(xq_ctx* ctx, const xq_gemm_desc* desc, void* stream);
@@ -195,7 +195,8 @@ int xq_net_gemm(xq_ctx* ctx, const xq_gemm_desc* desc, void* stream);
  * d_w1t [360][128] fp32 with k = pos*4 + ch. */
 int xq_net_value_head(xq_ctx* ctx, const float* d_feats, const float* d_w1t, const float* d_b1,
                       const float* d_w2, float b2, float* d_value, int B, void* stream);
-/* all layers of one forward + the value head, one call */
+/* all layers of one forward + the value head for the first B boards (B <= the descriptors' n_boards: every
+ * launch is sized to B), one call */
 int xq_net_run(xq_ctx* ctx, const xq_gemm_desc* layers, int n_layers, const float* d_vfeats,
                const float* d_w1t, const float* d_b1, const float* d_w2, float b2, float* d_value, int B,
                void* stream);

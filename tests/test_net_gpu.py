@@ -56,9 +56,8 @@ def test_layer_by_layer(eng, oracle, n):
         torch.cuda.synchronize()
         got = net.planes_to_nchw(net.act[0], n)
         assert rel(got, ref) < 5e-3, ("input conv", rel(got, ref))
-        # halo rows/cols of the output plane must be exactly zero (they are the next layer's padding)
-        full = net.act[0][:, 16:16 + n * 110].permute(1, 0, 2).reshape(n, 11, 10, 128).float()
-        assert float(full[:, 0].abs().max()) == 0.0 and float(full[:, :, 9].abs().max()) == 0.0
+        # rows past the last board are never written (no halo in the plane layout: off-board taps are masked in the MMAs)
+        assert float(net.act[0][:, 16 + n * 90:].float().abs().max()) == 0.0
         cur = 0
         li = 1
         for blk in mg.res_blocks:

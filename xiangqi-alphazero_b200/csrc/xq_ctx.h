@@ -28,12 +28,6 @@ struct xq_ctx {
     int movegen_impl = 1;                 // XQ_MOVEGEN_IMPL=thread|warp: K1 kernel generation (1 = one thread per board, the default: 2x the
                                           // positions/s of the one-warp-per-board kernel, same bytes out)
     bool tpb_attr_set = false;            // dynamic shared-memory limit of movegen_tpb_kernel raised on this context's device
-    bool net_pdl = false;                 // XQ_NET_PDL=1: programmatic dependent launch between layers (measured: no gain, off by default)
-    bool net_fc4 = true;                  // XQ_NET_FC4=0: first-generation FC kernel
-    int net_tps = 3;                      // XQ_NET_TPS=1: one tap per weight stage in the 128-channel conv
-    int net_gen = 4;                      // XQ_NET_GEN=2: previous conv kernel generation (A/B comparisons)
-    int net_cluster = 1;                  // XQ_NET_CLUSTER=1|2|4: CTAs per cluster sharing each weight stage by TMA multicast
-    bool net_v1 = false;                  // XQ_NET_V1=1: use the first-generation conv kernel (A/B comparisons)
 };
 
 extern char g_xq_last_error[512];

@@ -123,8 +123,7 @@ __device__ __forceinline__ void warp_emit_eval_inputs(const int8_t* b, int side,
             uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             if (ch >= 0) w[ch >> 1] = one << ((ch & 1) * 16);
             if (side == 1) w[7] |= one;   // channel 14 = low half of word 7; channel 15 is padding
-            const int r = sq / 9, c = sq - r * 9;
-            const size_t row = (size_t)(x_row0 + (long long)g * 110 + (r + 1) * 10 + c);
+            const size_t row = (size_t)(x_row0 + (long long)g * 90 + sq);
             uint4* p0 = reinterpret_cast<uint4*>(x_planes + row * 8);
             uint4* p1 = reinterpret_cast<uint4*>(x_planes + ((size_t)x_rows + row) * 8);
             *p0 = make_uint4(w[0], w[1], w[2], w[3]);

@@ -478,12 +478,6 @@ extern "C" int xq_create(int device, xq_ctx** out)
     if (device < 0 || device >= n) return xq_fail(nullptr, XQ_ERR_ARG, "xq_create: device %d out of range", device);
     xq_ctx* c = new xq_ctx();
     c->device = device;
-    c->net_v1 = getenv("XQ_NET_V1") != nullptr;
-    if (const char* e = getenv("XQ_NET_CLUSTER")) c->net_cluster = atoi(e);
-    if (const char* e = getenv("XQ_NET_GEN")) c->net_gen = atoi(e);
-    if (const char* e = getenv("XQ_NET_TPS")) c->net_tps = atoi(e);
-    if (const char* e = getenv("XQ_NET_FC4")) c->net_fc4 = atoi(e) != 0;
-    if (const char* e = getenv("XQ_NET_PDL")) c->net_pdl = atoi(e) != 0;
     if (const char* e = getenv("XQ_MOVEGEN_IMPL")) c->movegen_impl = (e[0] == 'w' || e[0] == '0') ? 0 : 1;
     XQ_CUDA(c, cudaSetDevice(device));
     cudaDeviceProp prop;

@@ -91,10 +91,12 @@ class _GemmDesc(C.Structure):
                 ("kchunks", C.c_int32), ("kch_iter", C.c_int32), ("relu", C.c_int32), ("n_boards", C.c_int32),
                 ("a_rows", C.c_int64), ("a_row0", C.c_int64), ("out_rows", C.c_int64), ("out_row0", C.c_int64),
                 ("out_stride", C.c_int64), ("a", C.c_void_p), ("w", C.c_void_p), ("bias", C.c_void_p),
-                ("residual", C.c_void_p), ("out", C.c_void_p), ("out2", C.c_void_p), ("w_half", C.c_void_p)]
+                ("residual", C.c_void_p), ("out", C.c_void_p), ("out2", C.c_void_p)]
 
 
-ROW0 = 16            # plane row of logical row 0 (front padding, >= 11 halo rows)
+ROW0 = 16            # plane row of logical row 0 (front padding, >= 10 rows: the A block of the first tile starts 10 rows early)
+BOARD_ROWS = 90      # plane rows per board: cell (r, c) of board b at row ROW0 + b*90 + r*9 + c, no halo (csrc/xq_net.cu)
+TAP_ORDER = [4, 0, 1, 2, 3, 5, 6, 7, 8]   # weight-image tap k -> 3x3 cell kh*3+kw: the (unmasked) centre tap is issued first
 LOGIT_STRIDE = 8192  # 8100 padded to 64 tiles of 128
 
 
@@ -115,6 +117,8 @@ def conv_image(w, nt, kch_iter):
     wp[:co, :ci] = w
     taps = kh * kw
     x = wp.permute(2, 3, 0, 1).reshape(taps, co_pad, ci_pad)                 # [tap][co][ci]
+    if taps == 9:
+        x = x[TAP_ORDER]
     x = x.reshape(taps, co_pad // nt, nt, ci_pad // (8 * kch_iter), kch_iter, 8)  # [tap][ntile][n][kb][chunk][8]
     x = x.permute(1, 0, 3, 4, 2, 5).contiguous()                             # [ntile][tap][kb][chunk][n][8]
     return x.to(torch.bfloat16)
@@ -135,9 +139,9 @@ class B200Net:
         Cc = (Cm + 127) // 128 * 128
         self.C, self.R, self.C_model = Cc, R, Cm
         B = self.max_batch
-        self.m_tiles = (B * 110 + 127) // 128
+        self.m_tiles = (B * BOARD_ROWS + 127) // 128
         pairs = (self.m_tiles + 1) // 2                            # conv kernels work on pairs of 128-row tiles,
-        self.rows = ROW0 + ((pairs + 3) // 4) * 4 * 256 + 16       # clusters of up to 4 CTAs on 4 consecutive pairs
+        self.rows = ROW0 + pairs * 256 + 16                        # + the 10 rows the last pair's A block reads past its end
         self.b_tiles = (B + 127) // 128
         self.fc_rows = ((self.b_tiles + 1) // 2) * 256               # the FC kernel works on pairs of 128-board tiles
         bf = torch.bfloat16
@@ -171,13 +175,12 @@ class B200Net:
         def conv_layer(w, b, a_buf, out_buf, residual, relu, kch_iter):
             w, b = pad_channels(w, b, Cc, w.shape[1] if w.shape[1] == 15 else Cc)
             img = dev_t(conv_image(w, 128, kch_iter))
-            img64 = dev_t(conv_image(w, 64, kch_iter)) if kch_iter == 8 else None   # halves of N for the CTA-pair kernel
             bias = dev_t(b, torch.float32)
             d = _GemmDesc(mode=0, m_tiles=self.m_tiles, n_tiles=Cc // 128, nt=128, kchunks=a_buf.shape[0],
                           kch_iter=kch_iter, relu=int(relu), n_boards=B, a_rows=self.rows, a_row0=ROW0,
                           out_rows=self.rows, out_row0=ROW0, out_stride=0, a=a_buf.data_ptr(), w=img.data_ptr(),
                           bias=bias.data_ptr(), residual=None if residual is None else residual.data_ptr(),
-                          out=out_buf.data_ptr(), out2=None, w_half=None if img64 is None else img64.data_ptr())
+                          out=out_buf.data_ptr(), out2=None)
             self.layers.append(d)
 
         with torch.no_grad():
@@ -235,18 +238,17 @@ class B200Net:
         n = planes.shape[0]
         assert n <= self.max_batch
         p = planes.to(self.e.dev, torch.float32)
-        x = torch.zeros((n, 11, 10, 16), dtype=torch.bfloat16, device=self.e.dev)
-        x[:, 1:, :9, :15] = p.permute(0, 2, 3, 1).to(torch.bfloat16)
-        x = x.reshape(n * 110, 2, 8).permute(1, 0, 2)
-        self.x0.zero_()
-        self.x0[:, ROW0:ROW0 + n * 110] = x
+        x = torch.zeros((n, 10, 9, 16), dtype=torch.bfloat16, device=self.e.dev)
+        x[..., :15] = p.permute(0, 2, 3, 1).to(torch.bfloat16)
+        self.x0[:, ROW0:ROW0 + n * BOARD_ROWS] = x.reshape(n * BOARD_ROWS, 2, 8).permute(1, 0, 2)
 
     def run(self, n_boards=None):
-        """Enqueue the whole forward on the current torch stream (xq_net_run)."""
+        """Enqueue the whole forward of the first n_boards boards (default: max_batch) on the current torch stream
+        (xq_net_run sizes every launch to that count)."""
         L = self.e.L
         rc = L.xq_net_run(self.e.h, self.desc_array, self.n_layers, self.vfeat.data_ptr(), self.w1t.data_ptr(),
                           self.b1.data_ptr(), self.w2.data_ptr(), C.c_float(self.b2), self.value.data_ptr(),
-                          self.max_batch, self.e._stream())
+                          self.max_batch if n_boards is None else int(n_boards), self.e._stream())
         self.e._check(rc)
 
     def run_layer(self, i):
@@ -255,14 +257,14 @@ class B200Net:
     def forward_planes(self, planes: torch.Tensor):
         n = planes.shape[0]
         self.load_planes(planes)
-        self.run()
+        self.run(n)
         return self.logits[:n], self.value[:n]
 
     # -- debugging / tests: read a plane tensor back as [n,C,10,9] float --------------------------
     def planes_to_nchw(self, buf: torch.Tensor, n: int):
         ch = buf.shape[0] * 8
-        x = buf[:, ROW0:ROW0 + n * 110].permute(1, 0, 2).reshape(n, 11, 10, ch)
-        return x[:, 1:, :9].permute(0, 3, 1, 2).float()
+        x = buf[:, ROW0:ROW0 + n * BOARD_ROWS].permute(1, 0, 2).reshape(n, 10, 9, ch)
+        return x.permute(0, 3, 1, 2).float()
 
     def flops_per_board(self):
         Cc, R = self.C_model, self.R                      # algorithmic FLOPs of the model, not of the padded tiles
