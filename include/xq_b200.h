@@ -86,6 +86,24 @@ int xq_is_attacked_batch(xq_ctx* ctx, const int8_t* d_boards, const uint8_t* d_s
 int xq_is_attacked_batch_host(xq_ctx* ctx, const int8_t* h_boards, const uint8_t* h_sq, const int8_t* h_by,
                               int B, uint8_t* h_out);
 
+/* Same as xq_movegen_batch_host with the feature planes as BITS: h_plane_bits [B][44] uint32, bit plane*90+square of
+ * a position's 1350 plane values at word (bit >> 5), bit (bit & 31) -- 176 bytes per position across PCIe instead of the
+ * 5400 of the float32 planes (which are 0.0 / 1.0 only); xiangqi-alphazero_b200/xq_native.py:unpack_planes expands them. */
+int xq_movegen_batch_host_packed(xq_ctx* ctx, const int8_t* h_boards, const int8_t* h_sides, int B,
+                                 int16_t* h_actions, uint8_t* h_n_moves, uint8_t* h_in_check, uint32_t* h_plane_bits);
+/* the packed planes alone, device buffers: d_bits [B][44] uint32 */
+int xq_planes_bits(xq_ctx* ctx, const int8_t* d_boards, const int8_t* d_sides, int B, uint32_t* d_bits, void* stream);
+
+/* Replaces cy_find_king (game_core.pyx:493-505 over _find_king :78-101): the king of side d_sides[i] searched only in
+ * that side's own palace (rows 0-2 / 7-9, columns 3-5) in row-major order; d_king_sq[i] = row*9+col, -1 if absent
+ * (the reference returns None). */
+int xq_find_king_batch(xq_ctx* ctx, const int8_t* d_boards, const int8_t* d_sides, int B, int8_t* d_king_sq, void* stream);
+int xq_find_king_batch_host(xq_ctx* ctx, const int8_t* h_boards, const int8_t* h_sides, int B, int8_t* h_king_sq);
+/* Replaces cy_has_legal_moves (game_core.pyx:558-569): d_has[i] = 1 iff side d_sides[i] has at least one legal move
+ * (the reference generates the full list and tests the count; so does this call, into the context's grow-only scratch). */
+int xq_has_legal_moves_batch(xq_ctx* ctx, const int8_t* d_boards, const int8_t* d_sides, int B, uint8_t* d_has, void* stream);
+int xq_has_legal_moves_batch_host(xq_ctx* ctx, const int8_t* h_boards, const int8_t* h_sides, int B, uint8_t* h_has);
+
 /* Which K1 kernel xq_movegen_batch[_host] launches: 1 = one thread per board (csrc/xq_rules_tpb.h, the default),
  * 0 = one warp per board (first generation; also the generator inside the MCTS kernels, where a warp owns a game).
  * Same outputs bit for bit; returns the previous value (or < 0 on a bad argument).  The default can also be chosen
@@ -150,6 +168,9 @@ int xq_mcts_leaf_info(xq_ctx* ctx, int32_t* d_state, int32_t* d_n, int16_t* d_ac
  * d_n [G], optional d_w [G][128] float64 total values. */
 int xq_mcts_root_visits(xq_ctx* ctx, int16_t* d_actions, int32_t* d_visits, int32_t* d_n, double* d_w,
                         void* stream);
+/* priors of the root children in child order as the PUCT arithmetic uses them (float64 [G][128]: the float32 P, or the
+ * noisy mix 0.75 P + 0.25 eta of mcts.py:117-121 after xq_mcts_root_expand with add_noise); d_n [G] optional. */
+int xq_mcts_root_priors(xq_ctx* ctx, double* d_priors, int32_t* d_n, void* stream);
 /* h_stats6: simulations, terminal-leaf simulations, max depth, evaluations consumed, nodes in the
  * current search, error bits (1 node pool overflow, 2 >128 legal moves). Synchronises. */
 int xq_mcts_stats(xq_ctx* ctx, long long* h_stats6, int reset);
@@ -201,11 +222,19 @@ int xq_net_run(xq_ctx* ctx, const xq_gemm_desc* layers, int n_layers, const floa
                const float* d_w1t, const float* d_b1, const float* d_w2, float b2, float* d_value, int B,
                void* stream);
 
+/* xq_net_run with the board count on the DEVICE (*d_n_boards, clamped to max_boards): grids are sized for max_boards and
+ * every kernel cuts its tile loop to the live count -- the leaf-compacting self-play loop never synchronises. */
+int xq_net_run_counted(xq_ctx* ctx, const xq_gemm_desc* layers, int n_layers, const float* d_vfeats,
+                       const float* d_w1t, const float* d_b1, const float* d_w2, float b2, float* d_value,
+                       const int* d_n_boards, int max_boards, void* stream);
+
 /* ---- device-resident self-play ------------------------------------------------------------------
  * Replaces parallel_selfplay.py:_play_one_game (:42-134) + the worker fan-out (:337-474): n_slots
  * games advance in lockstep on one GPU, each ply = root evaluation -> num_simulations x (select,
  * network forward, expand+backup) -> temperature sampling; finished games are replaced in their
- * slot until target_games have been started.  Config fields are the reference's 8 worker keys
+ * slot until target_games have been started.  The leaves that need the network are COMPACTED into the
+ * first rows of the batch (what inference_server.py:163-249 did by batching only live requests): idle
+ * slots, finished games and terminal leaves cost no forward rows.  Config fields are the reference's 8 worker keys
  * (parallel_selfplay.py:184-187).
  */
 typedef struct xq_selfplay_config {
@@ -221,6 +250,11 @@ typedef struct xq_selfplay_config {
     float dirichlet_alpha;      /* 0.3 */
     uint64_t seed;
     int32_t target_games;       /* games to start in total (num_games_per_iter share of this GPU) */
+    int32_t leaves_per_game;    /* K: descents per game and lockstep step.  0 or 1 = the reference's one simulation at a
+                                   time (mcts.py:126-153, visit counts bit-exact).  K > 1 = opt-in multi-leaf mode: K
+                                   descents per step with a VIRTUAL LOSS on the path of each (N += 1, W -= 1 until its
+                                   backup), all K leaves evaluated in the same forward; a search still makes exactly
+                                   num_simulations descents.  The network plan's batch must be >= n_slots * K. */
 } xq_selfplay_config;
 
 /* what the loop needs to run the evaluator: the layer list of xq_net_run plus its I/O buffers */
@@ -265,7 +299,8 @@ int xq_selfplay_device_buffers(xq_ctx* ctx, void** d_samples, int8_t** d_winner,
  * slots of xq_selfplay_create, game uid with the NEW model as red when uid is even (:474), every move =
  * get_action(game, temperature=0, add_noise=False) of the model to move (:481-483) with cfg->num_simulations
  * simulations, from the initial position, no resignation; a game still undecided after cfg->max_game_length plies is a
- * draw (:496-498).  Both networks evaluate every leaf batch; results land in the per-game result arrays
+ * draw (:496-498).  A game's leaves go to the network of the player to move at the root only (two compacted batches);
+ * results land in the per-game result arrays
  * (xq_selfplay_fetch / xq_selfplay_counters).  d_move_log [max_games_total][XQ_MAX_PLIES] int16 receives the actions played
  * (optional).  Call xq_selfplay_reset before a new match. */
 int xq_arena_play(xq_ctx* ctx, const xq_selfplay_config* cfg, const xq_net_plan* net_new, const xq_net_plan* net_old,

@@ -2,8 +2,9 @@
 
 Replaces AlphaZeroTrainer._serial_evaluate (train.py:453-535), which plays `eval_games` games one after the
 other with two MCTS objects.  Here every game is a slot of the device-resident loop (csrc/xq_mcts.cu,
-xq_arena_play): both networks evaluate every leaf batch and each game keeps the outputs of the model whose
-turn it is at the root.  Rules kept from the reference: game i has the new model as red when i is even
+xq_arena_play): a game's leaves go to the network of the player to move at the root, so each of the two forwards
+of a step is sized to its own share of the leaves; `leaves_per_game` > 1 (opt-in, virtual loss) widens the batch of
+the few evaluation games.  Rules kept from the reference: game i has the new model as red when i is even
 (:474), moves are get_action(temperature=0, add_noise=False) with `eval_simulations` simulations (:481-483),
 no random opening, no resignation, an undecided game after max_game_length plies is a draw (:496-498),
 win_rate = (new_wins + 0.5 draws) / games (:512).
@@ -33,13 +34,15 @@ def shard_pairs(num_games: int, rank: int, world: int) -> int:
 
 
 class Arena:
-    def __init__(self, eng: "xq_native.Engine", model_new, model_old, num_games: int, max_simulations: int):
+    def __init__(self, eng: "xq_native.Engine", model_new, model_old, num_games: int, max_simulations: int,
+                 leaves_per_game: int = 1):
         # NOTE: a context holds one self-play state; give the arena its own xq_native.Engine when a SelfPlayEngine on
         # `eng` must stay usable (AlphaZeroTrainer does)
         self.e = eng
         self.num_games = int(num_games)
+        self.leaves_per_game = max(1, int(leaves_per_game))
         self.sp = SelfPlayEngine(eng, model_new, n_slots=self.num_games, max_games=self.num_games, sample_capacity=1,
-                                 max_simulations=max_simulations)
+                                 max_simulations=max_simulations, leaves_per_game=self.leaves_per_game)
         self.plan_new, self.net_new = self.sp.plan, self.sp.net
         self.sp.set_model(model_old)                   # second weight set with the same batch geometry
         self.plan_old, self.net_old = self.sp.plan, self.sp.net
@@ -52,7 +55,7 @@ class Arena:
         self.move_log.fill_(-1)
         cfg = SelfPlayEngine.make_config(dict(num_simulations=num_simulations, c_puct=c_puct, max_game_length=max_game_length,
                                               random_opening_moves=0, enable_resign=False), self.num_games, seed=0,
-                                         add_noise=False)
+                                         add_noise=False, leaves_per_game=self.leaves_per_game)
         played = 0
         limit = max_game_length + 2
         while played < limit:
@@ -76,14 +79,14 @@ class Arena:
 
 
 def evaluate_models(eng, model_new, model_old, eval_games: int, eval_simulations: int, c_puct: float,
-                    max_game_length: int, dist=None):
+                    max_game_length: int, dist=None, leaves_per_game: int = 1):
     """The numbers of train.py:512-520: new_wins, old_wins, draws, win_rate (all ranks return the same dict).
     `eng`: the context the arena may take over (its previous SelfPlayEngine, if any, is superseded)."""
     rank, world = (dist.get_rank(), dist.get_world_size()) if dist is not None else (0, 1)
     mine = shard_pairs(eval_games, rank, world)
     counts = torch.zeros(3, dtype=torch.int64, device=eng.dev)
     if mine > 0:
-        r = Arena(eng, model_new, model_old, mine, eval_simulations).play(eval_simulations, c_puct, max_game_length)
+        r = Arena(eng, model_new, model_old, mine, eval_simulations, leaves_per_game).play(eval_simulations, c_puct, max_game_length)
         counts += torch.tensor([r["new_wins"], r["old_wins"], r["draws"]], dtype=torch.int64, device=eng.dev)
     if world > 1:
         dist.all_reduce(counts)

@@ -21,6 +21,8 @@ struct xq_ctx {
     cudaStream_t pipe[2] = {nullptr, nullptr};
     void* d_stage[2] = {nullptr, nullptr};
     size_t stage_bytes = 0;
+    void* d_scratch = nullptr;            // grow-only device scratch (xq_has_legal_moves_batch)
+    size_t scratch_bytes = 0;
     // subsystem state owned by other translation units
     void* mcts = nullptr;
     void* net = nullptr;

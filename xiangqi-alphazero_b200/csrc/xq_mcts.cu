@@ -39,7 +39,8 @@ struct __align__(16) NodeLink {
     int32_t pad;
 };
 
-enum { kLeafEval = 0, kLeafTerminal = 1, kLeafIdle = 2 };
+enum { kLeafEval = 0, kLeafTerminal = 1, kLeafIdle = 2, kLeafDup = 3 };   // kLeafDup: the leaf another descent of the same step already selected
+constexpr uint8_t kPendingFlag = 0x80;   // NodeLink.flags of a leaf that waits for its evaluation (pad = evaluator row)
 
 struct MctsState {
     int max_games = 0;
@@ -62,6 +63,11 @@ struct MctsState {
     int32_t* leaf_n = nullptr;        // [G]
     int64_t* stats = nullptr;         // [4] sims, terminal sims, max depth, evals
     int32_t* root_winner = nullptr;   // [G] is_game_over at the root: 1/-1/0, or 2 = game goes on
+    // self-play / arena loop (leaf slots are [G][leaf_k], slot g*K+j; the standalone xq_mcts_* calls use slot g, K = 1)
+    int leaf_k = 1;                   // leaf slots allocated per game
+    int32_t* leaf_row = nullptr;      // [G*leaf_k] evaluator row of the slot (compacted), -1 none
+    int32_t* sims_left = nullptr;     // [G] simulations still to run in the current search
+    int* n_eval = nullptr;            // [2] rows handed out in the current step, per network
 };
 
 constexpr int kSelWarps = 4;
@@ -140,6 +146,22 @@ __device__ __forceinline__ int backup_path(const MctsState& M, int node, double 
         NodeHot h = M.hot[node];
         h.N += 1;
         h.W = __dadd_rn(h.W, value);
+        M.hot[node] = h;
+        value = -value;
+        node = M.link[node].parent;
+        ++depth;
+    }
+    return depth;
+}
+
+// Backup of a descent that carried a virtual loss: the selection already counted the visit (N += 1) and charged a loss
+// (W -= 1) on every node of the path, so the real result replaces the loss and N stays.
+__device__ __forceinline__ int backup_path_vl(const MctsState& M, int node, double value)
+{
+    int depth = 0;
+    while (node >= 0) {
+        NodeHot h = M.hot[node];
+        h.W = __dadd_rn(__dadd_rn(h.W, 1.0), value);
         M.hot[node] = h;
         value = -value;
         node = M.link[node].parent;
@@ -436,6 +458,24 @@ __global__ void mcts_root_visits_kernel(MctsState M, int16_t* actions, int32_t* 
     if (lane == 0) n_out[g] = n;
 }
 
+// priors of the root children as the select arithmetic sees them: float32 P widened (flags 0), 1/n (flags 1: zero-mass
+// fallback) or the float64 noisy mix 0.75 P + 0.25 eta (flags 2, mcts.py:117-121)
+__global__ void mcts_root_priors_kernel(MctsState M, double* priors, int32_t* n_out)
+{
+    const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (g >= M.n_games) return;
+    const NodeLink l = M.link[g];
+    const int n = l.child0 >= 0 ? l.nchild : 0;
+    const int mode = l.flags & 3;
+    for (int i = lane; i < kMaxMoves; i += 32) {
+        double p = 0.0;
+        if (i < n) p = mode == 2 ? M.rootP64[(size_t)g * kMaxMoves + i] : (mode == 1 ? __ddiv_rn(1.0, (double)n) : (double)M.hot[l.child0 + i].P);
+        priors[(size_t)g * kMaxMoves + i] = p;
+    }
+    if (lane == 0 && n_out) n_out[g] = n;
+}
+
 __global__ void set_int_kernel(int* p, int v) { *p = v; }
 
 __global__ void mcts_set_games_kernel(MctsState M, const int8_t* boards, const int8_t* sides, const int32_t* move_count,
@@ -468,7 +508,8 @@ extern "C" void xq_mcts_free_(xq_ctx* c)
     MctsState* M = S_(c);
     if (!M) return;
     void* ptrs[] = {M->board, M->ring, M->meta, M->hot, M->link, M->rootP64, M->alloc, M->error,
-                    M->leaf_node, M->leaf_state, M->leaf_actions, M->leaf_n, M->stats, M->root_winner};
+                    M->leaf_node, M->leaf_state, M->leaf_actions, M->leaf_n, M->stats, M->root_winner,
+                    M->leaf_row, M->sims_left, M->n_eval};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     delete M;
@@ -511,9 +552,35 @@ extern "C" int xq_mcts_create(xq_ctx* c, int max_games, long long node_capacity)
     XQ_CUDA(c, cudaMalloc(&M->leaf_n, G * sizeof(int32_t)));
     XQ_CUDA(c, cudaMalloc(&M->stats, 4 * sizeof(int64_t)));
     XQ_CUDA(c, cudaMalloc(&M->root_winner, G * sizeof(int32_t)));
+    XQ_CUDA(c, cudaMalloc(&M->leaf_row, G * sizeof(int32_t)));
+    XQ_CUDA(c, cudaMalloc(&M->sims_left, G * sizeof(int32_t)));
+    XQ_CUDA(c, cudaMalloc(&M->n_eval, 2 * sizeof(int)));
+    XQ_CUDA(c, cudaMemset(M->sims_left, 0, G * sizeof(int32_t)));
+    XQ_CUDA(c, cudaMemset(M->n_eval, 0, 2 * sizeof(int)));
+    M->leaf_k = 1;
     XQ_CUDA(c, cudaMemset(M->error, 0, sizeof(int)));
     XQ_CUDA(c, cudaMemset(M->stats, 0, 4 * sizeof(int64_t)));
     XQ_CUDA(c, cudaMemset(M->meta, 0, G * 4 * sizeof(int32_t)));
+    return XQ_OK;
+}
+
+// leaf slots per game for the multi-leaf search of the self-play loop (grow-only)
+static int mcts_reserve_leaves(xq_ctx* c, MctsState* M, int K)
+{
+    if (K <= M->leaf_k) return XQ_OK;
+    XQ_CUDA(c, cudaDeviceSynchronize());
+    const size_t n = (size_t)M->max_games * (size_t)K;
+    void* old[] = {M->leaf_node, M->leaf_state, M->leaf_actions, M->leaf_n, M->leaf_row};
+    for (void* q : old)
+        if (q) cudaFree(q);
+    M->leaf_node = M->leaf_state = M->leaf_n = M->leaf_row = nullptr;
+    M->leaf_actions = nullptr;
+    XQ_CUDA(c, cudaMalloc(&M->leaf_node, n * sizeof(int32_t)));
+    XQ_CUDA(c, cudaMalloc(&M->leaf_state, n * sizeof(int32_t)));
+    XQ_CUDA(c, cudaMalloc(&M->leaf_actions, n * kMaxMoves * sizeof(int16_t)));
+    XQ_CUDA(c, cudaMalloc(&M->leaf_n, n * sizeof(int32_t)));
+    XQ_CUDA(c, cudaMalloc(&M->leaf_row, n * sizeof(int32_t)));
+    M->leaf_k = K;
     return XQ_OK;
 }
 
@@ -632,6 +699,17 @@ extern "C" int xq_mcts_root_visits(xq_ctx* c, int16_t* d_actions, int32_t* d_vis
     return XQ_OK;
 }
 
+extern "C" int xq_mcts_root_priors(xq_ctx* c, double* d_priors, int32_t* d_n, void* stream)
+{
+    NEED_MCTS(c);
+    if (M.n_games == 0) return XQ_OK;
+    if (!d_priors) return xq_fail(c, XQ_ERR_ARG, "xq_mcts_root_priors: bad arguments");
+    mcts_root_priors_kernel<<<blocks_for(M.n_games), kSelWarps * 32, 0, s>>>(M, d_priors, d_n);
+    c->launches += 1;
+    XQ_CUDA(c, cudaGetLastError());
+    return XQ_OK;
+}
+
 // stats[0..3] = simulations, terminal-leaf simulations, max depth, evaluator calls consumed;
 // stats[4] = nodes allocated in the current search; stats[5] = error bits (1 pool overflow, 2 move overflow)
 extern "C" int xq_mcts_stats(xq_ctx* c, long long* h_stats6, int reset)
@@ -682,6 +760,7 @@ struct SpConfig {
     // order, mcts.py:197-200), no sample records, a game that reaches max_game_length undecided is a draw (:496-498)
     int arena;
     int16_t* move_log;              // [max_games_total][XQ_MAX_PLIES] actions played, or nullptr
+    int leaves_per_game;            // K: descents per game and step (1 = mcts.py's one simulation at a time; > 1: virtual loss)
 };
 
 constexpr int kSampleBytes = 896;   // board 90 | side 1 | n 1 | uid 4 | ply 4 | played action 2 | pad | actions @128 (256) | probs @384 (512)
@@ -806,12 +885,85 @@ __device__ __forceinline__ void sp_finish_game(const MctsState& M, const SpState
     M.meta[g * 4 + 3] = 0;
 }
 
+// ---- evaluator ports: where a leaf's network input goes and where its results come from ------------------
+// Rows are COMPACTED: a leaf that needs the network takes the next row of its port's batch (atomic counter
+// n_eval[port]), so a forward is sized to the leaves that are really waiting (xq_net_run_counted), whatever the
+// number of idle slots, finished games and terminal leaves.  The arena has two ports (new / old model): a game's
+// search belongs to the player to move at the ROOT (train.py:481-483), so each leaf goes to ONE network.
+struct EvalPort {
+    __nv_bfloat16* x_planes;
+    long long x_rows, x_row0;
+    const void* logits;
+    size_t row_stride;
+    const float* value;
+};
+struct StepArgs {
+    EvalPort port[2];
+    int arena;
+    int K;                  // leaf slots per game and step (1 = the reference's one simulation at a time)
+};
+
+__device__ __forceinline__ int sp_port_of(const SpState& P, const StepArgs& A, int g, int root_side)
+{
+    if (!A.arena) return 0;
+    const int uid = P.game_uid[g];
+    return (((uid & 1) == 0) == (root_side == 1)) ? 0 : 1;     // the new model is red in even games (train.py:474)
+}
+
+// root preparation of the self-play loop: as mcts_root_begin_kernel, for the playing slots only, rows compacted
+__global__ void __launch_bounds__(kSelWarps * 32) sp_root_begin_kernel(MctsState M, SpState P, StepArgs A)
+{
+    __shared__ SelectSmem sm;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.x * kSelWarps + warp;
+    if (g >= M.n_games) return;
+    const int slot = g * A.K;
+    const bool active = M.meta[g * 4 + 3] != 0 && P.status[g] == 1;
+    if (!active) {
+        if (lane == 0) {
+            M.leaf_n[slot] = 0;
+            M.leaf_node[slot] = g;
+            M.leaf_state[slot] = kLeafIdle;
+            M.leaf_row[slot] = -1;
+            M.sims_left[g] = 0;
+            M.root_winner[g] = 2;
+            M.hot[g] = NodeHot{0.0, 0, 0.0f};
+            M.link[g] = NodeLink{-1, -1, (int16_t)-1, 0, 0, 0};
+        }
+        return;
+    }
+    int8_t* b = sm.board[warp];
+    GameMeta gm;
+    warp_load_game(M, g, b, sm.ring[warp], gm);
+    WarpScratch& S = sm.ws[warp];
+    MovegenResult r = warp_movegen(b, gm.side, S);
+    if (r.overflow && lane == 0) atomicOr(M.error, 2);
+    const int rw = warp_game_over(b, sm.ring[warp], gm, r);
+    const int n = min(r.n_legal, kMaxMoves);
+    reinterpret_cast<uint2*>(M.leaf_actions + (size_t)slot * kMaxMoves)[lane] = reinterpret_cast<const uint2*>(S.actions)[lane];
+    const int port = sp_port_of(P, A, g, gm.side);
+    int row = 0;
+    if (lane == 0) {
+        row = atomicAdd(&M.n_eval[port], 1);       // every playing root is evaluated: the resign probe reads its value
+        M.root_winner[g] = rw;
+        M.leaf_n[slot] = n;
+        M.leaf_node[slot] = g;
+        M.leaf_state[slot] = n > 0 ? kLeafEval : kLeafIdle;
+        M.leaf_row[slot] = row;
+        M.sims_left[g] = 0;
+        M.hot[g] = NodeHot{0.0, 0, 0.0f};          // fresh root (mcts.py:104)
+        M.link[g] = NodeLink{-1, -1, (int16_t)-1, 0, 0, 0};
+    }
+    row = warp_bcast(row, 0);
+    const EvalPort& e = A.port[port];
+    warp_emit_eval_inputs(b, gm.side, row, nullptr, e.x_planes, e.x_rows, e.x_row0, nullptr, nullptr);
+}
+
 // After the root evaluation: resign rule, termination, length adjudication, else expand the root
 // (parallel_selfplay.py:74-95,110-121 in the reference's order: resign probe first).
 template <int KIND>
 __global__ void __launch_bounds__(kSelWarps * 32)
-sp_after_root_kernel(MctsState M, SpState P, SpConfig cfg, const void* policy, size_t row_stride, const float* value,
-                     unsigned long long ply_idx)
+sp_after_root_kernel(MctsState M, SpState P, SpConfig cfg, StepArgs A, unsigned long long ply_idx)
 {
     __shared__ float pri[kSelWarps][kMaxMoves];
     __shared__ double nz[kSelWarps][kMaxMoves];
@@ -819,12 +971,21 @@ sp_after_root_kernel(MctsState M, SpState P, SpConfig cfg, const void* policy, s
     const int g = blockIdx.x * kSelWarps + warp;
     if (g >= M.n_games) return;
     if (P.status[g] != 1) return;
+    const int slot = g * A.K;
+    const int row = M.leaf_row[slot];
+    if (row < 0) return;
     const int side = M.meta[g * 4 + 0], move_count = M.meta[g * 4 + 1];
+    const EvalPort& e = A.port[sp_port_of(P, A, g, side)];
     // resign probe: the value of the position just reached, for the side to move
     if (cfg.enable_resign && P.n_samples[g] > 10) {
-        int run = P.resign_run[g];
-        run = value[g] < cfg.resign_threshold ? run + 1 : 0;
-        if (lane == 0) P.resign_run[g] = run;
+        // lane 0 alone reads, updates and stores the counter; the warp gets its value by broadcast (every lane
+        // loading it while lane 0 stores would be a race, and a lane seeing the new value would leave the warp)
+        int run = 0;
+        if (lane == 0) {
+            run = e.value[row] < cfg.resign_threshold ? P.resign_run[g] + 1 : 0;
+            P.resign_run[g] = run;
+        }
+        run = warp_bcast(run, 0);
         if (run >= cfg.resign_check_steps) {
             if (lane == 0) sp_finish_game(M, P, g, -side, move_count);
             return;
@@ -848,9 +1009,9 @@ sp_after_root_kernel(MctsState M, SpState P, SpConfig cfg, const void* policy, s
         if (lane == 0) sp_finish_game(M, P, g, diff > 30 ? 1 : (diff < -30 ? -1 : 0), move_count);
         return;
     }
-    const int n = M.leaf_n[g];
-    const int16_t* acts = M.leaf_actions + (size_t)g * kMaxMoves;
-    bool uniform = warp_priors<KIND>(policy, row_stride, g, acts, n, pri[warp]);
+    const int n = M.leaf_n[slot];
+    const int16_t* acts = M.leaf_actions + (size_t)slot * kMaxMoves;
+    bool uniform = warp_priors<KIND>(e.logits, e.row_stride, row, acts, n, pri[warp]);
     if (cfg.add_noise) {
         double s = 0.0;
         const uint64_t stream = ((uint64_t)P.game_uid[g] << 20) ^ ply_idx;
@@ -864,7 +1025,181 @@ sp_after_root_kernel(MctsState M, SpState P, SpConfig cfg, const void* policy, s
         warp_sync();
     }
     warp_expand(M, g, acts, n, pri[warp], uniform, g, nz[warp], cfg.add_noise != 0);
-    if (lane == 0) atomicAdd((unsigned long long*)&M.stats[3], 1ull);
+    if (lane == 0) {
+        atomicAdd((unsigned long long*)&M.stats[3], 1ull);
+        M.sims_left[g] = cfg.num_simulations;
+    }
+}
+
+// ---- one lockstep step of the self-play search: up to K descents per game -----------------------------------
+// K = 1 is mcts.py:126-153 exactly (the arithmetic of mcts_select_kernel / mcts_expand_backup_kernel).  K > 1 is the
+// opt-in multi-leaf mode: a game runs K descents per step, each leaving a VIRTUAL LOSS on its path (N += 1, W -= 1 on
+// every node, so the next descent of the step sees a worse q there and turns elsewhere); the K leaves are evaluated in
+// the same forward and backed up in descent order, each replacing its virtual loss by the real value.  A descent that
+// ends on a leaf already waiting for its evaluation in this step shares that evaluation (kLeafDup).  Small game counts
+// (the arena's eval_games, the tail of an iteration) fill the tensor-core batch this way.
+__global__ void __launch_bounds__(kSelWarps * 32) mcts_select_multi_kernel(MctsState M, SpState P, double c_puct, StepArgs A)
+{
+    __shared__ SelectSmem sm;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.x * kSelWarps + warp;
+    if (g >= M.n_games) return;
+    const int K = A.K;
+    const bool vl = K > 1;
+    int left = M.link[g].child0 < 0 ? 0 : M.sims_left[g];       // no tree (finished, idle): nothing to do
+    const int port = sp_port_of(P, A, g, M.meta[g * 4 + 0]);
+    const EvalPort& e = A.port[port];
+    int8_t* b = sm.board[warp];
+    int8_t* ring = sm.ring[warp];
+    const float c32 = (float)c_puct;
+    for (int j = 0; j < K; ++j) {
+        const int slot = g * K + j;
+        if (left <= 0) {
+            if (lane == 0) M.leaf_state[slot] = kLeafIdle;
+            continue;
+        }
+        --left;
+        GameMeta gm;
+        warp_load_game(M, g, b, ring, gm);
+        int node = g, depth = 0;
+        NodeLink ln = M.link[node];
+        if (vl) {
+            if (lane == 0) {
+                NodeHot h = M.hot[node];
+                h.N += 1;
+                h.W = __dadd_rn(h.W, -1.0);
+                M.hot[node] = h;
+            }
+            warp_sync();
+        }
+        while (ln.child0 >= 0) {
+            const int nch = ln.nchild, c0 = ln.child0, mode = ln.flags & 3;
+            // with a virtual loss the parent's count includes this descent's own visit: sqrt(N - 1) keeps K = 1 arithmetic
+            const double sqrt_parent = sqrt((double)(M.hot[node].N - (vl ? 1 : 0)));   // math.sqrt(self.visit_count)
+            const float sp32 = (float)sqrt_parent;
+            double best = -INFINITY;
+            int best_i = 0x7fffffff;
+            for (int i = lane; i < nch; i += 32) {
+                const NodeHot h = M.hot[c0 + i];
+                const double q = h.N == 0 ? 0.0 : __ddiv_rn(h.W, (double)h.N);
+                double score;
+                if (mode == 0) {
+                    float u = __fmul_rn(c32, h.P);
+                    u = __fmul_rn(u, sp32);
+                    u = __fdiv_rn(u, (float)(1 + h.N));
+                    score = (double)__fadd_rn((float)q, u);
+                } else {
+                    const double p = mode == 2 ? M.rootP64[(size_t)g * kMaxMoves + i] : __ddiv_rn(1.0, (double)nch);
+                    double u = __dmul_rn(c_puct, p);
+                    u = __dmul_rn(u, sqrt_parent);
+                    u = __ddiv_rn(u, (double)(1 + h.N));
+                    score = __dadd_rn(q, u);
+                }
+                if (score > best) {   // strict '>' : first maximum wins (i ascends within a lane)
+                    best = score;
+                    best_i = i;
+                }
+            }
+            best_i = warp_argmax_first(best, best_i);
+            if (best_i == 0x7fffffff) best_i = 0;
+            node = c0 + best_i;
+            ln = M.link[node];
+            if (vl) {
+                if (lane == 0) {
+                    NodeHot h = M.hot[node];
+                    h.N += 1;
+                    h.W = __dadd_rn(h.W, -1.0);
+                    M.hot[node] = h;
+                }
+                warp_sync();
+            }
+            warp_make_move(b, ring, gm, ln.action);
+            ++depth;
+        }
+        if (lane == 0) {
+            atomicAdd((unsigned long long*)&M.stats[0], 1ull);
+            atomicMax((unsigned long long*)&M.stats[2], (unsigned long long)depth);
+        }
+        if (vl && (ln.flags & kPendingFlag)) {
+            // an earlier descent of this step waits on this very leaf: share its evaluation
+            if (lane == 0) {
+                M.leaf_state[slot] = kLeafDup;
+                M.leaf_node[slot] = node;
+                M.leaf_row[slot] = ln.pad;
+            }
+            continue;
+        }
+        WarpScratch& S = sm.ws[warp];
+        MovegenResult r = warp_movegen(b, gm.side, S);
+        if (r.overflow && lane == 0) atomicOr(M.error, 2);
+        const int w = warp_game_over(b, ring, gm, r);
+        if (w != 2) {
+            // terminal leaf: value needs no evaluator; back up now (mcts.py:137-140,153)
+            if (lane == 0) {
+                M.leaf_state[slot] = kLeafTerminal;
+                M.leaf_node[slot] = node;
+                if (vl) backup_path_vl(M, node, w == 0 ? 0.0 : 1.0);
+                else backup_path(M, node, w == 0 ? 0.0 : 1.0);
+                atomicAdd((unsigned long long*)&M.stats[1], 1ull);
+            }
+            warp_sync();
+            continue;
+        }
+        reinterpret_cast<uint2*>(M.leaf_actions + (size_t)slot * kMaxMoves)[lane] = reinterpret_cast<const uint2*>(S.actions)[lane];
+        int row = 0;
+        if (lane == 0) {
+            row = atomicAdd(&M.n_eval[port], 1);
+            M.leaf_state[slot] = kLeafEval;
+            M.leaf_node[slot] = node;
+            M.leaf_n[slot] = min(r.n_legal, kMaxMoves);
+            M.leaf_row[slot] = row;
+            if (vl) {
+                NodeLink l2 = M.link[node];
+                l2.flags |= kPendingFlag;
+                l2.pad = row;
+                M.link[node] = l2;
+            }
+        }
+        row = warp_bcast(row, 0);
+        warp_emit_eval_inputs(b, gm.side, row, nullptr, e.x_planes, e.x_rows, e.x_row0, nullptr, nullptr);
+        warp_sync();
+    }
+    if (lane == 0 && M.link[g].child0 >= 0) M.sims_left[g] = left;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(kSelWarps * 32) mcts_expand_backup_multi_kernel(MctsState M, SpState P, StepArgs A)
+{
+    __shared__ float pri[kSelWarps][kMaxMoves];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.x * kSelWarps + warp;
+    if (g >= M.n_games) return;
+    const int K = A.K;
+    const bool vl = K > 1;
+    const EvalPort& e = A.port[sp_port_of(P, A, g, M.meta[g * 4 + 0])];
+    for (int j = 0; j < K; ++j) {
+        const int slot = g * K + j;
+        const int st = M.leaf_state[slot];
+        if (st != kLeafEval && st != kLeafDup) continue;
+        const int node = M.leaf_node[slot];
+        const int row = M.leaf_row[slot];
+        if (st == kLeafEval) {
+            const int n = M.leaf_n[slot];
+            const int16_t* acts = M.leaf_actions + (size_t)slot * kMaxMoves;
+            bool uniform = warp_priors<KIND>(e.logits, e.row_stride, row, acts, n, pri[warp]);
+            const bool ok = warp_expand(M, node, acts, n, pri[warp], uniform, g, nullptr, false);   // rewrites flags: pending bit gone
+            if (!ok && vl && lane == 0) M.link[node].flags &= (uint8_t)~kPendingFlag;
+            warp_sync();
+        }
+        if (lane == 0) {
+            __threadfence();
+            const double v = -(double)e.value[row];          // value = -value (mcts.py:150)
+            if (vl) backup_path_vl(M, node, v);
+            else backup_path(M, node, v);
+            if (st == kLeafEval) atomicAdd((unsigned long long*)&M.stats[3], 1ull);
+        }
+        warp_sync();
+    }
 }
 
 // End of a search: visit distribution -> sample record, temperature sampling, make the move
@@ -1016,6 +1351,74 @@ extern "C" int xq_selfplay_reset(xq_ctx* c, void* stream)
     return XQ_OK;
 }
 
+extern "C" int xq_net_run_counted(xq_ctx* c, const xq_gemm_desc* layers, int n_layers, const float* d_vfeats, const float* d_w1t,
+                                  const float* d_b1, const float* d_w2, float b2, float* d_value, const int* d_n_boards,
+                                  int max_boards, void* stream);
+
+static EvalPort port_of(const xq_net_plan* n)
+{
+    EvalPort e;
+    e.x_planes = (__nv_bfloat16*)n->x_planes;
+    e.x_rows = n->x_rows;
+    e.x_row0 = n->x_row0;
+    e.logits = n->logits;
+    e.row_stride = (size_t)n->logit_stride;
+    e.value = n->value;
+    return e;
+}
+
+// The ply loop of self-play (one network) and of the arena (two networks, each evaluating only its own games'
+// leaves): per ply  new games -> roots -> forward -> resign/terminal/expand -> ceil(S / K) x (select K leaves per game,
+// forward over the compacted leaves, expand + backup) -> move.  No host synchronisation anywhere: the forwards read
+// their batch size from the device counter the select kernel just filled.
+static int sp_play_loop(xq_ctx* c, MctsState& M, SpState& P, const SpConfig& k, const xq_net_plan* net0, const xq_net_plan* net1,
+                        int n_plies, cudaStream_t s)
+{
+    const int K = k.leaves_per_game;
+    if (int rc = mcts_reserve_leaves(c, &M, K)) return rc;
+    StepArgs A;
+    A.port[0] = port_of(net0);
+    A.port[1] = port_of(net1 ? net1 : net0);
+    A.arena = net1 ? 1 : 0;
+    A.K = K;
+    const int kind = net0->logits_kind;
+    const int nb = blocks_for(M.n_games), nt = kSelWarps * 32;
+    const int steps = (k.num_simulations + K - 1) / K;
+    auto run_nets = [&]() -> int {
+        int rc = xq_net_run_counted(c, net0->layers, net0->n_layers, net0->vfeats, net0->w1t, net0->b1, net0->w2, net0->b2, net0->value,
+                                    M.n_eval + 0, net0->batch, (void*)s);
+        if (rc || !net1) return rc;
+        return xq_net_run_counted(c, net1->layers, net1->n_layers, net1->vfeats, net1->w1t, net1->b1, net1->w2, net1->b2, net1->value,
+                                  M.n_eval + 1, net1->batch, (void*)s);
+    };
+    for (int ply = 0; ply < n_plies; ++ply) {
+        const unsigned long long pi = P.ply_counter++;
+        sp_new_games_kernel<<<nb, nt, 0, s>>>(M, P, k, pi);
+        set_int_kernel<<<1, 1, 0, s>>>(M.alloc, M.max_games);
+        XQ_CUDA(c, cudaMemsetAsync(M.n_eval, 0, 2 * sizeof(int), s));
+        sp_root_begin_kernel<<<nb, nt, 0, s>>>(M, P, A);
+        c->launches += 3;
+        int rc = run_nets();
+        if (rc) return rc;
+        if (kind == 1) sp_after_root_kernel<1><<<nb, nt, 0, s>>>(M, P, k, A, pi);
+        else sp_after_root_kernel<2><<<nb, nt, 0, s>>>(M, P, k, A, pi);
+        c->launches += 1;
+        for (int step = 0; step < steps; ++step) {
+            XQ_CUDA(c, cudaMemsetAsync(M.n_eval, 0, 2 * sizeof(int), s));
+            mcts_select_multi_kernel<<<nb, nt, 0, s>>>(M, P, (double)k.c_puct, A);
+            rc = run_nets();
+            if (rc) return rc;
+            if (kind == 1) mcts_expand_backup_multi_kernel<1><<<nb, nt, 0, s>>>(M, P, A);
+            else mcts_expand_backup_multi_kernel<2><<<nb, nt, 0, s>>>(M, P, A);
+            c->launches += 2;
+        }
+        sp_end_move_kernel<<<nb, nt, 0, s>>>(M, P, k, pi);
+        c->launches += 1;
+        XQ_CUDA(c, cudaGetLastError());
+    }
+    return XQ_OK;
+}
+
 extern "C" int xq_selfplay_play(xq_ctx* c, const xq_selfplay_config* cfg, const xq_net_plan* net, int n_plies, void* stream)
 {
     SpState* Pp = c ? SP_(c) : nullptr;
@@ -1044,63 +1447,17 @@ extern "C" int xq_selfplay_play(xq_ctx* c, const xq_selfplay_config* cfg, const 
     k.target_games = cfg->target_games < P.max_games_total ? cfg->target_games : P.max_games_total;
     k.arena = 0;
     k.move_log = nullptr;
-    const int nb = blocks_for(M.n_games), nt = kSelWarps * 32;
-    auto run_net = [&]() {
-        return xq_net_run(c, net->layers, net->n_layers, net->vfeats, net->w1t, net->b1, net->w2, net->b2, net->value, net->batch, stream);
-    };
-    for (int ply = 0; ply < n_plies; ++ply) {
-        const unsigned long long pi = P.ply_counter++;
-        sp_new_games_kernel<<<nb, nt, 0, s>>>(M, P, k, pi);
-        set_int_kernel<<<1, 1, 0, s>>>(M.alloc, M.max_games);
-        mcts_root_begin_kernel<<<nb, nt, 0, s>>>(M, nullptr, (__nv_bfloat16*)net->x_planes, net->x_rows, net->x_row0, nullptr, nullptr);
-        c->launches += 3;
-        int rc = run_net();
-        if (rc) return rc;
-        if (net->logits_kind == 1)
-            sp_after_root_kernel<1><<<nb, nt, 0, s>>>(M, P, k, net->logits, (size_t)net->logit_stride, net->value, pi);
-        else
-            sp_after_root_kernel<2><<<nb, nt, 0, s>>>(M, P, k, net->logits, (size_t)net->logit_stride, net->value, pi);
-        c->launches += 1;
-        for (int sim = 0; sim < k.num_simulations; ++sim) {
-            mcts_select_kernel<<<nb, nt, 0, s>>>(M, (double)k.c_puct, nullptr, (__nv_bfloat16*)net->x_planes, net->x_rows, net->x_row0,
-                                                 nullptr, nullptr);
-            rc = run_net();
-            if (rc) return rc;
-            if (net->logits_kind == 1)
-                mcts_expand_backup_kernel<1><<<nb, nt, 0, s>>>(M, net->logits, (size_t)net->logit_stride, net->value);
-            else
-                mcts_expand_backup_kernel<2><<<nb, nt, 0, s>>>(M, net->logits, (size_t)net->logit_stride, net->value);
-            c->launches += 2;
-        }
-        sp_end_move_kernel<<<nb, nt, 0, s>>>(M, P, k, pi);
-        c->launches += 1;
-        XQ_CUDA(c, cudaGetLastError());
-    }
-    return XQ_OK;
+    k.leaves_per_game = cfg->leaves_per_game > 1 ? cfg->leaves_per_game : 1;
+    if ((long long)P.n_slots * k.leaves_per_game > net->batch)
+        return xq_fail(c, XQ_ERR_ARG, "xq_selfplay_play: %d slots x %d leaves per game exceed the network batch %d", P.n_slots,
+                       k.leaves_per_game, net->batch);
+    return sp_play_loop(c, M, P, k, net, nullptr, n_plies, s);
 }
 
 // ---- evaluation arena: new model vs best model (train.py:453-535) -------------------------------------------
 // Game uid plays with the NEW model as red when uid is even (train.py:474).  Every search belongs to the player to
-// move at the ROOT; both networks evaluate every batch and this kernel overwrites the new model's outputs with the
-// old model's for the games whose root player is the old model.
-namespace xq {
-__global__ void __launch_bounds__(256)
-arena_blend_kernel(MctsState M, SpState P, void* logits_new, const void* logits_old, size_t row_bytes, float* value_new,
-                   const float* value_old)
-{
-    const int g = blockIdx.x;
-    if (g >= M.n_games || P.status[g] != 1) return;
-    const int uid = P.game_uid[g];
-    const int root_side = M.meta[g * 4 + 0];
-    const bool uses_new = ((uid & 1) == 0) == (root_side == 1);
-    if (uses_new) return;
-    uint4* d = reinterpret_cast<uint4*>((char*)logits_new + (size_t)g * row_bytes);
-    const uint4* s = reinterpret_cast<const uint4*>((const char*)logits_old + (size_t)g * row_bytes);
-    for (size_t i = threadIdx.x; i < row_bytes / 16; i += blockDim.x) d[i] = s[i];
-    if (threadIdx.x == 0) value_new[g] = value_old[g];
-}
-}  // namespace xq
-
+// move at the ROOT, so a game's leaves go to that player's network only (sp_port_of): each forward is sized to its
+// own share of the leaves.
 extern "C" int xq_arena_play(xq_ctx* c, const xq_selfplay_config* cfg, const xq_net_plan* net_new, const xq_net_plan* net_old,
                              int n_plies, int16_t* d_move_log, void* stream)
 {
@@ -1132,52 +1489,11 @@ extern "C" int xq_arena_play(xq_ctx* c, const xq_selfplay_config* cfg, const xq_
     k.target_games = cfg->target_games < P.max_games_total ? cfg->target_games : P.max_games_total;
     k.arena = 1;
     k.move_log = d_move_log;
-    const int nb = blocks_for(M.n_games), nt = kSelWarps * 32;
-    const size_t x_bytes = (size_t)2 * (size_t)net_new->x_rows * 8 * 2;        // bf16 [2][x_rows][8]
-    const size_t row_bytes = (size_t)net_new->logit_stride * (net_new->logits_kind == 1 ? 2 : 4);
-    auto run_both = [&]() -> int {
-        XQ_CUDA(c, cudaMemcpyAsync(net_old->x_planes, net_new->x_planes, x_bytes, cudaMemcpyDeviceToDevice, s));
-        int rc = xq_net_run(c, net_new->layers, net_new->n_layers, net_new->vfeats, net_new->w1t, net_new->b1, net_new->w2,
-                            net_new->b2, net_new->value, net_new->batch, stream);
-        if (rc) return rc;
-        rc = xq_net_run(c, net_old->layers, net_old->n_layers, net_old->vfeats, net_old->w1t, net_old->b1, net_old->w2,
-                        net_old->b2, net_old->value, net_old->batch, stream);
-        if (rc) return rc;
-        arena_blend_kernel<<<M.n_games, 256, 0, s>>>(M, P, (void*)net_new->logits, net_old->logits, row_bytes, net_new->value,
-                                                     net_old->value);
-        c->launches += 1;
-        return XQ_OK;
-    };
-    for (int ply = 0; ply < n_plies; ++ply) {
-        const unsigned long long pi = P.ply_counter++;
-        sp_new_games_kernel<<<nb, nt, 0, s>>>(M, P, k, pi);
-        set_int_kernel<<<1, 1, 0, s>>>(M.alloc, M.max_games);
-        mcts_root_begin_kernel<<<nb, nt, 0, s>>>(M, nullptr, (__nv_bfloat16*)net_new->x_planes, net_new->x_rows, net_new->x_row0, nullptr,
-                                                 nullptr);
-        c->launches += 3;
-        int rc = run_both();
-        if (rc) return rc;
-        if (net_new->logits_kind == 1)
-            sp_after_root_kernel<1><<<nb, nt, 0, s>>>(M, P, k, net_new->logits, (size_t)net_new->logit_stride, net_new->value, pi);
-        else
-            sp_after_root_kernel<2><<<nb, nt, 0, s>>>(M, P, k, net_new->logits, (size_t)net_new->logit_stride, net_new->value, pi);
-        c->launches += 1;
-        for (int sim = 0; sim < k.num_simulations; ++sim) {
-            mcts_select_kernel<<<nb, nt, 0, s>>>(M, (double)k.c_puct, nullptr, (__nv_bfloat16*)net_new->x_planes, net_new->x_rows,
-                                                 net_new->x_row0, nullptr, nullptr);
-            rc = run_both();
-            if (rc) return rc;
-            if (net_new->logits_kind == 1)
-                mcts_expand_backup_kernel<1><<<nb, nt, 0, s>>>(M, net_new->logits, (size_t)net_new->logit_stride, net_new->value);
-            else
-                mcts_expand_backup_kernel<2><<<nb, nt, 0, s>>>(M, net_new->logits, (size_t)net_new->logit_stride, net_new->value);
-            c->launches += 2;
-        }
-        sp_end_move_kernel<<<nb, nt, 0, s>>>(M, P, k, pi);
-        c->launches += 1;
-        XQ_CUDA(c, cudaGetLastError());
-    }
-    return XQ_OK;
+    k.leaves_per_game = cfg->leaves_per_game > 1 ? cfg->leaves_per_game : 1;
+    if ((long long)P.n_slots * k.leaves_per_game > net_new->batch)
+        return xq_fail(c, XQ_ERR_ARG, "xq_arena_play: %d slots x %d leaves per game exceed the network batch %d", P.n_slots,
+                       k.leaves_per_game, net_new->batch);
+    return sp_play_loop(c, M, P, k, net_new, net_old, n_plies, s);
 }
 
 // device pointers of the sample records and per-game results, for consumers that stay on the GPU (the replay ring)

@@ -392,6 +392,56 @@ is_attacked_kernel(const int8_t* __restrict__ boards, const uint8_t* __restrict_
     }
 }
 
+// cy_find_king (game_core.pyx:78-101, 493-505): the side's king searched ONLY in its own 3x3 palace, row-major;
+// out = row*9+col, or -1 when there is none (the reference returns None)
+__global__ void __launch_bounds__(128)
+find_king_kernel(const int8_t* __restrict__ boards, const int8_t* __restrict__ sides, int B, int8_t* __restrict__ out)
+{
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= B) return;
+    const int8_t* b = boards + (size_t)i * kSquares;
+    const int side = sides[i];
+    const int target = side == 1 ? 1 : -1, r0 = side == 1 ? 0 : 7;
+    int found = -1;
+    for (int r = r0 + 2; r >= r0; --r)
+        for (int c = 5; c >= 3; --c)
+            if (b[r * 9 + c] == target) found = r * 9 + c;      // descending scan: the first match in row-major order wins
+    out[i] = (int8_t)found;
+}
+
+// cy_has_legal_moves (game_core.pyx:558-569) = _generate_moves(...) > 0, from the counts of a movegen launch
+__global__ void __launch_bounds__(256) nonzero_kernel(const uint8_t* __restrict__ n, int B, uint8_t* __restrict__ out)
+{
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < B) out[i] = n[i] ? 1 : 0;
+}
+
+// get_state_for_nn (game.py:618-640) as bits: word w of a position holds plane-major bits 32w .. 32w+31, bit
+// index = plane*90 + square (1350 bits in 43 words, padded to 44 = 176 bytes; 5400 bytes as float32)
+__global__ void __launch_bounds__(256)
+planes_bits_kernel(const int8_t* __restrict__ boards, const int8_t* __restrict__ sides, int B, uint32_t* __restrict__ out)
+{
+    const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (t >= (long long)B * kPlaneWords) return;
+    const int i = (int)(t / kPlaneWords), w = (int)(t - (long long)i * kPlaneWords);
+    const int8_t* b = boards + (size_t)i * kSquares;
+    const int side = sides[i];
+    uint32_t bits = 0;
+    for (int k = 0; k < 32; ++k) {
+        const int e = w * 32 + k;
+        if (e >= 15 * kSquares) break;
+        const int p = e / kSquares, sq = e - p * kSquares;
+        bool on;
+        if (p == 14) on = side == 1;
+        else {
+            const int v = b[sq] * side;
+            on = (v > 0 ? v - 1 : (v < 0 ? 6 - v : -1)) == p;
+        }
+        bits |= (on ? 1u : 0u) << k;
+    }
+    out[t] = bits;
+}
+
 // ---- random playouts: one warp per game ----------------------------------------------------
 constexpr int kPlayWarps = 4;
 
@@ -509,6 +559,7 @@ extern "C" void xq_destroy(xq_ctx* c)
         if (c->d_stage[i]) cudaFree(c->d_stage[i]);
     }
     if (c->d_overflow) cudaFree(c->d_overflow);
+    if (c->d_scratch) cudaFree(c->d_scratch);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     delete c;
@@ -645,9 +696,27 @@ static int ensure_pipe(xq_ctx* c, size_t bytes)
     return XQ_OK;
 }
 
+extern "C" int xq_planes_bits(xq_ctx* c, const int8_t* d_boards, const int8_t* d_sides, int B, uint32_t* d_bits, void* stream);
+
+static int movegen_host_impl(xq_ctx* c, const int8_t* h_boards, const int8_t* h_sides, int B, int16_t* h_actions, uint8_t* h_n_moves,
+                             uint8_t* h_in_check, float* h_planes, uint32_t* h_plane_bits);
+
 extern "C" int xq_movegen_batch_host(xq_ctx* c, const int8_t* h_boards, const int8_t* h_sides, int B,
                                      int16_t* h_actions, uint8_t* h_n_moves, uint8_t* h_in_check,
                                      float* h_planes)
+{
+    return movegen_host_impl(c, h_boards, h_sides, B, h_actions, h_n_moves, h_in_check, h_planes, nullptr);
+}
+
+extern "C" int xq_movegen_batch_host_packed(xq_ctx* c, const int8_t* h_boards, const int8_t* h_sides, int B,
+                                            int16_t* h_actions, uint8_t* h_n_moves, uint8_t* h_in_check,
+                                            uint32_t* h_plane_bits)
+{
+    return movegen_host_impl(c, h_boards, h_sides, B, h_actions, h_n_moves, h_in_check, nullptr, h_plane_bits);
+}
+
+static int movegen_host_impl(xq_ctx* c, const int8_t* h_boards, const int8_t* h_sides, int B, int16_t* h_actions, uint8_t* h_n_moves,
+                             uint8_t* h_in_check, float* h_planes, uint32_t* h_plane_bits)
 {
     if (!c) return xq_fail(nullptr, XQ_ERR_ARG, "xq_movegen_batch_host: ctx is NULL");
     if (B < 0 || (B > 0 && (!h_boards || !h_sides || !h_actions || !h_n_moves || !h_in_check)))
@@ -661,7 +730,7 @@ extern "C" int xq_movegen_batch_host(xq_ctx* c, const int8_t* h_boards, const in
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const size_t o_boards = 0, o_sides = al(o_boards + (size_t)chunk * 90), o_act = al(o_sides + chunk),
                  o_n = al(o_act + (size_t)chunk * 256), o_chk = al(o_n + chunk), o_pl = al(o_chk + chunk),
-                 total = o_pl + (h_planes ? (size_t)chunk * 5400 : 0);
+                 total = o_pl + (h_planes ? (size_t)chunk * 5400 : (h_plane_bits ? (size_t)chunk * kPlaneWords * 4 : 0));
     (void)per_pos;
     int rc = ensure_pipe(c, total);
     if (rc) return rc;
@@ -682,6 +751,12 @@ extern "C" int xq_movegen_batch_host(xq_ctx* c, const int8_t* h_boards, const in
         XQ_CUDA(c, cudaMemcpyAsync(h_in_check + off, d + o_chk, (size_t)n, cudaMemcpyDeviceToHost, s));
         if (h_planes)
             XQ_CUDA(c, cudaMemcpyAsync(h_planes + (size_t)off * 1350, d + o_pl, (size_t)n * 5400, cudaMemcpyDeviceToHost, s));
+        if (h_plane_bits) {
+            rc = xq_planes_bits(c, (const int8_t*)(d + o_boards), (const int8_t*)(d + o_sides), n, (uint32_t*)(d + o_pl), s);
+            if (rc) return rc;
+            XQ_CUDA(c, cudaMemcpyAsync(h_plane_bits + (size_t)off * kPlaneWords, d + o_pl, (size_t)n * kPlaneWords * 4,
+                                       cudaMemcpyDeviceToHost, s));
+        }
     }
     XQ_CUDA(c, cudaStreamSynchronize(c->pipe[0]));
     XQ_CUDA(c, cudaStreamSynchronize(c->pipe[1]));
@@ -731,6 +806,93 @@ extern "C" int xq_is_attacked_batch_host(xq_ctx* c, const int8_t* h_boards, cons
     if (rc) return rc;
     XQ_CUDA(c, cudaMemcpyAsync(h_out, d + o_out, (size_t)B, cudaMemcpyDeviceToHost, s));
     XQ_CUDA(c, cudaStreamSynchronize(s));
+    return XQ_OK;
+}
+
+extern "C" int xq_find_king_batch(xq_ctx* c, const int8_t* d_boards, const int8_t* d_sides, int B, int8_t* d_king_sq, void* stream)
+{
+    if (!c) return xq_fail(nullptr, XQ_ERR_ARG, "xq_find_king_batch: ctx is NULL");
+    if (B < 0 || (B > 0 && (!d_boards || !d_sides || !d_king_sq))) return xq_fail(c, XQ_ERR_ARG, "xq_find_king_batch: bad arguments (B=%d)", B);
+    if (B == 0) return XQ_OK;
+    find_king_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_boards, d_sides, B, d_king_sq);
+    c->launches += 1;
+    XQ_CUDA(c, cudaGetLastError());
+    return XQ_OK;
+}
+
+static int ensure_pipe(xq_ctx* c, size_t bytes);
+
+// grow-only device scratch of the context (outputs a caller did not ask for)
+static int ensure_scratch(xq_ctx* c, size_t bytes)
+{
+    if (c->scratch_bytes >= bytes) return XQ_OK;
+    if (c->d_scratch) XQ_CUDA(c, cudaFree(c->d_scratch));
+    c->d_scratch = nullptr;
+    c->scratch_bytes = 0;
+    XQ_CUDA(c, cudaMalloc(&c->d_scratch, bytes));
+    c->scratch_bytes = bytes;
+    return XQ_OK;
+}
+
+extern "C" int xq_has_legal_moves_batch(xq_ctx* c, const int8_t* d_boards, const int8_t* d_sides, int B, uint8_t* d_has, void* stream)
+{
+    if (!c) return xq_fail(nullptr, XQ_ERR_ARG, "xq_has_legal_moves_batch: ctx is NULL");
+    if (B < 0 || (B > 0 && (!d_boards || !d_sides || !d_has))) return xq_fail(c, XQ_ERR_ARG, "xq_has_legal_moves_batch: bad arguments (B=%d)", B);
+    if (B == 0) return XQ_OK;
+    XQ_CUDA(c, cudaSetDevice(c->device));
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t o_n = al((size_t)B * 256), o_chk = al(o_n + B);
+    int rc = ensure_scratch(c, o_chk + B);
+    if (rc) return rc;
+    char* d = (char*)c->d_scratch;
+    rc = xq_movegen_batch(c, d_boards, d_sides, B, (int16_t*)d, (uint8_t*)(d + o_n), (uint8_t*)(d + o_chk), nullptr, stream);
+    if (rc) return rc;
+    nonzero_kernel<<<(B + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const uint8_t*)(d + o_n), B, d_has);
+    c->launches += 1;
+    XQ_CUDA(c, cudaGetLastError());
+    return XQ_OK;
+}
+
+// host-pointer forms of the two queries above (the per-position calls a game.py-level binding makes)
+static int seam_query_host(xq_ctx* c, const int8_t* h_boards, const int8_t* h_sides, int B, void* h_out, bool king)
+{
+    if (!c) return xq_fail(nullptr, XQ_ERR_ARG, "xq_*_batch_host: ctx is NULL");
+    if (B < 0 || (B > 0 && (!h_boards || !h_sides || !h_out))) return xq_fail(c, XQ_ERR_ARG, "xq_*_batch_host: bad arguments (B=%d)", B);
+    if (B == 0) return XQ_OK;
+    XQ_CUDA(c, cudaSetDevice(c->device));
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t o_s = al((size_t)B * 90), o_out = al(o_s + B);
+    int rc = ensure_pipe(c, o_out + B);
+    if (rc) return rc;
+    cudaStream_t s = c->pipe[0];
+    char* d = (char*)c->d_stage[0];
+    XQ_CUDA(c, cudaMemcpyAsync(d, h_boards, (size_t)B * 90, cudaMemcpyHostToDevice, s));
+    XQ_CUDA(c, cudaMemcpyAsync(d + o_s, h_sides, (size_t)B, cudaMemcpyHostToDevice, s));
+    rc = king ? xq_find_king_batch(c, (const int8_t*)d, (const int8_t*)(d + o_s), B, (int8_t*)(d + o_out), s)
+              : xq_has_legal_moves_batch(c, (const int8_t*)d, (const int8_t*)(d + o_s), B, (uint8_t*)(d + o_out), s);
+    if (rc) return rc;
+    XQ_CUDA(c, cudaMemcpyAsync(h_out, d + o_out, (size_t)B, cudaMemcpyDeviceToHost, s));
+    XQ_CUDA(c, cudaStreamSynchronize(s));
+    return XQ_OK;
+}
+extern "C" int xq_find_king_batch_host(xq_ctx* c, const int8_t* h_boards, const int8_t* h_sides, int B, int8_t* h_king_sq)
+{
+    return seam_query_host(c, h_boards, h_sides, B, h_king_sq, true);
+}
+extern "C" int xq_has_legal_moves_batch_host(xq_ctx* c, const int8_t* h_boards, const int8_t* h_sides, int B, uint8_t* h_has)
+{
+    return seam_query_host(c, h_boards, h_sides, B, h_has, false);
+}
+
+extern "C" int xq_planes_bits(xq_ctx* c, const int8_t* d_boards, const int8_t* d_sides, int B, uint32_t* d_bits, void* stream)
+{
+    if (!c) return xq_fail(nullptr, XQ_ERR_ARG, "xq_planes_bits: ctx is NULL");
+    if (B < 0 || (B > 0 && (!d_boards || !d_sides || !d_bits))) return xq_fail(c, XQ_ERR_ARG, "xq_planes_bits: bad arguments (B=%d)", B);
+    if (B == 0) return XQ_OK;
+    const long long n = (long long)B * kPlaneWords;
+    planes_bits_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_boards, d_sides, B, d_bits);
+    c->launches += 1;
+    XQ_CUDA(c, cudaGetLastError());
     return XQ_OK;
 }
 

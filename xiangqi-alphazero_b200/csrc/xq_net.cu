@@ -56,7 +56,22 @@ struct GemmArgs {
     uint8_t* out;
     float* out2;
     const uint4* tapmask;    // [45][9] disable-output-lane masks (NetState)
+    const int* n_dev;        // optional DEVICE board count (<= n_boards): the launch sizes itself to it (leaf compaction)
 };
+
+// boards / 128-row tiles this launch really has: the host's figures, cut down to the device-side count if there is one
+__device__ __forceinline__ void live_size(const GemmArgs& p, int rows_per_board, int* n_boards, int* m_tiles)
+{
+    *n_boards = p.n_boards;
+    *m_tiles = p.m_tiles;
+    if (p.n_dev) {
+        const int nd = *p.n_dev;
+        if (nd < p.n_boards) {
+            *n_boards = nd < 0 ? 0 : nd;
+            *m_tiles = (int)(((long long)*n_boards * rows_per_board + 127) / 128);
+        }
+    }
+}
 
 // per-context state of this translation unit
 struct NetState {
@@ -219,9 +234,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(const GemmArgs p,
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int tap_groups = Cfg::kTaps / TPS;
-    const int m_pairs = (p.m_tiles + 1) / 2;
+    int live_boards, live_tiles;
+    live_size(p, kBoardRows, &live_boards, &live_tiles);
+    const int m_pairs = (live_tiles + 1) / 2;
     const int total = m_pairs * p.n_tiles;
-    const long long real_rows = (long long)p.n_boards * kBoardRows;
+    const long long real_rows = (long long)live_boards * kBoardRows;
 
     __shared__ __align__(16) float sBias[256];
     for (int i = threadIdx.x; i < p.n_tiles * NT && i < 256; i += kConvThreads) sBias[i] = p.bias[i];
@@ -493,7 +510,10 @@ static int ensure_smem_attr(xq_ctx* c, K kern, int bit)
 {
     NetState* N = net_state(c);
     if (!(N->attr_done & (1u << bit))) {
-        XQ_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+        cudaFuncAttributes fa;
+        XQ_CUDA(c, cudaFuncGetAttributes(&fa, kern));
+        // 227 KB per CTA in all: what the kernel's static __shared__ arrays do not take is opened for dynamic use
+        XQ_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - (int)fa.sharedSizeBytes));
         N->attr_done |= 1u << bit;
     }
     return XQ_OK;
@@ -545,15 +565,18 @@ static int launch_conv(xq_ctx* c, GemmArgs& a, cudaStream_t s, int bit)
 // =============================================================================================
 // fc_kernel: dense layer (policy FC 2880 -> 8100) in the conv kernel's style
 // =============================================================================================
-// One CTA per SM, a 256-board x 128-output work item (two M tiles share each weight stage, one MMA-issuing
-// thread per tile), stages of KCH_ x 8 input features (W + A of both tiles; the two M tiles are adjacent rows of
-// the A planes so a chunk is ONE 4 KB bulk copy), accumulators double buffered in TMEM (2 x 2 x 128 columns),
-// epilogue on 8 warps.  Both operands stream, so the kernel is bound by shared-memory bandwidth (operand reads of
-// the MMAs + the bulk copies' writes = 14 KB per MMA against 128 B/clk).
-template <int KCH_, int STAGES_>
+// Both operands stream, so what bounds the layer is shared-memory bandwidth (128 B/clk per SM): the operand reads
+// of the MMAs plus the bulk copies' writes.  Work item = 256 boards x NT = 224 outputs: two M = 128 tiles share
+// every stage, each with ONE N = 224 MMA per 16 input features (A 4 KB + B 7 KB read per MMA, 15 KB of stage
+// written per K step: 165 B/clk at full tensor rate, against 219 B/clk for the first generation's 256 x 128 items
+// of N = 128 MMAs).  37 x 224 = 8288 >= 8100 columns x 16 board pairs = 592 items = exactly 4 per SM at batch 4096.
+// The two 224-column accumulators fill TMEM (no double buffering): the epilogue of an item (8 warps) is exposed,
+// ~2 us of ~28, while the producer keeps prefetching the next item's stages.
+template <int NT_, int KCH_, int STAGES_>
 struct FcCfgT {
+    static constexpr int kNT = NT_;
     static constexpr int kKch = KCH_;                          // 8 input features per chunk
-    static constexpr int kWBytes = kKch * 128 * 16;
+    static constexpr int kWBytes = kKch * NT_ * 16;
     static constexpr int kABytes = kKch * 256 * 16;
     static constexpr int kStage = kWBytes + kABytes;
     static constexpr int kStages = STAGES_;
@@ -563,19 +586,21 @@ struct FcCfgT {
 template <class FcCfg>
 __global__ void __launch_bounds__(kConvThreads, 1) fc_kernel(const GemmArgs p)
 {
-    constexpr int S = FcCfg::kStages, TS = 128, NT = 128;
+    constexpr int S = FcCfg::kStages, NT = FcCfg::kNT;
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * FcCfg::kStage);
     uint64_t* w_full = bars;
     uint64_t* w_empty = bars + S;
-    uint64_t* t_full = bars + 2 * S;          // [2 accumulator stages][2 tiles]
-    uint64_t* t_empty = t_full + 4;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 4);
-    __shared__ __align__(16) float sBias[2][128];
+    uint64_t* t_full = bars + 2 * S;          // [2 tiles]
+    uint64_t* t_empty = t_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+    __shared__ __align__(16) float sBias[2][256];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int iters = p.kchunks / FcCfg::kKch;
-    const int m_pairs = (p.m_tiles + 1) / 2;
+    int live_boards, live_tiles;
+    live_size(p, 1, &live_boards, &live_tiles);
+    const int m_pairs = (live_tiles + 1) / 2;
     const int total = m_pairs * p.n_tiles;
     const uint4 nomask = make_uint4(0, 0, 0, 0);
 
@@ -584,7 +609,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) fc_kernel(const GemmArgs p)
             mbar_init(&w_full[i], 1);
             mbar_init(&w_empty[i], 2);
         }
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 2; ++i) {
             mbar_init(&t_full[i], 1);
             mbar_init(&t_empty[i], 4);
         }
@@ -628,17 +653,15 @@ __global__ void __launch_bounds__(kConvThreads, 1) fc_kernel(const GemmArgs p)
             int s = 0;
             uint32_t ph = 0;
             int n = 0;
+            const uint32_t d_addr = tmem_base + (uint32_t)(t * 256);
             for (int work = blockIdx.x; work < total; work += gridDim.x, ++n) {
-                const int acc = n & 1;
-                const uint32_t tph = (uint32_t)(n >> 1) & 1u;
-                mbar_wait(&t_empty[acc * 2 + t], tph ^ 1);
+                mbar_wait(&t_empty[t], (uint32_t)(n & 1) ^ 1u);
                 tc_fence_after();
-                const uint32_t d_addr = tmem_base + (uint32_t)(acc * 2 * TS + t * TS);
                 for (int it = 0; it < iters; ++it) {
                     mbar_wait(&w_full[s], ph);
                     tc_fence_after();
                     const uint32_t st = smem_u32(smem + s * FcCfg::kStage);
-                    const uint32_t b_lo = ((st >> 4) & 0x3FFFu) | ((2048u >> 4) << 16);
+                    const uint32_t b_lo = ((st >> 4) & 0x3FFFu) | ((uint32_t)((NT * 16) >> 4) << 16);
                     const uint32_t a_lo = (((st + FcCfg::kWBytes + (uint32_t)t * 2048u) >> 4) & 0x3FFFu) | ((4096u >> 4) << 16);
 #pragma unroll
                     for (int j = 0; j < FcCfg::kKch / 2; ++j) {
@@ -649,7 +672,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) fc_kernel(const GemmArgs p)
                     umma_commit(&w_empty[s]);
                     if (++s == S) { s = 0; ph ^= 1; }
                 }
-                umma_commit(&t_full[acc * 2 + t]);
+                umma_commit(&t_full[t]);
             }
         }
     } else {
@@ -660,46 +683,46 @@ __global__ void __launch_bounds__(kConvThreads, 1) fc_kernel(const GemmArgs p)
         int n = 0;
         for (int work = blockIdx.x; work < total; work += gridDim.x, ++n) {
             const int pair = work / p.n_tiles, n_tile = work - pair * p.n_tiles;
-            const int acc = n & 1;
-            const uint32_t tph = (uint32_t)(n >> 1) & 1u;
+            const int bb = n & 1;
             const long long m = (long long)pair * 256 + t * 128 + row;
-            const bool real = m < (long long)p.n_boards;
-            // this work item's 128 bias values -> shared memory (double buffered by item parity)
-            if (et < 128) sBias[acc][et] = p.bias[n_tile * NT + et];
+            const bool real = m < (long long)live_boards;
+            // this work item's bias values -> shared memory (double buffered by item parity)
+            if (et < NT) sBias[bb][et] = p.bias[n_tile * NT + et];
             asm volatile("bar.sync 1, 256;" ::: "memory");
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 * TS + t * TS);
-            mbar_wait(&t_full[acc * 2 + t], tph);
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 256);
+            mbar_wait(&t_full[t], (uint32_t)(n & 1));
             tc_fence_after();
             auto emit = [&](const uint32_t* v, const int c0) {
                 if (!real) return;
                 uint4* dst = reinterpret_cast<uint4*>(p.out + ((size_t)m * p.out_stride + (size_t)(n_tile * NT + c0)) * 2);
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
-                    const float4 b0 = *reinterpret_cast<const float4*>(&sBias[acc][c0 + g * 8]);
-                    const float4 b1 = *reinterpret_cast<const float4*>(&sBias[acc][c0 + g * 8 + 4]);
+                    const float4 b0 = *reinterpret_cast<const float4*>(&sBias[bb][c0 + g * 8]);
+                    const float4 b1 = *reinterpret_cast<const float4*>(&sBias[bb][c0 + g * 8 + 4]);
                     dst[g] = make_uint4(pack_bf16(__uint_as_float(v[g * 8 + 0]) + b0.x, __uint_as_float(v[g * 8 + 1]) + b0.y),
                                         pack_bf16(__uint_as_float(v[g * 8 + 2]) + b0.z, __uint_as_float(v[g * 8 + 3]) + b0.w),
                                         pack_bf16(__uint_as_float(v[g * 8 + 4]) + b1.x, __uint_as_float(v[g * 8 + 5]) + b1.y),
                                         pack_bf16(__uint_as_float(v[g * 8 + 6]) + b1.z, __uint_as_float(v[g * 8 + 7]) + b1.w));
                 }
             };
+            constexpr int kSlabs = NT / 32;
             uint32_t va[32], vb[32];
             tmem_ld32(taddr, va);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < kSlabs; ++i) {
                 if (i & 1) {
-                    if (i + 1 < 4) tmem_ld32(taddr + (uint32_t)((i + 1) * 32), va);
+                    if (i + 1 < kSlabs) tmem_ld32(taddr + (uint32_t)((i + 1) * 32), va);
                     emit(vb, i * 32);
                 } else {
-                    if (i + 1 < 4) tmem_ld32(taddr + (uint32_t)((i + 1) * 32), vb);
+                    if (i + 1 < kSlabs) tmem_ld32(taddr + (uint32_t)((i + 1) * 32), vb);
                     emit(va, i * 32);
                 }
-                if (i + 1 < 4) tmem_ld_wait();
+                if (i + 1 < kSlabs) tmem_ld_wait();
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&t_empty[acc * 2 + t]);
+            if (lane == 0) mbar_arrive(&t_empty[t]);
         }
     }
 
@@ -713,6 +736,7 @@ static int launch_fc(xq_ctx* c, const GemmArgs& a, cudaStream_t s, int bit)
 {
     if (int rc = ensure_smem_attr(c, fc_kernel<FcCfg>, bit)) return rc;
     if (a.kchunks % FcCfg::kKch) return xq_fail(c, XQ_ERR_ARG, "fc: K/8 = %d is not a multiple of %d", a.kchunks, FcCfg::kKch);
+    if ((long long)a.n_tiles * FcCfg::kNT > a.out_stride) return xq_fail(c, XQ_ERR_ARG, "fc: %d tiles of %d columns exceed the output stride %lld", a.n_tiles, FcCfg::kNT, a.out_stride);
     const int total = ((a.m_tiles + 1) / 2) * a.n_tiles;
     const int grid = c->sm_count < total ? c->sm_count : total;
     fc_kernel<FcCfg><<<grid, kConvThreads, FcCfg::kSmem, s>>>(a);
@@ -729,8 +753,10 @@ constexpr int kVhBoards = 32;
 constexpr int kVhChunk = 40;    // k rows staged per step
 __global__ void __launch_bounds__(128) value_head_kernel(const float* __restrict__ feats, const float* __restrict__ w1t,
                                                           const float* __restrict__ b1, const float* __restrict__ w2,
-                                                          float b2, float* __restrict__ value, int B)
+                                                          float b2, float* __restrict__ value, int B, const int* __restrict__ n_dev)
 {
+    if (n_dev) B = min(B, *n_dev);
+    if ((int)(blockIdx.x * kVhBoards) >= B) return;
     __shared__ __align__(16) float wsm[kVhChunk][128];
     __shared__ __align__(16) float fsm[kVhChunk][kVhBoards];     // transposed: [k][board]
     const int b0 = blockIdx.x * kVhBoards;
@@ -800,7 +826,7 @@ extern "C" void xq_net_free_(xq_ctx* c)
 
 // n_boards_now > 0 overrides the descriptor's board count (and tile counts): the self-play loop sizes every
 // launch to the leaves that are really waiting for an evaluation.
-static int net_gemm(xq_ctx* c, const xq_gemm_desc* d, int n_boards_now, cudaStream_t s)
+static int net_gemm(xq_ctx* c, const xq_gemm_desc* d, int n_boards_now, const int* n_dev, cudaStream_t s)
 {
     if (!c || !d) return xq_fail(c, XQ_ERR_ARG, "xq_net_gemm: NULL argument");
     if (!d->a || !d->w || !d->bias || !d->out || d->m_tiles <= 0 || d->n_tiles <= 0 || d->kchunks <= 0)
@@ -828,12 +854,11 @@ static int net_gemm(xq_ctx* c, const xq_gemm_desc* d, int n_boards_now, cudaStre
     a.out = (uint8_t*)d->out;
     a.out2 = (float*)d->out2;
     a.tapmask = nullptr;
+    a.n_dev = n_dev;
     XQ_CUDA(c, cudaSetDevice(c->device));
     XqTimer tm(c, s);
-    if (d->mode == 2 && d->nt == 128 && d->kch_iter == 8 && d->kchunks % 8 == 0) {
-        if (d->kchunks % 12 == 0) return launch_fc<FcCfgT<12, 3>>(c, a, s, 0);
-        return launch_fc<FcCfgT<8, 4>>(c, a, s, 1);
-    }
+    if (d->mode == 2 && d->nt == 224 && d->kch_iter == 8 && d->kchunks % 8 == 0) return launch_fc<FcCfgT<224, 8, 3>>(c, a, s, 0);
+    if (d->mode == 2 && d->nt == 128 && d->kch_iter == 8 && d->kchunks % 8 == 0) return launch_fc<FcCfgT<128, 8, 4>>(c, a, s, 1);
     if (d->mode == 0 && d->nt == 128 && d->kch_iter == 8 && d->a_row0 >= kHalo) {
         // 128-channel layers: 3 taps per weight stage (48 KB x 3 stages): a stage hand-off costs an MMA-issuing
         // thread ~0.2 us, so fewer, larger stages beat a finer ring; wider layers only have room for 16 KB stages
@@ -850,19 +875,25 @@ static int net_gemm(xq_ctx* c, const xq_gemm_desc* d, int n_boards_now, cudaStre
                    d->nt, d->kch_iter, d->kchunks, d->n_tiles, (long long)d->a_row0);
 }
 
-extern "C" int xq_net_gemm(xq_ctx* c, const xq_gemm_desc* d, void* stream) { return net_gemm(c, d, 0, (cudaStream_t)stream); }
+extern "C" int xq_net_gemm(xq_ctx* c, const xq_gemm_desc* d, void* stream) { return net_gemm(c, d, 0, nullptr, (cudaStream_t)stream); }
 
-extern "C" int xq_net_value_head(xq_ctx* c, const float* d_feats, const float* d_w1t, const float* d_b1,
-                                 const float* d_w2, float b2, float* d_value, int B, void* stream)
+static int net_value_head(xq_ctx* c, const float* d_feats, const float* d_w1t, const float* d_b1, const float* d_w2, float b2,
+                          float* d_value, int B, const int* n_dev, cudaStream_t s)
 {
     if (!c || !d_feats || !d_w1t || !d_b1 || !d_w2 || !d_value || B < 0)
         return xq_fail(c, XQ_ERR_ARG, "xq_net_value_head: bad arguments");
     if (B == 0) return XQ_OK;
     XQ_CUDA(c, cudaSetDevice(c->device));
-    value_head_kernel<<<(B + kVhBoards - 1) / kVhBoards, 128, 0, (cudaStream_t)stream>>>(d_feats, d_w1t, d_b1, d_w2, b2, d_value, B);
+    value_head_kernel<<<(B + kVhBoards - 1) / kVhBoards, 128, 0, s>>>(d_feats, d_w1t, d_b1, d_w2, b2, d_value, B, n_dev);
     c->launches += 1;
     XQ_CUDA(c, cudaGetLastError());
     return XQ_OK;
+}
+
+extern "C" int xq_net_value_head(xq_ctx* c, const float* d_feats, const float* d_w1t, const float* d_b1,
+                                 const float* d_w2, float b2, float* d_value, int B, void* stream)
+{
+    return net_value_head(c, d_feats, d_w1t, d_b1, d_w2, b2, d_value, B, nullptr, (cudaStream_t)stream);
 }
 
 // Run a whole forward (a list of layer descriptors followed by the value head) for the first B boards.
@@ -872,8 +903,23 @@ extern "C" int xq_net_run(xq_ctx* c, const xq_gemm_desc* layers, int n_layers, c
 {
     if (B <= 0) return XQ_OK;
     for (int i = 0; i < n_layers; ++i) {
-        int rc = net_gemm(c, &layers[i], B, (cudaStream_t)stream);
+        int rc = net_gemm(c, &layers[i], B, nullptr, (cudaStream_t)stream);
         if (rc) return rc;
     }
-    return xq_net_value_head(c, d_vfeats, d_w1t, d_b1, d_w2, b2, d_value, B, stream);
+    return net_value_head(c, d_vfeats, d_w1t, d_b1, d_w2, b2, d_value, B, nullptr, (cudaStream_t)stream);
+}
+
+// Same with the board count on the DEVICE (*d_n_boards, clamped to max_boards): the grids are sized for max_boards and
+// every kernel cuts its tile loop to the live count, so a caller that compacts its leaves never synchronises.
+extern "C" int xq_net_run_counted(xq_ctx* c, const xq_gemm_desc* layers, int n_layers, const float* d_vfeats,
+                                  const float* d_w1t, const float* d_b1, const float* d_w2, float b2, float* d_value,
+                                  const int* d_n_boards, int max_boards, void* stream)
+{
+    if (max_boards <= 0) return XQ_OK;
+    if (!d_n_boards) return xq_fail(c, XQ_ERR_ARG, "xq_net_run_counted: d_n_boards is NULL");
+    for (int i = 0; i < n_layers; ++i) {
+        int rc = net_gemm(c, &layers[i], max_boards, d_n_boards, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
+    return net_value_head(c, d_vfeats, d_w1t, d_b1, d_w2, b2, d_value, max_boards, d_n_boards, (cudaStream_t)stream);
 }

@@ -49,6 +49,7 @@ class XiangqiNet(nn.Module):
                                         nn.Tanh())
         self._b200 = None
         self._b200_version = None
+        self._weights_generation = 0      # bumped by anything that rewrites the parameters through raw pointers (FlatAdam.step)
 
     def forward(self, x):
         out = self.input_conv(x)
@@ -58,7 +59,15 @@ class XiangqiNet(nn.Module):
 
     # ---- inference on the B200 kernels --------------------------------------------------------
     def _state_version(self):
-        return tuple(int(p._version) for p in self.state_dict().values())
+        """Changes whenever the weights may have changed: torch's in-place version counters (optimizer.step of a torch
+        optimiser, load_state_dict, BatchNorm statistics updates) plus the explicit generation counter for writers
+        torch cannot see (FlatAdam steps the flat parameter buffer through xq_adam_step's raw pointers)."""
+        return (self._weights_generation,) + tuple(int(p._version) for p in self.state_dict().values())
+
+    def invalidate_b200(self):
+        """Drop the kernel-side weight copy: the next predict()/b200() folds the current parameters again."""
+        self._weights_generation += 1
+        self._b200 = None
 
     def b200(self, max_batch: int = 1, device: int = 0) -> "B200Net":
         """Kernel-side copy of the current weights (rebuilt when the parameters change)."""
@@ -97,7 +106,9 @@ class _GemmDesc(C.Structure):
 ROW0 = 16            # plane row of logical row 0 (front padding, >= 10 rows: the A block of the first tile starts 10 rows early)
 BOARD_ROWS = 90      # plane rows per board: cell (r, c) of board b at row ROW0 + b*90 + r*9 + c, no halo (csrc/xq_net.cu)
 TAP_ORDER = [4, 0, 1, 2, 3, 5, 6, 7, 8]   # weight-image tap k -> 3x3 cell kh*3+kw: the (unmasked) centre tap is issued first
-LOGIT_STRIDE = 8192  # 8100 padded to 64 tiles of 128
+FC_NT = 224          # output columns per FC work item (one N = 224 MMA per tile and K step, csrc/xq_net.cu fc_kernel)
+FC_TILES = 37        # 37 x 224 = 8288 >= 8100
+LOGIT_STRIDE = 8320  # row stride of the logits (>= FC_TILES * FC_NT, multiple of 64 elements)
 
 
 def fold_bn(conv_w, bn):
@@ -211,13 +222,13 @@ class B200Net:
                                          out2=self.vfeat.data_ptr()))
             # policy FC 2880 -> 8100: torch flatten index ch*90+pos  ->  kernel index pos*32+ch
             wf = m.policy_head[4].weight.detach().float().reshape(ACTION_SPACE, 32, 90).permute(0, 2, 1)
-            wfp = torch.zeros((LOGIT_STRIDE, 2880))
+            wfp = torch.zeros((FC_TILES * FC_NT, 2880))
             wfp[:ACTION_SPACE] = wf.reshape(ACTION_SPACE, 2880)
-            bfp = torch.zeros(LOGIT_STRIDE)
+            bfp = torch.zeros(FC_TILES * FC_NT)
             bfp[:ACTION_SPACE] = m.policy_head[4].bias.detach().float()
-            img = dev_t(conv_image(wfp.reshape(LOGIT_STRIDE, 2880, 1, 1), 128, 8))
+            img = dev_t(conv_image(wfp.reshape(FC_TILES * FC_NT, 2880, 1, 1), FC_NT, 8))
             bias = dev_t(bfp, torch.float32)
-            self.layers.append(_GemmDesc(mode=2, m_tiles=self.b_tiles, n_tiles=LOGIT_STRIDE // 128, nt=128,
+            self.layers.append(_GemmDesc(mode=2, m_tiles=self.b_tiles, n_tiles=FC_TILES, nt=FC_NT,
                                          kchunks=360, kch_iter=8, relu=0, n_boards=B, a_rows=self.fc_rows, a_row0=0,
                                          out_rows=0, out_row0=0, out_stride=LOGIT_STRIDE, a=self.fc_in.data_ptr(),
                                          w=img.data_ptr(), bias=bias.data_ptr(), residual=None,

@@ -22,7 +22,8 @@ class _SpConfig(C.Structure):
     _fields_ = [("num_simulations", C.c_int32), ("c_puct", C.c_float), ("temperature_threshold", C.c_int32),
                 ("max_game_length", C.c_int32), ("random_opening_moves", C.c_int32), ("enable_resign", C.c_int32),
                 ("resign_threshold", C.c_float), ("resign_check_steps", C.c_int32), ("add_noise", C.c_int32),
-                ("dirichlet_alpha", C.c_float), ("seed", C.c_uint64), ("target_games", C.c_int32)]
+                ("dirichlet_alpha", C.c_float), ("seed", C.c_uint64), ("target_games", C.c_int32),
+                ("leaves_per_game", C.c_int32)]
 
 
 class _NetPlan(C.Structure):
@@ -73,8 +74,12 @@ def decode_samples(raw: np.ndarray):
 
 class SelfPlayEngine:
     def __init__(self, eng: "xq_native.Engine", model, n_slots: int, max_games: int, sample_capacity=None,
-                 node_capacity: int = 0, max_simulations: int = 800):
+                 node_capacity: int = 0, max_simulations: int = 800, leaves_per_game: int = 1):
+        """leaves_per_game = K: 1 runs the reference's search (one simulation per game and step, visit counts bit-exact);
+        K > 1 is the opt-in virtual-loss mode (K descents per game and step share one forward: the batch is n_slots * K
+        leaves, which is what fills the tensor cores when only a few games are in flight)."""
         self.e = eng
+        self.leaves_per_game = max(1, int(leaves_per_game))
         self.n_slots = int(n_slots)
         self.max_games = int(max_games)
         self.max_simulations = int(max_simulations)
@@ -94,7 +99,7 @@ class SelfPlayEngine:
 
     def set_model(self, model):
         """(Re)build the kernel-side weights: the 'hot update' of inference_server.py:479-496."""
-        self.net = B200Net(self.e, model, max_batch=self.n_slots)
+        self.net = B200Net(self.e, model, max_batch=self.n_slots * self.leaves_per_game)
         n = self.net
         self.plan = _NetPlan(layers=n.desc_array, n_layers=n.n_layers, batch=n.max_batch, vfeats=n.vfeat.data_ptr(),
                              w1t=n.w1t.data_ptr(), b1=n.b1.data_ptr(), w2=n.w2.data_ptr(), b2=n.b2,
@@ -102,7 +107,7 @@ class SelfPlayEngine:
                              logits=n.logits.data_ptr(), logit_stride=LOGIT_STRIDE, logits_kind=1)
 
     @staticmethod
-    def make_config(config, target_games, seed=0, add_noise=True):
+    def make_config(config, target_games, seed=0, add_noise=True, leaves_per_game=1):
         """TrainingConfig / worker dict (parallel_selfplay.py:184-187) -> xq_selfplay_config."""
         g = (lambda k, d=None: config.get(k, d)) if isinstance(config, dict) else (lambda k, d=None: getattr(config, k, d))
         return _SpConfig(num_simulations=int(g("num_simulations", 200)), c_puct=float(g("c_puct", 1.5)),
@@ -112,7 +117,8 @@ class SelfPlayEngine:
                          enable_resign=int(bool(g("enable_resign", True))),
                          resign_threshold=float(g("resign_threshold", -0.9)),
                          resign_check_steps=int(g("resign_check_steps", 5)), add_noise=int(bool(add_noise)),
-                         dirichlet_alpha=0.3, seed=int(seed) & 0xFFFFFFFFFFFFFFFF, target_games=int(target_games))
+                         dirichlet_alpha=0.3, seed=int(seed) & 0xFFFFFFFFFFFFFFFF, target_games=int(target_games),
+                         leaves_per_game=int(leaves_per_game))
 
     def _own(self):
         if getattr(self.e, "_selfplay_owner", None) is not self:
@@ -126,6 +132,9 @@ class SelfPlayEngine:
 
     def play(self, cfg: _SpConfig, n_plies: int):
         self._own()
+        if cfg.leaves_per_game > self.leaves_per_game:
+            raise xq_native.XqError(f"leaves_per_game {cfg.leaves_per_game} exceeds the {self.leaves_per_game} this SelfPlayEngine "
+                                    "(its network batch) was built for")
         if cfg.num_simulations > self.max_simulations:
             raise xq_native.XqError(f"num_simulations {cfg.num_simulations} exceeds the node pool sized for "
                                     f"{self.max_simulations}: build the SelfPlayEngine with max_simulations >= it")

@@ -86,6 +86,11 @@ class TrainingConfig:
         # additions of this build
         self.selfplay_slots = 4096      # concurrent games per GPU
         self.sync_batchnorm = True      # data parallel: BatchNorm statistics over the GLOBAL minibatch (reference semantics)
+        # opt-in multi-leaf search (virtual loss): descents per game and lockstep step.  1 = the reference's search
+        # (mcts.py:126-153, one simulation at a time).  > 1 trades the exact visit sequence for a fuller tensor-core
+        # batch when few games are in flight (evaluation's eval_games, small num_games_per_iter).
+        self.selfplay_leaves_per_game = 1
+        self.eval_leaves_per_game = 1
 
 
 class SelfPlayDataset(torch.utils.data.Dataset):
@@ -214,6 +219,7 @@ class FlatAdam(optim.Adam):
                              'exp_avg_sq': self.flat_v[off:off + k].view_as(p)}
             off += k
         self._params = params
+        self._model = model
 
     def zero_grad(self, set_to_none: bool = False):
         self.flat_g.zero_()
@@ -224,8 +230,15 @@ class FlatAdam(optim.Adam):
         for p in self._params:
             k = p.numel()
             st = self.state[p]
-            self.flat_m[off:off + k].copy_(st['exp_avg'].reshape(-1))
-            self.flat_v[off:off + k].copy_(st['exp_avg_sq'].reshape(-1))
+            if 'exp_avg' not in st:
+                # a checkpoint written before the first optimizer.step (train.py:543: the reference saves whatever
+                # Adam holds, which is nothing while the buffer is below min_buffer_size): start from zero moments
+                self.flat_m[off:off + k].zero_()
+                self.flat_v[off:off + k].zero_()
+                st['step'] = torch.tensor(0.0)
+            else:
+                self.flat_m[off:off + k].copy_(st['exp_avg'].reshape(-1))
+                self.flat_v[off:off + k].copy_(st['exp_avg_sq'].reshape(-1))
             st['exp_avg'] = self.flat_m[off:off + k].view_as(p)
             st['exp_avg_sq'] = self.flat_v[off:off + k].view_as(p)
             self.steps = int(float(st['step']))
@@ -253,6 +266,12 @@ class FlatAdam(optim.Adam):
                                   e._stream()))
         for p in self._params:
             self.state[p]['step'] = torch.tensor(float(self.steps))
+        # the kernels wrote the parameters through raw pointers: torch's version counters did not move, so tell the
+        # model that its kernel-side (folded bf16) weight copy is stale
+        if hasattr(self._model, "invalidate_b200"):
+            self._model.invalidate_b200()
+        elif hasattr(self._model, "_weights_generation"):
+            self._model._weights_generation += 1
         return None
 
 
@@ -373,16 +392,19 @@ class AlphaZeroTrainer:
         if my_games > 0:
             slots = min(my_games, int(getattr(cfg, "selfplay_slots", 4096)))
             sims = int(cfg.num_simulations)
+            kl = max(1, int(getattr(cfg, "selfplay_leaves_per_game", 1)))
             sp = self._sp
             if (sp is None or getattr(self.eng, "_selfplay_owner", None) is not sp or sp.n_slots != slots
-                    or sp.max_games < my_games or sp.max_simulations < sims):
+                    or sp.max_games < my_games or sp.max_simulations < sims or sp.leaves_per_game != kl):
                 self._sp = None
-                sp = SelfPlayEngine(self.eng, self.best_model, n_slots=slots, max_games=my_games, max_simulations=sims)
+                sp = SelfPlayEngine(self.eng, self.best_model, n_slots=slots, max_games=my_games, max_simulations=sims,
+                                    leaves_per_game=kl)
                 self._sp = sp
             else:
                 sp.set_model(self.best_model)
             sp.reset()
-            spcfg = SelfPlayEngine.make_config(cfg, my_games, seed=int.from_bytes(os.urandom(8), 'big'), add_noise=True)
+            spcfg = SelfPlayEngine.make_config(cfg, my_games, seed=int.from_bytes(os.urandom(8), 'big'), add_noise=True,
+                                               leaves_per_game=kl)
             c = sp.play_games(spcfg)
             local.append_from_selfplay(sp, c["samples"])
             wins += torch.tensor([c["red_wins"], c["black_wins"], c["draws"], c["plies_finished"], c["finished"]],
@@ -454,7 +476,8 @@ class AlphaZeroTrainer:
             import xq_native
             self._arena_eng = xq_native.Engine(self.local_device)
         r = _arena.evaluate_models(self._arena_eng, self.current_model, self.best_model, int(cfg.eval_games), int(cfg.eval_simulations),
-                                   float(cfg.c_puct), int(cfg.max_game_length), dist=self.dist if self.world > 1 else None)
+                                   float(cfg.c_puct), int(cfg.max_game_length), dist=self.dist if self.world > 1 else None,
+                                   leaves_per_game=max(1, int(getattr(cfg, "eval_leaves_per_game", 1))))
         stats = {'new_wins': r['new_wins'], 'old_wins': r['old_wins'], 'draws': r['draws'], 'win_rate': r['win_rate'],
                  'model_updated': r['win_rate'] >= cfg.eval_win_rate}
         logger.info("evaluation: new %d old %d draw %d, win rate %.2f%%", r['new_wins'], r['old_wins'], r['draws'], 100 * r['win_rate'])

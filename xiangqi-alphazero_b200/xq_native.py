@@ -64,6 +64,12 @@ def lib():
     _sig(L, "xq_movegen_batch_host", i32, vp, vp, vp, i32, vp, vp, vp, vp)
     _sig(L, "xq_is_attacked_batch", i32, vp, vp, vp, vp, i32, vp, vp)
     _sig(L, "xq_is_attacked_batch_host", i32, vp, vp, vp, vp, i32, vp)
+    _sig(L, "xq_movegen_batch_host_packed", i32, vp, vp, vp, i32, vp, vp, vp, vp)
+    _sig(L, "xq_planes_bits", i32, vp, vp, vp, i32, vp, vp)
+    _sig(L, "xq_find_king_batch", i32, vp, vp, vp, i32, vp, vp)
+    _sig(L, "xq_find_king_batch_host", i32, vp, vp, vp, i32, vp)
+    _sig(L, "xq_has_legal_moves_batch", i32, vp, vp, vp, i32, vp, vp)
+    _sig(L, "xq_has_legal_moves_batch_host", i32, vp, vp, vp, i32, vp)
     _sig(L, "xq_overflow_count", i32, vp, i32)
     _sig(L, "xq_set_movegen_impl", i32, vp, i32)
     _sig(L, "xq_random_playouts", i32, vp, u64, i32, vp, vp, vp, vp, vp)
@@ -76,10 +82,12 @@ def lib():
     _sig(L, "xq_mcts_expand_backup", i32, vp, vp, i32, i64, vp, vp)
     _sig(L, "xq_mcts_leaf_info", i32, vp, vp, vp, vp, vp)
     _sig(L, "xq_mcts_root_visits", i32, vp, vp, vp, vp, vp, vp)
+    _sig(L, "xq_mcts_root_priors", i32, vp, vp, vp, vp)
     _sig(L, "xq_mcts_stats", i32, vp, C.POINTER(i64), i32)
     _sig(L, "xq_net_gemm", i32, vp, vp, vp)
     _sig(L, "xq_net_value_head", i32, vp, vp, vp, vp, vp, C.c_float, vp, i32, vp)
     _sig(L, "xq_net_run", i32, vp, vp, i32, vp, vp, vp, vp, C.c_float, vp, i32, vp)
+    _sig(L, "xq_net_run_counted", i32, vp, vp, i32, vp, vp, vp, vp, C.c_float, vp, vp, i32, vp)
     _sig(L, "xq_selfplay_create", i32, vp, i32, i32, i64, i64)
     _sig(L, "xq_selfplay_reset", i32, vp, vp)
     _sig(L, "xq_selfplay_play", i32, vp, vp, vp, i32, vp)
@@ -100,10 +108,11 @@ def lib():
 
 EXPORTS = ["xq_create", "xq_destroy", "xq_last_error", "xq_version", "xq_launch_count", "xq_set_timing",
            "xq_last_kernel_ms", "xq_movegen_batch", "xq_movegen_batch_host", "xq_is_attacked_batch",
-           "xq_is_attacked_batch_host", "xq_overflow_count", "xq_set_movegen_impl", "xq_random_playouts",
+           "xq_is_attacked_batch_host", "xq_movegen_batch_host_packed", "xq_planes_bits", "xq_find_king_batch",
+           "xq_find_king_batch_host", "xq_has_legal_moves_batch", "xq_has_legal_moves_batch_host", "xq_overflow_count", "xq_set_movegen_impl", "xq_random_playouts",
            "xq_mcts_create", "xq_mcts_set_games", "xq_mcts_root_begin", "xq_mcts_root_expand", "xq_mcts_select",
-           "xq_mcts_expand_backup", "xq_mcts_leaf_info", "xq_mcts_root_visits", "xq_mcts_stats",
-           "xq_net_gemm", "xq_net_value_head", "xq_net_run", "xq_selfplay_create", "xq_selfplay_reset",
+           "xq_mcts_expand_backup", "xq_mcts_leaf_info", "xq_mcts_root_visits", "xq_mcts_root_priors", "xq_mcts_stats",
+           "xq_net_gemm", "xq_net_value_head", "xq_net_run", "xq_net_run_counted", "xq_selfplay_create", "xq_selfplay_reset",
            "xq_selfplay_play", "xq_selfplay_counters", "xq_selfplay_fetch", "xq_selfplay_slots",
            "xq_selfplay_device_buffers", "xq_arena_play", "xq_replay_append", "xq_train_batch", "xq_policy_value_loss",
            "xq_grad_sumsq", "xq_adam_step"]
@@ -111,6 +120,17 @@ EXPORTS = ["xq_create", "xq_destroy", "xq_last_error", "xq_version", "xq_launch_
 
 def _np_ptr(a: np.ndarray):
     return C.c_void_p(a.ctypes.data)
+
+
+PLANE_WORDS = 44
+
+
+def unpack_planes(bits: np.ndarray) -> np.ndarray:
+    """uint32 [B,44] plane bits (xq_movegen_batch_host_packed / xq_planes_bits) -> float32 [B,15,10,9], the
+    get_state_for_nn planes of game.py:618-640 (bit plane*90+square at word bit>>5, bit bit&31)."""
+    bits = np.ascontiguousarray(bits, np.uint32).reshape(-1, PLANE_WORDS)
+    b = np.unpackbits(bits.view(np.uint8), axis=1, bitorder="little")[:, :1350]
+    return b.reshape(-1, 15, 10, 9).astype(np.float32)
 
 
 class Engine:
@@ -199,23 +219,68 @@ class Engine:
                                             self._stream()))
         return actions, n, chk, pl
 
-    def movegen_host(self, boards: np.ndarray, sides: np.ndarray, planes: bool = False, out=None):
+    def movegen_host(self, boards: np.ndarray, sides: np.ndarray, planes=False, out=None):
         """Host arrays in, host arrays out (the reference-facing form: numpy boards, like
-        cy_generate_legal_moves).  Copies run inside the call; pass pinned arrays for full speed."""
+        cy_generate_legal_moves).  Copies run inside the call; pass pinned arrays for full speed.
+        planes: False, True (float32 [B,15,10,9], 5400 bytes per position over PCIe) or "packed" (uint32 [B,44]
+        plane bits, 176 bytes per position; unpack_planes() expands them on the host)."""
         boards = np.ascontiguousarray(boards, np.int8).reshape(-1, 90)
         sides = np.ascontiguousarray(sides, np.int8)
         B = boards.shape[0]
+        packed = isinstance(planes, str) and planes == "packed"
         if out is None:
             actions = np.empty((B, MAX_MOVES), np.int16)
             n = np.empty(B, np.uint8)
             chk = np.empty(B, np.uint8)
-            pl = np.empty((B, 15, 10, 9), np.float32) if planes else None
+            pl = np.empty((B, PLANE_WORDS), np.uint32) if packed else (np.empty((B, 15, 10, 9), np.float32) if planes else None)
         else:
             actions, n, chk, pl = out
-        rc = self.L.xq_movegen_batch_host(self.h, _np_ptr(boards), _np_ptr(sides), B, _np_ptr(actions), _np_ptr(n),
-                                          _np_ptr(chk), _np_ptr(pl) if pl is not None else None)
+        fn = self.L.xq_movegen_batch_host_packed if packed else self.L.xq_movegen_batch_host
+        rc = fn(self.h, _np_ptr(boards), _np_ptr(sides), B, _np_ptr(actions), _np_ptr(n), _np_ptr(chk),
+                _np_ptr(pl) if pl is not None else None)
         self._check(rc)
         return actions, n, chk, pl
+
+    def planes_bits(self, boards, sides):
+        """Device tensors: uint32-packed get_state_for_nn planes, int32 tensor [B,44] (bit pattern of the uint32 words)."""
+        t = self.torch
+        boards = boards.reshape(-1, 90).contiguous()
+        out = t.empty((boards.shape[0], PLANE_WORDS), dtype=t.int32, device=self.dev)
+        self._check(self.L.xq_planes_bits(self.h, boards.data_ptr(), sides.contiguous().data_ptr(), boards.shape[0],
+                                          out.data_ptr(), self._stream()))
+        return out
+
+    def find_king(self, boards, sides):
+        """cy_find_king batched: int8 [B] square (row*9+col) of side's king inside its own palace, -1 if absent."""
+        t = self.torch
+        boards = boards.reshape(-1, 90).contiguous()
+        out = t.empty((boards.shape[0],), dtype=t.int8, device=self.dev)
+        self._check(self.L.xq_find_king_batch(self.h, boards.data_ptr(), sides.contiguous().data_ptr(), boards.shape[0],
+                                              out.data_ptr(), self._stream()))
+        return out
+
+    def has_legal_moves(self, boards, sides):
+        """cy_has_legal_moves batched: uint8 [B]."""
+        t = self.torch
+        boards = boards.reshape(-1, 90).contiguous()
+        out = t.empty((boards.shape[0],), dtype=t.uint8, device=self.dev)
+        self._check(self.L.xq_has_legal_moves_batch(self.h, boards.data_ptr(), sides.contiguous().data_ptr(),
+                                                    boards.shape[0], out.data_ptr(), self._stream()))
+        return out
+
+    def find_king_host(self, boards: np.ndarray, sides: np.ndarray) -> np.ndarray:
+        boards = np.ascontiguousarray(boards, np.int8).reshape(-1, 90)
+        sides = np.ascontiguousarray(sides, np.int8)
+        out = np.empty(boards.shape[0], np.int8)
+        self._check(self.L.xq_find_king_batch_host(self.h, _np_ptr(boards), _np_ptr(sides), boards.shape[0], _np_ptr(out)))
+        return out
+
+    def has_legal_moves_host(self, boards: np.ndarray, sides: np.ndarray) -> np.ndarray:
+        boards = np.ascontiguousarray(boards, np.int8).reshape(-1, 90)
+        sides = np.ascontiguousarray(sides, np.int8)
+        out = np.empty(boards.shape[0], np.uint8)
+        self._check(self.L.xq_has_legal_moves_batch_host(self.h, _np_ptr(boards), _np_ptr(sides), boards.shape[0], _np_ptr(out)))
+        return out
 
     def is_attacked(self, boards, sq, by):
         t = self.torch
@@ -327,6 +392,14 @@ class MctsBatch:
         self.e._check(self.e.L.xq_mcts_root_visits(self.e.h, acts.data_ptr(), vis.data_ptr(), n.data_ptr(),
                                                    None if w is None else w.data_ptr(), self.e._stream()))
         return acts, vis, n, w
+
+    def root_priors(self):
+        """float64 [n,128] priors of the root children (after root_expand: with the Dirichlet mix when add_noise), n [n]."""
+        t, dev = self.t, self.e.dev
+        pri = t.empty((self.n, MAX_MOVES), dtype=t.float64, device=dev)
+        n = t.empty((self.n,), dtype=t.int32, device=dev)
+        self.e._check(self.e.L.xq_mcts_root_priors(self.e.h, pri.data_ptr(), n.data_ptr(), self.e._stream()))
+        return pri, n
 
     def stats(self, reset=False):
         buf = (C.c_longlong * 6)()
