@@ -66,6 +66,7 @@ def run(args, rank, world, local_rank, dist):
 
     sims = int(os.environ.get("XQ_BENCH_SIMS", SIMS))
     games = int(os.environ.get("XQ_BENCH_GAMES", GAMES_PER_GPU))
+    leaves = int(os.environ.get("XQ_BENCH_LEAVES", 1))   # > 1: opt-in multi-leaf (virtual loss) search, not the headline configuration
     torch.cuda.set_device(local_rank)
     eng = xq_native.Engine(local_rank)
     torch.manual_seed(20261018)                      # same random-init weights on every rank
@@ -74,9 +75,9 @@ def run(args, rank, world, local_rank, dist):
     cfgobj.num_simulations = sims
     total_plies = args.warmup + args.steps + 4
     sp = SelfPlayEngine(eng, model, n_slots=games, max_games=games * 4,
-                        sample_capacity=games * (2 * total_plies + 8), node_capacity=games * (sims + 1) * 48)
+                        sample_capacity=games * (2 * total_plies + 8), node_capacity=games * (sims + 1) * 48, leaves_per_game=leaves)
     sp.reset()
-    cfg = SelfPlayEngine.make_config(cfgobj, games * 4, seed=20261018 + rank, add_noise=True)
+    cfg = SelfPlayEngine.make_config(cfgobj, games * 4, seed=20261018 + rank, add_noise=True, leaves_per_game=leaves)
 
     def barrier():
         if world > 1:
@@ -187,8 +188,9 @@ def run(args, rank, world, local_rank, dist):
     # achieved = algorithmic FLOPs of every network evaluation in the timed region / the region's device time,
     # i.e. the whole step (search kernels, launch gaps, power-capped clocks) is charged to the tensor kernels
     achieved_tf = FLOPS_PER_EVAL * evals_done / world / (ms * 1e-3) / 1e12
-    isolated_tf = FLOPS_PER_EVAL * games / (fwd_ms * 1e-3) / 1e12
-    conv_flops = 2 * 90 * 9 * CHANNELS * CHANNELS * games          # algorithmic: 90 cells x 9 taps x C x C MACs per board
+    fwd_boards = sp.net.max_batch                                    # = games x leaves_per_game
+    isolated_tf = FLOPS_PER_EVAL * fwd_boards / (fwd_ms * 1e-3) / 1e12
+    conv_flops = 2 * 90 * 9 * CHANNELS * CHANNELS * fwd_boards          # algorithmic: 90 cells x 9 taps x C x C MACs per board
     conv_tf = conv_flops / (conv_ms * 1e-3) / 1e12
     # ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one tower conv at batch 4096 (profiles/r1_net_ncu.md)
     conv_traffic = {(128, 4096): 182.6e6, (256, 4096): None}.get((CHANNELS, games))
@@ -202,7 +204,7 @@ def run(args, rank, world, local_rank, dist):
         "metric": "mcts_sims_per_sec", "value": value, "unit": "sims/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic (seeded random-init weights, self-generated games)",
-        "config": workload_config(world, games, sims), "evals_in_region": evals_done,
+        "config": workload_config(world, games, sims), "evals_in_region": evals_done, "leaves_per_game": leaves,
         "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": achieved_tf / peak_tf,
                      "traffic": conv_traffic,

@@ -20,7 +20,7 @@
 //     off with the disable-output-lane mask of tcgen05.mma: bit i of the 128-bit mask keeps TMEM lane
 //     i (= output row i of the tile) from being updated by that MMA.  The masks depend only on
 //     (tile start row mod 90, tap), i.e. on tile_index mod 45: a 45 x 9 table of 16-byte masks built
-//     once per context and copied to shared memory by every CTA.  The centre tap is unmasked and is
+//     once per context into constant memory (a warp-uniform read lands in the uniform registers tcgen05.mma wants).  The centre tap is unmasked and is
 //     issued first (it initialises the accumulator).  Result: every executed MMA row is a real cell
 //     (the first generation carried a zero halo: 110 rows per board, 22 % of the MMAs wasted);
 //   * the epilogue stores 16 B per (chunk,row) with consecutive lanes on consecutive rows: fully
@@ -55,7 +55,6 @@ struct GemmArgs {
     const uint8_t* residual;
     uint8_t* out;
     float* out2;
-    const uint4* tapmask;    // [45][9] disable-output-lane masks (NetState)
     const int* n_dev;        // optional DEVICE board count (<= n_boards): the launch sizes itself to it (leaf compaction)
 };
 
@@ -75,7 +74,7 @@ __device__ __forceinline__ void live_size(const GemmArgs& p, int rows_per_board,
 
 // per-context state of this translation unit
 struct NetState {
-    uint4* d_tapmask = nullptr;
+    bool tapmask_done = false;
     uint32_t attr_done = 0;   // bit per kernel instantiation: dynamic shared-memory limit raised on THIS context's device
 };
 
@@ -170,6 +169,19 @@ __host__ __device__ constexpr int tap_cell(int k) { return k == 0 ? 4 : (k <= 4 
 __host__ __device__ constexpr int tap_dy(int k) { return tap_cell(k) / 3 - 1; }
 __host__ __device__ constexpr int tap_dx(int k) { return tap_cell(k) % 3 - 1; }
 
+// disable-output-lane masks, [tile phase][tap] (filled once per context's device by ensure_tapmask).  In constant
+// memory on purpose: tcgen05.mma takes its operands from UNIFORM registers, and a mask read with a warp-uniform index
+// from the constant bank lands there directly; from shared memory it took four register->uniform moves per MMA.
+__constant__ uint4 c_tapmask[kMaskPhases * 9];
+
+// one lane of the (converged) warp; the other lanes run the same uniform control flow next to it
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 constexpr int kConvThreads = 352;   // warp 0 producer, warps 1 and 10 MMA issuers (row tile 0 / 1), warps 2-9 epilogue
 constexpr int kMaxStages = 9;
 constexpr int kMaxSeg = 4;          // k-blocks of a layer (256 channels = 4 x 64)
@@ -185,7 +197,7 @@ struct ConvCfg {
     static constexpr int kTileCols = NT > 64 ? 128 : 64;
     static constexpr int kTmemCols = 4 * kTileCols;
     static constexpr int kTaps = HEADS ? 1 : 9;
-    static constexpr int kFixed = (HEADS ? 0 : kMaskBytes) + 768;           // mask table + barriers
+    static constexpr int kFixed = 768;                                       // barriers
     static constexpr int kBudget = 227 * 1024 - 1024 - 256;                 // per-CTA limit minus static bias minus slack
     // stages and A buffers for a layer with `kblocks` k-blocks: (stages, na), 0 stages = does not fit
     static void plan(int kblocks, int* stages, int* na)
@@ -222,8 +234,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(const GemmArgs p,
     const int kblocks = p.kchunks / KCH;
     uint8_t* sA = smem;                                         // [NA][kblocks][KCH][276][16 B]
     uint8_t* sStage = smem + NA * kblocks * Cfg::kSeg;          // [S][kWStage]
-    const uint4* sMask = reinterpret_cast<const uint4*>(sStage + S * Cfg::kWStage);   // [45][9] (3x3 layers only)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + S * Cfg::kWStage + (HEADS ? 0 : kMaskBytes));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + S * Cfg::kWStage);
     uint64_t* w_full = bars;                                    // [kMaxStages]
     uint64_t* w_empty = bars + kMaxStages;
     uint64_t* a_full = bars + 2 * kMaxStages;                   // [kMaxABufs]
@@ -232,7 +243,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(const GemmArgs p,
     uint64_t* t_empty = t_full + 4;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 4);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index through a shuffle: the compiler then knows it is warp-uniform (role tests, TMEM addresses and the
+    // MMA operands derived from it stay in uniform registers)
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     constexpr int tap_groups = Cfg::kTaps / TPS;
     int live_boards, live_tiles;
     live_size(p, kBoardRows, &live_boards, &live_tiles);
@@ -242,10 +255,6 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(const GemmArgs p,
 
     __shared__ __align__(16) float sBias[256];
     for (int i = threadIdx.x; i < p.n_tiles * NT && i < 256; i += kConvThreads) sBias[i] = p.bias[i];
-    if (!HEADS) {
-        uint4* dst = const_cast<uint4*>(sMask);
-        for (int i = threadIdx.x; i < kMaskPhases * 9; i += kConvThreads) dst[i] = __ldg(&p.tapmask[i]);
-    }
     if (threadIdx.x == 0) {
         for (int i = 0; i < S; ++i) {
             mbar_init(&w_full[i], 1);
@@ -317,11 +326,15 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(const GemmArgs p,
             }
         }
     } else if (warp == 1 || warp == 10) {
-        // ===================== MMA issuers: one thread per row tile =====================
-        // A single issuing thread spends ~0.2 us per stage hand-off (wait, fence, commit); two issuers interleave
-        // their MMAs and hide each other's hand-offs.
+        // ===================== MMA issuers: one warp per row tile =====================
+        // The whole warp runs the (uniform) loop and ONE elected lane issues the MMAs and commits: every MMA operand
+        // is then a warp-uniform value the compiler keeps in uniform registers.  (With the loop inside `if (lane == 0)`
+        // ptxas wrapped every tcgen05.mma in an elect / 9 x R2UR.BROADCAST / branch sequence, ~15 instructions per
+        // MMA on the critical issuing thread.)  Two issuers interleave their MMAs and hide each other's stage hand-offs
+        // (~0.2 us each: wait, fence, commit).
         const int t = warp == 1 ? 0 : 1;
-        if (lane == 0) {
+        const bool leader = elect_one();
+        {
             constexpr uint32_t idesc = make_idesc(128, NT);
             constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);            // SBO = 128 B, version 1
             constexpr uint32_t kLboA = (uint32_t)(kAPlane >> 4);
@@ -334,7 +347,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(const GemmArgs p,
                 const uint32_t tph = (uint32_t)(n >> 1) & 1u;
                 const int ab = (n % NA) * kblocks;
                 const uint32_t aph = (uint32_t)(n / NA) & 1u;
-                const uint4* mrow = sMask + ((pair * 2 + t) % kMaskPhases) * 9;
+                const int mphase = ((pair * 2 + t) % kMaskPhases) * 9;
                 mbar_wait(&t_empty[acc * 2 + t], tph ^ 1);
                 tc_fence_after();
                 const uint32_t d_addr = tmem_base + (uint32_t)(acc * 2 * TS + t * TS);
@@ -350,7 +363,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(const GemmArgs p,
                         for (int tp = 0; tp < TPS; ++tp) {
                             const int tap = tg * TPS + tp;
                             const int shift = HEADS ? 0 : tap_dy(tap) * 9 + tap_dx(tap);
-                            const uint4 mk = HEADS ? make_uint4(0, 0, 0, 0) : mrow[tap];
+                            const uint4 mk = HEADS ? make_uint4(0, 0, 0, 0) : c_tapmask[mphase + tap];
                             const uint32_t a_lo = a_seg + (uint32_t)(kHalo + shift);
                             const uint32_t b_lo = b_st + (uint32_t)(tp * (Cfg::kWTap >> 4));
                             const uint32_t first = (kb | tap) != 0 ? 1u : 0u;
@@ -358,17 +371,19 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(const GemmArgs p,
                             for (int j = 0; j < KCH / 2; ++j) {
                                 const uint64_t adesc = ((uint64_t)kDescHi << 32) | (uint64_t)(a_lo + (uint32_t)(2 * j) * kLboA + (uint32_t)(t * 128));
                                 const uint64_t bdesc = ((uint64_t)kDescHi << 32) | (uint64_t)(b_lo + (uint32_t)(2 * j * NT));
-                                umma_bf16(d_addr, adesc, bdesc, idesc, j == 0 ? first : 1u, mk);
+                                if (leader) umma_bf16(d_addr, adesc, bdesc, idesc, j == 0 ? first : 1u, mk);
                             }
                         }
                         if (!WRES) {
-                            umma_commit(&w_empty[s]);
+                            if (leader) umma_commit(&w_empty[s]);
                             if (++s == S) { s = 0; ph ^= 1; }
                         }
+                        __syncwarp();
                     }
-                    umma_commit(&a_empty[ab + kb]);              // this k-block's rows may be replaced by a later pair's
+                    if (leader) umma_commit(&a_empty[ab + kb]);  // this k-block's rows may be replaced by a later pair's
                 }
-                umma_commit(&t_full[acc * 2 + t]);
+                if (leader) umma_commit(&t_full[acc * 2 + t]);
+                __syncwarp();
             }
         }
     } else {
@@ -522,7 +537,7 @@ static int ensure_smem_attr(xq_ctx* c, K kern, int bit)
 static int ensure_tapmask(xq_ctx* c, cudaStream_t s)
 {
     NetState* N = net_state(c);
-    if (N->d_tapmask) return XQ_OK;
+    if (N->tapmask_done) return XQ_OK;
     static uint32_t h[kMaskPhases * 9 * 4];
     for (int ph = 0; ph < kMaskPhases; ++ph)
         for (int k = 0; k < 9; ++k) {
@@ -533,9 +548,10 @@ static int ensure_tapmask(xq_ctx* c, cudaStream_t s)
                 if (r < 0 || r > 9 || cc < 0 || cc > 8) w[i >> 5] |= 1u << (i & 31);   // source cell is off the board
             }
         }
-    XQ_CUDA(c, cudaMalloc(&N->d_tapmask, sizeof(h)));
-    XQ_CUDA(c, cudaMemcpyAsync(N->d_tapmask, h, sizeof(h), cudaMemcpyHostToDevice, s));
+    // the __constant__ symbol has one instance per device: this writes the one of the context's (current) device
+    XQ_CUDA(c, cudaMemcpyToSymbolAsync(c_tapmask, h, sizeof(h), 0, cudaMemcpyHostToDevice, s));
     XQ_CUDA(c, cudaStreamSynchronize(s));
+    N->tapmask_done = true;
     return XQ_OK;
 }
 
@@ -550,10 +566,8 @@ static int launch_conv(xq_ctx* c, GemmArgs& a, cudaStream_t s, int bit)
         return xq_fail(c, XQ_ERR_ARG, "conv kernel: %d k-blocks, %d stages, %d n-tiles do not fit", kblocks, S, a.n_tiles);
     auto kern = conv_kernel<NT, KCH, HEADS, TPS, WRES>;
     if (int rc = ensure_smem_attr(c, kern, bit)) return rc;
-    if (!HEADS) {
+    if (!HEADS)
         if (int rc = ensure_tapmask(c, s)) return rc;
-        a.tapmask = net_state(c)->d_tapmask;
-    }
     const int total = ((a.m_tiles + 1) / 2) * a.n_tiles;
     const int grid = c->sm_count < total ? c->sm_count : total;   // persistent, one CTA per SM
     kern<<<grid, kConvThreads, Cfg::smem_bytes(kblocks, S, NA), s>>>(a, S, NA);
@@ -596,7 +610,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) fc_kernel(const GemmArgs p)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
     __shared__ __align__(16) float sBias[2][256];
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
     const int iters = p.kchunks / FcCfg::kKch;
     int live_boards, live_tiles;
     live_size(p, 1, &live_boards, &live_tiles);
@@ -646,8 +660,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) fc_kernel(const GemmArgs p)
             }
         }
     } else if (warp == 1 || warp == 10) {
+        // the whole warp runs the loop, one elected lane issues (see conv_kernel): operands stay in uniform registers
         const int t = warp == 1 ? 0 : 1;
-        if (lane == 0) {
+        const bool leader = elect_one();
+        {
             constexpr uint32_t idesc = make_idesc(128, NT);
             constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);
             int s = 0;
@@ -667,12 +683,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) fc_kernel(const GemmArgs p)
                     for (int j = 0; j < FcCfg::kKch / 2; ++j) {
                         const uint64_t adesc = ((uint64_t)kDescHi << 32) | (uint64_t)(a_lo + (uint32_t)(2 * j) * (4096u >> 4));
                         const uint64_t bdesc = ((uint64_t)kDescHi << 32) | (uint64_t)(b_lo + (uint32_t)(2 * j * NT));
-                        umma_bf16(d_addr, adesc, bdesc, idesc, (it | j) != 0 ? 1u : 0u, nomask);
+                        if (leader) umma_bf16(d_addr, adesc, bdesc, idesc, (it | j) != 0 ? 1u : 0u, nomask);
                     }
-                    umma_commit(&w_empty[s]);
+                    if (leader) umma_commit(&w_empty[s]);
                     if (++s == S) { s = 0; ph ^= 1; }
+                    __syncwarp();
                 }
-                umma_commit(&t_full[t]);
+                if (leader) umma_commit(&t_full[t]);
+                __syncwarp();
             }
         }
     } else {
@@ -748,7 +766,9 @@ static int launch_fc(xq_ctx* c, const GemmArgs& a, cudaStream_t s, int bit)
 // ---- value head: Linear(360,128)+ReLU -> Linear(128,1) -> tanh (model.py:74-83) ----------------
 // feats [B][90][4] fp32 (already conv1x1+BN+ReLU) = [B][360] with k = pos*4+ch, w1t [360][128] fp32.
 // 32 boards per CTA, 4 warps; a thread owns 4 hidden units x 8 boards (32 accumulators): per k one 16-byte
-// read of W1^T (conflict-free) and two broadcast 16-byte reads of the features feed 32 FMAs.
+// read of W1^T (conflict-free) and two broadcast 16-byte reads of the features feed 32 FMAs.  The next 40-row chunk of
+// W1^T and of the features travels global -> registers while the current one is multiplied (the first version loaded,
+// synchronised and multiplied in turn and spent three quarters of its 38 us waiting for those loads).
 constexpr int kVhBoards = 32;
 constexpr int kVhChunk = 40;    // k rows staged per step
 __global__ void __launch_bounds__(128) value_head_kernel(const float* __restrict__ feats, const float* __restrict__ w1t,
@@ -761,27 +781,47 @@ __global__ void __launch_bounds__(128) value_head_kernel(const float* __restrict
     __shared__ __align__(16) float fsm[kVhChunk][kVhBoards];     // transposed: [k][board]
     const int b0 = blockIdx.x * kVhBoards;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int kWPer = kVhChunk * 32 / 128;                   // 10 float4 of W1^T per thread and chunk
+    constexpr int kFPer = (kVhBoards * (kVhChunk / 4) + 127) / 128;   // 3 (the last one partly used)
+    float4 wreg[kWPer], freg[kFPer];
+    auto fetch = [&](int k0) {
+#pragma unroll
+        for (int u = 0; u < kWPer; ++u)
+            wreg[u] = __ldg(reinterpret_cast<const float4*>(w1t + (size_t)k0 * 128) + threadIdx.x + u * 128);
+#pragma unroll
+        for (int u = 0; u < kFPer; ++u) {
+            const int i = threadIdx.x + u * 128, bb = i & 31, kq = i >> 5;     // consecutive lanes = consecutive boards
+            freg[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (kq < kVhChunk / 4 && b0 + bb < B)
+                freg[u] = __ldg(reinterpret_cast<const float4*>(feats + (size_t)(b0 + bb) * 360 + k0 + 4 * kq));
+        }
+    };
+    auto stash = [&]() {
+#pragma unroll
+        for (int u = 0; u < kWPer; ++u) reinterpret_cast<float4*>(&wsm[0][0])[threadIdx.x + u * 128] = wreg[u];
+#pragma unroll
+        for (int u = 0; u < kFPer; ++u) {
+            const int i = threadIdx.x + u * 128, bb = i & 31, kq = i >> 5;
+            if (kq < kVhChunk / 4) {
+                fsm[4 * kq + 0][bb] = freg[u].x;
+                fsm[4 * kq + 1][bb] = freg[u].y;
+                fsm[4 * kq + 2][bb] = freg[u].z;
+                fsm[4 * kq + 3][bb] = freg[u].w;
+            }
+        }
+    };
     float acc[8][4];
     {
         const float4 bb = *reinterpret_cast<const float4*>(b1 + 4 * lane);
 #pragma unroll
         for (int i = 0; i < 8; ++i) { acc[i][0] = bb.x; acc[i][1] = bb.y; acc[i][2] = bb.z; acc[i][3] = bb.w; }
     }
+    fetch(0);
     for (int k0 = 0; k0 < 360; k0 += kVhChunk) {
+        __syncthreads();                                  // everyone is done with the previous chunk
+        stash();
         __syncthreads();
-        for (int i = threadIdx.x; i < kVhChunk * 32; i += 128)
-            reinterpret_cast<float4*>(&wsm[0][0])[i] = __ldg(reinterpret_cast<const float4*>(w1t + (size_t)k0 * 128) + i);
-        // features: thread -> (board, 10 float4 of this chunk); written transposed
-        for (int i = threadIdx.x; i < kVhBoards * (kVhChunk / 4); i += 128) {
-            const int bb = i / (kVhChunk / 4), kk = (i - bb * (kVhChunk / 4)) * 4;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (b0 + bb < B) v = __ldg(reinterpret_cast<const float4*>(feats + (size_t)(b0 + bb) * 360 + k0 + kk));
-            fsm[kk + 0][bb] = v.x;
-            fsm[kk + 1][bb] = v.y;
-            fsm[kk + 2][bb] = v.z;
-            fsm[kk + 3][bb] = v.w;
-        }
-        __syncthreads();
+        if (k0 + kVhChunk < 360) fetch(k0 + kVhChunk);    // in flight during the multiply below
 #pragma unroll 4
         for (int k = 0; k < kVhChunk; ++k) {
             const float4 w = *reinterpret_cast<const float4*>(&wsm[k][4 * lane]);
@@ -819,7 +859,6 @@ extern "C" void xq_net_free_(xq_ctx* c)
 {
     if (!c || !c->net) return;
     NetState* N = reinterpret_cast<NetState*>(c->net);
-    if (N->d_tapmask) cudaFree(N->d_tapmask);
     delete N;
     c->net = nullptr;
 }
@@ -853,7 +892,6 @@ static int net_gemm(xq_ctx* c, const xq_gemm_desc* d, int n_boards_now, const in
     a.residual = (const uint8_t*)d->residual;
     a.out = (uint8_t*)d->out;
     a.out2 = (float*)d->out2;
-    a.tapmask = nullptr;
     a.n_dev = n_dev;
     XQ_CUDA(c, cudaSetDevice(c->device));
     XqTimer tm(c, s);
