@@ -250,12 +250,20 @@ def bench_movegen(args, rank, world, local_rank, dist):
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     h2d = NE * 91
     d2h = NE * (256 + 2 + 5400)
+    # the same call with the planes as bits (176 instead of 5400 bytes per position over PCIe)
+    import numpy as np
+    hp_out = h_out[:3] + (torch.empty((NE, 44), dtype=torch.int32).pin_memory().numpy().view(np.uint32),)
+    eng.movegen_host(hbn, hsn, planes="packed", out=hp_out)
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        eng.movegen_host(hbn, hsn, planes="packed", out=hp_out)
+    e2e_packed_s = (time.perf_counter() - t0) / e2e_steps
 
     # reductions over ranks: max time
     if world > 1:
-        t = torch.tensor([total_ms, kern_ms, e2e_s], device=eng.dev, dtype=torch.float64)
+        t = torch.tensor([total_ms, kern_ms, e2e_s, e2e_packed_s], device=eng.dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, kern_ms, e2e_s = t.tolist()
+        total_ms, kern_ms, e2e_s, e2e_packed_s = t.tolist()
     if rank != 0:
         return
     peaks, peak_kind = measured_peaks()
@@ -285,7 +293,9 @@ def bench_movegen(args, rank, world, local_rank, dist):
                      "kernel_ms": kern_ms},
         "cpu_baseline": cpu,
         "e2e": {"value": world * NE / e2e_s, "unit": "positions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "positions_per_step": NE},
+                "positions_per_step": NE, "api": "xq_movegen_batch_host (float32 planes: 97 % of the bytes over PCIe)",
+                "packed_planes": {"value": world * NE / e2e_packed_s, "unit": "positions/s", "h2d_bytes_per_step": h2d,
+                                  "d2h_bytes_per_step": NE * (256 + 2 + 176), "api": "xq_movegen_batch_host_packed"}},
         "gpu_launches": launches,
         "clocks": clocks,
     }

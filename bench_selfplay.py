@@ -129,9 +129,10 @@ def run(args, rank, world, local_rank, dist):
     k1.record()
     torch.cuda.synchronize()
     conv_ms = k0.elapsed_time(k1) / 20
+    fwd_boards = net.max_batch                                       # = games x leaves_per_game
 
-    # e2e: the same plies through the host-facing API -- per step the host uploads the step's control
-    # block and downloads that ply's sample records and counters (pinned host memory)
+    # e2e, engine level: the same plies through the host-facing engine calls -- per step the host uploads the step's
+    # control block and downloads that ply's sample records and counters (pinned host memory)
     h_raw = torch.empty((games * 2, SAMPLE_BYTES), dtype=torch.uint8).pin_memory().numpy()
     e2e_steps = max(1, min(args.steps, 3))
     barrier()
@@ -148,38 +149,68 @@ def run(args, rank, world, local_rank, dist):
     c2 = sp.counters()
     e2e_sims = c2["sims"] - s_before["sims"]
 
-    # secondary headline of BASELINE.json ("legal-move positions/sec"): K1 over 1M device-generated positions
+    # e2e through the reference's own entry point: parallel_selfplay.parallel_self_play(model, config) -> (data, stats)
+    # with HOST weights in (the fp32 state_dict is folded, converted and uploaded inside the call) and HOST samples out
+    # (sparse records downloaded, gathered over the ranks, densified on access).  Whole games from fresh openings,
+    # truncated to a ply budget by config.max_game_length like the reference arm; a simulation count is not returned by
+    # the contract, so it is counted the way the reference arm counts it: searched plies (samples / 2) x sims per move.
+    api = None
+    if not os.environ.get("XQ_BENCH_NO_API_E2E"):
+        import parallel_selfplay as ps
+
+        class ApiCfg(StdConfig):
+            pass
+        acfg = ApiCfg()
+        acfg.num_simulations = sims
+        acfg.max_game_length = 8                              # openings are 0..6 random plies: 2..8 searched plies per game
+        acfg.num_games_per_iter = games * world
+        acfg.selfplay_leaves_per_game = leaves
+        host_model = M.XiangqiNet(CHANNELS, BLOCKS).eval()
+        host_model.load_state_dict(model.state_dict())
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        data, stats = ps.parallel_self_play(host_model, acfg)
+        dense = data[:256]                                    # the dense (planes, policy[8100], z) tuples of the contract
+        api_s = time.perf_counter() - t0
+        rec_bytes = int(getattr(data, "records", np.zeros((0, 896), np.uint8)).nbytes)
+        wnet = ps._ENGINES[next(iter(ps._ENGINES))].net if ps._ENGINES else None
+        h2d_w = int(sum(t.numel() * t.element_size() for t in wnet.keep)) if wnet is not None else 0
+        api = {"value": stats["new_samples"] // 2 * sims / api_s, "seconds": api_s, "games": stats["games"],
+               "new_samples": stats["new_samples"], "dense_tuples_materialised": len(dense),
+               "h2d_bytes": h2d_w + 64, "d2h_bytes": rec_bytes // max(world, 1) + games * 3 + 14 * 8,
+               "config": f"{games * world} games, max_game_length 8 (2-8 searched plies after the random opening), {sims} sims/move"}
+        del data, dense
+        ps._ENGINES.clear()
+
+    # secondary headline of BASELINE.json ("legal-move positions/sec"): K1 over 1M device-generated positions, with its
+    # own end-to-end figure (host buffers through the C-ABI host call: float32 planes, and the 176-byte packed planes)
     mv = None
     try:
-        pb, ps_, _, _ = eng.random_playouts(20261018 + rank, 5600)
-        pb, ps_ = pb[:1_000_000].contiguous(), ps_[:1_000_000].contiguous()
-        outb = (torch.empty((pb.shape[0], 128), dtype=torch.int16, device=eng.dev), torch.empty((pb.shape[0],), dtype=torch.uint8, device=eng.dev),
-                torch.empty((pb.shape[0],), dtype=torch.uint8, device=eng.dev), torch.empty((pb.shape[0], 15, 10, 9), dtype=torch.float32, device=eng.dev))
-        for _ in range(3):
-            eng.movegen(pb, ps_, planes=True, out=outb)
-        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        m0.record()
-        for _ in range(5):
-            eng.movegen(pb, ps_, planes=True, out=outb)
-        m1.record()
-        torch.cuda.synchronize()
-        mv_ms = m0.elapsed_time(m1) / 5
-        mv = {"metric": "legal_move_positions_per_sec", "value": pb.shape[0] / (mv_ms * 1e-3), "unit": "positions/s (per GPU)",
-              "kernel": {"warp": "movegen_kernel<true>", "thread": "movegen_tpb_kernel<true>"}[eng.movegen_impl]
-                        + " (moves + in-check + fp32 planes)", "kernel_ms": mv_ms,
-              "achieved_gbs": 5563.4 * pb.shape[0] / (mv_ms * 1e-3) / 1e9,
-              "frac_of_hbm_peak": 5563.4 * pb.shape[0] / (mv_ms * 1e-3) / 1e9 / bench.measured_peaks()[0]["hbm_gbs"]}
-        del outb, pb, ps_
+        mv = movegen_block(eng, rank, world, args)
     except Exception as ex:   # never let the secondary line break the headline
-        mv = {"error": str(ex)[:200]}
+        mv = {"error": str(ex)[:300]}
+
+    # BASELINE configs[3]'s network (256 channels x 20 blocks) on the same kernels: 1 warm-up + 2 timed plies
+    c3 = None
+    if (CHANNELS, BLOCKS) == (128, 6) and not os.environ.get("XQ_BENCH_NO_CONFIGS3"):
+        try:
+            del sp, net
+            torch.cuda.empty_cache()
+            c3 = configs3_block(rank, world, local_rank, dist, sims)
+        except Exception as ex:
+            c3 = {"error": str(ex)[:300]}
 
     if world > 1:
-        t = torch.tensor([ms, e2e_s, fwd_ms, conv_ms], device=eng.dev, dtype=torch.float64)
+        t = torch.tensor([ms, e2e_s, fwd_ms, conv_ms, api["seconds"] if api else 0.0], device=eng.dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_s, fwd_ms, conv_ms = t.tolist()
+        ms, e2e_s, fwd_ms, conv_ms, api_max = t.tolist()
         cnt = torch.tensor([sims_done, evals_done, e2e_sims], device=eng.dev, dtype=torch.float64)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
         sims_done, evals_done, e2e_sims = cnt.tolist()
+        if api:
+            api["value"] = api["new_samples"] // 2 * sims / api_max        # every rank returns the union of the samples
+            api["seconds"] = api_max
     if rank != 0:
         return
     peaks, peak_kind = bench.measured_peaks()
@@ -188,12 +219,11 @@ def run(args, rank, world, local_rank, dist):
     # achieved = algorithmic FLOPs of every network evaluation in the timed region / the region's device time,
     # i.e. the whole step (search kernels, launch gaps, power-capped clocks) is charged to the tensor kernels
     achieved_tf = FLOPS_PER_EVAL * evals_done / world / (ms * 1e-3) / 1e12
-    fwd_boards = sp.net.max_batch                                    # = games x leaves_per_game
     isolated_tf = FLOPS_PER_EVAL * fwd_boards / (fwd_ms * 1e-3) / 1e12
     conv_flops = 2 * 90 * 9 * CHANNELS * CHANNELS * fwd_boards          # algorithmic: 90 cells x 9 taps x C x C MACs per board
     conv_tf = conv_flops / (conv_ms * 1e-3) / 1e12
-    # ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one tower conv at batch 4096 (profiles/r1_net_ncu.md)
-    conv_traffic = {(128, 4096): 182.6e6, (256, 4096): None}.get((CHANNELS, games))
+    # ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one tower conv at batch 4096 (profiles/r2_net_ncu.md)
+    conv_traffic = {(128, 4096): 142.5e6, (256, 4096): None}.get((CHANNELS, fwd_boards))
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cpu, why = reference_selfplay_rate(steps=1, warmup=1, sims=sims, plies=1)
@@ -209,11 +239,13 @@ def run(args, rank, world, local_rank, dist):
                      "frac": achieved_tf / peak_tf,
                      "traffic": conv_traffic,
                      "traffic_detail": {"unit": "MB per launch (ncu --set full, dram read + write, batch 4096, 128 channels)",
-                                        "conv4_kernel<128,8,0,3>": 182.6, "conv4_kernel<128,8,0,3> (+residual)": 306.3,
-                                        "fc4_kernel": 142.5, "algorithmic conv": 230.7, "source": "profiles/r1_net_ncu.md"},
+                                        "conv_kernel<128,8,0,3,0>": 142.5, "conv_kernel<128,8,0,3,0> (+residual)": 250.6,
+                                        "fc_kernel<224>": 144.9, "algorithmic conv (in + out, + residual)": [188.7, 283.1],
+                                        "note": "the write-back of a layer's output is partly absorbed by the 126 MB L2 before the next layer reads it",
+                                        "source": "profiles/r2_net_ncu.md"},
                      "peak_source": peak_kind + " (sustained bf16)",
-                     "kernel": f"conv4_kernel x{2 * BLOCKS + 2} + fc4_kernel (tcgen05 implicit-GEMM forward) + value_head_kernel",
-                     "dominant_kernel": {"name": f"conv4_kernel<{CHANNELS}->{CHANNELS}, 3x3> (residual tower, {2 * BLOCKS} launches per forward)",
+                     "kernel": f"conv_kernel x{2 * BLOCKS + 2} + fc_kernel (tcgen05 implicit-GEMM forward) + value_head_kernel",
+                     "dominant_kernel": {"name": f"conv_kernel<{CHANNELS}->{CHANNELS}, 3x3> (residual tower, {2 * BLOCKS} launches per forward)",
                                          "ms_per_launch": conv_ms, "algorithmic_flops_per_launch": conv_flops,
                                          "achieved_tflops": conv_tf, "frac_of_burst_peak": conv_tf / peaks["bf16_tflops"],
                                          "timing": "20 back-to-back launches alone, CUDA events"},
@@ -223,12 +255,125 @@ def run(args, rank, world, local_rank, dist):
                              "power-capped clocks included); the isolated forward is timed back to back for 20 launches"},
         "cpu_baseline": cpu,
         "secondary": mv,
-        "e2e": {"value": e2e_sims / e2e_s, "unit": "sims/s", "h2d_bytes_per_step": 64 + 160,
-                "d2h_bytes_per_step": d2h // e2e_steps},
+        "extra": {"configs3_256x20": c3},
+        "e2e": ({"value": api["value"], "unit": "sims/s", "api": "parallel_self_play",
+                 "h2d_bytes_per_step": api["h2d_bytes"], "d2h_bytes_per_step": api["d2h_bytes"],
+                 "step": "one parallel_self_play(model, config) call: " + api["config"], "seconds": api["seconds"],
+                 "games": api["games"], "new_samples": api["new_samples"],
+                 "engine_level": {"value": e2e_sims / e2e_s, "unit": "sims/s", "api": "SelfPlayEngine.play + counters + fetch per ply",
+                                  "h2d_bytes_per_step": 64 + 160, "d2h_bytes_per_step": d2h // e2e_steps}}
+                if api else
+                {"value": e2e_sims / e2e_s, "unit": "sims/s", "api": "SelfPlayEngine.play + counters + fetch per ply",
+                 "h2d_bytes_per_step": 64 + 160, "d2h_bytes_per_step": d2h // e2e_steps}),
         "gpu_launches": launches,
         "clocks": clocks,
     }
     bench.emit(line)
+
+
+def movegen_block(eng, rank, world, args):
+    """M2 of BASELINE.json (legal-move positions/s) with kernel rate, roofline share, end-to-end rates and the reference's
+    Cython engine on the host cores."""
+    import numpy as np
+    import torch
+    import bench
+    N = 1_000_000
+    pb, ps_, _, _ = eng.random_playouts(20261018 + rank, 5600)
+    pb, ps_ = pb[:N].contiguous(), ps_[:N].contiguous()
+    outb = (torch.empty((N, 128), dtype=torch.int16, device=eng.dev), torch.empty((N,), dtype=torch.uint8, device=eng.dev),
+            torch.empty((N,), dtype=torch.uint8, device=eng.dev), torch.empty((N, 15, 10, 9), dtype=torch.float32, device=eng.dev))
+    for _ in range(3):
+        eng.movegen(pb, ps_, planes=True, out=outb)
+    m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    m0.record()
+    for _ in range(5):
+        eng.movegen(pb, ps_, planes=True, out=outb)
+    m1.record()
+    torch.cuda.synchronize()
+    mv_ms = m0.elapsed_time(m1) / 5
+    gbs = 5563.4 * N / (mv_ms * 1e-3) / 1e9
+    mv = {"metric": "legal_move_positions_per_sec", "value": N / (mv_ms * 1e-3), "unit": "positions/s (per GPU)",
+          "kernel": {"warp": "movegen_kernel<true>", "thread": "movegen_tpb_kernel<true>"}[eng.movegen_impl]
+                    + " (moves + in-check + fp32 planes)", "kernel_ms": mv_ms,
+          "roofline": {"bound": "hbm", "achieved": gbs, "peak": bench.measured_peaks()[0]["hbm_gbs"], "unit": "GB/s",
+                       "frac": gbs / bench.measured_peaks()[0]["hbm_gbs"], "traffic": 5.69e9,
+                       "algorithmic_bytes_per_position": 5563.4}}
+    del outb
+    # end to end: pinned host buffers through xq_movegen_batch_host[_packed] (H2D + kernel + D2H in the timed region)
+    NE = 262_144
+    hb = torch.empty((NE, 90), dtype=torch.int8).pin_memory()
+    hs = torch.empty((NE,), dtype=torch.int8).pin_memory()
+    hb.copy_(pb[:NE].cpu())
+    hs.copy_(ps_[:NE].cpu())
+    hbn, hsn = hb.numpy(), hs.numpy()
+    pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()
+    base = (pin((NE, 128), torch.int16), pin((NE,), torch.uint8), pin((NE,), torch.uint8))
+    for name, planes, pl, d2h in (("fp32_planes", True, pin((NE, 15, 10, 9), torch.float32), NE * (256 + 2 + 5400)),
+                                  ("packed_planes", "packed", pin((NE, 44), torch.int32).view(np.uint32), NE * (256 + 2 + 176)),
+                                  ("no_planes", False, None, NE * (256 + 2))):
+        out = base + (pl,)
+        eng.movegen_host(hbn, hsn, planes=planes, out=out)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            eng.movegen_host(hbn, hsn, planes=planes, out=out)
+        dt = (time.perf_counter() - t0) / 3
+        mv.setdefault("e2e", {})[name] = {"value": NE / dt, "unit": "positions/s", "h2d_bytes_per_step": NE * 91,
+                                          "d2h_bytes_per_step": d2h, "positions_per_step": NE}
+    mv["e2e"]["api"] = "xq_movegen_batch_host / xq_movegen_batch_host_packed (pinned host buffers, chunked copy/compute overlap)"
+    del pb, ps_
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        r, kind, wall = bench.cpu_movegen_rate(40_000 * cores, cores)
+        mv["cpu_baseline"] = {"value": r, "unit": "positions/s", "cores": cores, "kind": kind,
+                              "sample": f"{40_000 * cores} random-playout positions, cy_generate_legal_moves + cy_is_in_check of the "
+                                        f"reference's Cython engine compiled as-is (oracle/_ref), {cores} processes, {wall:.1f} s"}
+    return mv
+
+
+def configs3_block(rank, world, local_rank, dist, sims):
+    """BASELINE configs[3]: XiangqiNet(256, 20), 4096 games per GPU (32768 over 8), Dirichlet root noise, 800 sims/move."""
+    import torch
+    import bench
+    import xq_native
+    import model as M
+    from selfplay_engine import SelfPlayEngine
+    C3, R3, games = 256, 20, GAMES_PER_GPU
+    eng = xq_native.Engine(local_rank)
+    torch.manual_seed(20261019)
+    model = M.XiangqiNet(C3, R3).eval()
+    cfgobj = StdConfig()
+    cfgobj.num_simulations = sims
+    sp = SelfPlayEngine(eng, model, n_slots=games, max_games=games * 2, sample_capacity=games * 8, node_capacity=games * (sims + 1) * 48)
+    sp.reset()
+    cfg = SelfPlayEngine.make_config(cfgobj, games * 2, seed=20261019 + rank, add_noise=True)
+    sp.play(cfg, 1)
+    torch.cuda.synchronize()
+    c0 = sp.counters()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        dist.barrier()
+    e0.record()
+    sp.play(cfg, 2)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    c1 = sp.counters()
+    vals = torch.tensor([ms], device=eng.dev, dtype=torch.float64)
+    cnt = torch.tensor([c1["sims"] - c0["sims"], c1["evals"] - c0["evals"]], device=eng.dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    ms = float(vals[0])
+    sims_done, evals_done = cnt.tolist()
+    peaks, _ = bench.measured_peaks()
+    tf = flops_per_eval(C3, R3) * evals_done / world / (ms * 1e-3) / 1e12
+    out = {"metric": "mcts_sims_per_sec", "value": sims_done / (ms * 1e-3), "unit": "sims/s", "n_gpus": world,
+           "workload": f"configs[3]: {games} games/GPU x {sims} sims/move, XiangqiNet(256,20), Dirichlet(0.3) root noise, 1 warm-up + 2 timed plies",
+           "ms_per_ply": ms / 2, "achieved_tflops": tf, "frac_of_sustained_peak": tf / peaks["bf16_tflops_sustained"],
+           "algorithmic_flops_per_eval": flops_per_eval(C3, R3), "error_bits": c1["error"]}
+    del sp
+    eng.close()
+    return out
 
 
 # ------------------------------------------------------------------------------------------------

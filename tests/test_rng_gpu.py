@@ -75,7 +75,8 @@ def test_temperature_sampling_follows_the_recorded_distribution(eng):
         p = d["probs"][i, :k].astype(np.float64)
         order = np.argsort(-p, kind="stable")
         ps = p[order]
-        exp[:R] += ps[:R]
+        m = min(R, k)                          # a position in check may have fewer than R legal moves
+        exp[:m] += ps[:m]
         exp[R] += ps[R:].sum()
         j = d["actions"][i, :k].tolist().index(int(d["played"][i]))
         r = int(np.nonzero(order == j)[0][0])
