@@ -2,7 +2,7 @@
 wd 1e-4, clip 1.0, XiangqiNet(128,6) -- on a device-resident replay ring of synthetic self-play records.
 
 Step = one optimiser step on one GLOBAL minibatch of 256 samples (split across the ranks under torchrun: strong
-scaling, the reference's batch size is kept; SyncBatchNorm + one flat gradient all-reduce per step).
+scaling, the reference's batch size is kept; global-minibatch BatchNorm (DPBatchNorm2d) + gradient all-reduce overlapped with backward).
 Metric = training samples per second.  The dominant HAND-WRITTEN kernels of the step are HBM-bound streaming
 kernels (clip+Adam over the flat buffers: 28 B per parameter; loss+gradient: 64.8 KB per sample); the roofline line
 reports the Adam kernel, the conv forward/backward itself is torch/cuDNN (library code, not claimed).
@@ -161,7 +161,7 @@ def run(args, rank, world, local_rank, dist):
         "config": {"workload": f"train: configs[4] training step, global batch {BATCH}, XiangqiNet({CHANNELS},{BLOCKS}) fp32 (TF32 convs as "
                                f"torch defaults), Adam lr 2e-3 wd 1e-4, clip 1.0, replay ring of {n} logical samples in HBM",
                    "parameters": nparam, "l2": "flat optimiser buffers 4 x %.0f MB > 126 MB L2" % (nparam * 4 / 1e6),
-                   "parallelism": f"dp{world}: minibatch split across ranks, SyncBatchNorm, one flat gradient all-reduce per step"},
+                   "parallelism": f"dp{world}: minibatch split across ranks, global-minibatch BatchNorm statistics, gradient all-reduce overlapped with backward"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                      "traffic": None, "peak_source": peak_kind, "kernel": "adam_kernel (clip + weight decay + Adam over flat buffers)",
                      "algorithmic_bytes_per_parameter": 28, "kernel_ms": k_ms,

@@ -339,6 +339,27 @@ int xq_adam_step(xq_ctx* ctx, float* d_param, const float* d_grad, float* d_exp_
                  float lr, float beta1, float beta2, float eps, float weight_decay, long long step,
                  const float* d_grad_sumsq, float max_norm, float grad_scale, void* stream);
 
+/* ---- data-parallel BatchNorm of the training step (csrc/xq_bn.cu) -------------------------------------------
+ * Training-mode BatchNorm2d (the 15 layers of XiangqiNet inside train.py:397-423) whose statistics are those of the
+ * WHOLE minibatch when it is split across the ranks of one NVSwitch box: per layer and direction one reduce kernel
+ * stores its per-channel partial sums straight into every peer's exchange buffer (CUDA IPC peer mapping, NVLink) and one
+ * apply kernel waits for all ranks' flags, adds the partials in rank order and normalises -- no collective call.
+ *   xq_peer_create: allocate this rank's exchange buffer, return its 64-byte IPC handle;
+ *   xq_peer_connect: open the other ranks' buffers (handles = world x 64 bytes in rank order, e.g. from an all_gather).
+ * Without these two calls a context is its own single-rank group.  Every rank must issue the same sequence of
+ * xq_bn_forward / xq_bn_backward calls.  x, y, dy, dx: float32 [N][C][HW] contiguous (NCHW); C <= 512. */
+int xq_peer_create(xq_ctx* ctx, int rank, int world, unsigned char* handle_out64);
+int xq_peer_connect(xq_ctx* ctx, const unsigned char* handles);
+/* y = (x - mean) * invstd * weight + bias with the global batch statistics; running_mean / running_var get F.batch_norm's
+ * momentum update (unbiased variance); save_mean / save_invstd [C] are what xq_bn_backward needs. */
+int xq_bn_forward(xq_ctx* ctx, const float* d_x, float* d_y, const float* d_weight, const float* d_bias,
+                  float* d_running_mean, float* d_running_var, float* d_save_mean, float* d_save_invstd, int N, int C,
+                  int HW, float eps, float momentum, void* stream);
+/* dx over the global batch; dweight / dbias [C] are this rank's LOCAL sums (the gradient all-reduce adds them up). */
+int xq_bn_backward(xq_ctx* ctx, const float* d_x, const float* d_dy, const float* d_weight, const float* d_save_mean,
+                   const float* d_save_invstd, float* d_dx, float* d_dweight, float* d_dbias, int N, int C, int HW,
+                   void* stream);
+
 #ifdef __cplusplus
 }
 #endif

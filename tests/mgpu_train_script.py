@@ -54,6 +54,23 @@ def main():
     dist.broadcast(ref, 0)
     assert torch.equal(flat, ref)
 
+    # dp_mode = "replicate": every rank runs the full minibatch (no collective inside the step) -- same run, same numbers
+    cfg_r = T.TrainingConfig()
+    cfg_r.num_channels, cfg_r.num_res_blocks, cfg_r.batch_size, cfg_r.num_epochs, cfg_r.min_buffer_size = ch, blocks, batch, epochs, 10
+    cfg_r.checkpoint_dir, cfg_r.dp_mode = "/tmp/xq_mgpu_train", "replicate"
+    torch.manual_seed(seed if dist.get_rank() == 0 else 999)
+    tr_r = T.AlphaZeroTrainer(cfg_r)
+    tr_r.replay_buffer.append_raw(torch.from_numpy(rec), torch.from_numpy(g["z"]))
+    torch.manual_seed(seed + 1 if dist.get_rank() == 0 else 5)
+    s_r = tr_r.train_network()
+    got_r = np.array([s_r["policy_loss"], s_r["value_loss"], s_r["total_loss"], s_r["learning_rate"]])
+    assert np.allclose(got_r, g["stats1"], rtol=2e-3), (got_r, g["stats1"])
+    fr = tr_r.optimizer.flat_p.clone()
+    fr0 = fr.clone()
+    dist.broadcast(fr0, 0)
+    assert torch.allclose(fr, fr0, rtol=1e-3, atol=1e-5)           # replicas agree up to the reduction order of library kernels
+    del tr_r
+
     # sharded self-play -> all ranks append the same records; evaluation pairs sharded; weights broadcast
     cfg2 = T.TrainingConfig()
     cfg2.num_channels, cfg2.num_res_blocks, cfg2.num_simulations, cfg2.num_games_per_iter = 128, 1, 6, 9

@@ -163,3 +163,64 @@ def test_train_module_augment_data_and_dataset_follow_the_reference():
         st, pol, val = ds[1]
         assert len(ds) == 2 and st.dtype == torch.float32 and st.shape == (15, 10, 9) and pol.shape == (8100,) and val.shape == (1,)
         assert float(val) == float(z)
+
+
+def test_dp_batchnorm_equals_batchnorm_on_the_global_minibatch():
+    """DPBatchNorm2d (train.py: one all-reduce of the per-channel sums each way, no host synchronisation) = nn.BatchNorm2d
+    on the concatenated minibatch: outputs, input gradients, parameter gradients (summed over the ranks, as the gradient
+    all-reduce does) and running statistics.  Two ranks are emulated by feeding each half the other half's partial sums."""
+    import torch
+    import train as T
+    torch.manual_seed(0)
+    C = 6
+    x = torch.randn(8, C, 10, 9)
+    ref = torch.nn.BatchNorm2d(C)
+    ref.weight.data.uniform_(0.5, 1.5)
+    ref.bias.data.normal_()
+    xa = x.clone().requires_grad_(True)
+    y = ref(xa)
+    gy = y.detach().sin()
+    (y * gy).sum().backward()
+    mean = x.double().mean((0, 2, 3))
+    inv = torch.rsqrt(x.double().var((0, 2, 3), unbiased=False) + ref.eps)
+
+    class OtherRank:
+        def __init__(self):
+            self.other = []
+
+        def get_world_size(self):
+            return 2
+
+        def all_reduce(self, t):
+            t.add_(self.other.pop(0))
+    halves = [x[:4], x[4:]]
+    out = []
+    for h in range(2):
+        o = halves[1 - h].double()
+        fake = OtherRank()
+        fake.other.append(torch.cat([o.sum((0, 2, 3)), (o * o).sum((0, 2, 3)), torch.tensor([o.numel() // C], dtype=torch.float64)]))
+        dyo = gy[(1 - h) * 4:(1 - h) * 4 + 4].double()
+        xhat_o = (o - mean.view(1, C, 1, 1)) * inv.view(1, C, 1, 1)
+        fake.other.append(torch.cat([dyo.sum((0, 2, 3)), (dyo * xhat_o).sum((0, 2, 3))]))
+        m = T.DPBatchNorm2d(C)
+        m.weight.data.copy_(ref.weight.data)
+        m.bias.data.copy_(ref.bias.data)
+        m.dist = fake
+        xh = halves[h].clone().requires_grad_(True)
+        yh = m(xh)
+        (yh * gy[h * 4:h * 4 + 4]).sum().backward()
+        out.append((yh.detach(), xh.grad, m.weight.grad, m.bias.grad, m.running_mean, m.running_var, int(m.num_batches_tracked)))
+    assert torch.allclose(torch.cat([out[0][0], out[1][0]]), y.detach(), atol=2e-6)
+    assert torch.allclose(torch.cat([out[0][1], out[1][1]]), xa.grad, atol=2e-6)
+    assert torch.allclose(out[0][2] + out[1][2], ref.weight.grad, atol=1e-4)
+    assert torch.allclose(out[0][3] + out[1][3], ref.bias.grad, atol=1e-5)
+    for h in range(2):
+        assert torch.allclose(out[h][4], ref.running_mean, atol=1e-7) and torch.allclose(out[h][5], ref.running_var, atol=1e-7)
+        assert out[h][6] == int(ref.num_batches_tracked) == 1
+    # conversion keeps parameters, buffers and state_dict keys
+    import model as M
+    net = M.XiangqiNet(16, 1)
+    keys = list(net.state_dict().keys())
+    w = net.input_conv[1].weight
+    T.convert_dp_batchnorm(net, fake)
+    assert list(net.state_dict().keys()) == keys and net.input_conv[1].weight is w and isinstance(net.res_blocks[0].bn1, T.DPBatchNorm2d)

@@ -302,3 +302,39 @@ def test_superseded_selfplay_engine_fails_loudly(eng):
         a.reset()
     b.reset()
     e2.close()
+
+
+def test_hand_written_batchnorm_matches_torch_batchnorm():
+    """csrc/xq_bn.cu (reduce+push / wait+apply, single-rank group) against nn.BatchNorm2d in training mode: outputs,
+    input / weight / bias gradients, running statistics -- the layer train.py:397-423 runs 15 times per step."""
+    import torch
+    import xq_native
+    import train as T
+    eng = xq_native.Engine(0)
+    assert T.setup_peer_group(eng, None)
+    torch.manual_seed(3)
+    for N, C, H, W in ((256, 128, 10, 9), (32, 4, 10, 9), (7, 32, 10, 9), (256, 256, 10, 9)):
+        x = (torch.randn(N, C, H, W, device=eng.dev) * 1.7 + 0.3)
+        ref = torch.nn.BatchNorm2d(C).to(eng.dev)
+        ref.weight.data.uniform_(0.5, 1.5)
+        ref.bias.data.normal_()
+        mine = T.DPBatchNorm2d(C).to(eng.dev)
+        mine.load_state_dict(ref.state_dict())
+        mine.eng = eng
+        for step in range(2):
+            xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+            ya, yb = ref(xa), mine(xb)
+            g = torch.randn_like(ya)
+            ya.backward(g)
+            yb.backward(g)
+            assert torch.allclose(yb, ya, atol=2e-5, rtol=1e-5)
+            assert torch.allclose(xb.grad, xa.grad, atol=2e-5, rtol=1e-4)
+            assert torch.allclose(mine.weight.grad, ref.weight.grad, atol=2e-3, rtol=1e-4)
+            assert torch.allclose(mine.bias.grad, ref.bias.grad, atol=2e-3, rtol=1e-4)
+            assert torch.allclose(mine.running_mean, ref.running_mean, atol=1e-6) and torch.allclose(mine.running_var, ref.running_var, atol=1e-5)
+            assert int(mine.num_batches_tracked) == int(ref.num_batches_tracked) == step + 1
+            ref.zero_grad()
+            mine.zero_grad()
+        mine.eval()
+        ref.eval()
+        assert torch.allclose(mine(x), ref(x), atol=1e-5)

@@ -546,6 +546,7 @@ extern "C" int xq_create(int device, xq_ctx** out)
 extern "C" void xq_mcts_free_(xq_ctx*);
 extern "C" void xq_net_free_(xq_ctx*);
 extern "C" void xq_selfplay_free_(xq_ctx*);
+extern "C" void xq_peer_free_(xq_ctx*);
 
 extern "C" void xq_destroy(xq_ctx* c)
 {
@@ -554,6 +555,7 @@ extern "C" void xq_destroy(xq_ctx* c)
     xq_selfplay_free_(c);
     xq_mcts_free_(c);
     xq_net_free_(c);
+    xq_peer_free_(c);
     for (int i = 0; i < 2; ++i) {
         if (c->pipe[i]) cudaStreamDestroy(c->pipe[i]);
         if (c->d_stage[i]) cudaFree(c->d_stage[i]);

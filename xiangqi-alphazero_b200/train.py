@@ -16,7 +16,7 @@ living on the GPU(s):
 Data parallel (launch with torchrun, one process per GPU, NCCL): games and evaluation pairs are sharded with
 no collective inside; the new sample records are all-gathered so every rank holds the same replay ring; every
 global minibatch of `batch_size` is split across the ranks, BatchNorm statistics are synchronised
-(SyncBatchNorm: the batch statistics are those of the reference's single 256-sample batch), the flat gradient is
+(DPBatchNorm2d: the batch statistics are those of the reference's single 256-sample batch), the flat gradient is
 summed with ONE all-reduce per step, and the promoted weights are broadcast from rank 0.
 """
 import argparse
@@ -91,6 +91,13 @@ class TrainingConfig:
         # batch when few games are in flight (evaluation's eval_games, small num_games_per_iter).
         self.selfplay_leaves_per_game = 1
         self.eval_leaves_per_game = 1
+        # multi-GPU training of the reference's 256-sample minibatch: "shard" = data parallel (each rank holds
+        # batch_size / world samples, global BatchNorm statistics, NCCL gradient all-reduce: the north star's mode); "replicate" = every
+        # rank runs the full minibatch (identical replicas, no collective inside the step; the replicas are re-synchronised by
+        # the weight broadcast after evaluation).  A 256-sample step is launch-latency bound on a B200 (4.7 ms, 60 TFLOP/s),
+        # so sharding it 8 ways cannot shorten it and adds 30 small BatchNorm-statistics all-reduces per step.
+        self.dp_mode = "shard"
+        self.hand_batchnorm = True      # training-mode BatchNorm on csrc/xq_bn.cu (statistics over NVLink peer memory when sharded)
 
 
 class SelfPlayDataset(torch.utils.data.Dataset):
@@ -188,6 +195,146 @@ def shard_batch(idx: torch.Tensor, rank: int, world: int) -> torch.Tensor:
     return torch.tensor_split(idx, world)[rank]
 
 
+class _DPBatchNormFn(torch.autograd.Function):
+    """BatchNorm2d over the GLOBAL minibatch of a data-parallel step: one all-reduce of the per-channel sums in forward
+    and one in backward, nothing that waits for the GPU on the host.  (torch.nn.SyncBatchNorm's forward masks the
+    gathered counts with a boolean index -- a device-to-host synchronisation in every one of the 15 layers, which made
+    the sharded step 2.3x slower than the single-GPU step.)  Statistics accumulate in float64."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, eps, momentum, dist):
+        C = x.shape[1]
+        xd = x.double()
+        stats = torch.cat([xd.sum((0, 2, 3)), (xd * xd).sum((0, 2, 3)),
+                           torch.full((1,), x.numel() // C, dtype=torch.float64, device=x.device)])
+        dist.all_reduce(stats)
+        n = stats[-1]
+        mean = stats[:C] / n
+        var = (stats[C:2 * C] / n - mean * mean).clamp_(min=0.0)          # biased: what normalises the batch
+        invstd = torch.rsqrt(var + eps)
+        with torch.no_grad():                                               # F.batch_norm's running update (unbiased variance)
+            running_mean.mul_(1.0 - momentum).add_(mean.to(running_mean.dtype), alpha=momentum)
+            running_var.mul_(1.0 - momentum).add_((var * (n / (n - 1.0))).to(running_var.dtype), alpha=momentum)
+        xhat = (x - mean.float().view(1, C, 1, 1)) * invstd.float().view(1, C, 1, 1)
+        ctx.save_for_backward(xhat, weight, invstd.float(), n)
+        ctx.dist = dist
+        return xhat * weight.view(1, C, 1, 1) + bias.view(1, C, 1, 1)
+
+    @staticmethod
+    def backward(ctx, dy):
+        xhat, weight, invstd, n = ctx.saved_tensors
+        C = dy.shape[1]
+        dyd = dy.double()
+        local = torch.cat([dyd.sum((0, 2, 3)), (dyd * xhat.double()).sum((0, 2, 3))])
+        red = local.clone()
+        ctx.dist.all_reduce(red)                                            # global sums for dx; the parameter gradients stay
+        mean_dy = (red[:C] / n).float().view(1, C, 1, 1)                    # local (the gradient all-reduce sums them)
+        mean_dy_xhat = (red[C:] / n).float().view(1, C, 1, 1)
+        dx = (weight * invstd).view(1, C, 1, 1) * (dy - mean_dy - xhat * mean_dy_xhat)
+        return dx, local[C:].to(weight.dtype), local[:C].to(weight.dtype), None, None, None, None, None
+
+
+class _BnKernelFn(torch.autograd.Function):
+    """The same layer on the hand-written kernels of csrc/xq_bn.cu: per direction one reduce kernel that stores its partial
+    sums into every rank's exchange buffer over NVLink and one apply kernel that waits for all ranks and normalises --
+    two launches, no collective call, nothing on the host."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, eps, momentum, eng):
+        x = x.contiguous()
+        N, C = x.shape[0], x.shape[1]
+        HW = x.numel() // (N * C)
+        y = torch.empty_like(x)
+        save = torch.empty((2, C), dtype=torch.float32, device=x.device)
+        eng._check(eng.L.xq_bn_forward(eng.h, x.data_ptr(), y.data_ptr(), weight.data_ptr(), bias.data_ptr(),
+                                       running_mean.data_ptr(), running_var.data_ptr(), save[0].data_ptr(), save[1].data_ptr(),
+                                       N, C, HW, float(eps), float(momentum), eng._stream()))
+        ctx.save_for_backward(x, weight, save)
+        ctx.eng = eng
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, save = ctx.saved_tensors
+        eng = ctx.eng
+        dy = dy.contiguous()
+        N, C = x.shape[0], x.shape[1]
+        HW = x.numel() // (N * C)
+        dx = torch.empty_like(x)
+        dwb = torch.empty((2, C), dtype=torch.float32, device=x.device)
+        eng._check(eng.L.xq_bn_backward(eng.h, x.data_ptr(), dy.data_ptr(), weight.data_ptr(), save[0].data_ptr(), save[1].data_ptr(),
+                                        dx.data_ptr(), dwb[0].data_ptr(), dwb[1].data_ptr(), N, C, HW, eng._stream()))
+        return dx, dwb[0], dwb[1], None, None, None, None, None
+
+
+def setup_peer_group(eng, dist=None) -> bool:
+    """Peer-map the BatchNorm exchange buffers of all ranks (CUDA IPC over NVLink; one process per GPU on one box).
+    Returns False -- and the layers fall back to all-reducing the sums with NCCL -- when the handles cannot be opened."""
+    import ctypes as C
+    rank, world = (dist.get_rank(), dist.get_world_size()) if dist is not None else (0, 1)
+    handle = (C.c_ubyte * 64)()
+    ok = 1
+    try:
+        eng._check(eng.L.xq_peer_create(eng.h, rank, world, handle))
+    except Exception as ex:
+        logger.warning("xq_peer_create failed: %s", ex)
+        ok = 0
+    if world <= 1:
+        return bool(ok)
+    dev = eng.dev if dist.get_backend() == "nccl" else "cpu"
+    mine = torch.tensor(list(handle), dtype=torch.uint8, device=dev)
+    allh = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(allh, mine)
+    if ok:
+        buf = (C.c_ubyte * (64 * world))(*[int(v) for t in allh for v in t.cpu().tolist()])
+        try:
+            eng._check(eng.L.xq_peer_connect(eng.h, buf))
+        except Exception as ex:
+            logger.warning("xq_peer_connect failed (%s): BatchNorm statistics go through NCCL instead", ex)
+            ok = 0
+    flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)           # all ranks or none
+    return bool(int(flag.item()))
+
+
+class DPBatchNorm2d(torch.nn.BatchNorm2d):
+    """nn.BatchNorm2d (same parameters, buffers and state_dict keys) whose training-mode statistics are those of the whole
+    data-parallel minibatch, i.e. of the reference's single-process 256-sample batch (train.py:397-423).  `eng` set: the
+    hand-written peer-memory kernels (csrc/xq_bn.cu); else, with `dist` set: torch ops + one NCCL all-reduce each way."""
+    dist = None
+    eng = None
+
+    def forward(self, x):
+        if not self.training:
+            return super().forward(x)
+        if self.eng is not None and x.is_cuda and x.dtype == torch.float32 and self.momentum is not None:
+            if self.num_batches_tracked is not None:
+                self.num_batches_tracked.add_(1)
+            return _BnKernelFn.apply(x, self.weight, self.bias, self.running_mean, self.running_var, self.eps, self.momentum, self.eng)
+        d = self.dist
+        if d is None or d.get_world_size() <= 1:
+            return super().forward(x)
+        if self.num_batches_tracked is not None:
+            self.num_batches_tracked.add_(1)
+        return _DPBatchNormFn.apply(x, self.weight, self.bias, self.running_mean, self.running_var, self.eps, self.momentum, d)
+
+
+def convert_dp_batchnorm(module, dist, eng=None):
+    """BatchNorm2d -> DPBatchNorm2d in place (parameters and buffers are kept, not copied)."""
+    for name, child in list(module.named_children()):
+        if isinstance(child, torch.nn.BatchNorm2d) and not isinstance(child, DPBatchNorm2d):
+            new = DPBatchNorm2d(child.num_features, eps=child.eps, momentum=child.momentum, device=child.weight.device)
+            new.weight, new.bias = child.weight, child.bias
+            new.running_mean, new.running_var, new.num_batches_tracked = child.running_mean, child.running_var, child.num_batches_tracked
+            new.dist = dist
+            new.eng = eng
+            new.train(child.training)
+            setattr(module, name, new)
+        else:
+            convert_dp_batchnorm(child, dist, eng)
+    return module
+
+
 class FlatAdam(optim.Adam):
     """torch.optim.Adam whose parameters, gradients and moments are views of four flat float32 buffers, stepped by
     xq_grad_sumsq + xq_adam_step (clip_grad_norm_ + Adam in two kernels).  state_dict()/load_state_dict() are Adam's
@@ -220,6 +367,23 @@ class FlatAdam(optim.Adam):
             off += k
         self._params = params
         self._model = model
+        # Data parallel: the gradient all-reduce is split at the policy FC weight (23.3 M of the 25.2 M parameters, 93 MB
+        # of the 100.7 MB).  Its gradient is the FIRST one backward produces (the FC is the last layer), so its all-reduce
+        # is issued from a post-accumulate hook and runs under the whole convolutional backward; only the remaining
+        # 7 MB are reduced after backward (C1).
+        self._early = None
+        self._big = None
+        if dist is not None and dist.get_world_size() > 1:
+            off = 0
+            for p in params:
+                if self._big is None or p.numel() > self._big[2]:
+                    self._big = (p, off, p.numel())
+                off += p.numel()
+            big_p, big_off, big_n = self._big
+
+            def _reduce_early(_param, self=self, lo=big_off, n=big_n):
+                self._early = self.dist.all_reduce(self.flat_g[lo:lo + n], async_op=True)
+            big_p.register_post_accumulate_grad_hook(_reduce_early)
 
     def zero_grad(self, set_to_none: bool = False):
         self.flat_g.zero_()
@@ -254,7 +418,20 @@ class FlatAdam(optim.Adam):
     def step(self, closure=None):
         e = self.e
         if self.dist is not None and self.dist.get_world_size() > 1:
-            self.dist.all_reduce(self.flat_g)           # C1: one NCCL all-reduce of the flat gradient (sum of per-rank shards)
+            # C1: NCCL all-reduce of the flat gradient (sum of per-rank shards).  The policy FC weight's slice is already
+            # in flight since the start of backward (see __init__); the two ranges around it follow here.
+            if self._early is not None:
+                _, lo, n = self._big
+                works = [self._early]
+                if lo > 0:
+                    works.append(self.dist.all_reduce(self.flat_g[:lo], async_op=True))
+                if lo + n < self.flat_g.numel():
+                    works.append(self.dist.all_reduce(self.flat_g[lo + n:], async_op=True))
+                for w in works:
+                    w.wait()
+                self._early = None
+            else:
+                self.dist.all_reduce(self.flat_g)
         g = self.param_groups[0]
         self.steps += 1
         b1, b2 = g['betas']
@@ -291,12 +468,18 @@ class AlphaZeroTrainer:
         self.best_model = XiangqiNet(config.num_channels, config.num_res_blocks).to(self.device)
         if self.world > 1:
             self._broadcast_model(self.current_model)           # C2: every rank starts from rank 0's weights
-            if getattr(config, "sync_batchnorm", True):
-                self.current_model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(self.current_model)
+        shard = self.world > 1 and getattr(config, "sync_batchnorm", True) and getattr(config, "dp_mode", "shard") == "shard"
+        if getattr(config, "hand_batchnorm", True):
+            # BatchNorm forward / backward on the kernels of csrc/xq_bn.cu; sharded minibatch: the statistics are exchanged
+            # through NVLink peer memory inside those kernels (falls back to NCCL all-reduces if IPC mapping is refused)
+            peers = setup_peer_group(self.eng, self.dist if shard else None)
+            convert_dp_batchnorm(self.current_model, self.dist if shard else None, self.eng if peers else None)
+        elif shard:
+            convert_dp_batchnorm(self.current_model, self.dist)           # global-minibatch statistics through NCCL, no host sync
         self.best_model.load_state_dict(self.current_model.state_dict())
 
         self.optimizer = FlatAdam(self.eng, self.current_model, lr=config.learning_rate, weight_decay=config.weight_decay,
-                                  max_grad_norm=1.0, dist=self.dist)
+                                  max_grad_norm=1.0, dist=self.dist if getattr(config, "dp_mode", "shard") == "shard" else None)
         self.scheduler = optim.lr_scheduler.MultiStepLR(self.optimizer, milestones=config.lr_milestones, gamma=config.lr_gamma)
         self.replay_buffer = DeviceReplayBuffer(self.eng, config.max_buffer_size)
 
@@ -446,9 +629,12 @@ class AlphaZeroTrainer:
             ep_batches = 0
             for lo in range(0, n, cfg.batch_size):
                 gidx = perm[lo:lo + cfg.batch_size]
-                mine = self._shard(gidx)
-                replicated = self.world > 1 and gidx.numel() < self.world
-                denom = gidx.numel() * (self.world if replicated else 1)
+                if getattr(cfg, "dp_mode", "shard") == "replicate":
+                    mine, denom = gidx, gidx.numel()                           # every rank runs the whole minibatch
+                else:
+                    mine = self._shard(gidx)
+                    replicated = self.world > 1 and gidx.numel() < self.world
+                    denom = gidx.numel() * (self.world if replicated else 1)
                 states, target, z = self.replay_buffer.batch(mine)
                 logits, values = self.current_model(states)
                 p_loss, v_loss = policy_value_loss(self.eng, logits, values, target, z, global_batch=denom)
@@ -457,7 +643,7 @@ class AlphaZeroTrainer:
                 self.optimizer.step()                                       # all-reduce + clip + Adam
                 ep += torch.stack([p_loss.detach(), v_loss.detach()]).double()
                 ep_batches += 1
-            if self.world > 1:
+            if self.world > 1 and getattr(cfg, "dp_mode", "shard") == "shard":
                 self.dist.all_reduce(ep)                                    # per-rank partial means -> full-batch means
             sums += ep
             num_batches += ep_batches

@@ -102,6 +102,10 @@ def lib():
     _sig(L, "xq_policy_value_loss", i32, vp, vp, i64, vp, vp, vp, vp, vp, i32, f32, vp, i64, vp, vp, vp, vp)
     _sig(L, "xq_grad_sumsq", i32, vp, vp, i64, vp, i32, vp, vp)
     _sig(L, "xq_adam_step", i32, vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i64, vp, f32, f32, vp)
+    _sig(L, "xq_peer_create", i32, vp, i32, i32, vp)
+    _sig(L, "xq_peer_connect", i32, vp, vp)
+    _sig(L, "xq_bn_forward", i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, f32, vp)
+    _sig(L, "xq_bn_backward", i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp)
     _lib = L
     return L
 
@@ -115,7 +119,7 @@ EXPORTS = ["xq_create", "xq_destroy", "xq_last_error", "xq_version", "xq_launch_
            "xq_net_gemm", "xq_net_value_head", "xq_net_run", "xq_net_run_counted", "xq_selfplay_create", "xq_selfplay_reset",
            "xq_selfplay_play", "xq_selfplay_counters", "xq_selfplay_fetch", "xq_selfplay_slots",
            "xq_selfplay_device_buffers", "xq_arena_play", "xq_replay_append", "xq_train_batch", "xq_policy_value_loss",
-           "xq_grad_sumsq", "xq_adam_step"]
+           "xq_grad_sumsq", "xq_adam_step", "xq_peer_create", "xq_peer_connect", "xq_bn_forward", "xq_bn_backward"]
 
 
 def _np_ptr(a: np.ndarray):
