@@ -209,6 +209,9 @@ typedef struct xq_gemm_desc {
     const void* residual; /* mode 0 only, may be NULL */
     void* out;
     void* out2;           /* mode 1 only */
+    const void* w_half;   /* mode 0 with 128 output channels per tile, optional: the same weights tiled by 64 output
+                             channels [n_tile64][tap][k_block][chunk][64][8] for the CTA-pair kernel (cta_group::2 MMAs, each
+                             CTA holds half of N); NULL: the single-CTA kernel runs the layer */
 } xq_gemm_desc;
 
 int xq_net_gemm(xq_ctx* ctx, const xq_gemm_desc* desc, void* stream);

@@ -55,6 +55,7 @@ struct GemmArgs {
     const uint8_t* residual;
     uint8_t* out;
     float* out2;
+    const uint8_t* w_half;   // 3x3 layers: the weight image tiled by 64 output channels (conv2_kernel: each CTA of a pair holds half of N)
     const int* n_dev;        // optional DEVICE board count (<= n_boards): the launch sizes itself to it (leaf compaction)
 };
 
@@ -513,6 +514,359 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(const GemmArgs p,
     if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
 }
 
+// =============================================================================================
+// conv2_kernel: the 3x3 tower conv on a CTA PAIR with cta_group::2 MMAs (M = 256 across two SMs)
+// =============================================================================================
+// conv_kernel is bound by shared-memory bandwidth: every M128 N128 K16 MMA reads 4 KB of A and 4 KB of B against the
+// SM's 128 B/clk, and the bulk copies write another ~2.5 KB per MMA into the same banks (87 cycles per MMA measured, 64
+// ideal).  With cta_group::2 the two SMs of a cluster run ONE M256 N128 K16 MMA: each CTA supplies its own 128 rows of A
+// and only HALF of B (64 of the 128 output channels: its own half of every weight stage); the tensor cores exchange the
+// halves.  Operand reads per SM drop to 6 KB and weight-stage writes to half, one instruction covers what took two, and the
+// freed shared memory holds six 24 KB stages instead of three 48 KB ones.
+//   * cluster (2,1,1); a work item = two consecutive tile pairs (512 rows), CTA r takes pair 2*item + r; rank 0 issues;
+//   * both CTAs run their own producer (own A segments, own half of every weight stage, image tiled by 64 channels);
+//     the follower's warp 1 relays "my stage / my segment has landed" to the leader with remote mbarrier arrives;
+//   * the leader's commits are multicast to both CTAs (stage empty, segment empty, accumulator full); both epilogues
+//     arrive on the leader's accumulator-empty barrier;
+//   * the disable-output-lane mask of a cta_group::2 MMA has 256 bits: lanes 0-127 = the leader's tile, 128-255 = the
+//     follower's tile (each with its own tile phase).
+constexpr int kMaxStages2 = 8;
+
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* local_bar, uint32_t target_cta)
+{
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(local_bar)),
+        "r"(target_cta)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* slot, uint32_t cols)
+{
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish2()
+{
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t addr, uint32_t cols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate,
+                                           const uint4 m0, const uint4 m1)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8, %9, %10, %11, %12}, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(m0.x), "r"(m0.y), "r"(m0.z), "r"(m0.w), "r"(m1.x),
+          "r"(m1.y), "r"(m1.z), "r"(m1.w)
+        : "memory");
+}
+__device__ __forceinline__ void umma2_commit_mc(uint64_t* bar, uint16_t cta_mask)
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"(cta_mask)
+                 : "memory");
+}
+
+template <int KCH, int TPS>
+struct Conv2Cfg {
+    static constexpr int NT = 128;                             // output channels per MMA (64 from each CTA's stage)
+    static constexpr int kWTap = KCH * 64 * 16;                // this CTA's half of one (tap, k-block) weight slice
+    static constexpr int kWStage = TPS * kWTap;
+    static constexpr int kSeg = KCH * kAPlane;
+    static constexpr int kTmemCols = 512;
+    static constexpr int kFixed = 1024;
+    static constexpr int kBudget = 227 * 1024 - 1024 - 256;
+    static int stages(int kblocks)
+    {
+        int st = (kBudget - kFixed - kblocks * kSeg) / kWStage;
+        return st > kMaxStages2 ? kMaxStages2 : st;
+    }
+    static int smem_bytes(int kblocks, int st)
+    {
+        const int total = kblocks * kSeg + st * kWStage + kFixed;
+        return total < 120 * 1024 ? 120 * 1024 : total;
+    }
+};
+
+template <int KCH, int TPS>
+__global__ void __launch_bounds__(kConvThreads, 1) conv2_kernel(const GemmArgs p, const int S)
+{
+    using Cfg = Conv2Cfg<KCH, TPS>;
+    constexpr int NT = 128, TS = 128;
+    constexpr int tap_groups = 9 / TPS;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int kblocks = p.kchunks / KCH;
+    uint8_t* sA = smem;
+    uint8_t* sStage = smem + kblocks * Cfg::kSeg;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + S * Cfg::kWStage);
+    uint64_t* w_full = bars;                                    // own half of the stage has landed
+    uint64_t* w_empty = bars + kMaxStages2;                     // the MMAs reading the stage are done (leader multicast)
+    uint64_t* w_peer = bars + 2 * kMaxStages2;                  // leader only: the follower's half has landed
+    uint64_t* a_full = bars + 3 * kMaxStages2;                  // [kMaxSeg]
+    uint64_t* a_empty = a_full + kMaxSeg;
+    uint64_t* a_peer = a_empty + kMaxSeg;
+    uint64_t* t_full = a_peer + kMaxSeg;                        // [2]
+    uint64_t* t_empty = t_full + 2;                             // [2] leader only: the 16 epilogue warps of the pair of CTAs
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    const uint32_t crank = cluster_ctarank();
+    const bool leader_cta = crank == 0;
+    const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+    int live_boards, live_tiles;
+    live_size(p, kBoardRows, &live_boards, &live_tiles);
+    const int m_pairs = (live_tiles + 1) / 2;
+    const int items = (m_pairs + 1) / 2;
+    const int total = items * p.n_tiles;
+    const long long real_rows = (long long)live_boards * kBoardRows;
+
+    __shared__ __align__(16) float sBias[256];
+    for (int i = threadIdx.x; i < p.n_tiles * NT && i < 256; i += kConvThreads) sBias[i] = p.bias[i];
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < S; ++i) {
+            mbar_init(&w_full[i], 1);
+            mbar_init(&w_empty[i], 1);
+            mbar_init(&w_peer[i], 1);
+        }
+        for (int i = 0; i < kblocks; ++i) {
+            mbar_init(&a_full[i], 1);
+            mbar_init(&a_empty[i], 1);
+            mbar_init(&a_peer[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&t_full[i], 1);
+            mbar_init(&t_empty[i], 16);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        tmem_alloc2(tmem_slot, Cfg::kTmemCols);
+        tmem_relinquish2();
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== producer (both CTAs): own rows, own half of the weights =====================
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            int n = 0;
+            for (int work = cluster_id; work < total; work += n_clusters, ++n) {
+                const int item = work / p.n_tiles, n_tile = work - item * p.n_tiles;
+                const int pair = item * 2 + (int)crank;
+                const long long m0 = (long long)pair * kPairRows;
+                // image tiled by 64 channels: [n_tile64][tap][k_block][chunk][64][8], n_tile64 = 2 * n_tile + rank
+                const uint8_t* wt = p.w_half + (size_t)(2 * n_tile + (int)crank) * 9 * kblocks * Cfg::kWTap;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&a_empty[kb], (uint32_t)(n & 1) ^ 1u);
+                    mbar_expect_tx(&a_full[kb], (uint32_t)Cfg::kSeg);
+#pragma unroll
+                    for (int c = 0; c < KCH; ++c)
+                        bulk_g2s(sA + kb * Cfg::kSeg + c * kAPlane,
+                                 p.a + ((size_t)(kb * KCH + c) * p.a_rows + (size_t)(p.a_row0 + m0 - kHalo)) * 16, kAPlane, &a_full[kb]);
+                    for (int tg = 0; tg < tap_groups; ++tg) {
+                        mbar_wait(&w_empty[s], ph ^ 1);
+                        mbar_expect_tx(&w_full[s], Cfg::kWStage);
+#pragma unroll
+                        for (int tp = 0; tp < TPS; ++tp)
+                            bulk_g2s(sStage + s * Cfg::kWStage + tp * Cfg::kWTap,
+                                     wt + (size_t)((tg * TPS + tp) * kblocks + kb) * Cfg::kWTap, Cfg::kWTap, &w_full[s]);
+                        if (++s == S) { s = 0; ph ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        int s = 0;
+        uint32_t ph = 0;
+        int n = 0;
+        if (!leader_cta) {
+            // ===================== follower: relay "landed" events to the leader =====================
+            if (lane == 0) {
+                for (int work = cluster_id; work < total; work += n_clusters, ++n) {
+                    for (int kb = 0; kb < kblocks; ++kb) {
+                        mbar_wait(&a_full[kb], (uint32_t)(n & 1));
+                        mbar_arrive_remote(&a_peer[kb], 0);
+                        for (int tg = 0; tg < tap_groups; ++tg) {
+                            mbar_wait(&w_full[s], ph);
+                            mbar_arrive_remote(&w_peer[s], 0);
+                            if (++s == S) { s = 0; ph ^= 1; }
+                        }
+                    }
+                }
+            }
+        } else {
+            // ===================== leader: one elected lane issues the MMAs of both SMs (uniform loop) =====================
+            const bool leader = elect_one();
+            constexpr uint32_t idesc = make_idesc(256, NT);
+            constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);
+            constexpr uint32_t kLboA = (uint32_t)(kAPlane >> 4);
+            for (int work = cluster_id; work < total; work += n_clusters, ++n) {
+                const int item = work / p.n_tiles;
+                const int acc = n & 1;
+                const uint32_t tph = (uint32_t)(n >> 1) & 1u;
+                // tile phases of the four tiles of the item: CTA r, row tile t -> tile index (item*2 + r)*2 + t
+                const int ph00 = ((item * 4 + 0) % kMaskPhases) * 9, ph01 = ((item * 4 + 1) % kMaskPhases) * 9;
+                const int ph10 = ((item * 4 + 2) % kMaskPhases) * 9, ph11 = ((item * 4 + 3) % kMaskPhases) * 9;
+                mbar_wait(&t_empty[acc], tph ^ 1);
+                tc_fence_after();
+                const uint32_t d_addr = tmem_base + (uint32_t)(acc * 2 * TS);
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&a_full[kb], (uint32_t)(n & 1));
+                    mbar_wait(&a_peer[kb], (uint32_t)(n & 1));
+                    const uint32_t a_seg = (((smem_u32(sA + kb * Cfg::kSeg)) >> 4) & 0x3FFFu) | (kLboA << 16);
+                    for (int tg = 0; tg < tap_groups; ++tg) {
+                        mbar_wait(&w_full[s], ph);
+                        mbar_wait(&w_peer[s], ph);
+                        tc_fence_after();
+                        const uint32_t b_st = ((smem_u32(sStage + s * Cfg::kWStage) >> 4) & 0x3FFFu) | ((uint32_t)((64 * 16) >> 4) << 16);
+#pragma unroll
+                        for (int tp = 0; tp < TPS; ++tp) {
+                            const int tap = tg * TPS + tp;
+                            const int shift = tap_dy(tap) * 9 + tap_dx(tap);
+                            const uint32_t a_lo = a_seg + (uint32_t)(kHalo + shift);
+                            const uint32_t b_lo = b_st + (uint32_t)(tp * (Cfg::kWTap >> 4));
+                            const uint32_t first = (kb | tap) != 0 ? 1u : 0u;
+#pragma unroll
+                            for (int t = 0; t < 2; ++t) {
+                                const uint4 m0 = c_tapmask[(t ? ph01 : ph00) + tap], m1 = c_tapmask[(t ? ph11 : ph10) + tap];
+#pragma unroll
+                                for (int j = 0; j < KCH / 2; ++j) {
+                                    const uint64_t adesc = ((uint64_t)kDescHi << 32) | (uint64_t)(a_lo + (uint32_t)(2 * j) * kLboA + (uint32_t)(t * 128));
+                                    const uint64_t bdesc = ((uint64_t)kDescHi << 32) | (uint64_t)(b_lo + (uint32_t)(2 * j * 64));
+                                    if (leader) umma2_bf16(d_addr + (uint32_t)(t * TS), adesc, bdesc, idesc, j == 0 ? first : 1u, m0, m1);
+                                }
+                            }
+                        }
+                        if (leader) umma2_commit_mc(&w_empty[s], 3);
+                        if (++s == S) { s = 0; ph ^= 1; }
+                        __syncwarp();
+                    }
+                    if (leader) umma2_commit_mc(&a_empty[kb], 3);
+                }
+                if (leader) umma2_commit_mc(&t_full[acc], 3);
+                __syncwarp();
+            }
+        }
+    } else if (warp < 10) {
+        // ===================== epilogue (both CTAs): as conv_kernel, accumulator release goes to the leader =====================
+        const int q = warp & 3;
+        const int t = (warp - 2) >> 2;
+        const int row = q * 32 + lane;
+        int n = 0;
+        uint4 res[NT / 8];
+        for (int work = cluster_id; work < total; work += n_clusters, ++n) {
+            const int item = work / p.n_tiles, n_tile = work - item * p.n_tiles;
+            const int pair = item * 2 + (int)crank;
+            const int acc = n & 1;
+            const uint32_t tph = (uint32_t)(n >> 1) & 1u;
+            const long long mrow = (long long)pair * kPairRows + t * 128 + row;
+            const bool real = mrow < real_rows;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 * TS + t * TS);
+            const bool has_res = p.residual != nullptr;
+            if (n == 0) {
+#pragma unroll
+                for (int k = 0; k < NT / 8; ++k) {
+                    res[k] = make_uint4(0, 0, 0, 0);
+                    if (has_res && real)
+                        res[k] = __ldg(reinterpret_cast<const uint4*>(
+                            p.residual + ((size_t)(n_tile * (NT / 8) + k) * p.out_rows + (size_t)(p.out_row0 + mrow)) * 16));
+                }
+            }
+            const int nwork = work + n_clusters;
+            const int nitem = nwork / p.n_tiles, nn_tile = nwork - nitem * p.n_tiles;
+            const long long nrow = (long long)(nitem * 2 + (int)crank) * kPairRows + t * 128 + row;
+            const bool nreal = nwork < total && nrow < real_rows;
+            mbar_wait(&t_full[acc], tph);
+            tc_fence_after();
+            auto emit = [&](const uint32_t* v, const int c0) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const int k = c0 / 8 + g;
+                    const int nn = n_tile * NT + c0 + g * 8;
+                    if (real) {
+                        float f[8];
+                        const float4 b0 = *reinterpret_cast<const float4*>(&sBias[nn]);
+                        const float4 b1 = *reinterpret_cast<const float4*>(&sBias[nn + 4]);
+                        f[0] = __uint_as_float(v[g * 8 + 0]) + b0.x;
+                        f[1] = __uint_as_float(v[g * 8 + 1]) + b0.y;
+                        f[2] = __uint_as_float(v[g * 8 + 2]) + b0.z;
+                        f[3] = __uint_as_float(v[g * 8 + 3]) + b0.w;
+                        f[4] = __uint_as_float(v[g * 8 + 4]) + b1.x;
+                        f[5] = __uint_as_float(v[g * 8 + 5]) + b1.y;
+                        f[6] = __uint_as_float(v[g * 8 + 6]) + b1.z;
+                        f[7] = __uint_as_float(v[g * 8 + 7]) + b1.w;
+                        const uint32_t rw[4] = {res[k].x, res[k].y, res[k].z, res[k].w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            f[2 * e] += __uint_as_float(rw[e] << 16);
+                            f[2 * e + 1] += __uint_as_float(rw[e] & 0xffff0000u);
+                        }
+                        if (p.relu) {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.0f);
+                        }
+                        const size_t off = ((size_t)(nn >> 3) * p.out_rows + (size_t)(p.out_row0 + mrow)) * 16;
+                        *reinterpret_cast<uint4*>(p.out + off) =
+                            make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+                    }
+                    res[k] = make_uint4(0, 0, 0, 0);
+                    if (has_res && nreal)
+                        res[k] = __ldg(reinterpret_cast<const uint4*>(
+                            p.residual + ((size_t)(nn_tile * (NT / 8) + k) * p.out_rows + (size_t)(p.out_row0 + nrow)) * 16));
+                }
+            };
+            {
+                constexpr int kSlabs = NT / 32;
+                uint32_t va[32], vb[32];
+                tmem_ld32(taddr, va);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < kSlabs; ++i) {
+                    if (i & 1) {
+                        if (i + 1 < kSlabs) tmem_ld32(taddr + (uint32_t)((i + 1) * 32), va);
+                        emit(vb, i * 32);
+                    } else {
+                        if (i + 1 < kSlabs) tmem_ld32(taddr + (uint32_t)((i + 1) * 32), vb);
+                        emit(va, i * 32);
+                    }
+                    if (i + 1 < kSlabs) tmem_ld_wait();
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (leader_cta) mbar_arrive(&t_empty[acc]);
+                else mbar_arrive_remote(&t_empty[acc], 0);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                // both CTAs are done with TMEM and with each other's barriers
+    if (warp == 1) tmem_dealloc2(tmem_base, Cfg::kTmemCols);
+}
+
 static NetState* net_state(xq_ctx* c)
 {
     if (!c->net) c->net = new NetState();
@@ -571,6 +925,38 @@ static int launch_conv(xq_ctx* c, GemmArgs& a, cudaStream_t s, int bit)
     const int total = ((a.m_tiles + 1) / 2) * a.n_tiles;
     const int grid = c->sm_count < total ? c->sm_count : total;   // persistent, one CTA per SM
     kern<<<grid, kConvThreads, Cfg::smem_bytes(kblocks, S, NA), s>>>(a, S, NA);
+    c->launches += 1;
+    XQ_CUDA(c, cudaGetLastError());
+    return XQ_OK;
+}
+
+template <int KCH, int TPS>
+static int launch_conv2(xq_ctx* c, GemmArgs& a, cudaStream_t s, int bit)
+{
+    using Cfg = Conv2Cfg<KCH, TPS>;
+    const int kblocks = a.kchunks / KCH;
+    const int S = Cfg::stages(kblocks);
+    if (kblocks > kMaxSeg || S < 2 || !a.w_half) return xq_fail(c, XQ_ERR_ARG, "conv2 kernel: %d k-blocks, %d stages, w_half %p", kblocks, S, (const void*)a.w_half);
+    auto kern = conv2_kernel<KCH, TPS>;
+    if (int rc = ensure_smem_attr(c, kern, bit)) return rc;
+    if (int rc = ensure_tapmask(c, s)) return rc;
+    const int items = (((a.m_tiles + 1) / 2) + 1) / 2;
+    const int total = items * a.n_tiles;
+    int clusters = c->sm_count / 2;
+    if (clusters > total) clusters = total;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(kConvThreads);
+    cfg.dynamicSmemBytes = Cfg::smem_bytes(kblocks, S);
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    XQ_CUDA(c, cudaLaunchKernelEx(&cfg, kern, (const GemmArgs)a, S));
     c->launches += 1;
     XQ_CUDA(c, cudaGetLastError());
     return XQ_OK;
@@ -892,6 +1278,7 @@ static int net_gemm(xq_ctx* c, const xq_gemm_desc* d, int n_boards_now, const in
     a.residual = (const uint8_t*)d->residual;
     a.out = (uint8_t*)d->out;
     a.out2 = (float*)d->out2;
+    a.w_half = (const uint8_t*)d->w_half;
     a.n_dev = n_dev;
     XQ_CUDA(c, cudaSetDevice(c->device));
     XqTimer tm(c, s);
@@ -900,6 +1287,7 @@ static int net_gemm(xq_ctx* c, const xq_gemm_desc* d, int n_boards_now, const in
     if (d->mode == 0 && d->nt == 128 && d->kch_iter == 8 && d->a_row0 >= kHalo) {
         // 128-channel layers: 3 taps per weight stage (48 KB x 3 stages): a stage hand-off costs an MMA-issuing
         // thread ~0.2 us, so fewer, larger stages beat a finer ring; wider layers only have room for 16 KB stages
+        if (c->net_2cta && d->w_half && d->kchunks % 8 == 0 && d->kchunks <= 32) return launch_conv2<8, 3>(c, a, s, 7);   // CTA pairs, cta_group::2
         if (d->kchunks == 16) return launch_conv<128, 8, false, 3, false>(c, a, s, 2);
         if (d->kchunks % 8 == 0 && d->kchunks <= 32) return launch_conv<128, 8, false, 1, false>(c, a, s, 3);
     }

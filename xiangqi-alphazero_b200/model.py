@@ -100,7 +100,7 @@ class _GemmDesc(C.Structure):
                 ("kchunks", C.c_int32), ("kch_iter", C.c_int32), ("relu", C.c_int32), ("n_boards", C.c_int32),
                 ("a_rows", C.c_int64), ("a_row0", C.c_int64), ("out_rows", C.c_int64), ("out_row0", C.c_int64),
                 ("out_stride", C.c_int64), ("a", C.c_void_p), ("w", C.c_void_p), ("bias", C.c_void_p),
-                ("residual", C.c_void_p), ("out", C.c_void_p), ("out2", C.c_void_p)]
+                ("residual", C.c_void_p), ("out", C.c_void_p), ("out2", C.c_void_p), ("w_half", C.c_void_p)]
 
 
 ROW0 = 16            # plane row of logical row 0 (front padding, >= 10 rows: the A block of the first tile starts 10 rows early)
@@ -152,7 +152,7 @@ class B200Net:
         B = self.max_batch
         self.m_tiles = (B * BOARD_ROWS + 127) // 128
         pairs = (self.m_tiles + 1) // 2                            # conv kernels work on pairs of 128-row tiles,
-        self.rows = ROW0 + pairs * 256 + 16                        # + the 10 rows the last pair's A block reads past its end
+        self.rows = ROW0 + (pairs + 1) // 2 * 2 * 256 + 16         # whole CTA-pair items (2 tile pairs) + the 10 rows read past the end
         self.b_tiles = (B + 127) // 128
         self.fc_rows = ((self.b_tiles + 1) // 2) * 256               # the FC kernel works on pairs of 128-board tiles
         bf = torch.bfloat16
@@ -186,12 +186,13 @@ class B200Net:
         def conv_layer(w, b, a_buf, out_buf, residual, relu, kch_iter):
             w, b = pad_channels(w, b, Cc, w.shape[1] if w.shape[1] == 15 else Cc)
             img = dev_t(conv_image(w, 128, kch_iter))
+            img64 = dev_t(conv_image(w, 64, kch_iter)) if kch_iter == 8 else None   # halves of N for the CTA-pair kernel
             bias = dev_t(b, torch.float32)
             d = _GemmDesc(mode=0, m_tiles=self.m_tiles, n_tiles=Cc // 128, nt=128, kchunks=a_buf.shape[0],
                           kch_iter=kch_iter, relu=int(relu), n_boards=B, a_rows=self.rows, a_row0=ROW0,
                           out_rows=self.rows, out_row0=ROW0, out_stride=0, a=a_buf.data_ptr(), w=img.data_ptr(),
                           bias=bias.data_ptr(), residual=None if residual is None else residual.data_ptr(),
-                          out=out_buf.data_ptr(), out2=None)
+                          out=out_buf.data_ptr(), out2=None, w_half=None if img64 is None else img64.data_ptr())
             self.layers.append(d)
 
         with torch.no_grad():
