@@ -100,7 +100,7 @@ def run(args, rank, world, local_rank, dist):
         "config": {"workload": f"iteration: configs[4], standard_train preset, {GAMES_PER_GPU} self-play games + {EVAL_PER_GPU} evaluation games per GPU, "
                                f"XiangqiNet(128,6), 200 sims/move, 5 epochs x batch 256 over a 50 000-sample ring, eval 100 sims",
                    "games_per_iteration": cfg.num_games_per_iter, "eval_games": cfg.eval_games,
-                   "parallelism": (f"games and evaluation pairs sharded x{world}; training dp{world} (SyncBN, gradient all-reduce split at the "
+                   "parallelism": (f"games and evaluation pairs sharded x{world}; training dp{world} (global-minibatch BatchNorm exchanged over NVLink peer memory, gradient all-reduce split at the "
                                    f"policy FC weight and overlapped with backward)" if cfg.dp_mode == "shard" else
                                    f"games and evaluation pairs sharded x{world}; training replicated on every rank (full minibatch, no collective in the step)"),
                    "dp_mode": cfg.dp_mode, "selfplay_leaves_per_game": cfg.selfplay_leaves_per_game,
