@@ -119,6 +119,14 @@ def run(args, rank, world, local_rank, dist):
     f1.record()
     torch.cuda.synchronize()
     fwd_ms = f0.elapsed_time(f1) / 20
+    # the same chain for ~0.4 s: the SM clock settles under the power cap like it does inside a ply
+    n_sus = max(50, int(400.0 / max(fwd_ms, 0.05)))
+    f0.record()
+    for _ in range(n_sus):
+        net.run()
+    f1.record()
+    torch.cuda.synchronize()
+    fwd_sus_ms = f0.elapsed_time(f1) / n_sus
     # the dominant kernel alone: one residual-tower conv (layer 1 = first conv of block 0), 20 back-to-back launches
     for _ in range(3):
         net.run_layer(1)
@@ -249,7 +257,7 @@ def run(args, rank, world, local_rank, dist):
                                          "ms_per_launch": conv_ms, "algorithmic_flops_per_launch": conv_flops,
                                          "achieved_tflops": conv_tf, "frac_of_burst_peak": conv_tf / peaks["bf16_tflops"],
                                          "timing": "20 back-to-back launches alone, CUDA events"},
-                     "algorithmic_flops_per_eval": FLOPS_PER_EVAL, "forward_ms_isolated": fwd_ms,
+                     "algorithmic_flops_per_eval": FLOPS_PER_EVAL, "forward_ms_isolated": fwd_ms, "forward_ms_back_to_back_400ms": fwd_sus_ms,
                      "forward_isolated_tflops": isolated_tf, "forward_isolated_frac_of_burst_peak": isolated_tf / peaks["bf16_tflops"],
                      "note": "achieved = FLOPs of all evaluations in the timed region / region time (search kernels and "
                              "power-capped clocks included); the isolated forward is timed back to back for 20 launches"},
@@ -370,6 +378,8 @@ def configs3_block(rank, world, local_rank, dist, sims):
     out = {"metric": "mcts_sims_per_sec", "value": sims_done / (ms * 1e-3), "unit": "sims/s", "n_gpus": world,
            "workload": f"configs[3]: {games} games/GPU x {sims} sims/move, XiangqiNet(256,20), Dirichlet(0.3) root noise, 1 warm-up + 2 timed plies",
            "ms_per_ply": ms / 2, "achieved_tflops": tf, "frac_of_sustained_peak": tf / peaks["bf16_tflops_sustained"],
+           "frac_of_burst_peak": tf / peaks["bf16_tflops"],
+           "note": "the sustained peak is cuBLAS bf16 8192^3 back to back for 4 s under the same power cap; a ratio above 1 means this path holds a higher rate than that GEMM did",
            "algorithmic_flops_per_eval": flops_per_eval(C3, R3), "error_bits": c1["error"]}
     del sp
     eng.close()

@@ -104,6 +104,14 @@ int xq_find_king_batch_host(xq_ctx* ctx, const int8_t* h_boards, const int8_t* h
 int xq_has_legal_moves_batch(xq_ctx* ctx, const int8_t* d_boards, const int8_t* d_sides, int B, uint8_t* d_has, void* stream);
 int xq_has_legal_moves_batch_host(xq_ctx* ctx, const int8_t* h_boards, const int8_t* h_sides, int B, uint8_t* h_has);
 
+/* Replaces _is_move_legal (game_core.pyx:209-252) / XiangqiGame._is_move_legal (game.py:441-490): out[i] = 1 iff after the
+ * move d_from[i] -> d_to[i] (squares row*9+col; ANY move, not only pseudo-legal ones, as in the reference) the king of
+ * d_sides[i] stands in its palace, does not face the other king on an open file and is not attacked. */
+int xq_move_is_legal_batch(xq_ctx* ctx, const int8_t* d_boards, const uint8_t* d_from, const uint8_t* d_to, const int8_t* d_sides,
+                           int B, uint8_t* d_out, void* stream);
+int xq_move_is_legal_batch_host(xq_ctx* ctx, const int8_t* h_boards, const uint8_t* h_from, const uint8_t* h_to, const int8_t* h_sides,
+                                int B, uint8_t* h_out);
+
 /* Which K1 kernel xq_movegen_batch[_host] launches: 1 = one thread per board (csrc/xq_rules_tpb.h, the default),
  * 0 = one warp per board (first generation; also the generator inside the MCTS kernels, where a warp owns a game).
  * Same outputs bit for bit; returns the previous value (or < 0 on a bad argument).  The default can also be chosen

@@ -52,6 +52,35 @@ def test_find_king_and_has_legal_moves_match_the_oracle(eng, oracle):
     assert np.array_equal(eng.has_legal_moves_host(boards[-999:], sides[-999:]), has[-999:])
 
 
+def test_move_is_legal_matches_the_oracle_on_any_move(eng, oracle):
+    """_is_move_legal (game_core.pyx:209-252) called directly through the C ABI: the legal moves of a position pass, and so
+    does exactly what the oracle passes among arbitrary (from, to) pairs -- the reference makes no pseudo-legality check."""
+    import torch
+    boards, sides = oracle.random_playout_positions(17, 4000)
+    rng = np.random.default_rng(3)
+    L = oracle.lib()
+    # (a) arbitrary moves of own pieces, empty squares and enemy pieces alike
+    frm = rng.integers(0, 90, size=len(sides)).astype(np.uint8)
+    to = rng.integers(0, 90, size=len(sides)).astype(np.uint8)
+    got = eng.move_is_legal(torch.from_numpy(boards).to(eng.dev), torch.from_numpy(frm).to(eng.dev), torch.from_numpy(to).to(eng.dev),
+                            torch.from_numpy(sides).to(eng.dev)).cpu().numpy()
+    want = np.array([L.xqo_move_is_legal(oracle._p(boards[i], oracle.C.c_int8), int(frm[i]), int(to[i]), int(sides[i]))
+                     for i in range(len(sides))], np.uint8)
+    assert np.array_equal(got, want) and 0 < want.sum() < len(want)
+    # (b) every generated legal move is legal, through the host-pointer form
+    acts, n, _, _ = oracle.movegen_batch(boards[:300], sides[:300])
+    bb, ff, tt, ss = [], [], [], []
+    for i in range(300):
+        for a in acts[i, :n[i]]:
+            bb.append(boards[i]); ff.append(a // 90); tt.append(a % 90); ss.append(sides[i])
+    ok = eng.move_is_legal_host(np.array(bb, np.int8), np.array(ff, np.uint8), np.array(tt, np.uint8), np.array(ss, np.int8))
+    assert ok.all()
+    # (c) the drop-in XiangqiGame._is_move_legal answers through it
+    import game
+    g = game.XiangqiGame()
+    assert g._is_move_legal(0, 0, 1, 0, 1) and not g._is_move_legal(0, 4, 5, 4, 1)     # rook step; king leaving its palace
+
+
 def test_packed_planes_are_the_float_planes(eng, oracle):
     import torch
     import xq_native

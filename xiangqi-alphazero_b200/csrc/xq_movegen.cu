@@ -392,6 +392,36 @@ is_attacked_kernel(const int8_t* __restrict__ boards, const uint8_t* __restrict_
     }
 }
 
+// _is_move_legal (game_core.pyx:209-252; game.py:441-490): make the move from -> to on a copy (ANY move: the reference
+// does not ask for pseudo-legality here), then `side`'s king must stand in its own palace, must not face the other king on
+// an open file and must not be attacked.  The facing test needs no clause of its own: _is_attacked counts the enemy king as
+// a rook on an open ray (pyx:117).
+__global__ void __launch_bounds__(kAtkThreads)
+move_is_legal_kernel(const int8_t* __restrict__ boards, const uint8_t* __restrict__ from, const uint8_t* __restrict__ to,
+                     const int8_t* __restrict__ sides, int B, uint8_t* __restrict__ out)
+{
+    __shared__ int8_t sb[kAtkThreads * kSquares];
+    const int base = blockIdx.x * kAtkThreads;
+    const int nb = min(kAtkThreads, B - base);
+    for (int i = threadIdx.x; i < nb * kSquares; i += kAtkThreads) sb[i] = boards[(size_t)base * kSquares + i];
+    __syncthreads();
+    if (threadIdx.x >= nb) return;
+    int8_t* b = &sb[threadIdx.x * kSquares];
+    const int f = from[base + threadIdx.x], t = to[base + threadIdx.x], side = sides[base + threadIdx.x];
+    bool ok = false;
+    if (f < kSquares && t < kSquares) {
+        b[t] = b[f];
+        b[f] = 0;
+        const int target = side == 1 ? 1 : -1, r0 = side == 1 ? 0 : 7;
+        int k = -1;
+        for (int r = r0 + 2; r >= r0; --r)
+            for (int c = 5; c >= 3; --c)
+                if (b[r * 9 + c] == target) k = r * 9 + c;
+        if (k >= 0) ok = !attacked_sq(b, k / 9, k % 9, -side, -1, -1, 0);
+    }
+    out[base + threadIdx.x] = ok ? 1 : 0;
+}
+
 // cy_find_king (game_core.pyx:78-101, 493-505): the side's king searched ONLY in its own 3x3 palace, row-major;
 // out = row*9+col, or -1 when there is none (the reference returns None)
 __global__ void __launch_bounds__(128)
@@ -812,6 +842,19 @@ extern "C" int xq_is_attacked_batch_host(xq_ctx* c, const int8_t* h_boards, cons
     return XQ_OK;
 }
 
+extern "C" int xq_move_is_legal_batch(xq_ctx* c, const int8_t* d_boards, const uint8_t* d_from, const uint8_t* d_to, const int8_t* d_sides,
+                                      int B, uint8_t* d_out, void* stream)
+{
+    if (!c) return xq_fail(nullptr, XQ_ERR_ARG, "xq_move_is_legal_batch: ctx is NULL");
+    if (B < 0 || (B > 0 && (!d_boards || !d_from || !d_to || !d_sides || !d_out)))
+        return xq_fail(c, XQ_ERR_ARG, "xq_move_is_legal_batch: bad arguments (B=%d)", B);
+    if (B == 0) return XQ_OK;
+    move_is_legal_kernel<<<(B + kAtkThreads - 1) / kAtkThreads, kAtkThreads, 0, (cudaStream_t)stream>>>(d_boards, d_from, d_to, d_sides, B, d_out);
+    c->launches += 1;
+    XQ_CUDA(c, cudaGetLastError());
+    return XQ_OK;
+}
+
 extern "C" int xq_find_king_batch(xq_ctx* c, const int8_t* d_boards, const int8_t* d_sides, int B, int8_t* d_king_sq, void* stream)
 {
     if (!c) return xq_fail(nullptr, XQ_ERR_ARG, "xq_find_king_batch: ctx is NULL");
@@ -878,6 +921,32 @@ static int seam_query_host(xq_ctx* c, const int8_t* h_boards, const int8_t* h_si
     XQ_CUDA(c, cudaStreamSynchronize(s));
     return XQ_OK;
 }
+extern "C" int xq_move_is_legal_batch_host(xq_ctx* c, const int8_t* h_boards, const uint8_t* h_from, const uint8_t* h_to, const int8_t* h_sides,
+                                           int B, uint8_t* h_out)
+{
+    if (!c) return xq_fail(nullptr, XQ_ERR_ARG, "xq_move_is_legal_batch_host: ctx is NULL");
+    if (B < 0 || (B > 0 && (!h_boards || !h_from || !h_to || !h_sides || !h_out)))
+        return xq_fail(c, XQ_ERR_ARG, "xq_move_is_legal_batch_host: bad arguments (B=%d)", B);
+    if (B == 0) return XQ_OK;
+    XQ_CUDA(c, cudaSetDevice(c->device));
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t o_f = al((size_t)B * 90), o_t = al(o_f + B), o_s = al(o_t + B), o_out = al(o_s + B);
+    int rc = ensure_pipe(c, o_out + B);
+    if (rc) return rc;
+    cudaStream_t s = c->pipe[0];
+    char* d = (char*)c->d_stage[0];
+    XQ_CUDA(c, cudaMemcpyAsync(d, h_boards, (size_t)B * 90, cudaMemcpyHostToDevice, s));
+    XQ_CUDA(c, cudaMemcpyAsync(d + o_f, h_from, (size_t)B, cudaMemcpyHostToDevice, s));
+    XQ_CUDA(c, cudaMemcpyAsync(d + o_t, h_to, (size_t)B, cudaMemcpyHostToDevice, s));
+    XQ_CUDA(c, cudaMemcpyAsync(d + o_s, h_sides, (size_t)B, cudaMemcpyHostToDevice, s));
+    rc = xq_move_is_legal_batch(c, (const int8_t*)d, (const uint8_t*)(d + o_f), (const uint8_t*)(d + o_t), (const int8_t*)(d + o_s), B,
+                                (uint8_t*)(d + o_out), s);
+    if (rc) return rc;
+    XQ_CUDA(c, cudaMemcpyAsync(h_out, d + o_out, (size_t)B, cudaMemcpyDeviceToHost, s));
+    XQ_CUDA(c, cudaStreamSynchronize(s));
+    return XQ_OK;
+}
+
 extern "C" int xq_find_king_batch_host(xq_ctx* c, const int8_t* h_boards, const int8_t* h_sides, int B, int8_t* h_king_sq)
 {
     return seam_query_host(c, h_boards, h_sides, B, h_king_sq, true);

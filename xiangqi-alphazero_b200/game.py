@@ -136,13 +136,9 @@ class XiangqiGame:
         """game.py:441-490: after the move `player`'s king must stand in its palace, must not face the other
         king on an open file and must not be attacked.  One GPU query on the moved board: the attack test
         counts the enemy king as a rook (game.py:176-200), which is the facing-kings test."""
-        b = self.board.copy()
-        b[tr, tc] = b[fr, fc]
-        b[fr, fc] = EMPTY
-        k = self._find_king_pos(player, b)
-        if k is None:
-            return False
-        return not self._is_attacked(b, k[0], k[1], -player)
+        out = engine().move_is_legal_host(self.board, np.array([fr * 9 + fc], np.uint8), np.array([tr * 9 + tc], np.uint8),
+                                          np.array([player], np.int8))
+        return bool(out[0])
 
     @staticmethod
     def _kings_facing_fast(board: np.ndarray) -> bool:

@@ -70,6 +70,8 @@ def lib():
     _sig(L, "xq_find_king_batch_host", i32, vp, vp, vp, i32, vp)
     _sig(L, "xq_has_legal_moves_batch", i32, vp, vp, vp, i32, vp, vp)
     _sig(L, "xq_has_legal_moves_batch_host", i32, vp, vp, vp, i32, vp)
+    _sig(L, "xq_move_is_legal_batch", i32, vp, vp, vp, vp, vp, i32, vp, vp)
+    _sig(L, "xq_move_is_legal_batch_host", i32, vp, vp, vp, vp, vp, i32, vp)
     _sig(L, "xq_overflow_count", i32, vp, i32)
     _sig(L, "xq_set_movegen_impl", i32, vp, i32)
     _sig(L, "xq_random_playouts", i32, vp, u64, i32, vp, vp, vp, vp, vp)
@@ -113,7 +115,8 @@ def lib():
 EXPORTS = ["xq_create", "xq_destroy", "xq_last_error", "xq_version", "xq_launch_count", "xq_set_timing",
            "xq_last_kernel_ms", "xq_movegen_batch", "xq_movegen_batch_host", "xq_is_attacked_batch",
            "xq_is_attacked_batch_host", "xq_movegen_batch_host_packed", "xq_planes_bits", "xq_find_king_batch",
-           "xq_find_king_batch_host", "xq_has_legal_moves_batch", "xq_has_legal_moves_batch_host", "xq_overflow_count", "xq_set_movegen_impl", "xq_random_playouts",
+           "xq_find_king_batch_host", "xq_has_legal_moves_batch", "xq_has_legal_moves_batch_host", "xq_move_is_legal_batch",
+           "xq_move_is_legal_batch_host", "xq_overflow_count", "xq_set_movegen_impl", "xq_random_playouts",
            "xq_mcts_create", "xq_mcts_set_games", "xq_mcts_root_begin", "xq_mcts_root_expand", "xq_mcts_select",
            "xq_mcts_expand_backup", "xq_mcts_leaf_info", "xq_mcts_root_visits", "xq_mcts_root_priors", "xq_mcts_stats",
            "xq_net_gemm", "xq_net_value_head", "xq_net_run", "xq_net_run_counted", "xq_selfplay_create", "xq_selfplay_reset",
@@ -270,6 +273,24 @@ class Engine:
         out = t.empty((boards.shape[0],), dtype=t.uint8, device=self.dev)
         self._check(self.L.xq_has_legal_moves_batch(self.h, boards.data_ptr(), sides.contiguous().data_ptr(),
                                                     boards.shape[0], out.data_ptr(), self._stream()))
+        return out
+
+    def move_is_legal(self, boards, frm, to, sides):
+        """_is_move_legal batched (device tensors): uint8 [B]; frm / to uint8 squares, any move."""
+        t = self.torch
+        boards = boards.reshape(-1, 90).contiguous()
+        out = t.empty((boards.shape[0],), dtype=t.uint8, device=self.dev)
+        self._check(self.L.xq_move_is_legal_batch(self.h, boards.data_ptr(), frm.contiguous().data_ptr(), to.contiguous().data_ptr(),
+                                                  sides.contiguous().data_ptr(), boards.shape[0], out.data_ptr(), self._stream()))
+        return out
+
+    def move_is_legal_host(self, boards: np.ndarray, frm: np.ndarray, to: np.ndarray, sides: np.ndarray) -> np.ndarray:
+        boards = np.ascontiguousarray(boards, np.int8).reshape(-1, 90)
+        frm, to = np.ascontiguousarray(frm, np.uint8), np.ascontiguousarray(to, np.uint8)
+        sides = np.ascontiguousarray(sides, np.int8)
+        out = np.empty(boards.shape[0], np.uint8)
+        self._check(self.L.xq_move_is_legal_batch_host(self.h, _np_ptr(boards), _np_ptr(frm), _np_ptr(to), _np_ptr(sides),
+                                                       boards.shape[0], _np_ptr(out)))
         return out
 
     def find_king_host(self, boards: np.ndarray, sides: np.ndarray) -> np.ndarray:
