@@ -187,7 +187,8 @@ def run(args, rank, world, local_rank, dist):
         api = {"value": stats["new_samples"] // 2 * sims / api_s, "seconds": api_s, "games": stats["games"],
                "new_samples": stats["new_samples"], "dense_tuples_materialised": len(dense),
                "h2d_bytes": h2d_w + 64, "d2h_bytes": rec_bytes // max(world, 1) + games * 3 + 14 * 8,
-               "config": f"{games * world} games, max_game_length 8 (2-8 searched plies after the random opening), {sims} sims/move"}
+               "config": f"{games * world} games, max_game_length 8 (2-8 searched plies after the random opening), {sims} sims/move",
+               "breakdown": dict(ps.LAST_TIMING)}
         del data, dense
         ps._ENGINES.clear()
 
@@ -267,7 +268,7 @@ def run(args, rank, world, local_rank, dist):
         "e2e": ({"value": api["value"], "unit": "sims/s", "api": "parallel_self_play",
                  "h2d_bytes_per_step": api["h2d_bytes"], "d2h_bytes_per_step": api["d2h_bytes"],
                  "step": "one parallel_self_play(model, config) call: " + api["config"], "seconds": api["seconds"],
-                 "games": api["games"], "new_samples": api["new_samples"],
+                 "games": api["games"], "new_samples": api["new_samples"], "breakdown": api.get("breakdown"),
                  "engine_level": {"value": e2e_sims / e2e_s, "unit": "sims/s", "api": "SelfPlayEngine.play + counters + fetch per ply",
                                   "h2d_bytes_per_step": 64 + 160, "d2h_bytes_per_step": d2h // e2e_steps}}
                 if api else

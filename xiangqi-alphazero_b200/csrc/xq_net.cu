@@ -1291,6 +1291,11 @@ static int net_gemm(xq_ctx* c, const xq_gemm_desc* d, int n_boards_now, const in
         if (d->kchunks == 16) return launch_conv<128, 8, false, 3, false>(c, a, s, 2);
         if (d->kchunks % 8 == 0 && d->kchunks <= 32) return launch_conv<128, 8, false, 1, false>(c, a, s, 3);
     }
+    // towers of at most 64 channels (the reference's quick preset, train.py:661): N = 64 tiles, no zero-padded channels
+    if (d->mode == 0 && d->nt == 64 && d->kch_iter == 8 && d->kchunks == 8 && d->n_tiles == 1 && d->a_row0 >= kHalo)
+        return launch_conv<64, 8, false, 3, false>(c, a, s, 8);
+    if (d->mode == 0 && d->nt == 64 && d->kch_iter == 2 && d->kchunks == 2 && d->n_tiles == 1 && d->a_row0 >= kHalo)
+        return launch_conv<64, 2, false, 9, true>(c, a, s, 9);
     if (d->mode == 0 && d->nt == 128 && d->kch_iter == 2 && d->kchunks == 2 && d->n_tiles == 1 && d->a_row0 >= kHalo)
         return launch_conv<128, 2, false, 9, true>(c, a, s, 4);                      // 15-plane input conv, weights resident
     if (d->mode == 0 && d->nt == 128 && d->kch_iter == 2 && d->kchunks == 2 && d->a_row0 >= kHalo)

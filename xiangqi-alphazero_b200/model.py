@@ -144,10 +144,11 @@ class B200Net:
         self.max_batch = int(max_batch)
         dev = eng.dev
         Cm, R = model.num_channels, model.num_res_blocks
-        # The conv kernels tile output channels by 128.  Narrower towers (the reference's quick preset uses 64,
-        # train.py:661) run zero-padded to the next multiple of 128: padded channels have zero weights and zero bias,
-        # stay exactly 0 through ReLU / residual adds and contribute nothing downstream.
-        Cc = (Cm + 127) // 128 * 128
+        # The conv kernels tile output channels by 128, or by 64 for towers of at most 64 channels (the reference's quick
+        # preset, train.py:661).  Other widths run zero-padded to the next multiple: padded channels have zero weights and
+        # zero bias, stay exactly 0 through ReLU / residual adds and contribute nothing downstream.
+        NTc = 64 if Cm <= 64 else 128
+        Cc = (Cm + NTc - 1) // NTc * NTc
         self.C, self.R, self.C_model = Cc, R, Cm
         B = self.max_batch
         self.m_tiles = (B * BOARD_ROWS + 127) // 128
@@ -165,10 +166,27 @@ class B200Net:
         self.value = z(B, dt=torch.float32)
         self.keep = []                                   # weight images / biases (owned here)
         self.layers = []
-        # fold on a private CPU copy so the caller's module (device, mode) is left untouched
-        m = XiangqiNet(Cm, R)
-        m.load_state_dict({k: v.detach().cpu().clone() for k, v in model.state_dict().items()})
-        m.eval()
+        # Fold and re-tile ON THE DEVICE from a float32 copy of the state dict (one 100 MB upload, then device ops): the caller's
+        # module (device, mode) is left untouched.  _SD gives attribute / index access by the state_dict key names.
+        sd = {k: v.detach().to(device=dev, dtype=torch.float32 if v.is_floating_point() else v.dtype) for k, v in model.state_dict().items()}
+        eps = {name: mod.eps for name, mod in model.named_modules() if isinstance(mod, nn.modules.batchnorm._BatchNorm)}
+
+        class _SD:
+            def __init__(self, prefix):
+                self._p = prefix
+
+            def _sub(self, name):
+                full = f"{self._p}.{name}" if self._p else str(name)
+                return sd[full] if full in sd else _SD(full)
+
+            __getattr__ = lambda self, name: self._sub(name) if not name.startswith("_") else object.__getattribute__(self, name)
+            __getitem__ = lambda self, i: self._sub(i)
+
+            @property
+            def eps(self):
+                return eps[self._p]
+        m = _SD("")
+        m_res_blocks = [_SD(f"res_blocks.{i}") for i in range(R)]
 
         def dev_t(t, dt=None):
             t = t.to(dev) if dt is None else t.to(device=dev, dtype=dt)
@@ -177,18 +195,18 @@ class B200Net:
             return t
 
         def pad_channels(w, b, co, ci):
-            wp = torch.zeros((co, ci) + tuple(w.shape[2:]), dtype=torch.float32)
+            wp = torch.zeros((co, ci) + tuple(w.shape[2:]), dtype=torch.float32, device=w.device)
             wp[:w.shape[0], :w.shape[1]] = w
-            bp = torch.zeros(co, dtype=torch.float32)
+            bp = torch.zeros(co, dtype=torch.float32, device=w.device)
             bp[:b.shape[0]] = b
             return wp, bp
 
         def conv_layer(w, b, a_buf, out_buf, residual, relu, kch_iter):
             w, b = pad_channels(w, b, Cc, w.shape[1] if w.shape[1] == 15 else Cc)
-            img = dev_t(conv_image(w, 128, kch_iter))
-            img64 = dev_t(conv_image(w, 64, kch_iter)) if kch_iter == 8 else None   # halves of N for the CTA-pair kernel
+            img = dev_t(conv_image(w, NTc, kch_iter))
+            img64 = dev_t(conv_image(w, 64, kch_iter)) if (kch_iter == 8 and NTc == 128) else None   # halves of N for the CTA-pair kernel
             bias = dev_t(b, torch.float32)
-            d = _GemmDesc(mode=0, m_tiles=self.m_tiles, n_tiles=Cc // 128, nt=128, kchunks=a_buf.shape[0],
+            d = _GemmDesc(mode=0, m_tiles=self.m_tiles, n_tiles=Cc // NTc, nt=NTc, kchunks=a_buf.shape[0],
                           kch_iter=kch_iter, relu=int(relu), n_boards=B, a_rows=self.rows, a_row0=ROW0,
                           out_rows=self.rows, out_row0=ROW0, out_stride=0, a=a_buf.data_ptr(), w=img.data_ptr(),
                           bias=bias.data_ptr(), residual=None if residual is None else residual.data_ptr(),
@@ -199,7 +217,7 @@ class B200Net:
             w, b = fold_bn(m.input_conv[0].weight, m.input_conv[1])
             conv_layer(w, b, self.x0, self.act[0], None, True, 2)
             cur = 0
-            for blk in m.res_blocks:
+            for blk in m_res_blocks:
                 t, o = (cur + 1) % 3, (cur + 2) % 3
                 w, b = fold_bn(blk.conv1.weight, blk.bn1)
                 conv_layer(w, b, self.act[cur], self.act[t], None, True, 8)
@@ -210,8 +228,8 @@ class B200Net:
             # heads: policy conv1x1 (32) and value conv1x1 (4) share one GEMM with N = 48
             wp, bp = fold_bn(m.policy_head[0].weight, m.policy_head[1])
             wv, bv = fold_bn(m.value_head[0].weight, m.value_head[1])
-            wh = torch.zeros((48, Cc, 1, 1))
-            bh = torch.zeros(48)
+            wh = torch.zeros((48, Cc, 1, 1), device=dev)
+            bh = torch.zeros(48, device=dev)
             wh[:32, :Cm], wh[32:36, :Cm] = wp, wv
             bh[:32], bh[32:36] = bp, bv
             img = dev_t(conv_image(wh, 48, 8))
@@ -223,9 +241,9 @@ class B200Net:
                                          out2=self.vfeat.data_ptr()))
             # policy FC 2880 -> 8100: torch flatten index ch*90+pos  ->  kernel index pos*32+ch
             wf = m.policy_head[4].weight.detach().float().reshape(ACTION_SPACE, 32, 90).permute(0, 2, 1)
-            wfp = torch.zeros((FC_TILES * FC_NT, 2880))
+            wfp = torch.zeros((FC_TILES * FC_NT, 2880), device=dev)
             wfp[:ACTION_SPACE] = wf.reshape(ACTION_SPACE, 2880)
-            bfp = torch.zeros(FC_TILES * FC_NT)
+            bfp = torch.zeros(FC_TILES * FC_NT, device=dev)
             bfp[:ACTION_SPACE] = m.policy_head[4].bias.detach().float()
             img = dev_t(conv_image(wfp.reshape(FC_TILES * FC_NT, 2880, 1, 1), FC_NT, 8))
             bias = dev_t(bfp, torch.float32)

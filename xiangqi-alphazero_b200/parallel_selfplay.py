@@ -115,6 +115,7 @@ def _play_local(model, config, my_games: int, local_device: int, detail: bool = 
     if my_games <= 0:
         out = (np.zeros((0, 896), np.uint8), np.zeros(0, np.float32), wins, total_steps, valid)
         return out + (np.zeros(0, np.int8), np.zeros(0, np.int16)) if detail else out
+    t0 = time.perf_counter()
     eng = engine(local_device)
     slots = min(my_games, int(os.environ.get("XQ_SELFPLAY_SLOTS", "4096")))
     sims = int(getattr(config, "num_simulations", 200))
@@ -134,9 +135,13 @@ def _play_local(model, config, my_games: int, local_device: int, detail: bool = 
     sp.reset()
     seed = int.from_bytes(os.urandom(8), 'big')  # the reference seeds workers from os.urandom (:167-170)
     cfg = SelfPlayEngine.make_config(config, my_games, seed=seed, add_noise=True, leaves_per_game=kl)
+    t1 = time.perf_counter()
     c = sp.play_games(cfg)
+    t2 = time.perf_counter()
     raw, winner, plies = sp.fetch(0, c["samples"])
     rec, z = records_with_labels(raw, winner)
+    LAST_TIMING.clear()
+    LAST_TIMING.update(setup_s=t1 - t0, play_s=t2 - t1, fetch_label_s=time.perf_counter() - t2, sims=c["sims"])
     for g in range(my_games):
         if winner[g] != 2:
             valid += 1
@@ -165,6 +170,7 @@ def _play_one_game(model_or_client, config, device='cpu') -> Tuple[List, int, in
     return list(SampleList(rec, z, augment=False)), int(winner[0]), int(plies[0])
 
 
+LAST_TIMING = {}    # phases of the most recent local self-play call: engine / weight set-up, device play loop, record download + labels
 LAST_FANIN = {}     # diagnostics of the most recent multi-rank fan-in: samples and bytes each rank contributed / received
 
 

@@ -171,8 +171,11 @@ class SelfPlayEngine:
         """Play until cfg.target_games games have finished (or max_plies plies)."""
         played = 0
         last_finished, last_progress = -1, 0
+        tail = False
         while played < max_plies:
-            step = min(chunk, max_plies - played)
+            # once every game has been started the loop is in its tail: ask after every ply, so that no ply of
+            # num_simulations lockstep steps is enqueued for slots that have all finished
+            step = min(1 if tail else chunk, max_plies - played)
             self.play(cfg, step)
             played += step
             c = self.counters()
@@ -180,6 +183,7 @@ class SelfPlayEngine:
                 raise xq_native.XqError(f"self-play device error bits {c['error']}")
             if c["finished"] >= min(cfg.target_games, self.max_games):
                 break
+            tail = c["started"] >= min(cfg.target_games, self.max_games)
             if c["finished"] != last_finished:
                 last_finished, last_progress = c["finished"], played
             elif played - last_progress > 2 * 201 + 64:      # no game can last this long (game.py:595: 200 plies)
