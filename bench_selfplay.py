@@ -170,11 +170,15 @@ def run(args, rank, world, local_rank, dist):
             pass
         acfg = ApiCfg()
         acfg.num_simulations = sims
-        acfg.max_game_length = 8                              # openings are 0..6 random plies: 2..8 searched plies per game
+        acfg.max_game_length = 16                             # openings are 0..6 random plies: 10..16 searched plies per game
         acfg.num_games_per_iter = games * world
         acfg.selfplay_leaves_per_game = leaves
         host_model = M.XiangqiNet(CHANNELS, BLOCKS).eval()
         host_model.load_state_dict(model.state_dict())
+        wcfg = ApiCfg()                                       # warm-up call (as train.py's second iteration sees it: the engine
+        wcfg.num_simulations, wcfg.max_game_length = sims, 2  # of the first call is reused, only the weights are folded again)
+        wcfg.num_games_per_iter, wcfg.selfplay_leaves_per_game = games * world, leaves
+        ps.parallel_self_play(host_model, wcfg)
         barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -187,7 +191,7 @@ def run(args, rank, world, local_rank, dist):
         api = {"value": stats["new_samples"] // 2 * sims / api_s, "seconds": api_s, "games": stats["games"],
                "new_samples": stats["new_samples"], "dense_tuples_materialised": len(dense),
                "h2d_bytes": h2d_w + 64, "d2h_bytes": rec_bytes // max(world, 1) + games * 3 + 14 * 8,
-               "config": f"{games * world} games, max_game_length 8 (2-8 searched plies after the random opening), {sims} sims/move",
+               "config": f"{games * world} games, max_game_length 16 (10-16 searched plies after the random opening), {sims} sims/move, after one warm-up call",
                "breakdown": dict(ps.LAST_TIMING)}
         del data, dense
         ps._ENGINES.clear()
