@@ -1287,7 +1287,14 @@ static int net_gemm(xq_ctx* c, const xq_gemm_desc* d, int n_boards_now, const in
     if (d->mode == 0 && d->nt == 128 && d->kch_iter == 8 && d->a_row0 >= kHalo) {
         // 128-channel layers: 3 taps per weight stage (48 KB x 3 stages): a stage hand-off costs an MMA-issuing
         // thread ~0.2 us, so fewer, larger stages beat a finer ring; wider layers only have room for 16 KB stages
-        if (c->net_2cta && d->w_half && d->kchunks % 8 == 0 && d->kchunks <= 32) return launch_conv2<8, 3>(c, a, s, 7);   // CTA pairs, cta_group::2
+        if (c->net_2cta && d->w_half && d->kchunks % 8 == 0 && d->kchunks <= 32) {
+            const int rc = launch_conv2<8, 3>(c, a, s, 7);                             // CTA pairs, cta_group::2
+            if (rc != XQ_ERR_CUDA) return rc;
+            // a device / partition that refuses the cluster launch: the single-CTA kernel computes the same layer
+            (void)cudaGetLastError();
+            c->net_2cta = false;
+            fprintf(stderr, "[xq_b200] cluster launch of conv2_kernel failed (%s): using the single-CTA conv kernel\n", c->err);
+        }
         if (d->kchunks == 16) return launch_conv<128, 8, false, 3, false>(c, a, s, 2);
         if (d->kchunks % 8 == 0 && d->kchunks <= 32) return launch_conv<128, 8, false, 1, false>(c, a, s, 3);
     }
