@@ -119,14 +119,6 @@ def run(args, rank, world, local_rank, dist):
     f1.record()
     torch.cuda.synchronize()
     fwd_ms = f0.elapsed_time(f1) / 20
-    # the same chain for ~0.4 s: the SM clock settles under the power cap like it does inside a ply
-    n_sus = max(50, int(400.0 / max(fwd_ms, 0.05)))
-    f0.record()
-    for _ in range(n_sus):
-        net.run()
-    f1.record()
-    torch.cuda.synchronize()
-    fwd_sus_ms = f0.elapsed_time(f1) / n_sus
     # the dominant kernel alone: one residual-tower conv (layer 1 = first conv of block 0), 20 back-to-back launches
     for _ in range(3):
         net.run_layer(1)
@@ -137,6 +129,14 @@ def run(args, rank, world, local_rank, dist):
     k1.record()
     torch.cuda.synchronize()
     conv_ms = k0.elapsed_time(k1) / 20
+    # the same chain for ~0.4 s: the SM clock settles under the power cap like it does inside a ply
+    n_sus = max(50, int(400.0 / max(fwd_ms, 0.05)))
+    f0.record()
+    for _ in range(n_sus):
+        net.run()
+    f1.record()
+    torch.cuda.synchronize()
+    fwd_sus_ms = f0.elapsed_time(f1) / n_sus
     fwd_boards = net.max_batch                                       # = games x leaves_per_game
 
     # e2e, engine level: the same plies through the host-facing engine calls -- per step the host uploads the step's

@@ -30,6 +30,8 @@ struct xq_ctx {
     void* peer = nullptr;                 // xq_bn.cu: NVLink peer exchange buffers of the data-parallel BatchNorm
     int movegen_impl = 1;                 // XQ_MOVEGEN_IMPL=thread|warp: K1 kernel generation (1 = one thread per board, the default: 2x the
                                           // positions/s of the one-warp-per-board kernel, same bytes out)
+    bool net_fork = false;                // XQ_NET_FORK=1: value MLP on a side stream next to the policy FC (measured: 1.002 ms per forward against
+                                          // 0.976 ms in sequence -- the co-running CTAs slow the FC more than the 19 us they hide; off)
     bool net_2cta = true;                 // XQ_NET_2CTA=0 (read once in xq_create): tower convs on the single-CTA kernel instead of CTA pairs
     bool tpb_attr_set = false;            // dynamic shared-memory limit of movegen_tpb_kernel raised on this context's device
 };

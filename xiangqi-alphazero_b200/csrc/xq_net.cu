@@ -76,6 +76,8 @@ __device__ __forceinline__ void live_size(const GemmArgs& p, int rows_per_board,
 // per-context state of this translation unit
 struct NetState {
     bool tapmask_done = false;
+    cudaStream_t side = nullptr;          // the value MLP runs here, next to the policy FC (both depend on the heads conv only)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     uint32_t attr_done = 0;   // bit per kernel instantiation: dynamic shared-memory limit raised on THIS context's device
 };
 
@@ -1245,6 +1247,9 @@ extern "C" void xq_net_free_(xq_ctx* c)
 {
     if (!c || !c->net) return;
     NetState* N = reinterpret_cast<NetState*>(c->net);
+    if (N->side) cudaStreamDestroy(N->side);
+    if (N->ev_fork) cudaEventDestroy(N->ev_fork);
+    if (N->ev_join) cudaEventDestroy(N->ev_join);
     delete N;
     c->net = nullptr;
 }
@@ -1334,17 +1339,46 @@ extern "C" int xq_net_value_head(xq_ctx* c, const float* d_feats, const float* d
     return net_value_head(c, d_feats, d_w1t, d_b1, d_w2, b2, d_value, B, nullptr, (cudaStream_t)stream);
 }
 
+// All layers of one forward.  The value MLP depends on the heads conv only; with XQ_NET_FORK=1 it is forked onto a side
+// stream right after that layer and runs next to the policy FC (their shared memory and registers fit one SM together).
+// Measured on one box (profiles/r2_fwd_ab.txt): 1.002 ms per forward forked against 0.976 ms in sequence, so the default
+// keeps the sequence.
+static int net_run_impl(xq_ctx* c, const xq_gemm_desc* layers, int n_layers, const float* d_vfeats, const float* d_w1t,
+                        const float* d_b1, const float* d_w2, float b2, float* d_value, int B, const int* n_dev, cudaStream_t s)
+{
+    NetState* N = net_state(c);
+    bool forked = false;
+    for (int i = 0; i < n_layers; ++i) {
+        int rc = net_gemm(c, &layers[i], B, n_dev, s);
+        if (rc) return rc;
+        if (c->net_fork && layers[i].mode == 1 && i + 1 < n_layers && !forked) {
+            if (!N->side) {
+                XQ_CUDA(c, cudaStreamCreateWithFlags(&N->side, cudaStreamNonBlocking));
+                XQ_CUDA(c, cudaEventCreateWithFlags(&N->ev_fork, cudaEventDisableTiming));
+                XQ_CUDA(c, cudaEventCreateWithFlags(&N->ev_join, cudaEventDisableTiming));
+            }
+            XQ_CUDA(c, cudaEventRecord(N->ev_fork, s));
+            XQ_CUDA(c, cudaStreamWaitEvent(N->side, N->ev_fork, 0));
+            rc = net_value_head(c, d_vfeats, d_w1t, d_b1, d_w2, b2, d_value, B, n_dev, N->side);
+            if (rc) return rc;
+            XQ_CUDA(c, cudaEventRecord(N->ev_join, N->side));
+            forked = true;
+        }
+    }
+    if (forked) {
+        XQ_CUDA(c, cudaStreamWaitEvent(s, N->ev_join, 0));
+        return XQ_OK;
+    }
+    return net_value_head(c, d_vfeats, d_w1t, d_b1, d_w2, b2, d_value, B, n_dev, s);
+}
+
 // Run a whole forward (a list of layer descriptors followed by the value head) for the first B boards.
 extern "C" int xq_net_run(xq_ctx* c, const xq_gemm_desc* layers, int n_layers, const float* d_vfeats,
                           const float* d_w1t, const float* d_b1, const float* d_w2, float b2, float* d_value, int B,
                           void* stream)
 {
     if (B <= 0) return XQ_OK;
-    for (int i = 0; i < n_layers; ++i) {
-        int rc = net_gemm(c, &layers[i], B, nullptr, (cudaStream_t)stream);
-        if (rc) return rc;
-    }
-    return net_value_head(c, d_vfeats, d_w1t, d_b1, d_w2, b2, d_value, B, nullptr, (cudaStream_t)stream);
+    return net_run_impl(c, layers, n_layers, d_vfeats, d_w1t, d_b1, d_w2, b2, d_value, B, nullptr, (cudaStream_t)stream);
 }
 
 // Same with the board count on the DEVICE (*d_n_boards, clamped to max_boards): the grids are sized for max_boards and
@@ -1355,9 +1389,5 @@ extern "C" int xq_net_run_counted(xq_ctx* c, const xq_gemm_desc* layers, int n_l
 {
     if (max_boards <= 0) return XQ_OK;
     if (!d_n_boards) return xq_fail(c, XQ_ERR_ARG, "xq_net_run_counted: d_n_boards is NULL");
-    for (int i = 0; i < n_layers; ++i) {
-        int rc = net_gemm(c, &layers[i], max_boards, d_n_boards, (cudaStream_t)stream);
-        if (rc) return rc;
-    }
-    return net_value_head(c, d_vfeats, d_w1t, d_b1, d_w2, b2, d_value, max_boards, d_n_boards, (cudaStream_t)stream);
+    return net_run_impl(c, layers, n_layers, d_vfeats, d_w1t, d_b1, d_w2, b2, d_value, max_boards, d_n_boards, (cudaStream_t)stream);
 }
