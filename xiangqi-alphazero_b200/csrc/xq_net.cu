@@ -228,7 +228,7 @@ struct ConvCfg {
     }
 };
 
-template <int NT, int KCH, bool HEADS, int TPS, bool WRES>
+template <int NT, int KCH, bool HEADS, int TPS, bool WRES, bool RES>
 __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(const GemmArgs p, const int S, const int NA)
 {
     using Cfg = ConvCfg<NT, KCH, HEADS, TPS, WRES>;
@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(const GemmArgs p,
             if (!HEADS) {
                 // Residual operand: res[k] always holds the values of this warp's NEXT tile; loaded before the
                 // first wait, then refilled slab by slab for the next work item, i.e. a whole pair ahead.
-                const bool has_res = p.residual != nullptr;
+                constexpr bool has_res = RES;              // compiled out for layers without a residual operand
                 if (n == 0) {
 #pragma unroll
                     for (int k = 0; k < NT / 8; ++k) {
@@ -441,11 +441,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(const GemmArgs p,
                             f[5] = __uint_as_float(v[g * 8 + 5]) + b1.y;
                             f[6] = __uint_as_float(v[g * 8 + 6]) + b1.z;
                             f[7] = __uint_as_float(v[g * 8 + 7]) + b1.w;
-                            const uint32_t rw[4] = {res[k].x, res[k].y, res[k].z, res[k].w};
+                            if (RES) {
+                                const uint32_t rw[4] = {res[k].x, res[k].y, res[k].z, res[k].w};
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                f[2 * e] += __uint_as_float(rw[e] << 16);
-                                f[2 * e + 1] += __uint_as_float(rw[e] & 0xffff0000u);
+                                for (int e = 0; e < 4; ++e) {
+                                    f[2 * e] += __uint_as_float(rw[e] << 16);
+                                    f[2 * e + 1] += __uint_as_float(rw[e] & 0xffff0000u);
+                                }
                             }
                             if (p.relu) {
 #pragma unroll
@@ -455,10 +457,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(const GemmArgs p,
                             *reinterpret_cast<uint4*>(p.out + off) =
                                 make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
                         }
-                        res[k] = make_uint4(0, 0, 0, 0);
-                        if (has_res && nreal)
-                            res[k] = __ldg(reinterpret_cast<const uint4*>(
-                                p.residual + ((size_t)(nn_tile * (NT / 8) + k) * p.out_rows + (size_t)(p.out_row0 + nrow)) * 16));
+                        if (RES) {
+                            res[k] = make_uint4(0, 0, 0, 0);
+                            if (nreal)
+                                res[k] = __ldg(reinterpret_cast<const uint4*>(
+                                    p.residual + ((size_t)(nn_tile * (NT / 8) + k) * p.out_rows + (size_t)(p.out_row0 + nrow)) * 16));
+                        }
                     }
                 };
                 // software pipeline over the NT/32 slabs: the TMEM load of slab i+1 is in flight while slab i is
@@ -911,8 +915,8 @@ static int ensure_tapmask(xq_ctx* c, cudaStream_t s)
     return XQ_OK;
 }
 
-template <int NT, int KCH, bool HEADS, int TPS, bool WRES>
-static int launch_conv(xq_ctx* c, GemmArgs& a, cudaStream_t s, int bit)
+template <int NT, int KCH, bool HEADS, int TPS, bool WRES, bool RES>
+static int launch_conv_r(xq_ctx* c, GemmArgs& a, cudaStream_t s, int bit)
 {
     using Cfg = ConvCfg<NT, KCH, HEADS, TPS, WRES>;
     const int kblocks = a.kchunks / KCH;
@@ -920,7 +924,7 @@ static int launch_conv(xq_ctx* c, GemmArgs& a, cudaStream_t s, int bit)
     Cfg::plan(kblocks, &S, &NA);
     if (kblocks > kMaxSeg || S < (WRES ? 1 : 2) || (WRES && a.n_tiles != 1))
         return xq_fail(c, XQ_ERR_ARG, "conv kernel: %d k-blocks, %d stages, %d n-tiles do not fit", kblocks, S, a.n_tiles);
-    auto kern = conv_kernel<NT, KCH, HEADS, TPS, WRES>;
+    auto kern = conv_kernel<NT, KCH, HEADS, TPS, WRES, RES>;
     if (int rc = ensure_smem_attr(c, kern, bit)) return rc;
     if (!HEADS)
         if (int rc = ensure_tapmask(c, s)) return rc;
@@ -930,6 +934,14 @@ static int launch_conv(xq_ctx* c, GemmArgs& a, cudaStream_t s, int bit)
     c->launches += 1;
     XQ_CUDA(c, cudaGetLastError());
     return XQ_OK;
+}
+
+// the residual operand is a compile-time property of the epilogue (a layer without one runs a third fewer instructions there)
+template <int NT, int KCH, bool HEADS, int TPS, bool WRES>
+static int launch_conv(xq_ctx* c, GemmArgs& a, cudaStream_t s, int bit)
+{
+    if (!HEADS && a.residual) return launch_conv_r<NT, KCH, HEADS, TPS, WRES, true>(c, a, s, bit + 16);
+    return launch_conv_r<NT, KCH, HEADS, TPS, WRES, false>(c, a, s, bit);
 }
 
 template <int KCH, int TPS>
