@@ -1355,6 +1355,8 @@ extern "C" int xq_net_run_counted(xq_ctx* c, const xq_gemm_desc* layers, int n_l
                                   const float* d_b1, const float* d_w2, float b2, float* d_value, const int* d_n_boards,
                                   int max_boards, void* stream);
 
+extern "C" int xq_net_side_stream_(xq_ctx* c, cudaStream_t* side, cudaEvent_t* ev_fork, cudaEvent_t* ev_join);
+
 static EvalPort port_of(const xq_net_plan* n)
 {
     EvalPort e;
@@ -1384,10 +1386,28 @@ static int sp_play_loop(xq_ctx* c, MctsState& M, SpState& P, const SpConfig& k, 
     const int kind = net0->logits_kind;
     const int nb = blocks_for(M.n_games), nt = kSelWarps * 32;
     const int steps = (k.num_simulations + K - 1) / K;
+    // The arena's two networks evaluate disjoint leaves with their own buffers: the second forward runs on a side stream
+    // next to the first (with a few evaluation games per GPU a forward is a chain of small kernels that leaves most SMs idle).
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    if (net1 && !c->net_fork)
+        if (int rc = xq_net_side_stream_(c, &side, &ev_fork, &ev_join)) return rc;
     auto run_nets = [&]() -> int {
+        if (net1 && side) {
+            XQ_CUDA(c, cudaEventRecord(ev_fork, s));
+            XQ_CUDA(c, cudaStreamWaitEvent(side, ev_fork, 0));
+            int rc1 = xq_net_run_counted(c, net1->layers, net1->n_layers, net1->vfeats, net1->w1t, net1->b1, net1->w2, net1->b2,
+                                         net1->value, M.n_eval + 1, net1->batch, (void*)side);
+            if (rc1) return rc1;
+            XQ_CUDA(c, cudaEventRecord(ev_join, side));
+        }
         int rc = xq_net_run_counted(c, net0->layers, net0->n_layers, net0->vfeats, net0->w1t, net0->b1, net0->w2, net0->b2, net0->value,
                                     M.n_eval + 0, net0->batch, (void*)s);
         if (rc || !net1) return rc;
+        if (side) {
+            XQ_CUDA(c, cudaStreamWaitEvent(s, ev_join, 0));
+            return XQ_OK;
+        }
         return xq_net_run_counted(c, net1->layers, net1->n_layers, net1->vfeats, net1->w1t, net1->b1, net1->w2, net1->b2, net1->value,
                                   M.n_eval + 1, net1->batch, (void*)s);
     };

@@ -1351,6 +1351,23 @@ extern "C" int xq_net_value_head(xq_ctx* c, const float* d_feats, const float* d
     return net_value_head(c, d_feats, d_w1t, d_b1, d_w2, b2, d_value, B, nullptr, (cudaStream_t)stream);
 }
 
+// side stream + fork / join events of the context (created on first use): the value-MLP fork below and the arena's second
+// network (xq_mcts.cu) run there
+extern "C" int xq_net_side_stream_(xq_ctx* c, cudaStream_t* side, cudaEvent_t* ev_fork, cudaEvent_t* ev_join)
+{
+    NetState* N = net_state(c);
+    if (!N->side) {
+        XQ_CUDA(c, cudaSetDevice(c->device));
+        XQ_CUDA(c, cudaStreamCreateWithFlags(&N->side, cudaStreamNonBlocking));
+        XQ_CUDA(c, cudaEventCreateWithFlags(&N->ev_fork, cudaEventDisableTiming));
+        XQ_CUDA(c, cudaEventCreateWithFlags(&N->ev_join, cudaEventDisableTiming));
+    }
+    *side = N->side;
+    *ev_fork = N->ev_fork;
+    *ev_join = N->ev_join;
+    return XQ_OK;
+}
+
 // All layers of one forward.  The value MLP depends on the heads conv only; with XQ_NET_FORK=1 it is forked onto a side
 // stream right after that layer and runs next to the policy FC (their shared memory and registers fit one SM together).
 // Measured on one box (profiles/r2_fwd_ab.txt): 1.002 ms per forward forked against 0.976 ms in sequence, so the default
@@ -1364,11 +1381,9 @@ static int net_run_impl(xq_ctx* c, const xq_gemm_desc* layers, int n_layers, con
         int rc = net_gemm(c, &layers[i], B, n_dev, s);
         if (rc) return rc;
         if (c->net_fork && layers[i].mode == 1 && i + 1 < n_layers && !forked) {
-            if (!N->side) {
-                XQ_CUDA(c, cudaStreamCreateWithFlags(&N->side, cudaStreamNonBlocking));
-                XQ_CUDA(c, cudaEventCreateWithFlags(&N->ev_fork, cudaEventDisableTiming));
-                XQ_CUDA(c, cudaEventCreateWithFlags(&N->ev_join, cudaEventDisableTiming));
-            }
+            cudaStream_t side_;
+            cudaEvent_t ef_, ej_;
+            if (int rc2 = xq_net_side_stream_(c, &side_, &ef_, &ej_)) return rc2;
             XQ_CUDA(c, cudaEventRecord(N->ev_fork, s));
             XQ_CUDA(c, cudaStreamWaitEvent(N->side, N->ev_fork, 0));
             rc = net_value_head(c, d_vfeats, d_w1t, d_b1, d_w2, b2, d_value, B, n_dev, N->side);
