@@ -371,6 +371,74 @@ int xq_bn_backward(xq_ctx* ctx, const float* d_x, const float* d_dy, const float
                    const float* d_save_invstd, float* d_dx, float* d_dweight, float* d_dbias, int N, int C, int HW,
                    void* stream);
 
+
+/* ---- f1: the training step's contractions on tcgen05 (csrc/xq_tnet.cu) ----------------------------------------
+ * Replaces the library calls (cuDNN convolutions, cuBLAS linears) inside AlphaZeroTrainer.train_network's
+ * forward/backward (train.py:397-423 over model.py:39-107) by hand-written kind::tf32 tcgen05 kernels, fp32 storage and
+ * fp32 accumulation.  TRAINING PLANE LAYOUT: a tensor is float32 X[C/4][rows][4 channels] (16 bytes per (chunk,row));
+ * board b, cell (r,c) lives at row row0 + b*110 + r*10 + c: every board row carries one zero pad column (c = 9) and every
+ * board one zero pad row (r = 10), so a 3x3 tap (dy,dx) is the same matrix shifted by dy*10+dx rows and the pad cells
+ * supply the zero padding of conv2d(padding=1) -- in the forward (fprop), the data gradient (dgrad) and the weight
+ * gradient (wgrad) alike, without masks.  Dense layers use the same layout with one row per board.
+ *
+ * xq_tgemm: out[row][n] = sum_tap sum_k A[row + s*shift(tap)][k] * Wtap[n][k], s = shift_sign.
+ * A: planes [kblocks*8 chunks][a_rows][4]; W: a weight image [img_nt][ntaps][img_kb][8 chunks][128 n][4 k] float32
+ * (tap = kh*3+kw for ntaps = 9), one 16 KB stage per (n_tile, tap, k_block).  fprop: the image of the layer's weights,
+ * s = +1.  dgrad: the image of the TRANSPOSED weights (n = input channel, k = output channel), s = -1.
+ * Output: planes (out, optional residual planes added) or row-major with bias (out_rm). */
+#define XQ_T_BOARD_ROWS 110
+#define XQ_T_ROW0 16
+typedef struct xq_tgemm_desc {
+    const void* a;
+    int64_t a_rows, a_row0;
+    const void* w;
+    int32_t kblocks;        /* contraction blocks of 32 (A chunks / 8) */
+    int32_t ntaps;          /* 9 (3x3) or 1 */
+    int32_t img_kb;         /* k-blocks of the weight image */
+    int32_t b_mn;           /* reserved, 0 */
+    int32_t shift_sign;     /* +1 / -1 */
+    int32_t m_pairs;        /* 256-row work items along M */
+    int32_t n_tiles;        /* 128-column output tiles */
+    int32_t out_chunks;     /* planes output: chunks (of 4 channels) to store, the rest of the last tile is dropped */
+    int64_t m_rows;         /* rows to store (rows >= m_rows of the last item are dropped) */
+    void* out;              /* planes [out_chunks][out_rows][4], logical row 0 at out_row0; or NULL */
+    int64_t out_rows, out_row0;
+    const void* residual;   /* planes like out, added in the epilogue; or NULL */
+    float* out_rm;          /* row-major [m_rows][out_stride] (+ bias[n]); or NULL */
+    int64_t out_stride;
+    const float* bias;
+    int32_t n_cols;         /* row-major output: columns to store (multiple of 4) */
+    int32_t pad_;
+} xq_tgemm_desc;
+int xq_tgemm(xq_ctx* ctx, const xq_tgemm_desc* desc, void* stream);
+
+/* xq_twgrad: D_t[m][n] = sum_row A[row][m] * B[row + off_t][n] over a range of rows (conv wgrad: A = dY, B = the layer
+ * input, taps = row shifts; dense wgrad: taps = column groups).  Both operands are MN-major for the tensor core, which for
+ * tf32 exists in one shared-memory form only (SWIZZLE_128B_BASE32B), so they are read from the G LAYOUT: float32
+ * G[C/32][rows][32 channels], the four 32-byte units of row r stored at position u ^ (r & 3); rows as in the plane layout.
+ * Work item = (m_tile of 128 A channels, slab of kr*stages_per_item rows, tap group g of taps_per_group taps).  B stage of
+ * group g: channel groups [b_group0 + g*b_group_step, + b_groups_stage) x rows [k0 + b_row_lo[g], + b_rows_stage)
+ * (b_row_lo and b_rows_stage multiples of 4); tap t of group g reads it at byte offset tap_off[g*4 + t] (with more than 4 groups every group uses entry 0 of both).  Output element
+ * (m, n) of tap t of item (mt, slab, g) goes to out[mt*mt_stride + slab*slab_stride + g*g_stride + t*tap_stride + m*ldo + n],
+ * stored when mt*128+m < m_limit and g*g_cols + t*t_cols + n < n_limit. */
+typedef struct xq_twgrad_desc {
+    const void* a;
+    const void* b;
+    int64_t a_rows, a_row0, b_rows, b_row0;
+    int32_t a_group0, b_group0;
+    int32_t nbg;              /* B channel groups per tap: N = 32*nbg (32 .. 128) */
+    int32_t kr;               /* rows per pipeline stage (multiple of 8) */
+    int32_t stages_per_item;
+    int32_t n_slabs, n_groups, n_mtiles, taps_per_group;
+    int32_t b_rows_stage, b_groups_stage, b_group_step;
+    int32_t b_row_lo[4];
+    int32_t tap_off[16];
+    float* out;
+    int64_t mt_stride, slab_stride, g_stride, tap_stride, ldo;
+    int32_t m_limit, n_limit, g_cols, t_cols;
+} xq_twgrad_desc;
+int xq_twgrad(xq_ctx* ctx, const xq_twgrad_desc* desc, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

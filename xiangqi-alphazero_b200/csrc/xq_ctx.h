@@ -27,6 +27,7 @@ struct xq_ctx {
     void* mcts = nullptr;
     void* net = nullptr;
     void* selfplay = nullptr;
+    void* tnet = nullptr;                 // xq_tnet.cu: the hand-written training step
     void* peer = nullptr;                 // xq_bn.cu: NVLink peer exchange buffers of the data-parallel BatchNorm
     int movegen_impl = 1;                 // XQ_MOVEGEN_IMPL=thread|warp: K1 kernel generation (1 = one thread per board, the default: 2x the
                                           // positions/s of the one-warp-per-board kernel, same bytes out)

@@ -579,6 +579,7 @@ extern "C" void xq_mcts_free_(xq_ctx*);
 extern "C" void xq_net_free_(xq_ctx*);
 extern "C" void xq_selfplay_free_(xq_ctx*);
 extern "C" void xq_peer_free_(xq_ctx*);
+extern "C" void xq_tnet_free_(xq_ctx*);
 
 extern "C" void xq_destroy(xq_ctx* c)
 {
@@ -588,6 +589,7 @@ extern "C" void xq_destroy(xq_ctx* c)
     xq_mcts_free_(c);
     xq_net_free_(c);
     xq_peer_free_(c);
+    xq_tnet_free_(c);
     for (int i = 0; i < 2; ++i) {
         if (c->pipe[i]) cudaStreamDestroy(c->pipe[i]);
         if (c->d_stage[i]) cudaFree(c->d_stage[i]);

@@ -108,6 +108,8 @@ def lib():
     _sig(L, "xq_peer_connect", i32, vp, vp)
     _sig(L, "xq_bn_forward", i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, f32, vp)
     _sig(L, "xq_bn_backward", i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp)
+    _sig(L, "xq_tgemm", i32, vp, vp, vp)
+    _sig(L, "xq_twgrad", i32, vp, vp, vp)
     _lib = L
     return L
 
@@ -122,7 +124,29 @@ EXPORTS = ["xq_create", "xq_destroy", "xq_last_error", "xq_version", "xq_launch_
            "xq_net_gemm", "xq_net_value_head", "xq_net_run", "xq_net_run_counted", "xq_selfplay_create", "xq_selfplay_reset",
            "xq_selfplay_play", "xq_selfplay_counters", "xq_selfplay_fetch", "xq_selfplay_slots",
            "xq_selfplay_device_buffers", "xq_arena_play", "xq_replay_append", "xq_train_batch", "xq_policy_value_loss",
-           "xq_grad_sumsq", "xq_adam_step", "xq_peer_create", "xq_peer_connect", "xq_bn_forward", "xq_bn_backward"]
+           "xq_grad_sumsq", "xq_adam_step", "xq_peer_create", "xq_peer_connect", "xq_bn_forward", "xq_bn_backward",
+           "xq_tgemm", "xq_twgrad"]
+
+
+class TGemmDesc(C.Structure):
+    """xq_tgemm_desc (include/xq_b200.h)"""
+    _fields_ = [("a", C.c_void_p), ("a_rows", C.c_int64), ("a_row0", C.c_int64), ("w", C.c_void_p),
+                ("kblocks", C.c_int32), ("ntaps", C.c_int32), ("img_kb", C.c_int32), ("b_mn", C.c_int32),
+                ("shift_sign", C.c_int32), ("m_pairs", C.c_int32), ("n_tiles", C.c_int32), ("out_chunks", C.c_int32),
+                ("m_rows", C.c_int64), ("out", C.c_void_p), ("out_rows", C.c_int64), ("out_row0", C.c_int64),
+                ("residual", C.c_void_p), ("out_rm", C.c_void_p), ("out_stride", C.c_int64), ("bias", C.c_void_p),
+                ("n_cols", C.c_int32), ("pad_", C.c_int32)]
+
+
+class TWgradDesc(C.Structure):
+    """xq_twgrad_desc (include/xq_b200.h)"""
+    _fields_ = [("a", C.c_void_p), ("b", C.c_void_p), ("a_rows", C.c_int64), ("a_row0", C.c_int64), ("b_rows", C.c_int64),
+                ("b_row0", C.c_int64), ("a_group0", C.c_int32), ("b_group0", C.c_int32), ("nbg", C.c_int32), ("kr", C.c_int32),
+                ("stages_per_item", C.c_int32), ("n_slabs", C.c_int32), ("n_groups", C.c_int32), ("n_mtiles", C.c_int32),
+                ("taps_per_group", C.c_int32), ("b_rows_stage", C.c_int32), ("b_groups_stage", C.c_int32),
+                ("b_group_step", C.c_int32), ("b_row_lo", C.c_int32 * 4), ("tap_off", C.c_int32 * 16), ("out", C.c_void_p),
+                ("mt_stride", C.c_int64), ("slab_stride", C.c_int64), ("g_stride", C.c_int64), ("tap_stride", C.c_int64),
+                ("ldo", C.c_int64), ("m_limit", C.c_int32), ("n_limit", C.c_int32), ("g_cols", C.c_int32), ("t_cols", C.c_int32)]
 
 
 def _np_ptr(a: np.ndarray):
