@@ -52,6 +52,9 @@ def run(args, rank, world, local_rank, dist):
     cfg = T.TrainingConfig()
     cfg.num_channels, cfg.num_res_blocks, cfg.batch_size = CHANNELS, BLOCKS, BATCH
     cfg.checkpoint_dir = "/tmp/xq_bench_train"
+    cfg.hand_step = os.environ.get("XQ_TRAIN_HAND", "1") != "0"       # A/B switch: 0 = the torch / cuDNN / cuBLAS step of round 1
+    if os.environ.get("XQ_TRAIN_DP_MODE"):
+        cfg.dp_mode = os.environ["XQ_TRAIN_DP_MODE"]
     torch.manual_seed(20261018)
     tr = T.AlphaZeroTrainer(cfg)
     eng = tr.eng
@@ -64,11 +67,15 @@ def run(args, rank, world, local_rank, dist):
     def step():
         gidx = torch.randint(0, n, (BATCH,), generator=gen)
         mine = tr._shard(gidx)
-        states, target, zz = tr.replay_buffer.batch(mine)           # H2D: the index list; everything else is resident
-        logits, values = tr.current_model(states)
-        pl, vl = policy_value_loss(eng, logits, values, target, zz, global_batch=BATCH)
-        tr.optimizer.zero_grad()
-        (pl + vl).backward()
+        hb = tr._hand.buffers(int(mine.numel())) if tr._hand is not None else None
+        states, target, zz = tr.replay_buffer.batch(mine, out=(hb.states, hb.act, hb.prob, hb.n, hb.z) if hb else None)   # H2D: the index list
+        if tr._hand is not None:                                    # the hand-written step (tnet.HandStep, csrc/xq_tnet.cu)
+            pl, vl = tr._hand.step(states, target[0], target[1], target[2], zz, 1.0 / BATCH)
+        else:
+            logits, values = tr.current_model(states)
+            pl, vl = policy_value_loss(eng, logits, values, target, zz, global_batch=BATCH)
+            tr.optimizer.zero_grad()
+            (pl + vl).backward()
         tr.optimizer.step()
         return pl, vl
 

@@ -408,7 +408,11 @@ typedef struct xq_tgemm_desc {
     int64_t out_stride;
     const float* bias;
     int32_t n_cols;         /* row-major output: columns to store (multiple of 4) */
-    int32_t pad_;
+    int32_t k_splits;       /* 0/1: none.  > 1: the contraction blocks are dealt to k_splits work items per output tile (fills the
+                               SMs when M x N alone gives few tiles).  Planes output: split s writes its partial sums to
+                               out + s*out_split_stride floats, the reader adds them (xq_tn_unflatten); row-major output: at most 2,
+                               added into the zeroed matrix (a two-term sum does not depend on the order) */
+    int64_t out_split_stride;
 } xq_tgemm_desc;
 int xq_tgemm(xq_ctx* ctx, const xq_tgemm_desc* desc, void* stream);
 
@@ -438,6 +442,99 @@ typedef struct xq_twgrad_desc {
     int32_t m_limit, n_limit, g_cols, t_cols;
 } xq_twgrad_desc;
 int xq_twgrad(xq_ctx* ctx, const xq_twgrad_desc* desc, void* stream);
+
+/* ---- the layers between the contractions (csrc/xq_tnet_ops.cuh) --------------------------------------------------------
+ * Everything else train.py:397-423 runs through torch modules (model.py:14-107): layout writers, training-mode BatchNorm
+ * (+ residual + ReLU) forward / backward, weight images, the slab reduction of the weight gradients, nn.Flatten around the
+ * policy FC and the value head's two small dense layers.  All reductions run in a fixed order (bit-reproducible).
+ * Tensors: planes float32 P[chunk][rows][4], G layout float32 G[group][rows][32] (see above); `rows` is the row count of
+ * the tensor, board b cell (r, c) at row XQ_T_ROW0 + b*110 + r*10 + c; dense tensors have one row per board at
+ * XQ_T_ROW0 + b. */
+
+/* x[n_boards][channels][10][9] -> planes chunks [0, 2*pairs) (channels >= `channels` zero) and, if g != NULL, the G layout. */
+int xq_tn_input(xq_ctx* ctx, const float* x, int32_t n_boards, int32_t channels, int32_t pairs, float* planes, float* g,
+                int64_t rows, void* stream);
+/* w[co][ci][taps] -> weight image [.][taps][img_kb][8][128][4] of xq_tgemm at (n0 + n, k0 + k): transposed = 0: n = co,
+ * k = ci (fprop); 1: n = ci, k = co (dgrad).  Positions without a weight are left untouched (allocate the image zeroed). */
+int xq_tn_wimage(xq_ctx* ctx, const float* w, int32_t co, int32_t ci, int32_t taps, float* img, int32_t img_kb, int32_t n0,
+                 int32_t k0, int32_t transposed, void* stream);
+/* The same for many small weight tensors in one launch per 32 items (the 3x3 and 1x1 convolutions of a step). */
+typedef struct xq_tn_wimage_item {
+    const float* w;
+    float* img;
+    int32_t co, ci, taps, img_kb, n0, k0, transposed, pad_;
+} xq_tn_wimage_item;
+int xq_tn_wimage_batch(xq_ctx* ctx, const xq_tn_wimage_item* items, int32_t n_items, void* stream);
+
+/* BatchNorm2d in training mode over chunks [chunk0, chunk0 + ceil(n_channels/8)*2) of y (nn.BatchNorm2d as used by
+ * model.py:14-36, 49-83): batch statistics over the n_boards*90 real cells, running statistics updated with `momentum`
+ * (unbiased variance), out = [relu](gamma*(y - mean)*invstd + beta [+ res]), pad cells zero.  partial: scratch,
+ * 256 doubles per chunk.  save[2][n_channels] receives mean and invstd for the backward pass. */
+typedef struct xq_tn_bn_desc {
+    const float* y;
+    const float* res;
+    float* out;
+    float* out_g;
+    int64_t rows;
+    int32_t n_boards, chunk0, n_channels, relu;
+    double* partial;
+    const float* gamma;
+    const float* beta;
+    float* running_mean;
+    float* running_var;
+    float* save;
+    float eps, momentum;
+} xq_tn_bn_desc;
+int xq_tn_bn_forward(xq_ctx* ctx, const xq_tn_bn_desc* desc, void* stream);
+
+/* Backward of the above: dz = dout * (act > 0) (relu) ; dgamma = sum dz*xhat, dbeta = sum dz (assigned, not accumulated);
+ * dy = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat)) as planes and (dy_g != NULL) G layout, pad cells zero;
+ * dskip (optional) receives dz, the gradient of the residual input. */
+typedef struct xq_tn_bn_bwd_desc {
+    const float* dout;
+    const float* act;
+    const float* y;
+    int64_t rows;
+    int32_t n_boards, chunk0, n_channels, relu;
+    const float* save;
+    double* partial;
+    const float* gamma;
+    float* dgamma;
+    float* dbeta;
+    float* dy;
+    float* dy_g;
+    float* dskip;
+} xq_tn_bn_bwd_desc;
+int xq_tn_bn_backward(xq_ctx* ctx, const xq_tn_bn_bwd_desc* desc, void* stream);
+
+/* Sum of the xq_twgrad slabs into a weight gradient in the parameter layout: ws[slab][tap][128][ldn] ->
+ * dw[(co0 + co)*ci_total + ci0 + ci][tap], (co, ci) = (m, n - n_src0), or (ci, co) = (m, n - n_src0) when transposed. */
+int xq_tn_wgrad_reduce(xq_ctx* ctx, const float* ws, int32_t slabs, int64_t slab_stride, int32_t taps, int32_t ldn, int32_t m_cnt,
+                       int32_t n_cnt, int32_t n_src0, int32_t transposed, float* dw, int32_t ci_total, int32_t co0, int32_t ci0,
+                       void* stream);
+
+/* nn.Flatten of the first `channels` channels: feature k = ch*90 + r*9 + c -> dense planes [k/4][drows][4] (+ G layout). */
+int xq_tn_flatten(xq_ctx* ctx, const float* act, int64_t rows, int32_t n_boards, int32_t channels, float* dense, float* dense_g,
+                  int64_t drows, void* stream);
+/* ... and back: dense planes (the sum of n_partials tensors part_stride floats apart, added in order) -> chunks
+ * [0, channels/4) of board planes (real cells). */
+int xq_tn_unflatten(xq_ctx* ctx, const float* dense, int64_t drows, int32_t n_boards, int32_t channels, float* planes, int64_t rows,
+                    int32_t n_partials, int64_t part_stride, void* stream);
+/* Row-major m[n_rows][stride] (n_cols used, multiple of 4) -> dense planes and / or G layout, one row per board. */
+int xq_tn_rows_layouts(xq_ctx* ctx, const float* m, int64_t stride, int32_t n_rows, int32_t n_cols, float* dense, float* dense_g,
+                       int64_t drows, void* stream);
+/* out[n] = sum over rows of m[row][n] (bias gradient of a dense layer). */
+int xq_tn_colsum(xq_ctx* ctx, const float* m, int64_t stride, int32_t n_rows, int32_t n_cols, float* out, void* stream);
+
+/* Value head after its BatchNorm (model.py:72-83): the 4 channels of plane chunk `chunk` of `act`, flattened (k = ch*90 + cell),
+ * h = relu(W1 f + b1) [n_boards][128], v = tanh(w2 h + b2) [n_boards]. */
+int xq_tn_value_forward(xq_ctx* ctx, const float* act, int64_t rows, int32_t chunk, int32_t n_boards, const float* w1, const float* b1,
+                        const float* w2, const float* b2, float* h, float* v, void* stream);
+/* Backward: g_value = dLoss/dv.  Writes the four parameter gradients and the gradient of the 4 channels into chunk
+ * `chunk` of dact (real cells); dh [n_boards][128] and dpre [n_boards] are scratch. */
+int xq_tn_value_backward(xq_ctx* ctx, const float* act, int64_t rows, int32_t chunk, int32_t n_boards, const float* w1, const float* w2,
+                         const float* h, const float* v, const float* g_value, float* dh, float* dpre, float* dact, float* dw1,
+                         float* db1, float* dw2, float* db2, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,6 +1,7 @@
 """Generate tests/golden/train_golden.npz by RUNNING THE REFERENCE's training step (build container only).
 
     python tests/golden/make_train_golden.py
+    python tests/golden/make_train_golden.py 128 2 train_golden_128.npz
 
 Imports /root/reference/training/train.py unmodified (with its game.py / model.py / parallel_selfplay.py and the
 Cython engine from oracle/_ref), builds a replay buffer of (sample, mirrored sample) pairs with the reference's own
@@ -28,6 +29,9 @@ from game import XiangqiGame                  # noqa: E402
 assert reftrain.__file__.startswith(REF)
 
 CHANNELS, BLOCKS, RECORDS, BATCH, EPOCHS, SEED = 16, 1, 150, 64, 2, 20261018
+OUT = "train_golden.npz"
+if len(sys.argv) > 1:        # python make_train_golden.py 128 2 train_golden_128.npz: the fixture of the hand-written step (128-wide tower)
+    CHANNELS, BLOCKS, OUT = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3]
 
 
 def checksums(model):
@@ -108,7 +112,7 @@ def main():
         mir_idx[i, :len(nz)] = nz
         mir_val[i, :len(nz)] = pairs[2 * i + 1][1][nz]
     np.savez_compressed(
-        os.path.join(HERE, "train_golden.npz"),
+        os.path.join(HERE, OUT),
         board=np.array(boards, np.int8), side=np.array(sides, np.int8), n=np.array(ns, np.uint8), actions=np.array(acts),
         probs=np.array(probs), z=np.array(zs, np.float32), init=init, after1=after1, after2=after2, buffers=bn,
         stats1=np.array([stats1['policy_loss'], stats1['value_loss'], stats1['total_loss'], stats1['learning_rate']]),

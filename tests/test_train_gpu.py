@@ -170,20 +170,26 @@ def _checksums(model):
     return np.array([[float(p.detach().double().sum()), float(p.detach().double().abs().sum())] for p in model.parameters()])
 
 
-def test_train_network_matches_the_reference_run(eng, tmp_path):
+@pytest.mark.parametrize("fixture,hand", [("train_golden.npz", True), ("train_golden_128.npz", True), ("train_golden_128.npz", False)])
+def test_train_network_matches_the_reference_run(eng, tmp_path, fixture, hand):
     """Same samples, same seeds as tests/golden/make_train_golden.py (the reference's AlphaZeroTrainer.train_network on
-    the CPU, fp32): same shuffles, losses within 2e-3 relative, parameter checksums within 2e-3 of the reference's change."""
+    the CPU, fp32): same shuffles, losses within 2e-3 relative, parameter checksums within 2e-3 of the reference's change.
+    train_golden.npz: 16-channel tower (the step runs through the torch modules + hand-written BatchNorm / loss / Adam);
+    train_golden_128.npz: 128 x 2 tower, the step on the hand-written tf32 kernels (tnet.HandStep) and, for comparison,
+    through torch."""
     import torch
     import train as T
-    g = dict(np.load(os.path.join(GOLDEN, "train_golden.npz")))
+    g = dict(np.load(os.path.join(GOLDEN, fixture)))
     ch, blocks, records, batch, epochs, seed = (int(x) for x in g["meta"])
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     cfg = T.TrainingConfig()
     cfg.num_channels, cfg.num_res_blocks, cfg.batch_size, cfg.num_epochs, cfg.min_buffer_size = ch, blocks, batch, epochs, 10
     cfg.checkpoint_dir = str(tmp_path)
+    cfg.hand_step = hand
     torch.manual_seed(seed)
     tr = T.AlphaZeroTrainer(cfg)
+    assert (tr._hand is not None) == (hand and ch % 128 == 0)
     assert np.allclose(_checksums(tr.current_model), g["init"], rtol=1e-6, atol=1e-6), "initial weights differ from the reference's"
     rec = np.zeros((records, 896), np.uint8)
     rec[:, :90] = g["board"].view(np.uint8)
@@ -198,15 +204,29 @@ def test_train_network_matches_the_reference_run(eng, tmp_path):
     c1 = _checksums(tr.current_model)
     s2 = tr.train_network()
     c2 = _checksums(tr.current_model)
+    # Tolerances.  16-channel fixture: the reference-run tolerances of round 1 (2e-3 on the losses, 0.1 on the checksums).
+    # 128 x 2 fixture: twenty Adam steps at lr 2e-3 take the loss from 9 to 5 and amplify rounding differences -- the fp32
+    # torch/cuDNN path itself lands 1e-3 (first call) and 1e-2 (second call) away from the reference's CPU run, and
+    # profiles/r2_train_trajectory.txt (same weights, samples and minibatches, 40 steps) shows the hand-written tf32 step
+    # tracking torch fp32 as closely as torch's own TF32 mode does (mean deviation: policy 4.5e-3 vs 5.3e-3, value 2.7e-2 vs
+    # 3.3e-2; the small value loss is the volatile one).  Bars for BOTH paths there: policy and total loss 1e-2, value loss
+    # 8e-2, checksums 0.5 of the reference's movement.
+    loss_tol, sum_tol = (np.array([2e-3, 2e-3, 2e-3]), 0.1) if ch < 128 else (np.array([1e-2, 8e-2, 1e-2]), 0.5)
+    devs, ratios = [], []
     for s, want in ((s1, g["stats1"]), (s2, g["stats2"])):
         got = np.array([s["policy_loss"], s["value_loss"], s["total_loss"], s["learning_rate"]])
-        assert np.allclose(got, want, rtol=2e-3), (got, want)
+        devs.append(np.abs(got / want - 1)[:3])
+        assert got[3] == want[3]
+        print(f"{fixture} hand={tr._hand is not None}: losses {got[:3]} reference {want[:3]} rel {devs[-1].max():.2e}")
     # parameters: per-tensor float64 checksums (sum, abs-sum) land where the reference's landed, measured against how far the
     # reference moved them (CPU vs cuDNN summation order is amplified by Adam's m / sqrt(v) on small gradients)
     for c, want in ((c1, g["after1"]), (c2, g["after2"])):
         moved = np.abs(want - g["init"]).max(axis=1)
         ratio = np.abs(c - want).max(axis=1) / (moved + 1e-2 * np.abs(want).max(axis=1) + 1e-6)
-        assert ratio.max() < 0.1, ratio
+        ratios.append(ratio.max())
+        print(f"  parameter checksums: worst deviation / reference movement {ratio.max():.3f}")
+    assert all((d < loss_tol).all() for d in devs), devs
+    assert max(ratios) < sum_tol, ratios
     # checkpoint dictionary: the reference's keys (train.py:539-551), loadable again
     tr.save_checkpoint(3, is_best=True)
     ck = torch.load(os.path.join(str(tmp_path), "checkpoint_iter3.pt"), map_location="cpu")

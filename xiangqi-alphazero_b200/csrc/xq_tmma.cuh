@@ -123,6 +123,9 @@ struct TgArgs {
     float* out_rm;
     long long out_stride;
     const float* bias;
+    int k_splits;                            // contraction split: item (pair, n_tile, ks) covers k-blocks [ks*kb_per, +kb_per)
+    int kb_per;
+    long long out_split_bytes;               // planes output of split ks goes to out + ks*out_split_bytes (partial sums, added by the reader)
 };
 
 // out[row][n] = sum_tap sum_k A[row + sign*shift(tap)][k] * image[n][k] (+ residual / + bias): fprop with the layer's weight
@@ -142,7 +145,7 @@ __global__ void __launch_bounds__(kTgThreads, 1) tg_kernel(const TgArgs p)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 4);
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-    const int total = p.m_pairs * p.n_tiles;
+    const int total = p.m_pairs * p.n_tiles * p.k_splits;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kTNSeg; ++i) {
@@ -173,9 +176,11 @@ __global__ void __launch_bounds__(kTgThreads, 1) tg_kernel(const TgArgs p)
         int sg = 0, s = 0;
         uint32_t sgph = 0, ph = 0;
         for (int work = blockIdx.x; work < total; work += gridDim.x) {
-            const int pair = work / p.n_tiles, n_tile = work - pair * p.n_tiles;
+            const int ks = work % p.k_splits, wr = work / p.k_splits;
+            const int pair = wr / p.n_tiles, n_tile = wr - pair * p.n_tiles;
             const long long m0 = (long long)pair * kTPair;
-            for (int kb = 0; kb < p.kblocks; ++kb) {
+            const int kb0 = ks * p.kb_per, kb1 = min(p.kblocks, kb0 + p.kb_per);
+            for (int kb = kb0; kb < kb1; ++kb) {
                 if (lane == 0) {
                     mbar_wait(&a_empty[sg], sgph ^ 1u);
                     mbar_expect_tx(&a_full[sg], (uint32_t)kTSeg);
@@ -207,7 +212,9 @@ __global__ void __launch_bounds__(kTgThreads, 1) tg_kernel(const TgArgs p)
             mbar_wait(&t_empty[acc * 2 + t], tph ^ 1u);
             tc_fence_after();
             const uint32_t d_addr = tmem_base + (uint32_t)(acc * 256 + t * 128);
-            for (int kb = 0; kb < p.kblocks; ++kb) {
+            const int ks = work % p.k_splits;
+            const int kb0 = ks * p.kb_per, kb1 = min(p.kblocks, kb0 + p.kb_per);
+            for (int kb = kb0; kb < kb1; ++kb) {
                 mbar_wait(&a_full[sg], sgph);
                 const uint32_t a_seg = smem_u32(sA + sg * kTSeg);
                 for (int tap = 0; tap < p.ntaps; ++tap) {
@@ -220,7 +227,7 @@ __global__ void __launch_bounds__(kTgThreads, 1) tg_kernel(const TgArgs p)
                     for (int j = 0; j < 4; ++j) {
                         const uint64_t adesc = smem_desc(a_addr + (uint32_t)(2 * j * kTAPlane), (uint32_t)kTAPlane, 128u);
                         const uint64_t bdesc = smem_desc(b_addr + (uint32_t)(2 * j * 2048), 2048u, 128u);
-                        if (leader) umma_tf32(d_addr, adesc, bdesc, idesc, (kb | tap | j) != 0 ? 1u : 0u);
+                        if (leader) umma_tf32(d_addr, adesc, bdesc, idesc, ((kb - kb0) | tap | j) != 0 ? 1u : 0u);
                     }
                     if (leader) umma_commit(&w_empty[s]);
                     if (++s == kTNStage) { s = 0; ph ^= 1u; }
@@ -239,10 +246,12 @@ __global__ void __launch_bounds__(kTgThreads, 1) tg_kernel(const TgArgs p)
         const int row = q * 32 + lane;
         int n = 0;
         for (int work = blockIdx.x; work < total; work += gridDim.x, ++n) {
-            const int pair = work / p.n_tiles, n_tile = work - pair * p.n_tiles;
+            const int ks = work % p.k_splits, wr = work / p.k_splits;
+            const int pair = wr / p.n_tiles, n_tile = wr - pair * p.n_tiles;
             const int acc = n & 1;
             const uint32_t tph = (uint32_t)(n >> 1) & 1u;
             const long long mrow = (long long)pair * kTPair + t * 128 + row;
+            uint8_t* const out_ks = p.out + (size_t)ks * p.out_split_bytes;
             const bool real = mrow < p.m_rows;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256 + t * 128);
             mbar_wait(&t_full[acc * 2 + t], tph);
@@ -261,26 +270,33 @@ __global__ void __launch_bounds__(kTgThreads, 1) tg_kernel(const TgArgs p)
                         if (col < p.n_cols) {
                             float4 o = make_float4(__uint_as_float(v[g * 4]), __uint_as_float(v[g * 4 + 1]), __uint_as_float(v[g * 4 + 2]),
                                                    __uint_as_float(v[g * 4 + 3]));
-                            if (p.bias) {
+                            if (p.bias && ks == 0) {
                                 const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col));
                                 o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
                             }
-                            *reinterpret_cast<float4*>(dst + col) = o;
+                            // two splits add into a zeroed matrix: 0 + a + b = 0 + b + a bit for bit, the order does not matter
+                            if (p.k_splits > 1) atomicAdd(reinterpret_cast<float4*>(dst + col), o);
+                            else *reinterpret_cast<float4*>(dst + col) = o;
                         }
                     }
                 } else {
+                    // the 8 residual loads of a slice are issued together, ahead of the stores (one round trip, not eight)
+                    float4 r[8];
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) {
+                        const int chunk = n_tile * 32 + sl * 8 + g;
+                        const size_t off = ((size_t)chunk * p.out_rows + (size_t)(p.out_row0 + mrow)) * 16;
+                        r[g] = (p.residual && chunk < p.out_chunks) ? __ldg(reinterpret_cast<const float4*>(p.residual + off))
+                                                                    : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    }
 #pragma unroll
                     for (int g = 0; g < 8; ++g) {
                         const int chunk = n_tile * 32 + sl * 8 + g;
                         if (chunk < p.out_chunks) {
                             const size_t off = ((size_t)chunk * p.out_rows + (size_t)(p.out_row0 + mrow)) * 16;
-                            float4 o = make_float4(__uint_as_float(v[g * 4]), __uint_as_float(v[g * 4 + 1]), __uint_as_float(v[g * 4 + 2]),
-                                                   __uint_as_float(v[g * 4 + 3]));
-                            if (p.residual) {
-                                const float4 r = __ldg(reinterpret_cast<const float4*>(p.residual + off));
-                                o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-                            }
-                            *reinterpret_cast<float4*>(p.out + off) = o;
+                            *reinterpret_cast<float4*>(out_ks + off) =
+                                make_float4(__uint_as_float(v[g * 4]) + r[g].x, __uint_as_float(v[g * 4 + 1]) + r[g].y,
+                                            __uint_as_float(v[g * 4 + 2]) + r[g].z, __uint_as_float(v[g * 4 + 3]) + r[g].w);
                         }
                     }
                 }

@@ -165,17 +165,21 @@ class DeviceReplayBuffer:
         return self.ring[idx], self.z[idx]
 
     # -- minibatch ---------------------------------------------------------------------------------
-    def batch(self, logical_index: torch.Tensor):
+    def batch(self, logical_index: torch.Tensor, out=None):
         """Logical indices (0 <= L < len(self)) -> planes float32 [B,15,10,9], (actions int16 [B,128], probs float32
-        [B,128], n int32 [B]), z float32 [B]  (xq_train_batch)."""
+        [B,128], n int32 [B]), z float32 [B]  (xq_train_batch).  out = (planes, act, prob, n, z): write into these tensors
+        (the static inputs of a captured training step) instead of new ones."""
         idx = logical_index.to(self.e.dev, torch.int64).contiguous()
         B = int(idx.numel())
         dev = self.e.dev
-        planes = torch.empty((B, 15, 10, 9), dtype=torch.float32, device=dev)
-        act = torch.empty((B, MAX_MOVES), dtype=torch.int16, device=dev)
-        prob = torch.empty((B, MAX_MOVES), dtype=torch.float32, device=dev)
-        n = torch.empty((B,), dtype=torch.int32, device=dev)
-        z = torch.empty((B,), dtype=torch.float32, device=dev)
+        if out is not None:
+            planes, act, prob, n, z = out
+        else:
+            planes = torch.empty((B, 15, 10, 9), dtype=torch.float32, device=dev)
+            act = torch.empty((B, MAX_MOVES), dtype=torch.int16, device=dev)
+            prob = torch.empty((B, MAX_MOVES), dtype=torch.float32, device=dev)
+            n = torch.empty((B,), dtype=torch.int32, device=dev)
+            z = torch.empty((B,), dtype=torch.float32, device=dev)
         e = self.e
         e._check(e.L.xq_train_batch(e.h, self.ring.data_ptr(), self.z.data_ptr(), self.capacity, self.start, idx.data_ptr(), B,
                                     planes.data_ptr(), act.data_ptr(), prob.data_ptr(), n.data_ptr(), z.data_ptr(), e._stream()))

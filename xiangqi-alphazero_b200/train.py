@@ -98,6 +98,9 @@ class TrainingConfig:
         # so sharding it 8 ways cannot shorten it and adds 30 small BatchNorm-statistics all-reduces per step.
         self.dp_mode = "shard"
         self.hand_batchnorm = True      # training-mode BatchNorm on csrc/xq_bn.cu (statistics over NVLink peer memory when sharded)
+        # forward + loss + backward of the step on the hand-written tf32 tcgen05 kernels (csrc/xq_tnet.cu, tnet.HandStep): used
+        # when a rank runs whole minibatches (one GPU or dp_mode "replicate") with a tower width that is a multiple of 128
+        self.hand_step = True
 
 
 class SelfPlayDataset(torch.utils.data.Dataset):
@@ -481,6 +484,14 @@ class AlphaZeroTrainer:
         self.optimizer = FlatAdam(self.eng, self.current_model, lr=config.learning_rate, weight_decay=config.weight_decay,
                                   max_grad_norm=1.0, dist=self.dist if getattr(config, "dp_mode", "shard") == "shard" else None)
         self.scheduler = optim.lr_scheduler.MultiStepLR(self.optimizer, milestones=config.lr_milestones, gamma=config.lr_gamma)
+        # f1: forward + loss + backward of the step on the hand-written kernels (tnet.HandStep, csrc/xq_tnet.cu) whenever every
+        # rank runs whole minibatches (one GPU, or dp_mode "replicate") and the tower is a multiple of 128 channels wide;
+        # otherwise (sharded minibatch, 64-channel quick preset) the torch modules run the step as before.
+        self._hand = None
+        whole = self.world == 1 or getattr(config, "dp_mode", "shard") == "replicate"
+        if getattr(config, "hand_step", True) and whole and config.num_channels % 128 == 0:
+            from tnet import HandStep
+            self._hand = HandStep(self.eng, self.current_model)
         self.replay_buffer = DeviceReplayBuffer(self.eng, config.max_buffer_size)
 
         self.iteration = 0
@@ -635,11 +646,16 @@ class AlphaZeroTrainer:
                     mine = self._shard(gidx)
                     replicated = self.world > 1 and gidx.numel() < self.world
                     denom = gidx.numel() * (self.world if replicated else 1)
-                states, target, z = self.replay_buffer.batch(mine)
-                logits, values = self.current_model(states)
-                p_loss, v_loss = policy_value_loss(self.eng, logits, values, target, z, global_batch=denom)
-                self.optimizer.zero_grad()
-                (p_loss + v_loss).backward()
+                hb = self._hand.buffers(int(mine.numel())) if self._hand is not None else None
+                states, target, z = self.replay_buffer.batch(mine, out=(hb.states, hb.act, hb.prob, hb.n, hb.z) if hb else None)
+                if self._hand is not None:
+                    # every layer, the loss and every gradient on the kernels of csrc/xq_tnet.cu (gradients are assigned)
+                    p_loss, v_loss = self._hand.step(states, target[0], target[1], target[2], z, 1.0 / float(denom))
+                else:
+                    logits, values = self.current_model(states)
+                    p_loss, v_loss = policy_value_loss(self.eng, logits, values, target, z, global_batch=denom)
+                    self.optimizer.zero_grad()
+                    (p_loss + v_loss).backward()
                 self.optimizer.step()                                       # all-reduce + clip + Adam
                 ep += torch.stack([p_loss.detach(), v_loss.detach()]).double()
                 ep_batches += 1
@@ -650,6 +666,8 @@ class AlphaZeroTrainer:
             e = (ep / max(ep_batches, 1)).tolist()
             logger.info("  epoch %d: policy_loss=%.4f, value_loss=%.4f", epoch + 1, e[0], e[1])
         self.scheduler.step()
+        if self._hand is not None:
+            self._hand.sync_counters()
         p, v = (sums / max(num_batches, 1)).tolist()
         stats = {'policy_loss': p, 'value_loss': v, 'total_loss': p + v, 'learning_rate': self.optimizer.param_groups[0]['lr']}
         logger.info("training done: policy_loss=%.4f, value_loss=%.4f, lr=%.6f", p, v, stats['learning_rate'])

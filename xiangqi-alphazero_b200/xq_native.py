@@ -110,6 +110,18 @@ def lib():
     _sig(L, "xq_bn_backward", i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp)
     _sig(L, "xq_tgemm", i32, vp, vp, vp)
     _sig(L, "xq_twgrad", i32, vp, vp, vp)
+    _sig(L, "xq_tn_input", i32, vp, vp, i32, i32, i32, vp, vp, i64, vp)
+    _sig(L, "xq_tn_wimage", i32, vp, vp, i32, i32, i32, vp, i32, i32, i32, i32, vp)
+    _sig(L, "xq_tn_wimage_batch", i32, vp, vp, i32, vp)
+    _sig(L, "xq_tn_bn_forward", i32, vp, vp, vp)
+    _sig(L, "xq_tn_bn_backward", i32, vp, vp, vp)
+    _sig(L, "xq_tn_wgrad_reduce", i32, vp, vp, i32, i64, i32, i32, i32, i32, i32, i32, vp, i32, i32, i32, vp)
+    _sig(L, "xq_tn_flatten", i32, vp, vp, i64, i32, i32, vp, vp, i64, vp)
+    _sig(L, "xq_tn_unflatten", i32, vp, vp, i64, i32, i32, vp, i64, i32, i64, vp)
+    _sig(L, "xq_tn_rows_layouts", i32, vp, vp, i64, i32, i32, vp, vp, i64, vp)
+    _sig(L, "xq_tn_colsum", i32, vp, vp, i64, i32, i32, vp, vp)
+    _sig(L, "xq_tn_value_forward", i32, vp, vp, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp)
+    _sig(L, "xq_tn_value_backward", i32, vp, vp, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp)
     _lib = L
     return L
 
@@ -125,7 +137,8 @@ EXPORTS = ["xq_create", "xq_destroy", "xq_last_error", "xq_version", "xq_launch_
            "xq_selfplay_play", "xq_selfplay_counters", "xq_selfplay_fetch", "xq_selfplay_slots",
            "xq_selfplay_device_buffers", "xq_arena_play", "xq_replay_append", "xq_train_batch", "xq_policy_value_loss",
            "xq_grad_sumsq", "xq_adam_step", "xq_peer_create", "xq_peer_connect", "xq_bn_forward", "xq_bn_backward",
-           "xq_tgemm", "xq_twgrad"]
+           "xq_tgemm", "xq_twgrad", "xq_tn_input", "xq_tn_wimage", "xq_tn_wimage_batch", "xq_tn_bn_forward", "xq_tn_bn_backward", "xq_tn_wgrad_reduce",
+           "xq_tn_flatten", "xq_tn_unflatten", "xq_tn_rows_layouts", "xq_tn_colsum", "xq_tn_value_forward", "xq_tn_value_backward"]
 
 
 class TGemmDesc(C.Structure):
@@ -135,7 +148,29 @@ class TGemmDesc(C.Structure):
                 ("shift_sign", C.c_int32), ("m_pairs", C.c_int32), ("n_tiles", C.c_int32), ("out_chunks", C.c_int32),
                 ("m_rows", C.c_int64), ("out", C.c_void_p), ("out_rows", C.c_int64), ("out_row0", C.c_int64),
                 ("residual", C.c_void_p), ("out_rm", C.c_void_p), ("out_stride", C.c_int64), ("bias", C.c_void_p),
-                ("n_cols", C.c_int32), ("pad_", C.c_int32)]
+                ("n_cols", C.c_int32), ("k_splits", C.c_int32), ("out_split_stride", C.c_int64)]
+
+
+class TnWimageItem(C.Structure):
+    """xq_tn_wimage_item (include/xq_b200.h)"""
+    _fields_ = [("w", C.c_void_p), ("img", C.c_void_p), ("co", C.c_int32), ("ci", C.c_int32), ("taps", C.c_int32),
+                ("img_kb", C.c_int32), ("n0", C.c_int32), ("k0", C.c_int32), ("transposed", C.c_int32), ("pad_", C.c_int32)]
+
+
+class TnBnDesc(C.Structure):
+    """xq_tn_bn_desc (include/xq_b200.h)"""
+    _fields_ = [("y", C.c_void_p), ("res", C.c_void_p), ("out", C.c_void_p), ("out_g", C.c_void_p), ("rows", C.c_int64),
+                ("n_boards", C.c_int32), ("chunk0", C.c_int32), ("n_channels", C.c_int32), ("relu", C.c_int32),
+                ("partial", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("running_mean", C.c_void_p),
+                ("running_var", C.c_void_p), ("save", C.c_void_p), ("eps", C.c_float), ("momentum", C.c_float)]
+
+
+class TnBnBwdDesc(C.Structure):
+    """xq_tn_bn_bwd_desc (include/xq_b200.h)"""
+    _fields_ = [("dout", C.c_void_p), ("act", C.c_void_p), ("y", C.c_void_p), ("rows", C.c_int64),
+                ("n_boards", C.c_int32), ("chunk0", C.c_int32), ("n_channels", C.c_int32), ("relu", C.c_int32),
+                ("save", C.c_void_p), ("partial", C.c_void_p), ("gamma", C.c_void_p), ("dgamma", C.c_void_p),
+                ("dbeta", C.c_void_p), ("dy", C.c_void_p), ("dy_g", C.c_void_p), ("dskip", C.c_void_p)]
 
 
 class TWgradDesc(C.Structure):
