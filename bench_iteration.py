@@ -28,7 +28,8 @@ def run(args, rank, world, local_rank, dist):
     cfg.num_games_per_iter = GAMES_PER_GPU * world
     cfg.eval_games = EVAL_PER_GPU * world
     cfg.selfplay_slots = GAMES_PER_GPU
-    cfg.dp_mode = os.environ.get("XQ_BENCH_DP_MODE", "shard")                       # shard (NCCL data parallel) | replicate
+    cfg.dp_mode = os.environ.get("XQ_BENCH_DP_MODE", "auto")                        # auto | shard (NCCL data parallel) | replicate
+    cfg.hand_step = os.environ.get("XQ_TRAIN_HAND", "1") != "0"
     cfg.selfplay_leaves_per_game = int(os.environ.get("XQ_BENCH_SP_LEAVES", 1))     # > 1: opt-in virtual-loss search
     cfg.eval_leaves_per_game = int(os.environ.get("XQ_BENCH_EVAL_LEAVES", 1))
     cfg.checkpoint_dir = "/tmp/xq_bench_iter"
@@ -101,9 +102,9 @@ def run(args, rank, world, local_rank, dist):
                                f"XiangqiNet(128,6), 200 sims/move, 5 epochs x batch 256 over a 50 000-sample ring, eval 100 sims",
                    "games_per_iteration": cfg.num_games_per_iter, "eval_games": cfg.eval_games,
                    "parallelism": (f"games and evaluation pairs sharded x{world}; training dp{world} (global-minibatch BatchNorm exchanged over NVLink peer memory, gradient all-reduce split at the "
-                                   f"policy FC weight and overlapped with backward)" if cfg.dp_mode == "shard" else
+                                   f"policy FC weight and overlapped with backward)" if tr.dp_mode == "shard" else
                                    f"games and evaluation pairs sharded x{world}; training replicated on every rank (full minibatch, no collective in the step)"),
-                   "dp_mode": cfg.dp_mode, "selfplay_leaves_per_game": cfg.selfplay_leaves_per_game,
+                   "dp_mode": tr.dp_mode, "train_step": "hand-written kernels (tnet.HandStep)" if tr._hand is not None else "torch modules", "selfplay_leaves_per_game": cfg.selfplay_leaves_per_game,
                    "eval_leaves_per_game": cfg.eval_leaves_per_game},
         "phases": {"self_play_s": mean("self_play_s"), "train_s": mean("train_s"), "eval_s": mean("eval_s"),
                    "games": mean("games"), "avg_plies": mean("avg_plies"), "new_samples": mean("samples"),

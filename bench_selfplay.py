@@ -214,6 +214,15 @@ def run(args, rank, world, local_rank, dist):
         except Exception as ex:
             c3 = {"error": str(ex)[:300]}
 
+    # f1: the training step of configs[4] on the hand-written kernels next to the torch/cuDNN step
+    f1 = None
+    if world == 1 and (CHANNELS, BLOCKS) == (128, 6) and not os.environ.get("XQ_BENCH_NO_TRAIN"):
+        try:
+            import bench_train
+            f1 = bench_train.train_block(local_rank)
+        except Exception as ex:
+            f1 = {"error": str(ex)[:300]}
+
     if world > 1:
         t = torch.tensor([ms, e2e_s, fwd_ms, conv_ms, api["seconds"] if api else 0.0], device=eng.dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -268,7 +277,7 @@ def run(args, rank, world, local_rank, dist):
                              "power-capped clocks included); the isolated forward is timed back to back for 20 launches"},
         "cpu_baseline": cpu,
         "secondary": mv,
-        "extra": {"configs3_256x20": c3},
+        "extra": {"configs3_256x20": c3, "f1_train_step": f1},
         "e2e": ({"value": api["value"], "unit": "sims/s", "api": "parallel_self_play",
                  "h2d_bytes_per_step": api["h2d_bytes"], "d2h_bytes_per_step": api["d2h_bytes"],
                  "step": "one parallel_self_play(model, config) call: " + api["config"], "seconds": api["seconds"],

@@ -1,11 +1,14 @@
 """bench.py --workload train: the training step of BASELINE configs[4] (train.py:376-447) -- batch 256, Adam lr 2e-3
 wd 1e-4, clip 1.0, XiangqiNet(128,6) -- on a device-resident replay ring of synthetic self-play records.
 
-Step = one optimiser step on one GLOBAL minibatch of 256 samples (split across the ranks under torchrun: strong
-scaling, the reference's batch size is kept; global-minibatch BatchNorm (DPBatchNorm2d) + gradient all-reduce overlapped with backward).
-Metric = training samples per second.  The dominant HAND-WRITTEN kernels of the step are HBM-bound streaming
-kernels (clip+Adam over the flat buffers: 28 B per parameter; loss+gradient: 64.8 KB per sample); the roofline line
-reports the Adam kernel, the conv forward/backward itself is torch/cuDNN (library code, not claimed).
+Step = one optimiser step on one GLOBAL minibatch of 256 samples.  One GPU (and dp_mode "replicate"): every layer, the loss
+and every gradient run on the hand-written kernels of csrc/xq_tnet.cu (tnet.HandStep: tf32 tcgen05 contractions, plane-layout
+BatchNorm / ReLU / residual kernels, replayed from a CUDA graph) followed by the clip + Adam kernels; XQ_TRAIN_HAND=0 runs the
+round-1 step through torch / cuDNN / cuBLAS for comparison.  Under torchrun with dp_mode "shard" the minibatch is split
+across the ranks (strong scaling, torch modules, peer-memory BatchNorm, gradient all-reduce overlapped with backward).
+Metric = training samples per second.  Roofline line: the dominant kernel of the hand-written step, the tf32 implicit-GEMM
+convolution tg_kernel (tensor bound; peak = half the measured bf16 rate, the tf32:bf16 ratio of the tensor core); the
+HBM-bound Adam kernel is reported next to it.
 """
 import os
 import sys
@@ -125,8 +128,27 @@ def run(args, rank, world, local_rank, dist):
         policy_value_loss(eng, lg, vv, target, zz)
         torch.cuda.synchronize()
         ks["loss"].append(eng.last_kernel_ms())
-    eng.set_timing(False)
     k_ms = {k: float(np.median(v)) for k, v in ks.items()}
+    conv = None
+    if tr._hand is not None:
+        # the dominant kernel of the hand-written step alone: one 3x3 tower convolution (fprop) at batch 256, 20 launches
+        import tnet
+        hs = tr._hand
+        hb = hs.buffers(BATCH)
+        kb, cc = CHANNELS // 32, CHANNELS // 4
+        eng.set_timing(False)
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for rep in range(2):
+            t0.record()
+            for _ in range(20):
+                tnet.tgemm(eng, hb.Ap[0], hb.R, kb, hs.img_f[1], 9, kb, False, hb.pairs, CHANNELS // 128, hb.n_rows, out=hb.Y[1], out_rows=hb.R,
+                           out_chunks=cc)
+            t1.record()
+            torch.cuda.synchronize()
+        conv_ms = t0.elapsed_time(t1) / 20
+        conv_flops = 2.0 * 90 * 9 * CHANNELS * CHANNELS * BATCH          # algorithmic: real cells only (the 110-row layout executes 22 % more)
+        conv = {"ms_per_launch": conv_ms, "algorithmic_flops_per_launch": conv_flops, "achieved_tflops": conv_flops / (conv_ms * 1e-3) / 1e12}
+    eng.set_timing(False)
 
     # e2e: the public call a user makes -- AlphaZeroTrainer.train_network() over one epoch of a 4096-sample buffer;
     # per step the host sends the minibatch index list, at the end it reads the loss statistics back
@@ -161,21 +183,36 @@ def run(args, rank, world, local_rank, dist):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cpu = cpu_train_rate(os.cpu_count() or 1)
+    hand = tr._hand is not None
+    tf32_peak = peaks["bf16_tflops"] / 2.0                             # tf32 runs at half the bf16 rate on the tensor core (4096 vs 8192 ops/clk/SM)
+    roof_adam = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                 "kernel": "adam_kernel (clip + weight decay + Adam over flat buffers)", "algorithmic_bytes_per_parameter": 28}
     line = {
         "metric": "train_samples_per_sec", "value": BATCH / (ms_per_step * 1e-3), "unit": "samples/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic (device-generated random-playout records)",
-        "config": {"workload": f"train: configs[4] training step, global batch {BATCH}, XiangqiNet({CHANNELS},{BLOCKS}) fp32 (TF32 convs as "
-                               f"torch defaults), Adam lr 2e-3 wd 1e-4, clip 1.0, replay ring of {n} logical samples in HBM",
+        "config": {"workload": f"train: configs[4] training step, global batch {BATCH}, XiangqiNet({CHANNELS},{BLOCKS}), "
+                               + ("hand-written step (tf32 tcgen05 contractions, fp32 storage and accumulation, CUDA graph)" if hand else
+                                  "torch modules (fp32 cuDNN / cuBLAS), hand-written BatchNorm / loss / Adam")
+                               + f", Adam lr 2e-3 wd 1e-4, clip 1.0, replay ring of {n} logical samples in HBM",
                    "parameters": nparam, "l2": "flat optimiser buffers 4 x %.0f MB > 126 MB L2" % (nparam * 4 / 1e6),
-                   "parallelism": f"dp{world}: minibatch split across ranks, global-minibatch BatchNorm statistics, gradient all-reduce overlapped with backward"},
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                     "traffic": None, "peak_source": peak_kind, "kernel": "adam_kernel (clip + weight decay + Adam over flat buffers)",
-                     "algorithmic_bytes_per_parameter": 28, "kernel_ms": k_ms,
-                     "loss_kernel_gbs": BATCH * 8100 * 8 / (k_ms["loss"] * 1e-3) / 1e9,
-                     "sumsq_kernel_gbs": nparam * 4 / (k_ms["sumsq"] * 1e-3) / 1e9,
-                     "note": "the conv forward/backward of the step is torch/cuDNN (library); hand-written: batch builder, loss+gradient, "
-                             "gradient norm, clip+Adam"},
+                   "parallelism": (f"replicas x{world}: every rank runs the whole minibatch, no collective in the step" if hand else
+                                   f"dp{world}: minibatch split across ranks, global-minibatch BatchNorm statistics, gradient all-reduce overlapped with backward")},
+        "roofline": ({"bound": "tensor", "achieved": conv["achieved_tflops"], "peak": tf32_peak, "unit": "TFLOP/s",
+                      "frac": conv["achieved_tflops"] / tf32_peak, "traffic": 15.05e6,
+                      "peak_source": peak_kind + " bf16 burst / 2 (tf32 rate of the tensor core)",
+                      "kernel": "tg_kernel: 3x3 tower convolution fprop / dgrad, tf32 tcgen05 implicit GEMM (24 launches per step)",
+                      "dominant_kernel": conv, "second_kernel": roof_adam, "kernel_ms": k_ms,
+                      "note": "110 work items of 256 rows on 148 SMs, one per CTA: the tensor pipe runs at the full tf32 rate while MMAs "
+                              "are in flight (ncu: 18.4 k tensor cycles = the algorithmic count) and the rest of the launch is prologue, "
+                              "first loads and the epilogue of the single item (profiles/r2_train_ncu.md); traffic = dram read + write of "
+                              "one launch from ncu --set full"}
+                     if hand else
+                     dict(roof_adam, traffic=None, peak_source=peak_kind, kernel_ms=k_ms,
+                          loss_kernel_gbs=BATCH * 8100 * 8 / (k_ms["loss"] * 1e-3) / 1e9,
+                          sumsq_kernel_gbs=nparam * 4 / (k_ms["sumsq"] * 1e-3) / 1e9,
+                          note="the conv forward/backward of this arm is torch/cuDNN (library); hand-written: batch builder, loss+gradient, "
+                               "BatchNorm, gradient norm, clip+Adam")),
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_samples / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": BATCH * 8, "d2h_bytes_per_step": 16,
                 "policy_loss": st.get("policy_loss")},
@@ -183,6 +220,65 @@ def run(args, rank, world, local_rank, dist):
         "clocks": clocks,
     }
     bench.emit(line)
+
+
+def train_block(local_rank=0, steps=30, torch_steps=10):
+    """The f1 line of the default bench: one optimiser step of configs[4]'s training (batch 256, XiangqiNet(128,6)) on the
+    hand-written kernels (tnet.HandStep + clip/Adam), and the same step through torch / cuDNN / cuBLAS on the same box."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "xiangqi-alphazero_b200"))
+    import train as T
+    from replay import policy_value_loss
+    out = {}
+    for name, hand, k in (("hand_written", True, steps), ("torch_cudnn", False, torch_steps)):
+        cfg = T.TrainingConfig()
+        cfg.num_channels, cfg.num_res_blocks, cfg.batch_size = CHANNELS, BLOCKS, BATCH
+        cfg.checkpoint_dir = "/tmp/xq_bench_train"
+        cfg.hand_step = hand
+        torch.manual_seed(20261018)
+        tr = T.AlphaZeroTrainer(cfg)
+        eng = tr.eng
+        rec, z = synthetic_records(eng, 4096, 20261018)
+        tr.replay_buffer.append_raw(rec, z)
+        n = len(tr.replay_buffer)
+        tr.current_model.train()
+        gen = torch.Generator().manual_seed(1)
+
+        def step():
+            idx = torch.randint(0, n, (BATCH,), generator=gen)
+            hb = tr._hand.buffers(BATCH) if tr._hand is not None else None
+            states, target, zz = tr.replay_buffer.batch(idx, out=(hb.states, hb.act, hb.prob, hb.n, hb.z) if hb else None)
+            if tr._hand is not None:
+                pl, vl = tr._hand.step(states, target[0], target[1], target[2], zz, 1.0 / BATCH)
+            else:
+                logits, values = tr.current_model(states)
+                pl, vl = policy_value_loss(eng, logits, values, target, zz, global_batch=BATCH)
+                tr.optimizer.zero_grad()
+                (pl + vl).backward()
+            tr.optimizer.step()
+            return pl
+
+        for _ in range(4):
+            step()
+        torch.cuda.synchronize()
+        l0 = eng.launch_count(reset=True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            pl = step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / k
+        out[name] = {"ms_per_step": ms, "samples_per_s": BATCH / (ms * 1e-3), "steps": k, "policy_loss_last": float(pl),
+                     "own_kernel_launches_per_step": eng.launch_count() / k}
+        del tr
+        torch.cuda.empty_cache()
+    out["speedup"] = out["torch_cudnn"]["ms_per_step"] / out["hand_written"]["ms_per_step"]
+    out["workload"] = (f"configs[4] training step: global batch {BATCH}, XiangqiNet({CHANNELS},{BLOCKS}), Adam lr 2e-3 wd 1e-4, clip 1.0; "
+                       "hand_written = every layer, the loss and every gradient on csrc/xq_tnet.cu (tf32 tcgen05 contractions, fp32 "
+                       "elsewhere) replayed from a CUDA graph + clip/Adam kernels; torch_cudnn = the same step through the torch modules "
+                       "(fp32 cuDNN / cuBLAS, hand-written BatchNorm / loss / Adam) as in round 1")
+    return out
 
 
 def cpu_train_rate(threads, steps=2):

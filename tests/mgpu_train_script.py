@@ -71,6 +71,33 @@ def main():
     assert torch.allclose(fr, fr0, rtol=1e-3, atol=1e-5)           # replicas agree up to the reduction order of library kernels
     del tr_r
 
+    # dp_mode "auto" on a 128-wide tower = "replicate" on the hand-written step (tnet.HandStep): the 128 x 2 reference run, and the
+    # replicas stay BIT-identical (every reduction of those kernels runs in a fixed order)
+    g2 = dict(np.load(os.path.join(ROOT, "tests", "golden", "train_golden_128.npz")))
+    ch2, blocks2, records2, batch2, epochs2, seed2 = (int(x) for x in g2["meta"])
+    cfg_h = T.TrainingConfig()
+    cfg_h.num_channels, cfg_h.num_res_blocks, cfg_h.batch_size, cfg_h.num_epochs, cfg_h.min_buffer_size = ch2, blocks2, batch2, epochs2, 10
+    cfg_h.checkpoint_dir = "/tmp/xq_mgpu_train"
+    torch.manual_seed(seed2 if dist.get_rank() == 0 else 999)
+    tr_h = T.AlphaZeroTrainer(cfg_h)
+    assert tr_h._hand is not None and tr_h.dp_mode == "replicate"
+    rec2 = np.zeros((records2, 896), np.uint8)
+    rec2[:, :90] = g2["board"].view(np.uint8)
+    rec2[:, 90] = g2["side"].view(np.uint8)
+    rec2[:, 91] = g2["n"]
+    rec2[:, 128:384] = g2["actions"].view(np.uint8).reshape(records2, 256)
+    rec2[:, 384:896] = g2["probs"].view(np.uint8).reshape(records2, 512)
+    tr_h.replay_buffer.append_raw(torch.from_numpy(rec2), torch.from_numpy(g2["z"]))
+    torch.manual_seed(seed2 + 1 if dist.get_rank() == 0 else 5)
+    s_h = tr_h.train_network()
+    got_h = np.array([s_h["policy_loss"], s_h["value_loss"], s_h["total_loss"]])
+    assert (np.abs(got_h / g2["stats1"][:3] - 1) < np.array([1e-2, 8e-2, 1e-2])).all(), (got_h, g2["stats1"])
+    fh = tr_h.optimizer.flat_p.clone()
+    fh0 = fh.clone()
+    dist.broadcast(fh0, 0)
+    assert torch.equal(fh, fh0), float((fh - fh0).abs().max())
+    del tr_h
+
     # sharded self-play -> all ranks append the same records; evaluation pairs sharded; weights broadcast
     cfg2 = T.TrainingConfig()
     cfg2.num_channels, cfg2.num_res_blocks, cfg2.num_simulations, cfg2.num_games_per_iter = 128, 1, 6, 9

@@ -337,8 +337,8 @@ def test_value_head_dense_layers_match_torch(eng):
     assert torch.allclose(T.from_planes(dact, B, 36)[:, 32:36].reshape(B, 360), f.grad, atol=1e-6, rtol=1e-4)
 
 
-@pytest.mark.parametrize("B,blocks", [(6, 1), (64, 2), (256, 6)])
-def test_hand_step_matches_torch_autograd(eng, B, blocks):
+@pytest.mark.parametrize("B,blocks,width", [(6, 1, 128), (64, 2, 128), (256, 6, 128), (10, 1, 256)])
+def test_hand_step_matches_torch_autograd(eng, B, blocks, width):
     """HandStep (forward + loss + backward of XiangqiNet on the kernels) against the torch module on the same weights and
     minibatch (train.py:397-413): logits / value / losses and every parameter gradient."""
     import torch
@@ -349,8 +349,8 @@ def test_hand_step_matches_torch_autograd(eng, B, blocks):
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.manual_seed(100 + B)
     dev = eng.dev
-    net = M.XiangqiNet(128, blocks).to(dev).train()
-    ref = M.XiangqiNet(128, blocks).to(dev).train()
+    net = M.XiangqiNet(width, blocks).to(dev).train()
+    ref = M.XiangqiNet(width, blocks).to(dev).train()
     ref.load_state_dict(net.state_dict())
     for p in net.parameters():
         p.grad = torch.full_like(p, 123.0)                  # a step must ASSIGN every gradient
@@ -371,7 +371,7 @@ def test_hand_step_matches_torch_autograd(eng, B, blocks):
     # tf32 forward errors (~1e-3) flip the few ReLU units whose pre-activation is that close to zero; a flipped fraction f of
     # the terms behind a random-sign sum moves it by ~sqrt(f) of its size, several per cent after 13 layers, which says
     # nothing about the backward kernels.  With the masks pinned the comparison is tight; the unpinned module bounds the rest.
-    C = 128
+    C = width
     masks = [(T.from_planes(b.Ap[i], B, C) > 0).float() for i in range(hs.L)]
     ah = T.from_planes(b.Ah, B, 36)
     mask_p, mask_v, mask_h = (ah[:, :32] > 0).float(), (ah[:, 32:36] > 0).float(), (b.h > 0).float()
@@ -409,8 +409,19 @@ def test_hand_step_matches_torch_autograd(eng, B, blocks):
             assert torch.allclose(p, q, atol=1e-4, rtol=1e-3), name
     hs.sync_counters()
     assert int(net.input_conv[1].num_batches_tracked) == 1
+    # the same step again (now replayed from the CUDA graph captured after the first one): bit-identical losses and gradients
+    first = [p.grad.clone() for p in net.parameters()]
+    l_first = (float(pl), float(vl))
+    for p in net.parameters():
+        p.grad.fill_(-7.0)
+    pl2, vl2 = hs.step(states, act, prob, n, z, 1.0 / B)
+    torch.cuda.synchronize()
+    assert hs.buffers(B).graph is not None
+    assert (float(pl2), float(vl2)) == l_first
+    for (name, p), q in zip(net.named_parameters(), first):
+        assert torch.equal(p.grad, q), name
     # the unpinned torch module: same outputs, gradients within the ReLU-flip noise
-    free = M.XiangqiNet(128, blocks).to(dev).train()
+    free = M.XiangqiNet(width, blocks).to(dev).train()
     free.load_state_dict(ref.state_dict())
     logits, values = free(states)
     fpl, fvl = replay.policy_value_loss(eng, logits, values, (act, prob, n), z)

@@ -348,6 +348,7 @@ __global__ void __launch_bounds__(kTwgThreads, 1) twg_kernel(const TwgArgs p)
     uint64_t* t_full = empty + kTwgMaxStages;
     uint64_t* t_empty = t_full + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 1);
+    float* scratch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 128);    // [4 epilogue warps][32][33]: transpose tiles
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int total = p.n_mtiles * p.n_slabs * p.n_groups;
@@ -428,15 +429,18 @@ __global__ void __launch_bounds__(kTwgThreads, 1) twg_kernel(const TwgArgs p)
         }
     } else {
         const int q = warp & 3;                                  // warps 2,3,4,5 -> TMEM lane quarters 2,3,0,1
-        const int m = q * 32 + lane;
+        float* scr = scratch + (warp - 2) * (32 * 33);
         int n = 0;
         for (int work = blockIdx.x; work < total; work += gridDim.x, ++n) {
             const int g = work % p.n_groups, rest = work / p.n_groups;
             const int slab = rest % p.n_slabs, mt = rest / p.n_slabs;
             mbar_wait(t_full, (uint32_t)(n & 1));
             tc_fence_after();
-            const bool m_ok = mt * 128 + m < p.m_limit;
-            float* base = p.out + (size_t)mt * p.mt_stride + (size_t)slab * p.slab_stride + (size_t)g * p.g_stride + (size_t)m * p.ldo;
+            // A thread holds 32 consecutive columns of ONE output row; stored as they are, a warp's store instruction would
+            // touch 32 rows x 16 B.  Each 32 x 32 tile goes through a padded shared-memory tile instead and leaves as 4 rows x
+            // 128 contiguous bytes per instruction (ncu: the scattered form kept the tensor pipe at 32 % of the active cycles).
+            float* base = p.out + (size_t)mt * p.mt_stride + (size_t)slab * p.slab_stride + (size_t)g * p.g_stride;
+            const int r_sub = lane >> 3, c4 = (lane & 7) * 4;
             for (int t = 0; t < p.taps_per_group; ++t) {
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * tcol);
                 float* dst = base + (size_t)t * p.tap_stride;
@@ -445,13 +449,18 @@ __global__ void __launch_bounds__(kTwgThreads, 1) twg_kernel(const TwgArgs p)
                     uint32_t v[32];
                     tmem_ld32(taddr + (uint32_t)c0, v);
                     tmem_ld_wait();
-                    if (m_ok) {
 #pragma unroll
-                        for (int e = 0; e < 8; ++e)
-                            if (col0 + c0 + e * 4 < p.n_limit)
-                                *reinterpret_cast<float4*>(dst + c0 + e * 4) = make_float4(__uint_as_float(v[e * 4]), __uint_as_float(v[e * 4 + 1]),
-                                                                                           __uint_as_float(v[e * 4 + 2]), __uint_as_float(v[e * 4 + 3]));
+                    for (int j = 0; j < 32; ++j) scr[lane * 33 + j] = __uint_as_float(v[j]);
+                    __syncwarp();
+                    const bool n_ok = col0 + c0 + c4 < p.n_limit;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int r = i * 4 + r_sub, m = q * 32 + r;
+                        const float* sp = scr + r * 33 + c4;
+                        const float4 o = make_float4(sp[0], sp[1], sp[2], sp[3]);
+                        if (n_ok && mt * 128 + m < p.m_limit) *reinterpret_cast<float4*>(dst + (size_t)m * p.ldo + c0 + c4) = o;
                     }
+                    __syncwarp();
                 }
             }
             tc_fence_before();

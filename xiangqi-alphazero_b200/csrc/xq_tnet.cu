@@ -123,11 +123,12 @@ int launch_twg(xq_ctx* c, const xq_twgrad_desc* d, cudaStream_t s)
     a.t_cols = d->t_cols;
     a.a_stage_bytes = 4 * d->kr * 128;
     a.stage_bytes = a.a_stage_bytes + d->b_groups_stage * d->b_rows_stage * 128;      // multiples of 512: kr % 8 == 0, b_rows_stage % 4 == 0
-    int ns = (224 * 1024) / a.stage_bytes;
+    constexpr int kTail = 128 + 4 * 32 * 33 * 4;                  // barriers + the epilogue's transpose tiles
+    int ns = (227 * 1024 - 512 - kTail) / a.stage_bytes;
     if (ns > kTwgMaxStages) ns = kTwgMaxStages;
     if (ns < 2) return xq_fail(c, XQ_ERR_ARG, "xq_twgrad: stage of %d bytes leaves fewer than 2 pipeline stages", a.stage_bytes);
     a.n_stages = ns;
-    int smem_bytes = ns * a.stage_bytes + 512 + 256;
+    int smem_bytes = ns * a.stage_bytes + 512 + kTail;
     if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;         // > half an SM: one CTA per SM (it owns all of TMEM)
     if (int rc = ensure_attr(c, twg_kernel, 2, 227 * 1024)) return rc;
     const int total = d->n_mtiles * d->n_slabs * d->n_groups;

@@ -19,11 +19,11 @@ constexpr int kTnRow0 = XQ_T_ROW0;
 constexpr int kTnBoard = XQ_T_BOARD_ROWS;        // 110
 constexpr int kTnSplit = 16;                     // row splits of the statistics kernels (partial sums per chunk)
 
-__device__ __forceinline__ bool tn_real(long long rel, int n_boards)
+__device__ __forceinline__ bool tn_real(int rel, int n_boards)          // rel = row - row0, 0 <= rel (32-bit: a step holds < 2^31 rows)
 {
-    const long long b = rel / kTnBoard;
-    const int r = (int)(rel - b * kTnBoard);
-    return rel >= 0 && b < n_boards && r < 100 && (r % 10) != 9;
+    const unsigned b = (unsigned)rel / (unsigned)kTnBoard;
+    const unsigned r = (unsigned)rel - b * (unsigned)kTnBoard;
+    return b < (unsigned)n_boards && r < 100u && (r % 10u) != 9u;
 }
 // float offset of the 8 floats of chunk pair `cp` (channels 8*cp .. 8*cp+7) of row `row` in a G tensor of `rows` rows
 __device__ __forceinline__ size_t tn_g_off(int cp, long long row, long long rows)
@@ -171,11 +171,19 @@ __global__ void __launch_bounds__(256) tn_bn_stat_kernel(const float* __restrict
     const long long n_rows = (long long)n_boards * kTnBoard;
     const float* src = y + ((size_t)(chunk0 + chunk) * rows + kTnRow0) * 4;
     float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
-    for (long long rel = (long long)sp * 256 + threadIdx.x; rel < n_rows; rel += (long long)gridDim.y * 256) {
-        if (!tn_real(rel, n_boards)) continue;
-        const float4 v = ld4(src + rel * 4);
-        s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
-        q[0] += v.x * v.x; q[1] += v.y * v.y; q[2] += v.z * v.z; q[3] += v.w * v.w;
+    const int stride = gridDim.y * 256;
+    for (int rel0 = sp * 256 + threadIdx.x; rel0 < (int)n_rows; rel0 += 4 * stride) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {                        // four independent loads in flight
+            const int rel = rel0 + u * stride;
+            v[u] = (rel < (int)n_rows && tn_real(rel, n_boards)) ? ld4(src + (size_t)rel * 4) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            s[0] += v[u].x; s[1] += v[u].y; s[2] += v[u].z; s[3] += v[u].w;
+            q[0] += v[u].x * v[u].x; q[1] += v[u].y * v[u].y; q[2] += v[u].z * v[u].z; q[3] += v[u].w * v[u].w;
+        }
     }
     double d[8] = {s[0], s[1], s[2], s[3], q[0], q[1], q[2], q[3]};
     const double t = tn_block_sum8(d, sm);
@@ -235,7 +243,7 @@ __global__ void __launch_bounds__(256) tn_bn_apply_kernel(const TnBnArgs p)
     __syncthreads();
     const long long n_rows = (long long)p.n_boards * kTnBoard;
     const int c0 = p.chunk0 + 2 * cp;
-    for (long long rel = (long long)blockIdx.y * 256 + threadIdx.x; rel < n_rows; rel += (long long)gridDim.y * 256) {
+    for (int rel = blockIdx.y * 256 + threadIdx.x; rel < (int)n_rows; rel += gridDim.y * 256) {
         const long long row = kTnRow0 + rel;
         float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         if (tn_real(rel, p.n_boards)) {
@@ -292,15 +300,28 @@ __global__ void __launch_bounds__(256) tn_bn_bwd_stat_kernel(const TnBnBwdArgs p
         inv[j] = c < p.n_channels ? p.save[p.n_channels + c] : 0.0f;
     }
     float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
-    for (long long rel = (long long)sp * 256 + threadIdx.x; rel < n_rows; rel += (long long)gridDim.y * 256) {
-        if (!tn_real(rel, p.n_boards)) continue;
-        const float4 g4 = ld4(p.dout + base + rel * 4), a4 = ld4(p.act + base + rel * 4), y4 = ld4(p.y + base + rel * 4);
-        const float g[4] = {g4.x, g4.y, g4.z, g4.w}, a[4] = {a4.x, a4.y, a4.z, a4.w}, yy[4] = {y4.x, y4.y, y4.z, y4.w};
+    const int stride = gridDim.y * 256;
+    const float4 zero4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    for (int rel0 = sp * 256 + threadIdx.x; rel0 < (int)n_rows; rel0 += 2 * stride) {
+        float4 g4[2], a4[2], y4[2];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float dz = (!p.relu || a[j] > 0.0f) ? g[j] : 0.0f;
-            s[j] += dz;
-            q[j] += dz * ((yy[j] - mean[j]) * inv[j]);
+        for (int u = 0; u < 2; ++u) {                        // six independent loads in flight
+            const int rel = rel0 + u * stride;
+            const bool ok = rel < (int)n_rows && tn_real(rel, p.n_boards);
+            g4[u] = ok ? ld4(p.dout + base + (size_t)rel * 4) : zero4;    // a pad cell contributes dz = 0
+            a4[u] = ok ? ld4(p.act + base + (size_t)rel * 4) : zero4;
+            y4[u] = ok ? ld4(p.y + base + (size_t)rel * 4) : zero4;
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const float g[4] = {g4[u].x, g4[u].y, g4[u].z, g4[u].w}, a[4] = {a4[u].x, a4[u].y, a4[u].z, a4[u].w},
+                        yy[4] = {y4[u].x, y4[u].y, y4[u].z, y4[u].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float dz = (!p.relu || a[j] > 0.0f) ? g[j] : 0.0f;
+                s[j] += dz;
+                q[j] += dz * ((yy[j] - mean[j]) * inv[j]);
+            }
         }
     }
     double d[8] = {s[0], s[1], s[2], s[3], q[0], q[1], q[2], q[3]};
@@ -335,7 +356,7 @@ __global__ void __launch_bounds__(256) tn_bn_bwd_apply_kernel(const TnBnBwdArgs 
     __syncthreads();
     const long long n_rows = (long long)p.n_boards * kTnBoard;
     const int c0 = p.chunk0 + 2 * cp;
-    for (long long rel = (long long)blockIdx.y * 256 + threadIdx.x; rel < n_rows; rel += (long long)gridDim.y * 256) {
+    for (int rel = blockIdx.y * 256 + threadIdx.x; rel < (int)n_rows; rel += gridDim.y * 256) {
         const long long row = kTnRow0 + rel;
         const size_t o0 = ((size_t)c0 * p.rows + row) * 4, o1 = ((size_t)(c0 + 1) * p.rows + row) * 4;
         float dz[8] = {0, 0, 0, 0, 0, 0, 0, 0}, dy[8] = {0, 0, 0, 0, 0, 0, 0, 0};

@@ -96,7 +96,9 @@ class TrainingConfig:
         # rank runs the full minibatch (identical replicas, no collective inside the step; the replicas are re-synchronised by
         # the weight broadcast after evaluation).  A 256-sample step is launch-latency bound on a B200 (4.7 ms, 60 TFLOP/s),
         # so sharding it 8 ways cannot shorten it and adds 30 small BatchNorm-statistics all-reduces per step.
-        self.dp_mode = "shard"
+        # "auto" (default): "replicate" when the hand-written step can run (it takes 1.9 ms per 256-sample step on one B200, less
+        # than a sharded step spends in its collectives), else "shard".
+        self.dp_mode = "auto"
         self.hand_batchnorm = True      # training-mode BatchNorm on csrc/xq_bn.cu (statistics over NVLink peer memory when sharded)
         # forward + loss + backward of the step on the hand-written tf32 tcgen05 kernels (csrc/xq_tnet.cu, tnet.HandStep): used
         # when a rank runs whole minibatches (one GPU or dp_mode "replicate") with a tower width that is a multiple of 128
@@ -471,7 +473,11 @@ class AlphaZeroTrainer:
         self.best_model = XiangqiNet(config.num_channels, config.num_res_blocks).to(self.device)
         if self.world > 1:
             self._broadcast_model(self.current_model)           # C2: every rank starts from rank 0's weights
-        shard = self.world > 1 and getattr(config, "sync_batchnorm", True) and getattr(config, "dp_mode", "shard") == "shard"
+        hand_ok = getattr(config, "hand_step", True) and config.num_channels % 128 == 0
+        self.dp_mode = getattr(config, "dp_mode", "auto")
+        if self.dp_mode == "auto":
+            self.dp_mode = "replicate" if hand_ok else "shard"
+        shard = self.world > 1 and getattr(config, "sync_batchnorm", True) and self.dp_mode == "shard"
         if getattr(config, "hand_batchnorm", True):
             # BatchNorm forward / backward on the kernels of csrc/xq_bn.cu; sharded minibatch: the statistics are exchanged
             # through NVLink peer memory inside those kernels (falls back to NCCL all-reduces if IPC mapping is refused)
@@ -482,14 +488,14 @@ class AlphaZeroTrainer:
         self.best_model.load_state_dict(self.current_model.state_dict())
 
         self.optimizer = FlatAdam(self.eng, self.current_model, lr=config.learning_rate, weight_decay=config.weight_decay,
-                                  max_grad_norm=1.0, dist=self.dist if getattr(config, "dp_mode", "shard") == "shard" else None)
+                                  max_grad_norm=1.0, dist=self.dist if self.dp_mode == "shard" else None)
         self.scheduler = optim.lr_scheduler.MultiStepLR(self.optimizer, milestones=config.lr_milestones, gamma=config.lr_gamma)
         # f1: forward + loss + backward of the step on the hand-written kernels (tnet.HandStep, csrc/xq_tnet.cu) whenever every
         # rank runs whole minibatches (one GPU, or dp_mode "replicate") and the tower is a multiple of 128 channels wide;
         # otherwise (sharded minibatch, 64-channel quick preset) the torch modules run the step as before.
         self._hand = None
-        whole = self.world == 1 or getattr(config, "dp_mode", "shard") == "replicate"
-        if getattr(config, "hand_step", True) and whole and config.num_channels % 128 == 0:
+        whole = self.world == 1 or self.dp_mode == "replicate"
+        if hand_ok and whole:
             from tnet import HandStep
             self._hand = HandStep(self.eng, self.current_model)
         self.replay_buffer = DeviceReplayBuffer(self.eng, config.max_buffer_size)
@@ -640,7 +646,7 @@ class AlphaZeroTrainer:
             ep_batches = 0
             for lo in range(0, n, cfg.batch_size):
                 gidx = perm[lo:lo + cfg.batch_size]
-                if getattr(cfg, "dp_mode", "shard") == "replicate":
+                if self.dp_mode == "replicate":
                     mine, denom = gidx, gidx.numel()                           # every rank runs the whole minibatch
                 else:
                     mine = self._shard(gidx)
@@ -659,7 +665,7 @@ class AlphaZeroTrainer:
                 self.optimizer.step()                                       # all-reduce + clip + Adam
                 ep += torch.stack([p_loss.detach(), v_loss.detach()]).double()
                 ep_batches += 1
-            if self.world > 1 and getattr(cfg, "dp_mode", "shard") == "shard":
+            if self.world > 1 and self.dp_mode == "shard":
                 self.dist.all_reduce(ep)                                    # per-rank partial means -> full-batch means
             sums += ep
             num_batches += ep_batches
