@@ -1,7 +1,8 @@
 // xq_tnet.cu -- f1: the training step of AlphaZeroTrainer.train_network (training/train.py:397-423)
 // on hand-written kernels end to end: tf32 tcgen05 convolutions / dense layers (xq_tmma.cuh), BatchNorm, ReLU, residual
-// adds, heads, loss and their backward passes in the training plane layout (xq_tnet_ops.cuh), driven from C++ (one host
-// call per forward+backward, ~130 launches, no torch op and no cuDNN / cuBLAS call inside).
+// adds, heads and their backward passes in the training plane layout (xq_tnet_ops.cuh).  The C ABI exposes the kernels one
+// by one (include/xq_b200.h, xq_tgemm ... xq_tn_value_backward); tnet.HandStep (Python) strings the ~140 launches of a step
+// together once and replays them from a CUDA graph.  No torch op and no cuDNN / cuBLAS call inside a step.
 #include "xq_tmma.cuh"
 #include "xq_tnet_ops.cuh"
 
