@@ -104,6 +104,8 @@ def run(args, rank, world, local_rank, dist):
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     launches = eng.launch_count()
+    if tr._hand is not None:
+        launches += args.steps * tr._hand.buffers(BATCH).launches     # the kernels replayed from the CUDA graph, counted at capture
     ms = e0.elapsed_time(e1)
 
     # dominant hand-written kernels in isolation (CUDA events on the launching stream, buffers >> L2: 4 x 100 MB)
@@ -269,8 +271,11 @@ def train_block(local_rank=0, steps=30, torch_steps=10):
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / k
+        own = eng.launch_count() / k                                  # host-issued launches of this repo's kernels (batch builder, clip, Adam, ...)
+        if tr._hand is not None:
+            own += tr._hand.buffers(BATCH).launches                   # + the kernels inside the replayed CUDA graph (counted when it was captured)
         out[name] = {"ms_per_step": ms, "samples_per_s": BATCH / (ms * 1e-3), "steps": k, "policy_loss_last": float(pl),
-                     "own_kernel_launches_per_step": eng.launch_count() / k}
+                     "own_kernel_launches_per_step": own}
         del tr
         torch.cuda.empty_cache()
     out["speedup"] = out["torch_cudnn"]["ms_per_step"] / out["hand_written"]["ms_per_step"]

@@ -189,7 +189,7 @@ def test_train_network_matches_the_reference_run(eng, tmp_path, fixture, hand):
     cfg.hand_step = hand
     torch.manual_seed(seed)
     tr = T.AlphaZeroTrainer(cfg)
-    assert (tr._hand is not None) == (hand and ch % 128 == 0)
+    assert (tr._hand is not None) == (hand and ch % 32 == 0)
     assert np.allclose(_checksums(tr.current_model), g["init"], rtol=1e-6, atol=1e-6), "initial weights differ from the reference's"
     rec = np.zeros((records, 896), np.uint8)
     rec[:, :90] = g["board"].view(np.uint8)

@@ -209,7 +209,7 @@ class _StepBuffers:
         self.n_rows = B * BOARD_ROWS
         self.pairs = (self.n_rows + PAIR - 1) // PAIR
         self.dpairs = (B + PAIR - 1) // PAIR
-        cc, cg = C // 4, C // 32
+        cc, cg = C // 4, (C // 32 + 3) // 4 * 4      # G tensors in whole M tiles of 128 channels (the wgrad kernel reads 4 groups; extra ones stay zero)
         self.x0p, self.x0g = z(8, R, 4), z(1, R, 32)
         self.Y = [z(cc, R, 4) for _ in range(layers)]
         self.Ap = [z(cc, R, 4) for _ in range(layers)]
@@ -238,6 +238,7 @@ class _StepBuffers:
         self.z = z(B)
         self.losses = z(2)
         self.graph, self.graph_inv = None, None
+        self.launches = 0
 
 
 class HandStep:
@@ -250,8 +251,8 @@ class HandStep:
     def __init__(self, eng, model):
         self.eng, self.model = eng, model
         self.C, self.nb = model.num_channels, model.num_res_blocks
-        if self.C % 128:
-            raise ValueError("HandStep needs a channel count that is a multiple of 128")
+        if self.C % 32:
+            raise ValueError("HandStep needs a channel count that is a multiple of 32")
         dev = next(model.parameters()).device
         self.dev = dev
         C = self.C
@@ -260,7 +261,7 @@ class HandStep:
             self.convs += [(blk.conv1, blk.bn1), (blk.conv2, blk.bn2)]
         self.L = len(self.convs)
         z = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)
-        nt, kb = C // 128, C // 32
+        nt, kb = (C + 127) // 128, C // 32
         self.img_f = [z(nt, 9, 1, 8, 128, 4)] + [z(nt, 9, kb, 8, 128, 4) for _ in range(self.L - 1)]
         self.img_t = [None] + [z(nt, 9, kb, 8, 128, 4) for _ in range(self.L - 1)]
         self.img_hf = z(1, 1, kb, 8, 128, 4)            # heads 1x1: n = 32 policy + 4 value channels
@@ -330,18 +331,18 @@ class HandStep:
         """conv.weight.grad[co][ci][3][3] from the G-layout gradient and input."""
         e, Cn = self.eng, self.C
         nbg = min(4, (ci + 31) // 32)
-        for mt in range(Cn // 128):
+        for mt in range((Cn + 127) // 128):
             for nt in range((ci + 127) // 128):
                 conv_wgrad(e, dy_g, x_g, b.R, b.n_rows, nbg, 9, b.ws, a_group0=mt * 4, b_group0=nt * 4)
-                n_cnt = min(128, ci - nt * 128)
-                e._check(e.L.xq_tn_wgrad_reduce(e.h, b.ws.data_ptr(), b.slabs, 9 * 128 * 32 * nbg, 9, 32 * nbg, 128, n_cnt, 0, 0,
+                m_cnt, n_cnt = min(128, Cn - mt * 128), min(128, ci - nt * 128)
+                e._check(e.L.xq_tn_wgrad_reduce(e.h, b.ws.data_ptr(), b.slabs, 9 * 128 * 32 * nbg, 9, 32 * nbg, m_cnt, n_cnt, 0, 0,
                                                 conv.weight.grad.data_ptr(), ci, mt * 128, nt * 128, e._stream()))
 
     # ---- the step --------------------------------------------------------------------------------------------
     def forward(self, b, states):
         e, L, Cn = self.eng, self.eng.L, self.C
         s = e._stream
-        nt, kb, cc = Cn // 128, Cn // 32, Cn // 4
+        nt, kb, cc = (Cn + 127) // 128, Cn // 32, Cn // 4
         e._check(L.xq_tn_input(e.h, states.data_ptr(), b.B, 15, 4, b.x0p.data_ptr(), b.x0g.data_ptr(), b.R, s()))
         tgemm(e, b.x0p, b.R, 1, self.img_f[0], 9, 1, False, b.pairs, nt, b.n_rows, out=b.Y[0], out_rows=b.R, out_chunks=cc)
         self._bn_fwd(b, self.convs[0][1], b.Y[0], b.Ap[0], b.Ag[0], 0, Cn, save=b.save[0])
@@ -369,7 +370,7 @@ class HandStep:
     def backward(self, b):
         e, L, Cn = self.eng, self.eng.L, self.C
         s = e._stream
-        nt, kb, cc = Cn // 128, Cn // 32, Cn // 4
+        nt, kb, cc = (Cn + 127) // 128, Cn // 32, Cn // 4
         fc = self.fc
         # policy FC
         e._check(L.xq_tn_colsum(e.h, b.g_logits.data_ptr(), ACTIONS, b.B, ACTIONS, fc.bias.grad.data_ptr(), s()))
@@ -391,8 +392,8 @@ class HandStep:
         for mt in range(nt):
             conv_wgrad(e, top_g, b.dYhg, b.R, b.n_rows, 2, 1, b.ws, a_group0=mt * 4)
             for conv, n0, cnt in ((self.pconv, 0, 32), (self.vconv, 32, 4)):
-                e._check(L.xq_tn_wgrad_reduce(e.h, b.ws.data_ptr(), b.slabs, 128 * 64, 1, 64, 128, cnt, n0, 1, conv.weight.grad.data_ptr(),
-                                              Cn, 0, mt * 128, s()))
+                e._check(L.xq_tn_wgrad_reduce(e.h, b.ws.data_ptr(), b.slabs, 128 * 64, 1, 64, min(128, Cn - mt * 128), cnt, n0, 1,
+                                              conv.weight.grad.data_ptr(), Cn, 0, mt * 128, s()))
         tgemm(e, b.dYh, b.R, 2, self.img_ht, 1, 2, True, b.pairs, nt, b.n_rows, out=b.dA, out_rows=b.R, out_chunks=cc)
         # tower, last layer first
         for i in range(self.L - 1, 0, -1):
@@ -432,7 +433,9 @@ class HandStep:
         elif b.graph is not None and b.graph_inv == inv_batch:
             b.graph.replay()
         else:
+            n0 = self.eng.launch_count()
             self._run(b, inv_batch)                  # eager: also sets the kernels' attributes before any capture
+            b.launches = self.eng.launch_count() - n0        # kernels of csrc/xq_tnet.cu + the loss kernel in one step (a replay launches the same)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):                # capture only (nothing executes): replayed from the next step on

@@ -101,7 +101,7 @@ class TrainingConfig:
         self.dp_mode = "auto"
         self.hand_batchnorm = True      # training-mode BatchNorm on csrc/xq_bn.cu (statistics over NVLink peer memory when sharded)
         # forward + loss + backward of the step on the hand-written tf32 tcgen05 kernels (csrc/xq_tnet.cu, tnet.HandStep): used
-        # when a rank runs whole minibatches (one GPU or dp_mode "replicate") with a tower width that is a multiple of 128
+        # when a rank runs whole minibatches (one GPU or dp_mode "replicate") with a tower width that is a multiple of 32
         self.hand_step = True
 
 
@@ -473,7 +473,7 @@ class AlphaZeroTrainer:
         self.best_model = XiangqiNet(config.num_channels, config.num_res_blocks).to(self.device)
         if self.world > 1:
             self._broadcast_model(self.current_model)           # C2: every rank starts from rank 0's weights
-        hand_ok = getattr(config, "hand_step", True) and config.num_channels % 128 == 0
+        hand_ok = getattr(config, "hand_step", True) and config.num_channels % 32 == 0
         self.dp_mode = getattr(config, "dp_mode", "auto")
         if self.dp_mode == "auto":
             self.dp_mode = "replicate" if hand_ok else "shard"
@@ -491,8 +491,8 @@ class AlphaZeroTrainer:
                                   max_grad_norm=1.0, dist=self.dist if self.dp_mode == "shard" else None)
         self.scheduler = optim.lr_scheduler.MultiStepLR(self.optimizer, milestones=config.lr_milestones, gamma=config.lr_gamma)
         # f1: forward + loss + backward of the step on the hand-written kernels (tnet.HandStep, csrc/xq_tnet.cu) whenever every
-        # rank runs whole minibatches (one GPU, or dp_mode "replicate") and the tower is a multiple of 128 channels wide;
-        # otherwise (sharded minibatch, 64-channel quick preset) the torch modules run the step as before.
+        # rank runs whole minibatches (one GPU, or dp_mode "replicate") and the tower is a multiple of 32 channels wide (all three
+        # presets: 64, 128, 256); otherwise (sharded minibatch, other widths) the torch modules run the step as before.
         self._hand = None
         whole = self.world == 1 or self.dp_mode == "replicate"
         if hand_ok and whole:
