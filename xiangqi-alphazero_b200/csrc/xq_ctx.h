@@ -34,6 +34,7 @@ struct xq_ctx {
     bool net_fork = false;                // XQ_NET_FORK=1: value MLP on a side stream next to the policy FC (measured: 1.002 ms per forward against
                                           // 0.976 ms in sequence -- the co-running CTAs slow the FC more than the 19 us they hide; off)
     bool net_2cta = true;                 // XQ_NET_2CTA=0 (read once in xq_create): tower convs on the single-CTA kernel instead of CTA pairs
+    bool net_pdl = true;                  // XQ_NET_PDL=0 (read once in xq_create): no programmatic dependent launch between the tower's layers
     bool tpb_attr_set = false;            // dynamic shared-memory limit of movegen_tpb_kernel raised on this context's device
 };
 

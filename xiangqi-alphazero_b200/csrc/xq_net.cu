@@ -78,10 +78,21 @@ struct NetState {
     bool tapmask_done = false;
     cudaStream_t side = nullptr;          // the value MLP runs here, next to the policy FC (both depend on the heads conv only)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // small batches: the value MLP of a forward runs on its own stream next to the policy FC; [0] for forwards on the caller's
+    // stream, [1] for forwards that themselves run on `side` (the arena's second network)
+    cudaStream_t vfork[2] = {nullptr, nullptr};
+    cudaEvent_t vev[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
     uint32_t attr_done = 0;   // bit per kernel instantiation: dynamic shared-memory limit raised on THIS context's device
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------
+// Programmatic dependent launch (every kernel of a forward is launched with cudaLaunchAttributeProgrammaticStreamSerialization):
+// a layer's CTAs may start while the previous kernel of the stream is still running -- on SMs it does not occupy, or as its
+// CTAs retire -- and do everything that does not depend on it (barriers, TMEM, weight stages) before griddep_wait() returns,
+// which is when the previous grid has completed and its stores are visible.
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -234,6 +245,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(const GemmArgs p,
     using Cfg = ConvCfg<NT, KCH, HEADS, TPS, WRES>;
     constexpr int TS = Cfg::kTileCols;
     extern __shared__ __align__(128) uint8_t smem[];
+    griddep_launch_dependents();
     const int kblocks = p.kchunks / KCH;
     uint8_t* sA = smem;                                         // [NA][kblocks][KCH][276][16 B]
     uint8_t* sStage = smem + NA * kblocks * Cfg::kSeg;          // [S][kWStage]
@@ -300,6 +312,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(const GemmArgs p,
                                      p.w + (size_t)((tg * TPS + tp) * kblocks + kb) * Cfg::kWTap, Cfg::kWTap, &w_full[st]);
                     }
             }
+            griddep_wait();                                     // the resident weights are on their way; now the previous layer's output
             for (int work = blockIdx.x; work < total; work += gridDim.x, ++n) {
                 const int pair = work / p.n_tiles, n_tile = work - pair * p.n_tiles;
                 const long long m0 = (long long)pair * kPairRows;
@@ -396,6 +409,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(const GemmArgs p,
         const int row = q * 32 + lane;
         int n = 0;
         uint4 res[NT / 8];
+        griddep_wait();                                  // residual reads and output stores come after the previous kernel
         for (int work = blockIdx.x; work < total; work += gridDim.x, ++n) {
             const int pair = work / p.n_tiles, n_tile = work - pair * p.n_tiles;
             const int acc = n & 1;
@@ -630,6 +644,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv2_kernel(const GemmArgs p
     uint64_t* t_empty = t_full + 2;                             // [2] leader only: the 16 epilogue warps of the pair of CTAs
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
 
+    griddep_launch_dependents();                                // the next layer may be scheduled as soon as every CTA of this one runs
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const uint32_t crank = cluster_ctarank();
     const bool leader_cta = crank == 0;
@@ -676,12 +691,31 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv2_kernel(const GemmArgs p
             int s = 0;
             uint32_t ph = 0;
             int n = 0;
+            // Weights do not depend on the previous layer: the first item's weight stages (all stages are empty at kernel
+            // start) go out BEFORE the dependency wait, in the order the main loop would issue them.
+            int pre = 0;
+            if (cluster_id < total) {
+                const int n_tile0 = cluster_id % p.n_tiles;
+                const uint8_t* wt0 = p.w_half + (size_t)(2 * n_tile0 + (int)crank) * 9 * kblocks * Cfg::kWTap;
+                const int per_item = kblocks * tap_groups;
+                pre = per_item < S ? per_item : S;
+                for (int q = 0; q < pre; ++q) {
+                    const int kb = q / tap_groups, tg = q - kb * tap_groups;
+                    mbar_expect_tx(&w_full[q], Cfg::kWStage);
+#pragma unroll
+                    for (int tp = 0; tp < TPS; ++tp)
+                        bulk_g2s(sStage + q * Cfg::kWStage + tp * Cfg::kWTap, wt0 + (size_t)((tg * TPS + tp) * kblocks + kb) * Cfg::kWTap,
+                                 Cfg::kWTap, &w_full[q]);
+                }
+            }
+            griddep_wait();                                     // from here on the previous layer's output may be read
             for (int work = cluster_id; work < total; work += n_clusters, ++n) {
                 const int item = work / p.n_tiles, n_tile = work - item * p.n_tiles;
                 const int pair = item * 2 + (int)crank;
                 const long long m0 = (long long)pair * kPairRows;
                 // image tiled by 64 channels: [n_tile64][tap][k_block][chunk][64][8], n_tile64 = 2 * n_tile + rank
                 const uint8_t* wt = p.w_half + (size_t)(2 * n_tile + (int)crank) * 9 * kblocks * Cfg::kWTap;
+                int q = 0;
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(&a_empty[kb], (uint32_t)(n & 1) ^ 1u);
                     mbar_expect_tx(&a_full[kb], (uint32_t)Cfg::kSeg);
@@ -689,13 +723,15 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv2_kernel(const GemmArgs p
                     for (int c = 0; c < KCH; ++c)
                         bulk_g2s(sA + kb * Cfg::kSeg + c * kAPlane,
                                  p.a + ((size_t)(kb * KCH + c) * p.a_rows + (size_t)(p.a_row0 + m0 - kHalo)) * 16, kAPlane, &a_full[kb]);
-                    for (int tg = 0; tg < tap_groups; ++tg) {
-                        mbar_wait(&w_empty[s], ph ^ 1);
-                        mbar_expect_tx(&w_full[s], Cfg::kWStage);
+                    for (int tg = 0; tg < tap_groups; ++tg, ++q) {
+                        if (n != 0 || q >= pre) {               // (the first item's first `pre` stages are already in flight)
+                            mbar_wait(&w_empty[s], ph ^ 1);
+                            mbar_expect_tx(&w_full[s], Cfg::kWStage);
 #pragma unroll
-                        for (int tp = 0; tp < TPS; ++tp)
-                            bulk_g2s(sStage + s * Cfg::kWStage + tp * Cfg::kWTap,
-                                     wt + (size_t)((tg * TPS + tp) * kblocks + kb) * Cfg::kWTap, Cfg::kWTap, &w_full[s]);
+                            for (int tp = 0; tp < TPS; ++tp)
+                                bulk_g2s(sStage + s * Cfg::kWStage + tp * Cfg::kWTap,
+                                         wt + (size_t)((tg * TPS + tp) * kblocks + kb) * Cfg::kWTap, Cfg::kWTap, &w_full[s]);
+                        }
                         if (++s == S) { s = 0; ph ^= 1; }
                     }
                 }
@@ -780,6 +816,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv2_kernel(const GemmArgs p
         const int row = q * 32 + lane;
         int n = 0;
         uint4 res[NT / 8];
+        griddep_wait();                                         // the residual operand is the previous layers' output
         for (int work = cluster_id; work < total; work += n_clusters, ++n) {
             const int item = work / p.n_tiles, n_tile = work - item * p.n_tiles;
             const int pair = item * 2 + (int)crank;
@@ -894,6 +931,23 @@ static int ensure_smem_attr(xq_ctx* c, K kern, int bit)
     return XQ_OK;
 }
 
+// launch with the programmatic-stream-serialization attribute (see griddep_wait)
+template <class... KArgs, class... Args>
+static cudaError_t launch_pdl(xq_ctx* c, void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t s, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = c->net_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 static int ensure_tapmask(xq_ctx* c, cudaStream_t s)
 {
     NetState* N = net_state(c);
@@ -930,7 +984,7 @@ static int launch_conv_r(xq_ctx* c, GemmArgs& a, cudaStream_t s, int bit)
         if (int rc = ensure_tapmask(c, s)) return rc;
     const int total = ((a.m_tiles + 1) / 2) * a.n_tiles;
     const int grid = c->sm_count < total ? c->sm_count : total;   // persistent, one CTA per SM
-    kern<<<grid, kConvThreads, Cfg::smem_bytes(kblocks, S, NA), s>>>(a, S, NA);
+    XQ_CUDA(c, launch_pdl(c, kern, grid, kConvThreads, (size_t)Cfg::smem_bytes(kblocks, S, NA), s, (const GemmArgs)a, (const int)S, (const int)NA));
     c->launches += 1;
     XQ_CUDA(c, cudaGetLastError());
     return XQ_OK;
@@ -963,13 +1017,17 @@ static int launch_conv2(xq_ctx* c, GemmArgs& a, cudaStream_t s, int bit)
     cfg.blockDim = dim3(kConvThreads);
     cfg.dynamicSmemBytes = Cfg::smem_bytes(kblocks, S);
     cfg.stream = s;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    // programmatic dependent launch: this layer may start while the previous kernel of the stream is draining (its CTAs call
+    // griddepcontrol.launch_dependents first thing) and waits for it with griddepcontrol.wait before touching its output
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = c->net_pdl ? 2 : 1;
     XQ_CUDA(c, cudaLaunchKernelEx(&cfg, kern, (const GemmArgs)a, S));
     c->launches += 1;
     XQ_CUDA(c, cudaGetLastError());
@@ -1002,6 +1060,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) fc_kernel(const GemmArgs p)
 {
     constexpr int S = FcCfg::kStages, NT = FcCfg::kNT;
     extern __shared__ __align__(128) uint8_t smem[];
+    griddep_launch_dependents();
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * FcCfg::kStage);
     uint64_t* w_full = bars;
     uint64_t* w_empty = bars + S;
@@ -1042,15 +1101,29 @@ __global__ void __launch_bounds__(kConvThreads, 1) fc_kernel(const GemmArgs p)
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 0;
-            for (int work = blockIdx.x; work < total; work += gridDim.x) {
+            // the weight halves of the first item's first stages do not depend on the previous kernel: they go out before the wait
+            int pre = 0;
+            if ((int)blockIdx.x < total) {
+                const uint8_t* wt0 = p.w + (size_t)((int)blockIdx.x % p.n_tiles) * iters * FcCfg::kWBytes;
+                pre = iters < S ? iters : S;
+                for (int q = 0; q < pre; ++q) {
+                    mbar_expect_tx(&w_full[q], FcCfg::kStage);
+                    bulk_g2s(smem + q * FcCfg::kStage, wt0 + (size_t)q * FcCfg::kWBytes, FcCfg::kWBytes, &w_full[q]);
+                }
+            }
+            griddep_wait();
+            bool first = true;
+            for (int work = blockIdx.x; work < total; work += gridDim.x, first = false) {
                 const int pair = work / p.n_tiles, n_tile = work - pair * p.n_tiles;
                 const long long m0 = (long long)pair * 256;
                 const uint8_t* wt = p.w + (size_t)n_tile * iters * FcCfg::kWBytes;
                 for (int it = 0; it < iters; ++it) {
-                    mbar_wait(&w_empty[s], ph ^ 1);
                     uint8_t* st = smem + s * FcCfg::kStage;
-                    mbar_expect_tx(&w_full[s], FcCfg::kStage);
-                    bulk_g2s(st, wt + (size_t)it * FcCfg::kWBytes, FcCfg::kWBytes, &w_full[s]);
+                    if (!first || it >= pre) {
+                        mbar_wait(&w_empty[s], ph ^ 1);
+                        mbar_expect_tx(&w_full[s], FcCfg::kStage);
+                        bulk_g2s(st, wt + (size_t)it * FcCfg::kWBytes, FcCfg::kWBytes, &w_full[s]);
+                    }
 #pragma unroll
                     for (int c = 0; c < FcCfg::kKch; ++c)
                         bulk_g2s(st + FcCfg::kWBytes + c * 4096,
@@ -1157,7 +1230,7 @@ static int launch_fc(xq_ctx* c, const GemmArgs& a, cudaStream_t s, int bit)
     if ((long long)a.n_tiles * FcCfg::kNT > a.out_stride) return xq_fail(c, XQ_ERR_ARG, "fc: %d tiles of %d columns exceed the output stride %lld", a.n_tiles, FcCfg::kNT, a.out_stride);
     const int total = ((a.m_tiles + 1) / 2) * a.n_tiles;
     const int grid = c->sm_count < total ? c->sm_count : total;
-    fc_kernel<FcCfg><<<grid, kConvThreads, FcCfg::kSmem, s>>>(a);
+    XQ_CUDA(c, launch_pdl(c, fc_kernel<FcCfg>, grid, kConvThreads, (size_t)FcCfg::kSmem, s, (const GemmArgs)a));
     c->launches += 1;
     XQ_CUDA(c, cudaGetLastError());
     return XQ_OK;
@@ -1175,6 +1248,8 @@ __global__ void __launch_bounds__(128) value_head_kernel(const float* __restrict
                                                           const float* __restrict__ b1, const float* __restrict__ w2,
                                                           float b2, float* __restrict__ value, int B, const int* __restrict__ n_dev)
 {
+    griddep_launch_dependents();
+    griddep_wait();                                              // feats is the heads conv's output
     if (n_dev) B = min(B, *n_dev);
     if ((int)(blockIdx.x * kVhBoards) >= B) return;
     __shared__ __align__(16) float wsm[kVhChunk][128];
@@ -1260,6 +1335,11 @@ extern "C" void xq_net_free_(xq_ctx* c)
     if (!c || !c->net) return;
     NetState* N = reinterpret_cast<NetState*>(c->net);
     if (N->side) cudaStreamDestroy(N->side);
+    for (int i = 0; i < 2; ++i) {
+        if (N->vfork[i]) cudaStreamDestroy(N->vfork[i]);
+        for (int j = 0; j < 2; ++j)
+            if (N->vev[i][j]) cudaEventDestroy(N->vev[i][j]);
+    }
     if (N->ev_fork) cudaEventDestroy(N->ev_fork);
     if (N->ev_join) cudaEventDestroy(N->ev_join);
     delete N;
@@ -1339,7 +1419,7 @@ static int net_value_head(xq_ctx* c, const float* d_feats, const float* d_w1t, c
         return xq_fail(c, XQ_ERR_ARG, "xq_net_value_head: bad arguments");
     if (B == 0) return XQ_OK;
     XQ_CUDA(c, cudaSetDevice(c->device));
-    value_head_kernel<<<(B + kVhBoards - 1) / kVhBoards, 128, 0, s>>>(d_feats, d_w1t, d_b1, d_w2, b2, d_value, B, n_dev);
+    XQ_CUDA(c, launch_pdl(c, value_head_kernel, (B + kVhBoards - 1) / kVhBoards, 128, (size_t)0, s, d_feats, d_w1t, d_b1, d_w2, b2, d_value, B, n_dev));
     c->launches += 1;
     XQ_CUDA(c, cudaGetLastError());
     return XQ_OK;
@@ -1376,24 +1456,41 @@ static int net_run_impl(xq_ctx* c, const xq_gemm_desc* layers, int n_layers, con
                         const float* d_b1, const float* d_w2, float b2, float* d_value, int B, const int* n_dev, cudaStream_t s)
 {
     NetState* N = net_state(c);
+    // Up to kForkBoards boards the forward is a chain of kernels that each leave most SMs idle, and the value MLP (19 us on a
+    // few CTAs) hides completely behind the policy FC (29 us on 37 CTAs): it is forked onto its own stream.  At batch 4096 the
+    // co-running CTAs cost the FC more than they hide (profiles/r2_fwd_ab.txt), so there the sequence stays (XQ_NET_FORK=1 forces
+    // the fork at every size).
+    constexpr int kForkBoards = 1024;
+    const bool want_fork = c->net_fork || B <= kForkBoards;
+    cudaStream_t fs = nullptr;
+    cudaEvent_t ef = nullptr, ej = nullptr;
+    if (want_fork) {
+        const int slot = (N->side && s == N->side) ? 1 : 0;
+        if (!N->vfork[slot]) {
+            XQ_CUDA(c, cudaSetDevice(c->device));
+            XQ_CUDA(c, cudaStreamCreateWithFlags(&N->vfork[slot], cudaStreamNonBlocking));
+            XQ_CUDA(c, cudaEventCreateWithFlags(&N->vev[slot][0], cudaEventDisableTiming));
+            XQ_CUDA(c, cudaEventCreateWithFlags(&N->vev[slot][1], cudaEventDisableTiming));
+        }
+        fs = N->vfork[slot];
+        ef = N->vev[slot][0];
+        ej = N->vev[slot][1];
+    }
     bool forked = false;
     for (int i = 0; i < n_layers; ++i) {
         int rc = net_gemm(c, &layers[i], B, n_dev, s);
         if (rc) return rc;
-        if (c->net_fork && layers[i].mode == 1 && i + 1 < n_layers && !forked) {
-            cudaStream_t side_;
-            cudaEvent_t ef_, ej_;
-            if (int rc2 = xq_net_side_stream_(c, &side_, &ef_, &ej_)) return rc2;
-            XQ_CUDA(c, cudaEventRecord(N->ev_fork, s));
-            XQ_CUDA(c, cudaStreamWaitEvent(N->side, N->ev_fork, 0));
-            rc = net_value_head(c, d_vfeats, d_w1t, d_b1, d_w2, b2, d_value, B, n_dev, N->side);
+        if (want_fork && layers[i].mode == 1 && i + 1 < n_layers && !forked) {
+            XQ_CUDA(c, cudaEventRecord(ef, s));
+            XQ_CUDA(c, cudaStreamWaitEvent(fs, ef, 0));
+            rc = net_value_head(c, d_vfeats, d_w1t, d_b1, d_w2, b2, d_value, B, n_dev, fs);
             if (rc) return rc;
-            XQ_CUDA(c, cudaEventRecord(N->ev_join, N->side));
+            XQ_CUDA(c, cudaEventRecord(ej, fs));
             forked = true;
         }
     }
     if (forked) {
-        XQ_CUDA(c, cudaStreamWaitEvent(s, N->ev_join, 0));
+        XQ_CUDA(c, cudaStreamWaitEvent(s, ej, 0));
         return XQ_OK;
     }
     return net_value_head(c, d_vfeats, d_w1t, d_b1, d_w2, b2, d_value, B, n_dev, s);
