@@ -1106,8 +1106,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) fc_kernel(const GemmArgs p)
             if ((int)blockIdx.x < total) {
                 const uint8_t* wt0 = p.w + (size_t)((int)blockIdx.x % p.n_tiles) * iters * FcCfg::kWBytes;
                 pre = iters < S ? iters : S;
+                long long lr0 = (long long)live_boards - (long long)((int)blockIdx.x / p.n_tiles) * 256;
+                lr0 = lr0 > 256 ? 256 : lr0;
+                const uint32_t tx0 = (uint32_t)FcCfg::kWBytes + (uint32_t)FcCfg::kKch * ((uint32_t)((lr0 + 7) / 8 * 8) * 16u);
                 for (int q = 0; q < pre; ++q) {
-                    mbar_expect_tx(&w_full[q], FcCfg::kStage);
+                    mbar_expect_tx(&w_full[q], tx0);
                     bulk_g2s(smem + q * FcCfg::kStage, wt0 + (size_t)q * FcCfg::kWBytes, FcCfg::kWBytes, &w_full[q]);
                 }
             }
@@ -1117,17 +1120,23 @@ __global__ void __launch_bounds__(kConvThreads, 1) fc_kernel(const GemmArgs p)
                 const int pair = work / p.n_tiles, n_tile = work - pair * p.n_tiles;
                 const long long m0 = (long long)pair * 256;
                 const uint8_t* wt = p.w + (size_t)n_tile * iters * FcCfg::kWBytes;
+                // only the live boards' rows of the A tile travel (a small batch is weight-bound: 46 MB of weights against a few
+                // KB of features); the rows behind them keep stale shared memory and their outputs are dropped by the epilogue
+                long long live_rows = (long long)live_boards - m0;
+                live_rows = live_rows > 256 ? 256 : live_rows;
+                const uint32_t a_bytes = (uint32_t)((live_rows + 7) / 8 * 8) * 16u;
+                const uint32_t stage_tx = (uint32_t)FcCfg::kWBytes + (uint32_t)FcCfg::kKch * a_bytes;
                 for (int it = 0; it < iters; ++it) {
                     uint8_t* st = smem + s * FcCfg::kStage;
                     if (!first || it >= pre) {
                         mbar_wait(&w_empty[s], ph ^ 1);
-                        mbar_expect_tx(&w_full[s], FcCfg::kStage);
+                        mbar_expect_tx(&w_full[s], stage_tx);
                         bulk_g2s(st, wt + (size_t)it * FcCfg::kWBytes, FcCfg::kWBytes, &w_full[s]);
                     }
 #pragma unroll
                     for (int c = 0; c < FcCfg::kKch; ++c)
                         bulk_g2s(st + FcCfg::kWBytes + c * 4096,
-                                 p.a + ((size_t)(it * FcCfg::kKch + c) * p.a_rows + (size_t)(p.a_row0 + m0)) * 16, 4096, &w_full[s]);
+                                 p.a + ((size_t)(it * FcCfg::kKch + c) * p.a_rows + (size_t)(p.a_row0 + m0)) * 16, a_bytes, &w_full[s]);
                     if (++s == S) { s = 0; ph ^= 1; }
                 }
             }
