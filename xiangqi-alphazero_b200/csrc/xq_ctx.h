@@ -35,6 +35,9 @@ struct xq_ctx {
                                           // 0.976 ms in sequence -- the co-running CTAs slow the FC more than the 19 us they hide; off)
     bool net_2cta = true;                 // XQ_NET_2CTA=0 (read once in xq_create): tower convs on the single-CTA kernel instead of CTA pairs
     bool net_pdl = true;                  // XQ_NET_PDL=0 (read once in xq_create): no programmatic dependent launch between the tower's layers
+    bool train_pdl = false;               // XQ_TRAIN_PDL=1: the same for the kernels of the training step (xq_tnet.cu).  Measured inside the
+                                          // step's CUDA graph: 1.94 ms per step with it against 1.86 ms without -- those kernels fill the
+                                          // GPU, a dependent CTA finds no free SM to set itself up on, and graph edges are cheap already
     bool tpb_attr_set = false;            // dynamic shared-memory limit of movegen_tpb_kernel raised on this context's device
 };
 
@@ -111,4 +114,27 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
                  "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// Programmatic dependent launch (kernels launched with cudaLaunchAttributeProgrammaticStreamSerialization): a kernel's CTAs
+// may start while the previous kernel of the stream is still running -- on SMs it does not occupy, or as its CTAs retire --
+// and do everything that does not depend on it (barriers, TMEM, weight stages) before griddep_wait() returns, which is when
+// the previous grid has completed and its stores are visible.  SASS: PREEXIT / ACQBULK.
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 }  // namespace xq
+
+// launch with the programmatic-stream-serialization attribute (see griddep_wait); pdl = false: a plain launch
+template <class... KArgs, class... Args>
+static inline cudaError_t xq_launch_pdl(bool pdl, void (*kern)(KArgs...), dim3 grid, int block, size_t smem, cudaStream_t s, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, args...);
+}

@@ -86,13 +86,6 @@ struct NetState {
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------
-// Programmatic dependent launch (every kernel of a forward is launched with cudaLaunchAttributeProgrammaticStreamSerialization):
-// a layer's CTAs may start while the previous kernel of the stream is still running -- on SMs it does not occupy, or as its
-// CTAs retire -- and do everything that does not depend on it (barriers, TMEM, weight stages) before griddep_wait() returns,
-// which is when the previous grid has completed and its stores are visible.
-__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -931,21 +924,10 @@ static int ensure_smem_attr(xq_ctx* c, K kern, int bit)
     return XQ_OK;
 }
 
-// launch with the programmatic-stream-serialization attribute (see griddep_wait)
 template <class... KArgs, class... Args>
 static cudaError_t launch_pdl(xq_ctx* c, void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t s, Args... args)
 {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(block);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = c->net_pdl ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, kern, args...);
+    return xq_launch_pdl(c->net_pdl, kern, dim3(grid), block, smem, s, args...);
 }
 
 static int ensure_tapmask(xq_ctx* c, cudaStream_t s)

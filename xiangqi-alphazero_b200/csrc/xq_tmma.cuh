@@ -133,6 +133,7 @@ struct TgArgs {
 __global__ void __launch_bounds__(kTgThreads, 1) tg_kernel(const TgArgs p)
 {
     extern __shared__ __align__(128) uint8_t smem[];
+    griddep_launch_dependents();                 // the next kernel of the step may set itself up while this one runs
     uint8_t* sA = smem;
     uint8_t* sB = smem + kTNSeg * kTSeg;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sB + kTNStage * kTStage);
@@ -175,11 +176,31 @@ __global__ void __launch_bounds__(kTgThreads, 1) tg_kernel(const TgArgs p)
         // ===================== bulk-copy producer =====================
         int sg = 0, s = 0;
         uint32_t sgph = 0, ph = 0;
-        for (int work = blockIdx.x; work < total; work += gridDim.x) {
+        // The weight image was written at the start of the step, long before the kernel in front of this one: the first
+        // item's first weight stages (all stages are empty at kernel start) go out BEFORE the dependency wait, in the order
+        // the loop below would issue them.
+        int pre = 0;
+        if ((int)blockIdx.x < total) {
+            const int ks0 = (int)blockIdx.x % p.k_splits, wr0 = (int)blockIdx.x / p.k_splits;
+            const int n_tile0 = wr0 % p.n_tiles;
+            const int kb00 = ks0 * p.kb_per, kb01 = min(p.kblocks, kb00 + p.kb_per);
+            const int n_first = (kb01 - kb00) * p.ntaps;
+            pre = n_first < kTNStage ? n_first : kTNStage;
+            if (lane == 0)
+                for (int q = 0; q < pre; ++q) {
+                    const int kb = kb00 + q / p.ntaps, tap = q % p.ntaps;
+                    mbar_expect_tx(&w_full[q], (uint32_t)kTStage);
+                    bulk_g2s(sB + q * kTStage, p.w + ((size_t)(n_tile0 * p.ntaps + tap) * p.img_kb + kb) * kTStage, kTStage, &w_full[q]);
+                }
+        }
+        griddep_wait();                          // from here on the previous kernels' outputs (the A operand) may be read
+        bool first = true;
+        for (int work = blockIdx.x; work < total; work += gridDim.x, first = false) {
             const int ks = work % p.k_splits, wr = work / p.k_splits;
             const int pair = wr / p.n_tiles, n_tile = wr - pair * p.n_tiles;
             const long long m0 = (long long)pair * kTPair;
             const int kb0 = ks * p.kb_per, kb1 = min(p.kblocks, kb0 + p.kb_per);
+            int q = 0;
             for (int kb = kb0; kb < kb1; ++kb) {
                 if (lane == 0) {
                     mbar_wait(&a_empty[sg], sgph ^ 1u);
@@ -189,8 +210,8 @@ __global__ void __launch_bounds__(kTgThreads, 1) tg_kernel(const TgArgs p)
                                  p.a + ((size_t)(kb * 8 + c) * p.a_rows + (size_t)(p.a_row0 + m0 - kTHalo)) * 16, kTAPlane, &a_full[sg]);
                 }
                 if (++sg == kTNSeg) { sg = 0; sgph ^= 1u; }
-                for (int tap = 0; tap < p.ntaps; ++tap) {
-                    if (lane == 0) {
+                for (int tap = 0; tap < p.ntaps; ++tap, ++q) {
+                    if (lane == 0 && (!first || q >= pre)) {
                         mbar_wait(&w_empty[s], ph ^ 1u);
                         mbar_expect_tx(&w_full[s], (uint32_t)kTStage);
                         bulk_g2s(sB + s * kTStage, p.w + ((size_t)(n_tile * p.ntaps + tap) * p.img_kb + kb) * kTStage, kTStage, &w_full[s]);
@@ -245,6 +266,7 @@ __global__ void __launch_bounds__(kTgThreads, 1) tg_kernel(const TgArgs p)
         const int t = (warp - 2) >> 2;
         const int row = q * 32 + lane;
         int n = 0;
+        griddep_wait();                          // residual reads and output stores come after the previous kernels
         for (int work = blockIdx.x; work < total; work += gridDim.x, ++n) {
             const int ks = work % p.k_splits, wr = work / p.k_splits;
             const int pair = wr / p.n_tiles, n_tile = wr - pair * p.n_tiles;
@@ -341,6 +363,7 @@ struct TwgArgs {
 __global__ void __launch_bounds__(kTwgThreads, 1) twg_kernel(const TwgArgs p)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
+    griddep_launch_dependents();
     uint8_t* smem = smem_raw + ((512u - (smem_u32(smem_raw) & 511u)) & 511u);     // stage bases 512-byte aligned (swizzle phase)
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.n_stages * p.stage_bytes);
     uint64_t* full = bars;                   // [kTwgMaxStages]
@@ -377,6 +400,7 @@ __global__ void __launch_bounds__(kTwgThreads, 1) twg_kernel(const TwgArgs p)
     if (warp == 0) {
         int s = 0;
         uint32_t ph = 0;
+        griddep_wait();                          // both operands are outputs of the kernels in front (barriers and TMEM are set up by now)
         for (int work = blockIdx.x; work < total; work += gridDim.x) {
             const int g = work % p.n_groups, rest = work / p.n_groups;
             const int slab = rest % p.n_slabs, mt = rest / p.n_slabs;
@@ -431,6 +455,7 @@ __global__ void __launch_bounds__(kTwgThreads, 1) twg_kernel(const TwgArgs p)
         const int q = warp & 3;                                  // warps 2,3,4,5 -> TMEM lane quarters 2,3,0,1
         float* scr = scratch + (warp - 2) * (32 * 33);
         int n = 0;
+        griddep_wait();                          // the output buffer may still be read by the kernel in front
         for (int work = blockIdx.x; work < total; work += gridDim.x, ++n) {
             const int g = work % p.n_groups, rest = work / p.n_groups;
             const int slab = rest % p.n_slabs, mt = rest / p.n_slabs;

@@ -74,7 +74,7 @@ int launch_tg(xq_ctx* c, const xq_tgemm_desc* d, cudaStream_t s)
     const int total = d->m_pairs * d->n_tiles * ks;
     const int grid = c->sm_count < total ? c->sm_count : total;
     if (int rc = ensure_attr(c, tg_kernel, 0, kTgSmem)) return rc;
-    tg_kernel<<<grid, kTgThreads, kTgSmem, s>>>(a);
+    XQ_CUDA(c, xq_launch_pdl(c->train_pdl, tg_kernel, dim3(grid), kTgThreads, (size_t)kTgSmem, s, (const TgArgs)a));
     c->launches += 1;
     XQ_CUDA(c, cudaGetLastError());
     return XQ_OK;
@@ -134,7 +134,7 @@ int launch_twg(xq_ctx* c, const xq_twgrad_desc* d, cudaStream_t s)
     if (int rc = ensure_attr(c, twg_kernel, 2, 227 * 1024)) return rc;
     const int total = d->n_mtiles * d->n_slabs * d->n_groups;
     const int grid = c->sm_count < total ? c->sm_count : total;
-    twg_kernel<<<grid, kTwgThreads, smem_bytes, s>>>(a);
+    XQ_CUDA(c, xq_launch_pdl(c->train_pdl, twg_kernel, dim3(grid), kTwgThreads, (size_t)smem_bytes, s, (const TwgArgs)a));
     c->launches += 1;
     XQ_CUDA(c, cudaGetLastError());
     return XQ_OK;
@@ -242,8 +242,9 @@ extern "C" int xq_tn_bn_forward(xq_ctx* c, const xq_tn_bn_desc* d, void* stream)
     a.y = d->y; a.res = d->res; a.out = d->out; a.out_g = d->out_g; a.rows = d->rows; a.n_boards = d->n_boards; a.chunk0 = d->chunk0;
     a.n_channels = d->n_channels; a.relu = d->relu; a.partial = d->partial; a.gamma = d->gamma; a.beta = d->beta;
     a.running_mean = d->running_mean; a.running_var = d->running_var; a.save = d->save; a.eps = d->eps; a.momentum = d->momentum;
-    tn_bn_stat_kernel<<<dim3(2 * pairs, kTnSplit), 256, 0, s>>>(d->y, d->rows, d->n_boards, d->chunk0, d->partial);
-    tn_bn_apply_kernel<<<dim3(pairs, tn_row_splits(d->n_boards)), 256, 0, s>>>(a);
+    XQ_CUDA(c, xq_launch_pdl(c->train_pdl, tn_bn_stat_kernel, dim3(2 * pairs, kTnSplit), 256, (size_t)0, s, d->y, (long long)d->rows, d->n_boards, d->chunk0,
+                             d->partial));
+    XQ_CUDA(c, xq_launch_pdl(c->train_pdl, tn_bn_apply_kernel, dim3(pairs, tn_row_splits(d->n_boards)), 256, (size_t)0, s, (const TnBnArgs)a));
     c->launches += 2;
     XQ_TN_DONE();
 }
@@ -259,8 +260,8 @@ extern "C" int xq_tn_bn_backward(xq_ctx* c, const xq_tn_bn_bwd_desc* d, void* st
     a.dout = d->dout; a.act = d->act; a.y = d->y; a.rows = d->rows; a.n_boards = d->n_boards; a.chunk0 = d->chunk0; a.n_channels = d->n_channels;
     a.relu = d->relu; a.save = d->save; a.partial = d->partial; a.gamma = d->gamma; a.dgamma = d->dgamma; a.dbeta = d->dbeta; a.dy = d->dy;
     a.dy_g = d->dy_g; a.dskip = d->dskip;
-    tn_bn_bwd_stat_kernel<<<dim3(2 * pairs, kTnSplit), 256, 0, s>>>(a);
-    tn_bn_bwd_apply_kernel<<<dim3(pairs, tn_row_splits(d->n_boards)), 256, 0, s>>>(a);
+    XQ_CUDA(c, xq_launch_pdl(c->train_pdl, tn_bn_bwd_stat_kernel, dim3(2 * pairs, kTnSplit), 256, (size_t)0, s, (const TnBnBwdArgs)a));
+    XQ_CUDA(c, xq_launch_pdl(c->train_pdl, tn_bn_bwd_apply_kernel, dim3(pairs, tn_row_splits(d->n_boards)), 256, (size_t)0, s, (const TnBnBwdArgs)a));
     c->launches += 2;
     XQ_TN_DONE();
 }
@@ -271,8 +272,8 @@ extern "C" int xq_tn_wgrad_reduce(xq_ctx* c, const float* ws, int slabs, int64_t
     XQ_TN_ENTER("xq_tn_wgrad_reduce");
     if (!ws || !dw || slabs <= 0 || taps <= 0 || m_cnt <= 0 || m_cnt > 128 || n_cnt <= 0 || n_src0 < 0 || n_src0 + n_cnt > ldn || ci_total <= 0)
         return xq_fail(c, XQ_ERR_ARG, "xq_tn_wgrad_reduce: bad arguments");
-    tn_wgrad_reduce_kernel<<<tn_blocks((long long)taps * m_cnt * n_cnt), 256, 0, s>>>(ws, slabs, slab_stride, taps, ldn, m_cnt, n_cnt, n_src0, transposed,
-                                                                                      dw, ci_total, co0, ci0);
+    XQ_CUDA(c, xq_launch_pdl(c->train_pdl, tn_wgrad_reduce_kernel, dim3(tn_blocks((long long)taps * m_cnt * n_cnt)), 256, (size_t)0, s, ws, slabs, slab_stride, taps, ldn, m_cnt, n_cnt, n_src0, transposed,
+                                                                                      dw, ci_total, co0, ci0));
     c->launches += 1;
     XQ_TN_DONE();
 }
@@ -283,7 +284,7 @@ extern "C" int xq_tn_flatten(xq_ctx* c, const float* act, int64_t rows, int n_bo
     XQ_TN_ENTER("xq_tn_flatten");
     if (!act || !dense || n_boards <= 0 || channels <= 0 || (channels * 90) % 4 || drows < kTnRow0 + n_boards)
         return xq_fail(c, XQ_ERR_ARG, "xq_tn_flatten: bad arguments");
-    tn_flatten_kernel<<<tn_blocks((long long)channels * 90 / 4 * n_boards), 256, 0, s>>>(act, rows, n_boards, channels, dense, dense_g, drows);
+    XQ_CUDA(c, xq_launch_pdl(c->train_pdl, tn_flatten_kernel, dim3(tn_blocks((long long)channels * 90 / 4 * n_boards)), 256, (size_t)0, s, act, rows, n_boards, channels, dense, dense_g, drows));
     c->launches += 1;
     XQ_TN_DONE();
 }
@@ -294,8 +295,8 @@ extern "C" int xq_tn_unflatten(xq_ctx* c, const float* dense, int64_t drows, int
     XQ_TN_ENTER("xq_tn_unflatten");
     if (!dense || !planes || n_boards <= 0 || channels <= 0 || (channels & 3) || drows < kTnRow0 + n_boards || n_partials < 1)
         return xq_fail(c, XQ_ERR_ARG, "xq_tn_unflatten: bad arguments");
-    tn_unflatten_kernel<<<tn_blocks((long long)n_boards * 90 * (channels / 4)), 256, 0, s>>>(dense, drows, n_boards, channels, planes, rows,
-                                                                                         n_partials, part_stride);
+    XQ_CUDA(c, xq_launch_pdl(c->train_pdl, tn_unflatten_kernel, dim3(tn_blocks((long long)n_boards * 90 * (channels / 4))), 256, (size_t)0, s, dense, drows, n_boards, channels, planes, rows,
+                                                                                         n_partials, part_stride));
     c->launches += 1;
     XQ_TN_DONE();
 }
@@ -306,7 +307,7 @@ extern "C" int xq_tn_rows_layouts(xq_ctx* c, const float* m, int64_t stride, int
     XQ_TN_ENTER("xq_tn_rows_layouts");
     if (!m || (!dense && !dense_g) || n_rows <= 0 || n_cols <= 0 || (n_cols & 3) || (stride & 3) || drows < kTnRow0 + n_rows)
         return xq_fail(c, XQ_ERR_ARG, "xq_tn_rows_layouts: bad arguments");
-    tn_rows_layouts_kernel<<<tn_blocks((long long)(n_cols / 4) * n_rows), 256, 0, s>>>(m, stride, n_rows, n_cols, dense, dense_g, drows);
+    XQ_CUDA(c, xq_launch_pdl(c->train_pdl, tn_rows_layouts_kernel, dim3(tn_blocks((long long)(n_cols / 4) * n_rows)), 256, (size_t)0, s, m, stride, n_rows, n_cols, dense, dense_g, drows));
     c->launches += 1;
     XQ_TN_DONE();
 }
@@ -315,7 +316,7 @@ extern "C" int xq_tn_colsum(xq_ctx* c, const float* m, int64_t stride, int n_row
 {
     XQ_TN_ENTER("xq_tn_colsum");
     if (!m || !out || n_rows <= 0 || n_cols <= 0) return xq_fail(c, XQ_ERR_ARG, "xq_tn_colsum: bad arguments");
-    tn_colsum_kernel<<<tn_blocks(n_cols, 32), 256, 0, s>>>(m, stride, n_rows, n_cols, out);
+    XQ_CUDA(c, xq_launch_pdl(c->train_pdl, tn_colsum_kernel, dim3(tn_blocks(n_cols, 32)), 256, (size_t)0, s, m, stride, n_rows, n_cols, out));
     c->launches += 1;
     XQ_TN_DONE();
 }
@@ -325,7 +326,7 @@ extern "C" int xq_tn_value_forward(xq_ctx* c, const float* act, int64_t rows, in
 {
     XQ_TN_ENTER("xq_tn_value_forward");
     if (!act || !w1 || !b1 || !w2 || !b2 || !h || !v || n_boards <= 0 || chunk < 0) return xq_fail(c, XQ_ERR_ARG, "xq_tn_value_forward: bad arguments");
-    tn_value_fwd_kernel<<<n_boards, 256, 0, s>>>(act, rows, chunk, w1, b1, w2, b2, h, v);
+    XQ_CUDA(c, xq_launch_pdl(c->train_pdl, tn_value_fwd_kernel, dim3(n_boards), 256, (size_t)0, s, act, rows, chunk, w1, b1, w2, b2, h, v));
     c->launches += 1;
     XQ_TN_DONE();
 }
@@ -337,8 +338,8 @@ extern "C" int xq_tn_value_backward(xq_ctx* c, const float* act, int64_t rows, i
     XQ_TN_ENTER("xq_tn_value_backward");
     if (!act || !w1 || !w2 || !h || !v || !g_value || !dh || !dpre || !dact || !dw1 || !db1 || !dw2 || !db2 || n_boards <= 0 || chunk < 0)
         return xq_fail(c, XQ_ERR_ARG, "xq_tn_value_backward: bad arguments");
-    tn_value_bwd_a_kernel<<<n_boards, 384, 0, s>>>(w1, w2, h, v, g_value, dh, dpre, dact, rows, chunk);
-    tn_value_bwd_w_kernel<<<kTnVH + 1, 384, 0, s>>>(act, rows, chunk, n_boards, h, dh, dpre, dw1, db1, dw2, db2);
+    XQ_CUDA(c, xq_launch_pdl(c->train_pdl, tn_value_bwd_a_kernel, dim3(n_boards), 384, (size_t)0, s, w1, w2, h, v, g_value, dh, dpre, dact, rows, chunk));
+    XQ_CUDA(c, xq_launch_pdl(c->train_pdl, tn_value_bwd_w_kernel, dim3(kTnVH + 1), 384, (size_t)0, s, act, rows, chunk, n_boards, h, dh, dpre, dw1, db1, dw2, db2));
     c->launches += 2;
     XQ_TN_DONE();
 }

@@ -166,6 +166,8 @@ __global__ void __launch_bounds__(256) tn_wimage_batch_kernel(const TnWimageBatc
 __global__ void __launch_bounds__(256) tn_bn_stat_kernel(const float* __restrict__ y, long long rows, int n_boards, int chunk0,
                                                          double* __restrict__ partial)
 {
+    griddep_launch_dependents();
+    griddep_wait();                                  // everything this kernel reads or overwrites belongs to earlier kernels of the step
     __shared__ double sm[8][8];
     const int chunk = blockIdx.x, sp = blockIdx.y;
     const long long n_rows = (long long)n_boards * kTnBoard;
@@ -210,6 +212,8 @@ struct TnBnArgs {
 // grid (chunk pairs, row splits)
 __global__ void __launch_bounds__(256) tn_bn_apply_kernel(const TnBnArgs p)
 {
+    griddep_launch_dependents();
+    griddep_wait();                                  // everything this kernel reads or overwrites belongs to earlier kernels of the step
     __shared__ float sa[8], sb[8];
     const int cp = blockIdx.x;
     if (threadIdx.x < 8) {
@@ -288,6 +292,8 @@ struct TnBnBwdArgs {
 
 __global__ void __launch_bounds__(256) tn_bn_bwd_stat_kernel(const TnBnBwdArgs p)
 {
+    griddep_launch_dependents();
+    griddep_wait();                                  // everything this kernel reads or overwrites belongs to earlier kernels of the step
     __shared__ double sm[8][8];
     const int chunk = blockIdx.x, sp = blockIdx.y;
     const long long n_rows = (long long)p.n_boards * kTnBoard;
@@ -331,6 +337,8 @@ __global__ void __launch_bounds__(256) tn_bn_bwd_stat_kernel(const TnBnBwdArgs p
 
 __global__ void __launch_bounds__(256) tn_bn_bwd_apply_kernel(const TnBnBwdArgs p)
 {
+    griddep_launch_dependents();
+    griddep_wait();                                  // everything this kernel reads or overwrites belongs to earlier kernels of the step
     __shared__ float s_mean[8], s_inv[8], s_k[8], s_m1[8], s_m2[8];
     const int cp = blockIdx.x;
     if (threadIdx.x < 8) {
@@ -393,6 +401,8 @@ __global__ void __launch_bounds__(256) tn_wgrad_reduce_kernel(const float* __res
                                                               int m_cnt, int n_cnt, int n_src0, int transposed, float* __restrict__ dw,
                                                               int ci_total, int co0, int ci0)
 {
+    griddep_launch_dependents();
+    griddep_wait();                                  // everything this kernel reads or overwrites belongs to earlier kernels of the step
     const long long total = (long long)taps * m_cnt * n_cnt;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
@@ -411,6 +421,8 @@ __global__ void __launch_bounds__(256) tn_wgrad_reduce_kernel(const float* __res
 __global__ void __launch_bounds__(256) tn_flatten_kernel(const float* __restrict__ act, long long rows, int n_boards, int channels,
                                                          float* __restrict__ dense, float* __restrict__ dense_g, long long drows)
 {
+    griddep_launch_dependents();
+    griddep_wait();                                  // everything this kernel reads or overwrites belongs to earlier kernels of the step
     const int k4_cnt = channels * 90 / 4;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)k4_cnt * n_boards) return;
@@ -431,6 +443,8 @@ __global__ void __launch_bounds__(256) tn_flatten_kernel(const float* __restrict
 __global__ void __launch_bounds__(256) tn_unflatten_kernel(const float* __restrict__ dense, long long drows, int n_boards, int channels,
                                                            float* __restrict__ planes, long long rows, int n_partials, long long part_stride)
 {
+    griddep_launch_dependents();
+    griddep_wait();                                  // everything this kernel reads or overwrites belongs to earlier kernels of the step
     const int chunks = channels / 4;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)n_boards * 90 * chunks) return;
@@ -454,6 +468,8 @@ __global__ void __launch_bounds__(256) tn_unflatten_kernel(const float* __restri
 __global__ void __launch_bounds__(256) tn_rows_layouts_kernel(const float* __restrict__ m, long long stride, int n_rows, int n_cols,
                                                               float* __restrict__ dense, float* __restrict__ dense_g, long long drows)
 {
+    griddep_launch_dependents();
+    griddep_wait();                                  // everything this kernel reads or overwrites belongs to earlier kernels of the step
     const int n4_cnt = n_cols / 4;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)n4_cnt * n_rows) return;
@@ -467,6 +483,8 @@ __global__ void __launch_bounds__(256) tn_rows_layouts_kernel(const float* __res
 // out[n] = sum_b m[b][n] (bias gradient): 32 columns x 8 row groups per block, fixed order
 __global__ void __launch_bounds__(256) tn_colsum_kernel(const float* __restrict__ m, long long stride, int n_rows, int n_cols, float* __restrict__ out)
 {
+    griddep_launch_dependents();
+    griddep_wait();                                  // everything this kernel reads or overwrites belongs to earlier kernels of the step
     __shared__ float sm[8][32];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int n = blockIdx.x * 32 + tx;
@@ -499,6 +517,8 @@ __global__ void __launch_bounds__(256) tn_value_fwd_kernel(const float* __restri
                                                            const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
                                                            float* __restrict__ h, float* __restrict__ v)
 {
+    griddep_launch_dependents();
+    griddep_wait();                                  // everything this kernel reads or overwrites belongs to earlier kernels of the step
     __shared__ float f[kTnVF], hs[kTnVH], red[4];
     const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int k = threadIdx.x; k < kTnVF; k += 256) f[k] = tn_value_feature(act, rows, chunk, b, k);
@@ -537,6 +557,8 @@ __global__ void __launch_bounds__(384) tn_value_bwd_a_kernel(const float* __rest
                                                              const float* __restrict__ v, const float* __restrict__ g_value, float* __restrict__ dh,
                                                              float* __restrict__ dpre, float* __restrict__ dact, long long rows, int chunk)
 {
+    griddep_launch_dependents();
+    griddep_wait();                                  // everything this kernel reads or overwrites belongs to earlier kernels of the step
     __shared__ float s_dh[kTnVH];
     const int b = blockIdx.x;
     const float vv = v[b];
@@ -565,6 +587,8 @@ __global__ void __launch_bounds__(384) tn_value_bwd_w_kernel(const float* __rest
                                                              float* __restrict__ dw1, float* __restrict__ db1, float* __restrict__ dw2,
                                                              float* __restrict__ db2)
 {
+    griddep_launch_dependents();
+    griddep_wait();                                  // everything this kernel reads or overwrites belongs to earlier kernels of the step
     const int j = blockIdx.x, k = threadIdx.x;
     if (j < kTnVH) {
         float acc = 0.0f, bacc = 0.0f;
