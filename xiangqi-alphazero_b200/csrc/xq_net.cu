@@ -305,13 +305,29 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(const GemmArgs p,
                                      p.w + (size_t)((tg * TPS + tp) * kblocks + kb) * Cfg::kWTap, Cfg::kWTap, &w_full[st]);
                     }
             }
-            griddep_wait();                                     // the resident weights are on their way; now the previous layer's output
+            // streamed weights: the first item's first stages (all empty at kernel start) go out before the dependency wait too
+            int pre = 0;
+            if (!WRES && (int)blockIdx.x < total) {
+                const uint8_t* wt0 = p.w + (size_t)((int)blockIdx.x % p.n_tiles) * Cfg::kTaps * kblocks * Cfg::kWTap;
+                const int per_item = kblocks * tap_groups;
+                pre = per_item < S ? per_item : S;
+                for (int q = 0; q < pre; ++q) {
+                    const int kb = q / tap_groups, tg = q - kb * tap_groups;
+                    mbar_expect_tx(&w_full[q], Cfg::kWStage);
+#pragma unroll
+                    for (int tp = 0; tp < TPS; ++tp)
+                        bulk_g2s(sStage + q * Cfg::kWStage + tp * Cfg::kWTap, wt0 + (size_t)((tg * TPS + tp) * kblocks + kb) * Cfg::kWTap,
+                                 Cfg::kWTap, &w_full[q]);
+                }
+            }
+            griddep_wait();                                     // the weights are on their way; now the previous layer's output
             for (int work = blockIdx.x; work < total; work += gridDim.x, ++n) {
                 const int pair = work / p.n_tiles, n_tile = work - pair * p.n_tiles;
                 const long long m0 = (long long)pair * kPairRows;
                 const uint8_t* wt = p.w + (size_t)n_tile * Cfg::kTaps * kblocks * Cfg::kWTap;
                 const int ab = (n % NA) * kblocks;
                 const uint32_t aph = (uint32_t)(n / NA) & 1u;
+                int q = 0;
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(&a_empty[ab + kb], aph ^ 1u);
                     mbar_expect_tx(&a_full[ab + kb], (uint32_t)Cfg::kSeg);
@@ -321,14 +337,16 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(const GemmArgs p,
                                  p.a + ((size_t)(kb * KCH + c) * p.a_rows + (size_t)(p.a_row0 + m0 - kHalo)) * 16, kAPlane,
                                  &a_full[ab + kb]);
                     if (WRES) continue;
-                    for (int tg = 0; tg < tap_groups; ++tg) {
-                        mbar_wait(&w_empty[s], ph ^ 1);
-                        mbar_expect_tx(&w_full[s], Cfg::kWStage);
-                        // host image order is [tap][k_block]: one copy per tap of the stage
+                    for (int tg = 0; tg < tap_groups; ++tg, ++q) {
+                        if (n != 0 || q >= pre) {               // (the first item's first `pre` stages are already in flight)
+                            mbar_wait(&w_empty[s], ph ^ 1);
+                            mbar_expect_tx(&w_full[s], Cfg::kWStage);
+                            // host image order is [tap][k_block]: one copy per tap of the stage
 #pragma unroll
-                        for (int tp = 0; tp < TPS; ++tp)
-                            bulk_g2s(sStage + s * Cfg::kWStage + tp * Cfg::kWTap,
-                                     wt + (size_t)((tg * TPS + tp) * kblocks + kb) * Cfg::kWTap, Cfg::kWTap, &w_full[s]);
+                            for (int tp = 0; tp < TPS; ++tp)
+                                bulk_g2s(sStage + s * Cfg::kWStage + tp * Cfg::kWTap,
+                                         wt + (size_t)((tg * TPS + tp) * kblocks + kb) * Cfg::kWTap, Cfg::kWTap, &w_full[s]);
+                        }
                         if (++s == S) { s = 0; ph ^= 1; }
                     }
                 }
@@ -1375,6 +1393,16 @@ static int net_gemm(xq_ctx* c, const xq_gemm_desc* d, int n_boards_now, const in
     if (d->mode == 0 && d->nt == 128 && d->kch_iter == 8 && d->a_row0 >= kHalo) {
         // 128-channel layers: 3 taps per weight stage (48 KB x 3 stages): a stage hand-off costs an MMA-issuing
         // thread ~0.2 us, so fewer, larger stages beat a finer ring; wider layers only have room for 16 KB stages
+        // A handful of boards (evaluation games, the tail of self-play): what counts is the latency of a layer, and a 512-row
+        // item of a CTA pair is 5.9 us of MMAs whatever the batch.  While every item fits one wave the layer runs as
+        // 256-row x 64-channel items on single CTAs instead (the image tiled by 64 output channels is the CTA pairs' own):
+        // 4x the items, a quarter of the MMA cycles each.
+        if (c->net_small && d->w_half && d->kchunks == 16 && ((a.m_tiles + 1) / 2) * a.n_tiles * 2 <= c->sm_count) {
+            GemmArgs a2 = a;
+            a2.w = a.w_half;
+            a2.n_tiles = a.n_tiles * 2;
+            return launch_conv<64, 8, false, 3, false>(c, a2, s, 8);
+        }
         if (c->net_2cta && d->w_half && d->kchunks % 8 == 0 && d->kchunks <= 32) {
             const int rc = launch_conv2<8, 3>(c, a, s, 7);                             // CTA pairs, cta_group::2
             if (rc != XQ_ERR_CUDA) return rc;
