@@ -1390,6 +1390,9 @@ static int net_gemm(xq_ctx* c, const xq_gemm_desc* d, int n_boards_now, const in
     XqTimer tm(c, s);
     if (d->mode == 2 && d->nt == 224 && d->kch_iter == 8 && d->kchunks % 8 == 0) return launch_fc<FcCfgT<224, 8, 3>>(c, a, s, 0);
     if (d->mode == 2 && d->nt == 128 && d->kch_iter == 8 && d->kchunks % 8 == 0) return launch_fc<FcCfgT<128, 8, 4>>(c, a, s, 1);
+    // plans of at most 256 boards (one pair of row tiles): the layer is the 46 MB of weights, streamed by as many CTAs as there are
+    // column tiles -- 127 tiles of 64 columns instead of 37 of 224 (29 -> ~10 us); the host tiles the image accordingly
+    if (d->mode == 2 && d->nt == 64 && d->kch_iter == 8 && d->kchunks % 8 == 0) return launch_fc<FcCfgT<64, 8, 5>>(c, a, s, 10);
     if (d->mode == 0 && d->nt == 128 && d->kch_iter == 8 && d->a_row0 >= kHalo) {
         // 128-channel layers: 3 taps per weight stage (48 KB x 3 stages): a stage hand-off costs an MMA-issuing
         // thread ~0.2 us, so fewer, larger stages beat a finer ring; wider layers only have room for 16 KB stages

@@ -108,6 +108,8 @@ BOARD_ROWS = 90      # plane rows per board: cell (r, c) of board b at row ROW0 
 TAP_ORDER = [4, 0, 1, 2, 3, 5, 6, 7, 8]   # weight-image tap k -> 3x3 cell kh*3+kw: the (unmasked) centre tap is issued first
 FC_NT = 224          # output columns per FC work item (one N = 224 MMA per tile and K step, csrc/xq_net.cu fc_kernel)
 FC_TILES = 37        # 37 x 224 = 8288 >= 8100
+FC_NT_SMALL = 64     # plans of at most FC_SMALL_BOARDS boards: 127 column tiles of 64, one CTA each (the layer is weight-bound there)
+FC_SMALL_BOARDS = 256
 LOGIT_STRIDE = 8320  # row stride of the logits (>= FC_TILES * FC_NT, multiple of 64 elements)
 
 
@@ -241,13 +243,16 @@ class B200Net:
                                          out2=self.vfeat.data_ptr()))
             # policy FC 2880 -> 8100: torch flatten index ch*90+pos  ->  kernel index pos*32+ch
             wf = m.policy_head[4].weight.detach().float().reshape(ACTION_SPACE, 32, 90).permute(0, 2, 1)
-            wfp = torch.zeros((FC_TILES * FC_NT, 2880), device=dev)
+            fc_nt = FC_NT_SMALL if B <= FC_SMALL_BOARDS else FC_NT
+            fc_tiles = (ACTION_SPACE + fc_nt - 1) // fc_nt
+            assert fc_tiles * fc_nt <= LOGIT_STRIDE
+            wfp = torch.zeros((fc_tiles * fc_nt, 2880), device=dev)
             wfp[:ACTION_SPACE] = wf.reshape(ACTION_SPACE, 2880)
-            bfp = torch.zeros(FC_TILES * FC_NT, device=dev)
+            bfp = torch.zeros(fc_tiles * fc_nt, device=dev)
             bfp[:ACTION_SPACE] = m.policy_head[4].bias.detach().float()
-            img = dev_t(conv_image(wfp.reshape(FC_TILES * FC_NT, 2880, 1, 1), FC_NT, 8))
+            img = dev_t(conv_image(wfp.reshape(fc_tiles * fc_nt, 2880, 1, 1), fc_nt, 8))
             bias = dev_t(bfp, torch.float32)
-            self.layers.append(_GemmDesc(mode=2, m_tiles=self.b_tiles, n_tiles=FC_TILES, nt=FC_NT,
+            self.layers.append(_GemmDesc(mode=2, m_tiles=self.b_tiles, n_tiles=fc_tiles, nt=fc_nt,
                                          kchunks=360, kch_iter=8, relu=0, n_boards=B, a_rows=self.fc_rows, a_row0=0,
                                          out_rows=0, out_row0=0, out_stride=LOGIT_STRIDE, a=self.fc_in.data_ptr(),
                                          w=img.data_ptr(), bias=bias.data_ptr(), residual=None,
