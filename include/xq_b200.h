@@ -286,6 +286,13 @@ typedef struct xq_net_plan {
     int32_t logits_kind;        /* 1 bf16, 2 float32 */
 } xq_net_plan;
 
+/* Optional hint for the self-play / arena loops: an upper bound on the games that are still alive (e.g. target_games -
+ * finished once every game has been started).  The forwards of the following plies are launched for that many boards instead
+ * of one per slot, which selects the small-batch variants of the layers when few games are left (the latency of a forward is
+ * what a lockstep step costs then).  0 = no bound.  A leaf beyond the bound is not evaluated and sets error bit 4 in the
+ * counters; xq_selfplay_reset clears the hint. */
+int xq_selfplay_set_live_bound(xq_ctx* ctx, int32_t max_live_games);
+
 /* sample record (896 bytes): board int8[90] @0, side int8 @90, n_moves uint8 @91, game uid int32 @92,
  * ply int32 @96, action played int16 @100, actions int16[128] @128, visit probabilities float32[128] @384 */
 #define XQ_SAMPLE_BYTES 896

@@ -159,3 +159,40 @@ def test_same_seed_same_games(eng, net_model):
         assert np.array_equal(a[3][k], b[3][k]), k
     sp2, c2, dec2, w2, p2 = play(eng, net_model, cfg, slots=8, games=12, seed=78)
     assert not np.array_equal(np.sort(dec2["played"]), np.sort(a[3]["played"])) or c2["samples"] != a[0]
+
+
+def test_live_bound_changes_the_kernels_not_the_games(eng, net_model):
+    """xq_selfplay_set_live_bound: with a correct upper bound on the live games the forwards are launched for that many
+    boards (small-batch layer variants: 64-channel single-CTA tower items, 64-column FC tiles) and the games are the same
+    records bit for bit; a bound that is too small is reported through the error counter, never silently."""
+    import xq_native
+    from selfplay_engine import SelfPlayEngine, decode_samples
+    cfg = Cfg()
+    cfg.num_simulations = 12
+    cfg.max_game_length = 24
+    cfg.random_opening_moves = 2
+    slots, games = 320, 40                     # a plan of 320 boards (CTA-pair tower, 224-column FC); only 40 games ever play
+
+    def run(bound):
+        sp = SelfPlayEngine(eng, net_model, n_slots=slots, max_games=games)
+        sp.reset()
+        scfg = SelfPlayEngine.make_config(cfg, games, seed=5)
+        if bound:
+            eng._check(eng.L.xq_selfplay_set_live_bound(eng.h, bound))
+        sp.play(scfg, 6)
+        c = sp.counters()
+        raw, winner, plies = sp.fetch(0, c["samples"])
+        dec = decode_samples(raw)
+        order = np.lexsort((dec["ply"], dec["uid"]))
+        return c, {k: dec[k][order] for k in ("board", "side", "n", "actions", "probs", "played", "uid", "ply")}
+
+    c0, d0 = run(0)
+    c1, d1 = run(games)                         # 40 games: every layer on its small-batch variant
+    assert c0["error"] == 0 and c1["error"] == 0 and c0["samples"] == c1["samples"] > 0
+    for k in d0:
+        assert np.array_equal(d0[k], d1[k]), k
+    c2, _ = run(games // 4)                     # wrong: more games are alive than the bound says
+    assert c2["error"] & 4
+    sp = SelfPlayEngine(eng, net_model, n_slots=slots, max_games=games)
+    sp.reset()                                  # reset clears the hint and the error bits
+    assert sp.counters()["error"] == 0

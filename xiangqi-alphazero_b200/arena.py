@@ -68,6 +68,8 @@ class Arena:
                 raise xq_native.XqError(f"arena device error bits {c['error']}")
             if c["finished"] >= self.num_games:
                 break
+            # every arena game starts at ply 0: the games still alive are the unfinished ones (forwards sized to them)
+            e._check(e.L.xq_selfplay_set_live_bound(e.h, max(1, self.num_games - c["finished"])))
         _, winner, plies = sp.fetch(0, 0)
         winner, plies = winner[:self.num_games], plies[:self.num_games]
         new_is_red = (np.arange(self.num_games) % 2) == 0

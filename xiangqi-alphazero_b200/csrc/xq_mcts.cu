@@ -778,6 +778,7 @@ struct SpState {
     int16_t* res_plies = nullptr;   // [max_games_total]
     uint8_t* samples = nullptr;     // [sample_cap][kSampleBytes]
     unsigned long long ply_counter = 0;   // host side: plies played since reset (RNG stream index)
+    int live_bound = 0;                   // host side: upper bound on the games still alive (0 = unknown: the slot count), xq_selfplay_set_live_bound
 };
 
 __device__ __forceinline__ void warp_store_game(const MctsState& M, int g, const int8_t* b, const int8_t* ring, const GameMeta& gm,
@@ -901,6 +902,7 @@ struct StepArgs {
     EvalPort port[2];
     int arena;
     int K;                  // leaf slots per game and step (1 = the reference's one simulation at a time)
+    int bound;              // rows the forwards of this step are sized for (the caller's upper bound on live games x K); a row beyond it sets error bit 4
 };
 
 __device__ __forceinline__ int sp_port_of(const SpState& P, const StepArgs& A, int g, int root_side)
@@ -945,6 +947,7 @@ __global__ void __launch_bounds__(kSelWarps * 32) sp_root_begin_kernel(MctsState
     int row = 0;
     if (lane == 0) {
         row = atomicAdd(&M.n_eval[port], 1);       // every playing root is evaluated: the resign probe reads its value
+        if (row >= A.bound) atomicOr(M.error, 4);   // the host's live-games bound was wrong: this leaf is not evaluated
         M.root_winner[g] = rw;
         M.leaf_n[slot] = n;
         M.leaf_node[slot] = g;
@@ -1149,6 +1152,7 @@ __global__ void __launch_bounds__(kSelWarps * 32) mcts_select_multi_kernel(MctsS
         int row = 0;
         if (lane == 0) {
             row = atomicAdd(&M.n_eval[port], 1);
+            if (row >= A.bound) atomicOr(M.error, 4);   // the host's live-games bound was wrong: this leaf is not evaluated
             M.leaf_state[slot] = kLeafEval;
             M.leaf_node[slot] = node;
             M.leaf_n[slot] = min(r.n_legal, kMaxMoves);
@@ -1348,6 +1352,7 @@ extern "C" int xq_selfplay_reset(xq_ctx* c, void* stream)
     XQ_CUDA(c, cudaMemsetAsync(S_(c)->stats, 0, 4 * sizeof(int64_t), s));
     XQ_CUDA(c, cudaMemsetAsync(S_(c)->error, 0, sizeof(int), s));
     P->ply_counter = 0;
+    P->live_bound = 0;
     return XQ_OK;
 }
 
@@ -1383,6 +1388,13 @@ static int sp_play_loop(xq_ctx* c, MctsState& M, SpState& P, const SpConfig& k, 
     A.port[1] = port_of(net1 ? net1 : net0);
     A.arena = net1 ? 1 : 0;
     A.K = K;
+    // Forward launches are sized (grid, kernel variant) for `rows` boards and cut to the live count on the device.  Late in an
+    // iteration few games are alive and what counts is the latency of a forward: with the caller's bound on the live games
+    // the small-batch variants of the layers are chosen (xq_net.cu) instead of the ones sized for every slot.
+    long long rows_ll = (long long)(P.live_bound > 0 && P.live_bound < M.n_games ? P.live_bound : M.n_games) * K;
+    const int rows0 = (int)(rows_ll < net0->batch ? rows_ll : net0->batch);
+    const int rows1 = net1 ? (int)(rows_ll < net1->batch ? rows_ll : net1->batch) : 0;
+    A.bound = rows0;
     const int kind = net0->logits_kind;
     const int nb = blocks_for(M.n_games), nt = kSelWarps * 32;
     const int steps = (k.num_simulations + K - 1) / K;
@@ -1397,19 +1409,19 @@ static int sp_play_loop(xq_ctx* c, MctsState& M, SpState& P, const SpConfig& k, 
             XQ_CUDA(c, cudaEventRecord(ev_fork, s));
             XQ_CUDA(c, cudaStreamWaitEvent(side, ev_fork, 0));
             int rc1 = xq_net_run_counted(c, net1->layers, net1->n_layers, net1->vfeats, net1->w1t, net1->b1, net1->w2, net1->b2,
-                                         net1->value, M.n_eval + 1, net1->batch, (void*)side);
+                                         net1->value, M.n_eval + 1, rows1, (void*)side);
             if (rc1) return rc1;
             XQ_CUDA(c, cudaEventRecord(ev_join, side));
         }
         int rc = xq_net_run_counted(c, net0->layers, net0->n_layers, net0->vfeats, net0->w1t, net0->b1, net0->w2, net0->b2, net0->value,
-                                    M.n_eval + 0, net0->batch, (void*)s);
+                                    M.n_eval + 0, rows0, (void*)s);
         if (rc || !net1) return rc;
         if (side) {
             XQ_CUDA(c, cudaStreamWaitEvent(s, ev_join, 0));
             return XQ_OK;
         }
         return xq_net_run_counted(c, net1->layers, net1->n_layers, net1->vfeats, net1->w1t, net1->b1, net1->w2, net1->b2, net1->value,
-                                  M.n_eval + 1, net1->batch, (void*)s);
+                                  M.n_eval + 1, rows1, (void*)s);
     };
     for (int ply = 0; ply < n_plies; ++ply) {
         const unsigned long long pi = P.ply_counter++;
@@ -1436,6 +1448,14 @@ static int sp_play_loop(xq_ctx* c, MctsState& M, SpState& P, const SpConfig& k, 
         c->launches += 1;
         XQ_CUDA(c, cudaGetLastError());
     }
+    return XQ_OK;
+}
+
+extern "C" int xq_selfplay_set_live_bound(xq_ctx* c, int max_live_games)
+{
+    SpState* Pp = c ? SP_(c) : nullptr;
+    if (!Pp) return xq_fail(c, XQ_ERR_STATE, "xq_selfplay_set_live_bound: call xq_selfplay_create first");
+    Pp->live_bound = max_live_games > 0 ? max_live_games : 0;
     return XQ_OK;
 }
 

@@ -1388,7 +1388,16 @@ static int net_gemm(xq_ctx* c, const xq_gemm_desc* d, int n_boards_now, const in
     a.n_dev = n_dev;
     XQ_CUDA(c, cudaSetDevice(c->device));
     XqTimer tm(c, s);
-    if (d->mode == 2 && d->nt == 224 && d->kch_iter == 8 && d->kchunks % 8 == 0) return launch_fc<FcCfgT<224, 8, 3>>(c, a, s, 0);
+    if (d->mode == 2 && d->nt == 224 && d->kch_iter == 8 && d->kchunks % 8 == 0) {
+        if (c->net_small && d->w_half && a.n_boards <= 256) {      // a launch bounded to a few boards: the 64-column tiling (below)
+            GemmArgs a2 = a;
+            a2.w = a.w_half;
+            a2.n_tiles = (d->n_tiles * 224) / 64;                  // the bias vector and the logit rows are the 224-tiling's, 8288 >= 127 x 64 + ...
+            if (a2.n_tiles > 127) a2.n_tiles = 127;                // 127 x 64 = 8128 >= 8100 logits
+            return launch_fc<FcCfgT<64, 8, 5>>(c, a2, s, 10);
+        }
+        return launch_fc<FcCfgT<224, 8, 3>>(c, a, s, 0);
+    }
     if (d->mode == 2 && d->nt == 128 && d->kch_iter == 8 && d->kchunks % 8 == 0) return launch_fc<FcCfgT<128, 8, 4>>(c, a, s, 1);
     // plans of at most 256 boards (one pair of row tiles): the layer is the 46 MB of weights, streamed by as many CTAs as there are
     // column tiles -- 127 tiles of 64 columns instead of 37 of 224 (29 -> ~10 us); the host tiles the image accordingly

@@ -252,11 +252,20 @@ class B200Net:
             bfp[:ACTION_SPACE] = m.policy_head[4].bias.detach().float()
             img = dev_t(conv_image(wfp.reshape(fc_tiles * fc_nt, 2880, 1, 1), fc_nt, 8))
             bias = dev_t(bfp, torch.float32)
+            # big plans also carry the image tiled by 64 columns: launches bounded to a few live boards (the tail of an
+            # iteration, xq_selfplay_set_live_bound) run the weight-bound layer on 127 CTAs instead of 37
+            img_small = None
+            if fc_nt != FC_NT_SMALL:
+                ts = (ACTION_SPACE + FC_NT_SMALL - 1) // FC_NT_SMALL
+                ws = torch.zeros((ts * FC_NT_SMALL, 2880), device=dev)
+                ws[:ACTION_SPACE] = wf.reshape(ACTION_SPACE, 2880)
+                img_small = dev_t(conv_image(ws.reshape(ts * FC_NT_SMALL, 2880, 1, 1), FC_NT_SMALL, 8))
             self.layers.append(_GemmDesc(mode=2, m_tiles=self.b_tiles, n_tiles=fc_tiles, nt=fc_nt,
                                          kchunks=360, kch_iter=8, relu=0, n_boards=B, a_rows=self.fc_rows, a_row0=0,
                                          out_rows=0, out_row0=0, out_stride=LOGIT_STRIDE, a=self.fc_in.data_ptr(),
                                          w=img.data_ptr(), bias=bias.data_ptr(), residual=None,
-                                         out=self.logits.data_ptr(), out2=None))
+                                         out=self.logits.data_ptr(), out2=None,
+                                         w_half=None if img_small is None else img_small.data_ptr()))
             # value MLP: k = ch*90+pos -> pos*4+ch, stored transposed [360][128]
             w1 = m.value_head[4].weight.detach().float().reshape(128, 4, 90).permute(2, 1, 0).reshape(360, 128)
             self.w1t = dev_t(w1, torch.float32)

@@ -184,6 +184,10 @@ class SelfPlayEngine:
             if c["finished"] >= min(cfg.target_games, self.max_games):
                 break
             tail = c["started"] >= min(cfg.target_games, self.max_games)
+            if tail:
+                # no game will be started any more: the games still alive are at most the ones that have not finished; the
+                # next ply's forwards are launched for that many boards (small-batch layer variants late in an iteration)
+                self.e._check(self.e.L.xq_selfplay_set_live_bound(self.e.h, max(1, min(cfg.target_games, self.max_games) - c["finished"])))
             if c["finished"] != last_finished:
                 last_finished, last_progress = c["finished"], played
             elif played - last_progress > 2 * 201 + 64:      # no game can last this long (game.py:595: 200 plies)

@@ -93,6 +93,7 @@ def lib():
     _sig(L, "xq_selfplay_create", i32, vp, i32, i32, i64, i64)
     _sig(L, "xq_selfplay_reset", i32, vp, vp)
     _sig(L, "xq_selfplay_play", i32, vp, vp, vp, i32, vp)
+    _sig(L, "xq_selfplay_set_live_bound", i32, vp, i32)
     _sig(L, "xq_selfplay_counters", i32, vp, C.POINTER(i64))
     _sig(L, "xq_selfplay_fetch", i32, vp, i64, i64, vp, vp, vp, i32)
     _sig(L, "xq_selfplay_slots", i32, vp, vp, vp, vp, vp)
@@ -134,7 +135,7 @@ EXPORTS = ["xq_create", "xq_destroy", "xq_last_error", "xq_version", "xq_launch_
            "xq_mcts_create", "xq_mcts_set_games", "xq_mcts_root_begin", "xq_mcts_root_expand", "xq_mcts_select",
            "xq_mcts_expand_backup", "xq_mcts_leaf_info", "xq_mcts_root_visits", "xq_mcts_root_priors", "xq_mcts_stats",
            "xq_net_gemm", "xq_net_value_head", "xq_net_run", "xq_net_run_counted", "xq_selfplay_create", "xq_selfplay_reset",
-           "xq_selfplay_play", "xq_selfplay_counters", "xq_selfplay_fetch", "xq_selfplay_slots",
+           "xq_selfplay_play", "xq_selfplay_set_live_bound", "xq_selfplay_counters", "xq_selfplay_fetch", "xq_selfplay_slots",
            "xq_selfplay_device_buffers", "xq_arena_play", "xq_replay_append", "xq_train_batch", "xq_policy_value_loss",
            "xq_grad_sumsq", "xq_adam_step", "xq_peer_create", "xq_peer_connect", "xq_bn_forward", "xq_bn_backward",
            "xq_tgemm", "xq_twgrad", "xq_tn_input", "xq_tn_wimage", "xq_tn_wimage_batch", "xq_tn_bn_forward", "xq_tn_bn_backward", "xq_tn_wgrad_reduce",
