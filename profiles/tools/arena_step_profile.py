@@ -25,10 +25,14 @@ def play(k):
     eng._check(eng.L.xq_arena_play(eng.h, C.byref(cfg), C.byref(ar.plan_new), C.byref(ar.plan_old), k, ar.move_log.data_ptr(), eng._stream()))
 play(2)
 torch.cuda.synchronize()
+import time
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
+t0 = time.perf_counter()
 play(plies)
+host_ms = (time.perf_counter() - t0) * 1e3          # time the host needs to ENQUEUE the plies (no synchronisation inside)
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1)
-print(f"{plies} plies x 101 lockstep steps of 32 games: {ms:.1f} ms = {ms / plies / 101 * 1000:.1f} us per step")
+print(f"{plies} plies x 101 lockstep steps of 32 games: {ms:.1f} ms = {ms / plies / 101 * 1000:.1f} us per step on the device; "
+      f"the host enqueues them in {host_ms:.1f} ms = {host_ms / plies / 101 * 1000:.1f} us per step")

@@ -196,3 +196,23 @@ def test_live_bound_changes_the_kernels_not_the_games(eng, net_model):
     sp = SelfPlayEngine(eng, net_model, n_slots=slots, max_games=games)
     sp.reset()                                  # reset clears the hint and the error bits
     assert sp.counters()["error"] == 0
+
+
+def test_graph_replay_dependent_launches_and_small_variants_do_not_change_the_games():
+    """The lockstep step replayed from a CUDA graph, programmatic dependent launches and the small-batch layer variants are
+    scheduling choices: a seeded self-play run + arena produce the same records and moves with each of them switched off."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    digests = {}
+    for name, env in (("default", {}), ("no_graph", {"XQ_SP_GRAPH": "0"}), ("no_pdl", {"XQ_NET_PDL": "0"}),
+                      ("no_small", {"XQ_NET_SMALL": "0"})):
+        e = dict(os.environ)
+        e.update(env)
+        out = subprocess.run([sys.executable, os.path.join(here, "sp_hash_script.py")], capture_output=True, text=True, timeout=600, env=e)
+        assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-3000:]
+        line = [l for l in out.stdout.splitlines() if l.startswith("SP_DIGEST")][-1].split()
+        assert int(line[3]) == 0 and int(line[1]) > 0
+        digests[name] = line[1:]
+    assert digests["default"] == digests["no_graph"] == digests["no_pdl"] == digests["no_small"], digests

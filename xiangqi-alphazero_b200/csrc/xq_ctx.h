@@ -34,6 +34,7 @@ struct xq_ctx {
     bool net_fork = false;                // XQ_NET_FORK=1: value MLP on a side stream next to the policy FC (measured: 1.002 ms per forward against
                                           // 0.976 ms in sequence -- the co-running CTAs slow the FC more than the 19 us they hide; off)
     bool net_2cta = true;                 // XQ_NET_2CTA=0 (read once in xq_create): tower convs on the single-CTA kernel instead of CTA pairs
+    bool sp_graph = true;                 // XQ_SP_GRAPH=0: the lockstep step of the self-play / arena loops is issued launch by launch (no CUDA graph)
     bool net_small = true;                // XQ_NET_SMALL=0: no 64-channel single-CTA items for tower layers whose work fits one wave (small batches)
     bool net_pdl = true;                  // XQ_NET_PDL=0 (read once in xq_create): no programmatic dependent launch between the tower's layers
     bool train_pdl = false;               // XQ_TRAIN_PDL=1: the same for the kernels of the training step (xq_tnet.cu).  Measured inside the

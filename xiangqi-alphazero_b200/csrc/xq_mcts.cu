@@ -779,6 +779,12 @@ struct SpState {
     uint8_t* samples = nullptr;     // [sample_cap][kSampleBytes]
     unsigned long long ply_counter = 0;   // host side: plies played since reset (RNG stream index)
     int live_bound = 0;                   // host side: upper bound on the games still alive (0 = unknown: the slot count), xq_selfplay_set_live_bound
+    // host side: the lockstep step (select -> forward(s) -> expand/backup) as an instantiated CUDA graph, rebuilt when anything
+    // that is baked into it changes (sp_play_loop)
+    cudaStream_t cap_stream = nullptr;
+    cudaGraphExec_t step_exec = nullptr;
+    unsigned long long step_key = 0;
+    long long step_launches = 0;
 };
 
 __device__ __forceinline__ void warp_store_game(const MctsState& M, int g, const int8_t* b, const int8_t* ring, const GameMeta& gm,
@@ -1300,6 +1306,16 @@ sp_end_move_kernel(MctsState M, SpState P, SpConfig cfg, unsigned long long ply_
 
 static SpState* SP_(xq_ctx* c) { return reinterpret_cast<SpState*>(c->selfplay); }
 
+static void sp_drop_step_graph(SpState* P)
+{
+    if (P->step_exec) {
+        cudaDeviceSynchronize();                // no replay may be in flight when the executable graph goes
+        cudaGraphExecDestroy(P->step_exec);
+        P->step_exec = nullptr;
+    }
+    P->step_key = 0;
+}
+
 extern "C" void xq_selfplay_free_(xq_ctx* c)
 {
     SpState* P = SP_(c);
@@ -1307,6 +1323,8 @@ extern "C" void xq_selfplay_free_(xq_ctx* c)
     void* ptrs[] = {P->status, P->n_samples, P->resign_run, P->game_uid, P->counters, P->res_winner, P->res_plies, P->samples};
     for (void* p : ptrs)
         if (p) cudaFree(p);
+    sp_drop_step_graph(P);
+    if (P->cap_stream) cudaStreamDestroy(P->cap_stream);
     delete P;
     c->selfplay = nullptr;
 }
@@ -1404,9 +1422,9 @@ static int sp_play_loop(xq_ctx* c, MctsState& M, SpState& P, const SpConfig& k, 
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     if (net1 && !c->net_fork)
         if (int rc = xq_net_side_stream_(c, &side, &ev_fork, &ev_join)) return rc;
-    auto run_nets = [&]() -> int {
+    auto run_nets = [&](cudaStream_t q) -> int {
         if (net1 && side) {
-            XQ_CUDA(c, cudaEventRecord(ev_fork, s));
+            XQ_CUDA(c, cudaEventRecord(ev_fork, q));
             XQ_CUDA(c, cudaStreamWaitEvent(side, ev_fork, 0));
             int rc1 = xq_net_run_counted(c, net1->layers, net1->n_layers, net1->vfeats, net1->w1t, net1->b1, net1->w2, net1->b2,
                                          net1->value, M.n_eval + 1, rows1, (void*)side);
@@ -1414,14 +1432,71 @@ static int sp_play_loop(xq_ctx* c, MctsState& M, SpState& P, const SpConfig& k, 
             XQ_CUDA(c, cudaEventRecord(ev_join, side));
         }
         int rc = xq_net_run_counted(c, net0->layers, net0->n_layers, net0->vfeats, net0->w1t, net0->b1, net0->w2, net0->b2, net0->value,
-                                    M.n_eval + 0, rows0, (void*)s);
+                                    M.n_eval + 0, rows0, (void*)q);
         if (rc || !net1) return rc;
         if (side) {
-            XQ_CUDA(c, cudaStreamWaitEvent(s, ev_join, 0));
+            XQ_CUDA(c, cudaStreamWaitEvent(q, ev_join, 0));
             return XQ_OK;
         }
         return xq_net_run_counted(c, net1->layers, net1->n_layers, net1->vfeats, net1->w1t, net1->b1, net1->w2, net1->b2, net1->value,
-                                  M.n_eval + 1, rows1, (void*)s);
+                                  M.n_eval + 1, rows1, (void*)q);
+    };
+    // one lockstep step: every game selects a leaf (or K), the live leaves are evaluated, every game expands and backs up
+    auto enqueue_step = [&](cudaStream_t q) -> int {
+        XQ_CUDA(c, cudaMemsetAsync(M.n_eval, 0, 2 * sizeof(int), q));
+        mcts_select_multi_kernel<<<nb, nt, 0, q>>>(M, P, (double)k.c_puct, A);
+        int rc = run_nets(q);
+        if (rc) return rc;
+        if (kind == 1) mcts_expand_backup_multi_kernel<1><<<nb, nt, 0, q>>>(M, P, A);
+        else mcts_expand_backup_multi_kernel<2><<<nb, nt, 0, q>>>(M, P, A);
+        c->launches += 2;
+        return XQ_OK;
+    };
+    // With up to ~1000 boards per forward a step is 25-45 launches of kernels that take a few microseconds each, and the host
+    // needs as long to issue them as the device to run them (arena, 32 games: 162 us of enqueue against 174 us on the device).
+    // The step is therefore captured once -- on a private stream: the caller's may be the legacy default stream, which cannot
+    // capture -- and replayed num_simulations times per ply.  Everything baked into the graph is in the key; the capture
+    // happens after the first eager forward of the call, which has done every one-time initialisation.
+    const bool want_graph = c->sp_graph && !c->timing && rows0 <= 1024 && steps >= 8;
+    unsigned long long key = 0;
+    if (want_graph) {
+        auto mix = [&](unsigned long long v) { key = (key ^ v) * 0x9E3779B97F4A7C15ull + 0x7F4A7C15ull; };
+        mix((unsigned long long)rows0); mix((unsigned long long)rows1); mix((unsigned long long)K); mix((unsigned long long)kind);
+        mix((unsigned long long)M.n_games); mix((unsigned long long)(uintptr_t)net0->layers); mix((unsigned long long)(uintptr_t)net0->value);
+        mix((unsigned long long)(uintptr_t)(net1 ? net1->layers : nullptr)); mix((unsigned long long)(uintptr_t)(net1 ? net1->value : nullptr));
+        mix((unsigned long long)(uintptr_t)net0->logits); mix((unsigned long long)net0->n_layers); mix((unsigned long long)net0->batch);
+        mix((unsigned long long)(uintptr_t)M.leaf_state); mix((unsigned long long)(uintptr_t)M.leaf_row); mix((unsigned long long)(uintptr_t)M.n_eval);
+        double cp = (double)k.c_puct;
+        unsigned long long cpb;
+        memcpy(&cpb, &cp, sizeof(cpb));
+        mix(cpb); mix((unsigned long long)(uintptr_t)M.hot); mix((unsigned long long)(uintptr_t)P.status); mix((unsigned long long)(uintptr_t)s);
+        key |= 1ull;
+        if (P.step_key != key) sp_drop_step_graph(&P);
+    } else {
+        sp_drop_step_graph(&P);
+    }
+    auto capture_step = [&]() -> int {
+        if (!P.cap_stream) XQ_CUDA(c, cudaStreamCreateWithFlags(&P.cap_stream, cudaStreamNonBlocking));
+        const long long l0 = c->launches;
+        XQ_CUDA(c, cudaStreamBeginCapture(P.cap_stream, cudaStreamCaptureModeThreadLocal));
+        const int rc = enqueue_step(P.cap_stream);
+        cudaGraph_t g = nullptr;
+        const cudaError_t e_end = cudaStreamEndCapture(P.cap_stream, &g);
+        P.step_launches = c->launches - l0;
+        c->launches = l0;                                       // nothing ran: replays add the count
+        if (rc || e_end != cudaSuccess || !g) {
+            if (g) cudaGraphDestroy(g);
+            (void)cudaGetLastError();
+            return rc ? rc : xq_fail(c, XQ_ERR_CUDA, "capture of the lockstep step failed: %s", cudaGetErrorString(e_end));
+        }
+        const cudaError_t e_inst = cudaGraphInstantiate(&P.step_exec, g, 0);
+        cudaGraphDestroy(g);
+        if (e_inst != cudaSuccess) {
+            P.step_exec = nullptr;
+            return xq_fail(c, XQ_ERR_CUDA, "instantiation of the lockstep step graph failed: %s", cudaGetErrorString(e_inst));
+        }
+        P.step_key = key;
+        return XQ_OK;
     };
     for (int ply = 0; ply < n_plies; ++ply) {
         const unsigned long long pi = P.ply_counter++;
@@ -1430,19 +1505,27 @@ static int sp_play_loop(xq_ctx* c, MctsState& M, SpState& P, const SpConfig& k, 
         XQ_CUDA(c, cudaMemsetAsync(M.n_eval, 0, 2 * sizeof(int), s));
         sp_root_begin_kernel<<<nb, nt, 0, s>>>(M, P, A);
         c->launches += 3;
-        int rc = run_nets();
+        int rc = run_nets(s);
         if (rc) return rc;
         if (kind == 1) sp_after_root_kernel<1><<<nb, nt, 0, s>>>(M, P, k, A, pi);
         else sp_after_root_kernel<2><<<nb, nt, 0, s>>>(M, P, k, A, pi);
         c->launches += 1;
+        if (want_graph && !P.step_exec) {
+            rc = capture_step();
+            if (rc) {                                           // a driver that cannot capture this step: issue it launch by launch
+                fprintf(stderr, "[xq_b200] %s: the lockstep step runs without a CUDA graph\n", c->err);
+                c->sp_graph = false;
+                sp_drop_step_graph(&P);
+            }
+        }
         for (int step = 0; step < steps; ++step) {
-            XQ_CUDA(c, cudaMemsetAsync(M.n_eval, 0, 2 * sizeof(int), s));
-            mcts_select_multi_kernel<<<nb, nt, 0, s>>>(M, P, (double)k.c_puct, A);
-            rc = run_nets();
-            if (rc) return rc;
-            if (kind == 1) mcts_expand_backup_multi_kernel<1><<<nb, nt, 0, s>>>(M, P, A);
-            else mcts_expand_backup_multi_kernel<2><<<nb, nt, 0, s>>>(M, P, A);
-            c->launches += 2;
+            if (P.step_exec && c->sp_graph) {
+                XQ_CUDA(c, cudaGraphLaunch(P.step_exec, s));
+                c->launches += P.step_launches;
+            } else {
+                rc = enqueue_step(s);
+                if (rc) return rc;
+            }
         }
         sp_end_move_kernel<<<nb, nt, 0, s>>>(M, P, k, pi);
         c->launches += 1;

@@ -562,6 +562,7 @@ extern "C" int xq_create(int device, xq_ctx** out)
     if (const char* e = getenv("XQ_NET_2CTA")) c->net_2cta = atoi(e) != 0;
     if (const char* e = getenv("XQ_NET_PDL")) c->net_pdl = atoi(e) != 0;
     if (const char* e = getenv("XQ_NET_SMALL")) c->net_small = atoi(e) != 0;
+    if (const char* e = getenv("XQ_SP_GRAPH")) c->sp_graph = atoi(e) != 0;
     if (const char* e = getenv("XQ_TRAIN_PDL")) c->train_pdl = atoi(e) != 0;
     if (const char* e = getenv("XQ_NET_FORK")) c->net_fork = atoi(e) != 0;
     XQ_CUDA(c, cudaSetDevice(device));
