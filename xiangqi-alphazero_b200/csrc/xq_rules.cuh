@@ -114,6 +114,17 @@ static __device__ __noinline__ int warp_argmax_first(double best, int best_i)
     return best_i;
 }
 
+// 16 bytes from lane `src` to every lane (non-inlined, __syncwarp first: see the note on warp collectives in DESIGN.md)
+static __device__ __noinline__ uint4 warp_bcast16(uint4 v, int src)
+{
+    __syncwarp();
+    v.x = __shfl_sync(kFullMask, v.x, src);
+    v.y = __shfl_sync(kFullMask, v.y, src);
+    v.z = __shfl_sync(kFullMask, v.z, src);
+    v.w = __shfl_sync(kFullMask, v.w, src);
+    return v;
+}
+
 struct alignas(16) WarpScratch {
     uint16_t pm[kMaxPseudo];      // pseudo-legal moves in reference order: from << 7 | to
     int16_t actions[kMaxMoves];   // compacted legal actions, unused slots = -1
