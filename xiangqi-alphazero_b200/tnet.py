@@ -276,10 +276,19 @@ class HandStep:
         self.bn_steps = 0        # num_batches_tracked is brought up to date by sync_counters()
 
     # ---- pieces ----------------------------------------------------------------------------------------------
+    MAX_BUFFER_SETS = 3      # the full minibatch, the shorter last minibatch of an epoch, one spare (a set is ~0.9 GB at 256 x 128 channels)
+
     def buffers(self, B):
-        b = self._bufs.get(B)
+        """The buffer set (and captured graph) of minibatch size B, most recently used last.  The last minibatch of an epoch
+        changes size as the replay buffer grows: only MAX_BUFFER_SETS sets are kept, the least recently used one is dropped."""
+        b = self._bufs.pop(B, None)
         if b is None:
-            b = self._bufs[B] = _StepBuffers(self.dev, B, self.C, self.L)
+            while len(self._bufs) >= self.MAX_BUFFER_SETS:
+                old = self._bufs.pop(next(iter(self._bufs)))
+                old.graph = None                     # the graph references the set's tensors: drop it first
+                del old
+            b = _StepBuffers(self.dev, B, self.C, self.L)
+        self._bufs[B] = b
         return b
 
     def _image_items(self):
