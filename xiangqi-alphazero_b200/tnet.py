@@ -285,6 +285,8 @@ class HandStep:
         if b is None:
             while len(self._bufs) >= self.MAX_BUFFER_SETS:
                 old = self._bufs.pop(next(iter(self._bufs)))
+                if old.graph is not None:
+                    torch.cuda.synchronize()         # no replay of it may be in flight (happens once per epoch at most)
                 old.graph = None                     # the graph references the set's tensors: drop it first
                 del old
             b = _StepBuffers(self.dev, B, self.C, self.L)
