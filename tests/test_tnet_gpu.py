@@ -433,3 +433,39 @@ def test_hand_step_matches_torch_autograd(eng, B, blocks, width):
         cos.append(float((p.grad * q.grad).sum() / (p.grad.norm() * q.grad.norm()).clamp_min(1e-30)))
     print(f"unpinned module: smallest gradient cosine {min(cos):.5f}")
     assert min(cos) > 0.98
+
+
+def test_hand_step_buffer_sets_are_bounded(eng):
+    """The last minibatch of an epoch changes size from iteration to iteration: HandStep keeps three buffer sets (and their
+    captured graphs) and a size that comes back after its set was dropped gives the same gradients again."""
+    import torch
+    import model as M
+    import tnet as T
+    torch.manual_seed(9)
+    dev = eng.dev
+    net = M.XiangqiNet(64, 1).to(dev).train()
+    for p in net.parameters():
+        p.grad = torch.zeros_like(p)
+    hs = T.HandStep(eng, net)
+
+    def batch(B):
+        g = torch.Generator(device=dev).manual_seed(B)
+        st = (torch.rand(B, 15, 10, 9, device=dev, generator=g) > 0.8).float()
+        act = torch.zeros((B, 128), dtype=torch.int16, device=dev)
+        prob = torch.zeros((B, 128), device=dev)
+        act[:, :2] = torch.tensor([17, 4000], dtype=torch.int16, device=dev)
+        prob[:, :2] = torch.tensor([0.75, 0.25], device=dev)
+        n = torch.full((B,), 2, dtype=torch.int32, device=dev)
+        z = torch.ones(B, device=dev)
+        return st, act, prob, n, z
+
+    first = None
+    for B in (4, 5, 4, 6, 7, 8, 4):
+        hs.step(*batch(B), 1.0 / B)
+        torch.cuda.synchronize()
+        assert len(hs._bufs) <= T.HandStep.MAX_BUFFER_SETS
+        if B == 4:
+            g = torch.cat([p.grad.reshape(-1) for p in net.parameters()]).clone()
+            assert first is None or torch.equal(g, first)       # eager, replayed, and rebuilt after eviction: the same gradients
+            first = g
+    assert list(hs._bufs) == [7, 8, 4]
