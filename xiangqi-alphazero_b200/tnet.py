@@ -1,9 +1,13 @@
-"""Host side of the hand-written training step (csrc/xq_tnet.cu): the training plane layout, weight images and the
-descriptors of the two tcgen05 tf32 kernels (xq_tgemm: fprop / dgrad, xq_twgrad: weight gradients).
+"""Host side of the hand-written training step (csrc/xq_tnet.cu, f1 of SURVEY 8(f)): `HandStep` runs forward + loss +
+backward of XiangqiNet (train.py:397-423 over model.py:39-107) on the kernels of libxq_b200.so and replays the ~140 launches
+of a step from a CUDA graph.  This module holds the training plane layout, the weight images, the descriptors of the two
+tcgen05 tf32 kernels (xq_tgemm: fprop / dgrad, xq_twgrad: weight gradients), torch restatements of the layouts for the tests,
+and the orchestration of the step.
 
 Training plane layout (include/xq_b200.h): float32 X[C/4][rows][4]; board b, cell (r, c) at row ROW0 + b*110 + r*10 + c.
 Every board row carries a zero pad column (c = 9) and every board a zero pad row (r = 10): a 3x3 tap (dy, dx) is a row shift
-of dy*10+dx and the pad cells are conv2d's zero padding (train.py:397-423 over model.py:39-107)."""
+of dy*10+dx and the pad cells are conv2d's zero padding.  G layout: float32 G[C/32][rows][32], the 32-byte units of row r
+XOR-swizzled by r & 3 -- the form in which the tf32 tensor core takes the MN-major operands of a weight gradient."""
 import ctypes as C
 import os
 
