@@ -51,7 +51,7 @@ class Arena:
     def play(self, num_simulations: int, c_puct: float, max_game_length: int, chunk: int = 8):
         """-> dict(new_wins, old_wins, draws, winners int8[num_games], plies int16[num_games], moves int16[num_games,201])."""
         sp, e = self.sp, self.e
-        sp.reset()
+        sp.reset()                                     # also clears a live-games bound left by an earlier run
         self.move_log.fill_(-1)
         cfg = SelfPlayEngine.make_config(dict(num_simulations=num_simulations, c_puct=c_puct, max_game_length=max_game_length,
                                               random_opening_moves=0, enable_resign=False), self.num_games, seed=0,

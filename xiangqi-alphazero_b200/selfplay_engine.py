@@ -172,6 +172,7 @@ class SelfPlayEngine:
         played = 0
         last_finished, last_progress = -1, 0
         tail = False
+        self.e._check(self.e.L.xq_selfplay_set_live_bound(self.e.h, 0))     # a bound left by an earlier call does not hold for this one
         while played < max_plies:
             # once every game has been started the loop is in its tail: ask after every ply, so that no ply of
             # num_simulations lockstep steps is enqueued for slots that have all finished
