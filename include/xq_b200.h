@@ -465,6 +465,10 @@ int xq_tn_input(xq_ctx* ctx, const float* x, int32_t n_boards, int32_t channels,
  * k = ci (fprop); 1: n = ci, k = co (dgrad).  Positions without a weight are left untouched (allocate the image zeroed). */
 int xq_tn_wimage(xq_ctx* ctx, const float* w, int32_t co, int32_t ci, int32_t taps, float* img, int32_t img_kb, int32_t n0,
                  int32_t k0, int32_t transposed, void* stream);
+/* Both images of a dense layer's weight w[co][ci] (ci a multiple of 32) in one pass over it: img (n = co, k = ci, fprop) and
+ * img_t (n = ci, k = co, dgrad). */
+int xq_tn_wimage_dense2(xq_ctx* ctx, const float* w, int32_t co, int32_t ci, float* img, int32_t img_kb, float* img_t,
+                        int32_t img_t_kb, void* stream);
 /* The same for many small weight tensors in one launch per 32 items (the 3x3 and 1x1 convolutions of a step). */
 typedef struct xq_tn_wimage_item {
     const float* w;

@@ -201,6 +201,9 @@ def test_layout_writers_and_weight_images_are_exact(eng):
     eng._check(L.xq_tn_wimage(eng.h, wd.data_ptr(), 8100, 2880, 1, img_t.data_ptr(), 254, 0, 0, 1, s()))
     assert torch.equal(img, T.weight_image(wd, img_nt=64, img_kb=90))
     assert torch.equal(img_t, T.weight_image(wd.t().contiguous(), img_nt=23, img_kb=254))
+    img2, img2_t = torch.zeros_like(img), torch.zeros_like(img_t)          # both images from one pass over the weight
+    eng._check(L.xq_tn_wimage_dense2(eng.h, wd.data_ptr(), 8100, 2880, img2.data_ptr(), 90, img2_t.data_ptr(), 254, s()))
+    assert torch.equal(img2, img) and torch.equal(img2_t, img_t)
     # flatten / unflatten
     a = _noise(B, 36, 10, 9, dev=dev)
     ap = T.to_planes(a, rows, chunks=16)

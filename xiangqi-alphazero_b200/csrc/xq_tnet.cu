@@ -209,6 +209,16 @@ extern "C" int xq_tn_wimage(xq_ctx* c, const float* w, int co, int ci, int taps,
     XQ_TN_DONE();
 }
 
+extern "C" int xq_tn_wimage_dense2(xq_ctx* c, const float* w, int co, int ci, float* img, int img_kb, float* img_t, int img_t_kb, void* stream)
+{
+    XQ_TN_ENTER("xq_tn_wimage_dense2");
+    if (!w || !img || !img_t || co <= 0 || ci <= 0 || (ci & 31) || ci > img_kb * 32 || co > img_t_kb * 32)
+        return xq_fail(c, XQ_ERR_ARG, "xq_tn_wimage_dense2: bad arguments");
+    tn_wimage_dense2_kernel<<<dim3(ci / 32, (co + 31) / 32), 256, 0, s>>>(w, co, ci, img, img_kb, img_t, img_t_kb);
+    c->launches += 1;
+    XQ_TN_DONE();
+}
+
 extern "C" int xq_tn_wimage_batch(xq_ctx* c, const xq_tn_wimage_item* items, int n_items, void* stream)
 {
     XQ_TN_ENTER("xq_tn_wimage_batch");

@@ -161,6 +161,33 @@ __global__ void __launch_bounds__(256) tn_wimage_batch_kernel(const TnWimageBatc
     }
 }
 
+// Both images of a dense layer's weight w[co][ci] (ci % 32 == 0) from ONE pass over it: 32 x 32 tiles through shared memory;
+// img: n = co, k = ci (fprop), img_t: n = ci, k = co (dgrad).  The 93 MB policy FC weight is read once instead of twice.
+__global__ void __launch_bounds__(256) tn_wimage_dense2_kernel(const float* __restrict__ w, int co, int ci, float* __restrict__ img, int img_kb,
+                                                               float* __restrict__ img_t, int img_t_kb)
+{
+    __shared__ float tile[32][33];
+    const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
+    const int r = threadIdx.x >> 3, c4 = (threadIdx.x & 7) * 4;
+    {
+        const int o = co0 + r;
+        float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (o < co) {
+            v = ld4(w + (size_t)o * ci + ci0 + c4);
+            const int K = ci0 + c4;
+            st4(img + ((((size_t)(o >> 7) * img_kb + (K >> 5)) * 8 + ((K >> 2) & 7)) * 128 + (o & 127)) * 4, v);
+        }
+        tile[r][c4] = v.x; tile[r][c4 + 1] = v.y; tile[r][c4 + 2] = v.z; tile[r][c4 + 3] = v.w;
+    }
+    __syncthreads();
+    {
+        const int i = ci0 + r, K = co0 + c4;                    // r = input channel within the tile, c4 = first of 4 output channels
+        if (K < co)                                             // (rows of the tile beyond co hold zeros: a partial group is zero padded)
+            st4(img_t + ((((size_t)(i >> 7) * img_t_kb + (K >> 5)) * 8 + ((K >> 2) & 7)) * 128 + (i & 127)) * 4,
+                make_float4(tile[c4][r], tile[c4 + 1][r], tile[c4 + 2][r], tile[c4 + 3][r]));
+    }
+}
+
 // ---- BatchNorm forward -------------------------------------------------------------------------------------
 // partial[chunk][split][8] = per-block sums of y (4 channels) and y^2 over the real cells of the block's rows
 __global__ void __launch_bounds__(256) tn_bn_stat_kernel(const float* __restrict__ y, long long rows, int n_boards, int chunk0,
@@ -592,11 +619,16 @@ __global__ void __launch_bounds__(384) tn_value_bwd_w_kernel(const float* __rest
     const int j = blockIdx.x, k = threadIdx.x;
     if (j < kTnVH) {
         float acc = 0.0f, bacc = 0.0f;
-#pragma unroll 8
+        // feature k of board b sits at a fixed offset plus b * 110 rows: the address arithmetic leaves the loop, whose 16-fold
+        // unrolling keeps that many loads in flight (the sum itself stays one chain in board order)
+        const int kk = k < kTnVF ? k : 0, ch = kk / 90, cell = kk - ch * 90;
+        const float* fk = act + ((size_t)chunk * rows + kTnRow0 + (cell / 9) * 10 + cell % 9) * 4 + ch;
+        const float* dj = dh + j;
+#pragma unroll 16
         for (int b = 0; b < n_boards; ++b) {
-            const float d = dh[(size_t)b * kTnVH + j];
+            const float d = dj[(size_t)b * kTnVH];
             bacc += d;
-            if (k < kTnVF) acc += d * tn_value_feature(act, rows, chunk, b, k);
+            acc += d * fk[(size_t)b * (kTnBoard * 4)];
         }
         if (k < kTnVF) dw1[(size_t)j * kTnVF + k] = acc;
         if (k == 0) db1[j] = bacc;

@@ -318,14 +318,14 @@ class HandStep:
 
     def build_images(self):
         """Weight images of every contraction from the current parameters (after each optimiser step): the convolutions in
-        one launch per 32 tensors, the two images of the 93 MB policy FC weight in one launch each."""
+        one launch per 32 tensors, the two images of the 93 MB policy FC weight in one pass over it."""
         e, L = self.eng, self.eng.L
         s = e._stream()
         if self._items is None:
             self._items = self._image_items()
         e._check(L.xq_tn_wimage_batch(e.h, self._items[0], self._items[1], s))
-        e._check(L.xq_tn_wimage(e.h, self.fc.weight.data_ptr(), ACTIONS, FC_IN, 1, self.img_fc.data_ptr(), FC_KB, 0, 0, 0, s))
-        e._check(L.xq_tn_wimage(e.h, self.fc.weight.data_ptr(), ACTIONS, FC_IN, 1, self.img_fct.data_ptr(), FCT_KB, 0, 0, 1, s))
+        e._check(L.xq_tn_wimage_dense2(e.h, self.fc.weight.data_ptr(), ACTIONS, FC_IN, self.img_fc.data_ptr(), FC_KB,
+                                       self.img_fct.data_ptr(), FCT_KB, s))
 
     def _bn_fwd(self, b, bn, y, out, out_g, chunk0, nch, res=None, save=None):
         e = self.eng

@@ -114,6 +114,7 @@ def lib():
     _sig(L, "xq_tn_input", i32, vp, vp, i32, i32, i32, vp, vp, i64, vp)
     _sig(L, "xq_tn_wimage", i32, vp, vp, i32, i32, i32, vp, i32, i32, i32, i32, vp)
     _sig(L, "xq_tn_wimage_batch", i32, vp, vp, i32, vp)
+    _sig(L, "xq_tn_wimage_dense2", i32, vp, vp, i32, i32, vp, i32, vp, i32, vp)
     _sig(L, "xq_tn_bn_forward", i32, vp, vp, vp)
     _sig(L, "xq_tn_bn_backward", i32, vp, vp, vp)
     _sig(L, "xq_tn_wgrad_reduce", i32, vp, vp, i32, i64, i32, i32, i32, i32, i32, i32, vp, i32, i32, i32, vp)
@@ -138,7 +139,7 @@ EXPORTS = ["xq_create", "xq_destroy", "xq_last_error", "xq_version", "xq_launch_
            "xq_selfplay_play", "xq_selfplay_set_live_bound", "xq_selfplay_counters", "xq_selfplay_fetch", "xq_selfplay_slots",
            "xq_selfplay_device_buffers", "xq_arena_play", "xq_replay_append", "xq_train_batch", "xq_policy_value_loss",
            "xq_grad_sumsq", "xq_adam_step", "xq_peer_create", "xq_peer_connect", "xq_bn_forward", "xq_bn_backward",
-           "xq_tgemm", "xq_twgrad", "xq_tn_input", "xq_tn_wimage", "xq_tn_wimage_batch", "xq_tn_bn_forward", "xq_tn_bn_backward", "xq_tn_wgrad_reduce",
+           "xq_tgemm", "xq_twgrad", "xq_tn_input", "xq_tn_wimage", "xq_tn_wimage_batch", "xq_tn_wimage_dense2", "xq_tn_bn_forward", "xq_tn_bn_backward", "xq_tn_wgrad_reduce",
            "xq_tn_flatten", "xq_tn_unflatten", "xq_tn_rows_layouts", "xq_tn_colsum", "xq_tn_value_forward", "xq_tn_value_backward"]
 
 
