@@ -224,3 +224,23 @@ def test_dp_batchnorm_equals_batchnorm_on_the_global_minibatch():
     w = net.input_conv[1].weight
     T.convert_dp_batchnorm(net, fake)
     assert list(net.state_dict().keys()) == keys and net.input_conv[1].weight is w and isinstance(net.res_blocks[0].bn1, T.DPBatchNorm2d)
+
+
+def test_training_plane_geometry_covers_every_read_of_the_kernels():
+    """tnet.plane_rows / dense_rows / conv_wgrad_geometry (host side of csrc/xq_tnet.cu): for every minibatch size the plane
+    tensors hold the rows the contraction kernels read -- the 11-row halo of the last 256-row work item (xq_tgemm) and the
+    last slab of the weight-gradient kernel with its 8 + 12 rows of tap overhang (xq_twgrad) -- and work items tile the rows."""
+    import tnet as T
+    for B in list(range(1, 300)) + [511, 512, 513, 1024, 4096]:
+        n_rows = B * T.BOARD_ROWS
+        rows = T.plane_rows(B)
+        pairs = (n_rows + T.PAIR - 1) // T.PAIR
+        assert rows >= T.ROW0 + pairs * T.PAIR + 11                      # A block of the last item: [m0 - 11, m0 + 267)
+        slabs, spi = T.conv_wgrad_geometry(n_rows)
+        assert slabs * spi * 64 >= n_rows and slabs * 3 <= 148           # every row in a slab; one wave of (slab, tap group) items
+        assert (slabs - 1) * spi * 64 < n_rows                           # no empty slab
+        assert rows >= T.ROW0 + slabs * spi * 64 + 8 + 12                # B stage of the last slab: 72 rows from row k0 + 8 (dy = +1)
+        assert T.ROW0 - 12 >= 0                                          # ... and from row k0 - 12 (dy = -1) of the first
+        drows = T.dense_rows(B)
+        dpairs = (B + T.PAIR - 1) // T.PAIR
+        assert drows >= T.ROW0 + dpairs * T.PAIR + 11 and drows >= T.ROW0 + (B + 31) // 32 * 32
