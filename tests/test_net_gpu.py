@@ -95,7 +95,7 @@ def test_layer_by_layer(eng, oracle, n):
         assert float((net.value[:n] - v_ref).abs().max()) < 2e-3, ("value mlp", float((net.value[:n] - v_ref).abs().max()))
 
 
-@pytest.mark.parametrize("C,R,n", [(128, 6, 513), (256, 3, 130), (64, 3, 70), (192, 2, 40)])   # 64: the reference's quick preset (zero-padded to 128)
+@pytest.mark.parametrize("C,R,n", [(128, 6, 513), (256, 3, 130), (256, 2, 24), (128, 3, 40), (64, 3, 70), (192, 2, 40)])   # 64: the reference's quick preset (zero-padded to 128)
 def test_end_to_end_vs_fp32(eng, oracle, C, R, n):
     import torch
     import model as M

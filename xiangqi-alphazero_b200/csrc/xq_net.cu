@@ -1409,7 +1409,7 @@ static int net_gemm(xq_ctx* c, const xq_gemm_desc* d, int n_boards_now, const in
         // item of a CTA pair is 5.9 us of MMAs whatever the batch.  While every item fits one wave the layer runs as
         // 256-row x 64-channel items on single CTAs instead (the image tiled by 64 output channels is the CTA pairs' own):
         // 4x the items, a quarter of the MMA cycles each.
-        if (c->net_small && d->w_half && d->kchunks == 16 && ((a.m_tiles + 1) / 2) * a.n_tiles * 2 <= c->sm_count) {
+        if (c->net_small && d->w_half && (d->kchunks == 16 || d->kchunks == 32) && ((a.m_tiles + 1) / 2) * a.n_tiles * 2 <= c->sm_count) {
             GemmArgs a2 = a;
             a2.w = a.w_half;
             a2.n_tiles = a.n_tiles * 2;
