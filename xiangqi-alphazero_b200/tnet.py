@@ -453,7 +453,9 @@ class HandStep:
             b.launches = self.eng.launch_count() - n0        # kernels of csrc/xq_tnet.cu + the loss kernel in one step (a replay launches the same)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):                # capture only (nothing executes): replayed from the next step on
+            # capture only (nothing executes): replayed from the next step on.  thread_local: CUDA calls of other threads
+            # (the NCCL watchdog of a multi-rank run) must not invalidate the capture
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
                 self._run(b, inv_batch)
             b.graph, b.graph_inv = g, inv_batch
         self.bn_steps += 1
